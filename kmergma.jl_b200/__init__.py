@@ -1,0 +1,689 @@
+"""kmergma.jl_b200 — host-side mirror of KmerGMA.jl's operator interface over libkmergma_cuda.
+
+Julia is not available in this image, so the host side above the C ABI is written in Python and
+mirrors the reference's names, keyword arguments, in-place output vectors and error behaviour
+(src/API.jl, src/GenomeMiner.jl, src/OmnGenomeMiner.jl, src/ExactMatch.jl,
+src/ReferenceGeneration.jl); the Julia shim a maintainer would add is in julia/ and INTEGRATION.md.
+All scanning, extension and matching work happens in the CUDA library; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import warnings
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib as L
+
+__all__ = [
+    "KmerGMAError", "Context", "Genome", "FastaRecord", "KFV", "AlignResult",
+    "gen_ref_ws_cons", "cluster_ref_API", "eliminate_null_params", "get_cluster_index",
+    "estimate_optimal_threshold", "ac_gma_testing", "Omn_KmerGMA", "record_KmerGMA",
+    "findGenes", "findGenes_cluster_mode", "exactMatch", "write_results", "align_unitrange",
+    "julia_round2", "julia_float_str",
+]
+
+
+class KmerGMAError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[kgma {code}] {msg}")
+        self.code = code
+
+
+# ------------------------------------------------------------------------------------------------
+class Context:
+    """One kgma_ctx = one GPU. No global state lives in the library; this module keeps one default
+    context per device for convenience."""
+
+    def __init__(self, device: int = 0):
+        self._lib = L.load()
+        h = C.c_void_p()
+        rc = self._lib.kgma_create(device, C.byref(h))
+        if rc != 0:
+            raise KmerGMAError(rc, (self._lib.kgma_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.kgma_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int, what: str = ""):
+        if rc != 0:
+            raise KmerGMAError(rc, (self._lib.kgma_last_error(self._h) or b"").decode() or what)
+
+    def stats(self) -> dict:
+        s = L.Stats()
+        self._lib.kgma_get_stats(self._h, C.byref(s))
+        return {f: getattr(s, f) for f, _ in L.Stats._fields_}
+
+
+_default_ctx: Dict[int, Context] = {}
+
+
+def default_context(device: Optional[int] = None) -> Context:
+    if device is None:
+        device = int(os.environ.get("KGMA_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class FastaRecord:
+    """Stand-in for FASTX.FASTA.Record: `description` is the whole header, `identifier` the text before
+    the first whitespace, `sequence` the residues."""
+    description: str
+    sequence: str
+
+    @property
+    def identifier(self) -> str:
+        return self.description.split(None, 1)[0] if self.description.strip() else ""
+
+    def __eq__(self, other):
+        return isinstance(other, FastaRecord) and self.description == other.description and \
+            self.sequence.upper() == other.sequence.upper()
+
+
+@dataclass
+class AlignResult:
+    """What do_return_align yields per hit (the reference pushes a BioAlignments PairwiseAlignmentResult)."""
+    cigar: str
+    score: int
+
+
+class Genome:
+    """Packed genome (2 bits/base + ambiguity mask + record table) owned by the C library."""
+
+    def __init__(self, handle, lib):
+        self._h, self._lib = handle, lib
+
+    @classmethod
+    def from_fasta(cls, path: str) -> "Genome":
+        lib = L.load()
+        h = C.c_void_p()
+        rc = lib.kgma_genome_from_fasta(os.fsencode(path), C.byref(h))
+        if rc != 0:
+            raise KmerGMAError(rc, f"cannot ingest {path}" + (" (symbol outside IUPAC DNA)" if rc == L.E_SYMBOL else ""))
+        return cls(h, lib)
+
+    @classmethod
+    def from_records(cls, records: Sequence[Union[FastaRecord, Tuple[str, str]]]) -> "Genome":
+        lib = L.load()
+        h = C.c_void_p()
+        lib.kgma_genome_create(C.byref(h))
+        g = cls(h, lib)
+        for r in records:
+            desc, seq = (r.description, r.sequence) if isinstance(r, FastaRecord) else r
+            ident = desc.split(None, 1)[0] if desc.strip() else ""
+            s = seq.encode() if isinstance(seq, str) else bytes(seq)
+            rc = lib.kgma_genome_append_ascii(h, ident.encode(), desc.encode(), s, len(s))
+            if rc != 0:
+                raise KmerGMAError(rc, "invalid sequence character")
+        rc = lib.kgma_genome_seal(h)
+        if rc != 0:
+            raise KmerGMAError(rc, "seal failed")
+        return g
+
+    @classmethod
+    def synth(cls, rec_len: Sequence[int], seed: int = 42, n_run_len: int = 0, centromere_len: int = 0,
+              ctx: Optional[Context] = None) -> "Genome":
+        ctx = ctx or default_context()
+        lens = np.asarray(rec_len, dtype=np.int64)
+        h = C.c_void_p()
+        ctx.check(ctx._lib.kgma_genome_synth(ctx._h, lens.size, lens.ctypes.data, seed, n_run_len, centromere_len, C.byref(h)))
+        return cls(h, ctx._lib)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.kgma_genome_destroy(self._h)
+            self._h = None
+
+    def __len__(self):
+        return self._lib.kgma_genome_n_records(self._h)
+
+    @property
+    def total_len(self) -> int:
+        return self._lib.kgma_genome_total_len(self._h)
+
+    def seqsize(self, r: int) -> int:
+        return self._lib.kgma_genome_record_len(self._h, r)
+
+    def identifier(self, r: int) -> str:
+        return self._lib.kgma_genome_identifier(self._h, r).decode()
+
+    def description(self, r: int) -> str:
+        return self._lib.kgma_genome_description(self._h, r).decode()
+
+    def seq(self, r: int, first: int = 1, last: Optional[int] = None) -> str:
+        """view(seq, first:last), 1-based inclusive."""
+        if last is None:
+            last = self.seqsize(r)
+        n = max(0, last - first + 1)
+        buf = C.create_string_buffer(n + 1)
+        rc = self._lib.kgma_genome_get_seq(self._h, r, first, last, buf)
+        if rc != 0:
+            raise KmerGMAError(rc, f"range {first}:{last} outside record {r}")
+        return buf.value.decode()
+
+    def put_seq(self, r: int, first: int, seq: str):
+        s = seq.encode()
+        rc = self._lib.kgma_genome_put_seq(self._h, r, first, s, len(s))
+        if rc != 0:
+            raise KmerGMAError(rc, "put_seq failed")
+
+    def make_resident(self, ctx: Optional[Context] = None):
+        ctx = ctx or default_context()
+        ctx.check(ctx._lib.kgma_genome_make_resident(ctx._h, self._h))
+
+
+def _as_genome(genome) -> Genome:
+    if isinstance(genome, Genome):
+        return genome
+    if isinstance(genome, (str, os.PathLike)):
+        return Genome.from_fasta(os.fspath(genome))
+    if isinstance(genome, (list, tuple)):
+        return Genome.from_records(genome)
+    raise TypeError("genome must be a FASTA path, a Genome or a list of FastaRecord")
+
+
+# ------------------------------------------------------------------------------------------------
+class KFV(np.ndarray):
+    """A Float64 k-mer frequency vector that remembers the integer sums it came from
+    (RV = S * (1/N), src/ReferenceGeneration.jl:35) so the device path stays exact."""
+
+    def __new__(cls, values, S=None, n_refs=None):
+        obj = np.asarray(values, dtype=np.float64).view(cls)
+        obj.S = None if S is None else np.ascontiguousarray(S, dtype=np.int32)
+        obj.n_refs = n_refs
+        return obj
+
+    def __array_finalize__(self, obj):
+        self.S = getattr(obj, "S", None)
+        self.n_refs = getattr(obj, "n_refs", None)
+
+
+def _ints_of(refVec, lib) -> Tuple[np.ndarray, int]:
+    """(S, N) behind a refVec: carried by KFV, otherwise recovered with kgma_profile_from_kfv."""
+    S = getattr(refVec, "S", None)
+    N = getattr(refVec, "n_refs", None)
+    if S is not None and N and np.asarray(refVec).shape == S.shape:
+        return np.ascontiguousarray(S, dtype=np.int32), int(N)
+    v = np.ascontiguousarray(refVec, dtype=np.float64)
+    S = np.zeros(v.size, dtype=np.int32)
+    n = C.c_int32()
+    rc = lib.kgma_profile_from_kfv(v.ctypes.data, v.size, 0, S.ctypes.data, C.byref(n))
+    if rc != 0:
+        raise KmerGMAError(rc, "refVec is not (k-mer count sums) / (family size): the exact device path needs a rational profile")
+    return S, n.value
+
+
+class _Refs:
+    def __init__(self, src):
+        self._lib = L.load()
+        h = C.c_void_p()
+        if isinstance(src, (str, os.PathLike)):
+            rc = self._lib.kgma_refs_from_fasta(os.fsencode(src), C.byref(h))
+            if rc != 0:
+                raise KmerGMAError(rc, f"cannot read references from {src}")
+        else:
+            self._lib.kgma_refs_create(C.byref(h))
+            for r in src:
+                s = (r.sequence if isinstance(r, FastaRecord) else r).encode()
+                rc = self._lib.kgma_refs_append_ascii(h, s, len(s))
+                if rc != 0:
+                    raise KmerGMAError(rc, "KeyError: reference symbol outside A,C,G,T,N")
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.kgma_refs_destroy(self._h)
+            self._h = None
+
+
+def gen_ref_ws_cons(reference_seqs, k: int, get_maxlen: bool = False):
+    """src/ReferenceGeneration.jl:4-41 -> (RV, windowsize, consensus[, maxlen]); RV is a KFV."""
+    refs = _Refs(reference_seqs)
+    lib = refs._lib
+    S = np.zeros(4 ** k, dtype=np.int32)
+    n, ws = C.c_int32(), C.c_int64()
+    maxlen = lib.kgma_refs_maxlen(refs._h)
+    cons = C.create_string_buffer(maxlen + 2)
+    rc = lib.kgma_refs_profile(refs._h, k, S.ctypes.data, C.byref(n), C.byref(ws), cons)
+    if rc != 0:
+        raise KmerGMAError(rc, "gen_ref_ws_cons failed")
+    rv = KFV(S.astype(np.float64) * (1.0 / n.value), S, n.value)      # answer .* (1/len)
+    if get_maxlen:
+        return rv, ws.value, cons.value.decode(), maxlen
+    return rv, ws.value, cons.value.decode()
+
+
+def get_cluster_index(inp, cutoffs) -> int:
+    """src/ReferenceGeneration.jl:50-57"""
+    answer = 1
+    for num in cutoffs:
+        if inp <= num:
+            return answer
+        answer += 1
+    return answer
+
+
+def cluster_ref_API(reference_seqs, k: int, cutoffs=(7, 12, 20, 25), get_dists: bool = False, include_avg: bool = True):
+    """src/ReferenceGeneration.jl:75-138 -> (KFVs, windowsizes, consensus_vec, invalid_vec[, dists])"""
+    refs = _Refs(reference_seqs)
+    lib = refs._lib
+    cut = np.asarray(cutoffs, dtype=np.float64)
+    maxc = cut.size + 2
+    nb = 4 ** k
+    S = np.zeros((maxc, nb), dtype=np.int32)
+    members = np.zeros(maxc, dtype=np.int32)
+    wss = np.zeros(maxc, dtype=np.int64)
+    stride = lib.kgma_refs_maxlen(refs._h) + 2
+    cons = C.create_string_buffer(maxc * stride)
+    invalid = np.zeros(maxc, dtype=np.int32)
+    dists = np.zeros(lib.kgma_refs_count(refs._h), dtype=np.float64)
+    n = lib.kgma_refs_cluster(refs._h, k, cut.ctypes.data, cut.size, int(include_avg), 0, S.ctypes.data,
+                              members.ctypes.data, wss.ctypes.data, cons, stride, invalid.ctypes.data, dists.ctypes.data)
+    if n < 0:
+        raise KmerGMAError(n, "cluster_ref_API failed")
+    raw = cons.raw
+    kfvs, cv = [], []
+    ncl = cut.size + 1
+    for i in range(n):
+        m = int(members[i])
+        if m == 0:
+            kfvs.append(KFV(np.zeros(nb), S[i].copy(), 0))
+        elif include_avg and i == n - 1:
+            kfvs.append(KFV(S[i].astype(np.float64) * (1.0 / m), S[i].copy(), m))      # average_KFV (:129)
+        else:
+            kfvs.append(KFV(S[i].astype(np.float64) / m, S[i].copy(), m))               # KFVs[i] ./= lens[i] (:118)
+        cv.append(raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0].decode())
+    inv = [bool(x) for x in invalid[:ncl + (1 if include_avg else 0)]]
+    out = (kfvs, [int(x) for x in wss[:n]], cv, inv)
+    return out + (dists,) if get_dists else out
+
+
+def eliminate_null_params(KFVs, windowsizes, consensus_vec, invalid_vec):
+    """src/ReferenceGeneration.jl:152-168"""
+    keep = [i for i, inv in enumerate(invalid_vec) if not inv]
+    return [KFVs[i] for i in keep], [windowsizes[i] for i in keep], [consensus_vec[i] for i in keep]
+
+
+def _kmer_count_np(codes: np.ndarray, k: int) -> np.ndarray:
+    n = codes.size - k + 1
+    idx = np.zeros(n, dtype=np.int64)
+    for j in range(k):
+        idx = idx * 4 + codes[j:j + n]
+    return np.bincount(idx, minlength=4 ** k).astype(np.float64)
+
+
+def estimate_optimal_threshold(RV, average_length, seed: int = 42, num_trials: int = 100, buffer: float = 8):
+    """src/DistanceTesting.jl:8-32: mean kmer_dist of `num_trials` random sequences to RV, minus `buffer`.
+    The reference draws them with Julia's RNG after Random.seed!(42); that stream is not reproducible
+    outside Julia, so this uses numpy's PCG64 with the same seed (values agree to within sampling noise,
+    see DESIGN.md).  One generator is consumed sequentially across clusters like the reference's."""
+    rng = np.random.default_rng(seed)
+
+    def one(rv, length):
+        rv = np.asarray(rv, dtype=np.float64)
+        k = int(round(np.log(rv.size) / np.log(4)))
+        tot = 0.0
+        for _ in range(num_trials):
+            c = _kmer_count_np(rng.integers(0, 4, size=length), k)
+            tot += (1.0 / (2 * k)) * float(np.sum((c - rv) ** 2))
+        return tot / num_trials - buffer
+
+    if isinstance(average_length, (list, tuple, np.ndarray)):
+        return [one(rv, int(l)) for rv, l in zip(RV, average_length)]
+    return one(RV, int(average_length))
+
+
+# ------------------------------------------------------------------------------------------------
+def julia_round2(x: float) -> float:
+    """round(x, digits = 2) as Base does it: round-half-even of x*100, then /100."""
+    return float(np.rint(x * 100.0) / 100.0)
+
+
+def julia_float_str(x: float) -> str:
+    """string(::Float64): shortest round-trip decimal, always with a fractional part."""
+    return repr(float(x))
+
+
+def _header(ident: str, h: L.Hit, cluster: bool, with_genome_pos: bool = True) -> str:
+    d = julia_float_str(julia_round2(h.dist))
+    rng = f"{h.first}:{h.last}"
+    ln = h.last - h.first + 1
+    if cluster:            # src/OmnGenomeMiner.jl:141-149
+        return f"{ident} | Dist = {d} | KFV = {h.profile} | MatchPos = {rng} | GenomePos = {h.genome_pos} | Len = {ln}"
+    gp = f" | GenomePos = {h.genome_pos}" if with_genome_pos else ""
+    return f"{ident} | dist = {d} | MatchPos = {rng}{gp} | Len = {ln}"      # src/Alignment.jl:71-78
+
+
+class ScanOutput:
+    """Raw result of one kgma_scan call (hits as ctypes structs + optional dists / cigars)."""
+
+    def __init__(self, ctx: Context, res_handle):
+        lib = ctx._lib
+        n = lib.kgma_result_n_hits(res_handle)
+        hp = lib.kgma_result_hits(res_handle)
+        self.hits: List[L.Hit] = []
+        for i in range(n):
+            h = L.Hit()
+            C.memmove(C.byref(h), C.byref(hp[i]), C.sizeof(L.Hit))
+            self.hits.append(h)
+        nr = lib.kgma_result_n_runs(res_handle)
+        rp = lib.kgma_result_runs(res_handle)
+        self.runs = np.ctypeslib.as_array(C.cast(rp, C.POINTER(C.c_uint8)), shape=(nr * C.sizeof(L.Run),)).copy() if nr else np.zeros(0, np.uint8)
+        self.n_runs = nr
+        self.first_D = None
+        self.dists: List[np.ndarray] = []
+        self.cigars: List[Optional[AlignResult]] = []
+        ops, cnt = lib.kgma_result_cigar_ops(res_handle), lib.kgma_result_cigar_counts(res_handle)
+        for h in self.hits:
+            if h.cigar_len and ops:
+                s = "".join(f"{cnt[h.cigar_off + t]}{ops[h.cigar_off + t].decode()}" for t in range(h.cigar_len))
+                self.cigars.append(AlignResult(s, h.align_score))
+            else:
+                self.cigars.append(None)
+        self._lib, self._res = lib, res_handle
+
+    def load_dists(self, n_profiles: int):
+        for q in range(n_profiles):
+            n = self._lib.kgma_result_n_dists(self._res, q)
+            p = self._lib.kgma_result_dists(self._res, q)
+            self.dists.append(np.ctypeslib.as_array(p, shape=(n,)).copy() if n else np.zeros(0))
+
+    def load_first_D(self, n_profiles: int, n_records: int):
+        p = self._lib.kgma_result_first_D(self._res)
+        self.first_D = np.ctypeslib.as_array(p, shape=(n_profiles * n_records,)).copy() if p else np.zeros(0, np.int64)
+
+    def free(self):
+        if self._res:
+            self._lib.kgma_result_free(self._res)
+            self._res = None
+
+    def __del__(self):
+        self.free()
+
+
+def _make_profiles(refVecs, windowsizes, consensus_seqs, thrs, k, lib):
+    keep = []
+    arr = (L.Profile * len(refVecs))()
+    for i, rv in enumerate(refVecs):
+        if np.asarray(rv).size != 4 ** k:
+            raise KmerGMAError(L.E_ARG, f"refVec length {np.asarray(rv).size} != 4^k")
+        S, N = _ints_of(rv, lib)
+        cons = consensus_seqs[i].upper().encode() if consensus_seqs[i] is not None else b""
+        keep.append((S, cons))
+        arr[i].k, arr[i].n_refs, arr[i].window = k, N, int(windowsizes[i])
+        arr[i].S = S.ctypes.data_as(C.POINTER(C.c_int32))
+        arr[i].consensus, arr[i].consensus_len = cons, len(cons)
+        arr[i].thr = float(thrs[i])
+    return arr, keep
+
+
+def scan_raw(genome: Genome, refVecs, windowsizes, consensus_seqs, thrs, k: int, mode: int, buff: int,
+             flags: int, gap_open: int, gap_extend: int, only_record: int = -1,
+             ctx: Optional[Context] = None, runs_only: bool = False, shard: Tuple[int, int] = (0, 1)) -> ScanOutput:
+    """Thin call into kgma_scan / kgma_scan_runs."""
+    ctx = ctx or default_context()
+    arr, keep = _make_profiles(refVecs, windowsizes, consensus_seqs, thrs, k, ctx._lib)
+    P = L.ScanParams(mode, flags, buff, gap_open, gap_extend, shard[0], shard[1], only_record, 0)
+    res = C.c_void_p()
+    fn = ctx._lib.kgma_scan_runs if runs_only else ctx._lib.kgma_scan
+    ctx.check(fn(ctx._h, genome._h, arr, len(refVecs), C.byref(P), C.byref(res)))
+    out = ScanOutput(ctx, res)
+    if flags & L.F_WANT_DISTS:
+        out.load_dists(len(refVecs))
+    if runs_only:
+        out.load_first_D(len(refVecs), len(genome))
+    return out
+
+
+def replay_raw(genome: Genome, refVecs, windowsizes, consensus_seqs, thrs, k: int, mode: int, buff: int,
+               flags: int, gap_open: int, gap_extend: int, runs: np.ndarray, first_D: np.ndarray,
+               only_record: int = -1, ctx: Optional[Context] = None) -> ScanOutput:
+    """kgma_replay over the concatenated run summaries of all shards (runs: raw bytes of kgma_run[])."""
+    ctx = ctx or default_context()
+    arr, keep = _make_profiles(refVecs, windowsizes, consensus_seqs, thrs, k, ctx._lib)
+    P = L.ScanParams(mode, flags, buff, gap_open, gap_extend, 0, 1, only_record, 0)
+    runs = np.ascontiguousarray(runs, dtype=np.uint8)
+    fd = np.ascontiguousarray(first_D, dtype=np.int64)
+    res = C.c_void_p()
+    ctx.check(ctx._lib.kgma_replay(ctx._h, genome._h, arr, len(refVecs), C.byref(P), runs.ctypes.data,
+                                   runs.size // C.sizeof(L.Run), fd.ctypes.data, C.byref(res)))
+    return ScanOutput(ctx, res)
+
+
+def _emit(genome: Genome, out: ScanOutput, cluster: bool, resultVec, hit_loci_vec, align_vec, with_genome_pos=True):
+    for h, cg in zip(out.hits, out.cigars):
+        ident = genome.identifier(h.record)
+        seq = genome.seq(h.record, h.first, h.last) if h.last >= h.first else ""
+        resultVec.append(FastaRecord(_header(ident, h, cluster, with_genome_pos), seq))
+        if hit_loci_vec is not None:
+            hit_loci_vec.append(h.first + h.genome_pos)
+        if align_vec is not None and cg is not None:
+            align_vec.append(cg)
+
+
+def ac_gma_testing(*, genome_path, refVec, consensus_refseq: str, k: int = 6, windowsize: int = 289,
+                   thr: float = 33.5, buff: int = 50, mask=None, Nt_bits=None, ScaleFactor=None,
+                   do_align: bool = True, result_align_vec: Optional[list] = None,
+                   gap_open_score: int = -69, gap_extend_score: int = -1,
+                   do_return_dists: bool = False, dist_vec: Optional[list] = None,
+                   do_return_align: bool = False, get_hit_loci: bool = False,
+                   hit_loci_vec: Optional[list] = None, resultVec: Optional[list] = None,
+                   dense: bool = False, ctx: Optional[Context] = None):
+    """ac_gma_testing! (src/GenomeMiner.jl:4-109): single-profile scan; appends to resultVec /
+    hit_loci_vec / result_align_vec / dist_vec in place and returns the raw ScanOutput.
+    `mask`, `Nt_bits`, `ScaleFactor` are accepted for signature parity (they are functions of k)."""
+    resultVec = [] if resultVec is None else resultVec
+    g = _as_genome(genome_path)
+    flags = (L.F_ALIGN if do_align else 0) | (L.F_WANT_DISTS if do_return_dists else 0) | \
+            (L.F_WANT_CIGARS if (do_align and do_return_align) else 0) | (L.F_DENSE if dense else 0)
+    out = scan_raw(g, [refVec], [windowsize], [consensus_refseq], [thr], k, L.MODE_SINGLE, buff, flags,
+                   gap_open_score, gap_extend_score, ctx=ctx)
+    _emit(g, out, False, resultVec, hit_loci_vec if get_hit_loci else None,
+          result_align_vec if do_return_align else None)
+    if do_return_dists and dist_vec is not None:
+        dist_vec.extend(out.dists[0].tolist()) if isinstance(dist_vec, list) else None
+    return out
+
+
+def record_KmerGMA(*, record: Union[FastaRecord, Tuple[str, str]], refVec, consensus_refseq: str,
+                   resultVec_vec: Optional[List[list]] = None, curr_kmer_freq_vec=None,
+                   k: int = 6, windowsize: int = 289, thr: float = 30, buff: int = 50,
+                   do_align: bool = True, gap_open_score: int = -69, gap_extend_score: int = -1,
+                   ctx: Optional[Context] = None):
+    """record_KmerGMA! (src/MultiThread/GenomeMiner.jl:8-98): the single-profile scan of one record; the
+    header carries no GenomePos (:88-91).  Results are appended to resultVec_vec[0]."""
+    resultVec_vec = [[]] if resultVec_vec is None else resultVec_vec
+    g = Genome.from_records([record])
+    flags = L.F_ALIGN if do_align else 0
+    out = scan_raw(g, [refVec], [windowsize], [consensus_refseq], [thr], k, L.MODE_SINGLE, buff, flags,
+                   gap_open_score, gap_extend_score, only_record=0, ctx=ctx)
+    _emit(g, out, False, resultVec_vec[0], None, None, with_genome_pos=False)
+    return out
+
+
+def Omn_KmerGMA(*, genome_path, refVecs, windowsizes, consensus_seqs, resultVec: list, k: int = 6,
+                ScaleFactor=None, mask=None, thr_vec=(35, 31, 38, 34, 27, 27), buff: int = 50, Nt_bits=None,
+                align_hits: bool = True, align_vec: Optional[list] = None,
+                gap_open_score: int = -200, gap_extend_score: int = -1, genome_pos: int = 0,
+                get_hit_loci: bool = False, hit_loci_vec: Optional[list] = None, get_aligns: bool = False,
+                do_return_dists: bool = False, dist_vec_vec: Optional[List[list]] = None,
+                dense: bool = False, ctx: Optional[Context] = None):
+    """Omn_KmerGMA! (src/OmnGenomeMiner.jl:7-162): C profiles scanned together."""
+    g = _as_genome(genome_path)
+    Cn = len(windowsizes)
+    flags = (L.F_ALIGN if align_hits else 0) | (L.F_WANT_DISTS if do_return_dists else 0) | \
+            (L.F_WANT_CIGARS if (align_hits and get_aligns) else 0) | (L.F_DENSE if dense else 0)
+    out = scan_raw(g, list(refVecs)[:Cn], windowsizes, list(consensus_seqs)[:Cn], list(thr_vec)[:Cn], k,
+                   L.MODE_CLUSTER, buff, flags, gap_open_score, gap_extend_score, ctx=ctx)
+    if genome_pos:
+        for h in out.hits:
+            h.genome_pos += genome_pos
+    _emit(g, out, True, resultVec, hit_loci_vec if get_hit_loci else None, align_vec if get_aligns else None)
+    if do_return_dists and dist_vec_vec is not None:
+        for q in range(min(Cn, len(dist_vec_vec))):
+            dist_vec_vec[q].extend(out.dists[q].tolist())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def warn_helper(k: int, do_return_dists: bool):
+    """src/API.jl:8-11"""
+    if k < 5:
+        warnings.warn(f"Such a low k value of {k} likely won't yield the most accurate results")
+    if do_return_dists:
+        warnings.warn("Setting do_return_dists to true may be very memory intensive")
+
+
+def _jl_num(x) -> str:
+    return julia_float_str(x) if isinstance(x, float) else str(x)
+
+
+def findGenes(*, genome_path, ref_path, k: int = 6, KmerDistThr: Union[int, float] = 0, buffer: int = 50,
+              do_align: bool = True, gap_open_score: int = -69, gap_extend_score: int = -1,
+              do_return_dists: bool = False, do_return_hit_loci: bool = False, do_return_align: bool = False,
+              verbose: bool = True, KmerDist_threshold_buffer: float = 8.0, ctx: Optional[Context] = None) -> list:
+    """KmerGMA.findGenes (src/API.jl:60-104).  Returns [hit_vector, (hit_loci), (alignments), (dists)]."""
+    warn_helper(k, do_return_dists)
+    RV, windowsize, consensus_refseq = gen_ref_ws_cons(ref_path, k)
+    if k >= windowsize:
+        raise KmerGMAError(L.E_WINDOW, f"the average reference sequence length {windowsize} exceeds/is equal to the chosen kmer length {k}. please reduce k. ")
+    est = estimate_optimal_threshold(RV, windowsize, buffer=KmerDist_threshold_buffer)
+    if KmerDistThr == 0:
+        KmerDistThr = est
+    elif KmerDistThr < est:     # (sic) src/API.jl:75-77
+        warnings.warn(f"The kmer distance threshold {_jl_num(KmerDistThr)} for k = {k} is likely too high, and can result in many false positives")
+    hit_vector, dist_vec, hit_loci_vec, alignment_vec = [], [], [], []
+    ac_gma_testing(genome_path=genome_path, refVec=RV, consensus_refseq=consensus_refseq, k=k,
+                   windowsize=windowsize, thr=KmerDistThr, buff=buffer, do_align=do_align,
+                   gap_open_score=gap_open_score, gap_extend_score=gap_extend_score,
+                   do_return_dists=do_return_dists, do_return_align=do_return_align,
+                   get_hit_loci=do_return_hit_loci, dist_vec=dist_vec, result_align_vec=alignment_vec,
+                   hit_loci_vec=hit_loci_vec, resultVec=hit_vector, ctx=ctx)
+    output_vector: list = [hit_vector]
+    if do_return_hit_loci:
+        output_vector.append(hit_loci_vec)
+    if do_return_align:
+        output_vector.append(alignment_vec)
+    if do_return_dists:
+        output_vector.append(dist_vec)
+    return output_vector
+
+
+def findGenes_cluster_mode(*, genome_path, ref_path, cluster_cutoffs=(7, 12, 20, 25), k: int = 6,
+                           KmerDistThrs=(0.0,), buffer: int = 100, do_align: bool = True,
+                           gap_open_score: int = -200, gap_extend_score: int = -1,
+                           do_return_dists: bool = False, do_return_hit_loci: bool = False,
+                           do_return_align: bool = False, verbose: bool = True,
+                           kmerDist_threshold_buffer: float = 7, ctx: Optional[Context] = None) -> list:
+    """KmerGMA.findGenes_cluster_mode (src/API.jl:161-226)."""
+    warn_helper(k, do_return_dists)
+    RVs, windowsizes, consensus_refseqs, invalids = cluster_ref_API(ref_path, k, cutoffs=cluster_cutoffs)
+    RVs, windowsizes, consensus_refseqs = eliminate_null_params(RVs, windowsizes, consensus_refseqs, invalids)
+    if k >= min(windowsizes):
+        raise KmerGMAError(L.E_WINDOW, f"some/all of the average reference sequence lengths exceeds/is equal to the chosen kmer length {k}. please reduce k. ")
+    est = estimate_optimal_threshold(RVs, windowsizes, buffer=kmerDist_threshold_buffer)
+    KmerDistThrs = [float(x) for x in KmerDistThrs]
+    if KmerDistThrs[0] == 0:
+        KmerDistThrs = est
+    else:
+        ind_warn, num_warn = "", ""
+        for i, num in enumerate(KmerDistThrs):
+            if i < len(est) and num > est[i]:
+                ind_warn += f"{i + 1}, "
+                num_warn += f"{_jl_num(num)}, "
+        if ind_warn:
+            thr_txt = "[" + ", ".join(_jl_num(x) for x in KmerDistThrs) + "]"
+            warnings.warn(f"The kmer distance thresholds {thr_txt} at index/indicies {ind_warn}"[:-2] +
+                          f" for k = {k} is potentially too high, and may result in more false positives.")
+    hit_vector, hit_loci_vec, alignment_vec = [], [], []
+    dist_vec_vec = [[] for _ in windowsizes]
+    Omn_KmerGMA(genome_path=genome_path, refVecs=RVs, windowsizes=windowsizes, consensus_seqs=consensus_refseqs,
+                resultVec=hit_vector, k=k, thr_vec=KmerDistThrs, buff=buffer, align_hits=do_align,
+                gap_open_score=gap_open_score, gap_extend_score=gap_extend_score, get_aligns=do_return_align,
+                get_hit_loci=do_return_hit_loci, hit_loci_vec=hit_loci_vec, align_vec=alignment_vec,
+                do_return_dists=do_return_dists, dist_vec_vec=dist_vec_vec, ctx=ctx)
+    output_vector: list = [hit_vector]
+    if do_return_hit_loci:
+        output_vector.append(hit_loci_vec)
+    if do_return_align:
+        output_vector.append(alignment_vec)
+    if do_return_dists:
+        output_vector.append(dist_vec_vec)
+    return output_vector
+
+
+def write_results(KmerGMA_result_vec: Sequence[FastaRecord], file_path: str, width: int = 95):
+    """src/API.jl:234-241: append the records to a FASTA file, `width` residues per line."""
+    with open(file_path, "a") as fh:
+        for hit in KmerGMA_result_vec:
+            fh.write(">" + hit.description + "\n")
+            s = hit.sequence
+            for i in range(0, len(s), width):
+                fh.write(s[i:i + width] + "\n")
+
+
+# ------------------------------------------------------------------------------------------------
+def align_unitrange(seq, seq_UnitRange: Tuple[int, int], consensus_seq: str, windowsize: int, sequence_length: int,
+                    gap_open: int = -69, gap_extend: int = -1, ctx: Optional[Context] = None) -> Tuple[int, int]:
+    """align_unitrange (src/Alignment.jl:33-52) on the GPU: seq is a residue string or (Genome, record)."""
+    ctx = ctx or default_context()
+    if isinstance(seq, tuple):
+        g, rec = seq
+    else:
+        g, rec = Genome.from_records([("seq", seq)]), 0
+    cons = consensus_seq.upper().encode()[:windowsize]
+    recs = np.asarray([rec], dtype=np.int32)
+    f = np.asarray([seq_UnitRange[0]], dtype=np.int64)
+    l = np.asarray([seq_UnitRange[1]], dtype=np.int64)
+    of, ol, sc = np.zeros(1, np.int64), np.zeros(1, np.int64), np.zeros(1, np.int64)
+    ctx.check(ctx._lib.kgma_align_batch(ctx._h, g._h, cons, len(cons), gap_open, gap_extend, 0, 1,
+                                        recs.ctypes.data, f.ctypes.data, l.ctypes.data,
+                                        of.ctypes.data, ol.ctypes.data, sc.ctypes.data))
+    return int(of[0]), int(ol[0])
+
+
+def exactMatch(query, subject_seq, overlap: bool = True, ctx: Optional[Context] = None, resident: bool = False):
+    """exactMatch (src/ExactMatch.jl:89-121).
+    subject = residue string / FastaRecord  -> list of (first, last) ranges, or None when there is no match;
+    subject = FASTA path / Genome (a Reader) -> dict identifier -> ranges, or the string "no match"."""
+    ctx = ctx or default_context()
+    if isinstance(query, FastaRecord):
+        query = query.sequence
+    q = str(query).upper().encode()
+    single = isinstance(subject_seq, FastaRecord) or (isinstance(subject_seq, str) and not os.path.exists(subject_seq))
+    if single:
+        s = subject_seq.sequence if isinstance(subject_seq, FastaRecord) else subject_seq
+        g = Genome.from_records([("subject", s)])
+    else:
+        g = _as_genome(subject_seq)
+    mp = C.POINTER(L.Match)()
+    n = C.c_int64()
+    ctx.check(ctx._lib.kgma_exact_match(ctx._h, g._h, q, len(q), int(overlap), L.F_RESIDENT if resident else 0,
+                                        C.byref(mp), C.byref(n)))
+    by_rec: Dict[int, List[Tuple[int, int]]] = {}
+    for i in range(n.value):
+        by_rec.setdefault(mp[i].record, []).append((mp[i].first, mp[i].last))
+    if n.value:
+        ctx._lib.kgma_free(mp)
+    if single:
+        return by_rec.get(0) or None
+    identify = {}
+    for r in sorted(by_rec):
+        identify[g.identifier(r)] = by_rec[r]        # duplicate identifiers overwrite (ExactMatch.jl:112)
+    return identify if identify else "no match"

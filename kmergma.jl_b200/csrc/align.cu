@@ -1,0 +1,299 @@
+// Batched semi-global affine-gap extension of candidate hits, one warp per candidate.
+// Replaces align_unitrange (src/Alignment.jl:33-52), i.e. BioAlignments'
+//   pairalign(SemiGlobalAlignment(), consensus, view(seq, range), AffineGapScoreModel(EDNAFULL, gap_open, gap_extend))
+// followed by cigar_to_UnitRange (src/Alignment.jl:13-30).
+//
+// DP (Gotoh): a = consensus is aligned end to end; gaps that consume only b (= genome slice) before a[1]
+// and after a[m] are free; a gap of length L costs gap_open + L*gap_extend; EDNAFULL restricted to
+// A,C,G,T,N (match 5, mismatch -4, N/base -2, N/N -1).  Traceback priority in the H state:
+// match > delete (consumes b) > insert (consumes a); on exact open/extend ties the gap is extended
+// unless KGMA_F_TIE_OPEN (BioAlignments' own tie rule is not pinned by any reference test).
+//
+// Mapping: a warp sweeps 32 rows of the DP matrix at a time, lane l owning row 32*rb+l+1, with the
+// classic one-column skew between neighbouring lanes so that the (i-1,j) / (i-1,j-1) operands arrive
+// by __shfl_up from the lane above.  The bottom row of each 32-row block is parked in shared memory
+// for the next block.  Trace bytes are packed four columns at a time into 32-bit global stores.
+#include "kgma_internal.h"
+#include <algorithm>
+
+namespace kgma {
+
+#define TR_MATCH 1u
+#define TR_DEL   2u
+#define TR_INS   4u
+#define TR_EXTF  8u
+#define TR_EXTE  16u
+
+struct AlignJob {
+    int64_t tr_off;      // byte offset of this job's trace matrix
+    int32_t a_off, m;    // consensus codes
+    int32_t b_off, n;    // subject codes
+    int32_t cig_off;     // offset into the cigar buffer (uint32 entries), capacity m+n+2
+    int32_t pad;
+};
+
+struct AlignOut { long long score; int32_t lower, num_sum, nops, cig_n; };
+
+struct AlignArgs {
+    const uint8_t *a, *b;        // codes 0..3, 4 = N
+    const AlignJob *jobs; int njobs;
+    int *next_job;
+    uint8_t *trace;
+    uint32_t *cigar;             // (count << 8) | op, reversed order; may be null
+    AlignOut *out;
+    int go, ge;                  // positive penalties
+    int tie_open;
+    int ncol_cap;                // shared-memory columns per warp
+};
+
+__device__ __forceinline__ int edna(int x, int y)
+{
+    if ((x | y) & 4) return (x & y & 4) ? -1 : -2;
+    return x == y ? 5 : -4;
+}
+
+__global__ void __launch_bounds__(128) kgma_align(AlignArgs A)
+{
+    extern __shared__ int s_bound[];                     // per warp: Hb[ncol_cap], Eb[ncol_cap]
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int *Hb = s_bound + (size_t)wid * 2 * A.ncol_cap, *Eb = Hb + A.ncol_cap;
+    const int NEG = -(1 << 29);
+    const int go = A.go, ge = A.ge;
+
+    for (;;) {
+        int ji = 0;
+        if (lane == 0) ji = atomicAdd(A.next_job, 1);
+        ji = __shfl_sync(FULL, ji, 0);
+        if (ji >= A.njobs) break;
+        const AlignJob J = A.jobs[ji];
+        const int m = J.m, n = J.n;
+        const uint8_t *a = A.a + J.a_off, *b = A.b + J.b_off;
+        const int stride = (n + 1 + 3) & ~3;
+        uint8_t *tr = A.trace + J.tr_off;
+        int score = 0;
+        const int nrb = (m + 31) >> 5;
+        for (int rb = 0; rb < nrb; rb++) {
+            const int i = rb * 32 + lane + 1;
+            const bool row_ok = i <= m;
+            const int ai = row_ok ? a[i - 1] : 0;
+            const bool last = (i == m);
+            int Hleft = -(go + i * ge), F = NEG;
+            int Hdiag = (i == 1) ? 0 : -(go + (i - 1) * ge);      // H[i-1][0]
+            int Hout = NEG, Eout = NEG;
+            uint32_t tp = 0;
+            uint8_t *trow = tr + (size_t)i * stride;
+            for (int s = 1; s <= n + 31; s++) {
+                const int j = s - lane;
+                int upH = __shfl_up_sync(FULL, Hout, 1), upE = __shfl_up_sync(FULL, Eout, 1);
+                if (lane == 0 && j <= n) {
+                    if (rb == 0) { upH = 0; upE = NEG; }           // row 0: free leading deletions
+                    else { upH = Hb[j]; upE = Eb[j]; }
+                }
+                if (row_ok && j >= 1 && j <= n) {
+                    uint32_t t = 0;
+                    const int eo = upH - go - ge, ee = upE - ge;
+                    int e;
+                    if (A.tie_open ? (ee > eo) : (ee >= eo)) { e = ee; t |= TR_EXTE; } else e = eo;
+                    const int fo = last ? Hleft : Hleft - go - ge, fe = last ? F : F - ge;
+                    int f;
+                    if (A.tie_open ? (fe > fo) : (fe >= fo)) { f = fe; t |= TR_EXTF; } else f = fo;
+                    const int mm = Hdiag + edna(ai, b[j - 1]);
+                    int h = max(mm, max(f, e));
+                    if (mm == h) t |= TR_MATCH;
+                    if (f == h) t |= TR_DEL;
+                    if (e == h) t |= TR_INS;
+                    Hdiag = upH; Hout = h; Eout = e; Hleft = h; F = f;
+                    tp |= t << (8 * (j & 3));
+                    if ((j & 3) == 3 || j == n) { *reinterpret_cast<uint32_t *>(trow + (j & ~3)) = tp; tp = 0; }
+                    if (lane == 31) { Hb[j] = h; Eb[j] = e; }      // bottom row of this block -> next block's row above
+                }
+            }
+            if (rb == nrb - 1) score = __shfl_sync(FULL, Hleft, (m - 1) & 31);
+            __syncwarp();
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) {
+            // traceback from (m,n); ops come out in reverse order
+            int i = m, j = n, state = 0;
+            int nops = 0, cur_op = 0, cur_cnt = 0, c_first = 0, c_last = 0; long long total = 0;
+            uint32_t *cg = A.cigar ? A.cigar + J.cig_off : nullptr;
+            auto flush = [&]() {
+                if (cur_cnt > 0) {
+                    if (nops == 0) c_last = cur_cnt;
+                    c_first = cur_cnt;
+                    if (cg) cg[nops] = ((uint32_t)cur_cnt << 8) | (uint32_t)cur_op;
+                    nops++; total += cur_cnt;
+                }
+            };
+            auto push = [&](int op) { if (op == cur_op) cur_cnt++; else { flush(); cur_op = op; cur_cnt = 1; } };
+            while (i > 0 || j > 0) {
+                if (i == 0) { push('D'); j--; continue; }
+                if (j == 0) { push('I'); i--; continue; }
+                const uint32_t t = tr[(size_t)i * stride + j];
+                if (state == 0) {
+                    if (t & TR_MATCH) { push(a[i - 1] == b[j - 1] ? '=' : 'X'); i--; j--; }
+                    else if (t & TR_DEL) state = 1;
+                    else state = 2;
+                } else if (state == 1) { push('D'); if (!(t & TR_EXTF)) state = 0; j--; }
+                else { push('I'); if (!(t & TR_EXTE)) state = 0; i--; }
+            }
+            flush();
+            // cigar_to_UnitRange (Alignment.jl:13-30): lower = count of the first op, num_sum = all ops but the last
+            AlignOut o;
+            o.score = score; o.nops = nops; o.cig_n = cg ? nops : 0;
+            o.lower = nops >= 2 ? c_first : 0;
+            o.num_sum = nops >= 2 ? (int)(total - c_last) : 0;
+            A.out[ji] = o;
+        }
+        __syncwarp();
+    }
+}
+
+static inline uint8_t sym_code(char c)
+{
+    switch (c) {
+    case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2;
+    case 'T': case 't': return 3; case 'N': case 'n': return 4; default: return 255;
+    }
+}
+
+int align_batch_device(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &reqs,
+                       const kgma_profile *profiles, int n_profiles, bool single_mode_truncate,
+                       int gap_open, int gap_extend, bool tie_open, bool want_cigars,
+                       std::vector<AlignRes> &out, std::vector<char> *cig_ops, std::vector<int32_t> *cig_cnt)
+{
+    out.assign(reqs.size(), AlignRes{ 1, 0, 0, 0, 0 });
+    if (reqs.empty()) return KGMA_OK;
+    KGMA_CUDA(ctx, cudaSetDevice(ctx->device));
+    // consensus codes per profile
+    std::vector<uint8_t> acodes; std::vector<int32_t> a_off(n_profiles), a_len(n_profiles);
+    for (int q = 0; q < n_profiles; q++) {
+        const kgma_profile &p = profiles[q];
+        if (!p.consensus) return set_err(ctx, KGMA_E_ARG, "profile %d has no consensus sequence to align against", q);
+        int len = p.consensus_len;
+        if (single_mode_truncate) {                      // Alignment.jl:42 view(consensus_seq, 1:windowsize)
+            if (len < p.window) return set_err(ctx, KGMA_E_ARG, "BoundsError: consensus (%d) shorter than the window (%lld)", len, (long long)p.window);
+            len = (int)p.window;
+        }
+        a_off[q] = (int32_t)acodes.size(); a_len[q] = len;
+        for (int i = 0; i < len; i++) {
+            uint8_t c = sym_code(p.consensus[i]);
+            if (c == 255) return set_err(ctx, KGMA_E_SYMBOL, "consensus of profile %d holds a symbol outside A,C,G,T,N", q);
+            acodes.push_back(c);
+        }
+    }
+    cudaEvent_t e0 = ctx->ev[0], e1 = ctx->ev[1];
+    double align_ms = 0;
+    const size_t TRACE_BUDGET = (size_t)768 << 20;
+    size_t done = 0;
+    while (done < reqs.size()) {
+        // ---- carve a batch that fits the trace budget
+        std::vector<AlignJob> jobs; std::vector<uint8_t> bcodes;
+        size_t tr_bytes = 0, cig_entries = 0; int maxn = 0;
+        size_t i = done;
+        for (; i < reqs.size(); i++) {
+            const AlignReq &rq = reqs[i];
+            if (rq.record < 0 || rq.record >= (int)g->recs.size() || rq.profile < 0 || rq.profile >= n_profiles)
+                return set_err(ctx, KGMA_E_ARG, "alignment request %zu out of range", i);
+            const kgma::Record &R = g->recs[rq.record];
+            if (rq.first < 1 || rq.last > R.len || rq.last < rq.first) return set_err(ctx, KGMA_E_ARG, "alignment range %lld:%lld invalid", (long long)rq.first, (long long)rq.last);
+            int n = (int)(rq.last - rq.first + 1), m = a_len[rq.profile];
+            size_t need = (size_t)(m + 1) * (size_t)((n + 1 + 3) & ~3);
+            need = (need + 15) & ~(size_t)15;
+            if (!jobs.empty() && tr_bytes + need > TRACE_BUDGET) break;
+            AlignJob J{};
+            J.tr_off = (int64_t)tr_bytes; J.a_off = a_off[rq.profile]; J.m = m;
+            J.b_off = (int32_t)bcodes.size(); J.n = n; J.cig_off = (int32_t)cig_entries;
+            tr_bytes += need; cig_entries += (size_t)(m + n + 2); maxn = std::max(maxn, n);
+            for (int64_t p = rq.first; p <= rq.last; p++) {
+                int64_t gp = R.off + p - 1;
+                uint8_t c = (uint8_t)base_code(g, gp);
+                if (base_masked(g, gp)) { if (c != 3) return set_err(ctx, KGMA_E_SYMBOL, "subject holds a symbol outside A,C,G,T,N"); c = 4; }
+                bcodes.push_back(c);
+            }
+            jobs.push_back(J);
+        }
+        const int nj = (int)jobs.size();
+        const int ncol = (maxn + 1 + 31) & ~31;
+        const int warps_per_block = 4;
+        size_t smem = (size_t)warps_per_block * 2 * ncol * sizeof(int);
+        if (smem > ctx->smem_optin) return set_err(ctx, KGMA_E_UNSUPPORTED, "subject slice of %d bases too long for the extension kernel", maxn);
+        // ---- device buffers
+        size_t o = 0;
+        auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
+        size_t o_a = carve(acodes.size()), o_b = carve(bcodes.size()), o_j = carve((size_t)nj * sizeof(AlignJob));
+        size_t o_o = carve((size_t)nj * sizeof(AlignOut)), o_c = carve(256);
+        size_t o_cg = carve(want_cigars ? cig_entries * 4 : 0), o_tr = carve(tr_bytes);
+        void *dv = nullptr;
+        int rc = dev_scratch(ctx, o, &dv);
+        if (rc) return rc;
+        unsigned char *d = (unsigned char *)dv;
+        cudaStream_t st = ctx->s_compute;
+        KGMA_CUDA(ctx, cudaMemcpyAsync(d + o_a, acodes.data(), acodes.size(), cudaMemcpyHostToDevice, st));
+        KGMA_CUDA(ctx, cudaMemcpyAsync(d + o_b, bcodes.data(), bcodes.size(), cudaMemcpyHostToDevice, st));
+        KGMA_CUDA(ctx, cudaMemcpyAsync(d + o_j, jobs.data(), (size_t)nj * sizeof(AlignJob), cudaMemcpyHostToDevice, st));
+        KGMA_CUDA(ctx, cudaMemsetAsync(d + o_c, 0, 256, st));
+        ctx->stats.h2d_bytes += acodes.size() + bcodes.size() + (size_t)nj * sizeof(AlignJob);
+        AlignArgs A{};
+        A.a = d + o_a; A.b = d + o_b; A.jobs = (const AlignJob *)(d + o_j); A.njobs = nj; A.next_job = (int *)(d + o_c);
+        A.trace = d + o_tr; A.cigar = want_cigars ? (uint32_t *)(d + o_cg) : nullptr; A.out = (AlignOut *)(d + o_o);
+        A.go = -gap_open; A.ge = -gap_extend; A.tie_open = tie_open ? 1 : 0; A.ncol_cap = ncol;
+        KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = std::min((nj + warps_per_block - 1) / warps_per_block, ctx->num_sms * 4);
+        KGMA_CUDA(ctx, cudaEventRecord(e0, st));
+        kgma_align<<<grid, warps_per_block * 32, smem, st>>>(A);
+        KGMA_CUDA(ctx, cudaGetLastError());
+        KGMA_CUDA(ctx, cudaEventRecord(e1, st));
+        ctx->stats.launches++;
+        std::vector<AlignOut> ho(nj);
+        KGMA_CUDA(ctx, cudaMemcpyAsync(ho.data(), d + o_o, (size_t)nj * sizeof(AlignOut), cudaMemcpyDeviceToHost, st));
+        std::vector<uint32_t> hc;
+        if (want_cigars) { hc.resize(cig_entries); KGMA_CUDA(ctx, cudaMemcpyAsync(hc.data(), d + o_cg, cig_entries * 4, cudaMemcpyDeviceToHost, st)); }
+        KGMA_CUDA(ctx, cudaStreamSynchronize(st));
+        ctx->stats.d2h_bytes += (size_t)nj * sizeof(AlignOut) + (want_cigars ? cig_entries * 4 : 0);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); align_ms += ms;
+        for (int q = 0; q < nj; q++) {
+            AlignRes &r = out[done + q];
+            r.lo = (int64_t)ho[q].lower + 1; r.hi = ho[q].num_sum; r.score = ho[q].score;
+            if (want_cigars && cig_ops && cig_cnt) {
+                r.cig_off = (uint32_t)cig_ops->size(); r.cig_len = (uint32_t)ho[q].cig_n;
+                for (int t = ho[q].cig_n - 1; t >= 0; t--) {         // device wrote them end-to-start
+                    uint32_t v = hc[(size_t)jobs[q].cig_off + t];
+                    cig_ops->push_back((char)(v & 0xFF)); cig_cnt->push_back((int32_t)(v >> 8));
+                }
+            }
+        }
+        done = i;
+    }
+    ctx->stats.align_ms += align_ms;
+    return KGMA_OK;
+}
+
+}  // namespace kgma
+
+using namespace kgma;
+
+extern "C" int kgma_align_batch(kgma_ctx *ctx, kgma_genome *g, const char *consensus, int32_t cons_len,
+                                int32_t gap_open, int32_t gap_extend, uint32_t flags, int64_t n,
+                                const int32_t *record, const int64_t *first, const int64_t *last,
+                                int64_t *out_first, int64_t *out_last, int64_t *out_score)
+{
+    if (!ctx || !g || !consensus || n < 0 || (n && (!record || !first || !last || !out_first || !out_last))) return KGMA_E_ARG;
+    kgma_profile p{};
+    p.k = 1; p.n_refs = 1; p.window = cons_len; p.S = nullptr; p.consensus = consensus; p.consensus_len = cons_len; p.thr = 0;
+    std::vector<AlignReq> reqs((size_t)n);
+    for (int64_t i = 0; i < n; i++) reqs[(size_t)i] = { record[i], 0, first[i], last[i] };
+    std::vector<AlignRes> res;
+    int rc = align_batch_device(ctx, g, reqs, &p, 1, false, gap_open, gap_extend, (flags & KGMA_F_TIE_OPEN) != 0, false, res, nullptr, nullptr);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; i++) {
+        int64_t L = g->recs[record[i]].len;
+        int64_t f = std::max<int64_t>(1, first[i] + res[(size_t)i].lo - 1), l = std::min<int64_t>(first[i] + res[(size_t)i].hi - 1, L);
+        if (l < f - 1) l = f - 1;
+        out_first[i] = f; out_last[i] = l;
+        if (out_score) out_score[i] = res[(size_t)i].score;
+    }
+    return KGMA_OK;
+}

@@ -1,0 +1,66 @@
+// Context life-cycle and result accessors of the C ABI (include/kmergma.h).
+#include "kgma_internal.h"
+
+namespace kgma { const char *create_err(); }
+using namespace kgma;
+
+extern "C" {
+
+int kgma_create(int device, kgma_ctx **out)
+{
+    if (!out) return KGMA_E_ARG;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_err(nullptr, KGMA_E_CUDA, "no CUDA device available (%s); libkmergma_cuda has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= ndev) return set_err(nullptr, KGMA_E_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return set_err(nullptr, KGMA_E_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return set_err(nullptr, KGMA_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10) return set_err(nullptr, KGMA_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    kgma_ctx *c = new kgma_ctx();
+    c->device = device; c->num_sms = prop.multiProcessorCount; c->smem_optin = prop.sharedMemPerBlockOptin;
+    bool ok = cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 8 && ok; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+    if (!ok) { kgma_destroy(c); return set_err(nullptr, KGMA_E_CUDA, "stream/event creation failed"); }
+    *out = c;
+    return KGMA_OK;
+}
+
+void kgma_destroy(kgma_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->s_compute) cudaStreamSynchronize(c->s_compute);
+    if (c->s_copy) cudaStreamSynchronize(c->s_copy);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->s_compute) cudaStreamDestroy(c->s_compute);
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    if (c->d_seq2) cudaFree(c->d_seq2);
+    if (c->d_mask) cudaFree(c->d_mask);
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    delete c;
+}
+
+const char *kgma_last_error(const kgma_ctx *c) { return c ? c->err.c_str() : create_err(); }
+
+int kgma_get_stats(const kgma_ctx *c, kgma_stats *out) { if (!c || !out) return KGMA_E_ARG; *out = c->stats; return KGMA_OK; }
+
+int64_t kgma_result_n_hits(const kgma_result *r) { return r ? (int64_t)r->hits.size() : 0; }
+const kgma_hit *kgma_result_hits(const kgma_result *r) { return r && !r->hits.empty() ? r->hits.data() : nullptr; }
+int64_t kgma_result_n_runs(const kgma_result *r) { return r ? (int64_t)r->runs.size() : 0; }
+const kgma_run *kgma_result_runs(const kgma_result *r) { return r && !r->runs.empty() ? r->runs.data() : nullptr; }
+const int64_t *kgma_result_first_D(const kgma_result *r) { return r && !r->first_D.empty() ? r->first_D.data() : nullptr; }
+int64_t kgma_result_n_dists(const kgma_result *r, int p) { return (r && p >= 0 && p < (int)r->dists.size()) ? (int64_t)r->dists[p].size() : 0; }
+const double *kgma_result_dists(const kgma_result *r, int p) { return (r && p >= 0 && p < (int)r->dists.size() && !r->dists[p].empty()) ? r->dists[p].data() : nullptr; }
+const char *kgma_result_cigar_ops(const kgma_result *r) { return r && !r->cigar_ops.empty() ? r->cigar_ops.data() : nullptr; }
+const int32_t *kgma_result_cigar_counts(const kgma_result *r) { return r && !r->cigar_cnt.empty() ? r->cigar_cnt.data() : nullptr; }
+void kgma_result_free(kgma_result *r) { delete r; }
+void kgma_free(void *p) { free(p); }
+
+}  // extern "C"

@@ -1,0 +1,322 @@
+// Host-side genome container: FASTA parsing, 2-bit packing + ambiguity mask, record table.
+// Replaces FASTX.FASTA.Reader + getSeq (src/Consts.jl:37-39) + the per-base NUCLEOTIDE_BITS
+// dictionary lookups (src/Consts.jl:22-28) of the reference's hot loops.
+#include "kgma_internal.h"
+#include <atomic>
+#include <cstdarg>
+#include <cstdlib>
+#include <thread>
+#include <algorithm>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <fcntl.h>
+#include <unistd.h>
+
+namespace kgma {
+
+static thread_local std::string g_create_err;
+
+int set_err(kgma_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_err = buf;
+    return code;
+}
+const char *create_err() { return g_create_err.c_str(); }
+
+// code table: low 2 bits = 2-bit code, bit 2 = masked (N or other IUPAC), bit 3 = not N (ambiguous IUPAC), 0xFF = invalid
+struct CodeTab {
+    uint8_t t[256];
+    CodeTab()
+    {
+        memset(t, 0xFF, sizeof t);
+        auto set = [&](char c, uint8_t v) { t[(uint8_t)c] = v; t[(uint8_t)(c | 0x20)] = v; };
+        set('A', 0); set('C', 1); set('G', 2); set('T', 3);
+        set('N', 3 | 4);                                       // Consts.jl:27  N -> 3
+        for (const char *p = "RYSWKMBDHVU"; *p; ++p) set(*p, 0 | 4 | 8);   // other IUPAC: masked + ambiguous
+        t[(uint8_t)'-'] = 0 | 4 | 8;
+    }
+};
+static const CodeTab CT;
+
+int genome_reserve(kgma_genome *g, int64_t bases)
+{
+    if (bases <= g->cap_bases) return KGMA_OK;
+    int64_t nc = std::max<int64_t>(bases, g->cap_bases + g->cap_bases / 2);
+    nc = (nc + 4095) / 4096 * 4096;
+    if (g->pinned || g->host_alloc) return KGMA_E_STATE;
+    uint32_t *s = (uint32_t *)realloc(g->seq2, (size_t)nc / 4);
+    if (!s) return KGMA_E_CAPACITY;
+    g->seq2 = s;
+    uint32_t *m = (uint32_t *)realloc(g->mask, (size_t)nc / 8);
+    if (!m) return KGMA_E_CAPACITY;
+    g->mask = m;
+    memset((char *)g->seq2 + g->cap_bases / 4, 0, (size_t)(nc - g->cap_bases) / 4);
+    memset((char *)g->mask + g->cap_bases / 8, 0, (size_t)(nc - g->cap_bases) / 8);
+    g->cap_bases = nc;
+    return KGMA_OK;
+}
+
+int genome_pin(kgma_ctx *ctx, kgma_genome *g)
+{
+    if (g->pinned) return KGMA_OK;
+    // page-lock in place so cudaMemcpyAsync is a true async DMA (north_star: pinned, double-buffered)
+    cudaError_t e1 = cudaHostRegister(g->seq2, (size_t)g->cap_bases / 4, cudaHostRegisterDefault);
+    cudaError_t e2 = cudaHostRegister(g->mask, (size_t)g->cap_bases / 8, cudaHostRegisterDefault);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        if (e1 == cudaSuccess) cudaHostUnregister(g->seq2);
+        if (e2 == cudaSuccess) cudaHostUnregister(g->mask);
+        cudaGetLastError();
+        return set_err(ctx, KGMA_E_CUDA, "cudaHostRegister of the packed genome failed");
+    }
+    g->pinned = true;
+    return KGMA_OK;
+}
+
+static std::atomic<uint64_t> g_uid{1};
+
+// start a new record at the next aligned offset; returns its index
+static int begin_record(kgma_genome *g, const char *ident, const char *desc, int64_t len)
+{
+    kgma::Record r;
+    r.ident = ident ? ident : "";
+    r.desc = desc ? desc : r.ident;
+    r.len = len;
+    int64_t end = g->recs.empty() ? 0 : g->recs.back().off + g->recs.back().len;
+    r.off = (end + REC_ALIGN - 1) / REC_ALIGN * REC_ALIGN;
+    g->recs.push_back(std::move(r));
+    return (int)g->recs.size() - 1;
+}
+
+// pack [lo,hi) of an ASCII record into the planes; returns first bad position or -1; sets flags
+static void pack_ascii_range(kgma_genome *g, int64_t off, const char *s, int64_t lo, int64_t hi,
+                             int64_t *bad, bool *amb, int64_t *amb_pos, bool *anymask)
+{
+    // lo is a multiple of 32 (except possibly 0 handled the same) so words are owned by one thread
+    for (int64_t i = lo; i < hi;) {
+        int64_t gp = off + i;
+        uint32_t w = 0, mbits = 0;
+        int n = (int)std::min<int64_t>(16, hi - i);
+        for (int j = 0; j < n; j++) {
+            uint8_t c = CT.t[(uint8_t)s[i + j]];
+            if (c == 0xFF) { if (*bad < 0) *bad = i + j; c = 0; }
+            w |= (uint32_t)(c & 3) << (2 * j);
+            if (c & 4) { mbits |= 1u << j; if (c & 8) { if (!*amb) { *amb = true; *amb_pos = i + j; } } }
+        }
+        g->seq2[gp >> 4] = w;           // off is 128-aligned and i advances by 16: word aligned
+        if (mbits) { *anymask = true; g->mask[gp >> 5] |= mbits << (gp & 31); }
+        i += n;
+    }
+}
+
+static int append_ascii_impl(kgma_genome *g, const char *ident, const char *desc, const char *seq, int64_t len)
+{
+    if (g->sealed) return KGMA_E_STATE;
+    if (len < 0 || (len > 0 && !seq)) return KGMA_E_ARG;
+    int r = begin_record(g, ident, desc, len);
+    int64_t off = g->recs[r].off;
+    int rc = genome_reserve(g, off + len + REC_ALIGN + TAIL_PAD + FGROUP);
+    if (rc) return rc;
+    int nt = (int)std::min<int64_t>(std::max<int64_t>(1, len >> 22), std::max(1u, std::thread::hardware_concurrency()));
+    nt = std::min(nt, 32);
+    std::vector<int64_t> bad(nt, -1), apos(nt, -1);
+    std::vector<char> amb(nt, 0), anym(nt, 0);
+    auto work = [&](int t) {
+        int64_t chunk = ((len + nt - 1) / nt + 31) / 32 * 32;
+        int64_t lo = std::min<int64_t>(len, chunk * t), hi = std::min<int64_t>(len, chunk * (t + 1));
+        bool a = false, m = false;
+        pack_ascii_range(g, off, seq, lo, hi, &bad[t], &a, &apos[t], &m);
+        amb[t] = a; anym[t] = m;
+    };
+    if (nt == 1) work(0);
+    else { std::vector<std::thread> th; for (int t = 0; t < nt; t++) th.emplace_back(work, t); for (auto &x : th) x.join(); }
+    for (int t = 0; t < nt; t++) {
+        if (bad[t] >= 0) { g->err = "record " + std::to_string(r) + ": invalid character at position " + std::to_string(bad[t] + 1); return KGMA_E_SYMBOL; }
+        if (amb[t] && !g->ambiguous) { g->ambiguous = true; g->amb_record = r; g->amb_pos = apos[t] + 1; }
+        if (anym[t]) g->any_mask = true;
+    }
+    g->total_len += len;
+    return KGMA_OK;
+}
+
+}  // namespace kgma
+
+using namespace kgma;
+
+extern "C" {
+
+int kgma_version(void) { return 100; }
+
+int kgma_genome_create(kgma_genome **out)
+{
+    if (!out) return KGMA_E_ARG;
+    *out = new kgma_genome();
+    (*out)->uid = g_uid.fetch_add(1);
+    return KGMA_OK;
+}
+
+void kgma_genome_destroy(kgma_genome *g)
+{
+    if (!g) return;
+    if (g->host_alloc) { cudaFreeHost(g->seq2); cudaFreeHost(g->mask); }
+    else {
+        if (g->pinned) { cudaHostUnregister(g->seq2); cudaHostUnregister(g->mask); }
+        free(g->seq2); free(g->mask);
+    }
+    delete g;
+}
+
+int kgma_genome_append_ascii(kgma_genome *g, const char *identifier, const char *description,
+                             const char *seq, int64_t len)
+{
+    if (!g) return KGMA_E_ARG;
+    return append_ascii_impl(g, identifier, description, seq, len);
+}
+
+int kgma_genome_append_packed(kgma_genome *g, const char *identifier, const char *description,
+                              const uint32_t *seq2, const uint32_t *mask, int64_t len)
+{
+    if (!g || g->sealed) return g ? KGMA_E_STATE : KGMA_E_ARG;
+    if (len < 0 || (len > 0 && !seq2)) return KGMA_E_ARG;
+    int r = begin_record(g, identifier, description, len);
+    int64_t off = g->recs[r].off;
+    int rc = genome_reserve(g, off + len + REC_ALIGN + TAIL_PAD + FGROUP);
+    if (rc) return rc;
+    int64_t nw = (len + 15) / 16;
+    memcpy(g->seq2 + (off >> 4), seq2, (size_t)nw * 4);
+    if (len & 15) g->seq2[(off >> 4) + nw - 1] &= (1u << (2 * (len & 15))) - 1;     // clear bits past the end
+    if (mask) {
+        int64_t mw = (len + 31) / 32;
+        memcpy(g->mask + (off >> 5), mask, (size_t)mw * 4);
+        if (len & 31) g->mask[(off >> 5) + mw - 1] &= (1u << (len & 31)) - 1;
+        for (int64_t i = 0; i < mw && !g->any_mask; i++) if (g->mask[(off >> 5) + i]) g->any_mask = true;
+    }
+    g->total_len += len;
+    return KGMA_OK;
+}
+
+int kgma_genome_append_bio4(kgma_genome *g, const char *identifier, const char *description,
+                            const uint64_t *data, int64_t len)
+{
+    if (!g || g->sealed) return g ? KGMA_E_STATE : KGMA_E_ARG;
+    if (len < 0 || (len > 0 && !data)) return KGMA_E_ARG;
+    int r = begin_record(g, identifier, description, len);
+    int64_t off = g->recs[r].off;
+    int rc = genome_reserve(g, off + len + REC_ALIGN + TAIL_PAD + FGROUP);
+    if (rc) return rc;
+    for (int64_t i = 0; i < len; i += 16) {
+        uint64_t w = data[i >> 4];
+        uint32_t o = 0, mb = 0;
+        int n = (int)std::min<int64_t>(16, len - i);
+        for (int j = 0; j < n; j++) {
+            unsigned nib = (unsigned)(w >> (4 * j)) & 15u;
+            unsigned code;
+            if (nib == 1) code = 0; else if (nib == 2) code = 1; else if (nib == 4) code = 2; else if (nib == 8) code = 3;
+            else if (nib == 15) { code = 3; mb |= 1u << j; }
+            else { code = 0; mb |= 1u << j; if (!g->ambiguous) { g->ambiguous = true; g->amb_record = r; g->amb_pos = i + j + 1; } }
+            o |= code << (2 * j);
+        }
+        int64_t gp = off + i;
+        g->seq2[gp >> 4] = o;
+        if (mb) { g->any_mask = true; g->mask[gp >> 5] |= mb << (gp & 31); }
+    }
+    g->total_len += len;
+    return KGMA_OK;
+}
+
+int kgma_genome_seal(kgma_genome *g)
+{
+    if (!g) return KGMA_E_ARG;
+    if (g->sealed) return KGMA_OK;
+    int64_t end = g->recs.empty() ? 0 : g->recs.back().off + g->recs.back().len;
+    int64_t G = (end + FGROUP - 1) / FGROUP * FGROUP + FGROUP;     // whole warp groups + one spare group
+    int rc = genome_reserve(g, G + TAIL_PAD);
+    if (rc) return rc;
+    g->G = G;
+    g->sealed = true;
+    return KGMA_OK;
+}
+
+int kgma_genome_from_fasta(const char *path, kgma_genome **out)
+{
+    if (!path || !out) return KGMA_E_ARG;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return KGMA_E_IO;
+    struct stat st; if (fstat(fd, &st) != 0) { close(fd); return KGMA_E_IO; }
+    size_t sz = (size_t)st.st_size;
+    const char *buf = sz ? (const char *)mmap(nullptr, sz, PROT_READ, MAP_PRIVATE, fd, 0) : "";
+    if (sz && buf == MAP_FAILED) { close(fd); return KGMA_E_IO; }
+    kgma_genome *g = nullptr; kgma_genome_create(&g);
+    int rc = KGMA_OK;
+    size_t i = 0;
+    std::string seq;
+    while (i < sz && rc == KGMA_OK) {
+        if (buf[i] != '>') { while (i < sz && buf[i] != '\n') i++; i++; continue; }
+        size_t hs = i + 1; while (i < sz && buf[i] != '\n') i++;
+        size_t he = i; if (he > hs && buf[he - 1] == '\r') he--;
+        std::string desc(buf + hs, he - hs);
+        size_t ie = 0; while (ie < desc.size() && !isspace((unsigned char)desc[ie])) ie++;
+        std::string ident = desc.substr(0, ie);
+        // gather residues until the next header line
+        seq.clear();
+        size_t j = i + 1;
+        while (j < sz) {
+            if (buf[j] == '>') break;                       // j is at a line start here
+            size_t ls = j; const char *nl = (const char *)memchr(buf + j, '\n', sz - j);
+            size_t le = nl ? (size_t)(nl - buf) : sz;
+            j = nl ? le + 1 : sz;
+            while (le > ls && (buf[le - 1] == '\r' || buf[le - 1] == ' ' || buf[le - 1] == '\t')) le--;
+            seq.append(buf + ls, le - ls);
+        }
+        rc = append_ascii_impl(g, ident.c_str(), desc.c_str(), seq.data(), (int64_t)seq.size());
+        i = j;
+    }
+    if (sz) munmap((void *)buf, sz);
+    close(fd);
+    if (rc == KGMA_OK) rc = kgma_genome_seal(g);
+    if (rc != KGMA_OK) { kgma_genome_destroy(g); return rc; }
+    *out = g;
+    return KGMA_OK;
+}
+
+int kgma_genome_n_records(const kgma_genome *g) { return g ? (int)g->recs.size() : 0; }
+int64_t kgma_genome_record_len(const kgma_genome *g, int r) { return (g && r >= 0 && r < (int)g->recs.size()) ? g->recs[r].len : -1; }
+int64_t kgma_genome_total_len(const kgma_genome *g) { return g ? g->total_len : 0; }
+const char *kgma_genome_identifier(const kgma_genome *g, int r) { return (g && r >= 0 && r < (int)g->recs.size()) ? g->recs[r].ident.c_str() : nullptr; }
+const char *kgma_genome_description(const kgma_genome *g, int r) { return (g && r >= 0 && r < (int)g->recs.size()) ? g->recs[r].desc.c_str() : nullptr; }
+
+int kgma_genome_get_seq(const kgma_genome *g, int r, int64_t first, int64_t last, char *out)
+{
+    if (!g || !out || r < 0 || r >= (int)g->recs.size()) return KGMA_E_ARG;
+    const auto &R = g->recs[r];
+    if (first < 1 || last > R.len || last < first - 1) return KGMA_E_ARG;
+    static const char sym[4] = { 'A', 'C', 'G', 'T' };
+    for (int64_t p = first; p <= last; p++) {
+        int64_t gp = R.off + p - 1;
+        char c = sym[base_code(g, gp)];
+        if (base_masked(g, gp)) c = (c == 'T') ? 'N' : '?';      // '?' = an IUPAC symbol other than N was ingested
+        out[p - first] = c;
+    }
+    out[last - first + 1] = 0;
+    return KGMA_OK;
+}
+
+int kgma_genome_put_seq(kgma_genome *g, int r, int64_t first, const char *seq, int64_t len)
+{
+    if (!g || !seq || r < 0 || r >= (int)g->recs.size()) return KGMA_E_ARG;
+    const auto &R = g->recs[r];
+    if (first < 1 || first + len - 1 > R.len) return KGMA_E_ARG;
+    for (int64_t i = 0; i < len; i++) {
+        uint8_t c = CT.t[(uint8_t)seq[i]];
+        if (c == 0xFF || (c & 8)) return KGMA_E_SYMBOL;
+        int64_t gp = R.off + first - 1 + i;
+        uint32_t &w = g->seq2[gp >> 4];
+        w = (w & ~(3u << (2 * (gp & 15)))) | ((uint32_t)(c & 3) << (2 * (gp & 15)));
+        uint32_t &m = g->mask[gp >> 5];
+        if (c & 4) { m |= 1u << (gp & 31); g->any_mask = true; } else m &= ~(1u << (gp & 31));
+    }
+    return KGMA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// Internal declarations shared by the translation units of libkmergma_cuda.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cstdio>
+#include "../../include/kmergma.h"
+
+namespace kgma {
+
+// ------------------------------------------------------------------ layout constants
+constexpr int     REC_ALIGN   = 128;       // every record starts at a multiple of 128 bases (32 B of packed data)
+constexpr int64_t TAIL_PAD    = 16384;     // zero bases after the last record (kernels may over-read)
+constexpr int     FBLOCK      = 64;        // prefilter block: 64 bases = one 128-bit load per thread
+constexpr int     FGROUP      = 32 * FBLOCK; // bases one warp covers per iteration
+constexpr int     WFRAC       = 14;        // prefilter fixed point: weights are scaled by 2^14
+constexpr uint32_t WCLAMP     = (1u << WFRAC) + 1;
+constexpr int     MAX_K       = 7;
+constexpr int     MAX_PROFILES = 16;
+
+struct Record {
+    std::string ident, desc;
+    int64_t len = 0;
+    int64_t off = 0;     // global base offset (multiple of REC_ALIGN)
+};
+
+}  // namespace kgma
+
+struct kgma_genome {
+    std::vector<kgma::Record> recs;
+    // packed planes in the global coordinate space (records concatenated with alignment padding)
+    uint32_t *seq2 = nullptr;      // 16 bases / word
+    uint32_t *mask = nullptr;      // 32 bases / word
+    int64_t   cap_bases = 0;       // allocated bases (multiple of 128)
+    int64_t   G = 0;               // used bases incl. padding (set by seal; multiple of FGROUP)
+    int64_t   total_len = 0;       // sum of record lengths
+    bool      sealed = false;
+    bool      ambiguous = false;   // a symbol other than A,C,G,T,N was ingested
+    bool      any_mask = false;
+    bool      pinned = false;      // planes are page-locked (cudaHostRegister / cudaHostAlloc)
+    bool      host_alloc = false;  // allocated with cudaHostAlloc (else malloc)
+    int64_t   amb_record = -1, amb_pos = -1;
+    uint64_t  uid = 0;
+    std::string err;
+};
+
+struct kgma_refs {
+    std::vector<std::string> seqs;   // upper-case
+    std::string err;
+};
+
+struct kgma_result {
+    std::vector<kgma_hit> hits;
+    std::vector<kgma_run> runs;
+    std::vector<int64_t>  first_D;                 // [n_profiles][n_records]
+    std::vector<std::vector<double>> dists;        // per profile
+    std::vector<char>     cigar_ops;
+    std::vector<int32_t>  cigar_cnt;
+};
+
+struct kgma_ctx {
+    int device = 0;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaEvent_t  ev[8] = {};
+    int num_sms = 0;
+    size_t smem_optin = 0;
+    std::string err;
+    kgma_stats stats{};
+    // device copy of one genome
+    uint64_t  dg_uid = 0;
+    uint32_t *d_seq2 = nullptr, *d_mask = nullptr;
+    int64_t   d_cap_bases = 0;
+    bool      d_seq_valid = false, d_mask_valid = false;
+    int64_t   d_valid_lo = 0, d_valid_hi = 0;       // base range of seq2 present on the device
+    // scratch
+    void     *d_scratch = nullptr; size_t d_scratch_bytes = 0;
+    void     *h_scratch = nullptr; size_t h_scratch_bytes = 0;   // pinned
+};
+
+namespace kgma {
+
+int set_err(kgma_ctx *ctx, int code, const char *fmt, ...);
+#define KGMA_CUDA(ctx, call)                                                              \
+    do { cudaError_t e_ = (call);                                                         \
+         if (e_ != cudaSuccess) return kgma::set_err((ctx), KGMA_E_CUDA, "%s failed: %s (%s:%d)", #call, \
+                                                      cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// ---- genome.cpp
+int  genome_reserve(kgma_genome *g, int64_t bases);
+int  genome_pin(kgma_ctx *ctx, kgma_genome *g);
+inline int base_code(const kgma_genome *g, int64_t gp) { return (g->seq2[gp >> 4] >> (2 * (gp & 15))) & 3; }
+inline int base_masked(const kgma_genome *g, int64_t gp) { return (g->mask[gp >> 5] >> (gp & 31)) & 1; }
+
+// ---- device genome management (scan.cu)
+int  dev_genome_prepare(kgma_ctx *ctx, kgma_genome *g, bool need_mask);
+
+// ---- per-profile exact integer tables (host side)
+struct ProfTab {
+    int k = 0; int64_t ws = 0, nk = 0; int32_t N = 0;
+    std::vector<int32_t> S_rev;      // S in reversed-2-bit-group index order (matches packed bit order)
+    int64_t N2 = 0, twoN = 0, sumS2 = 0;
+    int64_t T = 0;                   // d < thr  <=>  D < T
+    int64_t Tlo = 0, Thi = 0;        // |d - thr| <= 1e-9*thr  <=>  Tlo <= D < Thi  (near-threshold band)
+    double  denom = 0;               // 2 k N^2
+    double  thr = 0;
+};
+int  build_proftab(kgma_ctx *ctx, const kgma_profile &p, ProfTab &t);
+inline uint32_t rev_kmer(uint32_t c, int k) { uint32_t r = 0; for (int j = 0; j < k; j++) { r = (r << 2) | (c & 3); c >>= 2; } return r; }
+
+// ---- replay.cpp
+struct AlignReq { int32_t record, profile; int64_t first, last; };       // 1-based range to extend
+struct AlignRes { int64_t lo, hi, score; uint32_t cig_off, cig_len; };   // cigar_to_UnitRange result (relative, 1-based)
+void merge_runs(std::vector<kgma_run> &runs);
+int  replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, const kgma_profile *profiles,
+            const kgma_scan_params &P, std::vector<kgma_run> &runs, const std::vector<int64_t> &first_D,
+            kgma_result *res);
+
+// ---- align.cu
+int  align_batch_device(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &reqs,
+                        const kgma_profile *profiles, int n_profiles, bool single_mode_truncate,
+                        int gap_open, int gap_extend, bool tie_open, bool want_cigars,
+                        std::vector<AlignRes> &out, std::vector<char> *cig_ops, std::vector<int32_t> *cig_cnt);
+
+// ---- scratch helpers
+int  dev_scratch(kgma_ctx *ctx, size_t bytes, void **out);
+int  host_scratch(kgma_ctx *ctx, size_t bytes, void **out);
+
+}  // namespace kgma

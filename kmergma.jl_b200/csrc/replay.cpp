@@ -1,0 +1,218 @@
+// Host replay of the reference's sequential hit state machine from run summaries
+// (SURVEY Appendix B).  Replaces the minima finder / hit processing of
+//   ac_gma_testing!  src/GenomeMiner.jl:57,82-104   and   Omn_KmerGMA!  src/OmnGenomeMiner.jl:59,114-156
+// which carry (currminim, CMI, stop, goal_ind / prev_hit_range) base to base.  A run is a maximal
+// stretch of loop steps with d < thr; (t_last, D_min, first argmin) per run is a sufficient
+// statistic, so the replay is O(#runs) and independent of how the device segmented the genome.
+#include "kgma_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <climits>
+
+namespace kgma {
+
+void merge_runs(std::vector<kgma_run> &runs)
+{
+    std::sort(runs.begin(), runs.end(), [](const kgma_run &a, const kgma_run &b) {
+        if (a.profile != b.profile) return a.profile < b.profile;
+        if (a.record != b.record) return a.record < b.record;
+        if (a.t_first != b.t_first) return a.t_first < b.t_first;
+        return (a.flags & KGMA_RUN_MARKER) < (b.flags & KGMA_RUN_MARKER);
+    });
+    std::vector<kgma_run> out;
+    out.reserve(runs.size());
+    for (const kgma_run &r : runs) {
+        if (!(r.flags & KGMA_RUN_MARKER) && !out.empty()) {
+            // find the previous real run (markers never sit between two halves of a split run: they have d >= thr)
+            kgma_run &p = out.back();
+            if (!(p.flags & KGMA_RUN_MARKER) && p.profile == r.profile && p.record == r.record && p.t_last + 1 == r.t_first) {
+                // a run cut by a segment / chunk / shard boundary: min of mins, earlier argmin on ties
+                if (r.D_min < p.D_min) { p.D_min = r.D_min; p.t_argmin = r.t_argmin; p.flags = (p.flags & ~KGMA_HIT_ARGMIN_TIE) | (r.flags & KGMA_HIT_ARGMIN_TIE); }
+                else if (r.D_min == p.D_min) p.flags |= KGMA_HIT_ARGMIN_TIE;
+                p.flags |= (r.flags & (KGMA_HIT_NEAR_THR | KGMA_RUN_OPEN_RIGHT));
+                if (!(r.flags & KGMA_RUN_OPEN_RIGHT)) p.flags &= ~KGMA_RUN_OPEN_RIGHT;
+                p.t_last = r.t_last;
+                continue;
+            }
+        }
+        out.push_back(r);
+    }
+    runs.swap(out);
+}
+
+static uint32_t round_half_flag(double d)
+{
+    double x = d * 100.0, f = x - std::floor(x);
+    return std::fabs(f - 0.5) < 1e-7 ? KGMA_HIT_ROUND_HALF : 0u;
+}
+
+// Alignment.jl:49-51 / OmnGenomeMiner.jl:135-136: remap the aligned sub-range into record coordinates
+static void remap(int64_t first, int64_t L, const AlignRes &a, int64_t *nf, int64_t *nl)
+{
+    int64_t f = std::max<int64_t>(1, first + a.lo - 1);
+    int64_t l = std::min<int64_t>(first + a.hi - 1, L);
+    if (l < f - 1) l = f - 1;                            // Julia UnitRange normalisation
+    *nf = f; *nl = l;
+}
+
+int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, const kgma_profile *profiles,
+           const kgma_scan_params &P, std::vector<kgma_run> &runs, const std::vector<int64_t> &first_D,
+           kgma_result *res)
+{
+    const int C = (int)tabs.size(), nr = (int)g->recs.size(), k = tabs[0].k;
+    const bool cluster = P.mode == KGMA_MODE_CLUSTER;
+    const bool do_align = (P.flags & KGMA_F_ALIGN) != 0;
+    const bool want_cig = (P.flags & KGMA_F_WANT_CIGARS) != 0;
+    const int64_t buff = P.buff;
+    int64_t maxws = 0; for (auto &t : tabs) maxws = std::max(maxws, t.ws);
+    merge_runs(runs);
+    res->hits.clear(); res->cigar_ops.clear(); res->cigar_cnt.clear();
+
+    // index runs per (profile, record)
+    struct Span { size_t b = 0, e = 0; };
+    std::vector<Span> span((size_t)C * nr);
+    for (size_t i = 0; i < runs.size();) {
+        size_t j = i;
+        while (j < runs.size() && runs[j].profile == runs[i].profile && runs[j].record == runs[i].record) j++;
+        if (runs[i].profile < 0 || runs[i].profile >= C || runs[i].record < 0 || runs[i].record >= nr)
+            return set_err(ctx, KGMA_E_ARG, "run with invalid profile/record index");
+        span[(size_t)runs[i].profile * nr + runs[i].record] = { i, j };
+        i = j;
+    }
+    auto steps_of = [&](int r) -> int64_t {
+        if (P.only_record >= 0 && r != P.only_record) return 0;
+        int64_t L = g->recs[r].len;
+        return std::max<int64_t>(0, cluster ? L - maxws - k + 2 : L - maxws);
+    };
+
+    std::vector<AlignReq> reqs; std::vector<AlignRes> ares;
+    std::vector<int64_t> req_of_run;                      // cluster mode: run index -> request index
+    struct Pending { size_t hit; size_t req; int64_t first; };
+    std::vector<Pending> pend;                            // single mode: hits waiting for their extension
+
+    if (!cluster) {
+        // ---------------- ac_gma_testing! ----------------
+        const ProfTab &t = tabs[0]; const int64_t ws = t.ws;
+        int64_t genome_pos = 0;
+        for (int r = 0; r < nr; r++) {
+            const int64_t L = g->recs[r].len;
+            if (L < ws) continue;                         // GenomeMiner.jl:37-39 (genome_pos not advanced)
+            const int64_t steps = steps_of(r);
+            Span sp = span[r];
+            if (steps > 0 && sp.e > sp.b) {
+                int64_t cur = first_D[r];                 // :57 currminim = kmerDist of the first window
+                if (cur == INT64_MIN) return set_err(ctx, KGMA_E_STATE, "first-window distance of record %d missing", r);
+                int64_t CMI = 2, goal = 0; bool stop = true;
+                for (size_t i = sp.b; i < sp.e; i++) {
+                    const kgma_run &ru = runs[i];
+                    if (ru.flags & KGMA_RUN_MARKER) continue;
+                    uint32_t hflags = ru.flags & (KGMA_HIT_NEAR_THR | KGMA_HIT_ARGMIN_TIE);
+                    if (ru.D_min < cur) { cur = ru.D_min; CMI = (k - 1) + ru.t_argmin; stop = false; }   // :82-87 CMI = i_left
+                    if (ru.t_last >= steps) break;        // run still open at the record end: never emitted (A.1 step 5)
+                    if (!stop) {                          // :90-104 at step t_last+1
+                        stop = true; CMI += 1;
+                        if (CMI > goal) {
+                            goal = CMI + ws - 1;
+                            int64_t a = std::max<int64_t>(CMI - buff, 1), b = std::min<int64_t>(CMI + ws - 1 + buff, L);
+                            kgma_hit h{};
+                            h.record = r; h.profile = 0; h.cmi = CMI; h.first = a; h.last = b; h.genome_pos = genome_pos;
+                            h.D = cur; h.dist = (double)cur / t.denom; h.flags = hflags | round_half_flag(h.dist);
+                            if (do_align) { pend.push_back({ res->hits.size(), reqs.size(), a }); reqs.push_back({ r, 0, a, b }); }
+                            res->hits.push_back(h);
+                            cur = INT64_MAX;              // :102 currminim = kmerDist (some value >= thr)
+                        }
+                    }
+                }
+            }
+            genome_pos += L;                              // :106
+        }
+        if (do_align && !reqs.empty()) {
+            int rc = align_batch_device(ctx, g, reqs, profiles, 1, true, P.gap_open, P.gap_extend,
+                                        (P.flags & KGMA_F_TIE_OPEN) != 0, want_cig, ares,
+                                        want_cig ? &res->cigar_ops : nullptr, want_cig ? &res->cigar_cnt : nullptr);
+            if (rc) return rc;
+            for (const Pending &p : pend) {
+                kgma_hit &h = res->hits[p.hit];
+                remap(p.first, g->recs[h.record].len, ares[p.req], &h.first, &h.last);
+                h.align_score = ares[p.req].score; h.cigar_off = ares[p.req].cig_off; h.cigar_len = ares[p.req].cig_len;
+            }
+        }
+        ctx->stats.n_align = (int64_t)reqs.size();
+        return KGMA_OK;
+    }
+
+    // ---------------- Omn_KmerGMA! ----------------
+    // extension results feed back into prev_hit_range (:139,:152), so every terminated run's candidate is extended up front
+    req_of_run.assign(runs.size(), -1);
+    if (do_align) {
+        for (size_t i = 0; i < runs.size(); i++) {
+            const kgma_run &ru = runs[i];
+            if (ru.flags & KGMA_RUN_MARKER) continue;
+            const int64_t L = g->recs[ru.record].len, steps = steps_of(ru.record);
+            if (ru.t_last >= steps) continue;
+            const int64_t CMI = ru.t_argmin, wsq = tabs[ru.profile].ws;
+            int64_t a = std::max<int64_t>(CMI - buff, 1), b = std::min<int64_t>(CMI + wsq - 1 + buff, L);
+            req_of_run[i] = (int64_t)reqs.size();
+            reqs.push_back({ ru.record, ru.profile, a, b });
+        }
+        if (!reqs.empty()) {
+            int rc = align_batch_device(ctx, g, reqs, profiles, C, false, P.gap_open, P.gap_extend,
+                                        (P.flags & KGMA_F_TIE_OPEN) != 0, want_cig, ares,
+                                        want_cig ? &res->cigar_ops : nullptr, want_cig ? &res->cigar_cnt : nullptr);
+            if (rc) return rc;
+        }
+    }
+    ctx->stats.n_align = (int64_t)reqs.size();
+    int64_t genome_pos = 0;
+    struct Ev { int64_t end_step; int q; size_t run; };
+    std::vector<Ev> evs;
+    for (int r = 0; r < nr; r++) {
+        const int64_t L = g->recs[r].len, steps = steps_of(r);
+        if (steps > 0) {
+            evs.clear();
+            for (int q = 0; q < C; q++) {
+                Span sp = span[(size_t)q * nr + r];
+                for (size_t i = sp.b; i < sp.e; i++) if (!(runs[i].flags & KGMA_RUN_MARKER)) evs.push_back({ runs[i].t_last + 1, q, i });
+            }
+            // the reference visits profiles in index order inside each loop step (:95)
+            std::sort(evs.begin(), evs.end(), [](const Ev &a, const Ev &b) { return a.end_step != b.end_step ? a.end_step < b.end_step : a.q < b.q; });
+            std::vector<int64_t> cur(C), CMIs(C, 1); std::vector<char> stop(C, 1);
+            for (int q = 0; q < C; q++) cur[q] = first_D[(size_t)q * nr + r];     // :73 curr_mins = first-window distance
+            int64_t prev_a = 0, prev_b = 0;                                          // :59 prev_hit_range = 0:0
+            for (const Ev &e : evs) {
+                const kgma_run &ru = runs[e.run]; const int q = e.q;
+                if (cur[q] == INT64_MIN) return set_err(ctx, KGMA_E_STATE, "first-window distance of record %d profile %d missing", r, q);
+                if (ru.D_min < cur[q]) { cur[q] = ru.D_min; CMIs[q] = ru.t_argmin; stop[q] = 0; }   // :114-119 CMI = i
+                if (ru.t_last >= steps) continue;                                   // open at the end of the loop
+                if (stop[q]) continue;
+                stop[q] = 1;                                                        // :122
+                const int64_t CMI = CMIs[q];
+                if (CMI >= prev_a && CMI <= prev_b) continue;                       // :126
+                const int64_t wsq = tabs[q].ws;
+                int64_t hl = std::max<int64_t>(CMI - buff, 1), hr = std::min<int64_t>(CMI + wsq - 1 + buff, L);
+                int64_t a = hl, b = hr; int64_t score = 0; uint32_t co = 0, cl = 0;
+                if (do_align) {
+                    int64_t ri = req_of_run[e.run];
+                    if (ri < 0 || reqs[(size_t)ri].first != hl || reqs[(size_t)ri].last != hr)
+                        return set_err(ctx, KGMA_E_STATE, "internal: extension request mismatch");
+                    remap(hl, L, ares[(size_t)ri], &a, &b);
+                    score = ares[(size_t)ri].score; co = ares[(size_t)ri].cig_off; cl = ares[(size_t)ri].cig_len;
+                }
+                if (b < prev_a || a > prev_b) {                                     // :139
+                    kgma_hit h{};
+                    h.record = r; h.profile = q + 1; h.cmi = CMI; h.first = a; h.last = b; h.genome_pos = genome_pos;
+                    h.D = cur[q]; h.dist = (double)cur[q] / tabs[q].denom;
+                    h.flags = (ru.flags & (KGMA_HIT_NEAR_THR | KGMA_HIT_ARGMIN_TIE)) | round_half_flag(h.dist);
+                    h.align_score = score; h.cigar_off = co; h.cigar_len = cl;
+                    res->hits.push_back(h);
+                    prev_a = a; prev_b = b;                                         // :152
+                    cur[q] = INT64_MAX;                                             // :153 curr_mins[ind] = kmerDist
+                }
+            }
+        }
+        genome_pos += L;                                                            // :159 — every record
+    }
+    return KGMA_OK;
+}
+
+}  // namespace kgma
