@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py — findGenes throughput (Mb/s = 1e6 genome bases scanned per second) on the synthetic
+3.1 Gb genome of BASELINE.json configs[1] (24 hg38-like contigs, N runs, 2000 planted IGHV homologues,
+single profile, k = 6, thr = 30, buffer 50, gap (-69,-1), do_align = true).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one complete findGenes scan of the genome (prefilter + count-table kernel + run compaction +
+host replay + batched extension).  For N > 1 (torchrun, one rank per GPU) the packed genome is cut into N
+equal shards with a window-length halo, each rank scans its shard and ships its run summaries (KBs) to
+rank 0 over a gloo side group, rank 0 replays and extends: strong scaling of the 3.1 Gb job, no data-path
+collective.
+
+  value : genome resident in HBM when the timed region starts (tier T0+host replay)
+  e2e   : the same call from pinned pre-packed HOST buffers: H2D of the 2-bit genome + kernels + D2H of
+          run lists / hits inside the timed region (tier T1, the headline against the reference arm)
+  roofline : the prefilter kernel (the one launch that streams the whole genome), 0.25 B/base algorithmic
+  cpu_baseline / --impl reference : the CPU oracle (a C restatement of GenomeMiner.jl:60-104; Julia is not
+          installed here) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+FIX = os.path.join(ROOT, "tests", "fixtures")
+TF = os.path.join(FIX, "fasta_files", "Alp_V_ref.fasta")
+
+# hg38-like contig lengths in Mb: sum ~ 3.1e9
+CONTIG_MB = [248.9, 242.2, 198.3, 190.2, 181.5, 170.8, 159.3, 145.1, 138.4, 133.8, 135.1, 133.3, 114.4, 107.0,
+             102.0, 90.3, 83.3, 80.4, 58.6, 64.4, 46.7, 50.8, 156.0, 57.2]
+SEED = 42
+N_RUN = 10_000          # N run at both contig ends
+CENTROMERE = 3_000_000  # one N run per contig
+N_PLANTS = 2000
+THR, BUFF, GAP_OPEN, GAP_EXT, KMER = 30.0, 50, -69, -1, 6
+METRIC = "findGenes throughput, 3.1 Gb synthetic genome, single profile, k=6"
+UNIT = "Mb/s"
+
+
+def contig_lengths(scale: float):
+    return [max(100_000, int(round(mb * 1e6 * scale))) // 128 * 128 + 77 for mb in CONTIG_MB]
+
+
+def record_offsets(lens):
+    """global (padded) base offset of every record: records start at multiples of 128 (kgma_internal.h REC_ALIGN)"""
+    offs, end = [], 0
+    for L in lens:
+        off = (end + 127) // 128 * 128
+        offs.append(off)
+        end = off + L
+    return offs
+
+
+def read_refs():
+    refs, cur = [], []
+    with open(TF) as fh:
+        for line in fh:
+            if line.startswith(">"):
+                if cur:
+                    refs.append("".join(cur).upper())
+                cur = []
+            else:
+                cur.append(line.strip())
+    if cur:
+        refs.append("".join(cur).upper())
+    return refs
+
+
+def plant_list(lens, n_plants=N_PLANTS, seed=1234):
+    """(record, 1-based position, residues) of the planted homologues: the 84 fixture refs, substitution rates
+    {0,2,5,10,15,20}%, 1-6 nt indels in 25%; every 50th copy is flush against an N run / a 2^k-aligned packed
+    boundary (64 Mi bases) so that shard, chunk and segment edges are exercised."""
+    rng = np.random.default_rng(seed)
+    refs = read_refs()
+    w = np.asarray(lens, dtype=np.float64)
+    w /= w.sum()
+    out = []
+    for i in range(n_plants):
+        r = int(rng.choice(len(lens), p=w))
+        s = list(refs[int(rng.integers(0, len(refs)))])
+        rate = [0.0, 0.02, 0.05, 0.10, 0.15, 0.20][i % 6]
+        for j in range(len(s)):
+            if rng.random() < rate:
+                s[j] = "ACGT"[int(rng.integers(0, 4))]
+        if i % 4 == 0:
+            for _ in range(int(rng.integers(1, 3))):
+                p = int(rng.integers(1, len(s) - 1))
+                n = int(rng.integers(1, 7))
+                if rng.random() < 0.5:
+                    del s[p:p + n]
+                else:
+                    s[p:p] = list("ACGT"[int(rng.integers(0, 4))] * n)
+        s = "".join(s)
+        L = lens[r]
+        lo, hi = N_RUN + 1, L - N_RUN - len(s)
+        pos = int(rng.integers(lo, hi))
+        if i % 50 == 0:
+            b = (pos >> 26) << 26
+            if b - 150 > lo:
+                pos = b - 150            # straddles a 64 Mi-base boundary
+        out.append((r, pos, s))
+    return out
+
+
+def clocks_sampler(device_index, stop, samples):
+    """sample SM clock + throttle reasons while the timed region runs (B200_PROFILING.md clocks line)"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        while not stop.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            try:
+                rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            samples.append((sm, mx, int(rs)))
+            time.sleep(0.002)
+    except Exception as e:       # clocks are evidence, not a dependency
+        samples.append(("error", str(e), 0))
+
+
+def summarise_clocks(samples):
+    good = [s for s in samples if s[0] != "error"]
+    if not good:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable: %s" % (samples[0][1] if samples else "no samples")]}
+    names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+             0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+             0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+    bits = 0
+    for s in good:
+        bits |= s[2]
+    return {"sm_mhz": float(np.median([s[0] for s in good])), "sm_max_mhz": float(good[0][1]),
+            "reasons": [n for b, n in names.items() if bits & b and n != "gpu_idle"], "samples": len(good)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU oracle on host cores
+def gen_chunk(O, lens, offs, plants, rec, start, n):
+    """n residues of record `rec` from 0-based `start`: generator + N runs + planted copies, as kgma_genome_synth + put_seq"""
+    buf = O.synth(SEED, offs[rec] + start, n)
+    L = lens[rec]
+    c0 = (L * 2 // 5) // 32 * 32
+    for a, b in ((0, N_RUN), (L - N_RUN, L), (c0, c0 + CENTROMERE)):     # same N runs as kgma_genome_synth
+        lo, hi = max(a, start), min(b, start + n)
+        if hi > lo:
+            buf[lo - start:hi - start] = b"N" * (hi - lo)
+    for (r, pos, s) in plants:
+        if r == rec and pos - 1 >= start and pos - 1 + len(s) <= start + n:
+            buf[pos - 1 - start:pos - 1 - start + len(s)] = s.encode()
+    return bytes(buf)
+
+
+def cpu_chunk(O, RV, lens, offs, plants, rec, start, n):
+    """scan n bases of record `rec` starting at 0-based `start` with the oracle's GenomeMiner.jl loop"""
+    buf = gen_chunk(O, lens, offs, plants, rec, start, n)
+    t0 = time.perf_counter()
+    nh = O.ac_gma_seq_count(buf, RV, KMER, 289, THR, BUFF)
+    return time.perf_counter() - t0, nh
+
+
+def cpu_baseline(seconds=12.0, chunk=100_000_000):
+    """single-thread oracle on consecutive chunks of contig 1 until ~`seconds` of CPU work"""
+    from oracle import oracle as O
+    RV, ws, cons = O.gen_ref_ws_cons(TF, KMER)
+    lens = contig_lengths(1.0)
+    offs = record_offsets(lens)
+    plants = plant_list(lens)
+    spent, bases, start, hits = 0.0, 0, 0, 0
+    while spent < seconds and start + chunk <= lens[0]:
+        dt, nh = cpu_chunk(O, RV, lens, offs, plants, 0, start, chunk)
+        spent += dt; bases += chunk; start += chunk; hits += nh
+    return {"value": bases / spent / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "first %d Mb of contig 1 of the same synthetic genome (N runs + planted copies included), "
+                      "oracle ac_gma hot loop without extension, %d hits, %.1f s" % (bases // 1_000_000, hits, spent)}
+
+
+def run_reference(args):
+    """--impl reference: the oracle's GenomeMiner.jl loop, one task per chunk over all host threads (the reference's
+    only parallel strategy is one task per FASTA record, MultiThread/GenomeMiner.jl:127-140)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    RV, ws, cons = O.gen_ref_ws_cons(TF, KMER)
+    lens = contig_lengths(1.0)
+    offs = record_offsets(lens)
+    plants = plant_list(lens)
+    T = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    chunk = 16_000_000
+    tasks = [(i % len(lens), (i // len(lens)) * chunk) for i in range(T)]
+
+    def prep(t):
+        return gen_chunk(O, lens, offs, plants, t[0], t[1], chunk)
+
+    with ThreadPoolExecutor(T) as ex:
+        bufs = list(ex.map(prep, tasks))
+
+        def step():
+            return sum(ex.map(lambda b: O.ac_gma_seq_count(b, RV, KMER, 289, THR, BUFF), bufs))
+
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            nh = step()
+        dt = time.perf_counter() - t0
+    val = T * chunk * args.steps / dt / 1e6
+    sample = "%d chunks of %d Mb of the same synthetic genome per step, one oracle task per chunk on %d threads" % (T, chunk // 1_000_000, T)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "findGenes, 3.1 Gb synthetic genome (24 contigs), single profile k=6, thr=30 (BASELINE configs[1])",
+                   "note": "Julia is not installed: the reference's algorithm is timed as the C oracle port (oracle/kmergma_oracle.c), "
+                           "scan loop only, inputs in memory"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": T, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "hits_per_step": int(nh)}))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import kmergma_jl_b200 as K
+    L = K.L
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    side = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        side = dist.new_group(backend="gloo")       # host-side plumbing for the KB-sized run lists
+
+    ctx = K.Context(local)
+    lens = contig_lengths(args.scale)
+    plants = plant_list(lens, n_plants=max(10, int(N_PLANTS * args.scale)))
+    t_setup = time.perf_counter()
+    g = K.Genome.synth(lens, seed=SEED, n_run_len=N_RUN, centromere_len=CENTROMERE, ctx=ctx)
+    for (r, pos, s) in plants:
+        g.put_seq(r, pos, s)
+    total = g.total_len
+    RV, ws, cons = K.gen_ref_ws_cons(TF, KMER)
+    t_setup = time.perf_counter() - t_setup
+    shard = (rank, world)
+    base_flags = L.F_ALIGN
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    agg = {"launches": 0, "h2d": 0, "d2h": 0, "filter_ms": 0.0, "exact_ms": 0.0, "align_ms": 0.0, "dev_ms": 0.0,
+           "h2d_ms": 0.0, "blocks": 0, "flagged": 0, "exact_windows": 0}
+
+    def acc():
+        st = ctx.stats()
+        agg["launches"] += st["launches"]; agg["h2d"] += st["h2d_bytes"]; agg["d2h"] += st["d2h_bytes"]
+        agg["filter_ms"] += st["filter_ms"]; agg["exact_ms"] += st["exact_ms"]; agg["align_ms"] += st["align_ms"]
+        agg["dev_ms"] += st["total_ms"] + st["align_ms"]; agg["h2d_ms"] += st["h2d_ms"]
+        agg["blocks"] += st["blocks_total"]; agg["flagged"] += st["blocks_flagged"]; agg["exact_windows"] += st["exact_windows"]
+
+    def step(resident: bool):
+        fl = base_flags | (L.F_RESIDENT if resident else 0)
+        if world == 1:
+            out = K.scan_raw(g, [RV], [ws], [cons], [THR], KMER, L.MODE_SINGLE, BUFF, fl, GAP_OPEN, GAP_EXT, ctx=ctx)
+            acc()
+            return out
+        part = K.scan_raw(g, [RV], [ws], [cons], [THR], KMER, L.MODE_SINGLE, BUFF, fl & ~L.F_ALIGN, GAP_OPEN, GAP_EXT,
+                          ctx=ctx, runs_only=True, shard=shard)
+        acc()
+        st1 = ctx.stats()
+        payload = (part.runs.tobytes(), part.first_D.tobytes())
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(payload, gathered, dst=0, group=side)
+        if rank != 0:
+            return None
+        runs = np.concatenate([np.frombuffer(p[0], dtype=np.uint8) for p in gathered])
+        firsts = np.max(np.stack([np.frombuffer(p[1], dtype=np.int64) for p in gathered]), axis=0)
+        out = K.replay_raw(g, [RV], [ws], [cons], [THR], KMER, L.MODE_SINGLE, BUFF, fl, GAP_OPEN, GAP_EXT, runs, firsts, ctx=ctx)
+        st2 = ctx.stats()                            # replay adds the extension launches to the scan's counters
+        agg["launches"] += st2["launches"] - st1["launches"]
+        agg["align_ms"] += st2["align_ms"]; agg["dev_ms"] += st2["align_ms"]
+        return out
+
+    def timed(resident: bool):
+        for k_ in agg:
+            agg[k_] = 0
+        stop, samples = threading.Event(), []
+        th = threading.Thread(target=clocks_sampler, args=(local, stop, samples), daemon=True)
+        barrier()
+        th.start()
+        t0 = time.perf_counter()
+        out = None
+        for _ in range(args.steps):
+            out = step(resident)
+        barrier()
+        dt = time.perf_counter() - t0
+        stop.set(); th.join()
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out, summarise_clocks(samples), dict(agg)
+
+    # ---- value: genome resident in HBM
+    g.make_resident(ctx)
+    for _ in range(args.warmup):
+        step(True)
+    dt_res, out_res, clocks, a_res = timed(True)
+    # ---- e2e: pinned host -> device inside the timed region
+    for _ in range(args.warmup):
+        step(False)
+    dt_e2e, out_e2e, clocks_e2e, a_e2e = timed(False)
+
+    if world > 1:
+        tl = torch.tensor([a_res["launches"], a_e2e["h2d"], a_e2e["d2h"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tl)
+        launches_all, h2d_all, d2h_all = [float(x) for x in tl.tolist()]
+    else:
+        launches_all, h2d_all, d2h_all = a_res["launches"], a_e2e["h2d"], a_e2e["d2h"]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        filt_ms = a_res["filter_ms"] / args.steps
+        alg_bytes = a_res["blocks"] / args.steps * 64 * 0.25
+        achieved = alg_bytes / (filt_ms * 1e-3) / 1e9 if filt_ms > 0 else 0.0
+        hits = out_res.hits
+        same = [(h.record, h.first, h.last, h.D) for h in hits] == [(h.record, h.first, h.last, h.D) for h in out_e2e.hits]
+        line = {
+            "metric": METRIC, "value": total * args.steps / dt_res / 1e6, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt_res / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "findGenes, %.2f Gb synthetic genome (24 contigs, N runs, %d planted IGHV homologues), single profile "
+                                   "k=6 ws=%d N=84, thr=30, buffer 50, gap (-69,-1), do_align=true (BASELINE configs[1])" % (total / 1e9, len(plants), ws),
+                       "parallelism": "genome sharded x%d with window halo, host merge of run lists" % world,
+                       "l2": "input (%.0f MB packed) larger than L2; no flush needed" % (total / 4e6),
+                       "timing": "host clock around blocking C-ABI calls bracketed by device sync + barrier, max over ranks "
+                                 "(>= the CUDA-event device time reported in device_ms_per_step)"},
+            "e2e": {"value": total * args.steps / dt_e2e / 1e6, "unit": UNIT, "ms_per_step": dt_e2e / args.steps * 1e3,
+                    "h2d_bytes_per_step": h2d_all / args.steps, "d2h_bytes_per_step": d2h_all / args.steps},
+            "gpu_launches": int(launches_all),
+            "device_ms_per_step": {"rank0_total": a_res["dev_ms"] / args.steps, "prefilter": filt_ms,
+                                   "count_table": a_res["exact_ms"] / args.steps, "extension": a_res["align_ms"] / args.steps,
+                                   "e2e_h2d": a_e2e["h2d_ms"] / args.steps},
+            "roofline": {"bound": "hbm", "kernel": "kgma_prefilter<6>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                         "algorithmic_bytes_per_launch": alg_bytes},
+            "clocks": clocks, "clocks_e2e": clocks_e2e,
+            "hits_per_step": len(hits), "hits_equal_resident_vs_e2e": bool(same),
+            "prefilter_blocks_flagged_per_step": a_res["flagged"] / args.steps,
+            "count_table_windows_per_step": a_res["exact_windows"] / args.steps,
+            "setup_s": t_setup, "readme_julia_mbs": 40,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="genome size as a fraction of 3.1 Gb (testing only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -307,6 +307,7 @@ int kgma_genome_put_seq(kgma_genome *g, int r, int64_t first, const char *seq, i
     if (!g || !seq || r < 0 || r >= (int)g->recs.size()) return KGMA_E_ARG;
     const auto &R = g->recs[r];
     if (first < 1 || first + len - 1 > R.len) return KGMA_E_ARG;
+    g->uid = g_uid.fetch_add(1);                         // any device copy of the old contents is stale now
     for (int64_t i = 0; i < len; i++) {
         uint8_t c = CT.t[(uint8_t)seq[i]];
         if (c == 0xFF || (c & 8)) return KGMA_E_SYMBOL;

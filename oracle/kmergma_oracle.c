@@ -661,3 +661,21 @@ int64_t orc_ac_gma_seq(const char *s, int64_t L, const double *RV, int k, int64_
     int rc = orc_ac_gma(&f, RV, NULL, 0, k, ws, thr, buff, 0, -69, -1, 1, hits, hit_cap, &nh, NULL, 0, NULL, -1);
     return rc ? rc : nh;
 }
+
+/* ------------------------------------------------------------------ */
+/* Synthetic genome generator shared with the device generator (kgma_genome_synth,
+ * SURVEY §8d): base(p) = splitmix64(seed ^ p) & 3 over the global (padded) base
+ * coordinate p.  Writes n upper-case residues for p0 .. p0+n-1. */
+static inline uint64_t orc_splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+void orc_synth(uint64_t seed, int64_t p0, int64_t n, char *out)
+{
+    static const char nt[4] = { 'A', 'C', 'G', 'T' };
+    for (int64_t i = 0; i < n; i++) out[i] = nt[orc_splitmix64(seed ^ (uint64_t)(p0 + i)) & 3];
+}

@@ -88,6 +88,8 @@ def lib():
         L.orc_ac_gma_seq.restype = C.c_int64
         L.orc_ac_gma_seq.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_double,
                                      C.c_int64, C.c_void_p, C.c_int64]
+        L.orc_synth.restype = None
+        L.orc_synth.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_void_p]
     return _lib
 
 
@@ -434,10 +436,19 @@ def exactMatch(query, subject, overlap: bool = True):
     return one(_b(subject))
 
 
+def synth(seed: int, p0: int, n: int) -> bytearray:
+    """residues p0..p0+n-1 of the synthetic genome (same generator as kgma_genome_synth)"""
+    buf = bytearray(n)
+    cbuf = (C.c_char * n).from_buffer(buf)
+    lib().orc_synth(seed, p0, n, C.addressof(cbuf))
+    del cbuf
+    return buf
+
+
 def ac_gma_seq_count(seq: bytes, RV: np.ndarray, k: int, ws: int, thr: float, buff: int = 50) -> int:
     """bench helper: hot loop of GenomeMiner.jl:60-104 (no alignment) on an in-memory sequence."""
     rv = np.ascontiguousarray(RV, dtype=np.float64)
-    cap = 1 << 20
+    cap = 1 << 16
     arr = (_Hit * cap)()
     n = lib().orc_ac_gma_seq(seq, len(seq), rv.ctypes.data, k, ws, float(thr), buff, arr, cap)
     _check(int(n), "ac_gma_seq")

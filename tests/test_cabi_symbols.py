@@ -1,0 +1,114 @@
+"""CPU-side checks of the drop-in boundary: libkmergma_cuda.so loads without a GPU and exports every
+function include/kmergma.h declares; host-only entry points (ingest, profile generation) agree with the oracle.
+No compute entry point is called here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, TF, GENOME, MINI_GENOME, TEST_CONSENSUS
+
+
+def declared_functions():
+    txt = open(os.path.join(ROOT, "include", "kmergma.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(kgma_[A-Za-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import kmergma_jl_b200 as K
+    lib = K.L.load()
+    names = declared_functions()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(lib, n), n
+        assert n in K.L.SYMBOLS, "ctypes prototype missing for " + n
+    assert set(K.L.SYMBOLS) == set(names)
+    assert lib.kgma_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    import kmergma_jl_b200 as K
+    L = K.L
+    assert C.sizeof(L.Run) == 48 and C.sizeof(L.Hit) == 80 and C.sizeof(L.Match) == 24
+    assert C.sizeof(L.ScanParams) == 40 and C.sizeof(L.Profile) == 48
+
+
+def test_no_gpu_means_loud_failure():
+    """there is no CPU fallback: without a device kgma_create fails with KGMA_E_CUDA"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import kmergma_jl_b200 as K
+    with pytest.raises(K.KmerGMAError) as e:
+        K.Context(0)
+    assert e.value.code == K.L.E_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "kmergma.jl_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cpp", ".cu", ".h")):
+                src = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle" not in src.lower().replace("# oracle", ""), os.path.join(dp, f)
+
+
+def test_profile_generation_matches_oracle():
+    import kmergma_jl_b200 as K
+    from oracle import oracle as O
+    for k in (1, 2, 6, 7):
+        rv, ws, cons = K.gen_ref_ws_cons(TF, k)
+        orv, ows, ocons = O.gen_ref_ws_cons(TF, k)
+        assert ws == ows == 289 and cons == ocons == TEST_CONSENSUS
+        assert np.array_equal(np.asarray(rv), orv)
+    kf, kw, kc, kinv = K.cluster_ref_API(TF, 6)
+    of = O.cluster_ref_API(TF, 6)
+    assert kw == list(of[1]) == [288, 288, 288, 289, 290, 289]
+    assert all(np.array_equal(np.asarray(a), b) for a, b in zip(kf, of[0]))
+    assert list(kc) == list(of[2])
+    # KFV -> (S, N) recovery used when a plain Float64 refVec crosses the boundary
+    lib = K.L.load()
+    for v in list(kf) + [K.gen_ref_ws_cons(TF, 6)[0]]:
+        S = np.zeros(v.size, np.int32); n = C.c_int32()
+        assert lib.kgma_profile_from_kfv(np.ascontiguousarray(v, np.float64).ctypes.data, v.size, 0, S.ctypes.data, C.byref(n)) == 0
+        assert np.array_equal(S * v.n_refs, v.S.astype(np.int64) * n.value)     # same rational profile
+
+
+def test_ingest_round_trip_and_packed_paths():
+    import kmergma_jl_b200 as K
+    from oracle import oracle as O
+    g, f = K.Genome.from_fasta(GENOME), O.Fasta(GENOME)
+    assert len(g) == len(f) == 4
+    for r in range(4):
+        assert g.identifier(r) == f.identifier(r) and g.description(r) == f.description(r)
+        assert g.seq(r) == f.seq(r)
+    assert g.seq(3, 6852, 7140) == f.seq(3)[6851:7140]
+    # ASCII vs pre-packed vs BioSequences 4-bit ingest give the same container
+    s = "ACGTNNacgtn" * 37 + "TTGACA"
+    lib = K.L.load()
+    codes = np.array([{"A": 0, "C": 1, "G": 2, "T": 3, "N": 3}[c] for c in s.upper()], dtype=np.uint64)
+    n = len(s)
+    w2 = np.zeros((n + 15) // 16, np.uint32); m = np.zeros((n + 31) // 32, np.uint32); b4 = np.zeros((n + 15) // 16, np.uint64)
+    for i, c in enumerate(s.upper()):
+        w2[i >> 4] |= np.uint32(int(codes[i]) << (2 * (i & 15)))
+        if c == "N":
+            m[i >> 5] |= np.uint32(1 << (i & 31))
+        b4[i >> 4] |= np.uint64((15 if c == "N" else 1 << int(codes[i])) << (4 * (i & 15)))
+    outs = []
+    for mode in ("ascii", "packed", "bio4"):
+        h = C.c_void_p(); lib.kgma_genome_create(C.byref(h))
+        if mode == "ascii":
+            rc = lib.kgma_genome_append_ascii(h, b"x", b"x y", s.encode(), n)
+        elif mode == "packed":
+            rc = lib.kgma_genome_append_packed(h, b"x", b"x y", w2.ctypes.data, m.ctypes.data, n)
+        else:
+            rc = lib.kgma_genome_append_bio4(h, b"x", b"x y", b4.ctypes.data, n)
+        assert rc == 0 and lib.kgma_genome_seal(h) == 0
+        gg = K.Genome(h, lib)
+        outs.append(gg.seq(0))
+    assert outs[0] == outs[1] == outs[2] == s.upper()
+    with pytest.raises(K.KmerGMAError):
+        K.Genome.from_records([("bad", "ACGT!ACGT")])

@@ -1,0 +1,438 @@
+"""GPU parity tests: every call goes through the C ABI of libkmergma_cuda (via the host mirror
+kmergma_jl_b200) and is compared (a) with the reference's own golden strings
+(test/test_folder/test-KmerGMA.jl, cited per test) and (b) with the CPU oracle on the same inputs.
+
+Bar: hit coordinates / record names / exact-match positions bit-exact; distances within 1e-9 relative
+(the device computes the exact rational D/(2kN^2), the oracle the reference's Float64 accumulator).
+"""
+import ctypes as C
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import TF, MINI_GENOME, GENOME, EIGHT, TEST_CONSENSUS
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def K():
+    import kmergma_jl_b200 as K
+    K.default_context()          # fails loudly without a B200 / without the built library
+    return K
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle as O
+    return O
+
+
+@pytest.fixture(scope="module")
+def prof(K):
+    return K.gen_ref_ws_cons(TF, 6)
+
+
+def descs(res):
+    return [r.description for r in res]
+
+
+def assert_hits_equal(K, kout, ohits, cluster=False):
+    """device hits (ctypes structs) vs oracle hits: coordinates bit-exact, distance within REL."""
+    assert len(kout.hits) == len(ohits), (len(kout.hits), len(ohits))
+    for h, o in zip(kout.hits, ohits):
+        assert (h.record, h.first, h.last, h.genome_pos) == (o.record, o.first, o.last, o.genome_pos)
+        if cluster:
+            assert h.profile == o.kfv
+        assert abs(h.dist - o.dist) <= REL * max(abs(o.dist), 1e-300), (h.dist, o.dist)
+        assert K.julia_round2(h.dist) == K.julia_round2(o.dist) or (h.flags & K.L.HIT_ROUND_HALF)
+
+
+# ------------------------------------------------------------------ goldens: GenomeMiner.jl
+def test_ac_gma_no_align_golden(K, prof):
+    """test-KmerGMA.jl:167-177"""
+    RV, ws, cons = prof
+    res = [K.FastaRecord("test", "tt")]
+    K.ac_gma_testing(genome_path=GENOME, refVec=RV, consensus_refseq=cons, windowsize=ws, thr=30,
+                     do_align=False, resultVec=res)
+    assert len(res) == 8
+    assert res[2].description == "JQ684648.1 | dist = 9.21 | MatchPos = 20380:20768 | GenomePos = 0 | Len = 389"
+    assert res[-3].description == "AM773548.1 | dist = 8.1 | MatchPos = 6807:7195 | GenomePos = 444023 | Len = 389"
+    assert all(len(r.sequence) == 389 for r in res[1:])
+
+
+def test_ac_gma_align_golden(K, prof):
+    """test-KmerGMA.jl:179-193"""
+    RV, ws, cons = prof
+    res, hit_vec = [], []
+    K.ac_gma_testing(genome_path=GENOME, refVec=RV, consensus_refseq=cons, windowsize=ws, thr=30,
+                     do_align=True, get_hit_loci=True, resultVec=res, hit_loci_vec=hit_vec)
+    assert len(res) == 7
+    assert hit_vec == [8543, 20425, 221912, 234018, 450875, 467930, 477868]
+    assert res[1].description == "JQ684648.1 | dist = 9.21 | MatchPos = 20425:20713 | GenomePos = 0 | Len = 289"
+    assert res[-3].description == "AM773548.1 | dist = 8.1 | MatchPos = 6852:7140 | GenomePos = 444023 | Len = 289"
+    assert res[5].description == "AM773548.1 | dist = 24.87 | MatchPos = 23907:24201 | GenomePos = 444023 | Len = 295"
+
+
+def test_ac_gma_dists_golden(K, O, prof):
+    """test-KmerGMA.jl:195-211 + every distance against the oracle's Float64 accumulator"""
+    RV, ws, cons = prof
+    res, dist_vec = [], []
+    K.ac_gma_testing(genome_path=GENOME, refVec=RV, consensus_refseq=cons, windowsize=ws, thr=10,
+                     do_align=False, do_return_dists=True, resultVec=res, dist_vec=dist_vec)
+    assert len(dist_vec) == 484127
+    assert round(float(np.mean(dist_vec))) == 46
+    assert len(res) == 3
+    assert res[0].description == "JQ684648.1 | dist = 9.21 | MatchPos = 20380:20768 | GenomePos = 0 | Len = 389"
+    assert res[-1].description == "AM773548.1 | dist = 8.1 | MatchPos = 6807:7195 | GenomePos = 444023 | Len = 389"
+    _, _, od = O.ac_gma_testing(GENOME, np.asarray(RV), cons, windowsize=ws, thr=10, do_align=False, do_return_dists=True)
+    d = np.asarray(dist_vec)
+    assert d.shape == od.shape
+    assert np.max(np.abs(d - od) / np.maximum(np.abs(od), 1e-300)) <= REL
+
+
+def test_record_kmergma_golden(K, prof):
+    """test-KmerGMA.jl:229-250"""
+    RV, ws, cons = prof
+    g = K.Genome.from_fasta(MINI_GENOME)
+    rec = K.FastaRecord(g.description(0), g.seq(0))
+    res = [[]]
+    K.record_KmerGMA(record=rec, refVec=RV, consensus_refseq=cons, resultVec_vec=res, thr=30)
+    assert descs(res[0]) == [
+        "AM773548.1 | dist = 8.1 | MatchPos = 6852:7140 | Len = 289",
+        "AM773548.1 | dist = 24.87 | MatchPos = 23907:24201 | Len = 295",
+        "AM773548.1 | dist = 10.99 | MatchPos = 33845:34133 | Len = 289"]
+
+
+# ------------------------------------------------------------------ goldens: OmnGenomeMiner.jl / API.jl
+def test_omn_golden(K):
+    """test-KmerGMA.jl:214-227"""
+    rvs, ws, cons, inv = K.cluster_ref_API(TF, 6, cutoffs=[7, 12, 20, 25], include_avg=False)
+    res = []
+    K.Omn_KmerGMA(genome_path=MINI_GENOME, refVecs=rvs, windowsizes=ws, consensus_seqs=cons, resultVec=res,
+                  buff=200, thr_vec=[37, 33, 38, 34, 28, 27])
+    assert descs(res) == [
+        "AM773548.1 | Dist = 20.17 | KFV = 3 | MatchPos = 6852:7139 | GenomePos = 0 | Len = 288",
+        "AM773548.1 | Dist = 33.96 | KFV = 4 | MatchPos = 23907:24198 | GenomePos = 0 | Len = 292",
+        "AM773548.1 | Dist = 26.17 | KFV = 3 | MatchPos = 33845:34132 | GenomePos = 0 | Len = 288"]
+
+
+def test_findgenes_cluster_mode_golden(K):
+    """test-KmerGMA.jl:265-271"""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = K.findGenes_cluster_mode(genome_path=MINI_GENOME, ref_path=TF, KmerDistThrs=[35., 31, 38, 34, 27, 27],
+                                     buffer=100, verbose=False)[0]
+    assert descs(a) == [
+        "AM773548.1 | Dist = 20.17 | KFV = 3 | MatchPos = 6852:7139 | GenomePos = 0 | Len = 288",
+        "AM773548.1 | Dist = 33.96 | KFV = 4 | MatchPos = 23907:24193 | GenomePos = 0 | Len = 287",
+        "AM773548.1 | Dist = 26.17 | KFV = 3 | MatchPos = 33845:34132 | GenomePos = 0 | Len = 288"]
+
+
+def test_findgenes_golden(K):
+    """test-KmerGMA.jl:257-263; the automatic threshold comes from a non-Julia RNG, the three hits
+    are far below any plausible value of it"""
+    a = K.findGenes(genome_path=MINI_GENOME, ref_path=TF, verbose=False)[0]
+    assert descs(a) == [
+        "AM773548.1 | dist = 8.1 | MatchPos = 6852:7140 | GenomePos = 0 | Len = 289",
+        "AM773548.1 | dist = 24.87 | MatchPos = 23907:24201 | GenomePos = 0 | Len = 295",
+        "AM773548.1 | dist = 10.99 | MatchPos = 33845:34133 | GenomePos = 0 | Len = 289"]
+
+
+def test_warnings(K):
+    """test-KmerGMA.jl:275-294"""
+    with pytest.warns(UserWarning, match="Such a low k value of 3 likely won't yield the most accurate results"):
+        K.findGenes(genome_path=MINI_GENOME, ref_path=TF, k=3, verbose=False)
+    with pytest.warns(UserWarning, match="Setting do_return_dists to true may be very memory intensive"):
+        K.findGenes(genome_path=MINI_GENOME, ref_path=TF, verbose=False, do_return_dists=True)
+    with pytest.warns(UserWarning) as rec:
+        K.findGenes_cluster_mode(genome_path=MINI_GENOME, ref_path=TF, verbose=False,
+                                 KmerDistThrs=[100., 200, 20, 300, 200, 100])
+    assert any(str(w.message) == "The kmer distance thresholds [100.0, 200.0, 20.0, 300.0, 200.0, 100.0] at index/indicies "
+               "1, 2, 4, 5, 6 for k = 6 is potentially too high, and may result in more false positives." for w in rec)
+
+
+def test_k_ge_window_error(K):
+    """API.jl:70"""
+    with pytest.raises(K.KmerGMAError):
+        K.ac_gma_testing(genome_path=MINI_GENOME, refVec=K.KFV(np.zeros(4 ** 6), np.zeros(4 ** 6, np.int32), 1),
+                         consensus_refseq="ACGT", k=6, windowsize=5, thr=10, do_align=False, resultVec=[])
+
+
+# ------------------------------------------------------------------ goldens: Alignment.jl
+def test_align_unitrange_golden(K):
+    """test-KmerGMA.jl:129-145"""
+    g = K.Genome.from_fasta(EIGHT)
+    assert K.align_unitrange((g, 0), (450, 900), TEST_CONSENSUS, 289, 1000) == (501, 789)
+    # cigar_to_UnitRange goldens: consensus = query, gap model (-5,-1)
+    assert K.align_unitrange("GGGGGATGCATGCAAAAA", (1, 18), "ATGCATGC", 8, 18, gap_open=-5, gap_extend=-1) == (6, 13)
+    assert K.align_unitrange("GGGGGATGCTTATGCAAAAA", (1, 20), "ATGCATGC", 8, 20, gap_open=-5, gap_extend=-1) == (6, 15)
+
+
+def test_align_batch_vs_oracle(K, O, prof):
+    """random slices with substitutions, indels and N against the oracle's semiglobal DP (range + score)"""
+    RV, ws, cons = prof
+    rng = np.random.default_rng(7)
+    f = O.Fasta(GENOME)
+    seq = f.seq(3)
+    recs = []
+    for t in range(40):
+        base = list(cons[:ws])
+        # mutate the consensus, then embed it in genomic context
+        for _ in range(int(rng.integers(0, 40))):
+            base[int(rng.integers(0, len(base)))] = "ACGTN"[int(rng.integers(0, 5))]
+        for _ in range(int(rng.integers(0, 4))):
+            p = int(rng.integers(1, len(base) - 1))
+            if rng.random() < 0.5:
+                del base[p:p + int(rng.integers(1, 7))]
+            else:
+                base[p:p] = list("ACGT"[int(rng.integers(0, 4))] * int(rng.integers(1, 7)))
+        a = int(rng.integers(0, 30000))
+        left, right = int(rng.integers(0, 120)), int(rng.integers(0, 120))
+        recs.append(("r%d" % t, seq[a:a + left] + "".join(base) + seq[a + 500:a + 500 + right]))
+    g = K.Genome.from_records(recs)
+    ctx = K.default_context()
+    n = len(recs)
+    rec = np.arange(n, dtype=np.int32)
+    first = np.ones(n, np.int64)
+    last = np.asarray([len(s) for _, s in recs], np.int64)
+    for go, ge in ((-69, -1), (-200, -1), (-5, -1), (-10, -3)):
+        of, ol, sc = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.int64)
+        c = cons[:ws].encode()
+        ctx.check(ctx._lib.kgma_align_batch(ctx._h, g._h, c, len(c), go, ge, 0, n, rec.ctypes.data, first.ctypes.data,
+                                            last.ctypes.data, of.ctypes.data, ol.ctypes.data, sc.ctypes.data))
+        for i, (_, s) in enumerate(recs):
+            cig, score = O.pairalign_semiglobal(cons[:ws], s, go, ge)
+            lo, hi = O.align_unitrange(s, (1, len(s)), cons, ws, len(s), go, ge)
+            assert (int(of[i]), int(ol[i])) == (lo, hi), (i, go, ge, cig)
+            assert int(sc[i]) == score
+
+
+# ------------------------------------------------------------------ oracle sweeps: single mode
+@pytest.mark.parametrize("thr", [10, 20, 30, 35, 40, 44, 48, 55])
+@pytest.mark.parametrize("dense", [False, True])
+def test_single_vs_oracle_thresholds(K, O, prof, thr, dense):
+    RV, ws, cons = prof
+    out = K.ac_gma_testing(genome_path=GENOME, refVec=RV, consensus_refseq=cons, windowsize=ws, thr=thr,
+                           do_align=False, resultVec=[], dense=dense)
+    oh, _, _ = O.ac_gma_testing(GENOME, np.asarray(RV), cons, windowsize=ws, thr=thr, do_align=False)
+    assert_hits_equal(K, out, oh)
+
+
+@pytest.mark.parametrize("thr,buff", [(30, 50), (40, 0), (44, 100)])
+def test_single_align_vs_oracle(K, O, prof, thr, buff):
+    RV, ws, cons = prof
+    res = []
+    out = K.ac_gma_testing(genome_path=GENOME, refVec=RV, consensus_refseq=cons, windowsize=ws, thr=thr, buff=buff,
+                           do_align=True, resultVec=res)
+    oh, _, _ = O.ac_gma_testing(GENOME, np.asarray(RV), cons, windowsize=ws, thr=thr, buff=buff, do_align=True)
+    assert_hits_equal(K, out, oh)
+    assert [r.sequence for r in res] == [h.seq for h in oh]
+    assert descs(res) == [h.description() for h in oh]
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7])
+def test_single_other_k_vs_oracle(K, O, k):
+    RV, ws, cons = K.gen_ref_ws_cons(TF, k)
+    orv, ows, ocons = O.gen_ref_ws_cons(TF, k)
+    assert ws == ows and cons == ocons and np.array_equal(np.asarray(RV), orv)
+    # a threshold low enough to give a handful of hits for every k
+    _, _, od = O.ac_gma_testing(MINI_GENOME, orv, cons, k=k, windowsize=ws, thr=0, do_align=False, do_return_dists=True)
+    thr = float(np.quantile(od, 0.02))
+    for dense in (False, True):
+        out = K.ac_gma_testing(genome_path=MINI_GENOME, refVec=RV, consensus_refseq=cons, k=k, windowsize=ws, thr=thr,
+                               do_align=False, resultVec=[], dense=dense)
+        oh, _, _ = O.ac_gma_testing(MINI_GENOME, orv, cons, k=k, windowsize=ws, thr=thr, do_align=False)
+        assert len(oh) > 0
+        assert_hits_equal(K, out, oh)
+
+
+# ------------------------------------------------------------------ oracle sweeps: cluster mode
+@pytest.mark.parametrize("thrs", [[35, 31, 38, 34, 27, 27], [37, 33, 38, 34, 28, 27], [45, 45, 45, 45, 45, 45], [20, 50, 30, 44, 25, 41]])
+@pytest.mark.parametrize("buff,align", [(100, True), (0, False), (200, True)])
+def test_cluster_vs_oracle(K, O, thrs, buff, align):
+    rvs, wss, cons, inv = K.cluster_ref_API(TF, 6)
+    rvs, wss, cons = K.eliminate_null_params(rvs, wss, cons, inv)
+    for dense in (False, True):
+        res = []
+        out = K.Omn_KmerGMA(genome_path=GENOME, refVecs=rvs, windowsizes=wss, consensus_seqs=cons, resultVec=res,
+                            thr_vec=thrs, buff=buff, align_hits=align, dense=dense)
+        oh, _, _ = O.Omn_KmerGMA(GENOME, [np.asarray(v) for v in rvs], wss, cons, thr_vec=thrs, buff=buff, align_hits=align)
+        assert_hits_equal(K, out, oh, cluster=True)
+        assert descs(res) == [h.description() for h in oh]
+
+
+def test_cluster_dists_vs_oracle(K, O):
+    rvs, wss, cons, inv = K.cluster_ref_API(TF, 6)
+    rvs, wss, cons = K.eliminate_null_params(rvs, wss, cons, inv)
+    dvv = [[] for _ in wss]
+    K.Omn_KmerGMA(genome_path=MINI_GENOME, refVecs=rvs, windowsizes=wss, consensus_seqs=cons, resultVec=[],
+                  align_hits=False, do_return_dists=True, dist_vec_vec=dvv)
+    _, _, od = O.Omn_KmerGMA(MINI_GENOME, [np.asarray(v) for v in rvs], wss, cons, align_hits=False, do_return_dists=True)
+    for q in range(len(wss)):
+        d = np.asarray(dvv[q])
+        assert d.shape == od[q].shape
+        assert np.max(np.abs(d - od[q]) / np.maximum(np.abs(od[q]), 1e-300)) <= REL
+
+
+# ------------------------------------------------------------------ synthetic genomes with adversarial placements
+def _mutate(rng, s, sub, indel):
+    b = list(s)
+    for i in range(len(b)):
+        if rng.random() < sub:
+            b[i] = "ACGT"[int(rng.integers(0, 4))]
+    if indel:
+        for _ in range(int(rng.integers(1, 4))):
+            p = int(rng.integers(1, len(b) - 1))
+            if rng.random() < 0.5:
+                del b[p:p + int(rng.integers(1, 7))]
+            else:
+                b[p:p] = list("ACGT"[int(rng.integers(0, 4))] * int(rng.integers(1, 7)))
+    return "".join(b)
+
+
+def _synthetic_records(O, seed=3):
+    rng = np.random.default_rng(seed)
+    refs = O.Fasta(TF)
+    rseq = [refs.seq(i) for i in range(len(refs))]
+
+    def rnd(n):
+        return "".join(np.asarray(list("ACGT"))[rng.integers(0, 4, size=n)])
+
+    recs = []
+    # record 0: homologue at position 1 (first-window quirk), pair < ws apart, homologue flush with the end
+    body = rseq[0] + rnd(3000) + _mutate(rng, rseq[5], 0.05, False) + rnd(120) + _mutate(rng, rseq[9], 0.02, False) + rnd(5000)
+    body += "A" * 700 + rnd(100) + "CA" * 400 + rnd(2000) + "N" * 500 + rnd(1500) + _mutate(rng, rseq[20], 0.1, True)
+    recs.append(("syn0 first record", body))
+    recs.append(("short1", rnd(100)))                       # shorter than the window: skipped, GenomePos not advanced
+    recs.append(("exact2", rnd(289)))                       # exactly the window: no loop steps
+    # record 3: long, homologues planted at many offsets so that some straddle segment / block / shard boundaries
+    parts = []
+    for i in range(60):
+        parts.append(rnd(int(rng.integers(200, 9000))))
+        parts.append(_mutate(rng, rseq[int(rng.integers(0, len(rseq)))], [0, 0.02, 0.05, 0.1, 0.15, 0.2][i % 6], i % 4 == 0))
+        if i % 13 == 0:
+            parts.append("N" * int(rng.integers(1, 400)))
+    recs.append(("syn3 long", "".join(parts) + rnd(777)))
+    recs.append(("lower4", (rnd(1000) + rseq[33] + rnd(1000)).lower()))
+    recs.append(("nn5", "N" * 1200))
+    recs.append(("tail6", rnd(290) + rseq[40][:288]))
+    return recs
+
+
+def _write_fasta(path, recs, width=70):
+    with open(path, "w") as fh:
+        for d, s in recs:
+            fh.write(">" + d + "\n")
+            for i in range(0, len(s), width):
+                fh.write(s[i:i + width] + "\n")
+
+
+@pytest.fixture(scope="module")
+def synth(tmp_path_factory, O):
+    recs = _synthetic_records(O)
+    p = tmp_path_factory.mktemp("syn") / "syn.fasta"
+    _write_fasta(p, recs)
+    return str(p), recs
+
+
+@pytest.mark.parametrize("thr", [12, 30, 42])
+@pytest.mark.parametrize("align", [False, True])
+def test_synthetic_single_vs_oracle(K, O, prof, synth, thr, align):
+    path, recs = synth
+    RV, ws, cons = prof
+    for dense in (False, True):
+        res = []
+        out = K.ac_gma_testing(genome_path=path, refVec=RV, consensus_refseq=cons, windowsize=ws, thr=thr,
+                               do_align=align, resultVec=res, dense=dense)
+        oh, _, _ = O.ac_gma_testing(path, np.asarray(RV), cons, windowsize=ws, thr=thr, do_align=align)
+        assert len(oh) >= 10
+        assert_hits_equal(K, out, oh)
+        assert descs(res) == [h.description() for h in oh]
+        assert [r.sequence for r in res] == [h.seq for h in oh]
+
+
+def test_synthetic_cluster_vs_oracle(K, O, synth):
+    path, recs = synth
+    rvs, wss, cons, inv = K.cluster_ref_API(TF, 6)
+    rvs, wss, cons = K.eliminate_null_params(rvs, wss, cons, inv)
+    for dense in (False, True):
+        res = []
+        out = K.Omn_KmerGMA(genome_path=path, refVecs=rvs, windowsizes=wss, consensus_seqs=cons, resultVec=res,
+                            thr_vec=[35, 31, 38, 34, 27, 27], buff=100, dense=dense)
+        oh, _, _ = O.Omn_KmerGMA(path, [np.asarray(v) for v in rvs], wss, cons, thr_vec=[35, 31, 38, 34, 27, 27], buff=100)
+        assert len(oh) >= 5
+        assert_hits_equal(K, out, oh, cluster=True)
+        assert descs(res) == [h.description() for h in oh]
+
+
+def test_synthetic_dists_vs_oracle(K, O, prof, synth):
+    path, recs = synth
+    RV, ws, cons = prof
+    dv = []
+    K.ac_gma_testing(genome_path=path, refVec=RV, consensus_refseq=cons, windowsize=ws, thr=30, do_align=False,
+                     do_return_dists=True, resultVec=[], dist_vec=dv)
+    _, _, od = O.ac_gma_testing(path, np.asarray(RV), cons, windowsize=ws, thr=30, do_align=False, do_return_dists=True)
+    d = np.asarray(dv)
+    assert d.shape == od.shape
+    assert np.max(np.abs(d - od) / np.maximum(np.abs(od), 1e-300)) <= REL
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_sharded_runs_replay_equals_whole(K, prof, synth, shards):
+    """multi-GPU form on one device: per-shard run lists, concatenated in arbitrary order, replayed once"""
+    path, recs = synth
+    RV, ws, cons = prof
+    g = K.Genome.from_fasta(path)
+    L = K.L
+    for dense in (0, L.F_DENSE):
+        whole = K.scan_raw(g, [RV], [ws], [cons], [30], 6, L.MODE_SINGLE, 50, L.F_ALIGN | dense, -69, -1)
+        runs, firsts = [], None
+        for s in reversed(range(shards)):
+            part = K.scan_raw(g, [RV], [ws], [cons], [30], 6, L.MODE_SINGLE, 50, dense, -69, -1, runs_only=True, shard=(s, shards))
+            runs.append(part.runs)
+            firsts = part.first_D if firsts is None else np.maximum(firsts, part.first_D)
+        rep = K.replay_raw(g, [RV], [ws], [cons], [30], 6, L.MODE_SINGLE, 50, L.F_ALIGN, -69, -1, np.concatenate(runs), firsts)
+        assert [(h.record, h.first, h.last, h.D, h.genome_pos) for h in rep.hits] == \
+               [(h.record, h.first, h.last, h.D, h.genome_pos) for h in whole.hits]
+        assert len(whole.hits) >= 10
+
+
+def test_scan_rejects_iupac(K, prof):
+    """Consts.jl:22-28: symbols outside A,C,G,T,N raise KeyError in the reference scan"""
+    RV, ws, cons = prof
+    g = K.Genome.from_records([("amb", "ACGT" * 100 + "R" + "ACGT" * 100)])
+    with pytest.raises(K.KmerGMAError) as e:
+        K.ac_gma_testing(genome_path=g, refVec=RV, consensus_refseq=cons, windowsize=ws, thr=30, do_align=False, resultVec=[])
+    assert e.value.code == K.L.E_SYMBOL
+
+
+# ------------------------------------------------------------------ ExactMatch.jl
+def test_exact_match_goldens(K):
+    """test-KmerGMA.jl:299-334"""
+    assert K.exactMatch("GAG", "CCCCCCCGAGCTTTT") == [(8, 10)]
+    assert K.exactMatch("GAG", "CGAGCCCGAGCTTTT") == [(2, 4), (8, 10)]
+    assert K.exactMatch("GAG", "CGAGAGAGAAGGCCGAGCTTTT") == [(2, 4), (4, 6), (6, 8), (15, 17)]
+    assert K.exactMatch("GAG", "CGAGAGAGAAGGCCGAGCTTTT", overlap=False) == [(2, 4), (6, 8), (15, 17)]
+    assert K.exactMatch("GAG", "CCCCCCTTT") is None
+    refs = K.Genome.from_fasta(TF)
+    first = refs.seq(0)
+    assert K.exactMatch(first[41:69], TF) == {"AM773729|IGHV1-1*01|Vicugna": [(42, 69)]}
+    assert K.exactMatch(K.FastaRecord(refs.description(0), first), TF) == {"AM773729|IGHV1-1*01|Vicugna": [(1, 296)]}
+    assert K.exactMatch("AAAAAAAAA", TF) == "no match"
+    assert K.exactMatch("AAATT", TF) == {"AM773729|IGHV1-1*01|Vicugna": [(174, 178)], "AM939700|IGHV1S5*01|Vicugna": [(174, 178)]}
+
+
+def test_exact_match_vs_oracle(K, O, synth):
+    path, recs = synth
+    f = O.Fasta(path)
+    g = K.Genome.from_fasta(path)
+    s3 = f.seq(3)
+    queries = ["A", "AC", "CACACA", "N", "NNNN", "AAAAAAAAAAAAAAAAAAAAAAAA", s3[1000:1300], s3[5:22], s3[-300:], s3[:33],
+               "N" * 17 + s3[s3.find("N") + 400:][:5] if "N" in s3 else "NNNNNN", f.seq(0)[:289], "ACGTN"]
+    for q in queries:
+        for overlap in (True, False):
+            assert K.exactMatch(q, g, overlap=overlap) == O.exactMatch(q, f, overlap=overlap), (q[:20], overlap)
