@@ -176,12 +176,15 @@ def cpu_baseline(seconds=12.0, chunk=100_000_000):
     lens = contig_lengths(1.0)
     offs = record_offsets(lens)
     plants = plant_list(lens)
-    spent, bases, start, hits = 0.0, 0, 0, 0
-    while spent < seconds and start + chunk <= lens[0]:
-        dt, nh = cpu_chunk(O, RV, lens, offs, plants, 0, start, chunk)
-        spent += dt; bases += chunk; start += chunk; hits += nh
+    spent, bases, hits, rec, start = 0.0, 0, 0, 0, 0
+    while spent < seconds and rec < len(lens):
+        n = min(chunk, lens[rec] - start)
+        dt, nh = cpu_chunk(O, RV, lens, offs, plants, rec, start, n)
+        spent += dt; bases += n; hits += nh; start += n
+        if start >= lens[rec]:
+            rec, start = rec + 1, 0
     return {"value": bases / spent / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "first %d Mb of contig 1 of the same synthetic genome (N runs + planted copies included), "
+            "sample": "first %d Mb of the same synthetic genome (N runs + planted copies included), "
                       "oracle ac_gma hot loop without extension, %d hits, %.1f s" % (bases // 1_000_000, hits, spent)}
 
 

@@ -403,8 +403,9 @@ static bool build_filter_table(const ScanPlan &pl, std::vector<uint16_t> &tab8, 
     if (M > 32 || M < 1) return false;
     std::vector<uint32_t> W(nb, 0);
     for (const ProfTab &t : pl.tabs) {
-        // candidate  <=>  2N * A > R,  R = N^2 nk + sumS2 - T
-        __int128 R = (__int128)t.N2 * t.nk + t.sumS2 - t.T;
+        // candidate  <=>  2N * A > R,  R = N^2 nk + sumS2 - Thi.  Thi (>= T) is the upper edge of the 1e-9 band around
+        // thr, so that every window the reference's Float64 accumulator could still see below thr is evaluated and reported.
+        __int128 R = (__int128)t.N2 * t.nk + t.sumS2 - t.Thi;
         if (R <= 0) return false;
         for (size_t i = 0; i < nb; i++) {
             if (!t.S_rev[i]) continue;

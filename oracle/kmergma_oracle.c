@@ -456,6 +456,36 @@ typedef struct {
     int64_t cmi;         /* CMI used for the hit (diagnostics) */
 } orc_hit;
 
+/* ------------------------------------------------------------------ */
+/* EXACT-ARITHMETIC MODE (test switch).  The reference accumulates the distance in Float64 over the whole
+ * record, so `d < thr` at an exact tie d == thr, and the choice between two windows attaining the same run
+ * minimum, depend on its rounding history (and on Distances.sqeuclidean's unpinned summation order).  With
+ * RV = S/N the same state machine can be run without any rounding: D = sum (N c_i - S_i)^2 = d * 2kN^2 is an
+ * integer < 2^53, so holding D in a double and sliding it with integer increments is exact.  When enabled
+ * (orc_set_exact), orc_ac_gma / orc_omn_gma run the identical control flow on D and T = ceil(thr * 2kN^2)
+ * and report dist = D / (2kN^2).  Disabled (the default), they are the faithful Float64 restatement. */
+static int g_exact_n = 0;
+static int32_t g_exact_N[64];
+void orc_set_exact(int n, const int32_t *N)
+{
+    g_exact_n = (n > 64) ? 64 : (n < 0 ? 0 : n);
+    for (int i = 0; i < g_exact_n; i++) g_exact_N[i] = N[i];
+}
+/* exact ceil(x * m), x >= 0 a double, m > 0 */
+static int64_t ceil_times(double x, int64_t m)
+{
+    if (!(x > 0)) return 0;
+    int e; double f = frexp(x, &e);
+    int64_t mant = (int64_t)ldexp(f, 53); e -= 53;          /* x = mant * 2^e exactly */
+    __int128 p = (__int128)mant * (__int128)m;
+    if (e >= 0) return (int64_t)(p << e);
+    int sft = -e;
+    if (sft > 120) return 1;
+    __int128 q = p >> sft;
+    if ((q << sft) != p) q += 1;
+    return (int64_t)q;
+}
+
 /* src/GenomeMiner.jl:4-109 ac_gma_testing!  (also MultiThread/GenomeMiner.jl:8-98
  * record_KmerGMA! — same loop for one record; CMI=i_left+1 folded at :73).
  * dist_out (optional): L-ws values per scanned record, first window excluded (:79). */
@@ -473,6 +503,14 @@ int orc_ac_gma(const orc_fasta *g, const double *RV, const char *cons, int cons_
     int64_t *c = (int64_t *)malloc(nb * sizeof(int64_t));
     double *cf = (double *)malloc(nb * sizeof(double));
     int64_t genome_pos = 0, nh = 0, nd = 0; int rc = ORC_OK;
+    const int exact = g_exact_n > 0;                         /* test switch, see orc_set_exact */
+    double EN = 0, Eden = 1, thr_eff = thr, *ES = NULL;
+    if (exact) {
+        EN = (double)g_exact_N[0]; Eden = 2.0 * (double)k * EN * EN;
+        thr_eff = (double)ceil_times(thr, (int64_t)Eden);
+        ES = (double *)malloc(nb * sizeof(double));
+        for (size_t i = 0; i < nb; i++) ES[i] = (double)llround(RV[i] * EN);
+    }
     for (int r = 0; r < g->n && rc == ORC_OK; r++) {
         if (only_record >= 0 && r != only_record) continue;
         const char *s = g->seq[r]; int64_t L = g->len[r];
@@ -489,6 +527,7 @@ int orc_ac_gma(const orc_fasta *g, const double *RV, const char *cons, int cons_
         }
         for (size_t i = 0; i < nb; i++) cf[i] = (double)c[i];
         double d = SF0 * sqeuclidean(RV, cf, nb);            /* :46-47 */
+        if (exact) { d = 0; for (size_t i = 0; i < nb; i++) { double x = EN * cf[i] - ES[i]; d += x * x; } }
         uint64_t lk = 0, rk = 0;
         for (int64_t i = 0; i < k - 1; i++) lk = (lk << 2) | (uint64_t)nt_bits(s[i]);           /* :49-51 */
         for (int64_t i = ws - k + 1; i < ws; i++) rk = (rk << 2) | (uint64_t)nt_bits(s[i]);     /* :53-55 */
@@ -501,13 +540,13 @@ int orc_ac_gma(const orc_fasta *g, const double *RV, const char *cons, int cons_
             rk = ((rk << 2) & mask) | (uint64_t)br;
             if (lk != rk) {                                  /* :69-77, left-to-right Float64 */
                 double x = (double)(1 + c[rk]);
-                x = x + RV[lk]; x = x - RV[rk]; x = x - (double)c[lk];
-                d += SF * x;
+                if (exact) d += 2.0 * EN * (EN * (x - (double)c[lk]) + ES[lk] - ES[rk]);
+                else { x = x + RV[lk]; x = x - RV[rk]; x = x - (double)c[lk]; d += SF * x; }
                 c[lk] -= 1; c[rk] += 1;
             }
-            if (dist_out) { if (nd >= dist_cap) { rc = ORC_E_CAP; break; } dist_out[nd] = d; }
+            if (dist_out) { if (nd >= dist_cap) { rc = ORC_E_CAP; break; } dist_out[nd] = exact ? d / Eden : d; }
             nd++;
-            if (d < thr) {                                   /* :82-87 */
+            if (d < thr_eff) {                               /* :82-87 */
                 if (d < cur) { cur = d; CMI = il; stop = 0; }
             } else if (!stop) {                              /* :90-104 */
                 stop = 1; CMI += 1;
@@ -521,7 +560,7 @@ int orc_ac_gma(const orc_fasta *g, const double *RV, const char *cons, int cons_
                     }
                     if (nh >= hit_cap) { rc = ORC_E_CAP; break; }
                     orc_hit *h = &hits[nh++];
-                    h->record = r; h->kfv = 0; h->dist = cur; h->first = a; h->last = b;
+                    h->record = r; h->kfv = 0; h->dist = exact ? cur / Eden : cur; h->first = a; h->last = b;
                     h->genome_pos = genome_pos; h->cmi = CMI;
                     cur = d;
                 }
@@ -530,7 +569,7 @@ int orc_ac_gma(const orc_fasta *g, const double *RV, const char *cons, int cons_
         genome_pos += L;                                     /* :106 */
     }
     (void)cons_len;
-    free(c); free(cf);
+    free(c); free(cf); free(ES);
     *nhits = nh; if (ndist) *ndist = nd;
     return rc;
 }
@@ -556,6 +595,17 @@ int orc_omn_gma(const orc_fasta *g, const double *RVs, const int64_t *wss, int C
     uint64_t *rk = (uint64_t *)calloc((size_t)C, sizeof(uint64_t));
     int64_t maxws = 0, nh = 0, genome_pos = 0; int rc = ORC_OK;
     for (int q = 0; q < C; q++) { curmin[q] = 10000.0; CMIs[q] = 1; stops[q] = 1; if (wss[q] > maxws) maxws = wss[q]; if (ndist) ndist[q] = 0; }
+    const int exact = g_exact_n >= C;                         /* test switch, see orc_set_exact */
+    double *ES = NULL, *EN = NULL, *Eden = NULL, *thr_eff = (double *)malloc((size_t)C * sizeof(double));
+    for (int q = 0; q < C; q++) thr_eff[q] = thr[q];
+    if (exact) {
+        ES = (double *)malloc(nb * (size_t)C * sizeof(double)); EN = (double *)malloc((size_t)C * sizeof(double)); Eden = (double *)malloc((size_t)C * sizeof(double));
+        for (int q = 0; q < C; q++) {
+            EN[q] = (double)g_exact_N[q]; Eden[q] = 2.0 * (double)k * EN[q] * EN[q];
+            thr_eff[q] = (double)ceil_times(thr[q], (int64_t)Eden[q]);
+            for (size_t i = 0; i < nb; i++) ES[(size_t)q * nb + i] = (double)llround(RVs[(size_t)q * nb + i] * EN[q]);
+        }
+    }
     for (int r = 0; r < g->n && rc == ORC_OK; r++) {
         const char *s = g->seq[r]; int64_t L = g->len[r];
         int64_t prev_a = 0, prev_b = 0;                       /* :59 prev_hit_range = 0:0 */
@@ -565,6 +615,7 @@ int orc_omn_gma(const orc_fasta *g, const double *RVs, const int64_t *wss, int C
             memset(c, 0, nb * sizeof(double));
             rc = orc_kmer_count_add(s, wss[q], k, c); if (rc) break;
             kd[q] = curmin[q] = SF * 0.5 * sqeuclidean(RVs + (size_t)q * nb, c, nb);
+            if (exact) { double a = 0; for (size_t i = 0; i < nb; i++) { double x = EN[q] * c[i] - ES[(size_t)q * nb + i]; a += x * x; } kd[q] = curmin[q] = a; }
             CMIs[q] = 1; stops[q] = 1; rk[q] = 0;
             for (int64_t i = wss[q] - k + 1; i < wss[q]; i++) rk[q] = (rk[q] << 2) | (uint64_t)nt_bits(s[i]);
         }
@@ -583,14 +634,14 @@ int orc_omn_gma(const orc_fasta *g, const double *RVs, const int64_t *wss, int C
                 uint64_t rr = rk[q];
                 if (lk != rr) {                                /* :101-108 */
                     double x = 1.0 + c[rr];
-                    x = x + RV[lk]; x = x - RV[rr]; x = x - c[lk];
-                    kd[q] += SF * x;
+                    if (exact) kd[q] += 2.0 * EN[q] * (EN[q] * (x - c[lk]) + ES[(size_t)q * nb + lk] - ES[(size_t)q * nb + rr]);
+                    else { x = x + RV[lk]; x = x - RV[rr]; x = x - c[lk]; kd[q] += SF * x; }
                     c[lk] -= 1.0; c[rr] += 1.0;
                 }
                 double d = kd[q];
-                if (dist_out) { if (ndist[q] >= dist_cap) { rc = ORC_E_CAP; break; } dist_out[(size_t)q * (size_t)dist_cap + (size_t)ndist[q]] = d; }
+                if (dist_out) { if (ndist[q] >= dist_cap) { rc = ORC_E_CAP; break; } dist_out[(size_t)q * (size_t)dist_cap + (size_t)ndist[q]] = exact ? d / Eden[q] : d; }
                 if (ndist) ndist[q]++;
-                if (d < thr[q]) {                              /* :114-119 */
+                if (d < thr_eff[q]) {                          /* :114-119 */
                     if (d < curmin[q]) { curmin[q] = d; CMIs[q] = i; stops[q] = 0; }
                 } else if (!stops[q]) {                        /* :122-156 */
                     stops[q] = 1;
@@ -607,7 +658,7 @@ int orc_omn_gma(const orc_fasta *g, const double *RVs, const int64_t *wss, int C
                         if (b < prev_a || a > prev_b) {        /* :139 */
                             if (nh >= hit_cap) { rc = ORC_E_CAP; break; }
                             orc_hit *h = &hits[nh++];
-                            h->record = r; h->kfv = q + 1; h->dist = curmin[q]; h->first = a; h->last = b;
+                            h->record = r; h->kfv = q + 1; h->dist = exact ? curmin[q] / Eden[q] : curmin[q]; h->first = a; h->last = b;
                             h->genome_pos = genome_pos; h->cmi = CMI;
                             prev_a = a; prev_b = b;            /* :152 */
                             curmin[q] = d;                     /* :153 */
@@ -618,7 +669,7 @@ int orc_omn_gma(const orc_fasta *g, const double *RVs, const int64_t *wss, int C
         }
         genome_pos += L;                                       /* :159 — every record */
     }
-    free(cnt); free(kd); free(curmin); free(CMIs); free(stops); free(rk);
+    free(cnt); free(kd); free(curmin); free(CMIs); free(stops); free(rk); free(ES); free(EN); free(Eden); free(thr_eff);
     *nhits = nh;
     return rc;
 }

@@ -88,6 +88,8 @@ def lib():
         L.orc_ac_gma_seq.restype = C.c_int64
         L.orc_ac_gma_seq.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_double,
                                      C.c_int64, C.c_void_p, C.c_int64]
+        L.orc_set_exact.restype = None
+        L.orc_set_exact.argtypes = [C.c_int, C.c_void_p]
         L.orc_synth.restype = None
         L.orc_synth.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_void_p]
     return _lib
@@ -335,6 +337,24 @@ def _hits(f: Fasta, arr, n) -> List[Hit]:
         out.append(Hit(h.record, f.identifier(h.record), h.kfv, h.dist, h.first, h.last,
                        h.genome_pos, h.cmi, s[h.first - 1:h.last]))
     return out
+
+
+class exact_arithmetic:
+    """with exact_arithmetic(N) / exact_arithmetic([n_1..n_C]): run ac_gma_testing / Omn_KmerGMA with the
+    rounding-free integer distance D = d*2kN^2 (see orc_set_exact in kmergma_oracle.c) instead of the reference's
+    accumulated Float64.  Used to check the device at exact ties (d == thr, equal run minima), where the
+    reference's own outcome depends on its rounding history."""
+
+    def __init__(self, N):
+        self.N = np.atleast_1d(np.asarray(N, dtype=np.int32))
+
+    def __enter__(self):
+        lib().orc_set_exact(int(self.N.size), self.N.ctypes.data)
+        return self
+
+    def __exit__(self, *a):
+        lib().orc_set_exact(0, None)
+        return False
 
 
 # ---------------------------------------------------------------- GenomeMiner.jl

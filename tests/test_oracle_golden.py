@@ -180,3 +180,23 @@ def test_exactMatch_reader():                 # :308-334
     assert O.exactMatch("AAAAAAAAA", f) == "no match"
     assert O.exactMatch("AAATT", f) == {"AM773729|IGHV1-1*01|Vicugna": [(174, 178)],
                                          "AM939700|IGHV1S5*01|Vicugna": [(174, 178)]}
+
+
+def test_exact_arithmetic_mode_agrees_with_faithful_on_goldens():
+    """O.exact_arithmetic runs the same state machine on the rounding-free integer distance; away from exact ties it
+    must give the faithful Float64 restatement's hits (test-KmerGMA.jl:174-176,189-192,223-225 inputs)."""
+    from oracle import oracle as O
+    RV, ws, cons = O.gen_ref_ws_cons(TF, 6)
+    for thr, align in ((30, False), (30, True), (10, False)):
+        a = O.ac_gma_testing(GENOME, RV, cons, windowsize=ws, thr=thr, do_align=align)[0]
+        with O.exact_arithmetic(84):
+            b = O.ac_gma_testing(GENOME, RV, cons, windowsize=ws, thr=thr, do_align=align)[0]
+        assert [h.description() for h in a] == [h.description() for h in b]
+        assert all(abs(x.dist - y.dist) <= 1e-9 * x.dist for x, y in zip(a, b))
+    cl = O.cluster_ref_API(TF, 6, include_avg=False)
+    rvs, wss, cs = cl[0], cl[1], cl[2]
+    a = O.Omn_KmerGMA(MINI_GENOME, rvs, wss, cs, thr_vec=[37, 33, 38, 34, 28, 27], buff=200)[0]
+    with O.exact_arithmetic([14, 52, 1, 5, 12]):
+        b = O.Omn_KmerGMA(MINI_GENOME, rvs, wss, cs, thr_vec=[37, 33, 38, 34, 28, 27], buff=200)[0]
+    assert [h.description() for h in a] == [h.description() for h in b]
+    assert a[0].description() == "AM773548.1 | Dist = 20.17 | KFV = 3 | MatchPos = 6852:7139 | GenomePos = 0 | Len = 288"
