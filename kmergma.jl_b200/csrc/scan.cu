@@ -345,7 +345,7 @@ int build_proftab(kgma_ctx *ctx, const kgma_profile &p, ProfTab &t)
 
 int dev_genome_prepare(kgma_ctx *ctx, kgma_genome *g, bool need_mask)
 {
-    int64_t need = g->G + TAIL_PAD;
+    int64_t need = (g->G + TAIL_PAD + 4095) / 4096 * 4096;   // same rounding as the host planes (genome_reserve / kgma_genome_synth)
     if (ctx->dg_uid != g->uid || ctx->d_cap_bases < need) {
         if (ctx->d_seq2) cudaFree(ctx->d_seq2);
         if (ctx->d_mask) cudaFree(ctx->d_mask);
