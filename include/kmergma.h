@@ -126,6 +126,11 @@ typedef struct {
     int64_t n_runs, n_align;
     int64_t launches;             /* kernels launched by the last call */
     int64_t h2d_bytes, d2h_bytes;
+    /* host wall-clock breakdown of the last call (milliseconds) */
+    double wall_ms;               /* whole call */
+    double host_setup_ms;         /* plan, tables, scratch, small uploads (until the genome stream starts) */
+    double host_cand_ms;          /* candidate list D2H + sort + segment building */
+    double host_replay_ms;        /* run merge + replay of the reference state machine (without the extension kernel) */
 } kgma_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */

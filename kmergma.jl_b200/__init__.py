@@ -360,8 +360,8 @@ def julia_float_str(x: float) -> str:
     return repr(float(x))
 
 
-def _header(ident: str, h: L.Hit, cluster: bool, with_genome_pos: bool = True) -> str:
-    d = julia_float_str(julia_round2(h.dist))
+def _header(ident: str, h, cluster: bool, with_genome_pos: bool = True) -> str:
+    d = julia_float_str(julia_round2(float(h.dist)))
     rng = f"{h.first}:{h.last}"
     ln = h.last - h.first + 1
     if cluster:            # src/OmnGenomeMiner.jl:141-149
@@ -370,33 +370,49 @@ def _header(ident: str, h: L.Hit, cluster: bool, with_genome_pos: bool = True) -
     return f"{ident} | dist = {d} | MatchPos = {rng}{gp} | Len = {ln}"      # src/Alignment.jl:71-78
 
 
+HIT_DT = np.dtype([("record", "<i4"), ("profile", "<i4"), ("cmi", "<i8"), ("first", "<i8"), ("last", "<i8"),
+                   ("genome_pos", "<i8"), ("D", "<i8"), ("dist", "<f8"), ("align_score", "<i8"), ("flags", "<u4"),
+                   ("cigar_off", "<u4"), ("cigar_len", "<u4"), ("reserved", "<u4")])
+RUN_DT = np.dtype([("record", "<i4"), ("profile", "<i4"), ("t_first", "<i8"), ("t_last", "<i8"), ("t_argmin", "<i8"),
+                   ("D_min", "<i8"), ("flags", "<u4"), ("reserved", "<u4")])
+assert HIT_DT.itemsize == C.sizeof(L.Hit) and RUN_DT.itemsize == C.sizeof(L.Run)
+
+
 class ScanOutput:
-    """Raw result of one kgma_scan call (hits as ctypes structs + optional dists / cigars)."""
+    """Raw result of one kgma_scan call: `hits` is a numpy record array over kgma_hit (h.record, h.first, ...),
+    `runs` the raw bytes of the kgma_run list (view with RUN_DT), plus optional dists / cigars."""
 
     def __init__(self, ctx: Context, res_handle):
         lib = ctx._lib
         n = lib.kgma_result_n_hits(res_handle)
         hp = lib.kgma_result_hits(res_handle)
-        self.hits: List[L.Hit] = []
-        for i in range(n):
-            h = L.Hit()
-            C.memmove(C.byref(h), C.byref(hp[i]), C.sizeof(L.Hit))
-            self.hits.append(h)
+        if n:
+            raw = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(n * HIT_DT.itemsize,)).copy()
+            self.hits = raw.view(HIT_DT).view(np.recarray)
+        else:
+            self.hits = np.zeros(0, dtype=HIT_DT).view(np.recarray)
         nr = lib.kgma_result_n_runs(res_handle)
         rp = lib.kgma_result_runs(res_handle)
         self.runs = np.ctypeslib.as_array(C.cast(rp, C.POINTER(C.c_uint8)), shape=(nr * C.sizeof(L.Run),)).copy() if nr else np.zeros(0, np.uint8)
         self.n_runs = nr
         self.first_D = None
         self.dists: List[np.ndarray] = []
-        self.cigars: List[Optional[AlignResult]] = []
-        ops, cnt = lib.kgma_result_cigar_ops(res_handle), lib.kgma_result_cigar_counts(res_handle)
-        for h in self.hits:
-            if h.cigar_len and ops:
-                s = "".join(f"{cnt[h.cigar_off + t]}{ops[h.cigar_off + t].decode()}" for t in range(h.cigar_len))
-                self.cigars.append(AlignResult(s, h.align_score))
-            else:
-                self.cigars.append(None)
+        self._cigars = None
         self._lib, self._res = lib, res_handle
+
+    @property
+    def cigars(self) -> List[Optional[AlignResult]]:
+        if self._cigars is None:
+            ops, cnt = self._lib.kgma_result_cigar_ops(self._res), self._lib.kgma_result_cigar_counts(self._res)
+            out = []
+            for h in self.hits:
+                if h.cigar_len and ops:
+                    s = "".join(f"{cnt[int(h.cigar_off) + t]}{ops[int(h.cigar_off) + t].decode()}" for t in range(int(h.cigar_len)))
+                    out.append(AlignResult(s, int(h.align_score)))
+                else:
+                    out.append(None)
+            self._cigars = out
+        return self._cigars
 
     def load_dists(self, n_profiles: int):
         for q in range(n_profiles):
@@ -467,12 +483,14 @@ def replay_raw(genome: Genome, refVecs, windowsizes, consensus_seqs, thrs, k: in
 
 
 def _emit(genome: Genome, out: ScanOutput, cluster: bool, resultVec, hit_loci_vec, align_vec, with_genome_pos=True):
-    for h, cg in zip(out.hits, out.cigars):
-        ident = genome.identifier(h.record)
-        seq = genome.seq(h.record, h.first, h.last) if h.last >= h.first else ""
+    cigars = out.cigars if align_vec is not None else [None] * len(out.hits)
+    for h, cg in zip(out.hits, cigars):
+        rec, first, last = int(h.record), int(h.first), int(h.last)
+        ident = genome.identifier(rec)
+        seq = genome.seq(rec, first, last) if last >= first else ""
         resultVec.append(FastaRecord(_header(ident, h, cluster, with_genome_pos), seq))
         if hit_loci_vec is not None:
-            hit_loci_vec.append(h.first + h.genome_pos)
+            hit_loci_vec.append(first + int(h.genome_pos))
         if align_vec is not None and cg is not None:
             align_vec.append(cg)
 
@@ -532,8 +550,7 @@ def Omn_KmerGMA(*, genome_path, refVecs, windowsizes, consensus_seqs, resultVec:
     out = scan_raw(g, list(refVecs)[:Cn], windowsizes, list(consensus_seqs)[:Cn], list(thr_vec)[:Cn], k,
                    L.MODE_CLUSTER, buff, flags, gap_open_score, gap_extend_score, ctx=ctx)
     if genome_pos:
-        for h in out.hits:
-            h.genome_pos += genome_pos
+        out.hits.genome_pos += genome_pos
     _emit(g, out, True, resultVec, hit_loci_vec if get_hit_loci else None, align_vec if get_aligns else None)
     if do_return_dists and dist_vec_vec is not None:
         for q in range(min(Cn, len(dist_vec_vec))):

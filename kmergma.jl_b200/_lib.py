@@ -46,7 +46,9 @@ class Stats(C.Structure):
                 ("align_ms", C.c_double), ("total_ms", C.c_double),
                 ("bases_scanned", C.c_int64), ("blocks_total", C.c_int64), ("blocks_flagged", C.c_int64),
                 ("exact_windows", C.c_int64), ("n_runs", C.c_int64), ("n_align", C.c_int64),
-                ("launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("wall_ms", C.c_double), ("host_setup_ms", C.c_double), ("host_cand_ms", C.c_double),
+                ("host_replay_ms", C.c_double)]
 
 
 class Match(C.Structure):

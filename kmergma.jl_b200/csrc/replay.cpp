@@ -22,6 +22,9 @@ void merge_runs(std::vector<kgma_run> &runs)
     std::vector<kgma_run> out;
     out.reserve(runs.size());
     for (const kgma_run &r : runs) {
+        // a block evaluated twice (seeded as a record start AND flagged by the prefilter) reports identical entries
+        if (!out.empty() && out.back().profile == r.profile && out.back().record == r.record && out.back().t_first == r.t_first &&
+            ((out.back().flags ^ r.flags) & KGMA_RUN_MARKER) == 0) continue;
         if (!(r.flags & KGMA_RUN_MARKER) && !out.empty()) {
             // find the previous real run (markers never sit between two halves of a split run: they have d >= thr)
             kgma_run &p = out.back();

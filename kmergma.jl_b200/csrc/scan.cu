@@ -13,15 +13,17 @@
 //      shared-memory table indexed by 8-mers (128 KB).  Blocks whose covering sum cannot reach the
 //      threshold contain no window with d < thr; the others are appended to a candidate list with
 //      warp ballot/popc compaction + one atomic per warp.
-//  (2) kgma_exact: the count-table kernel.  One chain per thread, each with its own 4^k x u16
-//      count table in shared memory next to the profile's S table; the distance is updated
-//      incrementally as one k-mer leaves and one enters the window, re-initialised per segment.
-//      It emits run summaries (maximal stretches of D < T) with an atomic append, and optionally
-//      every D (do_return_dists).  It runs on the candidate segments, or on everything in dense mode.
+//  (2) kgma_eval: the count-table kernel.  One warp per span of consecutive windows (a flagged 64-base
+//      block read straight from the device candidate list, or a slice of a record in dense mode), with a
+//      4^k x u16 count table in shared memory next to the profile's S table; the distance is updated
+//      incrementally as one k-mer leaves and one enters the window, re-initialised per span.  Windows are
+//      classified 64 at a time (ballot + warp min) and run summaries (maximal stretches of D < T) are
+//      appended with an atomic; optionally every D is written (do_return_dists).
 #include "kgma_internal.h"
 #include <algorithm>
 #include <cmath>
 #include <climits>
+#include <chrono>
 
 namespace kgma {
 
@@ -118,122 +120,207 @@ __global__ void __launch_bounds__(1024, 1) kgma_prefilter(FilterArgs a)
 }
 
 // =============================================================================================
-// (2) count-table kernel
+// (2) count-table kernel: one warp per span of consecutive windows
 // =============================================================================================
-struct Segment {
-    int64_t gpos;      // global base position of the first window of the segment
-    int64_t dist_off;  // index into the D output for window w0 (step w0), or -1
-    int32_t rec;
-    int32_t w0;        // first window (0-based start in the record) == loop step
-    int32_t n;         // number of windows
-    int32_t last_step; // last loop step of the record (a run reaching it is unterminated)
+// A span is either one flagged 64-base block of the candidate list (written by the prefilter, read here
+// straight from device memory: no host round trip) or, in dense mode, an implicit slice of `span` windows
+// of a record.  The warp keeps a 4^k x u16 k-mer count table in shared memory next to the profile's S
+// table: it is initialised from the first window of the span (all lanes, packed 16-bit atomics), then one
+// k-mer leaves and one enters per step (GenomeMiner.jl:69-77) while Q = sum c^2 and A = sum S[kmer] are
+// updated incrementally; D = N^2 Q - 2N A + sum S^2.  Every 64 windows the warp classifies them in
+// parallel (D < T by ballot, run minima by warp reduction) and appends run summaries with an atomic.
+// The table is returned to zero by clearing the entries of the last window.
+struct RecDev {
+    long long off;          // global base offset of the record
+    long long w_begin, w_end;   // window starts (== loop steps, 0-based) owned by this shard: [w_begin, w_end)
+    long long item_base;    // dense mode: index of the record's first item
+    long long dist_base;    // do_return_dists: index of step 1 of this record in the D output
 };
 
-struct ExactArgs {
+struct ProfDev { long long N2, twoN, sumS2, T, Tlo, Thi; int nk, pad; };
+
+struct EvalArgs {
     const uint32_t *seq;
-    const int32_t  *S;          // [4^k] reversed-index profile sums
-    const Segment  *segs;
-    int       nseg;
-    int      *next_seg;         // dynamic work counter
-    int       k, nk, nch;       // chains (threads) per CTA that own a table
-    int       profile;
-    long long N2, twoN, sumS2, T, Tlo, Thi;
+    const int32_t  *S;              // [C][4^k] reversed-index profile sums
+    const uint32_t *cand;           // candidate mode: flagged block ids (null = dense mode)
+    const uint32_t *cand_count; uint32_t cand_cap;
+    long long n_items;              // dense mode: number of implicit items
+    const RecDev *recs; int nrec;
+    int C, k, span;                 // span: windows per dense item
+    ProfDev prof[MAX_PROFILES];
     kgma_run *runs; uint32_t run_cap; uint32_t *run_count;
-    long long *first_D;         // [n_records] for this profile
-    long long *dists;           // optional dense output of D per step
+    long long *first_D;             // [C][nrec]
+    long long *dists; long long dist_stride;
 };
 
+__device__ __forceinline__ uint32_t kmer_at(const uint32_t *seq, long long gp, uint32_t kmask)
+{
+    const uint32_t *p = seq + (gp >> 4);
+    return __funnelshift_r(__ldg(p), __ldg(p + 1), (int)(gp & 15) * 2) & kmask;
+}
 
-struct BitReader {
-    const uint32_t *p; uint32_t lo, hi; int sh;
-    __device__ __forceinline__ void init(const uint32_t *seq, int64_t pos)
-    { p = seq + (pos >> 4); lo = p[0]; hi = p[1]; sh = (int)(pos & 15) * 2; }
-    __device__ __forceinline__ uint32_t next(uint32_t kmask)
-    {
-        uint32_t v = __funnelshift_r(lo, hi, sh) & kmask;
-        sh += 2;
-        if (sh == 32) { sh = 0; ++p; lo = hi; hi = p[1]; }
-        return v;
-    }
-};
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    return v;
+}
 
-__device__ __forceinline__ void emit_run(const ExactArgs &a, int rec, long long tf, long long tl, long long ta,
+__device__ __forceinline__ void emit_run(const EvalArgs &a, int rec, int q, long long tf, long long tl, long long ta,
                                          long long dmin, uint32_t flags)
 {
     uint32_t i = atomicAdd(a.run_count, 1u);
     if (i < a.run_cap) {
-        kgma_run r; r.record = rec; r.profile = a.profile; r.t_first = tf; r.t_last = tl; r.t_argmin = ta;
+        kgma_run r; r.record = rec; r.profile = q; r.t_first = tf; r.t_last = tl; r.t_argmin = ta;
         r.D_min = dmin; r.flags = flags; r.reserved = 0;
         a.runs[i] = r;
     }
 }
 
-__global__ void __launch_bounds__(256, 1) kgma_exact(ExactArgs a)
+__global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned FULL = 0xFFFFFFFFu;
     const int nb = 1 << (2 * a.k);
-    int32_t *sS = reinterpret_cast<int32_t *>(smem_raw);
-    uint16_t *cnt_all = reinterpret_cast<uint16_t *>(smem_raw + (size_t)nb * 4);
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) sS[i] = a.S[i];
-    {   // zero every chain's table once; chains return their table to zero after each segment
-        uint32_t *z = reinterpret_cast<uint32_t *>(cnt_all);
-        int words = a.nch * nb / 2;
-        for (int i = threadIdx.x; i < words; i += blockDim.x) z[i] = 0;
-    }
-    __syncthreads();
-    if ((int)threadIdx.x >= a.nch) return;
-    uint16_t *cnt = cnt_all + (size_t)threadIdx.x * nb;
     const uint32_t kmask = (uint32_t)nb - 1;
-    const int nk = a.nk;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int32_t *sS = reinterpret_cast<int32_t *>(smem_raw);
+    const size_t per_warp = (size_t)nb * 2 + 64 * 2 * 2 + 64 * 8;
+    unsigned char *wb = smem_raw + (size_t)nb * 4 + (size_t)wid * per_warp;
+    long long *dw = reinterpret_cast<long long *>(wb);                        // [64] D of the current 64 windows
+    uint16_t *tab = reinterpret_cast<uint16_t *>(wb + 64 * 8);                // [4^k] counts
+    uint16_t *lk = tab + nb, *rk = lk + 64;                                  // leaving / entering k-mers of 64 steps
+    for (int i = lane; i < nb / 2; i += 32) reinterpret_cast<uint32_t *>(tab)[i] = 0;
+    if (nb < 2 && lane == 0) tab[0] = 0;
 
-    for (;;) {
-        int si = atomicAdd(a.next_seg, 1);
-        if (si >= a.nseg) break;
-        const Segment sg = a.segs[si];
-        BitReader R, L;
-        R.init(a.seq, sg.gpos);
-        L.init(a.seq, sg.gpos);
-        long long Q = 0, A = 0;
-        bool inrun = false; long long tf = 0, ta = 0, dmin = 0; uint32_t rflags = 0;
-        // unified time loop: step u enters k-mer u (u < n+nk-1) and removes k-mer u-nk (u >= nk);
-        // window (u-nk+1) is complete after the update when nk-1 <= u < n+nk-1.  The tail
-        // (u >= n+nk-1) only removes, which returns the table to all-zero for the next segment.
-        const int total = sg.n + 2 * nk - 1;
-        for (int u = 0; u < total; ++u) {
-            const bool hasR = u < sg.n + nk - 1, hasL = u >= nk;
-            uint32_t r = 0, l = 0;
-            if (hasR) r = R.next(kmask);
-            if (hasL) l = L.next(kmask);
-            if (!(hasR && hasL && l == r)) {            // GenomeMiner.jl:69 `if left_ind != right_ind`
-                int cl = 0, cr = 0;
-                if (hasL) cl = cnt[l];
-                if (hasR) cr = cnt[r];
-                if (hasL) { Q -= 2 * cl - 1; A -= sS[l]; cnt[l] = (uint16_t)(cl - 1); }
-                if (hasR) { Q += 2 * cr + 1; A += sS[r]; cnt[r] = (uint16_t)(cr + 1); }
+    const long long gwarp = (long long)blockIdx.x * nw + wid, nwarps = (long long)gridDim.x * nw;
+    long long nitems = a.n_items;
+    if (a.cand) { uint32_t c = *a.cand_count; nitems = c < a.cand_cap ? c : a.cand_cap; }
+
+    for (int q = 0; q < a.C; q++) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) sS[i] = a.S[(size_t)q * nb + i];
+        __syncthreads();
+        const ProfDev P = a.prof[q];
+        const int nk = P.nk;
+        for (long long item = gwarp; item < nitems; item += nwarps) {
+            // ---- locate the span: record r, first window w0 (== loop step), n windows
+            int r; long long w0, n;
+            if (a.cand) {
+                const long long gp = (long long)a.cand[item] * FBLOCK;
+                int lo = 0, hi = a.nrec;                                      // last record with off <= gp
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (a.recs[mid].off <= gp) lo = mid; else hi = mid; }
+                r = lo;
+                const RecDev R = a.recs[r];
+                const long long b0 = gp - R.off;
+                if (b0 < 0) continue;
+                w0 = b0 > R.w_begin ? b0 : R.w_begin;
+                long long we = b0 + FBLOCK < R.w_end ? b0 + FBLOCK : R.w_end;
+                n = we - w0;
+            } else {
+                int lo = 0, hi = a.nrec;                                      // last record with item_base <= item
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (a.recs[mid].item_base <= item) lo = mid; else hi = mid; }
+                r = lo;
+                const RecDev R = a.recs[r];
+                w0 = R.w_begin + (item - R.item_base) * a.span;
+                n = R.w_end - w0 < a.span ? R.w_end - w0 : a.span;
             }
-            const int wi = u - (nk - 1);                // window index within the segment
-            if (wi >= 0 && wi < sg.n) {
-                const long long D = a.N2 * Q - a.twoN * A + a.sumS2;
-                const long long t = (long long)sg.w0 + wi;      // loop step == 0-based window start
-                if (t == 0) { a.first_D[sg.rec] = D; }
-                else {
-                    if (a.dists && sg.dist_off >= 0) a.dists[sg.dist_off + wi - (sg.w0 == 0 ? 1 : 0)] = D;
-                    const bool near = (D >= a.Tlo) && (D < a.Thi);
-                    if (D < a.T) {                       // GenomeMiner.jl:82 `kmerDist < thr`
-                        if (!inrun) { inrun = true; tf = t; ta = t; dmin = D; rflags = (wi == 0 || (wi == 1 && sg.w0 == 0)) ? KGMA_RUN_OPEN_LEFT : 0; }
-                        else if (D < dmin) { dmin = D; ta = t; rflags &= ~KGMA_HIT_ARGMIN_TIE; }
-                        else if (D == dmin) rflags |= KGMA_HIT_ARGMIN_TIE;
-                        if (near) rflags |= KGMA_HIT_NEAR_THR;
-                    } else {
-                        if (inrun) { emit_run(a, sg.rec, tf, t - 1, ta, dmin, rflags); inrun = false; }
-                        if (near) emit_run(a, sg.rec, t, t, t, D, KGMA_RUN_MARKER | KGMA_HIT_NEAR_THR);
-                    }
-                    if (wi == sg.n - 1 && inrun) {       // segment ends inside a run: host merges with the neighbour
-                        emit_run(a, sg.rec, tf, t, ta, dmin, rflags | KGMA_RUN_OPEN_RIGHT);
-                        inrun = false;
+            if (n <= 0) continue;
+            const long long gpos = a.recs[r].off + w0;
+            const long long dist_base = a.recs[r].dist_base;
+
+            // ---- first window of the span: build the table, Q = sum_p c[kmer_p], A = sum_p S[kmer_p]
+            for (int p = lane; p < nk; p += 32) {
+                const uint32_t km = kmer_at(a.seq, gpos + p, kmask);
+                atomicAdd(reinterpret_cast<uint32_t *>(tab) + (km >> 1), 1u << ((km & 1) * 16));
+            }
+            __syncwarp();
+            long long Q = 0, A = 0;
+            for (int p = lane; p < nk; p += 32) {
+                const uint32_t km = kmer_at(a.seq, gpos + p, kmask);
+                Q += tab[km]; A += sS[km];
+            }
+            Q = warp_sum_ll(Q); A = warp_sum_ll(A);
+
+            for (long long s0 = 0; s0 < n; s0 += 64) {
+                const int m = (int)(n - s0 < 64 ? n - s0 : 64);
+                for (int j = lane; j < m; j += 32) {                          // step j: window s0+j -> s0+j+1
+                    lk[j] = (uint16_t)kmer_at(a.seq, gpos + s0 + j, kmask);
+                    rk[j] = (uint16_t)kmer_at(a.seq, gpos + s0 + j + nk, kmask);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    uint32_t l = lk[0], rr = rk[0];
+                    for (int j = 0; j < m; j++) {
+                        dw[j] = P.N2 * Q - P.twoN * A + P.sumS2;
+                        const uint32_t ln = lk[(j + 1) & 63], rn = rk[(j + 1) & 63];   // software-pipelined k-mer fetch
+                        if (l != rr && s0 + j + 1 < n) {                      // GenomeMiner.jl:69 `if left_ind != right_ind`
+                            const int cl = tab[l], cr = tab[rr];
+                            Q += 2 * (cr - cl) + 2; A += sS[rr] - sS[l];
+                            tab[l] = (uint16_t)(cl - 1); tab[rr] = (uint16_t)(cr + 1);
+                        }
+                        l = ln; rr = rn;
                     }
                 }
+                __syncwarp();
+                // ---- classify the m windows: lanes own windows lane and lane+32
+                unsigned bm[2], nm[2]; long long Dm[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int wi = lane + 32 * h;
+                    const bool valid = wi < m;
+                    const long long t = w0 + s0 + wi;
+                    const long long D = valid ? dw[wi] : 0;
+                    Dm[h] = D;
+                    if (valid && t == 0) a.first_D[(size_t)q * a.nrec + r] = D;      // first window: never compared with thr
+                    const bool inloop = valid && t >= 1;
+                    if (a.dists && inloop) a.dists[(size_t)q * a.dist_stride + dist_base + t - 1] = D;
+                    bm[h] = __ballot_sync(FULL, inloop && D < P.T);             // GenomeMiner.jl:82 `kmerDist < thr`
+                    nm[h] = __ballot_sync(FULL, inloop && D >= P.Tlo && D < P.Thi);
+                }
+                const unsigned long long below = (unsigned long long)bm[0] | ((unsigned long long)bm[1] << 32);
+                const unsigned long long near = (unsigned long long)nm[0] | ((unsigned long long)nm[1] << 32);
+                unsigned long long rem = below;
+                while (rem) {                                                  // maximal stretches of D < T inside these 64 windows
+                    const int b0 = __ffsll((long long)rem) - 1;
+                    const unsigned long long sh = rem >> b0;
+                    const int len = (~sh == 0ull) ? 64 : (__ffsll((long long)~sh) - 1);
+                    const unsigned long long stretch = (len == 64 ? ~0ull : ((1ull << len) - 1)) << b0;
+                    const int b1 = b0 + len - 1;
+                    long long bestD = LLONG_MAX; int bestI = 64;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int wi = lane + 32 * h;
+                        if (wi >= b0 && wi <= b1 && Dm[h] < bestD) { bestD = Dm[h]; bestI = wi; }
+                    }
+#pragma unroll
+                    for (int d = 16; d; d >>= 1) {                             // min D, earliest window on ties
+                        const long long oD = __shfl_xor_sync(FULL, bestD, d); const int oI = __shfl_xor_sync(FULL, bestI, d);
+                        if (oD < bestD || (oD == bestD && oI < bestI)) { bestD = oD; bestI = oI; }
+                    }
+                    int ties = 0;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int wi = lane + 32 * h;
+                        ties += __popc(__ballot_sync(FULL, wi >= b0 && wi <= b1 && Dm[h] == bestD));
+                    }
+                    if (lane == 0) {
+                        uint32_t fl = (ties > 1 ? KGMA_HIT_ARGMIN_TIE : 0u) | ((near & stretch) ? KGMA_HIT_NEAR_THR : 0u) |
+                                      (b0 == 0 ? KGMA_RUN_OPEN_LEFT : 0u) | (b1 == m - 1 ? KGMA_RUN_OPEN_RIGHT : 0u);
+                        emit_run(a, r, q, w0 + s0 + b0, w0 + s0 + b1, w0 + s0 + bestI, bestD, fl);
+                    }
+                    rem &= ~stretch;
+                }
+                unsigned long long mk = near & ~below;                          // d >= thr inside the 1e-9 band: reported, never replayed
+                while (mk) {
+                    const int i = __ffsll((long long)mk) - 1; mk &= mk - 1;
+                    if (lane == 0) emit_run(a, r, q, w0 + s0 + i, w0 + s0 + i, w0 + s0 + i, dw[i], KGMA_RUN_MARKER | KGMA_HIT_NEAR_THR);
+                }
+                __syncwarp();
             }
+            // ---- return the table to zero: only the k-mers of the last window are still counted
+            for (int p = lane; p < nk; p += 32) tab[kmer_at(a.seq, gpos + n - 1 + p, kmask)] = 0;
+            __syncwarp();
         }
     }
 }
@@ -441,71 +528,36 @@ static void launch_filter_k(int k, const FilterArgs &fa, int grid, cudaStream_t 
     }
 }
 
-struct Interval { int64_t lo, hi; };   // [lo,hi) global base positions of window starts
-
-// Turn flagged 64-base blocks (or everything, in dense mode) into per-record window segments.
-static void build_segments(const kgma_genome *g, const ScanPlan &pl, const std::vector<uint32_t> *cand /*sorted, unique*/,
-                           int64_t pos_lo, int64_t pos_hi, int64_t seg_max, bool want_dists,
-                           const std::vector<int64_t> &dist_base, std::vector<Segment> &segs)
+static double now_ms()
 {
-    int nr = (int)g->recs.size();
-    size_t ci = 0;
-    for (int r = 0; r < nr; r++) {
-        if (pl.steps[r] <= 0) continue;
-        const int64_t off = g->recs[r].off;
-        const int64_t vlo = std::max(off, pos_lo), vhi = std::min(off + pl.steps[r] + 1, pos_hi);   // windows 0..steps
-        if (vlo >= vhi) { continue; }
-        std::vector<Interval> iv;
-        if (!cand) iv.push_back({ vlo, vhi });
-        else {
-            // the first window of every record is always evaluated (GenomeMiner.jl:42-47 initialises currminim from it)
-            if (off >= pos_lo && off < pos_hi) iv.push_back({ off, std::min(off + 1, vhi) });
-            while (ci < cand->size() && ((int64_t)(*cand)[ci] + 1) * FBLOCK <= vlo) ci++;
-            size_t cj = ci;
-            while (cj < cand->size() && (int64_t)(*cand)[cj] * FBLOCK < vhi) {
-                int64_t lo = std::max<int64_t>((int64_t)(*cand)[cj] * FBLOCK, vlo);
-                int64_t hi = std::min<int64_t>(((int64_t)(*cand)[cj] + 1) * FBLOCK, vhi);
-                if (!iv.empty() && iv.back().hi >= lo) iv.back().hi = std::max(iv.back().hi, hi);
-                else iv.push_back({ lo, hi });
-                cj++;
-            }
-            // a block may straddle into the next record: do not consume the last one
-            ci = (cj > ci) ? cj - 1 : cj;
-        }
-        for (const Interval &I : iv) {
-            int64_t len = I.hi - I.lo;
-            int64_t pieces = (len + seg_max - 1) / seg_max;
-            for (int64_t p = 0; p < pieces; p++) {
-                int64_t a = I.lo + len * p / pieces, b = I.lo + len * (p + 1) / pieces;
-                Segment s;
-                s.gpos = a; s.rec = r; s.w0 = (int32_t)(a - off); s.n = (int32_t)(b - a);
-                s.last_step = (int32_t)pl.steps[r];
-                s.dist_off = want_dists ? dist_base[r] + std::max<int64_t>(0, (a - off) - 1) : -1;
-                segs.push_back(s);
-            }
-        }
-    }
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
-static int exact_chains(const kgma_ctx *ctx, int k, int *nch_out, size_t *smem_out)
+// warps per CTA and dynamic shared memory of kgma_eval for this k
+static int eval_shape(const kgma_ctx *ctx, int k, int *warps_out, size_t *smem_out)
 {
-    size_t nb = (size_t)1 << (2 * k);
-    size_t avail = ctx->smem_optin;
-    size_t sbytes = nb * 4;
-    if (avail < sbytes + nb * 2) return KGMA_E_UNSUPPORTED;
-    int nch = (int)std::min<size_t>((avail - sbytes) / (nb * 2), 256);
-    *nch_out = nch; *smem_out = sbytes + (size_t)nch * nb * 2;
+    const size_t nb = (size_t)1 << (2 * k);
+    const size_t per_warp = nb * 2 + 64 * 2 * 2 + 64 * 8;
+    if (ctx->smem_optin < nb * 4 + per_warp) return KGMA_E_UNSUPPORTED;
+    int w = (int)std::min<size_t>((ctx->smem_optin - nb * 4) / per_warp, 16);
+    *warps_out = w; *smem_out = nb * 4 + (size_t)w * per_warp;
     return KGMA_OK;
 }
+
+constexpr long long NO_D = (long long)0x8080808080808080ull;   // cudaMemset(0x80) pattern = "first window not evaluated"
 
 }  // namespace kgma
 
 using namespace kgma;
 
 // The scan proper (one context / one GPU / one shard).  Fills res->runs, res->first_D, res->dists.
+// Device work is queued back to back (uploads, prefilter launches chasing the genome chunks, count-table
+// kernel reading the candidate list from device memory, result copies) with ONE host synchronisation at the end.
 static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int C,
                           const kgma_scan_params &P, ScanPlan &pl, kgma_result *res)
 {
+    const double t_wall0 = now_ms();
     if (!g->sealed) return set_err(ctx, KGMA_E_STATE, "genome is not sealed");
     if (g->ambiguous)
         return set_err(ctx, KGMA_E_SYMBOL, "KeyError: record %lld position %lld holds a symbol outside A,C,G,T,N",
@@ -533,9 +585,78 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     rc = genome_pin(ctx, g);
     if (rc) return rc;
 
+    int ewarps = 0; size_t esmem = 0;
+    rc = eval_shape(ctx, pl.k, &ewarps, &esmem);
+    if (rc) return set_err(ctx, rc, "k = %d does not fit the shared-memory count tables", pl.k);
+    const size_t nb = (size_t)1 << (2 * pl.k);
+    const int egrid = ctx->num_sms;
+    const int64_t total_warps = (int64_t)egrid * ewarps;
+
+    // ---- per-record window ranges owned by this shard (+ dense items, dist offsets)
+    std::vector<RecDev> recs((size_t)std::max(nr, 1));
+    std::vector<uint32_t> seeds;                                   // blocks holding window 0 of a record: always evaluated
+    int64_t span_windows = 0, ndist = 0;
+    for (int r = 0; r < nr; r++) {
+        RecDev &R = recs[(size_t)r];
+        R.off = g->recs[r].off; R.w_begin = R.w_end = 0; R.item_base = 0; R.dist_base = ndist;
+        if (want_dists) ndist += pl.steps[r];
+        if (pl.steps[r] <= 0) continue;
+        const int64_t lo = std::max<int64_t>(R.off, pos_lo), hi = std::min<int64_t>(R.off + pl.steps[r] + 1, pos_hi);   // windows 0..steps
+        if (lo >= hi) continue;
+        R.w_begin = lo - R.off; R.w_end = hi - R.off;
+        span_windows += hi - lo;
+        if (R.w_begin == 0) seeds.push_back((uint32_t)(R.off / FBLOCK));
+    }
+    st.bases_scanned = span_windows;
+    int span = 0; int64_t n_items = 0;
+    auto plan_dense = [&]() {
+        int64_t sp = span_windows / std::max<int64_t>(1, total_warps * 4) + 1;
+        sp = std::min<int64_t>(std::max<int64_t>((sp + 63) / 64 * 64, 64), 1 << 16);
+        span = (int)sp; n_items = 0;
+        for (int r = 0; r < nr; r++) { recs[(size_t)r].item_base = n_items; n_items += (recs[(size_t)r].w_end - recs[(size_t)r].w_begin + sp - 1) / sp; }
+    };
+    if (dense) plan_dense();
+
+    // ---- device scratch layout + one pinned staging block for all small uploads
+    const uint32_t cand_cap = (uint32_t)std::min<int64_t>(std::max<int64_t>((blk_hi - blk_lo) / 16, 1 << 16) + (int64_t)seeds.size(), 1 << 26);
+    const uint32_t run_cap = 1u << 20;
+    const uint32_t run_head = 4096;                                // runs copied back with the counters; more only if needed
+    size_t o = 0;
+    auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
+    const size_t o_S = carve((size_t)C * nb * 4), o_tab = carve(65536 * 2), o_recs = carve(recs.size() * sizeof(RecDev));
+    const size_t o_seed = carve((seeds.size() + 1) * 4);
+    const size_t up_bytes = o;                                     // everything above is uploaded from the staging block
+    const size_t o_cnt = carve(256), o_first = carve((size_t)C * std::max(nr, 1) * 8), o_runs = carve((size_t)run_cap * sizeof(kgma_run));
+    const size_t o_cand = carve((size_t)cand_cap * 4);
+    const size_t o_dists = carve(want_dists ? (size_t)C * (size_t)std::max<int64_t>(ndist, 1) * 8 : 0);
+    void *dsv = nullptr;
+    rc = dev_scratch(ctx, o, &dsv);
+    if (rc) return rc;
+    unsigned char *ds = (unsigned char *)dsv;
+    const size_t back_bytes = 256 + (size_t)C * std::max(nr, 1) * 8 + (size_t)run_head * sizeof(kgma_run);
+    void *hsv = nullptr;
+    rc = host_scratch(ctx, up_bytes + back_bytes, &hsv);
+    if (rc) return rc;
+    unsigned char *hs = (unsigned char *)hsv, *hback = hs + up_bytes;
+    for (int q = 0; q < C; q++) memcpy(hs + o_S + (size_t)q * nb * 4, pl.tabs[q].S_rev.data(), nb * 4);
+    if (!dense) memcpy(hs + o_tab, tab8.data(), 65536 * 2);
+    memcpy(hs + o_recs, recs.data(), recs.size() * sizeof(RecDev));
+    if (!seeds.empty()) memcpy(hs + o_seed, seeds.data(), seeds.size() * 4);
+    { const uint32_t ns = (uint32_t)seeds.size(); memcpy(hs + o_seed + seeds.size() * 4, &ns, 4); }
+
     cudaStream_t sc_ = ctx->s_compute, sp = ctx->s_copy;
     cudaEvent_t e_start = ctx->ev[0], e_h2d = ctx->ev[1], e_filt = ctx->ev[2], e_exact = ctx->ev[3], e_fstart = ctx->ev[4];
+    uint32_t *d_counters = (uint32_t *)(ds + o_cnt);               // [0] = cand_count, [1] = run_count
     KGMA_CUDA(ctx, cudaEventRecord(e_start, sc_));
+    KGMA_CUDA(ctx, cudaMemcpyAsync(ds, hs, up_bytes, cudaMemcpyHostToDevice, sc_));
+    KGMA_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 256, sc_));
+    KGMA_CUDA(ctx, cudaMemsetAsync(ds + o_first, 0x80, (size_t)C * std::max(nr, 1) * 8, sc_));
+    if (!dense && !seeds.empty()) {                                // pre-seed the candidate list
+        KGMA_CUDA(ctx, cudaMemcpyAsync(ds + o_cand, ds + o_seed, seeds.size() * 4, cudaMemcpyDeviceToDevice, sc_));
+        KGMA_CUDA(ctx, cudaMemcpyAsync(d_counters, ds + o_seed + seeds.size() * 4, 4, cudaMemcpyDeviceToDevice, sc_));
+    }
+    st.h2d_bytes += up_bytes;
+    st.host_setup_ms = now_ms() - t_wall0;
 
     // ---- upload range (bases): shard + halo, unless resident
     const int64_t halo = (int64_t)(dense ? pl.maxws + 64 : (M + 1) * FBLOCK + pl.maxws + 64);
@@ -543,35 +664,6 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     if (si == sc - 1) up_hi = g->G + TAIL_PAD;
     up_hi = (up_hi + 127) / 128 * 128; up_hi = std::min(up_hi, g->G + TAIL_PAD);
     const bool resident_ok = (P.flags & KGMA_F_RESIDENT) && ctx->d_seq_valid && ctx->d_valid_lo <= up_lo && ctx->d_valid_hi >= up_hi;
-
-    // ---- device scratch layout
-    const uint32_t cand_cap = (uint32_t)std::min<int64_t>(std::max<int64_t>((blk_hi - blk_lo) / 16, 1 << 16), 1 << 24);
-    const size_t nb = (size_t)1 << (2 * pl.k);
-    size_t o = 0;
-    auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
-    size_t o_tab = carve(65536 * 2), o_cnt = carve(256), o_cand = carve((size_t)cand_cap * 4), o_S = carve((size_t)C * nb * 4);
-    size_t o_first = carve((size_t)C * nr * 8);
-    const uint32_t run_cap = 1u << 20;
-    size_t o_runs = carve((size_t)run_cap * sizeof(kgma_run));
-    void *dsv = nullptr;
-    // segments + dists are sized later; reserve generously for segments now
-    const size_t seg_cap_bytes = (size_t)64 << 20;
-    size_t o_segs = carve(seg_cap_bytes);
-    rc = dev_scratch(ctx, o, &dsv);
-    if (rc) return rc;
-    unsigned char *ds = (unsigned char *)dsv;
-    uint32_t *d_counters = (uint32_t *)(ds + o_cnt);      // [0]=cand_count [1]=run_count [2]=next_seg
-    KGMA_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 256, sc_));
-    {   // profile tables + first_D init
-        std::vector<int32_t> Sall((size_t)C * nb);
-        for (int q = 0; q < C; q++) memcpy(&Sall[(size_t)q * nb], pl.tabs[q].S_rev.data(), nb * 4);
-        KGMA_CUDA(ctx, cudaMemcpyAsync(ds + o_S, Sall.data(), Sall.size() * 4, cudaMemcpyHostToDevice, sc_));
-        std::vector<int64_t> fd((size_t)C * nr, INT64_MIN);
-        KGMA_CUDA(ctx, cudaMemcpyAsync(ds + o_first, fd.data(), fd.size() * 8, cudaMemcpyHostToDevice, sc_));
-        if (!dense) KGMA_CUDA(ctx, cudaMemcpyAsync(ds + o_tab, tab8.data(), 65536 * 2, cudaMemcpyHostToDevice, sc_));
-        KGMA_CUDA(ctx, cudaStreamSynchronize(sc_));         // staging vectors go out of scope
-        st.h2d_bytes += Sall.size() * 4 + fd.size() * 8 + (dense ? 0 : 65536 * 2);
-    }
 
     // ---- stream the packed genome: chunked cudaMemcpyAsync on the copy stream, prefilter on the
     //      compute stream chasing it (double buffering falls out of the two streams + per-chunk events)
@@ -621,99 +713,82 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     if (first_filter) KGMA_CUDA(ctx, cudaEventRecord(e_fstart, sc_));
     KGMA_CUDA(ctx, cudaEventRecord(e_filt, sc_));
 
-    // ---- candidates -> segments
-    std::vector<uint32_t> cand;
-    if (!dense) {
-        uint32_t ncand = 0;
-        KGMA_CUDA(ctx, cudaMemcpyAsync(&ncand, d_counters, 4, cudaMemcpyDeviceToHost, sc_));
+    // ---- count-table kernel over the candidate list (read on the device) or over everything
+    EvalArgs ea{};
+    ea.seq = ctx->d_seq2; ea.S = (const int32_t *)(ds + o_S);
+    ea.cand_count = d_counters; ea.cand_cap = cand_cap;
+    ea.recs = (const RecDev *)(ds + o_recs); ea.nrec = nr;
+    ea.C = C; ea.k = pl.k;
+    for (int q = 0; q < C; q++) {
+        const ProfTab &t = pl.tabs[q];
+        ea.prof[q].N2 = t.N2; ea.prof[q].twoN = t.twoN; ea.prof[q].sumS2 = t.sumS2;
+        ea.prof[q].T = t.T; ea.prof[q].Tlo = t.Tlo; ea.prof[q].Thi = t.Thi; ea.prof[q].nk = (int)t.nk; ea.prof[q].pad = 0;
+    }
+    ea.runs = (kgma_run *)(ds + o_runs); ea.run_cap = run_cap; ea.run_count = d_counters + 1;
+    ea.first_D = (long long *)(ds + o_first);
+    ea.dists = want_dists ? (long long *)(ds + o_dists) : nullptr; ea.dist_stride = std::max<int64_t>(ndist, 1);
+    KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+    uint32_t cnts[2] = { 0, 0 };
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (nr == 0) break;
+        ea.cand = dense ? nullptr : (const uint32_t *)(ds + o_cand);
+        ea.n_items = dense ? n_items : 0; ea.span = span;
+        kgma_eval<<<egrid, ewarps * 32, esmem, sc_>>>(ea);
+        KGMA_CUDA(ctx, cudaGetLastError());
+        st.launches++;
+        KGMA_CUDA(ctx, cudaEventRecord(e_exact, sc_));
+        // counters + first-window distances + the head of the run list, one synchronisation
+        KGMA_CUDA(ctx, cudaMemcpyAsync(hback, d_counters, 256, cudaMemcpyDeviceToHost, sc_));
+        KGMA_CUDA(ctx, cudaMemcpyAsync(hback + 256, ds + o_first, (size_t)C * nr * 8, cudaMemcpyDeviceToHost, sc_));
+        KGMA_CUDA(ctx, cudaMemcpyAsync(hback + 256 + (size_t)C * nr * 8, ds + o_runs, (size_t)run_head * sizeof(kgma_run), cudaMemcpyDeviceToHost, sc_));
         KGMA_CUDA(ctx, cudaStreamSynchronize(sc_));
-        st.d2h_bytes += 4;
-        st.blocks_total = blk_hi - blk_lo; st.blocks_flagged = ncand;
-        if (ncand > cand_cap) dense = true;                  // too many survivors: evaluate everything
-        else {
-            cand.resize(ncand);
-            if (ncand) KGMA_CUDA(ctx, cudaMemcpy(cand.data(), ds + o_cand, (size_t)ncand * 4, cudaMemcpyDeviceToHost));
-            st.d2h_bytes += (size_t)ncand * 4;
-            std::sort(cand.begin(), cand.end());
+        memcpy(cnts, hback, 8);
+        st.d2h_bytes += back_bytes;
+        if (!dense && cnts[0] > cand_cap) {                        // too many survivors: evaluate everything
+            dense = true; plan_dense();
+            memcpy(hs + o_recs, recs.data(), recs.size() * sizeof(RecDev));
+            KGMA_CUDA(ctx, cudaMemcpyAsync(ds + o_recs, hs + o_recs, recs.size() * sizeof(RecDev), cudaMemcpyHostToDevice, sc_));
+            KGMA_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 256, sc_));
+            continue;
         }
+        break;
     }
-    std::vector<int64_t> dist_base(nr, 0); int64_t ndist = 0;
-    if (want_dists) for (int r = 0; r < nr; r++) { dist_base[r] = ndist; ndist += pl.steps[r]; }
-
-    int nch = 0; size_t esmem = 0;
-    rc = exact_chains(ctx, pl.k, &nch, &esmem);
-    if (rc) return set_err(ctx, rc, "k = %d does not fit the shared-memory count tables", pl.k);
-    const int eblock = std::min(256, (nch + 31) / 32 * 32);
-    const int64_t total_chains = (int64_t)nch * ctx->num_sms;
-    int64_t span = 0; for (int r = 0; r < nr; r++) span += pl.steps[r] ? pl.steps[r] + 1 : 0;
-    int64_t seg_max = dense ? std::min<int64_t>(std::max<int64_t>(span / (total_chains * 8) + 1, 2048), 1 << 20) : 8192;
-    std::vector<Segment> segs;
-    build_segments(g, pl, dense ? nullptr : &cand, pos_lo, pos_hi, seg_max, want_dists, dist_base, segs);
-    if (!dense && segs.size() * sizeof(Segment) > seg_cap_bytes) {          // survivors too fragmented: evaluate everything
-        dense = true; segs.clear();
-        seg_max = std::min<int64_t>(std::max<int64_t>(span / (total_chains * 8) + 1, 2048), 1 << 20);
-        build_segments(g, pl, nullptr, pos_lo, pos_hi, seg_max, want_dists, dist_base, segs);
-    }
-    if (segs.size() * sizeof(Segment) > seg_cap_bytes) return set_err(ctx, KGMA_E_CAPACITY, "too many segments (%zu)", segs.size());
-    int64_t exact_windows = 0; for (auto &s : segs) exact_windows += s.n;
-    st.exact_windows = exact_windows * C;
-    for (int r = 0; r < nr; r++) if (pl.steps[r]) {
-        int64_t lo = std::max(g->recs[r].off, pos_lo), hi = std::min(g->recs[r].off + pl.steps[r] + 1, pos_hi);
-        if (hi > lo) st.bases_scanned += hi - lo;
-    }
-
-    long long *d_dists = nullptr;
-    if (want_dists && ndist > 0) KGMA_CUDA(ctx, cudaMalloc(&d_dists, (size_t)ndist * 8));
-    res->dists.assign(C, {});
-    res->first_D.assign((size_t)C * nr, INT64_MIN);
-    std::vector<kgma_run> &runs = res->runs; runs.clear();
-    if (!segs.empty()) {
-        KGMA_CUDA(ctx, cudaMemcpyAsync(ds + o_segs, segs.data(), segs.size() * sizeof(Segment), cudaMemcpyHostToDevice, sc_));
-        st.h2d_bytes += segs.size() * sizeof(Segment);
-        KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
-        const int egrid = (int)std::min<int64_t>(ctx->num_sms, ((int64_t)segs.size() + nch - 1) / nch);
-        for (int q = 0; q < C; q++) {
-            const ProfTab &t = pl.tabs[q];
-            ExactArgs ea{};
-            ea.seq = ctx->d_seq2; ea.S = (const int32_t *)(ds + o_S) + (size_t)q * nb;
-            ea.segs = (const Segment *)(ds + o_segs); ea.nseg = (int)segs.size();
-            ea.next_seg = (int *)(d_counters + 2 + q);
-            ea.k = pl.k; ea.nk = (int)t.nk; ea.nch = nch; ea.profile = q;
-            ea.N2 = t.N2; ea.twoN = t.twoN; ea.sumS2 = t.sumS2; ea.T = t.T; ea.Tlo = t.Tlo; ea.Thi = t.Thi;
-            ea.runs = (kgma_run *)(ds + o_runs); ea.run_cap = run_cap; ea.run_count = d_counters + 1;
-            ea.first_D = (long long *)(ds + o_first) + (size_t)q * nr;
-            ea.dists = d_dists;
-            kgma_exact<<<egrid, eblock, esmem, sc_>>>(ea);
-            KGMA_CUDA(ctx, cudaGetLastError());
-            st.launches++;
-            if (want_dists && ndist > 0) {                   // one profile's D at a time through the same buffer
-                std::vector<long long> Dh((size_t)ndist);
-                KGMA_CUDA(ctx, cudaMemcpyAsync(Dh.data(), d_dists, (size_t)ndist * 8, cudaMemcpyDeviceToHost, sc_));
-                KGMA_CUDA(ctx, cudaStreamSynchronize(sc_));
-                st.d2h_bytes += (size_t)ndist * 8;
-                res->dists[q].resize((size_t)ndist);
-                const double den = t.denom;
-                for (int64_t i = 0; i < ndist; i++) res->dists[q][(size_t)i] = (double)Dh[(size_t)i] / den;
-            }
-        }
-    }
-    KGMA_CUDA(ctx, cudaEventRecord(e_exact, sc_));
-    uint32_t cnts[3] = { 0, 0, 0 };
-    KGMA_CUDA(ctx, cudaMemcpyAsync(cnts, d_counters, 8, cudaMemcpyDeviceToHost, sc_));
-    KGMA_CUDA(ctx, cudaMemcpyAsync(res->first_D.data(), ds + o_first, (size_t)C * nr * 8, cudaMemcpyDeviceToHost, sc_));
-    KGMA_CUDA(ctx, cudaStreamSynchronize(sc_));
-    if (d_dists) cudaFree(d_dists);
+    const double t_cand0 = now_ms();
+    if (!dense) { st.blocks_total = blk_hi - blk_lo; st.blocks_flagged = cnts[0]; st.exact_windows = (int64_t)cnts[0] * FBLOCK * C; }
+    else st.exact_windows = span_windows * C;
     if (cnts[1] > run_cap) return set_err(ctx, KGMA_E_CAPACITY, "run list overflow (%u runs)", cnts[1]);
+    std::vector<kgma_run> &runs = res->runs;
     runs.resize(cnts[1]);
-    if (cnts[1]) KGMA_CUDA(ctx, cudaMemcpy(runs.data(), ds + o_runs, (size_t)cnts[1] * sizeof(kgma_run), cudaMemcpyDeviceToHost));
-    st.d2h_bytes += 8 + (size_t)C * nr * 8 + (size_t)cnts[1] * sizeof(kgma_run);
+    if (cnts[1]) memcpy(runs.data(), hback + 256 + (size_t)C * nr * 8, (size_t)std::min(cnts[1], run_head) * sizeof(kgma_run));
+    if (cnts[1] > run_head) {
+        KGMA_CUDA(ctx, cudaMemcpy(runs.data() + run_head, ds + o_runs + (size_t)run_head * sizeof(kgma_run),
+                                  (size_t)(cnts[1] - run_head) * sizeof(kgma_run), cudaMemcpyDeviceToHost));
+        st.d2h_bytes += (size_t)(cnts[1] - run_head) * sizeof(kgma_run);
+    }
+    res->first_D.assign((size_t)C * nr, INT64_MIN);
+    {
+        const long long *fd = (const long long *)(hback + 256);
+        for (size_t i = 0; i < (size_t)C * nr; i++) if (fd[i] != NO_D) res->first_D[i] = fd[i];
+    }
+    res->dists.assign(C, {});
+    if (want_dists && ndist > 0) {
+        std::vector<long long> Dh((size_t)ndist);
+        for (int q = 0; q < C; q++) {
+            KGMA_CUDA(ctx, cudaMemcpy(Dh.data(), ds + o_dists + (size_t)q * ndist * 8, (size_t)ndist * 8, cudaMemcpyDeviceToHost));
+            st.d2h_bytes += (size_t)ndist * 8;
+            res->dists[q].resize((size_t)ndist);
+            const double den = pl.tabs[q].denom;
+            for (int64_t i = 0; i < ndist; i++) res->dists[q][(size_t)i] = (double)Dh[(size_t)i] / den;
+        }
+    }
     st.n_runs = cnts[1];
     float ms = 0;
     cudaEventElapsedTime(&ms, e_start, e_h2d); st.h2d_ms = ms;
     cudaEventElapsedTime(&ms, e_fstart, e_filt); st.filter_ms = ms;
-    cudaEventElapsedTime(&ms, e_filt, e_exact); st.exact_ms = ms;
-    cudaEventElapsedTime(&ms, e_start, e_exact); st.total_ms = ms;
+    if (nr) { cudaEventElapsedTime(&ms, e_filt, e_exact); st.exact_ms = ms; cudaEventElapsedTime(&ms, e_start, e_exact); st.total_ms = ms; }
     if (!(P.flags & KGMA_F_RESIDENT)) { ctx->d_seq_valid = false; }
+    st.host_cand_ms = now_ms() - t_cand0;
+    st.wall_ms = now_ms() - t_wall0;
     return KGMA_OK;
 }
 
@@ -757,7 +832,13 @@ int kgma_scan(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int n
     kgma_result *res = new kgma_result();
     ScanPlan pl;
     int rc = scan_runs_impl(ctx, g, profiles, n_profiles, P, pl, res);
-    if (rc == KGMA_OK) rc = replay(ctx, g, pl.tabs, profiles, P, res->runs, res->first_D, res);
+    if (rc == KGMA_OK) {
+        const double t0 = now_ms();
+        rc = replay(ctx, g, pl.tabs, profiles, P, res->runs, res->first_D, res);
+        const double dt = now_ms() - t0;
+        ctx->stats.host_replay_ms = dt - ctx->stats.align_ms;
+        ctx->stats.wall_ms += dt;
+    }
     if (rc) { delete res; return rc; }
     *out = res;
     return KGMA_OK;
