@@ -151,6 +151,147 @@ __global__ void __launch_bounds__(128) kgma_align(AlignArgs A)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Trace-free variant (the default; the trace kernel above is only used when CIGARs are requested).
+// cigar_to_UnitRange needs three numbers of the optimal path only: the length of its first run, the length of
+// its last run and its total number of columns.  Those are carried forward with the scores as a packed
+// "path summary" per DP state (H, E, F), choosing the predecessor with exactly the priorities the traceback
+// uses (match > delete > insert; extend-vs-open as configured), so no trace matrix is written or walked.
+// The subject is read straight from the packed genome on the device (2-bit plane + ambiguity plane).
+struct AlignJob2 { long long gpos; int32_t n, a_off, m, b_off; };   // b_off >= 0: subject codes were uploaded (not on the device)
+
+struct AlignArgs2 {
+    const uint8_t *a;            // consensus codes 0..3, 4 = N
+    const uint32_t *seq;         // packed 2-bit genome on the device
+    const long long *nruns; int n_nruns;   // maximal runs of masked (N) bases, [start,end) global positions, ascending
+    const uint8_t *b;            // uploaded subject codes for jobs whose slice is not on the device
+    const AlignJob2 *jobs; int njobs;
+    int *next_job;
+    AlignOut *out;
+    int go, ge, tie_open, ncol_cap;
+};
+
+// path summary, two 32-bit words:  lo = total columns | first-run length << 16
+//                                   hi = last-run length (0-11.. up to 65535 & 0xFFFF) | last op << 16 | (>= 2 runs) << 18 | non-empty << 19
+// Gap states do not append per cell: E / F keep the summary of the H cell the gap was opened from plus the gap
+// length, and the run is appended only when H actually selects the gap (rare with EDNAFULL and gap_open << 0).
+#define PS_EQ 0u
+#define PS_X  1u
+#define PS_I  2u
+#define PS_D  3u
+#define PS_MULTI (1u << 18)
+#define PS_NE    (1u << 19)
+struct PathSum { uint32_t lo, hi; };
+__device__ __forceinline__ PathSum ps_run(uint32_t len, uint32_t op)
+{
+    PathSum r; r.lo = len ? (len | (len << 16)) : 0u; r.hi = len ? (len | (op << 16) | PS_NE) : 0u; return r;
+}
+__device__ __forceinline__ PathSum ps_append(PathSum s, uint32_t op, uint32_t len)
+{
+    PathSum r;
+    if (!(s.hi & PS_NE)) return ps_run(len, op);
+    if (((s.hi >> 16) & 3u) == op) { r.lo = s.lo + len + ((s.hi & PS_MULTI) ? 0u : (len << 16)); r.hi = s.hi + len; }
+    else { r.lo = s.lo + len; r.hi = len | (op << 16) | PS_MULTI | PS_NE; }
+    return r;
+}
+
+__global__ void __launch_bounds__(128) kgma_align_summary(AlignArgs2 A)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t per_warp = (size_t)A.ncol_cap * (7 * 4 + 1);
+    unsigned char *wb = s_raw + (size_t)wid * ((per_warp + 15) & ~(size_t)15);
+    int *Hb = reinterpret_cast<int *>(wb), *Eb = Hb + A.ncol_cap;
+    uint32_t *sHlo = reinterpret_cast<uint32_t *>(Eb + A.ncol_cap), *sHhi = sHlo + A.ncol_cap;
+    uint32_t *bElo = sHhi + A.ncol_cap, *bEhi = bElo + A.ncol_cap, *lEb = bEhi + A.ncol_cap;
+    uint8_t *bs = reinterpret_cast<uint8_t *>(lEb + A.ncol_cap);
+    const int NEG = -(1 << 29);
+    const int go = A.go, ge = A.ge;
+
+    for (;;) {
+        int ji = 0;
+        if (lane == 0) ji = atomicAdd(A.next_job, 1);
+        ji = __shfl_sync(FULL, ji, 0);
+        if (ji >= A.njobs) break;
+        const AlignJob2 J = A.jobs[ji];
+        const int m = J.m, n = J.n;
+        const uint8_t *a = A.a + J.a_off;
+        // stage the subject codes: 2-bit code from the packed genome, 4 = N inside a masked run
+        if (J.b_off >= 0) { for (int j = lane; j < n; j += 32) bs[j] = A.b[J.b_off + j]; }
+        else for (int j = lane; j < n; j += 32) {
+            const long long gp = J.gpos + j;
+            uint32_t c = (__ldg(A.seq + (gp >> 4)) >> (2 * (int)(gp & 15))) & 3u;
+            if (A.n_nruns) {
+                int lo = -1, hi = A.n_nruns;                       // last run with start <= gp
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (A.nruns[2 * mid] <= gp) lo = mid; else hi = mid; }
+                if (lo >= 0 && gp < A.nruns[2 * lo + 1]) c = 4u;
+            }
+            bs[j] = (uint8_t)c;
+        }
+        __syncwarp();
+        int score = 0; PathSum sfin = { 0u, 0u };
+        const int nrb = (m + 31) >> 5;
+        for (int rb = 0; rb < nrb; rb++) {
+            const int i = rb * 32 + lane + 1;
+            const bool row_ok = i <= m;
+            const int ai = row_ok ? a[i - 1] : 0;
+            const bool last = (i == m);
+            int Hleft = -(go + i * ge), F = NEG;                                  // H[i][0], F[i][0]
+            PathSum sHleft = ps_run((uint32_t)i, PS_I), bF = { 0u, 0u }; uint32_t lF = 0;
+            int Hdiag = (i == 1) ? 0 : -(go + (i - 1) * ge);                      // H[i-1][0]
+            PathSum sHdiag = ps_run((uint32_t)(i - 1), PS_I);
+            int Hout = NEG, Eout = NEG; PathSum sHout = { 0u, 0u }, bEout = { 0u, 0u }; uint32_t lEout = 0;
+            for (int s = 1; s <= n + 31; s++) {
+                const int j = s - lane;
+                int upH = __shfl_up_sync(FULL, Hout, 1), upE = __shfl_up_sync(FULL, Eout, 1);
+                PathSum supH, ubE; uint32_t ulE;
+                supH.lo = __shfl_up_sync(FULL, sHout.lo, 1); supH.hi = __shfl_up_sync(FULL, sHout.hi, 1);
+                ubE.lo = __shfl_up_sync(FULL, bEout.lo, 1); ubE.hi = __shfl_up_sync(FULL, bEout.hi, 1);
+                ulE = __shfl_up_sync(FULL, lEout, 1);
+                if (lane == 0 && j >= 1 && j <= n) {
+                    if (rb == 0) { upH = 0; upE = NEG; supH = ps_run((uint32_t)j, PS_D); ubE.lo = ubE.hi = 0; ulE = 0; }   // row 0: free leading deletions
+                    else { upH = Hb[j]; upE = Eb[j]; supH.lo = sHlo[j]; supH.hi = sHhi[j]; ubE.lo = bElo[j]; ubE.hi = bEhi[j]; ulE = lEb[j]; }
+                }
+                if (row_ok && j >= 1 && j <= n) {
+                    const int eo = upH - go - ge, ee = upE - ge;
+                    const bool xe = A.tie_open ? (ee > eo) : (ee >= eo);
+                    const int e = xe ? ee : eo;
+                    PathSum bE; bE.lo = xe ? ubE.lo : supH.lo; bE.hi = xe ? ubE.hi : supH.hi;
+                    const uint32_t lE = xe ? ulE + 1 : 1u;
+                    const int fo = last ? Hleft : Hleft - go - ge, fe = last ? F : F - ge;
+                    const bool xf = A.tie_open ? (fe > fo) : (fe >= fo);
+                    const int f = xf ? fe : fo;
+                    bF.lo = xf ? bF.lo : sHleft.lo; bF.hi = xf ? bF.hi : sHleft.hi; lF = xf ? lF + 1 : 1u;
+                    const int bj = bs[j - 1];
+                    const int mm = Hdiag + edna(ai, bj);
+                    const int h = max(mm, max(f, e));
+                    PathSum sH = ps_append(sHdiag, ai == bj ? PS_EQ : PS_X, 1u);
+                    if (mm != h) sH = (f == h) ? ps_append(bF, PS_D, lF) : ps_append(bE, PS_I, lE);
+                    Hdiag = upH; sHdiag = supH; Hout = h; Eout = e; sHout = sH; bEout = bE; lEout = lE;
+                    Hleft = h; sHleft = sH; F = f;
+                    if (lane == 31) { Hb[j] = h; Eb[j] = e; sHlo[j] = sH.lo; sHhi[j] = sH.hi; bElo[j] = bE.lo; bEhi[j] = bE.hi; lEb[j] = lE; }
+                }
+            }
+            if (rb == nrb - 1) {
+                score = __shfl_sync(FULL, Hleft, (m - 1) & 31);
+                sfin.lo = __shfl_sync(FULL, sHleft.lo, (m - 1) & 31); sfin.hi = __shfl_sync(FULL, sHleft.hi, (m - 1) & 31);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            // cigar_to_UnitRange (Alignment.jl:13-30): lower = count of the first op, num_sum = all ops but the last
+            AlignOut o;
+            const bool multi = (sfin.hi & PS_MULTI) != 0;
+            o.score = score; o.nops = multi ? 2 : ((sfin.hi & PS_NE) ? 1 : 0); o.cig_n = 0;
+            o.lower = multi ? (int)(sfin.lo >> 16) : 0;
+            o.num_sum = multi ? (int)((sfin.lo & 0xFFFFu) - (sfin.hi & 0xFFFFu)) : 0;
+            A.out[ji] = o;
+        }
+        __syncwarp();
+    }
+}
+
 static inline uint8_t sym_code(char c)
 {
     switch (c) {
@@ -186,6 +327,79 @@ int align_batch_device(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq
     }
     cudaEvent_t e0 = ctx->ev[0], e1 = ctx->ev[1];
     double align_ms = 0;
+    cudaStream_t st = ctx->s_compute;
+    if (!want_cigars) {
+        // ---- trace-free path: one launch for everything; subjects come from the packed genome already on the device
+        const std::vector<int64_t> &nruns = genome_nruns(g);
+        const bool on_dev = ctx->dg_uid == g->uid && ctx->d_seq2 && ctx->d_have_hi > ctx->d_have_lo;
+        std::vector<AlignJob2> jobs(reqs.size()); std::vector<uint8_t> bcodes; int maxn = 0;
+        for (size_t i = 0; i < reqs.size(); i++) {
+            const AlignReq &rq = reqs[i];
+            if (rq.record < 0 || rq.record >= (int)g->recs.size() || rq.profile < 0 || rq.profile >= n_profiles)
+                return set_err(ctx, KGMA_E_ARG, "alignment request %zu out of range", i);
+            const kgma::Record &R = g->recs[rq.record];
+            if (rq.first < 1 || rq.last > R.len || rq.last < rq.first) return set_err(ctx, KGMA_E_ARG, "alignment range %lld:%lld invalid", (long long)rq.first, (long long)rq.last);
+            AlignJob2 &J = jobs[i];
+            J.gpos = R.off + rq.first - 1; J.n = (int)(rq.last - rq.first + 1); J.a_off = a_off[rq.profile]; J.m = a_len[rq.profile]; J.b_off = -1;
+            maxn = std::max(maxn, J.n);
+            if (J.m + J.n >= 65535) return set_err(ctx, KGMA_E_UNSUPPORTED, "alignment of %d x %d too long", J.m, J.n);
+            if (!(on_dev && J.gpos >= ctx->d_have_lo && J.gpos + J.n + 16 <= ctx->d_have_hi)) {      // slice lives on another shard's device: ship codes
+                J.b_off = (int32_t)bcodes.size();
+                for (int64_t p = rq.first; p <= rq.last; p++) {
+                    int64_t gp = R.off + p - 1;
+                    uint8_t c = (uint8_t)base_code(g, gp);
+                    if (base_masked(g, gp)) { if (c != 3) return set_err(ctx, KGMA_E_SYMBOL, "subject holds a symbol outside A,C,G,T,N"); c = 4; }
+                    bcodes.push_back(c);
+                }
+            }
+        }
+        if (g->ambiguous) return set_err(ctx, KGMA_E_SYMBOL, "subject holds a symbol outside A,C,G,T,N");
+        const int nj = (int)jobs.size();
+        const int ncol = (maxn + 1 + 31) & ~31;
+        const int warps_per_block = 4;
+        const size_t per_warp = (((size_t)ncol * (7 * 4 + 1)) + 15) & ~(size_t)15;
+        const size_t smem = (size_t)warps_per_block * per_warp;
+        if (smem > ctx->smem_optin) return set_err(ctx, KGMA_E_UNSUPPORTED, "subject slice of %d bases too long for the extension kernel", maxn);
+        size_t o = 0;
+        auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
+        const size_t o_a = carve(acodes.size()), o_b = carve(bcodes.size()), o_j = carve((size_t)nj * sizeof(AlignJob2));
+        const size_t o_n = carve(nruns.size() * 8 + 8);
+        const size_t up = o;
+        const size_t o_c = carve(256), o_o = carve((size_t)nj * sizeof(AlignOut));
+        // the scan's scratch (run lists etc.) has been consumed by now: reuse it
+        void *dv = nullptr, *hv = nullptr;
+        int rc = dev_scratch(ctx, o, &dv);
+        if (rc) return rc;
+        rc = host_scratch(ctx, up + (size_t)nj * sizeof(AlignOut), &hv);
+        if (rc) return rc;
+        unsigned char *d = (unsigned char *)dv, *h = (unsigned char *)hv;
+        memcpy(h + o_a, acodes.data(), acodes.size());
+        if (!bcodes.empty()) memcpy(h + o_b, bcodes.data(), bcodes.size());
+        memcpy(h + o_j, jobs.data(), (size_t)nj * sizeof(AlignJob2));
+        if (!nruns.empty()) memcpy(h + o_n, nruns.data(), nruns.size() * 8);
+        KGMA_CUDA(ctx, cudaMemcpyAsync(d, h, up, cudaMemcpyHostToDevice, st));
+        KGMA_CUDA(ctx, cudaMemsetAsync(d + o_c, 0, 256, st));
+        ctx->stats.h2d_bytes += up;
+        AlignArgs2 A{};
+        A.a = d + o_a; A.seq = ctx->d_seq2; A.nruns = (const long long *)(d + o_n); A.n_nruns = (int)(nruns.size() / 2);
+        A.b = d + o_b; A.jobs = (const AlignJob2 *)(d + o_j); A.njobs = nj; A.next_job = (int *)(d + o_c);
+        A.out = (AlignOut *)(d + o_o); A.go = -gap_open; A.ge = -gap_extend; A.tie_open = tie_open ? 1 : 0; A.ncol_cap = ncol;
+        KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = std::min((nj + warps_per_block - 1) / warps_per_block, ctx->num_sms * 8);
+        KGMA_CUDA(ctx, cudaEventRecord(e0, st));
+        kgma_align_summary<<<grid, warps_per_block * 32, smem, st>>>(A);
+        KGMA_CUDA(ctx, cudaGetLastError());
+        KGMA_CUDA(ctx, cudaEventRecord(e1, st));
+        ctx->stats.launches++;
+        AlignOut *ho = (AlignOut *)(h + up);
+        KGMA_CUDA(ctx, cudaMemcpyAsync(ho, d + o_o, (size_t)nj * sizeof(AlignOut), cudaMemcpyDeviceToHost, st));
+        KGMA_CUDA(ctx, cudaStreamSynchronize(st));
+        ctx->stats.d2h_bytes += (size_t)nj * sizeof(AlignOut);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); align_ms += ms;
+        for (int q = 0; q < nj; q++) { out[q].lo = (int64_t)ho[q].lower + 1; out[q].hi = ho[q].num_sum; out[q].score = ho[q].score; }
+        ctx->stats.align_ms += align_ms;
+        return KGMA_OK;
+    }
     const size_t TRACE_BUDGET = (size_t)768 << 20;
     size_t done = 0;
     while (done < reqs.size()) {
@@ -230,7 +444,6 @@ int align_batch_device(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq
         int rc = dev_scratch(ctx, o, &dv);
         if (rc) return rc;
         unsigned char *d = (unsigned char *)dv;
-        cudaStream_t st = ctx->s_compute;
         KGMA_CUDA(ctx, cudaMemcpyAsync(d + o_a, acodes.data(), acodes.size(), cudaMemcpyHostToDevice, st));
         KGMA_CUDA(ctx, cudaMemcpyAsync(d + o_b, bcodes.data(), bcodes.size(), cudaMemcpyHostToDevice, st));
         KGMA_CUDA(ctx, cudaMemcpyAsync(d + o_j, jobs.data(), (size_t)nj * sizeof(AlignJob), cudaMemcpyHostToDevice, st));

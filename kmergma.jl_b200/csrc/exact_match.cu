@@ -132,6 +132,7 @@ extern "C" int kgma_exact_match(kgma_ctx *ctx, kgma_genome *g, const char *query
         KGMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_mask, g->mask, bases / 8, cudaMemcpyHostToDevice, st));
         S.h2d_bytes += bases / 4 + bases / 8;
         ctx->d_seq_valid = ctx->d_mask_valid = true; ctx->d_valid_lo = 0; ctx->d_valid_hi = (int64_t)bases;
+        ctx->d_have_lo = 0; ctx->d_have_hi = (int64_t)bases;
     }
     KGMA_CUDA(ctx, cudaEventRecord(e1, st));
     const uint32_t cap = 1u << 24;

@@ -76,6 +76,30 @@ int genome_pin(kgma_ctx *ctx, kgma_genome *g)
 
 static std::atomic<uint64_t> g_uid{1};
 
+// maximal runs of masked bases as [start,end) pairs in global coordinates; rebuilt when the genome changed
+const std::vector<int64_t> &genome_nruns(kgma_genome *g)
+{
+    if (g->nruns_uid == g->uid) return g->nruns;
+    g->nruns.clear();
+    if (g->any_mask) {
+        const int64_t nwords = (g->G + 31) / 32;
+        int64_t open = -1;
+        for (int64_t w = 0; w < nwords; w++) {
+            uint32_t m = g->mask[w];
+            if (m == 0) { if (open >= 0) { g->nruns.push_back(open); g->nruns.push_back(w * 32); open = -1; } continue; }
+            if (m == 0xFFFFFFFFu) { if (open < 0) open = w * 32; continue; }
+            for (int b = 0; b < 32; b++) {
+                const bool set = (m >> b) & 1;
+                if (set && open < 0) open = w * 32 + b;
+                else if (!set && open >= 0) { g->nruns.push_back(open); g->nruns.push_back(w * 32 + b); open = -1; }
+            }
+        }
+        if (open >= 0) { g->nruns.push_back(open); g->nruns.push_back(nwords * 32); }
+    }
+    g->nruns_uid = g->uid;
+    return g->nruns;
+}
+
 // start a new record at the next aligned offset; returns its index
 static int begin_record(kgma_genome *g, const char *ident, const char *desc, int64_t len)
 {

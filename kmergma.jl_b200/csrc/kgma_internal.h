@@ -44,6 +44,8 @@ struct kgma_genome {
     int64_t   amb_record = -1, amb_pos = -1;
     uint64_t  uid = 0;
     std::string err;
+    std::vector<int64_t> nruns;    // cache: maximal runs of masked bases, [start,end) global positions (genome_nruns)
+    uint64_t  nruns_uid = 0;
 };
 
 struct kgma_refs {
@@ -73,7 +75,8 @@ struct kgma_ctx {
     uint32_t *d_seq2 = nullptr, *d_mask = nullptr;
     int64_t   d_cap_bases = 0;
     bool      d_seq_valid = false, d_mask_valid = false;
-    int64_t   d_valid_lo = 0, d_valid_hi = 0;       // base range of seq2 present on the device
+    int64_t   d_valid_lo = 0, d_valid_hi = 0;       // base range of seq2 a RESIDENT scan may reuse without upload
+    int64_t   d_have_lo = 0, d_have_hi = 0;         // base range of seq2 physically present (same genome uid) - extension reads it
     // scratch
     void     *d_scratch = nullptr; size_t d_scratch_bytes = 0;
     void     *h_scratch = nullptr; size_t h_scratch_bytes = 0;   // pinned
@@ -90,6 +93,7 @@ int set_err(kgma_ctx *ctx, int code, const char *fmt, ...);
 // ---- genome.cpp
 int  genome_reserve(kgma_genome *g, int64_t bases);
 int  genome_pin(kgma_ctx *ctx, kgma_genome *g);
+const std::vector<int64_t> &genome_nruns(kgma_genome *g);
 inline int base_code(const kgma_genome *g, int64_t gp) { return (g->seq2[gp >> 4] >> (2 * (gp & 15))) & 3; }
 inline int base_masked(const kgma_genome *g, int64_t gp) { return (g->mask[gp >> 5] >> (gp & 31)) & 1; }
 

@@ -441,6 +441,7 @@ int dev_genome_prepare(kgma_ctx *ctx, kgma_genome *g, bool need_mask)
         KGMA_CUDA(ctx, cudaMalloc(&ctx->d_mask, (size_t)need / 8));
         ctx->d_cap_bases = need; ctx->dg_uid = g->uid;
         ctx->d_seq_valid = ctx->d_mask_valid = false; ctx->d_valid_lo = ctx->d_valid_hi = 0;
+        ctx->d_have_lo = ctx->d_have_hi = 0;
     }
     (void)need_mask;
     return KGMA_OK;
@@ -705,6 +706,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
         }
         KGMA_CUDA(ctx, cudaEventRecord(e_h2d, sc_));
         ctx->d_seq_valid = true; ctx->d_valid_lo = up_lo; ctx->d_valid_hi = up_hi;
+        ctx->d_have_lo = up_lo; ctx->d_have_hi = up_hi;
     } else {
         KGMA_CUDA(ctx, cudaEventRecord(e_h2d, sc_));
         rc = run_filter_to(up_hi, true);
@@ -858,6 +860,7 @@ int kgma_genome_make_resident(kgma_ctx *ctx, kgma_genome *g)
     KGMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_mask, g->mask, bases / 8, cudaMemcpyHostToDevice, ctx->s_compute));
     KGMA_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
     ctx->d_seq_valid = ctx->d_mask_valid = true; ctx->d_valid_lo = 0; ctx->d_valid_hi = g->G + TAIL_PAD;
+    ctx->d_have_lo = 0; ctx->d_have_hi = g->G + TAIL_PAD;
     return KGMA_OK;
 }
 
@@ -924,6 +927,7 @@ int kgma_genome_synth(kgma_ctx *ctx, int n_records, const int64_t *rec_len, uint
     fill(prev_end, cap, 0, false);
     g->sealed = true;
     ctx->d_seq_valid = ctx->d_mask_valid = false;           // device copy predates the host-side edits
+    ctx->d_have_lo = ctx->d_have_hi = 0;
     *out = g;
     return KGMA_OK;
 }

@@ -491,3 +491,21 @@ def test_exact_match_vs_oracle(K, O, synth):
     for q in queries:
         for overlap in (True, False):
             assert K.exactMatch(q, g, overlap=overlap) == O.exactMatch(q, f, overlap=overlap), (q[:20], overlap)
+
+
+def test_returned_alignments_match_oracle_cigars(K, O, prof):
+    """do_return_align (GenomeMiner.jl:98-99): the CIGAR of every extended hit equals the oracle's pairalign"""
+    RV, ws, cons = prof
+    res, aligns = [], []
+    out = K.ac_gma_testing(genome_path=GENOME, refVec=RV, consensus_refseq=cons, windowsize=ws, thr=30, buff=50,
+                           do_align=True, do_return_align=True, resultVec=res, result_align_vec=aligns)
+    plain = K.ac_gma_testing(genome_path=GENOME, refVec=RV, consensus_refseq=cons, windowsize=ws, thr=30, buff=50,
+                             do_align=True, resultVec=[])
+    assert [(h.first, h.last, h.align_score) for h in out.hits] == [(h.first, h.last, h.align_score) for h in plain.hits]
+    f = O.Fasta(GENOME)
+    assert len(aligns) == len(out.hits) == 7
+    for h, al in zip(out.hits, aligns):
+        L = f.seqsize(int(h.record))
+        a, b = max(int(h.cmi) - 50, 1), min(int(h.cmi) + ws - 1 + 50, L)
+        cig, score = O.pairalign_semiglobal(cons[:ws], f.seq(int(h.record))[a - 1:b], -69, -1)
+        assert (al.cigar, al.score) == (cig, score)
