@@ -382,8 +382,7 @@ class ScanOutput:
     """Raw result of one kgma_scan call: `hits` is a numpy record array over kgma_hit (h.record, h.first, ...),
     `runs` the raw bytes of the kgma_run list (view with RUN_DT), plus optional dists / cigars."""
 
-    def __init__(self, ctx: Context, res_handle):
-        lib = ctx._lib
+    def __init__(self, lib, res_handle):
         n = lib.kgma_result_n_hits(res_handle)
         hp = lib.kgma_result_hits(res_handle)
         if n:
@@ -459,7 +458,7 @@ def scan_raw(genome: Genome, refVecs, windowsizes, consensus_seqs, thrs, k: int,
     res = C.c_void_p()
     fn = ctx._lib.kgma_scan_runs if runs_only else ctx._lib.kgma_scan
     ctx.check(fn(ctx._h, genome._h, arr, len(refVecs), C.byref(P), C.byref(res)))
-    out = ScanOutput(ctx, res)
+    out = ScanOutput(ctx._lib, res)
     if flags & L.F_WANT_DISTS:
         out.load_dists(len(refVecs))
     if runs_only:
@@ -469,17 +468,24 @@ def scan_raw(genome: Genome, refVecs, windowsizes, consensus_seqs, thrs, k: int,
 
 def replay_raw(genome: Genome, refVecs, windowsizes, consensus_seqs, thrs, k: int, mode: int, buff: int,
                flags: int, gap_open: int, gap_extend: int, runs: np.ndarray, first_D: np.ndarray,
-               only_record: int = -1, ctx: Optional[Context] = None) -> ScanOutput:
-    """kgma_replay over the concatenated run summaries of all shards (runs: raw bytes of kgma_run[])."""
-    ctx = ctx or default_context()
-    arr, keep = _make_profiles(refVecs, windowsizes, consensus_seqs, thrs, k, ctx._lib)
+               only_record: int = -1, ctx: Optional[Context] = None, host_only: bool = False) -> ScanOutput:
+    """kgma_replay over the concatenated run summaries of all shards (runs: raw bytes of kgma_run[]).
+    host_only: merge + replay without a device context (only valid without F_ALIGN; the extension needs the GPU)."""
+    lib = L.load()
+    handle = None
+    if not host_only:
+        ctx = ctx or default_context()
+        handle = ctx._h
+    arr, keep = _make_profiles(refVecs, windowsizes, consensus_seqs, thrs, k, lib)
     P = L.ScanParams(mode, flags, buff, gap_open, gap_extend, 0, 1, only_record, 0)
     runs = np.ascontiguousarray(runs, dtype=np.uint8)
     fd = np.ascontiguousarray(first_D, dtype=np.int64)
     res = C.c_void_p()
-    ctx.check(ctx._lib.kgma_replay(ctx._h, genome._h, arr, len(refVecs), C.byref(P), runs.ctypes.data,
-                                   runs.size // C.sizeof(L.Run), fd.ctypes.data, C.byref(res)))
-    return ScanOutput(ctx, res)
+    rc = lib.kgma_replay(handle, genome._h, arr, len(refVecs), C.byref(P), runs.ctypes.data,
+                         runs.size // C.sizeof(L.Run), fd.ctypes.data, C.byref(res))
+    if rc != 0:
+        raise KmerGMAError(rc, (lib.kgma_last_error(handle) or b"").decode() or "kgma_replay failed")
+    return ScanOutput(lib, res)
 
 
 def _emit(genome: Genome, out: ScanOutput, cluster: bool, resultVec, hit_loci_vec, align_vec, with_genome_pos=True):

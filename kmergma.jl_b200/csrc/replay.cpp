@@ -140,7 +140,7 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
                 h.align_score = ares[p.req].score; h.cigar_off = ares[p.req].cig_off; h.cigar_len = ares[p.req].cig_len;
             }
         }
-        ctx->stats.n_align = (int64_t)reqs.size();
+        if (ctx) ctx->stats.n_align = (int64_t)reqs.size();
         return KGMA_OK;
     }
 
@@ -165,7 +165,7 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
             if (rc) return rc;
         }
     }
-    ctx->stats.n_align = (int64_t)reqs.size();
+    if (ctx) ctx->stats.n_align = (int64_t)reqs.size();
     int64_t genome_pos = 0;
     struct Ev { int64_t end_step; int q; size_t run; };
     std::vector<Ev> evs;

@@ -812,7 +812,9 @@ int kgma_replay(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int
                 const kgma_scan_params *params, const kgma_run *runs, int64_t n_runs,
                 const int64_t *first_window_D, kgma_result **out)
 {
-    if (!ctx || !g || !params || !out || (n_runs && !runs) || !first_window_D) return KGMA_E_ARG;
+    // ctx may be NULL for a host-only replay (no KGMA_F_ALIGN): merging and replaying run lists needs no device
+    if (!g || !params || !out || (n_runs && !runs) || !first_window_D) return KGMA_E_ARG;
+    if (!ctx && (params->flags & KGMA_F_ALIGN)) return KGMA_E_ARG;
     ScanPlan pl;
     int rc = make_plan(ctx, g, profiles, n_profiles, *params, pl);
     if (rc) return rc;
