@@ -8,8 +8,8 @@ single profile, k = 6, thr = 30, buffer 50, gap (-69,-1), do_align = true).
 One step = one complete findGenes scan of the genome (prefilter + count-table kernel + run compaction +
 host replay + batched extension).  For N > 1 (torchrun, one rank per GPU) the packed genome is cut into N
 equal shards with a window-length halo, each rank scans its shard and ships its run summaries (KBs) to
-rank 0 over a gloo side group, rank 0 replays and extends: strong scaling of the 3.1 Gb job, no data-path
-collective.
+rank 0 over a gloo side group, rank 0 replays and extends (reported under "strong").  The headline for N > 1
+is weak scaling: every rank scans its own 3.1 Gb genome, no communication on the path.
 
   value : genome resident in HBM when the timed region starts (tier T0+host replay)
   e2e   : the same call from pinned pre-packed HOST buffers: H2D of the 2-bit genome + kernels + D2H of
@@ -223,7 +223,7 @@ def run_reference(args):
     sample = "%d chunks of %d Mb of the same synthetic genome per step, one oracle task per chunk on %d threads" % (T, chunk // 1_000_000, T)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "findGenes, 3.1 Gb synthetic genome (24 contigs), single profile k=6, thr=30 (BASELINE configs[1])",
                    "note": "Julia is not installed: the reference's algorithm is timed as the C oracle port (oracle/kmergma_oracle.c), "
@@ -250,20 +250,18 @@ def run_ours(args):
     side = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        side = dist.new_group(backend="gloo")       # host-side plumbing for the KB-sized run lists
+        side = dist.new_group(backend="gloo")       # host-side plumbing for the KB-sized run lists (strong mode only)
 
     ctx = K.Context(local)
     lens = contig_lengths(args.scale)
     plants = plant_list(lens, n_plants=max(10, int(N_PLANTS * args.scale)))
-    t_setup = time.perf_counter()
-    g = K.Genome.synth(lens, seed=SEED, n_run_len=N_RUN, centromere_len=CENTROMERE, ctx=ctx)
-    for (r, pos, s) in plants:
-        g.put_seq(r, pos, s)
-    total = g.total_len
     RV, ws, cons = K.gen_ref_ws_cons(TF, KMER)
-    t_setup = time.perf_counter() - t_setup
-    shard = (rank, world)
-    base_flags = L.F_ALIGN
+
+    def make_genome(seed):
+        g = K.Genome.synth(lens, seed=seed, n_run_len=N_RUN, centromere_len=CENTROMERE, ctx=ctx)
+        for (r, pos, s) in plants:
+            g.put_seq(r, pos, s)
+        return g
 
     def barrier():
         torch.cuda.synchronize()
@@ -271,42 +269,47 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    agg = {"launches": 0, "h2d": 0, "d2h": 0, "filter_ms": 0.0, "exact_ms": 0.0, "align_ms": 0.0, "dev_ms": 0.0,
-           "h2d_ms": 0.0, "blocks": 0, "flagged": 0, "exact_windows": 0}
+    KEYS = ("launches", "h2d_bytes", "d2h_bytes", "filter_ms", "exact_ms", "align_ms", "total_ms", "h2d_ms", "blocks_total",
+            "blocks_flagged", "exact_windows", "wall_ms", "host_setup_ms", "host_cand_ms", "host_replay_ms", "n_runs")
 
-    def acc():
-        st = ctx.stats()
-        agg["launches"] += st["launches"]; agg["h2d"] += st["h2d_bytes"]; agg["d2h"] += st["d2h_bytes"]
-        agg["filter_ms"] += st["filter_ms"]; agg["exact_ms"] += st["exact_ms"]; agg["align_ms"] += st["align_ms"]
-        agg["dev_ms"] += st["total_ms"] + st["align_ms"]; agg["h2d_ms"] += st["h2d_ms"]
-        agg["blocks"] += st["blocks_total"]; agg["flagged"] += st["blocks_flagged"]; agg["exact_windows"] += st["exact_windows"]
+    def measure(g, sharded: bool, resident: bool):
+        """W warm-up + K timed steps; returns (seconds max over ranks, last result, clocks, per-step stats of this rank)"""
+        agg = {k_: 0.0 for k_ in KEYS}
+        fl = L.F_ALIGN | (L.F_RESIDENT if resident else 0)
 
-    def step(resident: bool):
-        fl = base_flags | (L.F_RESIDENT if resident else 0)
-        if world == 1:
-            out = K.scan_raw(g, [RV], [ws], [cons], [THR], KMER, L.MODE_SINGLE, BUFF, fl, GAP_OPEN, GAP_EXT, ctx=ctx)
-            acc()
+        def acc(st, base=None):
+            for k_ in KEYS:
+                agg[k_] += st[k_] - (base[k_] if base else 0)
+
+        def step(count: bool):
+            if not sharded:
+                out = K.scan_raw(g, [RV], [ws], [cons], [THR], KMER, L.MODE_SINGLE, BUFF, fl, GAP_OPEN, GAP_EXT, ctx=ctx)
+                if count:
+                    acc(ctx.stats())
+                return out
+            part = K.scan_raw(g, [RV], [ws], [cons], [THR], KMER, L.MODE_SINGLE, BUFF, fl & ~L.F_ALIGN, GAP_OPEN, GAP_EXT,
+                              ctx=ctx, runs_only=True, shard=(rank, world))
+            st1 = ctx.stats()
+            if count:
+                acc(st1)
+            payload = (part.runs.tobytes(), part.first_D.tobytes())
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object(payload, gathered, dst=0, group=side)
+            if rank != 0:
+                return None
+            runs = np.concatenate([np.frombuffer(p_[0], dtype=np.uint8) for p_ in gathered])
+            firsts = np.max(np.stack([np.frombuffer(p_[1], dtype=np.int64) for p_ in gathered]), axis=0)
+            out = K.replay_raw(g, [RV], [ws], [cons], [THR], KMER, L.MODE_SINGLE, BUFF, fl, GAP_OPEN, GAP_EXT, runs, firsts, ctx=ctx)
+            if count:
+                st2 = ctx.stats()                        # replay adds the extension's launches / bytes to the scan's counters
+                for k_ in ("launches", "h2d_bytes", "d2h_bytes", "align_ms"):
+                    agg[k_] += st2[k_] - st1[k_]
             return out
-        part = K.scan_raw(g, [RV], [ws], [cons], [THR], KMER, L.MODE_SINGLE, BUFF, fl & ~L.F_ALIGN, GAP_OPEN, GAP_EXT,
-                          ctx=ctx, runs_only=True, shard=shard)
-        acc()
-        st1 = ctx.stats()
-        payload = (part.runs.tobytes(), part.first_D.tobytes())
-        gathered = [None] * world if rank == 0 else None
-        dist.gather_object(payload, gathered, dst=0, group=side)
-        if rank != 0:
-            return None
-        runs = np.concatenate([np.frombuffer(p[0], dtype=np.uint8) for p in gathered])
-        firsts = np.max(np.stack([np.frombuffer(p[1], dtype=np.int64) for p in gathered]), axis=0)
-        out = K.replay_raw(g, [RV], [ws], [cons], [THR], KMER, L.MODE_SINGLE, BUFF, fl, GAP_OPEN, GAP_EXT, runs, firsts, ctx=ctx)
-        st2 = ctx.stats()                            # replay adds the extension launches to the scan's counters
-        agg["launches"] += st2["launches"] - st1["launches"]
-        agg["align_ms"] += st2["align_ms"]; agg["dev_ms"] += st2["align_ms"]
-        return out
 
-    def timed(resident: bool):
-        for k_ in agg:
-            agg[k_] = 0
+        if resident:
+            g.make_resident(ctx)
+        for _ in range(args.warmup):
+            step(False)
         stop, samples = threading.Event(), []
         th = threading.Thread(target=clocks_sampler, args=(local, stop, samples), daemon=True)
         barrier()
@@ -314,31 +317,46 @@ def run_ours(args):
         t0 = time.perf_counter()
         out = None
         for _ in range(args.steps):
-            out = step(resident)
+            out = step(True)
         barrier()
         dt = time.perf_counter() - t0
         stop.set(); th.join()
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), out, summarise_clocks(samples), dict(agg)
+        return float(t.item()), out, summarise_clocks(samples), {k_: v / args.steps for k_, v in agg.items()}
 
-    # ---- value: genome resident in HBM
-    g.make_resident(ctx)
-    for _ in range(args.warmup):
-        step(True)
-    dt_res, out_res, clocks, a_res = timed(True)
-    # ---- e2e: pinned host -> device inside the timed region
-    for _ in range(args.warmup):
-        step(False)
-    dt_e2e, out_e2e, clocks_e2e, a_e2e = timed(False)
+    def allsum(vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return [float(x) for x in t.tolist()]
 
+    # ---- headline (weak): every rank scans its own 3.1 Gb genome end to end, no communication on the path
+    t_setup = time.perf_counter()
+    g = make_genome(SEED + rank)
+    t_setup = time.perf_counter() - t_setup
+    total = g.total_len
+    dt_res, out_res, clocks, a_res = measure(g, False, True)
+    dt_e2e, out_e2e, clocks_e2e, a_e2e = measure(g, False, False)
+    launches_all, h2d_all, d2h_all, nhits_all = allsum([a_res["launches"] * args.steps, a_e2e["h2d_bytes"], a_e2e["d2h_bytes"], len(out_res.hits)])
+    same = np.array_equal(out_res.hits[["record", "first", "last", "D"]], out_e2e.hits[["record", "first", "last", "D"]])
+
+    # ---- secondary (strong, N > 1): ONE 3.1 Gb genome cut into N shards with halos, run lists merged on rank 0
+    strong = None
     if world > 1:
-        tl = torch.tensor([a_res["launches"], a_e2e["h2d"], a_e2e["d2h"]], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tl)
-        launches_all, h2d_all, d2h_all = [float(x) for x in tl.tolist()]
-    else:
-        launches_all, h2d_all, d2h_all = a_res["launches"], a_e2e["h2d"], a_e2e["d2h"]
+        gs = make_genome(SEED) if rank != 0 else g
+        sdt_res, sout, _, sa_res = measure(gs, True, True)
+        sdt_e2e, sout2, _, sa_e2e = measure(gs, True, False)
+        sh2d, = allsum([sa_e2e["h2d_bytes"]])
+        if rank == 0:
+            ok = np.array_equal(sout.hits[["record", "first", "last", "D"]], out_res.hits[["record", "first", "last", "D"]])
+            strong = {"scaling": "strong", "workload": "one %.2f Gb genome cut into %d shards with window halo; run lists gathered to rank 0, "
+                                                       "replayed and extended there" % (total / 1e9, world),
+                      "value": total * args.steps / sdt_res / 1e6, "ms_per_step": sdt_res / args.steps * 1e3,
+                      "e2e": {"value": total * args.steps / sdt_e2e / 1e6, "ms_per_step": sdt_e2e / args.steps * 1e3, "h2d_bytes_per_step": sh2d},
+                      "unit": UNIT, "hits_equal_unsharded": bool(ok), "hits_per_step": int(len(sout.hits))}
 
     if rank == 0:
         peaks = {}
@@ -347,37 +365,39 @@ def run_ours(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        filt_ms = a_res["filter_ms"] / args.steps
-        alg_bytes = a_res["blocks"] / args.steps * 64 * 0.25
+        filt_ms = a_res["filter_ms"]
+        alg_bytes = a_res["blocks_total"] * 64 * 0.25
         achieved = alg_bytes / (filt_ms * 1e-3) / 1e9 if filt_ms > 0 else 0.0
-        hits = out_res.hits
-        same = [(h.record, h.first, h.last, h.D) for h in hits] == [(h.record, h.first, h.last, h.D) for h in out_e2e.hits]
         line = {
-            "metric": METRIC, "value": total * args.steps / dt_res / 1e6, "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": world * total * args.steps / dt_res / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt_res / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": "findGenes, %.2f Gb synthetic genome (24 contigs, N runs, %d planted IGHV homologues), single profile "
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "findGenes, one %.2f Gb synthetic genome per GPU (24 contigs, N runs, %d planted IGHV homologues), single profile "
                                    "k=6 ws=%d N=84, thr=30, buffer 50, gap (-69,-1), do_align=true (BASELINE configs[1])" % (total / 1e9, len(plants), ws),
-                       "parallelism": "genome sharded x%d with window halo, host merge of run lists" % world,
+                       "parallelism": "%d independent genome(s), one per GPU, no collective on the path%s" % (world, "; the sharded single-genome run is under 'strong'" if world > 1 else ""),
                        "l2": "input (%.0f MB packed) larger than L2; no flush needed" % (total / 4e6),
                        "timing": "host clock around blocking C-ABI calls bracketed by device sync + barrier, max over ranks "
                                  "(>= the CUDA-event device time reported in device_ms_per_step)"},
-            "e2e": {"value": total * args.steps / dt_e2e / 1e6, "unit": UNIT, "ms_per_step": dt_e2e / args.steps * 1e3,
-                    "h2d_bytes_per_step": h2d_all / args.steps, "d2h_bytes_per_step": d2h_all / args.steps},
+            "e2e": {"value": world * total * args.steps / dt_e2e / 1e6, "unit": UNIT, "ms_per_step": dt_e2e / args.steps * 1e3,
+                    "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all},
             "gpu_launches": int(launches_all),
-            "device_ms_per_step": {"rank0_total": a_res["dev_ms"] / args.steps, "prefilter": filt_ms,
-                                   "count_table": a_res["exact_ms"] / args.steps, "extension": a_res["align_ms"] / args.steps,
-                                   "e2e_h2d": a_e2e["h2d_ms"] / args.steps},
+            "device_ms_per_step": {"prefilter": filt_ms, "count_table": a_res["exact_ms"], "extension": a_res["align_ms"],
+                                   "scan_total": a_res["total_ms"], "e2e_h2d": a_e2e["h2d_ms"]},
+            "host_ms_per_step": {"call_wall": a_res["wall_ms"], "setup": a_res["host_setup_ms"], "results": a_res["host_cand_ms"],
+                                 "replay": a_res["host_replay_ms"], "e2e_call_wall": a_e2e["wall_ms"]},
             "roofline": {"bound": "hbm", "kernel": "kgma_prefilter<6>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": 784.9e6 if args.scale == 1.0 else None,
+                         "traffic_source": "ncu --set full, profiles/r1_prefilter_ncu_full_summary.csv (dram read+write per launch)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "algorithmic_bytes_per_launch": alg_bytes},
             "clocks": clocks, "clocks_e2e": clocks_e2e,
-            "hits_per_step": len(hits), "hits_equal_resident_vs_e2e": bool(same),
-            "prefilter_blocks_flagged_per_step": a_res["flagged"] / args.steps,
-            "count_table_windows_per_step": a_res["exact_windows"] / args.steps,
+            "hits_per_step": int(nhits_all), "runs_per_step": a_res["n_runs"], "hits_equal_resident_vs_e2e": bool(same),
+            "prefilter_blocks_flagged_per_step": a_res["blocks_flagged"],
+            "count_table_windows_per_step": a_res["exact_windows"],
             "setup_s": t_setup, "readme_julia_mbs": 40,
         }
+        if strong:
+            line["strong"] = strong
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         print(json.dumps(line))

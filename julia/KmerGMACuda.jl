@@ -1,0 +1,151 @@
+# KmerGMACuda.jl — the binding a KmerGMA.jl maintainer would add so that `ac_gma_testing!`, `Omn_KmerGMA!` and
+# `exactMatch(query, path)` run on libkmergma_cuda (include/kmergma.h) while `findGenes(...)`,
+# `findGenes_cluster_mode(...)` keep their keyword arguments and `Any[hit_vector, ...]` return value
+# (src/API.jl:60-104, :161-226).  NOT EXECUTED in this repository's CI: Julia is not installed in the build
+# image; the same call sequence is exercised through ctypes by kmergma.jl_b200/__init__.py and tests/.
+#
+# Drop-in use:  include("KmerGMACuda.jl") after `using KmerGMA`; the methods below replace the three operators.
+module KmerGMACuda
+
+using KmerGMA, FASTX, BioSequences
+
+const LIB = get(ENV, "KMERGMA_CUDA_LIB", "libkmergma_cuda")
+
+# ---- mirrors of the POD structs in include/kmergma.h -------------------------------------------------------
+struct KgmaProfile                  # kgma_profile
+    k::Int32; n_refs::Int32; window::Int64
+    S::Ptr{Int32}; consensus::Ptr{UInt8}; consensus_len::Int32
+    thr::Float64
+end
+struct KgmaScanParams               # kgma_scan_params
+    mode::Int32; flags::UInt32; buff::Int64
+    gap_open::Int32; gap_extend::Int32
+    shard_index::Int32; shard_count::Int32; only_record::Int32; reserved::Int32
+end
+struct KgmaHit                      # kgma_hit
+    record::Int32; profile::Int32; cmi::Int64; first::Int64; last::Int64; genome_pos::Int64
+    D::Int64; dist::Float64; align_score::Int64
+    flags::UInt32; cigar_off::UInt32; cigar_len::UInt32; reserved::UInt32
+end
+struct KgmaMatch; record::Int32; reserved::Int32; first::Int64; last::Int64; end
+
+const F_ALIGN, F_DENSE, F_WANT_DISTS, F_WANT_CIGARS = UInt32(1), UInt32(2), UInt32(4), UInt32(8)
+
+check(ctx, rc) = rc == 0 || error(unsafe_string(ccall((:kgma_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx)))
+
+function with_ctx(f; device::Int = 0)
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:kgma_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, ctx)
+    rc == 0 || error(unsafe_string(ccall((:kgma_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))   # no GPU => error, never a CPU fallback
+    try f(ctx[]) finally ccall((:kgma_destroy, LIB), Cvoid, (Ptr{Cvoid},), ctx[]) end
+end
+
+# FASTX parses; the 4-bit BioSequences words go over as they are (kgma_genome_append_bio4), no per-base Dict lookup.
+function load_genome(path::String)
+    g = Ref{Ptr{Cvoid}}(C_NULL)
+    ccall((:kgma_genome_create, LIB), Cint, (Ref{Ptr{Cvoid}},), g)
+    records = FASTA.Record[]; seqs = KmerGMA.Seq[]
+    open(FASTA.Reader, path) do reader
+        for record in reader
+            seq = getSeq(record)
+            GC.@preserve seq begin
+                rc = ccall((:kgma_genome_append_bio4, LIB), Cint, (Ptr{Cvoid}, Cstring, Cstring, Ptr{UInt64}, Int64),
+                           g[], FASTA.identifier(record), FASTA.description(record), pointer(seq.data), length(seq))
+                rc == 0 || error("kgma_genome_append_bio4 failed ($rc)")
+            end
+            push!(records, record); push!(seqs, seq)
+        end
+    end
+    ccall((:kgma_genome_seal, LIB), Cint, (Ptr{Cvoid},), g[])
+    return g[], records, seqs
+end
+
+# refVec = S .* (1/N) (gen_ref_ws_cons) or S ./ N (cluster_ref_API): recover the integers the device needs
+function ints_of(refVec::Vector{Float64})
+    S = Vector{Int32}(undef, length(refVec)); n = Ref{Int32}(0)
+    rc = ccall((:kgma_profile_from_kfv, LIB), Cint, (Ptr{Float64}, Int64, Int32, Ptr{Int32}, Ref{Int32}), refVec, length(refVec), 0, S, n)
+    rc == 0 || error("refVec is not (k-mer count sums)/(family size)")
+    return S, n[]
+end
+
+function scan!(resultVec, hit_loci_vec, dist_vecs, genome_path, refVecs, windowsizes, consensus_seqs, thrs, k, mode, buff,
+               flags, gap_open, gap_extend; cluster::Bool, get_hit_loci::Bool)
+    with_ctx() do ctx
+        g, records, seqs = load_genome(genome_path)
+        try
+            Ss = [ints_of(Vector{Float64}(rv)) for rv in refVecs]
+            cons = [Vector{UInt8}(string(c)) for c in consensus_seqs]
+            GC.@preserve Ss cons begin
+                profs = [KgmaProfile(k, Ss[i][2], windowsizes[i], pointer(Ss[i][1]), pointer(cons[i]), length(cons[i]), Float64(thrs[i])) for i in eachindex(Ss)]
+                P = Ref(KgmaScanParams(mode, flags, buff, gap_open, gap_extend, 0, 1, -1, 0))
+                res = Ref{Ptr{Cvoid}}(C_NULL)
+                check(ctx, ccall((:kgma_scan, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{KgmaProfile}, Cint, Ref{KgmaScanParams}, Ref{Ptr{Cvoid}}),
+                                 ctx, g, profs, length(profs), P, res))
+                n = ccall((:kgma_result_n_hits, LIB), Int64, (Ptr{Cvoid},), res[])
+                hits = unsafe_wrap(Array, ccall((:kgma_result_hits, LIB), Ptr{KgmaHit}, (Ptr{Cvoid},), res[]), n)
+                for h in hits
+                    record, seq = records[h.record + 1], seqs[h.record + 1]
+                    rng = h.first:h.last
+                    if cluster      # src/OmnGenomeMiner.jl:141-149
+                        push!(resultVec, FASTA.Record(FASTA.identifier(record) * " | Dist = " * string(round(h.dist, digits = 2)) *
+                              " | KFV = $(h.profile) | MatchPos = $rng | GenomePos = $(h.genome_pos) | Len = " * string(length(rng)), view(seq, rng)))
+                    else            # src/Alignment.jl:57-81 append_hit!
+                        KmerGMA.append_hit!(resultVec, record, seq, false, 0, h.dist, rng, h.genome_pos)
+                    end
+                    get_hit_loci && push!(hit_loci_vec, h.first + h.genome_pos)
+                end
+                if (flags & F_WANT_DISTS) != 0
+                    for q in eachindex(dist_vecs)
+                        nd = ccall((:kgma_result_n_dists, LIB), Int64, (Ptr{Cvoid}, Cint), res[], q - 1)
+                        append!(dist_vecs[q], unsafe_wrap(Array, ccall((:kgma_result_dists, LIB), Ptr{Float64}, (Ptr{Cvoid}, Cint), res[], q - 1), nd))
+                    end
+                end
+                ccall((:kgma_result_free, LIB), Cvoid, (Ptr{Cvoid},), res[])
+            end
+        finally
+            ccall((:kgma_genome_destroy, LIB), Cvoid, (Ptr{Cvoid},), g)
+        end
+    end
+end
+
+# ---- the three operators, same keyword arguments as the reference (unused ones accepted and ignored) -------
+function KmerGMA.ac_gma_testing!(; genome_path::String, refVec, consensus_refseq, k::Int64 = 6, windowsize::Int64 = 289,
+        thr = 33.5, buff::Int64 = 50, mask = nothing, Nt_bits = nothing, ScaleFactor = nothing, do_align::Bool = true,
+        result_align_vec = [], gap_open_score::Int = -69, gap_extend_score::Int = -1, do_return_dists::Bool = false,
+        dist_vec = Float64[], do_return_align::Bool = false, get_hit_loci::Bool = false, hit_loci_vec = Int[],
+        resultVec = FASTA.Record[])
+    flags = (do_align ? F_ALIGN : UInt32(0)) | (do_return_dists ? F_WANT_DISTS : UInt32(0)) | ((do_align && do_return_align) ? F_WANT_CIGARS : UInt32(0))
+    scan!(resultVec, hit_loci_vec, [dist_vec], genome_path, [collect(refVec)], [windowsize], [consensus_refseq], [thr], k, 0, buff,
+          flags, gap_open_score, gap_extend_score; cluster = false, get_hit_loci = get_hit_loci)
+end
+
+function KmerGMA.Omn_KmerGMA!(; genome_path::String, refVecs, windowsizes, consensus_seqs, resultVec, k::Int = 6, ScaleFactor = nothing,
+        mask = nothing, thr_vec = Float64[35, 31, 38, 34, 27, 27], buff::Int = 50, Nt_bits = nothing, align_hits::Bool = true,
+        align_vec = [], gap_open_score::Int = -200, gap_extend_score::Int = -1, genome_pos::Int = 0, get_hit_loci::Bool = false,
+        hit_loci_vec = Int[], get_aligns::Bool = false, do_return_dists::Bool = false, dist_vec_vec = [Float64[] for _ in windowsizes])
+    flags = (align_hits ? F_ALIGN : UInt32(0)) | (do_return_dists ? F_WANT_DISTS : UInt32(0))
+    scan!(resultVec, hit_loci_vec, dist_vec_vec, genome_path, refVecs, windowsizes, consensus_seqs, thr_vec, k, 1, buff,
+          flags, gap_open_score, gap_extend_score; cluster = true, get_hit_loci = get_hit_loci)
+end
+
+function KmerGMA.exactMatch(query, genome_path::String; overlap::Bool = true)
+    with_ctx() do ctx
+        g, records, _ = load_genome(genome_path)
+        try
+            q = Vector{UInt8}(string(query isa FASTA.Record ? getSeq(query) : query))
+            out = Ref{Ptr{KgmaMatch}}(C_NULL); n = Ref{Int64}(0)
+            check(ctx, ccall((:kgma_exact_match, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt8}, Int64, Cint, UInt32, Ref{Ptr{KgmaMatch}}, Ref{Int64}),
+                             ctx, g, q, length(q), overlap, 0, out, n))
+            identify = Dict{String, Vector{UnitRange{Int64}}}()
+            for m in unsafe_wrap(Array, out[], n[])
+                push!(get!(identify, FASTA.identifier(records[m.record + 1]), UnitRange{Int64}[]), m.first:m.last)
+            end
+            n[] > 0 && ccall((:kgma_free, LIB), Cvoid, (Ptr{Cvoid},), out[])
+            return isempty(identify) ? "no match" : identify      # src/ExactMatch.jl:116-120
+        finally
+            ccall((:kgma_genome_destroy, LIB), Cvoid, (Ptr{Cvoid},), g)
+        end
+    end
+end
+
+end # module
