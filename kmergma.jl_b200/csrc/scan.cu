@@ -39,6 +39,7 @@ struct FilterArgs {
     uint32_t *cand;             // out: flagged block ids
     uint32_t  cand_cap;
     uint32_t *cand_count;       // out: number flagged (may exceed cap -> caller falls back to dense)
+    uint32_t *bitmap;           // out: one bit per block, set for flagged blocks (lets the count-table kernel join neighbours)
 };
 
 template <int K>
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(1024, 1) kgma_prefilter(FilterArgs a)
             if (flag) {
                 uint32_t pos = base + __popc(bal & ((1u << lane) - 1));
                 if (pos < a.cand_cap) a.cand[pos] = (uint32_t)tgt;
+                atomicOr(a.bitmap + (tgt >> 5), 1u << (tgt & 31));
             }
         }
         cur = nxt; nxt = nx2;
@@ -142,8 +144,10 @@ struct ProfDev { long long N2, twoN, sumS2, T, Tlo, Thi; int nk, pad; };
 struct EvalArgs {
     const uint32_t *seq;
     const int32_t  *S;              // [C][4^k] reversed-index profile sums
-    const uint32_t *cand;           // candidate mode: flagged block ids (null = dense mode)
-    const uint32_t *cand_count; uint32_t cand_cap;
+    const uint32_t *cand;           // candidate mode: flagged block ids (null = dense mode); the first n_seed entries are
+    const uint32_t *cand_count; uint32_t cand_cap;   // record-start blocks of which only window 0 is evaluated
+    const uint32_t *bitmap; uint32_t n_seed;
+    unsigned long long *next_item;  // [C] dynamic work counters (spans differ a lot in length: static striding leaves warps idle)
     long long n_items;              // dense mode: number of implicit items
     const RecDev *recs; int nrec;
     int C, k, span;                 // span: windows per dense item
@@ -187,13 +191,12 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
     int32_t *sS = reinterpret_cast<int32_t *>(smem_raw);
     const size_t per_warp = (size_t)nb * 2 + 64 * 2 * 2 + 64 * 8;
     unsigned char *wb = smem_raw + (size_t)nb * 4 + (size_t)wid * per_warp;
-    long long *dw = reinterpret_cast<long long *>(wb);                        // [64] D of the current 64 windows
+    uint32_t *qw = reinterpret_cast<uint32_t *>(wb), *aw = qw + 64;           // [64] Q and A of the current 64 windows
     uint16_t *tab = reinterpret_cast<uint16_t *>(wb + 64 * 8);                // [4^k] counts
     uint16_t *lk = tab + nb, *rk = lk + 64;                                  // leaving / entering k-mers of 64 steps
     for (int i = lane; i < nb / 2; i += 32) reinterpret_cast<uint32_t *>(tab)[i] = 0;
     if (nb < 2 && lane == 0) tab[0] = 0;
 
-    const long long gwarp = (long long)blockIdx.x * nw + wid, nwarps = (long long)gridDim.x * nw;
     long long nitems = a.n_items;
     if (a.cand) { uint32_t c = *a.cand_count; nitems = c < a.cand_cap ? c : a.cand_cap; }
 
@@ -203,20 +206,35 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
         __syncthreads();
         const ProfDev P = a.prof[q];
         const int nk = P.nk;
-        for (long long item = gwarp; item < nitems; item += nwarps) {
+        for (;;) {
+            long long item = 0;
+            if (lane == 0) item = (long long)atomicAdd(a.next_item + q, 1ull);
+            item = __shfl_sync(FULL, item, 0);
+            if (item >= nitems) break;
             // ---- locate the span: record r, first window w0 (== loop step), n windows
             int r; long long w0, n;
             if (a.cand) {
-                const long long gp = (long long)a.cand[item] * FBLOCK;
+                const long long b = (long long)a.cand[item];
+                const long long gp = b * FBLOCK;
                 int lo = 0, hi = a.nrec;                                      // last record with off <= gp
                 while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (a.recs[mid].off <= gp) lo = mid; else hi = mid; }
                 r = lo;
                 const RecDev R = a.recs[r];
                 const long long b0 = gp - R.off;
                 if (b0 < 0) continue;
-                w0 = b0 > R.w_begin ? b0 : R.w_begin;
-                long long we = b0 + FBLOCK < R.w_end ? b0 + FBLOCK : R.w_end;
-                n = we - w0;
+                if (item < (long long)a.n_seed) { w0 = 0; n = (b0 == 0 && R.w_begin == 0 && R.w_end > 0) ? 1 : 0; }   // window 0 only
+                else {
+                    // consecutive flagged blocks of one record are evaluated as ONE span by the warp that owns their head;
+                    // spans are also cut every 8 blocks so that long flagged stretches still spread over many warps
+                    const bool prev_same_rec = b0 >= FBLOCK;
+                    const bool prev_set = b > 0 && ((a.bitmap[(b - 1) >> 5] >> ((b - 1) & 31)) & 1u);
+                    if (prev_set && prev_same_rec && (b & 7) != 0) continue;
+                    long long e = b;
+                    while (((e + 1) & 7) != 0 && ((a.bitmap[(e + 1) >> 5] >> ((e + 1) & 31)) & 1u)) e++;
+                    w0 = b0 > R.w_begin ? b0 : R.w_begin;
+                    const long long we = (e + 1) * FBLOCK - R.off < R.w_end ? (e + 1) * FBLOCK - R.off : R.w_end;
+                    n = we - w0;
+                }
             } else {
                 int lo = 0, hi = a.nrec;                                      // last record with item_base <= item
                 while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (a.recs[mid].item_base <= item) lo = mid; else hi = mid; }
@@ -235,13 +253,15 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
                 atomicAdd(reinterpret_cast<uint32_t *>(tab) + (km >> 1), 1u << ((km & 1) * 16));
             }
             __syncwarp();
-            long long Q = 0, A = 0;
+            uint32_t Q = 0, A = 0;                                            // < 2^32: nk <= 65535, nk * max S checked on the host
             for (int p = lane; p < nk; p += 32) {
                 const uint32_t km = kmer_at(a.seq, gpos + p, kmask);
-                Q += tab[km]; A += sS[km];
+                Q += tab[km]; A += (uint32_t)sS[km];
             }
-            Q = warp_sum_ll(Q); A = warp_sum_ll(A);
+#pragma unroll
+            for (int d = 16; d; d >>= 1) { Q += __shfl_xor_sync(FULL, Q, d); A += __shfl_xor_sync(FULL, A, d); }
 
+            bool c_in = false; long long c_tf = 0, c_ta = 0, c_dmin = 0; uint32_t c_fl = 0;   // run carried across 64-window batches
             for (long long s0 = 0; s0 < n; s0 += 64) {
                 const int m = (int)(n - s0 < 64 ? n - s0 : 64);
                 for (int j = lane; j < m; j += 32) {                          // step j: window s0+j -> s0+j+1
@@ -252,11 +272,11 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
                 if (lane == 0) {
                     uint32_t l = lk[0], rr = rk[0];
                     for (int j = 0; j < m; j++) {
-                        dw[j] = P.N2 * Q - P.twoN * A + P.sumS2;
+                        qw[j] = Q; aw[j] = A;
                         const uint32_t ln = lk[(j + 1) & 63], rn = rk[(j + 1) & 63];   // software-pipelined k-mer fetch
                         if (l != rr && s0 + j + 1 < n) {                      // GenomeMiner.jl:69 `if left_ind != right_ind`
-                            const int cl = tab[l], cr = tab[rr];
-                            Q += 2 * (cr - cl) + 2; A += sS[rr] - sS[l];
+                            const uint32_t cl = tab[l], cr = tab[rr];
+                            Q += 2u * (cr - cl) + 2u; A += (uint32_t)(sS[rr] - sS[l]);
                             tab[l] = (uint16_t)(cl - 1); tab[rr] = (uint16_t)(cr + 1);
                         }
                         l = ln; rr = rn;
@@ -270,7 +290,7 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
                     const int wi = lane + 32 * h;
                     const bool valid = wi < m;
                     const long long t = w0 + s0 + wi;
-                    const long long D = valid ? dw[wi] : 0;
+                    const long long D = valid ? P.N2 * (long long)qw[wi] - P.twoN * (long long)aw[wi] + P.sumS2 : 0;
                     Dm[h] = D;
                     if (valid && t == 0) a.first_D[(size_t)q * a.nrec + r] = D;      // first window: never compared with thr
                     const bool inloop = valid && t >= 1;
@@ -280,6 +300,11 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
                 }
                 const unsigned long long below = (unsigned long long)bm[0] | ((unsigned long long)bm[1] << 32);
                 const unsigned long long near = (unsigned long long)nm[0] | ((unsigned long long)nm[1] << 32);
+                const bool more = s0 + 64 < n;                                 // another batch of this span follows
+                if (c_in && !(below & 1ull)) {                                 // the carried run ended with the previous batch
+                    if (lane == 0) emit_run(a, r, q, c_tf, w0 + s0 - 1, c_ta, c_dmin, c_fl);
+                    c_in = false;
+                }
                 unsigned long long rem = below;
                 while (rem) {                                                  // maximal stretches of D < T inside these 64 windows
                     const int b0 = __ffsll((long long)rem) - 1;
@@ -304,17 +329,23 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
                         const int wi = lane + 32 * h;
                         ties += __popc(__ballot_sync(FULL, wi >= b0 && wi <= b1 && Dm[h] == bestD));
                     }
-                    if (lane == 0) {
-                        uint32_t fl = (ties > 1 ? KGMA_HIT_ARGMIN_TIE : 0u) | ((near & stretch) ? KGMA_HIT_NEAR_THR : 0u) |
-                                      (b0 == 0 ? KGMA_RUN_OPEN_LEFT : 0u) | (b1 == m - 1 ? KGMA_RUN_OPEN_RIGHT : 0u);
-                        emit_run(a, r, q, w0 + s0 + b0, w0 + s0 + b1, w0 + s0 + bestI, bestD, fl);
-                    }
+                    uint32_t fl = (ties > 1 ? KGMA_HIT_ARGMIN_TIE : 0u) | ((near & stretch) ? KGMA_HIT_NEAR_THR : 0u);
+                    long long tf = w0 + s0 + b0, ta = w0 + s0 + bestI, dmin = bestD;
+                    if (c_in && b0 == 0) {                                     // continues the run carried over from the previous batch
+                        fl |= c_fl;
+                        if (c_dmin < dmin) { dmin = c_dmin; ta = c_ta; fl = (fl & ~KGMA_HIT_ARGMIN_TIE) | (c_fl & KGMA_HIT_ARGMIN_TIE); }
+                        else if (c_dmin == dmin) { ta = c_ta; fl |= KGMA_HIT_ARGMIN_TIE; }
+                        tf = c_tf; c_in = false;
+                    } else if (w0 + s0 + b0 == w0 || (w0 == 0 && s0 == 0 && b0 == 1)) fl |= KGMA_RUN_OPEN_LEFT;
+                    if (b1 == m - 1 && more) { c_in = true; c_tf = tf; c_ta = ta; c_dmin = dmin; c_fl = fl; }   // may continue
+                    else if (lane == 0) emit_run(a, r, q, tf, w0 + s0 + b1, ta, dmin, fl | (b1 == m - 1 ? KGMA_RUN_OPEN_RIGHT : 0u));
                     rem &= ~stretch;
                 }
                 unsigned long long mk = near & ~below;                          // d >= thr inside the 1e-9 band: reported, never replayed
                 while (mk) {
                     const int i = __ffsll((long long)mk) - 1; mk &= mk - 1;
-                    if (lane == 0) emit_run(a, r, q, w0 + s0 + i, w0 + s0 + i, w0 + s0 + i, dw[i], KGMA_RUN_MARKER | KGMA_HIT_NEAR_THR);
+                    if (lane == 0) emit_run(a, r, q, w0 + s0 + i, w0 + s0 + i, w0 + s0 + i,
+                                            P.N2 * (long long)qw[i] - P.twoN * (long long)aw[i] + P.sumS2, KGMA_RUN_MARKER | KGMA_HIT_NEAR_THR);
                 }
                 __syncwarp();
             }
@@ -415,6 +446,11 @@ int build_proftab(kgma_ctx *ctx, const kgma_profile &p, ProfTab &t)
         s2 += (__int128)p.S[c] * p.S[c];
     }
     t.N2 = (int64_t)p.n_refs * p.n_refs; t.twoN = 2LL * p.n_refs;
+    {   // the count-table kernel keeps Q = sum c^2 <= nk^2 and A = sum S[kmer] <= nk * max S in 32 bits
+        int64_t maxS = 0; for (size_t c = 0; c < nb; c++) maxS = std::max<int64_t>(maxS, p.S[c]);
+        if ((__int128)t.nk * maxS >= ((__int128)1 << 32) || t.nk > 65535)
+            return set_err(ctx, KGMA_E_UNSUPPORTED, "profile too large for the 32-bit window sums");
+    }
     // magnitude check: D <= N^2 nk^2 + sumS2 + 2N*nk*maxS must stay far below 2^62
     __int128 bound = (__int128)t.N2 * t.nk * t.nk * 2 + s2 * 2;
     if (bound > ((__int128)1 << 61)) return set_err(ctx, KGMA_E_UNSUPPORTED, "profile too large for 64-bit exact distances");
@@ -578,8 +614,16 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     const int64_t blk_lo = (ngrp_total * si / sc) * 32, blk_hi = (ngrp_total * (si + 1) / sc) * 32;
     const int64_t pos_lo = blk_lo * FBLOCK, pos_hi = blk_hi * FBLOCK;
 
-    std::vector<uint16_t> tab8; int M = 0;
-    if (!dense && !build_filter_table(pl, tab8, M)) dense = true;
+    int M = 0;
+    if (!dense) {
+        uint64_t key = 1469598103934665603ull;                     // FNV-1a over everything the table depends on
+        auto mix = [&](const void *p, size_t n) { const unsigned char *b = (const unsigned char *)p; for (size_t i = 0; i < n; i++) { key ^= b[i]; key *= 1099511628211ull; } };
+        for (const ProfTab &t : pl.tabs) { mix(t.S_rev.data(), t.S_rev.size() * 4); mix(&t.Thi, 8); mix(&t.N, 4); mix(&t.nk, 8); mix(&t.k, 4); }
+        if (ctx->ftab_key != key || ctx->ftab.empty()) { ctx->ftab_ok = build_filter_table(pl, ctx->ftab, ctx->ftab_M); ctx->ftab_key = key; }
+        if (!ctx->ftab_ok) dense = true;
+        M = ctx->ftab_M;
+    }
+    const std::vector<uint16_t> &tab8 = ctx->ftab;
 
     rc = dev_genome_prepare(ctx, g, false);
     if (rc) return rc;
@@ -629,6 +673,8 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     const size_t up_bytes = o;                                     // everything above is uploaded from the staging block
     const size_t o_cnt = carve(256), o_first = carve((size_t)C * std::max(nr, 1) * 8), o_runs = carve((size_t)run_cap * sizeof(kgma_run));
     const size_t o_cand = carve((size_t)cand_cap * 4);
+    const size_t bitmap_bytes = ((size_t)nblk_total / 32 + 4) * 4;
+    const size_t o_bits = carve(bitmap_bytes);
     const size_t o_dists = carve(want_dists ? (size_t)C * (size_t)std::max<int64_t>(ndist, 1) * 8 : 0);
     void *dsv = nullptr;
     rc = dev_scratch(ctx, o, &dsv);
@@ -652,6 +698,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     KGMA_CUDA(ctx, cudaMemcpyAsync(ds, hs, up_bytes, cudaMemcpyHostToDevice, sc_));
     KGMA_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 256, sc_));
     KGMA_CUDA(ctx, cudaMemsetAsync(ds + o_first, 0x80, (size_t)C * std::max(nr, 1) * 8, sc_));
+    if (!dense) KGMA_CUDA(ctx, cudaMemsetAsync(ds + o_bits + (size_t)(blk_lo / 32) * 4, 0, (size_t)((blk_hi - blk_lo) / 32 + 2) * 4, sc_));
     if (!dense && !seeds.empty()) {                                // pre-seed the candidate list
         KGMA_CUDA(ctx, cudaMemcpyAsync(ds + o_cand, ds + o_seed, seeds.size() * 4, cudaMemcpyDeviceToDevice, sc_));
         KGMA_CUDA(ctx, cudaMemcpyAsync(d_counters, ds + o_seed + seeds.size() * 4, 4, cudaMemcpyDeviceToDevice, sc_));
@@ -672,6 +719,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     FilterArgs fa{};
     fa.seq = (const uint4 *)ctx->d_seq2; fa.tab = (const uint16_t *)(ds + o_tab); fa.M = M; fa.thrw = 1u << WFRAC;
     fa.cand = (uint32_t *)(ds + o_cand); fa.cand_cap = cand_cap; fa.cand_count = d_counters;
+    fa.bitmap = (uint32_t *)(ds + o_bits);
     const int fgrid = ctx->num_sms;
     int64_t done_blk = blk_lo;                               // target blocks already filtered
     const int64_t need_after = (int64_t)(M + 1) * FBLOCK + 3 * FGROUP;     // bases that must be present past a target block
@@ -719,6 +767,8 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     EvalArgs ea{};
     ea.seq = ctx->d_seq2; ea.S = (const int32_t *)(ds + o_S);
     ea.cand_count = d_counters; ea.cand_cap = cand_cap;
+    ea.bitmap = (const uint32_t *)(ds + o_bits); ea.n_seed = (uint32_t)seeds.size();
+    ea.next_item = (unsigned long long *)(d_counters + 8);         // bytes 32.. of the zeroed counter block
     ea.recs = (const RecDev *)(ds + o_recs); ea.nrec = nr;
     ea.C = C; ea.k = pl.k;
     for (int q = 0; q < C; q++) {
