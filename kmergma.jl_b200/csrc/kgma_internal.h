@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <string>
 #include <vector>
+#include <deque>
 #include <cstring>
 #include <cstdio>
 #include "../../include/kmergma.h"
@@ -77,8 +78,9 @@ struct kgma_ctx {
     bool      d_seq_valid = false, d_mask_valid = false;
     int64_t   d_valid_lo = 0, d_valid_hi = 0;       // base range of seq2 a RESIDENT scan may reuse without upload
     int64_t   d_have_lo = 0, d_have_hi = 0;         // base range of seq2 physically present (same genome uid) - extension reads it
-    // prefilter weight table of the last scan (rebuilt only when the profiles / thresholds change)
-    uint64_t  ftab_key = 0; std::vector<uint16_t> ftab; int ftab_M = 0; bool ftab_ok = false;
+    // prefilter weight tables of recent scans (rebuilt only when the profiles / thresholds change)
+    struct FTab { uint64_t key = 0; std::vector<uint16_t> tab; int M = 0; bool ok = false; double load = 0; };
+    std::deque<FTab> ftabs;        // deque: references stay valid while entries are appended
     // scratch
     void     *d_scratch = nullptr; size_t d_scratch_bytes = 0;
     void     *h_scratch = nullptr; size_t h_scratch_bytes = 0;   // pinned

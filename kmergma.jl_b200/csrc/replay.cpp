@@ -22,19 +22,21 @@ void merge_runs(std::vector<kgma_run> &runs)
     std::vector<kgma_run> out;
     out.reserve(runs.size());
     for (const kgma_run &r : runs) {
-        // a block evaluated twice (seeded as a record start AND flagged by the prefilter) reports identical entries
-        if (!out.empty() && out.back().profile == r.profile && out.back().record == r.record && out.back().t_first == r.t_first &&
-            ((out.back().flags ^ r.flags) & KGMA_RUN_MARKER) == 0) continue;
-        if (!(r.flags & KGMA_RUN_MARKER) && !out.empty()) {
-            // find the previous real run (markers never sit between two halves of a split run: they have d >= thr)
+        if (!out.empty() && out.back().profile == r.profile && out.back().record == r.record) {
             kgma_run &p = out.back();
-            if (!(p.flags & KGMA_RUN_MARKER) && p.profile == r.profile && p.record == r.record && p.t_last + 1 == r.t_first) {
-                // a run cut by a segment / chunk / shard boundary: min of mins, earlier argmin on ties
+            const bool pm = (p.flags & KGMA_RUN_MARKER) != 0, rm = (r.flags & KGMA_RUN_MARKER) != 0;
+            if (pm && rm && p.t_first == r.t_first) continue;            // the same marker reported twice
+            if (!pm && !rm && r.t_first <= p.t_last + 1) {
+                // pieces of one maximal run: cut by a span / chunk / shard boundary (adjacent), or reported twice because a
+                // span was evaluated again (overlapping, same D values).  Min of minima, earlier argmin on ties.
                 if (r.D_min < p.D_min) { p.D_min = r.D_min; p.t_argmin = r.t_argmin; p.flags = (p.flags & ~KGMA_HIT_ARGMIN_TIE) | (r.flags & KGMA_HIT_ARGMIN_TIE); }
-                else if (r.D_min == p.D_min) p.flags |= KGMA_HIT_ARGMIN_TIE;
-                p.flags |= (r.flags & (KGMA_HIT_NEAR_THR | KGMA_RUN_OPEN_RIGHT));
-                if (!(r.flags & KGMA_RUN_OPEN_RIGHT)) p.flags &= ~KGMA_RUN_OPEN_RIGHT;
-                p.t_last = r.t_last;
+                else if (r.D_min == p.D_min) {
+                    if (r.t_argmin != p.t_argmin) p.flags |= KGMA_HIT_ARGMIN_TIE;
+                    p.t_argmin = std::min(p.t_argmin, r.t_argmin);
+                    p.flags |= (r.flags & KGMA_HIT_ARGMIN_TIE);
+                }
+                p.flags |= (r.flags & KGMA_HIT_NEAR_THR);
+                if (r.t_last >= p.t_last) { p.flags = (p.flags & ~KGMA_RUN_OPEN_RIGHT) | (r.flags & KGMA_RUN_OPEN_RIGHT); p.t_last = r.t_last; }
                 continue;
             }
         }

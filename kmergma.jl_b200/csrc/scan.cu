@@ -151,6 +151,7 @@ struct EvalArgs {
     long long n_items;              // dense mode: number of implicit items
     const RecDev *recs; int nrec;
     int C, k, span;                 // span: windows per dense item
+    int nq; int qlist[MAX_PROFILES];    // the profiles this launch evaluates
     ProfDev prof[MAX_PROFILES];
     kgma_run *runs; uint32_t run_cap; uint32_t *run_count;
     long long *first_D;             // [C][nrec]
@@ -200,7 +201,8 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
     long long nitems = a.n_items;
     if (a.cand) { uint32_t c = *a.cand_count; nitems = c < a.cand_cap ? c : a.cand_cap; }
 
-    for (int q = 0; q < a.C; q++) {
+    for (int qi = 0; qi < a.nq; qi++) {
+        const int q = a.qlist[qi];
         __syncthreads();
         for (int i = threadIdx.x; i < nb; i += blockDim.x) sS[i] = a.S[(size_t)q * nb + i];
         __syncthreads();
@@ -518,15 +520,19 @@ static int make_plan(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles
     return KGMA_OK;
 }
 
-// fixed-point prefilter table; returns false when some profile cannot be filtered (R <= 0) -> dense mode
-static bool build_filter_table(const ScanPlan &pl, std::vector<uint16_t> &tab8, int &M)
+// Fixed-point prefilter table for a group of profiles (weights = max over the group).  Returns false when some profile
+// cannot be filtered at all (R <= 0: even a window sharing no k-mer with the profile could be below thr).
+// *load = expected covering sum of a uniformly random sequence as a fraction of the flag threshold: the closer to 1,
+// the more blocks survive the filter.
+static bool build_filter_table(const ScanPlan &pl, const std::vector<int> &group, std::vector<uint16_t> &tab8, int &M, double *load)
 {
     const int k = pl.k; const size_t nb = (size_t)1 << (2 * k);
     if (k > 8) return false;
     M = (int)((pl.maxnk - 1 + FBLOCK - 1) / FBLOCK) + 1;
     if (M > 32 || M < 1) return false;
     std::vector<uint32_t> W(nb, 0);
-    for (const ProfTab &t : pl.tabs) {
+    for (int q : group) {
+        const ProfTab &t = pl.tabs[(size_t)q];
         // candidate  <=>  2N * A > R,  R = N^2 nk + sumS2 - Thi.  Thi (>= T) is the upper edge of the 1e-9 band around
         // thr, so that every window the reference's Float64 accumulator could still see below thr is evaluated and reported.
         __int128 R = (__int128)t.N2 * t.nk + t.sumS2 - t.Thi;
@@ -541,11 +547,15 @@ static bool build_filter_table(const ScanPlan &pl, std::vector<uint16_t> &tab8, 
     }
     const int nper = 9 - k; const uint32_t kmask = (uint32_t)nb - 1;
     tab8.resize(65536);
+    double sum = 0;
     for (uint32_t x = 0; x < 65536; x++) {
-        uint32_t s = 0;
-        for (int j = 0; j < nper; j++) s += W[(x >> (2 * j)) & kmask];
-        tab8[x] = (uint16_t)std::min<uint32_t>(s, 65535u);
+        uint32_t v = 0;
+        for (int j = 0; j < nper; j++) v += W[(x >> (2 * j)) & kmask];
+        tab8[x] = (uint16_t)std::min<uint32_t>(v, 65535u);
+        sum += tab8[x];
     }
+    const int nlook = (FBLOCK + nper - 1) / nper;
+    *load = sum / 65536.0 * nlook * M / (double)(1u << WFRAC);
     return true;
 }
 
@@ -588,13 +598,36 @@ constexpr long long NO_D = (long long)0x8080808080808080ull;   // cudaMemset(0x8
 
 using namespace kgma;
 
+// One prefilter pass = one group of profiles sharing a weight table, a candidate list and a block bitmap.
+struct FilterGroup {
+    std::vector<int> q;            // profile indices
+    bool dense = false;            // no prefilter: the count-table kernel sees every window
+    const kgma_ctx::FTab *ft = nullptr;
+    size_t o_tab = 0, o_cand = 0, o_bits = 0;
+};
+
+static const kgma_ctx::FTab *get_ftab(kgma_ctx *ctx, const ScanPlan &pl, const std::vector<int> &group)
+{
+    uint64_t key = 1469598103934665603ull;                         // FNV-1a over everything the table depends on
+    auto mix = [&](const void *p, size_t n) { const unsigned char *b = (const unsigned char *)p; for (size_t i = 0; i < n; i++) { key ^= b[i]; key *= 1099511628211ull; } };
+    for (int q : group) { const ProfTab &t = pl.tabs[(size_t)q]; mix(t.S_rev.data(), t.S_rev.size() * 4); mix(&t.Thi, 8); mix(&t.N, 4); mix(&t.nk, 8); mix(&t.k, 4); }
+    mix(&pl.maxnk, 8);
+    for (const auto &f : ctx->ftabs) if (f.key == key) return &f;
+    ctx->ftabs.emplace_back();
+    kgma_ctx::FTab &f = ctx->ftabs.back();
+    f.key = key; f.ok = build_filter_table(pl, group, f.tab, f.M, &f.load);
+    return &f;
+}
+
 // The scan proper (one context / one GPU / one shard).  Fills res->runs, res->first_D, res->dists.
 // Device work is queued back to back (uploads, prefilter launches chasing the genome chunks, count-table
-// kernel reading the candidate list from device memory, result copies) with ONE host synchronisation at the end.
+// kernel reading the candidate lists from device memory, result copies) with ONE host synchronisation at the end.
+// Returns KGMA_E_CAPACITY with *need_runs set when the run list was too small (the caller retries once).
 static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int C,
-                          const kgma_scan_params &P, ScanPlan &pl, kgma_result *res)
+                          const kgma_scan_params &P, ScanPlan &pl, kgma_result *res, uint32_t run_cap, uint64_t *need_runs)
 {
     const double t_wall0 = now_ms();
+    *need_runs = 0;
     if (!g->sealed) return set_err(ctx, KGMA_E_STATE, "genome is not sealed");
     if (g->ambiguous)
         return set_err(ctx, KGMA_E_SYMBOL, "KeyError: record %lld position %lld holds a symbol outside A,C,G,T,N",
@@ -605,7 +638,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     kgma_stats &st = ctx->stats; st = kgma_stats{};
     const int nr = (int)g->recs.size();
     const bool want_dists = (P.flags & KGMA_F_WANT_DISTS) != 0;
-    bool dense = (P.flags & KGMA_F_DENSE) != 0 || want_dists;
+    const bool force_dense = (P.flags & KGMA_F_DENSE) != 0 || want_dists;
 
     // ---- shard range in 64-base blocks (whole warp groups)
     const int64_t nblk_total = g->G / FBLOCK;
@@ -614,16 +647,31 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     const int64_t blk_lo = (ngrp_total * si / sc) * 32, blk_hi = (ngrp_total * (si + 1) / sc) * 32;
     const int64_t pos_lo = blk_lo * FBLOCK, pos_hi = blk_hi * FBLOCK;
 
-    int M = 0;
-    if (!dense) {
-        uint64_t key = 1469598103934665603ull;                     // FNV-1a over everything the table depends on
-        auto mix = [&](const void *p, size_t n) { const unsigned char *b = (const unsigned char *)p; for (size_t i = 0; i < n; i++) { key ^= b[i]; key *= 1099511628211ull; } };
-        for (const ProfTab &t : pl.tabs) { mix(t.S_rev.data(), t.S_rev.size() * 4); mix(&t.Thi, 8); mix(&t.N, 4); mix(&t.nk, 8); mix(&t.k, 4); }
-        if (ctx->ftab_key != key || ctx->ftab.empty()) { ctx->ftab_ok = build_filter_table(pl, ctx->ftab, ctx->ftab_M); ctx->ftab_key = key; }
-        if (!ctx->ftab_ok) dense = true;
-        M = ctx->ftab_M;
+    // ---- prefilter groups.  One table for all profiles when a random sequence stays well below the flag threshold
+    //      under the combined (max) weights; otherwise one pass per profile; profiles that cannot be filtered go dense.
+    std::vector<FilterGroup> groups;
+    if (ctx->ftabs.size() > 48) ctx->ftabs.clear();                // bounded cache; nothing points into it between calls
+    {
+        std::vector<int> all((size_t)C); for (int q = 0; q < C; q++) all[(size_t)q] = q;
+        const double LOAD_OK = 0.62, LOAD_MAX = 0.85;
+        FilterGroup dg; dg.dense = true;
+        if (force_dense) dg.q = all;
+        else {
+            const kgma_ctx::FTab *f = get_ftab(ctx, pl, all);
+            if (f->ok && (f->load <= LOAD_OK || (C == 1 && f->load <= LOAD_MAX))) { FilterGroup fg; fg.q = all; fg.ft = f; groups.push_back(fg); }
+            else if (C == 1) dg.q = all;
+            else for (int q = 0; q < C; q++) {
+                const kgma_ctx::FTab *fq = get_ftab(ctx, pl, std::vector<int>{ q });   // note: pointers into ctx->ftabs stay valid (capacity reserved)
+                if (fq->ok && fq->load <= LOAD_MAX) { FilterGroup fg; fg.q = { q }; fg.ft = fq; groups.push_back(fg); }
+                else dg.q.push_back(q);
+            }
+        }
+        if (!dg.q.empty()) groups.push_back(dg);
     }
-    const std::vector<uint16_t> &tab8 = ctx->ftab;
+    int M = 1;
+    for (const FilterGroup &fg : groups) if (!fg.dense) M = std::max(M, fg.ft->M);
+    bool any_filter = false, any_dense = false;
+    for (const FilterGroup &fg : groups) { any_filter |= !fg.dense; any_dense |= fg.dense; }
 
     rc = dev_genome_prepare(ctx, g, false);
     if (rc) return rc;
@@ -653,28 +701,26 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
         if (R.w_begin == 0) seeds.push_back((uint32_t)(R.off / FBLOCK));
     }
     st.bases_scanned = span_windows;
-    int span = 0; int64_t n_items = 0;
-    auto plan_dense = [&]() {
+    int64_t n_items = 0; int span = 64;
+    {   // dense items (also the fallback when a candidate list overflows)
         int64_t sp = span_windows / std::max<int64_t>(1, total_warps * 4) + 1;
         sp = std::min<int64_t>(std::max<int64_t>((sp + 63) / 64 * 64, 64), 1 << 16);
-        span = (int)sp; n_items = 0;
+        span = (int)sp;
         for (int r = 0; r < nr; r++) { recs[(size_t)r].item_base = n_items; n_items += (recs[(size_t)r].w_end - recs[(size_t)r].w_begin + sp - 1) / sp; }
-    };
-    if (dense) plan_dense();
+    }
 
     // ---- device scratch layout + one pinned staging block for all small uploads
     const uint32_t cand_cap = (uint32_t)std::min<int64_t>(std::max<int64_t>((blk_hi - blk_lo) / 16, 1 << 16) + (int64_t)seeds.size(), 1 << 26);
-    const uint32_t run_cap = 1u << 20;
     const uint32_t run_head = 4096;                                // runs copied back with the counters; more only if needed
     size_t o = 0;
     auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
-    const size_t o_S = carve((size_t)C * nb * 4), o_tab = carve(65536 * 2), o_recs = carve(recs.size() * sizeof(RecDev));
+    const size_t o_S = carve((size_t)C * nb * 4), o_recs = carve(recs.size() * sizeof(RecDev));
     const size_t o_seed = carve((seeds.size() + 1) * 4);
+    for (FilterGroup &fg : groups) if (!fg.dense) fg.o_tab = carve(65536 * 2);
     const size_t up_bytes = o;                                     // everything above is uploaded from the staging block
     const size_t o_cnt = carve(256), o_first = carve((size_t)C * std::max(nr, 1) * 8), o_runs = carve((size_t)run_cap * sizeof(kgma_run));
-    const size_t o_cand = carve((size_t)cand_cap * 4);
     const size_t bitmap_bytes = ((size_t)nblk_total / 32 + 4) * 4;
-    const size_t o_bits = carve(bitmap_bytes);
+    for (FilterGroup &fg : groups) if (!fg.dense) { fg.o_cand = carve((size_t)cand_cap * 4); fg.o_bits = carve(bitmap_bytes); }
     const size_t o_dists = carve(want_dists ? (size_t)C * (size_t)std::max<int64_t>(ndist, 1) * 8 : 0);
     void *dsv = nullptr;
     rc = dev_scratch(ctx, o, &dsv);
@@ -686,28 +732,33 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     if (rc) return rc;
     unsigned char *hs = (unsigned char *)hsv, *hback = hs + up_bytes;
     for (int q = 0; q < C; q++) memcpy(hs + o_S + (size_t)q * nb * 4, pl.tabs[q].S_rev.data(), nb * 4);
-    if (!dense) memcpy(hs + o_tab, tab8.data(), 65536 * 2);
+    for (const FilterGroup &fg : groups) if (!fg.dense) memcpy(hs + fg.o_tab, fg.ft->tab.data(), 65536 * 2);
     memcpy(hs + o_recs, recs.data(), recs.size() * sizeof(RecDev));
     if (!seeds.empty()) memcpy(hs + o_seed, seeds.data(), seeds.size() * 4);
     { const uint32_t ns = (uint32_t)seeds.size(); memcpy(hs + o_seed + seeds.size() * 4, &ns, 4); }
 
     cudaStream_t sc_ = ctx->s_compute, sp = ctx->s_copy;
     cudaEvent_t e_start = ctx->ev[0], e_h2d = ctx->ev[1], e_filt = ctx->ev[2], e_exact = ctx->ev[3], e_fstart = ctx->ev[4];
-    uint32_t *d_counters = (uint32_t *)(ds + o_cnt);               // [0] = cand_count, [1] = run_count
+    // counter block (256 B): [0] run_count, [1 + gi] candidate count of group gi, bytes 128.. next_item[q]
+    uint32_t *d_counters = (uint32_t *)(ds + o_cnt);
     KGMA_CUDA(ctx, cudaEventRecord(e_start, sc_));
     KGMA_CUDA(ctx, cudaMemcpyAsync(ds, hs, up_bytes, cudaMemcpyHostToDevice, sc_));
     KGMA_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 256, sc_));
     KGMA_CUDA(ctx, cudaMemsetAsync(ds + o_first, 0x80, (size_t)C * std::max(nr, 1) * 8, sc_));
-    if (!dense) KGMA_CUDA(ctx, cudaMemsetAsync(ds + o_bits + (size_t)(blk_lo / 32) * 4, 0, (size_t)((blk_hi - blk_lo) / 32 + 2) * 4, sc_));
-    if (!dense && !seeds.empty()) {                                // pre-seed the candidate list
-        KGMA_CUDA(ctx, cudaMemcpyAsync(ds + o_cand, ds + o_seed, seeds.size() * 4, cudaMemcpyDeviceToDevice, sc_));
-        KGMA_CUDA(ctx, cudaMemcpyAsync(d_counters, ds + o_seed + seeds.size() * 4, 4, cudaMemcpyDeviceToDevice, sc_));
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+        const FilterGroup &fg = groups[gi];
+        if (fg.dense) continue;
+        KGMA_CUDA(ctx, cudaMemsetAsync(ds + fg.o_bits + (size_t)(blk_lo / 32) * 4, 0, (size_t)((blk_hi - blk_lo) / 32 + 2) * 4, sc_));
+        if (!seeds.empty()) {                                      // pre-seed the candidate list
+            KGMA_CUDA(ctx, cudaMemcpyAsync(ds + fg.o_cand, ds + o_seed, seeds.size() * 4, cudaMemcpyDeviceToDevice, sc_));
+            KGMA_CUDA(ctx, cudaMemcpyAsync(d_counters + 1 + gi, ds + o_seed + seeds.size() * 4, 4, cudaMemcpyDeviceToDevice, sc_));
+        }
     }
     st.h2d_bytes += up_bytes;
     st.host_setup_ms = now_ms() - t_wall0;
 
     // ---- upload range (bases): shard + halo, unless resident
-    const int64_t halo = (int64_t)(dense ? pl.maxws + 64 : (M + 1) * FBLOCK + pl.maxws + 64);
+    const int64_t halo = (int64_t)((M + 1) * FBLOCK + pl.maxws + 64);
     int64_t up_lo = pos_lo, up_hi = std::min(g->G + TAIL_PAD, pos_hi + halo + 3 * FGROUP);
     if (si == sc - 1) up_hi = g->G + TAIL_PAD;
     up_hi = (up_hi + 127) / 128 * 128; up_hi = std::min(up_hi, g->G + TAIL_PAD);
@@ -716,23 +767,27 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     // ---- stream the packed genome: chunked cudaMemcpyAsync on the copy stream, prefilter on the
     //      compute stream chasing it (double buffering falls out of the two streams + per-chunk events)
     const int64_t CH = (int64_t)128 << 20;                  // bases per chunk (32 MB of packed data)
-    FilterArgs fa{};
-    fa.seq = (const uint4 *)ctx->d_seq2; fa.tab = (const uint16_t *)(ds + o_tab); fa.M = M; fa.thrw = 1u << WFRAC;
-    fa.cand = (uint32_t *)(ds + o_cand); fa.cand_cap = cand_cap; fa.cand_count = d_counters;
-    fa.bitmap = (uint32_t *)(ds + o_bits);
     const int fgrid = ctx->num_sms;
     int64_t done_blk = blk_lo;                               // target blocks already filtered
     const int64_t need_after = (int64_t)(M + 1) * FBLOCK + 3 * FGROUP;     // bases that must be present past a target block
     bool first_filter = true;
     auto run_filter_to = [&](int64_t avail_hi, bool last) -> int {
-        if (dense) return KGMA_OK;
+        if (!any_filter) return KGMA_OK;
         int64_t lim = last ? blk_hi : std::min(blk_hi, ((avail_hi - need_after) / FBLOCK) / 32 * 32);
         if (lim <= done_blk) return KGMA_OK;
         if (first_filter) { KGMA_CUDA(ctx, cudaEventRecord(e_fstart, sc_)); first_filter = false; }
-        fa.blk_begin = done_blk; fa.blk_end = lim;
-        launch_filter_k(pl.k, fa, fgrid, sc_);
-        KGMA_CUDA(ctx, cudaGetLastError());
-        st.launches++;
+        for (size_t gi = 0; gi < groups.size(); gi++) {
+            const FilterGroup &fg = groups[gi];
+            if (fg.dense) continue;
+            FilterArgs fa{};
+            fa.seq = (const uint4 *)ctx->d_seq2; fa.tab = (const uint16_t *)(ds + fg.o_tab); fa.M = fg.ft->M; fa.thrw = 1u << WFRAC;
+            fa.cand = (uint32_t *)(ds + fg.o_cand); fa.cand_cap = cand_cap; fa.cand_count = d_counters + 1 + gi;
+            fa.bitmap = (uint32_t *)(ds + fg.o_bits);
+            fa.blk_begin = done_blk; fa.blk_end = lim;
+            launch_filter_k(pl.k, fa, fgrid, sc_);
+            KGMA_CUDA(ctx, cudaGetLastError());
+            st.launches++;
+        }
         done_blk = lim;
         return KGMA_OK;
     };
@@ -763,59 +818,71 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     if (first_filter) KGMA_CUDA(ctx, cudaEventRecord(e_fstart, sc_));
     KGMA_CUDA(ctx, cudaEventRecord(e_filt, sc_));
 
-    // ---- count-table kernel over the candidate list (read on the device) or over everything
+    // ---- count-table kernel over the candidate lists (read on the device) or over everything
     EvalArgs ea{};
     ea.seq = ctx->d_seq2; ea.S = (const int32_t *)(ds + o_S);
-    ea.cand_count = d_counters; ea.cand_cap = cand_cap;
-    ea.bitmap = (const uint32_t *)(ds + o_bits); ea.n_seed = (uint32_t)seeds.size();
-    ea.next_item = (unsigned long long *)(d_counters + 8);         // bytes 32.. of the zeroed counter block
+    ea.cand_cap = cand_cap; ea.n_seed = (uint32_t)seeds.size();
+    ea.next_item = (unsigned long long *)(d_counters + 32);        // bytes 128.. of the zeroed counter block
     ea.recs = (const RecDev *)(ds + o_recs); ea.nrec = nr;
-    ea.C = C; ea.k = pl.k;
+    ea.C = C; ea.k = pl.k; ea.span = span;
     for (int q = 0; q < C; q++) {
         const ProfTab &t = pl.tabs[q];
         ea.prof[q].N2 = t.N2; ea.prof[q].twoN = t.twoN; ea.prof[q].sumS2 = t.sumS2;
         ea.prof[q].T = t.T; ea.prof[q].Tlo = t.Tlo; ea.prof[q].Thi = t.Thi; ea.prof[q].nk = (int)t.nk; ea.prof[q].pad = 0;
     }
-    ea.runs = (kgma_run *)(ds + o_runs); ea.run_cap = run_cap; ea.run_count = d_counters + 1;
+    ea.runs = (kgma_run *)(ds + o_runs); ea.run_cap = run_cap; ea.run_count = d_counters;
     ea.first_D = (long long *)(ds + o_first);
     ea.dists = want_dists ? (long long *)(ds + o_dists) : nullptr; ea.dist_stride = std::max<int64_t>(ndist, 1);
     KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
-    uint32_t cnts[2] = { 0, 0 };
-    for (int attempt = 0; attempt < 2; attempt++) {
-        if (nr == 0) break;
-        ea.cand = dense ? nullptr : (const uint32_t *)(ds + o_cand);
-        ea.n_items = dense ? n_items : 0; ea.span = span;
+    auto launch_eval = [&](const std::vector<int> &qs, bool dense_items, size_t gi, const FilterGroup *fg) -> int {
+        ea.nq = (int)qs.size();
+        for (size_t i = 0; i < qs.size(); i++) ea.qlist[i] = qs[i];
+        if (dense_items) { ea.cand = nullptr; ea.cand_count = nullptr; ea.bitmap = nullptr; ea.n_items = n_items; }
+        else { ea.cand = (const uint32_t *)(ds + fg->o_cand); ea.cand_count = d_counters + 1 + gi; ea.bitmap = (const uint32_t *)(ds + fg->o_bits); ea.n_items = 0; }
         kgma_eval<<<egrid, ewarps * 32, esmem, sc_>>>(ea);
         KGMA_CUDA(ctx, cudaGetLastError());
         st.launches++;
-        KGMA_CUDA(ctx, cudaEventRecord(e_exact, sc_));
-        // counters + first-window distances + the head of the run list, one synchronisation
+        return KGMA_OK;
+    };
+    uint32_t cnts[64] = { 0 };
+    auto fetch = [&]() -> int {     // counters + first-window distances + the head of the run list, one synchronisation
         KGMA_CUDA(ctx, cudaMemcpyAsync(hback, d_counters, 256, cudaMemcpyDeviceToHost, sc_));
         KGMA_CUDA(ctx, cudaMemcpyAsync(hback + 256, ds + o_first, (size_t)C * nr * 8, cudaMemcpyDeviceToHost, sc_));
         KGMA_CUDA(ctx, cudaMemcpyAsync(hback + 256 + (size_t)C * nr * 8, ds + o_runs, (size_t)run_head * sizeof(kgma_run), cudaMemcpyDeviceToHost, sc_));
         KGMA_CUDA(ctx, cudaStreamSynchronize(sc_));
-        memcpy(cnts, hback, 8);
+        memcpy(cnts, hback, 256);
         st.d2h_bytes += back_bytes;
-        if (!dense && cnts[0] > cand_cap) {                        // too many survivors: evaluate everything
-            dense = true; plan_dense();
-            memcpy(hs + o_recs, recs.data(), recs.size() * sizeof(RecDev));
-            KGMA_CUDA(ctx, cudaMemcpyAsync(ds + o_recs, hs + o_recs, recs.size() * sizeof(RecDev), cudaMemcpyHostToDevice, sc_));
-            KGMA_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 256, sc_));
-            continue;
+        return KGMA_OK;
+    };
+    if (nr > 0) {
+        for (size_t gi = 0; gi < groups.size(); gi++) { rc = launch_eval(groups[gi].q, groups[gi].dense, gi, &groups[gi]); if (rc) return rc; }
+        KGMA_CUDA(ctx, cudaEventRecord(e_exact, sc_));
+        rc = fetch(); if (rc) return rc;
+        std::vector<int> redo;                                     // groups whose candidate list overflowed: evaluate every window
+        for (size_t gi = 0; gi < groups.size(); gi++)
+            if (!groups[gi].dense && cnts[1 + gi] > cand_cap) { redo.insert(redo.end(), groups[gi].q.begin(), groups[gi].q.end()); groups[gi].dense = true; any_dense = true; }
+        if (!redo.empty() && cnts[0] <= run_cap) {
+            // partial runs of the overflowed groups are duplicates of what the dense pass will report: drop them on the host below
+            for (int q : redo) KGMA_CUDA(ctx, cudaMemsetAsync((unsigned long long *)(d_counters + 32) + q, 0, 8, sc_));
+            rc = launch_eval(redo, true, 0, nullptr); if (rc) return rc;
+            KGMA_CUDA(ctx, cudaEventRecord(e_exact, sc_));
+            rc = fetch(); if (rc) return rc;
         }
-        break;
     }
     const double t_cand0 = now_ms();
-    if (!dense) { st.blocks_total = blk_hi - blk_lo; st.blocks_flagged = cnts[0]; st.exact_windows = (int64_t)cnts[0] * FBLOCK * C; }
-    else st.exact_windows = span_windows * C;
-    if (cnts[1] > run_cap) return set_err(ctx, KGMA_E_CAPACITY, "run list overflow (%u runs)", cnts[1]);
+    st.blocks_total = any_filter ? blk_hi - blk_lo : 0;
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+        if (groups[gi].ft) { st.blocks_flagged += cnts[1 + gi]; }
+        st.exact_windows += groups[gi].dense ? span_windows * (int64_t)groups[gi].q.size() : (int64_t)std::min(cnts[1 + gi], cand_cap) * FBLOCK * (int64_t)groups[gi].q.size();
+    }
+    if (cnts[0] > run_cap) { *need_runs = cnts[0]; return set_err(ctx, KGMA_E_CAPACITY, "run list overflow (%u runs)", cnts[0]); }
     std::vector<kgma_run> &runs = res->runs;
-    runs.resize(cnts[1]);
-    if (cnts[1]) memcpy(runs.data(), hback + 256 + (size_t)C * nr * 8, (size_t)std::min(cnts[1], run_head) * sizeof(kgma_run));
-    if (cnts[1] > run_head) {
+    runs.resize(cnts[0]);
+    if (cnts[0]) memcpy(runs.data(), hback + 256 + (size_t)C * nr * 8, (size_t)std::min(cnts[0], run_head) * sizeof(kgma_run));
+    if (cnts[0] > run_head) {
         KGMA_CUDA(ctx, cudaMemcpy(runs.data() + run_head, ds + o_runs + (size_t)run_head * sizeof(kgma_run),
-                                  (size_t)(cnts[1] - run_head) * sizeof(kgma_run), cudaMemcpyDeviceToHost));
-        st.d2h_bytes += (size_t)(cnts[1] - run_head) * sizeof(kgma_run);
+                                  (size_t)(cnts[0] - run_head) * sizeof(kgma_run), cudaMemcpyDeviceToHost));
+        st.d2h_bytes += (size_t)(cnts[0] - run_head) * sizeof(kgma_run);
     }
     res->first_D.assign((size_t)C * nr, INT64_MIN);
     {
@@ -833,7 +900,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
             for (int64_t i = 0; i < ndist; i++) res->dists[q][(size_t)i] = (double)Dh[(size_t)i] / den;
         }
     }
-    st.n_runs = cnts[1];
+    st.n_runs = cnts[0];
     float ms = 0;
     cudaEventElapsedTime(&ms, e_start, e_h2d); st.h2d_ms = ms;
     cudaEventElapsedTime(&ms, e_fstart, e_filt); st.filter_ms = ms;
@@ -844,6 +911,19 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     return KGMA_OK;
 }
 
+// run list capacity: 1 Mi runs to start with, grown to what the device counted when that was not enough
+static int scan_runs_retry(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int C,
+                           const kgma_scan_params &P, ScanPlan &pl, kgma_result *res)
+{
+    uint64_t need = 0;
+    int rc = scan_runs_impl(ctx, g, profiles, C, P, pl, res, 1u << 20, &need);
+    if (rc == KGMA_E_CAPACITY && need > 0 && need < (1ull << 28)) {
+        pl = ScanPlan();
+        rc = scan_runs_impl(ctx, g, profiles, C, P, pl, res, (uint32_t)(need + need / 8 + 1024), &need);
+    }
+    return rc;
+}
+
 extern "C" {
 
 int kgma_scan_runs(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int n_profiles,
@@ -852,7 +932,7 @@ int kgma_scan_runs(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, 
     if (!ctx || !g || !params || !out) return KGMA_E_ARG;
     kgma_result *res = new kgma_result();
     ScanPlan pl;
-    int rc = scan_runs_impl(ctx, g, profiles, n_profiles, *params, pl, res);
+    int rc = scan_runs_retry(ctx, g, profiles, n_profiles, *params, pl, res);
     if (rc) { delete res; return rc; }
     *out = res;
     return KGMA_OK;
@@ -885,7 +965,7 @@ int kgma_scan(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int n
     kgma_scan_params P = *params; P.shard_index = 0; P.shard_count = 1;
     kgma_result *res = new kgma_result();
     ScanPlan pl;
-    int rc = scan_runs_impl(ctx, g, profiles, n_profiles, P, pl, res);
+    int rc = scan_runs_retry(ctx, g, profiles, n_profiles, P, pl, res);
     if (rc == KGMA_OK) {
         const double t0 = now_ms();
         rc = replay(ctx, g, pl.tabs, profiles, P, res->runs, res->first_D, res);

@@ -509,3 +509,46 @@ def test_returned_alignments_match_oracle_cigars(K, O, prof):
         a, b = max(int(h.cmi) - 50, 1), min(int(h.cmi) + ws - 1 + 50, L)
         cig, score = O.pairalign_semiglobal(cons[:ws], f.seq(int(h.record))[a - 1:b], -69, -1)
         assert (al.cigar, al.score) == (cig, score)
+
+
+def test_candidate_overflow_falls_back_to_dense(K, O, prof, tmp_path):
+    """a genome that is homologue wall to wall: every 64-base block survives the prefilter, the candidate list
+    overflows and the scan must transparently evaluate every window instead (same hits as the oracle)"""
+    RV, ws, cons = prof
+    refs = O.Fasta(TF)
+    rng = np.random.default_rng(11)
+    parts = []
+    for i in range(18000):
+        s = refs.seq(int(rng.integers(0, len(refs))))
+        parts.append(s if i % 3 else s[:200])
+    path = tmp_path / "wall.fasta"
+    _write_fasta(path, [("wall homologues", "".join(parts))], width=100)
+    out = K.ac_gma_testing(genome_path=str(path), refVec=RV, consensus_refseq=cons, windowsize=ws, thr=30,
+                           do_align=False, resultVec=[])
+    st = K.default_context().stats()
+    assert st["blocks_flagged"] > 65536 + 1                      # the list did overflow
+    oh = assert_parity(K, O, out, lambda: O.ac_gma_testing(str(path), np.asarray(RV), cons, windowsize=ws, thr=30, do_align=False)[0], RV.n_refs)
+    assert len(oh) > 100
+
+
+def test_loose_threshold_many_runs(K, O, prof):
+    """thr at the level of random sequence: hundreds of thousands of runs; the run list grows instead of failing"""
+    RV, ws, cons = prof
+    out = K.ac_gma_testing(genome_path=GENOME, refVec=RV, consensus_refseq=cons, windowsize=ws, thr=47.5,
+                           do_align=False, resultVec=[])
+    oh = assert_parity(K, O, out, lambda: O.ac_gma_testing(GENOME, np.asarray(RV), cons, windowsize=ws, thr=47.5, do_align=False)[0], RV.n_refs)
+    assert len(oh) > 50
+
+
+def test_cluster_per_profile_filter_groups(K, O, synth):
+    """cluster thresholds for which the combined (max over profiles) prefilter table is too loose: the scan runs one
+    prefilter pass per profile; results must not depend on the grouping (compare with the dense scan and the oracle)"""
+    path, recs = synth
+    rvs, wss, cons, inv = K.cluster_ref_API(TF, 6)
+    rvs, wss, cons = K.eliminate_null_params(rvs, wss, cons, inv)
+    thrs = [35, 31, 38, 34, 27, 27]
+    a = K.Omn_KmerGMA(genome_path=path, refVecs=rvs, windowsizes=wss, consensus_seqs=cons, resultVec=[], thr_vec=thrs, buff=100)
+    st = K.default_context().stats()
+    b = K.Omn_KmerGMA(genome_path=path, refVecs=rvs, windowsizes=wss, consensus_seqs=cons, resultVec=[], thr_vec=thrs, buff=100, dense=True)
+    assert st["blocks_total"] > 0 and st["exact_windows"] < K.default_context().stats()["exact_windows"]     # the prefilter was used
+    assert np.array_equal(a.hits[["record", "profile", "first", "last", "D"]], b.hits[["record", "profile", "first", "last", "D"]])
