@@ -168,7 +168,7 @@ struct AlignArgs2 {
     const AlignJob2 *jobs; int njobs;
     int *next_job;
     AlignOut *out;
-    int go, ge, tie_open, ncol_cap;
+    int go, ge, tie_open, ncol_cap, need_boundary;
 };
 
 // path summary, two 32-bit words:  lo = total columns | first-run length << 16
@@ -195,17 +195,22 @@ __device__ __forceinline__ PathSum ps_append(PathSum s, uint32_t op, uint32_t le
     return r;
 }
 
+// Each lane owns R consecutive DP rows (register blocked), the warp 32*R rows per sweep; neighbouring lanes are
+// skewed by one column, so a whole 289-row alignment is ONE sweep of n+31 steps with R = 10 (instead of ten
+// sweeps of 32 rows): 7 shuffles per step are amortised over R cells and the per-step bookkeeping shrinks 10x.
+template <int R>
 __global__ void __launch_bounds__(128) kgma_align_summary(AlignArgs2 A)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const size_t per_warp = (size_t)A.ncol_cap * (7 * 4 + 1);
+    const size_t per_warp = (size_t)A.ncol_cap * (A.need_boundary ? (7 * 4 + 1) : 1);
     unsigned char *wb = s_raw + (size_t)wid * ((per_warp + 15) & ~(size_t)15);
+    // bottom row of a sweep, parked for the next sweep (only when the consensus is longer than 32*R)
     int *Hb = reinterpret_cast<int *>(wb), *Eb = Hb + A.ncol_cap;
     uint32_t *sHlo = reinterpret_cast<uint32_t *>(Eb + A.ncol_cap), *sHhi = sHlo + A.ncol_cap;
     uint32_t *bElo = sHhi + A.ncol_cap, *bEhi = bElo + A.ncol_cap, *lEb = bEhi + A.ncol_cap;
-    uint8_t *bs = reinterpret_cast<uint8_t *>(lEb + A.ncol_cap);
+    uint8_t *bs = A.need_boundary ? reinterpret_cast<uint8_t *>(lEb + A.ncol_cap) : wb;
     const int NEG = -(1 << 29);
     const int go = A.go, ge = A.ge;
 
@@ -231,17 +236,21 @@ __global__ void __launch_bounds__(128) kgma_align_summary(AlignArgs2 A)
         }
         __syncwarp();
         int score = 0; PathSum sfin = { 0u, 0u };
-        const int nrb = (m + 31) >> 5;
+        const int nrb = (m + 32 * R - 1) / (32 * R);
         for (int rb = 0; rb < nrb; rb++) {
-            const int i = rb * 32 + lane + 1;
-            const bool row_ok = i <= m;
-            const int ai = row_ok ? a[i - 1] : 0;
-            const bool last = (i == m);
-            int Hleft = -(go + i * ge), F = NEG;                                  // H[i][0], F[i][0]
-            PathSum sHleft = ps_run((uint32_t)i, PS_I), bF = { 0u, 0u }; uint32_t lF = 0;
-            int Hdiag = (i == 1) ? 0 : -(go + (i - 1) * ge);                      // H[i-1][0]
-            PathSum sHdiag = ps_run((uint32_t)(i - 1), PS_I);
+            const int i0 = rb * 32 * R + lane * R;                                // this lane owns rows i0+1 .. i0+R
+            int H[R], F[R]; PathSum sH[R], bF[R]; uint32_t lF[R]; int ac[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int i = i0 + r + 1;
+                H[r] = -(go + i * ge); F[r] = NEG;                                // H[i][0], F[i][0]
+                sH[r] = ps_run((uint32_t)i, PS_I); bF[r].lo = bF[r].hi = 0; lF[r] = 0;
+                ac[r] = i <= m ? a[i - 1] : 0;
+            }
+            int Hdiag0 = (i0 == 0) ? 0 : -(go + i0 * ge);                         // H[i0][0]: diagonal of my first row at column 1
+            PathSum sHdiag0 = ps_run((uint32_t)i0, PS_I);
             int Hout = NEG, Eout = NEG; PathSum sHout = { 0u, 0u }, bEout = { 0u, 0u }; uint32_t lEout = 0;
+            const bool lane_ok = i0 < m;
             for (int s = 1; s <= n + 31; s++) {
                 const int j = s - lane;
                 int upH = __shfl_up_sync(FULL, Hout, 1), upE = __shfl_up_sync(FULL, Eout, 1);
@@ -253,29 +262,44 @@ __global__ void __launch_bounds__(128) kgma_align_summary(AlignArgs2 A)
                     if (rb == 0) { upH = 0; upE = NEG; supH = ps_run((uint32_t)j, PS_D); ubE.lo = ubE.hi = 0; ulE = 0; }   // row 0: free leading deletions
                     else { upH = Hb[j]; upE = Eb[j]; supH.lo = sHlo[j]; supH.hi = sHhi[j]; ubE.lo = bElo[j]; ubE.hi = bEhi[j]; ulE = lEb[j]; }
                 }
-                if (row_ok && j >= 1 && j <= n) {
-                    const int eo = upH - go - ge, ee = upE - ge;
-                    const bool xe = A.tie_open ? (ee > eo) : (ee >= eo);
-                    const int e = xe ? ee : eo;
-                    PathSum bE; bE.lo = xe ? ubE.lo : supH.lo; bE.hi = xe ? ubE.hi : supH.hi;
-                    const uint32_t lE = xe ? ulE + 1 : 1u;
-                    const int fo = last ? Hleft : Hleft - go - ge, fe = last ? F : F - ge;
-                    const bool xf = A.tie_open ? (fe > fo) : (fe >= fo);
-                    const int f = xf ? fe : fo;
-                    bF.lo = xf ? bF.lo : sHleft.lo; bF.hi = xf ? bF.hi : sHleft.hi; lF = xf ? lF + 1 : 1u;
+                if (lane_ok && j >= 1 && j <= n) {
                     const int bj = bs[j - 1];
-                    const int mm = Hdiag + edna(ai, bj);
-                    const int h = max(mm, max(f, e));
-                    PathSum sH = ps_append(sHdiag, ai == bj ? PS_EQ : PS_X, 1u);
-                    if (mm != h) sH = (f == h) ? ps_append(bF, PS_D, lF) : ps_append(bE, PS_I, lE);
-                    Hdiag = upH; sHdiag = supH; Hout = h; Eout = e; sHout = sH; bEout = bE; lEout = lE;
-                    Hleft = h; sHleft = sH; F = f;
-                    if (lane == 31) { Hb[j] = h; Eb[j] = e; sHlo[j] = sH.lo; sHhi[j] = sH.hi; bElo[j] = bE.lo; bEhi[j] = bE.hi; lEb[j] = lE; }
+                    int hU = upH, eU = upE; PathSum shU = supH, beU = ubE; uint32_t leU = ulE;    // row above, column j
+                    int hD = Hdiag0; PathSum shD = sHdiag0;                                       // row above, column j-1
+                    Hdiag0 = upH; sHdiag0 = supH;
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const int i = i0 + r + 1;
+                        if (i <= m) {
+                            const bool last = (i == m);
+                            const int eo = hU - go - ge, ee = eU - ge;
+                            const bool xe = A.tie_open ? (ee > eo) : (ee >= eo);
+                            const int e = xe ? ee : eo;
+                            PathSum bE; bE.lo = xe ? beU.lo : shU.lo; bE.hi = xe ? beU.hi : shU.hi;
+                            const uint32_t lE = xe ? leU + 1 : 1u;
+                            const int fo = last ? H[r] : H[r] - go - ge, fe = last ? F[r] : F[r] - ge;
+                            const bool xf = A.tie_open ? (fe > fo) : (fe >= fo);
+                            const int f = xf ? fe : fo;
+                            bF[r].lo = xf ? bF[r].lo : sH[r].lo; bF[r].hi = xf ? bF[r].hi : sH[r].hi; lF[r] = xf ? lF[r] + 1 : 1u;
+                            const int mm = hD + edna(ac[r], bj);
+                            const int h = max(mm, max(f, e));
+                            PathSum sHn = ps_append(shD, ac[r] == bj ? PS_EQ : PS_X, 1u);
+                            if (mm != h) sHn = (f == h) ? ps_append(bF[r], PS_D, lF[r]) : ps_append(bE, PS_I, lE);
+                            hD = H[r]; shD = sH[r];                                // my old value (column j-1) is the next row's diagonal
+                            H[r] = h; sH[r] = sHn; F[r] = f;
+                            hU = h; eU = e; shU = sHn; beU = bE; leU = lE;
+                        }
+                    }
+                    Hout = hU; Eout = eU; sHout = shU; bEout = beU; lEout = leU;  // my last row at column j -> next lane
+                    if (lane == 31 && rb + 1 < nrb) { Hb[j] = hU; Eb[j] = eU; sHlo[j] = shU.lo; sHhi[j] = shU.hi; bElo[j] = beU.lo; bEhi[j] = beU.hi; lEb[j] = leU; }
                 }
             }
             if (rb == nrb - 1) {
-                score = __shfl_sync(FULL, Hleft, (m - 1) & 31);
-                sfin.lo = __shfl_sync(FULL, sHleft.lo, (m - 1) & 31); sfin.hi = __shfl_sync(FULL, sHleft.hi, (m - 1) & 31);
+                int hs = 0; PathSum ss = { 0u, 0u };
+#pragma unroll
+                for (int r = 0; r < R; r++) if (i0 + r + 1 == m) { hs = H[r]; ss = sH[r]; }
+                const int src = ((m - 1) - rb * 32 * R) / R;
+                score = __shfl_sync(FULL, hs, src); sfin.lo = __shfl_sync(FULL, ss.lo, src); sfin.hi = __shfl_sync(FULL, ss.hi, src);
             }
             __syncwarp();
         }
@@ -357,7 +381,10 @@ int align_batch_device(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq
         const int nj = (int)jobs.size();
         const int ncol = (maxn + 1 + 31) & ~31;
         const int warps_per_block = 4;
-        const size_t per_warp = (((size_t)ncol * (7 * 4 + 1)) + 15) & ~(size_t)15;
+        constexpr int ROWS = 10;                                   // DP rows per lane: one sweep covers 320 consensus rows
+        int maxm = 0; for (int q = 0; q < n_profiles; q++) maxm = std::max(maxm, a_len[q]);
+        const bool need_boundary = maxm > 32 * ROWS;
+        const size_t per_warp = (((size_t)ncol * (need_boundary ? (7 * 4 + 1) : 1)) + 15) & ~(size_t)15;
         const size_t smem = (size_t)warps_per_block * per_warp;
         if (smem > ctx->smem_optin) return set_err(ctx, KGMA_E_UNSUPPORTED, "subject slice of %d bases too long for the extension kernel", maxn);
         size_t o = 0;
@@ -384,10 +411,11 @@ int align_batch_device(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq
         A.a = d + o_a; A.seq = ctx->d_seq2; A.nruns = (const long long *)(d + o_n); A.n_nruns = (int)(nruns.size() / 2);
         A.b = d + o_b; A.jobs = (const AlignJob2 *)(d + o_j); A.njobs = nj; A.next_job = (int *)(d + o_c);
         A.out = (AlignOut *)(d + o_o); A.go = -gap_open; A.ge = -gap_extend; A.tie_open = tie_open ? 1 : 0; A.ncol_cap = ncol;
-        KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        A.need_boundary = need_boundary ? 1 : 0;
+        KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = std::min((nj + warps_per_block - 1) / warps_per_block, ctx->num_sms * 8);
         KGMA_CUDA(ctx, cudaEventRecord(e0, st));
-        kgma_align_summary<<<grid, warps_per_block * 32, smem, st>>>(A);
+        kgma_align_summary<ROWS><<<grid, warps_per_block * 32, smem, st>>>(A);
         KGMA_CUDA(ctx, cudaGetLastError());
         KGMA_CUDA(ctx, cudaEventRecord(e1, st));
         ctx->stats.launches++;
