@@ -552,3 +552,100 @@ def test_cluster_per_profile_filter_groups(K, O, synth):
     b = K.Omn_KmerGMA(genome_path=path, refVecs=rvs, windowsizes=wss, consensus_seqs=cons, resultVec=[], thr_vec=thrs, buff=100, dense=True)
     assert st["blocks_total"] > 0 and st["exact_windows"] < K.default_context().stats()["exact_windows"]     # the prefilter was used
     assert np.array_equal(a.hits[["record", "profile", "first", "last", "D"]], b.hits[["record", "profile", "first", "last", "D"]])
+
+
+# ------------------------------------------------------------------ BASELINE.json full sizes: size-independent properties
+@pytest.fixture(scope="module")
+def big(K):
+    """configs[1] at full size: the 3.09 Gb synthetic genome bench.py scans (24 contigs, N runs, 2000 planted copies)"""
+    import bench
+    ctx = K.default_context()
+    lens = bench.contig_lengths(1.0)
+    plants = bench.plant_list(lens)
+    g = K.Genome.synth(lens, seed=bench.SEED, n_run_len=bench.N_RUN, centromere_len=bench.CENTROMERE, ctx=ctx)
+    for (r, pos, s) in plants:
+        g.put_seq(r, pos, s)
+    return g, lens, plants
+
+
+def test_full_size_properties(K, O, prof, big):
+    import bench
+    g, lens, plants = big
+    RV, ws, cons = prof
+    L = K.L
+    args = ([RV], [ws], [cons], [bench.THR], 6, L.MODE_SINGLE, bench.BUFF)
+    key = ["record", "first", "last", "D", "genome_pos"]
+    a = K.scan_raw(g, *args, L.F_ALIGN, -69, -1)                                  # streamed from pinned host memory
+    g.make_resident()
+    b = K.scan_raw(g, *args, L.F_ALIGN | L.F_RESIDENT, -69, -1)                   # resident
+    c = K.scan_raw(g, *args, L.F_ALIGN | L.F_RESIDENT | L.F_DENSE, -69, -1)       # every window through the count-table kernel
+    assert len(a.hits) > 1500
+    assert np.array_equal(a.hits[key], b.hits[key]) and np.array_equal(a.hits[key], c.hits[key])
+    # idempotence + sortedness (hits come out in genome order, like the reference's single pass)
+    assert np.array_equal(K.scan_raw(g, *args, L.F_ALIGN | L.F_RESIDENT, -69, -1).hits[key], b.hits[key])
+    order = a.hits["genome_pos"] + a.hits["cmi"]
+    assert np.all(np.diff(order) > 0)
+    # 8 shards, arbitrary order, one replay == the unsharded scan
+    runs, firsts = [], None
+    for s in (5, 2, 7, 0, 3, 6, 1, 4):
+        part = K.scan_raw(g, *args, L.F_RESIDENT, -69, -1, runs_only=True, shard=(s, 8))
+        runs.append(part.runs)
+        firsts = part.first_D if firsts is None else np.maximum(firsts, part.first_D)
+    rep = K.replay_raw(g, *args, L.F_ALIGN, -69, -1, np.concatenate(runs), firsts)
+    assert np.array_equal(rep.hits[key], a.hits[key])
+    # precision / recall against the planted positions: random sequence sits at d ~ 46 +- 4, so every hit must overlap a
+    # planted copy, and the copies within thr of the family profile (most of the <= 10 % ones) must be found
+    by_rec = {}
+    for (r, pos, s) in plants:
+        by_rec.setdefault(r, []).append((pos, pos + len(s) - 1))
+    found = set()
+    for h in a.hits:
+        ov = [(p0, p1) for (p0, p1) in by_rec.get(int(h.record), []) if int(h.first) <= p1 and int(h.last) >= p0]
+        assert ov, "hit %d:%d-%d overlaps no planted copy" % (h.record, h.first, h.last)
+        found.update((int(h.record), p0) for p0, _ in ov)
+    assert len(found) >= 0.75 * len(plants)
+    # the two smallest contigs against the CPU oracle, bit for bit (97 Mb, ~1 s of oracle time)
+    for r in (20, 21):
+        sub = K.Genome.from_records([(g.description(r), g.seq(r))])
+        out = K.scan_raw(sub, *args, L.F_ALIGN, -69, -1)
+        seq = g.seq(r)
+        import tempfile, os
+        with tempfile.TemporaryDirectory() as td:
+            p = os.path.join(td, "c.fasta")
+            with open(p, "w") as fh:
+                fh.write(">" + g.description(r) + "\n" + seq + "\n")
+            oh = assert_parity(K, O, out, lambda: O.ac_gma_testing(p, np.asarray(RV), cons, windowsize=ws, thr=bench.THR, buff=bench.BUFF, do_align=True)[0], RV.n_refs)
+        whole = [(int(h.first), int(h.last), int(h.D)) for h in a.hits if int(h.record) == r]
+        assert whole == [(int(h.first), int(h.last), int(h.D)) for h in out.hits] and len(oh) == len(whole) > 10
+
+
+def test_full_size_exact_match(K, big):
+    """configs[3]: a 300-nt query planted 1000 times (some overlapping themselves, some touching an N run)"""
+    g, lens, plants = big
+    rng = np.random.default_rng(5)
+    unit = "".join(np.asarray(list("ACGT"))[rng.integers(0, 4, size=100)])
+    query = unit * 3                                                       # period 100: overlapping self-matches exist
+    want = {}
+    for i in range(1000):
+        r = int(rng.integers(0, len(lens)))
+        p = int(rng.integers(20000, lens[r] - 20000)) if i % 10 else 10001            # right after the leading N run
+        s = query + (unit if i % 7 == 0 else "")                          # 400-nt tandem: matches at p, p+100
+        g.put_seq(r, p, s)
+        want.setdefault(r, set()).add(p)
+        if i % 7 == 0:
+            want[r].add(p + 100)
+    res = K.exactMatch(query, g, overlap=True)
+    got = {r: set(f for f, l in res.get(g.identifier(r), [])) for r in range(len(lens))}
+    for r in want:
+        assert want[r] <= got[r]                                           # every planted occurrence is found
+    extra = sum(len(got[r] - want.get(r, set())) for r in got)
+    assert extra <= 1000                                                   # later plants may overwrite parts of earlier ones; no spurious flood
+    for r, ranges in ((r, res.get(g.identifier(r), [])) for r in range(len(lens))):
+        assert all(l - f + 1 == 300 for f, l in ranges) and [f for f, _ in ranges] == sorted(f for f, _ in ranges)
+        for f, l in ranges[:50]:
+            assert g.seq(r, f, l) == query                                 # matches really are the query
+    non = K.exactMatch(query, g, overlap=False)
+    for r in range(len(lens)):
+        rs = non.get(g.identifier(r), [])
+        assert all(rs[i + 1][0] > rs[i][1] for i in range(len(rs) - 1))    # FindAll: no two reported matches overlap
+        assert set(f for f, _ in rs) <= got[r]
