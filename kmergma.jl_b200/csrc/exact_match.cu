@@ -58,18 +58,48 @@ __global__ void __launch_bounds__(256) kgma_exact_match_kernel(MatchArgs a)
         uint32_t nw = __shfl_down_sync(FULL, v.x, 1);
         if (lane == 31) nw = __ldg(a.seq + (blk + 1) * 4);
         const uint32_t W[5] = { v.x, v.y, v.z, v.w, nw };
-        unsigned long long hits = 0;                     // bit o set: first 16 bases match at offset o
+        unsigned long long ok = 0;                       // bit o set: the query occurs at offset o of this block
+        if (a.qlen >= 4) {
+            // stage 1, SIMD within a register: a word shifted by r bases holds the 4-mers at offsets r, r+4, r+8, r+12 in its
+            // four bytes; XOR with the query's first 4-mer replicated and the zero-byte test flag the candidates, 4 offsets
+            // per ~5 integer instructions (borrows may flag the byte above a true zero: harmless, stage 2 re-checks).
+            const uint32_t Qb = (a.q0 & 0xFFu) * 0x01010101u;
+            uint32_t T[4];
 #pragma unroll
-        for (int o = 0; o < 64; o++) {
-            const int wi = o >> 4, s = (o & 15) * 2;
-            uint32_t x = s ? __funnelshift_r(W[wi], W[wi + 1], s) : W[wi];
-            if (((x ^ a.q0) & a.m0) == 0) hits |= 1ull << o;
-        }
-        // verify survivors (rare unless the query is low-complexity)
-        unsigned long long ok = 0;
-        while (hits) {
-            int o = __ffsll((long long)hits) - 1; hits &= hits - 1;
-            if (verify_match(a, blk * 64 + o)) ok |= 1ull << o;
+            for (int i = 0; i < 4; i++) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const uint32_t y = r ? __funnelshift_r(W[i], W[i + 1], 2 * r) : W[i];
+                    const uint32_t z = y ^ Qb;
+                    const uint32_t t = (z - 0x01010101u) & ~z & 0x80808080u;
+                    acc |= t >> (7 - r);                 // bit 8b+r  <=>  offset 16i + 4b + r
+                }
+                T[i] = acc;
+            }
+            // stage 2 on the survivors (1 in 64 offsets for random DNA): first 16 bases, then the whole query on both planes
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint32_t t = T[i];
+                while (t) {
+                    const int bit = __ffs((int)t) - 1; t &= t - 1;
+                    const int off = (bit >> 3) * 4 + (bit & 7), o = 16 * i + off;      // off < 16: the offset stays in word i
+                    const uint32_t x = __funnelshift_r(W[i], W[i + 1], 2 * off);
+                    if (((x ^ a.q0) & a.m0) == 0 && verify_match(a, blk * 64 + o)) ok |= 1ull << o;
+                }
+            }
+        } else {
+            unsigned long long hits = 0;                 // bit o set: the (short) query's bases match at offset o
+#pragma unroll
+            for (int o = 0; o < 64; o++) {
+                const int wi = o >> 4, s = (o & 15) * 2;
+                uint32_t x = s ? __funnelshift_r(W[wi], W[wi + 1], s) : W[wi];
+                if (((x ^ a.q0) & a.m0) == 0) hits |= 1ull << o;
+            }
+            while (hits) {
+                int o = __ffsll((long long)hits) - 1; hits &= hits - 1;
+                if (verify_match(a, blk * 64 + o)) ok |= 1ull << o;
+            }
         }
         int n = __popcll(ok);
         // warp-level compaction: exclusive prefix of per-lane counts, one atomic per warp
@@ -87,6 +117,73 @@ __global__ void __launch_bounds__(256) kgma_exact_match_kernel(MatchArgs a)
                 if (pos < a.out_cap) a.out[pos] = (unsigned long long)(blk * 64 + o);
                 pos++;
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sampled search for queries of >= 31 bases (the Horspool idea of BioSequences' own search, turned into a filter that
+// fits a streaming GPU pass).  Take every SW-th aligned 16-base word of the genome (SW = 1, 2, 4 or 8 with
+// qlen >= 16*SW + 15): an occurrence starting at o fully contains the first sampled word at or after o, at query
+// offset j = p - o < 16*SW, so that genome word must be one of the 16*SW query 16-mers at offsets 0 .. 16*SW-1.
+// One hash probe per sampled word (a 512-slot table in shared memory) replaces 16*SW shifted compares; the rare
+// survivors are verified over the whole query on the 2-bit plane and against the list of masked (N) runs.
+// Each occurrence is found exactly once (through its first sampled word).
+struct SampledArgs {
+    const uint32_t *seq;
+    const uint32_t *tab_key; const uint16_t *tab_j;   // [512] open-addressing table: 16-mer -> query offset (0xFFFF = empty)
+    const uint32_t *q2, *qm;                          // packed query planes (padded with one zero word)
+    const long long *nruns; int n_nruns;              // maximal masked runs of the genome, [start,end) ascending
+    int qlen, sw, q_has_n;
+    long long t_begin, t_end;                         // sampled-word indices to test
+    long long g_end;                                  // end of the packed genome (bases): no occurrence may reach past it
+    unsigned long long *out; uint32_t out_cap; uint32_t *out_count;
+};
+
+__device__ bool verify_sampled(const SampledArgs &a, long long p)
+{
+    const int nw = (a.qlen + 15) >> 4;
+    const uint32_t *w = a.seq + (p >> 4); const int sh = (int)(p & 15) * 2;
+    for (int i = 0; i < nw; i++) {
+        uint32_t x = __funnelshift_r(__ldg(w + i), __ldg(w + i + 1), sh);
+        uint32_t m = (i == nw - 1 && (a.qlen & 15)) ? ((1u << (2 * (a.qlen & 15))) - 1) : 0xFFFFFFFFu;
+        if ((x ^ a.q2[i]) & m) return false;
+    }
+    // ambiguity: a masked genome base only equals a masked (N) query base and vice versa
+    int lo = -1, hi = a.n_nruns;                       // last run with start < p + qlen
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (a.nruns[2 * mid] < p + a.qlen) lo = mid; else hi = mid; }
+    const bool genome_masked_here = lo >= 0 && a.nruns[2 * lo + 1] > p;     // some run intersects [p, p+qlen)
+    if (!genome_masked_here) return !a.q_has_n;
+    for (int i = 0; i < a.qlen; i++) {                 // rare: a run touches the window, compare base by base
+        const long long gp = p + i;
+        int l2 = -1, h2 = a.n_nruns;
+        while (h2 - l2 > 1) { int mid = (l2 + h2) >> 1; if (a.nruns[2 * mid] <= gp) l2 = mid; else h2 = mid; }
+        const bool gm = l2 >= 0 && gp < a.nruns[2 * l2 + 1];
+        const bool qmk = (a.qm[i >> 5] >> (i & 31)) & 1u;
+        if (gm != qmk) return false;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(256) kgma_exact_match_sampled(SampledArgs a)
+{
+    __shared__ uint32_t s_key[512];
+    __shared__ uint16_t s_j[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) { s_key[i] = a.tab_key[i]; s_j[i] = a.tab_j[i]; }
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = a.t_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; t < a.t_end; t += stride) {
+        const uint32_t w = __ldg(a.seq + t * a.sw);
+        uint32_t h = (w * 2654435761u) >> 23;          // 9-bit multiplicative hash
+        while (s_j[h] != 0xFFFFu) {
+            if (s_key[h] == w) {
+                const long long start = t * a.sw * 16 - (long long)s_j[h];
+                if (start >= 0 && start + a.qlen <= a.g_end && verify_sampled(a, start)) {
+                    const uint32_t pos = atomicAdd(a.out_count, 1u);
+                    if (pos < a.out_cap) a.out[pos] = (unsigned long long)start;
+                }
+            }
+            h = (h + 1) & 511u;
         }
     }
 }
@@ -121,41 +218,106 @@ extern "C" int kgma_exact_match(kgma_ctx *ctx, kgma_genome *g, const char *query
     if (rc) return rc;
     rc = genome_pin(ctx, g);
     if (rc) return rc;
-    cudaStream_t st = ctx->s_compute;
+    cudaStream_t st = ctx->s_compute, sp = ctx->s_copy;
     kgma_stats &S = ctx->stats; S = kgma_stats{};
-    cudaEvent_t e0 = ctx->ev[0], e1 = ctx->ev[1], e2 = ctx->ev[2];
-    KGMA_CUDA(ctx, cudaEventRecord(e0, st));
+    cudaEvent_t e0 = ctx->ev[0], e1 = ctx->ev[1], e2 = ctx->ev[2], ek = ctx->ev[3];
     const size_t bases = (size_t)(g->G + TAIL_PAD);
-    const bool have = (flags & KGMA_F_RESIDENT) && ctx->d_seq_valid && ctx->d_mask_valid && ctx->d_valid_lo == 0 && ctx->d_valid_hi >= (int64_t)bases;
-    if (!have) {
-        KGMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_seq2, g->seq2, bases / 4, cudaMemcpyHostToDevice, st));
-        KGMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_mask, g->mask, bases / 8, cudaMemcpyHostToDevice, st));
-        S.h2d_bytes += bases / 4 + bases / 8;
-        ctx->d_seq_valid = ctx->d_mask_valid = true; ctx->d_valid_lo = 0; ctx->d_valid_hi = (int64_t)bases;
-        ctx->d_have_lo = 0; ctx->d_have_hi = (int64_t)bases;
+    const bool have = (flags & KGMA_F_RESIDENT) && ctx->d_seq_valid && ctx->d_valid_lo == 0 && ctx->d_valid_hi >= (int64_t)bases;
+    // sampling stride in 16-base words: the largest of 8,4,2,1 with qlen >= 16*sw + 15 (0: short query, dense compare)
+    int sw = 0;
+    for (int c = 8; c >= 1; c >>= 1) if (qlen >= 16 * c + 15) { sw = c; break; }
+    const std::vector<int64_t> &nruns = genome_nruns(g);
+    const bool need_mask_plane = sw == 0;               // only the dense kernel reads the ambiguity plane
+    bool q_has_n = false; for (uint32_t w : qm) q_has_n |= w != 0;
+    // hash table of the query 16-mers at offsets 0 .. 16*sw-1
+    std::vector<uint32_t> tkey(512, 0); std::vector<uint16_t> tj(512, 0xFFFFu);
+    for (int j = 0; j < 16 * sw; j++) {
+        const uint32_t w = (uint32_t)((((uint64_t)q2[(size_t)(j >> 4) + 1] << 32 | q2[(size_t)(j >> 4)]) >> (2 * (j & 15))) & 0xFFFFFFFFu);
+        uint32_t h = (w * 2654435761u) >> 23;
+        while (tj[h] != 0xFFFFu) h = (h + 1) & 511u;
+        tkey[h] = w; tj[h] = (uint16_t)j;
     }
-    KGMA_CUDA(ctx, cudaEventRecord(e1, st));
     const uint32_t cap = 1u << 24;
     size_t o = 0;
     auto carve = [&](size_t b) { size_t r = o; o += (b + 255) / 256 * 256; return r; };
-    size_t o_q2 = carve(q2.size() * 4), o_qm = carve(qm.size() * 4), o_c = carve(256), o_out = carve((size_t)cap * 8);
-    void *dv = nullptr;
+    size_t o_q2 = carve(q2.size() * 4), o_qm = carve(qm.size() * 4), o_tk = carve(512 * 4), o_tj = carve(512 * 2), o_nr = carve(nruns.size() * 8 + 8);
+    const size_t up = o;
+    size_t o_c = carve(256), o_out = carve((size_t)cap * 8);
+    void *dv = nullptr, *hv = nullptr;
     rc = dev_scratch(ctx, o, &dv);
     if (rc) return rc;
-    unsigned char *d = (unsigned char *)dv;
-    KGMA_CUDA(ctx, cudaMemcpyAsync(d + o_q2, q2.data(), q2.size() * 4, cudaMemcpyHostToDevice, st));
-    KGMA_CUDA(ctx, cudaMemcpyAsync(d + o_qm, qm.data(), qm.size() * 4, cudaMemcpyHostToDevice, st));
+    rc = host_scratch(ctx, up, &hv);
+    if (rc) return rc;
+    unsigned char *d = (unsigned char *)dv, *h = (unsigned char *)hv;
+    memcpy(h + o_q2, q2.data(), q2.size() * 4); memcpy(h + o_qm, qm.data(), qm.size() * 4);
+    memcpy(h + o_tk, tkey.data(), 512 * 4); memcpy(h + o_tj, tj.data(), 512 * 2);
+    if (!nruns.empty()) memcpy(h + o_nr, nruns.data(), nruns.size() * 8);
+    KGMA_CUDA(ctx, cudaEventRecord(e0, st));
+    KGMA_CUDA(ctx, cudaMemcpyAsync(d, h, up, cudaMemcpyHostToDevice, st));
     KGMA_CUDA(ctx, cudaMemsetAsync(d + o_c, 0, 256, st));
+    S.h2d_bytes += up;
+
     MatchArgs a{};
     a.seq4 = (const uint4 *)ctx->d_seq2; a.seq = ctx->d_seq2; a.mask = ctx->d_mask;
     a.q2 = (const uint32_t *)(d + o_q2); a.qm = (const uint32_t *)(d + o_qm); a.qlen = (int)qlen;
     const int f = (int)std::min<int64_t>(qlen, 16);
     a.q0 = q2[0]; a.m0 = f == 16 ? 0xFFFFFFFFu : ((1u << (2 * f)) - 1);
-    a.blk_begin = 0; a.blk_end = g->G / FBLOCK;
     a.out = (unsigned long long *)(d + o_out); a.out_cap = cap; a.out_count = (uint32_t *)(d + o_c);
-    kgma_exact_match_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(a);
-    KGMA_CUDA(ctx, cudaGetLastError());
-    S.launches++;
+    SampledArgs sa{};
+    sa.seq = ctx->d_seq2; sa.tab_key = (const uint32_t *)(d + o_tk); sa.tab_j = (const uint16_t *)(d + o_tj);
+    sa.q2 = a.q2; sa.qm = a.qm; sa.nruns = (const long long *)(d + o_nr); sa.n_nruns = (int)(nruns.size() / 2);
+    sa.qlen = (int)qlen; sa.sw = sw; sa.q_has_n = q_has_n ? 1 : 0; sa.g_end = g->G;
+    sa.out = a.out; sa.out_cap = cap; sa.out_count = a.out_count;
+
+    // search [done, upto) in bases (multiples of 2048), given that the genome is on the device up to avail_hi
+    const int64_t G = g->G;
+    int64_t done = 0; bool first_kernel = true;
+    auto search_to = [&](int64_t avail_hi, bool last) -> int {
+        int64_t upto = last ? G : std::min<int64_t>(G, (avail_hi - qlen - 4 * FGROUP) / FGROUP * FGROUP);
+        if (upto <= done) return KGMA_OK;
+        if (first_kernel) { KGMA_CUDA(ctx, cudaEventRecord(ek, st)); first_kernel = false; }
+        if (sw > 0) {
+            sa.t_begin = done / (16 * sw); sa.t_end = upto / (16 * sw);
+            const long long nt = sa.t_end - sa.t_begin;
+            const int grid = (int)std::min<long long>((nt + 255) / 256, (long long)ctx->num_sms * 16);
+            kgma_exact_match_sampled<<<std::max(grid, 1), 256, 0, st>>>(sa);
+        } else {
+            a.blk_begin = done / FBLOCK; a.blk_end = upto / FBLOCK;
+            kgma_exact_match_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(a);
+        }
+        KGMA_CUDA(ctx, cudaGetLastError());
+        S.launches++;
+        done = upto;
+        return KGMA_OK;
+    };
+    if (!have) {
+        // stream the 2-bit plane in 32 MB chunks on the copy stream, the search chasing it (the ambiguity plane is only
+        // uploaded for short queries; long ones check N against the list of masked runs)
+        if (need_mask_plane) { KGMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_mask, g->mask, bases / 8, cudaMemcpyHostToDevice, st)); S.h2d_bytes += bases / 8; ctx->d_mask_valid = true; }
+        cudaEvent_t e_c[2] = { ctx->ev[5], ctx->ev[6] };
+        KGMA_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
+        KGMA_CUDA(ctx, cudaStreamWaitEvent(sp, ctx->ev[7], 0));
+        const int64_t CH = (int64_t)128 << 20; int ci = 0;
+        for (int64_t lo = 0; lo < (int64_t)bases; lo += CH, ci++) {
+            const int64_t hi = std::min<int64_t>((int64_t)bases, lo + CH);
+            KGMA_CUDA(ctx, cudaMemcpyAsync((char *)ctx->d_seq2 + lo / 4, (char *)g->seq2 + lo / 4, (size_t)(hi - lo) / 4, cudaMemcpyHostToDevice, sp));
+            KGMA_CUDA(ctx, cudaEventRecord(e_c[ci & 1], sp));
+            KGMA_CUDA(ctx, cudaStreamWaitEvent(st, e_c[ci & 1], 0));
+            S.h2d_bytes += (hi - lo) / 4;
+            rc = search_to(hi, hi >= (int64_t)bases);
+            if (rc) return rc;
+            if (ci >= 1) KGMA_CUDA(ctx, cudaEventSynchronize(e_c[(ci - 1) & 1]));
+        }
+        ctx->d_seq_valid = true; ctx->d_valid_lo = 0; ctx->d_valid_hi = (int64_t)bases;
+        ctx->d_have_lo = 0; ctx->d_have_hi = (int64_t)bases;
+        KGMA_CUDA(ctx, cudaEventRecord(e1, st));
+    } else {
+        if (need_mask_plane && !ctx->d_mask_valid) { KGMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_mask, g->mask, bases / 8, cudaMemcpyHostToDevice, st)); S.h2d_bytes += bases / 8; ctx->d_mask_valid = true; }
+        KGMA_CUDA(ctx, cudaEventRecord(e1, st));
+        rc = search_to((int64_t)bases, true);
+        if (rc) return rc;
+    }
+    if (first_kernel) KGMA_CUDA(ctx, cudaEventRecord(ek, st));
     KGMA_CUDA(ctx, cudaEventRecord(e2, st));
     uint32_t cnt = 0;
     KGMA_CUDA(ctx, cudaMemcpyAsync(&cnt, d + o_c, 4, cudaMemcpyDeviceToHost, st));
@@ -165,7 +327,7 @@ extern "C" int kgma_exact_match(kgma_ctx *ctx, kgma_genome *g, const char *query
     if (cnt) KGMA_CUDA(ctx, cudaMemcpy(pos.data(), d + o_out, (size_t)cnt * 8, cudaMemcpyDeviceToHost));
     S.d2h_bytes += 4 + (size_t)cnt * 8;
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); S.h2d_ms = ms;
-    cudaEventElapsedTime(&ms, e1, e2); S.filter_ms = ms;
+    cudaEventElapsedTime(&ms, ek, e2); S.filter_ms = ms;
     cudaEventElapsedTime(&ms, e0, e2); S.total_ms = ms;
     S.bases_scanned = g->total_len;
     if (!(flags & KGMA_F_RESIDENT)) ctx->d_seq_valid = ctx->d_mask_valid = false;
