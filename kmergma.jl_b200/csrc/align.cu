@@ -171,8 +171,10 @@ struct AlignArgs2 {
     int go, ge, tie_open, ncol_cap, need_boundary;
 };
 
-// path summary, two 32-bit words:  lo = total columns | first-run length << 16
-//                                   hi = last-run length (0-11.. up to 65535 & 0xFFFF) | last op << 16 | (>= 2 runs) << 18 | non-empty << 19
+// path summary, two 32-bit words:
+//   lo = total columns (bits 0-15) | length of the first run << 16   (the first-run field stays 0 while the path is
+//        still ONE run and is captured from `total` at the first change of op)
+//   hi = last-run length (0-15) | last op << 16 | (>= 2 runs) << 18 | non-empty << 19
 // Gap states do not append per cell: E / F keep the summary of the H cell the gap was opened from plus the gap
 // length, and the run is appended only when H actually selects the gap (rare with EDNAFULL and gap_open << 0).
 #define PS_EQ 0u
@@ -184,14 +186,15 @@ struct AlignArgs2 {
 struct PathSum { uint32_t lo, hi; };
 __device__ __forceinline__ PathSum ps_run(uint32_t len, uint32_t op)
 {
-    PathSum r; r.lo = len ? (len | (len << 16)) : 0u; r.hi = len ? (len | (op << 16) | PS_NE) : 0u; return r;
+    PathSum r; r.lo = len; r.hi = len ? (len | (op << 16) | PS_NE) : 0u; return r;
 }
 __device__ __forceinline__ PathSum ps_append(PathSum s, uint32_t op, uint32_t len)
 {
     PathSum r;
-    if (!(s.hi & PS_NE)) return ps_run(len, op);
-    if (((s.hi >> 16) & 3u) == op) { r.lo = s.lo + len + ((s.hi & PS_MULTI) ? 0u : (len << 16)); r.hi = s.hi + len; }
-    else { r.lo = s.lo + len; r.hi = len | (op << 16) | PS_MULTI | PS_NE; }
+    const bool same = ((s.hi ^ (op << 16)) & ((3u << 16) | PS_NE)) == PS_NE;          // non-empty and same op
+    const uint32_t cap = (same || (s.hi & PS_MULTI)) ? 0u : (s.lo << 16);           // first change of op: first run = total so far
+    r.lo = s.lo + len + cap;
+    r.hi = same ? s.hi + len : (len | (op << 16) | PS_NE | ((s.hi >> 1) & PS_MULTI));
     return r;
 }
 
@@ -199,18 +202,18 @@ __device__ __forceinline__ PathSum ps_append(PathSum s, uint32_t op, uint32_t le
 // skewed by one column, so a whole 289-row alignment is ONE sweep of n+31 steps with R = 10 (instead of ten
 // sweeps of 32 rows): 7 shuffles per step are amortised over R cells and the per-step bookkeeping shrinks 10x.
 template <int R>
-__global__ void __launch_bounds__(128) kgma_align_summary(AlignArgs2 A)
+__global__ void __launch_bounds__(128, 3) kgma_align_summary(AlignArgs2 A)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const size_t per_warp = (size_t)A.ncol_cap * (A.need_boundary ? (7 * 4 + 1) : 1);
+    const size_t per_warp = (size_t)A.ncol_cap * (A.need_boundary ? (6 * 4 + 1) : 1);
     unsigned char *wb = s_raw + (size_t)wid * ((per_warp + 15) & ~(size_t)15);
     // bottom row of a sweep, parked for the next sweep (only when the consensus is longer than 32*R)
     int *Hb = reinterpret_cast<int *>(wb), *Eb = Hb + A.ncol_cap;
     uint32_t *sHlo = reinterpret_cast<uint32_t *>(Eb + A.ncol_cap), *sHhi = sHlo + A.ncol_cap;
-    uint32_t *bElo = sHhi + A.ncol_cap, *bEhi = bElo + A.ncol_cap, *lEb = bEhi + A.ncol_cap;
-    uint8_t *bs = A.need_boundary ? reinterpret_cast<uint8_t *>(lEb + A.ncol_cap) : wb;
+    uint32_t *bElo = sHhi + A.ncol_cap, *bEhi = bElo + A.ncol_cap;
+    uint8_t *bs = A.need_boundary ? reinterpret_cast<uint8_t *>(bEhi + A.ncol_cap) : wb;
     const int NEG = -(1 << 29);
     const int go = A.go, ge = A.ge;
 
@@ -239,59 +242,69 @@ __global__ void __launch_bounds__(128) kgma_align_summary(AlignArgs2 A)
         const int nrb = (m + 32 * R - 1) / (32 * R);
         for (int rb = 0; rb < nrb; rb++) {
             const int i0 = rb * 32 * R + lane * R;                                // this lane owns rows i0+1 .. i0+R
-            int H[R], F[R]; PathSum sH[R], bF[R]; uint32_t lF[R]; int ac[R];
+            // per row: scores, H-path summary, and the deletion-gap state (summary at gap open; its hi word carries the
+            // gap length in bits 20-31, which the summary itself never uses)
+            int H[R], F[R]; PathSum sH[R], bF[R]; uint32_t sc[R]; int gof[R], gef[R];
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const int i = i0 + r + 1;
                 H[r] = -(go + i * ge); F[r] = NEG;                                // H[i][0], F[i][0]
-                sH[r] = ps_run((uint32_t)i, PS_I); bF[r].lo = bF[r].hi = 0; lF[r] = 0;
-                ac[r] = i <= m ? a[i - 1] : 0;
+                sH[r] = ps_run((uint32_t)i, PS_I); bF[r].lo = bF[r].hi = 0;
+                const int ai = i <= m ? a[i - 1] : 0;
+                // EDNAFULL row for this consensus symbol: 4 bits per subject code (score + 4), the symbol itself in bits 20-22
+                uint32_t t = (uint32_t)ai << 20;
+#pragma unroll
+                for (int c = 0; c < 5; c++) t |= (uint32_t)(edna(ai, c) + 4) << (4 * c);
+                sc[r] = t;
+                gof[r] = (i == m) ? 0 : go + ge; gef[r] = (i == m) ? 0 : ge;      // trailing deletions after the last row are free
             }
             int Hdiag0 = (i0 == 0) ? 0 : -(go + i0 * ge);                         // H[i0][0]: diagonal of my first row at column 1
             PathSum sHdiag0 = ps_run((uint32_t)i0, PS_I);
-            int Hout = NEG, Eout = NEG; PathSum sHout = { 0u, 0u }, bEout = { 0u, 0u }; uint32_t lEout = 0;
+            int Hout = NEG, Eout = NEG; PathSum sHout = { 0u, 0u }, bEout = { 0u, 0u };
             const bool lane_ok = i0 < m;
+            const int gog = go + ge;
+            const uint32_t GL1 = 1u << 20, SUMM = GL1 - 1;                        // gap-length unit / summary bits of a hi word
             for (int s = 1; s <= n + 31; s++) {
                 const int j = s - lane;
                 int upH = __shfl_up_sync(FULL, Hout, 1), upE = __shfl_up_sync(FULL, Eout, 1);
-                PathSum supH, ubE; uint32_t ulE;
+                PathSum supH, ubE;
                 supH.lo = __shfl_up_sync(FULL, sHout.lo, 1); supH.hi = __shfl_up_sync(FULL, sHout.hi, 1);
                 ubE.lo = __shfl_up_sync(FULL, bEout.lo, 1); ubE.hi = __shfl_up_sync(FULL, bEout.hi, 1);
-                ulE = __shfl_up_sync(FULL, lEout, 1);
                 if (lane == 0 && j >= 1 && j <= n) {
-                    if (rb == 0) { upH = 0; upE = NEG; supH = ps_run((uint32_t)j, PS_D); ubE.lo = ubE.hi = 0; ulE = 0; }   // row 0: free leading deletions
-                    else { upH = Hb[j]; upE = Eb[j]; supH.lo = sHlo[j]; supH.hi = sHhi[j]; ubE.lo = bElo[j]; ubE.hi = bEhi[j]; ulE = lEb[j]; }
+                    if (rb == 0) { upH = 0; upE = NEG; supH = ps_run((uint32_t)j, PS_D); ubE.lo = ubE.hi = 0; }   // row 0: free leading deletions
+                    else { upH = Hb[j]; upE = Eb[j]; supH.lo = sHlo[j]; supH.hi = sHhi[j]; ubE.lo = bElo[j]; ubE.hi = bEhi[j]; }
                 }
                 if (lane_ok && j >= 1 && j <= n) {
-                    const int bj = bs[j - 1];
-                    int hU = upH, eU = upE; PathSum shU = supH, beU = ubE; uint32_t leU = ulE;    // row above, column j
+                    const uint32_t bj = bs[j - 1];
+                    const int bsh = 4 * (int)bj;
+                    int hU = upH, eU = upE; PathSum shU = supH, beU = ubE;                        // row above, column j
                     int hD = Hdiag0; PathSum shD = sHdiag0;                                       // row above, column j-1
                     Hdiag0 = upH; sHdiag0 = supH;
+                    // rows past the end of the consensus (last lane only) compute harmless garbage nobody reads
 #pragma unroll
                     for (int r = 0; r < R; r++) {
-                        const int i = i0 + r + 1;
-                        if (i <= m) {
-                            const bool last = (i == m);
-                            const int eo = hU - go - ge, ee = eU - ge;
-                            const bool xe = A.tie_open ? (ee > eo) : (ee >= eo);
-                            const int e = xe ? ee : eo;
-                            PathSum bE; bE.lo = xe ? beU.lo : shU.lo; bE.hi = xe ? beU.hi : shU.hi;
-                            const uint32_t lE = xe ? leU + 1 : 1u;
-                            const int fo = last ? H[r] : H[r] - go - ge, fe = last ? F[r] : F[r] - ge;
-                            const bool xf = A.tie_open ? (fe > fo) : (fe >= fo);
-                            const int f = xf ? fe : fo;
-                            bF[r].lo = xf ? bF[r].lo : sH[r].lo; bF[r].hi = xf ? bF[r].hi : sH[r].hi; lF[r] = xf ? lF[r] + 1 : 1u;
-                            const int mm = hD + edna(ac[r], bj);
-                            const int h = max(mm, max(f, e));
-                            PathSum sHn = ps_append(shD, ac[r] == bj ? PS_EQ : PS_X, 1u);
-                            if (mm != h) sHn = (f == h) ? ps_append(bF[r], PS_D, lF[r]) : ps_append(bE, PS_I, lE);
-                            hD = H[r]; shD = sH[r];                                // my old value (column j-1) is the next row's diagonal
-                            H[r] = h; sH[r] = sHn; F[r] = f;
-                            hU = h; eU = e; shU = sHn; beU = bE; leU = lE;
+                        const int eo = hU - gog, ee = eU - ge;
+                        const bool xe = A.tie_open ? (ee > eo) : (ee >= eo);
+                        const int e = xe ? ee : eo;
+                        PathSum bE; bE.lo = xe ? beU.lo : shU.lo; bE.hi = (xe ? beU.hi : shU.hi) + GL1;   // extend: +1; open: summary | 1
+                        const int fo = H[r] - gof[r], fe = F[r] - gef[r];
+                        const bool xf = A.tie_open ? (fe > fo) : (fe >= fo);
+                        const int f = xf ? fe : fo;
+                        bF[r].lo = xf ? bF[r].lo : sH[r].lo; bF[r].hi = (xf ? bF[r].hi : sH[r].hi) + GL1;
+                        const int mm = hD + (int)((sc[r] >> bsh) & 15u) - 4;
+                        const int h = max(mm, max(f, e));
+                        PathSum sHn = ps_append(shD, (sc[r] >> 20) == bj ? PS_EQ : PS_X, 1u);
+                        if (mm != h) {
+                            PathSum g = (f == h) ? bF[r] : bE;
+                            const uint32_t glen = g.hi >> 20; g.hi &= SUMM;
+                            sHn = ps_append(g, (f == h) ? PS_D : PS_I, glen);
                         }
+                        hD = H[r]; shD = sH[r];                                    // my old value (column j-1) is the next row's diagonal
+                        H[r] = h; sH[r] = sHn; F[r] = f;
+                        hU = h; eU = e; shU = sHn; beU = bE;
                     }
-                    Hout = hU; Eout = eU; sHout = shU; bEout = beU; lEout = leU;  // my last row at column j -> next lane
-                    if (lane == 31 && rb + 1 < nrb) { Hb[j] = hU; Eb[j] = eU; sHlo[j] = shU.lo; sHhi[j] = shU.hi; bElo[j] = beU.lo; bEhi[j] = beU.hi; lEb[j] = leU; }
+                    Hout = hU; Eout = eU; sHout = shU; bEout = beU;               // my last row at column j -> next lane
+                    if (lane == 31 && rb + 1 < nrb) { Hb[j] = hU; Eb[j] = eU; sHlo[j] = shU.lo; sHhi[j] = shU.hi; bElo[j] = beU.lo; bEhi[j] = beU.hi; }
                 }
             }
             if (rb == nrb - 1) {
@@ -366,7 +379,7 @@ int align_batch_device(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq
             AlignJob2 &J = jobs[i];
             J.gpos = R.off + rq.first - 1; J.n = (int)(rq.last - rq.first + 1); J.a_off = a_off[rq.profile]; J.m = a_len[rq.profile]; J.b_off = -1;
             maxn = std::max(maxn, J.n);
-            if (J.m + J.n >= 65535) return set_err(ctx, KGMA_E_UNSUPPORTED, "alignment of %d x %d too long", J.m, J.n);
+            if (J.m + J.n >= 4095) return set_err(ctx, KGMA_E_UNSUPPORTED, "alignment of %d x %d too long for the extension kernel (12-bit gap lengths)", J.m, J.n);
             if (!(on_dev && J.gpos >= ctx->d_have_lo && J.gpos + J.n + 16 <= ctx->d_have_hi)) {      // slice lives on another shard's device: ship codes
                 J.b_off = (int32_t)bcodes.size();
                 for (int64_t p = rq.first; p <= rq.last; p++) {
@@ -384,7 +397,7 @@ int align_batch_device(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq
         constexpr int ROWS = 10;                                   // DP rows per lane: one sweep covers 320 consensus rows
         int maxm = 0; for (int q = 0; q < n_profiles; q++) maxm = std::max(maxm, a_len[q]);
         const bool need_boundary = maxm > 32 * ROWS;
-        const size_t per_warp = (((size_t)ncol * (need_boundary ? (7 * 4 + 1) : 1)) + 15) & ~(size_t)15;
+        const size_t per_warp = (((size_t)ncol * (need_boundary ? (6 * 4 + 1) : 1)) + 15) & ~(size_t)15;
         const size_t smem = (size_t)warps_per_block * per_warp;
         if (smem > ctx->smem_optin) return set_err(ctx, KGMA_E_UNSUPPORTED, "subject slice of %d bases too long for the extension kernel", maxn);
         size_t o = 0;
