@@ -262,6 +262,71 @@ int kgma_genome_seal(kgma_genome *g)
     return KGMA_OK;
 }
 
+}  // extern "C"
+
+// ---- parallel FASTA ingest -------------------------------------------------------------------------------------
+// The file is mmap'ed; header lines are located, every record's residue bytes are cut into ~4 MB tasks, a first
+// parallel pass counts residues per task (so every task knows its base offset), a second packs straight from the
+// mapping into the 2-bit and ambiguity planes.  Words shared by two tasks are merged with atomic ORs.
+namespace kgma {
+
+struct FastaTask { int rec; const char *b, *e; int64_t base0 = 0, nres = 0, bad = -1, amb = -1; bool anymask = false; };
+
+static inline bool is_ws(unsigned char c) { return c == '\n' || c == '\r' || c == ' ' || c == '\t'; }
+
+static void count_task(FastaTask &t)
+{
+    int64_t n = 0;
+    for (const char *p = t.b; p < t.e; ++p) n += !is_ws((unsigned char)*p);
+    t.nres = n;
+}
+
+static void pack_task(kgma_genome *g, int64_t rec_off, FastaTask &t)
+{
+    int64_t gp = rec_off + t.base0, i = t.base0;            // global position / position in the record of the next residue
+    const int64_t gp_end = gp + t.nres;
+    uint32_t w = 0, mw = 0;
+    auto flush_seq = [&](int64_t word, bool shared) {
+        if (!w) return;
+        if (shared) __atomic_fetch_or(&g->seq2[word], w, __ATOMIC_RELAXED); else g->seq2[word] = w;
+        w = 0;
+    };
+    auto flush_mask = [&](int64_t word, bool shared) {
+        if (!mw) return;
+        if (shared) __atomic_fetch_or(&g->mask[word], mw, __ATOMIC_RELAXED); else g->mask[word] |= mw;
+        mw = 0;
+    };
+    const int64_t first_w = gp >> 4, last_w = (gp_end - 1) >> 4, first_m = gp >> 5, last_m = (gp_end - 1) >> 5;
+    for (const char *p = t.b; p < t.e; ++p) {
+        const unsigned char ch = (unsigned char)*p;
+        if (is_ws(ch)) continue;
+        uint8_t c = CT.t[ch];
+        if (c == 0xFF) { if (t.bad < 0) t.bad = i; c = 0; }
+        w |= (uint32_t)(c & 3) << (2 * (gp & 15));
+        if (c & 4) { mw |= 1u << (gp & 31); t.anymask = true; if ((c & 8) && t.amb < 0) t.amb = i; }
+        ++gp; ++i;
+        if ((gp & 15) == 0) { const int64_t wd = (gp >> 4) - 1; flush_seq(wd, wd == first_w || wd == last_w); }
+        if ((gp & 31) == 0) { const int64_t wd = (gp >> 5) - 1; flush_mask(wd, wd == first_m || wd == last_m); }
+    }
+    if (gp & 15) flush_seq(gp >> 4, true);
+    if (gp & 31) flush_mask(gp >> 5, true);
+}
+
+template <typename F> static void parallel_for(size_t n, int nthreads, F f)
+{
+    if (n == 0) return;
+    nthreads = (int)std::min<size_t>((size_t)std::max(1, nthreads), n);
+    if (nthreads == 1) { for (size_t i = 0; i < n; i++) f(i); return; }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) th.emplace_back([&]() { for (;;) { size_t i = next.fetch_add(1); if (i >= n) break; f(i); } });
+    for (auto &x : th) x.join();
+}
+
+}  // namespace kgma
+
+extern "C" {
+
 int kgma_genome_from_fasta(const char *path, kgma_genome **out)
 {
     if (!path || !out) return KGMA_E_ARG;
@@ -271,30 +336,66 @@ int kgma_genome_from_fasta(const char *path, kgma_genome **out)
     size_t sz = (size_t)st.st_size;
     const char *buf = sz ? (const char *)mmap(nullptr, sz, PROT_READ, MAP_PRIVATE, fd, 0) : "";
     if (sz && buf == MAP_FAILED) { close(fd); return KGMA_E_IO; }
+    if (sz) madvise((void *)buf, sz, MADV_SEQUENTIAL | MADV_WILLNEED);
+    const int nthreads = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
     kgma_genome *g = nullptr; kgma_genome_create(&g);
-    int rc = KGMA_OK;
-    size_t i = 0;
-    std::string seq;
-    while (i < sz && rc == KGMA_OK) {
-        if (buf[i] != '>') { while (i < sz && buf[i] != '\n') i++; i++; continue; }
-        size_t hs = i + 1; while (i < sz && buf[i] != '\n') i++;
-        size_t he = i; if (he > hs && buf[he - 1] == '\r') he--;
-        std::string desc(buf + hs, he - hs);
-        size_t ie = 0; while (ie < desc.size() && !isspace((unsigned char)desc[ie])) ie++;
-        std::string ident = desc.substr(0, ie);
-        // gather residues until the next header line
-        seq.clear();
-        size_t j = i + 1;
-        while (j < sz) {
-            if (buf[j] == '>') break;                       // j is at a line start here
-            size_t ls = j; const char *nl = (const char *)memchr(buf + j, '\n', sz - j);
-            size_t le = nl ? (size_t)(nl - buf) : sz;
-            j = nl ? le + 1 : sz;
-            while (le > ls && (buf[le - 1] == '\r' || buf[le - 1] == ' ' || buf[le - 1] == '\t')) le--;
-            seq.append(buf + ls, le - ls);
+
+    // ---- header lines: '>' at the start of a line (found in parallel over 8 MB slices)
+    const size_t SL = (size_t)8 << 20, nsl = (sz + SL - 1) / SL;
+    std::vector<std::vector<size_t>> hdrs(nsl);
+    parallel_for(nsl, nthreads, [&](size_t si) {
+        const size_t lo = si * SL, hi = std::min(sz, lo + SL);
+        const char *p = buf + lo;
+        while (p < buf + hi) {
+            const char *q = (const char *)memchr(p, '>', (size_t)(buf + hi - p));
+            if (!q) break;
+            if (q == buf || q[-1] == '\n') hdrs[si].push_back((size_t)(q - buf));
+            p = q + 1;
         }
-        rc = append_ascii_impl(g, ident.c_str(), desc.c_str(), seq.data(), (int64_t)seq.size());
-        i = j;
+    });
+    std::vector<size_t> hpos;
+    for (auto &v : hdrs) hpos.insert(hpos.end(), v.begin(), v.end());
+
+    // ---- records and tasks
+    const size_t TASK = (size_t)4 << 20;
+    std::vector<FastaTask> tasks;
+    struct RecSpan { std::string ident, desc; size_t first_task, n_tasks; };
+    std::vector<RecSpan> spans(hpos.size());
+    for (size_t r = 0; r < hpos.size(); r++) {
+        const size_t hs = hpos[r] + 1;
+        const char *nl = (const char *)memchr(buf + hs, '\n', sz - hs);
+        size_t he = nl ? (size_t)(nl - buf) : sz;
+        const size_t ss = nl ? he + 1 : sz, se = (r + 1 < hpos.size()) ? hpos[r + 1] : sz;
+        if (he > hs && buf[he - 1] == '\r') he--;
+        spans[r].desc.assign(buf + hs, he - hs);
+        size_t ie = 0; while (ie < spans[r].desc.size() && !isspace((unsigned char)spans[r].desc[ie])) ie++;
+        spans[r].ident = spans[r].desc.substr(0, ie);
+        spans[r].first_task = tasks.size();
+        for (size_t a = ss; a < se || a == ss; a += TASK) {
+            FastaTask t; t.rec = (int)r; t.b = buf + a; t.e = buf + std::min(se, a + TASK);
+            tasks.push_back(t);
+            if (a + TASK >= se) break;
+        }
+        spans[r].n_tasks = tasks.size() - spans[r].first_task;
+    }
+    parallel_for(tasks.size(), nthreads, [&](size_t i) { count_task(tasks[i]); });
+
+    // ---- layout: record lengths, offsets, one reservation
+    int rc = KGMA_OK;
+    for (size_t r = 0; r < spans.size(); r++) {
+        int64_t len = 0;
+        for (size_t i = 0; i < spans[r].n_tasks; i++) { FastaTask &t = tasks[spans[r].first_task + i]; t.base0 = len; len += t.nres; }
+        begin_record(g, spans[r].ident.c_str(), spans[r].desc.c_str(), len);
+        g->total_len += len;
+    }
+    if (!g->recs.empty()) rc = genome_reserve(g, g->recs.back().off + g->recs.back().len + REC_ALIGN + TAIL_PAD + FGROUP);
+    if (rc == KGMA_OK) {
+        parallel_for(tasks.size(), nthreads, [&](size_t i) { if (tasks[i].nres) pack_task(g, g->recs[(size_t)tasks[i].rec].off, tasks[i]); });
+        for (const FastaTask &t : tasks) {
+            if (t.bad >= 0 && rc == KGMA_OK) { g->err = "record " + std::to_string(t.rec) + ": invalid character at position " + std::to_string(t.bad + 1); rc = KGMA_E_SYMBOL; }
+            if (t.amb >= 0 && !g->ambiguous) { g->ambiguous = true; g->amb_record = t.rec; g->amb_pos = t.amb + 1; }
+            if (t.anymask) g->any_mask = true;
+        }
     }
     if (sz) munmap((void *)buf, sz);
     close(fd);

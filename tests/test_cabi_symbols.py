@@ -112,3 +112,38 @@ def test_ingest_round_trip_and_packed_paths():
     assert outs[0] == outs[1] == outs[2] == s.upper()
     with pytest.raises(K.KmerGMAError):
         K.Genome.from_records([("bad", "ACGT!ACGT")])
+
+
+def test_fasta_ingest_edge_cases(tmp_path):
+    """parallel mmap ingest vs the oracle's line-by-line reader: CRLF, blank lines, lower case, no trailing newline,
+    N / IUPAC symbols, an empty record, records larger than one 4 MB packing task, task boundaries inside a line"""
+    import kmergma_jl_b200 as K
+    from oracle import oracle as O
+    rng = np.random.default_rng(1)
+    big = "".join(np.asarray(list("ACGTN"))[rng.integers(0, 5, size=9_500_003)])
+    recs = [("r1 first record", "ACGTNNNNacgtn" * 11), ("empty", ""), ("r3\ttabbed desc", big), ("r4", "T"), ("r5 last", "GATTACA" * 3)]
+    p = tmp_path / "edge.fasta"
+    with open(p, "wb") as fh:
+        for i, (d, s) in enumerate(recs):
+            eol = b"\r\n" if i % 2 else b"\n"
+            fh.write(b">" + d.encode() + eol)
+            width = [7, 60, 61, 80, 5][i]
+            for a in range(0, len(s), width):
+                fh.write(s[a:a + width].encode() + eol)
+            if i == 0:
+                fh.write(eol)                                  # blank line between records
+        fh.seek(-1, 1); fh.truncate()                          # no trailing newline
+    g, f = K.Genome.from_fasta(str(p)), O.Fasta(str(p))
+    assert len(g) == len(f) == 5
+    for r in range(5):
+        assert g.identifier(r) == f.identifier(r) == recs[r][0].split()[0]
+        assert g.seqsize(r) == f.seqsize(r) == len(recs[r][1])
+        assert g.seq(r) == f.seq(r) == recs[r][1].upper()
+    q = tmp_path / "iupac.fasta"
+    q.write_text(">x\nACGTRYACGT\n")
+    gi = K.Genome.from_fasta(str(q))                           # IUPAC other than N: ingested (exact match may use it) ...
+    assert gi.seq(0) == "ACGT??ACGT"
+    bad = tmp_path / "bad.fasta"
+    bad.write_text(">x\nACGT!ACGT\n")
+    with pytest.raises(K.KmerGMAError):
+        K.Genome.from_fasta(str(bad))

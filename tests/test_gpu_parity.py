@@ -649,3 +649,49 @@ def test_full_size_exact_match(K, big):
         rs = non.get(g.identifier(r), [])
         assert all(rs[i + 1][0] > rs[i][1] for i in range(len(rs) - 1))    # FindAll: no two reported matches overlap
         assert set(f for f, _ in rs) <= got[r]
+
+
+def test_k7_large_family_multicontig(K, O, tmp_path):
+    """configs[4] in miniature: k = 7 (16 384 bins), a 500-member family derived from the fixture references, 300 contigs of
+    10 kb .. 1 Mb with planted members, threshold from estimate_optimal_threshold; single GPU and 4 shards"""
+    rng = np.random.default_rng(21)
+    refs = O.Fasta(TF)
+    base = [refs.seq(i) for i in range(len(refs))]
+    fam = []
+    for i in range(500):
+        fam.append(_mutate(rng, base[i % len(base)], float(rng.uniform(0, 0.08)), i % 9 == 0))
+    fam_path = tmp_path / "family.fasta"
+    _write_fasta(fam_path, [("fam%d" % i, s) for i, s in enumerate(fam)])
+    RV, ws, cons = K.gen_ref_ws_cons(str(fam_path), 7)
+    orv, ows, ocons = O.gen_ref_ws_cons(str(fam_path), 7)
+    assert RV.n_refs == 500 and ws == ows and cons == ocons and np.array_equal(np.asarray(RV), orv)
+    lens = np.exp(rng.uniform(np.log(10_000), np.log(1_000_000), size=300)).astype(int)
+    gpath = tmp_path / "contigs.fasta"
+    alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
+    with open(gpath, "wb") as fh:
+        for c, L in enumerate(lens):
+            seq = alphabet[rng.integers(0, 4, size=int(L))].copy()
+            for _ in range(int(rng.integers(0, 4))):
+                m = _mutate(rng, fam[int(rng.integers(0, 500))], float(rng.uniform(0, 0.12)), rng.random() < 0.3).encode()
+                p = int(rng.integers(0, max(1, L - len(m))))
+                if p + len(m) <= L:
+                    seq[p:p + len(m)] = np.frombuffer(m, dtype=np.uint8)
+            fh.write(b">contig%d len=%d\n" % (c, L))
+            fh.write(seq.tobytes() + b"\n")
+    thr = K.estimate_optimal_threshold(RV, ws, buffer=8.0)
+    g = K.Genome.from_fasta(str(gpath))
+    assert len(g) == 300
+    L_ = K.L
+    args = ([RV], [ws], [cons], [thr], 7, L_.MODE_SINGLE, 50)
+    out = K.scan_raw(g, *args, L_.F_ALIGN, -69, -1)
+    assert K.default_context().stats()["blocks_total"] > 0            # the prefilter (8-mer table, 2 k-mers per lookup) was in use
+    oh = assert_parity(K, O, out, lambda: O.ac_gma_testing(str(gpath), orv, cons, k=7, windowsize=ws, thr=thr, buff=50, do_align=True)[0], 500)
+    assert len(oh) > 100
+    runs, firsts = [], None
+    for s in (2, 0, 3, 1):
+        part = K.scan_raw(g, *args, 0, -69, -1, runs_only=True, shard=(s, 4))
+        runs.append(part.runs)
+        firsts = part.first_D if firsts is None else np.maximum(firsts, part.first_D)
+    rep = K.replay_raw(g, *args, L_.F_ALIGN, -69, -1, np.concatenate(runs), firsts)
+    key = ["record", "first", "last", "D", "genome_pos"]
+    assert np.array_equal(rep.hits[key], out.hits[key])
