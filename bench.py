@@ -398,12 +398,63 @@ def run_ours(args):
         }
         if strong:
             line["strong"] = strong
+        if world == 1 and not args.no_extra:
+            line["other_configs"] = other_configs(K, ctx, g, lens, total, RV, ws, cons, peak)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def other_configs(K, ctx, g, lens, total, RV, ws, cons, peak):
+    """BASELINE configs[2] (cluster mode, 6 profiles) and configs[3] (exactMatch, 300-nt query) on the same resident genome,
+    plus the dense count-table pass; a few iterations each, reported for context (parity for them is in tests/)."""
+    import ctypes as C
+    L = K.L
+
+    def timeit(f, n):
+        f()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            out = f()
+        return (time.perf_counter() - t0) / n * 1e3, out
+
+    res = {}
+    rvs, wss, cs, inv = K.cluster_ref_API(TF, KMER)
+    rvs, wss, cs = K.eliminate_null_params(rvs, wss, cs, inv)
+    thr = [35, 31, 38, 34, 27, 27]
+    ms, out = timeit(lambda: K.scan_raw(g, rvs, wss, cs, thr, KMER, L.MODE_CLUSTER, 100, L.F_ALIGN | L.F_RESIDENT, -200, -1, ctx=ctx), 5)
+    st = ctx.stats()
+    res["findGenes_cluster_mode"] = {"profiles": len(wss), "ms_per_step": ms, "value": total / ms / 1e3, "unit": UNIT, "hits": int(len(out.hits)),
+                                     "device_ms": {"prefilter": st["filter_ms"], "count_table": st["exact_ms"], "extension": st["align_ms"]},
+                                     "prefilter_passes": int(st["launches"]) - 2, "extensions": int(st["n_align"])}
+    rng = np.random.default_rng(5)
+    query = "".join(np.asarray(list("ACGT"))[rng.integers(0, 4, size=300)])
+    for i in range(1000):
+        r = int(rng.integers(0, len(lens)))
+        g.put_seq(r, int(rng.integers(20000, lens[r] - 20000)), query)
+    g.make_resident(ctx)
+
+    def em():
+        mp = C.POINTER(L.Match)(); n = C.c_int64()
+        ctx.check(ctx._lib.kgma_exact_match(ctx._h, g._h, query.encode(), len(query), 1, L.F_RESIDENT, C.byref(mp), C.byref(n)))
+        if n.value:
+            ctx._lib.kgma_free(mp)
+        return n.value
+
+    ms, n = timeit(em, 10)
+    st = ctx.stats()
+    ach = total * 0.25 / (st["filter_ms"] * 1e-3) / 1e9
+    res["exactMatch_300nt"] = {"ms_per_step": ms, "value": total / ms / 1e3, "unit": UNIT, "matches": int(n), "planted": 1000,
+                               "roofline": {"bound": "hbm", "kernel": "kgma_exact_match_sampled", "achieved": ach, "peak": peak, "unit": "GB/s",
+                                            "frac": ach / peak, "algorithmic_bytes": "0.25 B/base: the 2-bit plane, one sampled word per 32 B sector; "
+                                            "N is checked against the masked-run list, the ambiguity plane is not read"}}
+    ms, out = timeit(lambda: K.scan_raw(g, [RV], [ws], [cons], [THR], KMER, L.MODE_SINGLE, BUFF, L.F_ALIGN | L.F_RESIDENT | L.F_DENSE, GAP_OPEN, GAP_EXT, ctx=ctx), 2)
+    res["findGenes_dense_count_table"] = {"ms_per_step": ms, "value": total / ms / 1e3, "unit": UNIT, "hits": int(len(out.hits)),
+                                          "note": "KGMA_F_DENSE: every window through the shared-memory count-table kernel, no prefilter"}
+    return res
 
 
 def main():
@@ -414,6 +465,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="genome size as a fraction of 3.1 Gb (testing only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other_configs block (cluster mode, exact match, dense)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     if args.impl == "reference":
