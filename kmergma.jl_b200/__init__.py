@@ -23,7 +23,7 @@ __all__ = [
     "gen_ref_ws_cons", "cluster_ref_API", "eliminate_null_params", "get_cluster_index",
     "estimate_optimal_threshold", "ac_gma_testing", "Omn_KmerGMA", "record_KmerGMA",
     "findGenes", "findGenes_cluster_mode", "exactMatch", "write_results", "align_unitrange",
-    "julia_round2", "julia_float_str",
+    "julia_round2", "julia_float_str", "kmer_count", "kmer_dist", "as_UInt", "as_kmer",
 ]
 
 
@@ -326,6 +326,45 @@ def _kmer_count_np(codes: np.ndarray, k: int) -> np.ndarray:
     for j in range(k):
         idx = idx * 4 + codes[j:j + n]
     return np.bincount(idx, minlength=4 ** k).astype(np.float64)
+
+
+_CODE = np.full(256, 255, dtype=np.uint8)
+for _c, _v in (("A", 0), ("C", 1), ("G", 2), ("T", 3), ("N", 3)):       # src/Consts.jl:22-28 (N -> 3)
+    _CODE[ord(_c)] = _CODE[ord(_c.lower())] = _v
+
+
+def _codes(seq) -> np.ndarray:
+    b = seq.encode() if isinstance(seq, str) else bytes(seq)
+    c = _CODE[np.frombuffer(b, dtype=np.uint8)]
+    if c.size and c.max() == 255:
+        raise KeyError("symbol outside A,C,G,T,N")                          # the reference's Dict lookup fails the same way
+    return c
+
+
+def kmer_count(seq, k: int) -> np.ndarray:
+    """kmer_count (src/Kmers.jl:14-28): Float64 counts of the 4^k k-mers, first base most significant."""
+    c = _codes(seq)
+    return _kmer_count_np(c.astype(np.int64), k) if c.size >= k else np.zeros(4 ** k)
+
+
+def kmer_dist(seq1, seq2, k: int) -> float:
+    """kmer_dist (src/Kmers.jl:54-60): (1/2k) * sqeuclidean(kmer_count(seq1), kmer_count(seq2) or a KFV)."""
+    a = kmer_count(seq1, k)
+    b = kmer_count(seq2, k) if isinstance(seq2, (str, bytes)) else np.asarray(seq2, dtype=np.float64)
+    return (1.0 / (2 * k)) * float(np.sum((a - b) ** 2))
+
+
+def as_UInt(seq) -> int:
+    """as_UInt (src/Kmers.jl:101): the 2-bit integer of a k-mer, first base most significant."""
+    v = 0
+    for c in _codes(seq):
+        v = (v << 2) | int(c)
+    return v
+
+
+def as_kmer(value: int, length: int) -> str:
+    """as_kmer (src/Kmers.jl:80): inverse of as_UInt."""
+    return "".join("ACGT"[(value >> (2 * (length - 1 - i))) & 3] for i in range(length))
 
 
 def estimate_optimal_threshold(RV, average_length, seed: int = 42, num_trials: int = 100, buffer: float = 8):

@@ -147,3 +147,31 @@ def test_fasta_ingest_edge_cases(tmp_path):
     bad.write_text(">x\nACGT!ACGT\n")
     with pytest.raises(K.KmerGMAError):
         K.Genome.from_fasta(str(bad))
+
+
+def test_host_mirror_goldens():
+    """host-side mirrors of the small reference utilities, against the reference's own goldens
+    (test/test_folder/test-KmerGMA.jl:2-26, :28-46 via gen_ref_ws_cons, :96-110, :116-120)"""
+    import kmergma_jl_b200 as K
+    ts = "ATGCATGC"                                                        # test/runtests.jl:47
+    test_KFV = [0, 0, 0, 2, 1, 0, 0, 0, 0, 2, 0, 0, 0, 0, 2, 0]           # test/runtests.jl:50-51
+    assert K.kmer_count(ts, 1).tolist() == [2, 2, 2, 2]
+    assert K.kmer_count(ts[:8], 2).tolist() == test_KFV
+    assert K.kmer_dist(ts * 25 + "A" + ts * 25, ts * 25 + "G" + ts * 25, 2) == 1.0
+    assert K.kmer_dist(ts * 25 + "AA" + ts * 25, ts * 25 + "GT" + ts * 25, 2) == 2.0
+    assert K.as_UInt(ts) == 14649 and K.as_kmer(14649, 8) == ts
+    # Consensus.jl through the native profile builder: column votes, ties to the earlier symbol, shorter refs vote less
+    assert K.gen_ref_ws_cons([ts, "ATGCATGG", "ATGCATGG"], 1)[2] == "ATGCATGG"
+    assert K.gen_ref_ws_cons(["ACGT", "ACGTA"], 1)[1:] == (4, "ACGTA")     # Int(round(4.5)) == 4 (round half even)
+    # eliminate_null_params
+    kf, w, c = K.eliminate_null_params([np.array(test_KFV, float), np.array(test_KFV, float) + 0.3], [8, 9], [ts, ts + "Y"], [False, True])
+    assert [v.tolist() for v in kf] == [test_KFV] and w == [8] and c == [ts]
+    rvs, wss, cs, inv = K.cluster_ref_API(TF, 6, cutoffs=[7, 12, 20, 25])
+    rvs, wss, cs = K.eliminate_null_params(rvs, wss, cs, inv)
+    assert wss == [288, 288, 288, 289, 290, 289] and len(rvs) == len(cs) == 6
+    # estimate_optimal_threshold: same algorithm, numpy's RNG instead of Julia's (DESIGN.md section 1): the cluster goldens
+    # round to the reference's values, the single-profile one lands within 1 of it
+    rvs5, ws5, _, _ = K.cluster_ref_API(TF, 6, cutoffs=[7, 12, 20, 25], include_avg=False)
+    assert [int(round(x)) for x in K.estimate_optimal_threshold(rvs5, ws5, buffer=8)] == [38, 33, 41, 37, 29]
+    RV, _, _ = K.gen_ref_ws_cons(TF, 6)
+    assert abs(K.estimate_optimal_threshold(RV, 299, buffer=12) - 27) <= 1.0
