@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <climits>
+#include <cstdlib>
 #include <chrono>
 
 namespace kgma {
@@ -650,7 +651,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     // ---- prefilter groups.  One table for all profiles when a random sequence stays well below the flag threshold
     //      under the combined (max) weights; otherwise one pass per profile; profiles that cannot be filtered go dense.
     std::vector<FilterGroup> groups;
-    if (ctx->ftabs.size() > 48) ctx->ftabs.clear();                // bounded cache; nothing points into it between calls
+    if (ctx->ftabs.size() > 96) ctx->ftabs.clear();                // bounded cache; nothing points into it between calls
     {
         std::vector<int> all((size_t)C); for (int q = 0; q < C; q++) all[(size_t)q] = q;
         const double LOAD_OK = 0.62, LOAD_MAX = 0.85;
@@ -661,7 +662,16 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
             if (f->ok && (f->load <= LOAD_OK || (C == 1 && f->load <= LOAD_MAX))) { FilterGroup fg; fg.q = all; fg.ft = f; groups.push_back(fg); }
             else if (C == 1) dg.q = all;
             else for (int q = 0; q < C; q++) {
-                const kgma_ctx::FTab *fq = get_ftab(ctx, pl, std::vector<int>{ q });   // note: pointers into ctx->ftabs stay valid (capacity reserved)
+                // greedy packing: join the first group whose combined (max-weight) table still keeps random sequence well
+                // below the flag threshold, else open a new group; tables are cached, so this costs nothing on repeat scans
+                bool placed = false;
+                for (FilterGroup &fg : groups) {
+                    std::vector<int> trial = fg.q; trial.push_back(q);
+                    const kgma_ctx::FTab *ft = get_ftab(ctx, pl, trial);           // (references into the deque stay valid)
+                    if (ft->ok && ft->load <= LOAD_OK) { fg.q = trial; fg.ft = ft; placed = true; break; }
+                }
+                if (placed) continue;
+                const kgma_ctx::FTab *fq = get_ftab(ctx, pl, std::vector<int>{ q });
                 if (fq->ok && fq->load <= LOAD_MAX) { FilterGroup fg; fg.q = { q }; fg.ft = fq; groups.push_back(fg); }
                 else dg.q.push_back(q);
             }

@@ -22,3 +22,7 @@ TEST_CONSENSUS = ("CAGGTGCAGCTGGTGGAGTCTGGGGGAGGCTTGGTGCAGCCTGGGGGGTCTCTGAGACTCT
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the shared libraries are git-ignored build products: (re)build them when missing or older than their sources
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "kmergma.jl_b200", "csrc")], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
