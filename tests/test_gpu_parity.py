@@ -695,3 +695,30 @@ def test_k7_large_family_multicontig(K, O, tmp_path):
     rep = K.replay_raw(g, *args, L_.F_ALIGN, -69, -1, np.concatenate(runs), firsts)
     key = ["record", "first", "last", "D", "genome_pos"]
     assert np.array_equal(rep.hits[key], out.hits[key])
+
+
+def test_low_complexity_counts_above_255(K, O, prof, tmp_path):
+    """homopolymers, N runs (folded to T: one k-mer 284 times in a window, more than a byte holds), dinucleotide repeats and a
+    homologue inside a repeat: dense and prefiltered scans must give the oracle's distances and hits"""
+    RV, ws, cons = prof
+    refs = O.Fasta(TF)
+    rng = np.random.default_rng(4)
+
+    def rnd(n):
+        return "".join(np.asarray(list("ACGT"))[rng.integers(0, 4, size=n)])
+
+    seq = (rnd(3000) + "A" * 900 + rnd(50) + "N" * 1500 + refs.seq(3) + "T" * 700 + "CA" * 600 + refs.seq(10)[:150] + "G" * 300 +
+           refs.seq(10)[150:] + rnd(2000) + "TTTTTTA" * 120 + rnd(4000) + "N" * 300)
+    recs = [("lowcomplexity", seq), ("polyT", "T" * 5000), ("mix", rnd(1500) + "C" * 256 + rnd(40) + "C" * 255 + rnd(3000))]
+    path = tmp_path / "lc.fasta"
+    _write_fasta(path, recs)
+    dv = []
+    a = K.ac_gma_testing(genome_path=str(path), refVec=RV, consensus_refseq=cons, windowsize=ws, thr=36, do_align=False,
+                         do_return_dists=True, resultVec=[], dist_vec=dv)
+    b = K.ac_gma_testing(genome_path=str(path), refVec=RV, consensus_refseq=cons, windowsize=ws, thr=36, do_align=False, resultVec=[])
+    da = np.asarray(dv)
+    assert da.size == sum(len(s) - ws for _, s in recs)
+    assert np.array_equal(a.hits[["record", "first", "last", "D"]], b.hits[["record", "first", "last", "D"]])
+    _, _, od = O.ac_gma_testing(str(path), np.asarray(RV), cons, windowsize=ws, thr=36, do_align=False, do_return_dists=True)
+    assert np.max(np.abs(da - od) / np.maximum(np.abs(od), 1e-300)) <= REL
+    assert_parity(K, O, a, lambda: O.ac_gma_testing(str(path), np.asarray(RV), cons, windowsize=ws, thr=36, do_align=False)[0], RV.n_refs)
