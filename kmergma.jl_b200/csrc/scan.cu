@@ -193,9 +193,9 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
     int32_t *sS = reinterpret_cast<int32_t *>(smem_raw);
     const size_t per_warp = (size_t)nb * 2 + 64 * 2 * 2 + 64 * 8;
     unsigned char *wb = smem_raw + (size_t)nb * 4 + (size_t)wid * per_warp;
-    uint32_t *qw = reinterpret_cast<uint32_t *>(wb), *aw = qw + 64;           // [64] Q and A of the current 64 windows
+    uint2 *qa = reinterpret_cast<uint2 *>(wb);                                // [64] (Q, A) of the current 64 windows
     uint16_t *tab = reinterpret_cast<uint16_t *>(wb + 64 * 8);                // [4^k] counts
-    uint16_t *lk = tab + nb, *rk = lk + 64;                                  // leaving / entering k-mers of 64 steps
+    uint32_t *lr = reinterpret_cast<uint32_t *>(tab + nb);                    // [64] leaving | entering << 16 k-mers of 64 steps
     for (int i = lane; i < nb / 2; i += 32) reinterpret_cast<uint32_t *>(tab)[i] = 0;
     if (nb < 2 && lane == 0) tab[0] = 0;
 
@@ -267,22 +267,24 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
             bool c_in = false; long long c_tf = 0, c_ta = 0, c_dmin = 0; uint32_t c_fl = 0;   // run carried across 64-window batches
             for (long long s0 = 0; s0 < n; s0 += 64) {
                 const int m = (int)(n - s0 < 64 ? n - s0 : 64);
-                for (int j = lane; j < m; j += 32) {                          // step j: window s0+j -> s0+j+1
-                    lk[j] = (uint16_t)kmer_at(a.seq, gpos + s0 + j, kmask);
-                    rk[j] = (uint16_t)kmer_at(a.seq, gpos + s0 + j + nk, kmask);
-                }
+                for (int j = lane; j < m; j += 32)                            // step j: window s0+j -> s0+j+1
+                    lr[j] = kmer_at(a.seq, gpos + s0 + j, kmask) | (kmer_at(a.seq, gpos + s0 + j + nk, kmask) << 16);
                 __syncwarp();
                 if (lane == 0) {
-                    uint32_t l = lk[0], rr = rk[0];
+                    // the serial part: one warp instruction stream, so every instruction counts (one packed k-mer load,
+                    // one 64-bit store per step; the last slide of the span is cut off by the loop bound, not per step)
+                    const int msl = (int)((n - 1 - s0) < m ? (n - 1 - s0) : m);       // steps that do slide
+                    uint32_t cur = lr[0];
                     for (int j = 0; j < m; j++) {
-                        qw[j] = Q; aw[j] = A;
-                        const uint32_t ln = lk[(j + 1) & 63], rn = rk[(j + 1) & 63];   // software-pipelined k-mer fetch
-                        if (l != rr && s0 + j + 1 < n) {                      // GenomeMiner.jl:69 `if left_ind != right_ind`
+                        qa[j] = make_uint2(Q, A);
+                        const uint32_t nxt = lr[(j + 1) & 63];                        // software-pipelined k-mer fetch
+                        const uint32_t l = cur & 0xFFFFu, rr = cur >> 16;
+                        if (l != rr && j < msl) {                             // GenomeMiner.jl:69 `if left_ind != right_ind`
                             const uint32_t cl = tab[l], cr = tab[rr];
                             Q += 2u * (cr - cl) + 2u; A += (uint32_t)(sS[rr] - sS[l]);
                             tab[l] = (uint16_t)(cl - 1); tab[rr] = (uint16_t)(cr + 1);
                         }
-                        l = ln; rr = rn;
+                        cur = nxt;
                     }
                 }
                 __syncwarp();
@@ -293,7 +295,8 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
                     const int wi = lane + 32 * h;
                     const bool valid = wi < m;
                     const long long t = w0 + s0 + wi;
-                    const long long D = valid ? P.N2 * (long long)qw[wi] - P.twoN * (long long)aw[wi] + P.sumS2 : 0;
+                    const uint2 v = qa[wi & 63];
+                    const long long D = valid ? P.N2 * (long long)v.x - P.twoN * (long long)v.y + P.sumS2 : 0;
                     Dm[h] = D;
                     if (valid && t == 0) a.first_D[(size_t)q * a.nrec + r] = D;      // first window: never compared with thr
                     const bool inloop = valid && t >= 1;
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
                 while (mk) {
                     const int i = __ffsll((long long)mk) - 1; mk &= mk - 1;
                     if (lane == 0) emit_run(a, r, q, w0 + s0 + i, w0 + s0 + i, w0 + s0 + i,
-                                            P.N2 * (long long)qw[i] - P.twoN * (long long)aw[i] + P.sumS2, KGMA_RUN_MARKER | KGMA_HIT_NEAR_THR);
+                                            P.N2 * (long long)qa[i].x - P.twoN * (long long)qa[i].y + P.sumS2, KGMA_RUN_MARKER | KGMA_HIT_NEAR_THR);
                 }
                 __syncwarp();
             }
