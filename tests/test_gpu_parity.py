@@ -722,3 +722,78 @@ def test_low_complexity_counts_above_255(K, O, prof, tmp_path):
     _, _, od = O.ac_gma_testing(str(path), np.asarray(RV), cons, windowsize=ws, thr=36, do_align=False, do_return_dists=True)
     assert np.max(np.abs(da - od) / np.maximum(np.abs(od), 1e-300)) <= REL
     assert_parity(K, O, a, lambda: O.ac_gma_testing(str(path), np.asarray(RV), cons, windowsize=ws, thr=36, do_align=False)[0], RV.n_refs)
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_fuzz_vs_oracle(K, O, tmp_path, seed):
+    """randomised end-to-end comparison: random k, family, window, thresholds, buffer, gap model, record lengths (including
+    records shorter than the window and empty ones), N runs and repeats; single and cluster mode; prefiltered and dense"""
+    rng = np.random.default_rng(1000 + seed)
+
+    def rnd(n):
+        return "".join(np.asarray(list("ACGT"))[rng.integers(0, 4, size=int(n))])
+
+    k = int(rng.integers(2, 8))
+    reflen = int(rng.integers(max(3 * k, 20), 420))
+    root = rnd(reflen)
+    fam = []
+    for i in range(int(rng.integers(1, 25))):
+        s = _mutate(rng, root, float(rng.uniform(0, 0.25)), rng.random() < 0.3)
+        if rng.random() < 0.1:
+            s = s[:len(s) // 2] + "N" + s[len(s) // 2 + 1:]
+        fam.append(s)
+    fpath = tmp_path / "fam.fasta"
+    _write_fasta(fpath, [("f%d" % i, s) for i, s in enumerate(fam)])
+    recs = []
+    for r in range(int(rng.integers(1, 6))):
+        L = int(rng.choice([0, 5, reflen - 1, reflen, reflen + 1, int(rng.integers(reflen, 30000))]))
+        parts, tot = [], 0
+        while tot < L:
+            c = rng.random()
+            if c < 0.25:
+                p = _mutate(rng, fam[int(rng.integers(0, len(fam)))], float(rng.uniform(0, 0.2)), rng.random() < 0.3)
+            elif c < 0.32:
+                p = "N" * int(rng.integers(1, 600))
+            elif c < 0.4:
+                p = rnd(int(rng.integers(1, 4))) * int(rng.integers(5, 300))
+            else:
+                p = rnd(int(rng.integers(1, 4000)))
+            parts.append(p); tot += len(p)
+        recs.append(("rec%d some description" % r, "".join(parts)[:L]))
+    gpath = tmp_path / "g.fasta"
+    _write_fasta(gpath, recs, width=int(rng.integers(20, 200)))
+    buff = int(rng.choice([0, 7, 50, 100]))
+    go, ge = (int(rng.choice([-5, -30, -69, -200])), int(rng.choice([-1, -2])))
+    align = bool(rng.random() < 0.6)
+    # ---- single mode
+    RV, ws, cons = K.gen_ref_ws_cons(str(fpath), k)
+    orv, ows, ocons = O.gen_ref_ws_cons(str(fpath), k)
+    assert ws == ows and cons == ocons and np.array_equal(np.asarray(RV), orv)
+    if k >= ws:
+        pytest.skip("k >= window")
+    _, _, od = O.ac_gma_testing(str(gpath), orv, cons, k=k, windowsize=ws, thr=0, do_align=False, do_return_dists=True)
+    thr = float(np.quantile(od, float(rng.choice([0.002, 0.02, 0.1, 0.3])))) if od.size else 10.0
+    thr = float(np.round(thr, int(rng.integers(0, 4))))                  # round thresholds: exact ties do happen
+    for dense in (False, True):
+        res = []
+        out = K.ac_gma_testing(genome_path=str(gpath), refVec=RV, consensus_refseq=cons, k=k, windowsize=ws, thr=thr, buff=buff,
+                               do_align=align, gap_open_score=go, gap_extend_score=ge, resultVec=res, dense=dense)
+        oh = assert_parity(K, O, out, lambda: O.ac_gma_testing(str(gpath), orv, cons, k=k, windowsize=ws, thr=thr, buff=buff, do_align=align,
+                                                               gap_open_score=go, gap_extend_score=ge)[0], RV.n_refs)
+        assert [r.sequence for r in res] == [h.seq for h in oh]
+    # ---- cluster mode (k >= 2; cutoffs at quantiles of the reference-to-mean distances)
+    if k >= 2 and len(fam) >= 2:
+        dists = K.cluster_ref_API(str(fpath), k, get_dists=True)[4]
+        cut = sorted(set(float(np.round(np.quantile(dists, qq), 2)) for qq in (0.3, 0.7)))
+        rvs, wss, cs, inv = K.cluster_ref_API(str(fpath), k, cutoffs=cut)
+        orvs, owss, ocs, oinv = O.cluster_ref_API(str(fpath), k, cutoffs=cut)[:4]
+        assert wss == list(owss) and list(cs) == list(ocs) and [bool(x) for x in inv] == [bool(x) for x in oinv]
+        rvs, wss, cs = K.eliminate_null_params(rvs, wss, cs, inv)
+        if k < min(wss):
+            thrs = [float(np.round(thr * float(rng.uniform(0.8, 1.2)), 2)) for _ in wss]
+            for dense in (False, True):
+                out = K.Omn_KmerGMA(genome_path=str(gpath), refVecs=rvs, windowsizes=wss, consensus_seqs=cs, resultVec=[], k=k, thr_vec=thrs,
+                                    buff=buff, align_hits=align, gap_open_score=go, gap_extend_score=ge, dense=dense)
+                assert_parity(K, O, out, lambda: O.Omn_KmerGMA(str(gpath), [np.asarray(v) for v in rvs], wss, cs, k=k, thr_vec=thrs, buff=buff,
+                                                               align_hits=align, gap_open_score=go, gap_extend_score=ge)[0],
+                              [v.n_refs for v in rvs], cluster=True)
