@@ -418,7 +418,8 @@ assert HIT_DT.itemsize == C.sizeof(L.Hit) and RUN_DT.itemsize == C.sizeof(L.Run)
 
 
 class ScanOutput:
-    """Raw result of one kgma_scan call: `hits` is a numpy record array over kgma_hit (h.record, h.first, ...),
+    """Raw result of one kgma_scan call: `hits` is a numpy record array over kgma_hit (h.record, h.first, ...; the
+    kgma_hit.flags field must be read as h["flags"], `.flags` being numpy's own attribute),
     `runs` the raw bytes of the kgma_run list (view with RUN_DT), plus optional dists / cigars."""
 
     def __init__(self, lib, res_handle):

@@ -201,7 +201,7 @@ __device__ __forceinline__ PathSum ps_append(PathSum s, uint32_t op, uint32_t le
 // Each lane owns R consecutive DP rows (register blocked), the warp 32*R rows per sweep; neighbouring lanes are
 // skewed by one column, so a whole 289-row alignment is ONE sweep of n+31 steps with R = 10 (instead of ten
 // sweeps of 32 rows): 7 shuffles per step are amortised over R cells and the per-step bookkeeping shrinks 10x.
-template <int R>
+template <int R, bool TIE_OPEN>
 __global__ void __launch_bounds__(128, 3) kgma_align_summary(AlignArgs2 A)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -284,11 +284,11 @@ __global__ void __launch_bounds__(128, 3) kgma_align_summary(AlignArgs2 A)
 #pragma unroll
                     for (int r = 0; r < R; r++) {
                         const int eo = hU - gog, ee = eU - ge;
-                        const bool xe = A.tie_open ? (ee > eo) : (ee >= eo);
+                        const bool xe = TIE_OPEN ? (ee > eo) : (ee >= eo);
                         const int e = xe ? ee : eo;
                         PathSum bE; bE.lo = xe ? beU.lo : shU.lo; bE.hi = (xe ? beU.hi : shU.hi) + GL1;   // extend: +1; open: summary | 1
                         const int fo = H[r] - gof[r], fe = F[r] - gef[r];
-                        const bool xf = A.tie_open ? (fe > fo) : (fe >= fo);
+                        const bool xf = TIE_OPEN ? (fe > fo) : (fe >= fo);
                         const int f = xf ? fe : fo;
                         bF[r].lo = xf ? bF[r].lo : sH[r].lo; bF[r].hi = (xf ? bF[r].hi : sH[r].hi) + GL1;
                         const int mm = hD + (int)((sc[r] >> bsh) & 15u) - 4;
@@ -425,10 +425,12 @@ int align_batch_device(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq
         A.b = d + o_b; A.jobs = (const AlignJob2 *)(d + o_j); A.njobs = nj; A.next_job = (int *)(d + o_c);
         A.out = (AlignOut *)(d + o_o); A.go = -gap_open; A.ge = -gap_extend; A.tie_open = tie_open ? 1 : 0; A.ncol_cap = ncol;
         A.need_boundary = need_boundary ? 1 : 0;
-        KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = std::min((nj + warps_per_block - 1) / warps_per_block, ctx->num_sms * 8);
         KGMA_CUDA(ctx, cudaEventRecord(e0, st));
-        kgma_align_summary<ROWS><<<grid, warps_per_block * 32, smem, st>>>(A);
+        if (tie_open) kgma_align_summary<ROWS, true><<<grid, warps_per_block * 32, smem, st>>>(A);
+        else kgma_align_summary<ROWS, false><<<grid, warps_per_block * 32, smem, st>>>(A);
         KGMA_CUDA(ctx, cudaGetLastError());
         KGMA_CUDA(ctx, cudaEventRecord(e1, st));
         ctx->stats.launches++;

@@ -62,7 +62,7 @@ def hits_equal(K, kout, ohits, cluster=False):
             return "hit %d: KFV %d != %d" % (i, h.profile, o.kfv)
         if abs(h.dist - o.dist) > REL * max(abs(o.dist), 1e-300):
             return "hit %d: dist %r != %r" % (i, h.dist, o.dist)
-        if K.julia_round2(h.dist) != K.julia_round2(o.dist) and not (h.flags & K.L.HIT_ROUND_HALF):
+        if K.julia_round2(h.dist) != K.julia_round2(o.dist) and not (int(h["flags"]) & K.L.HIT_ROUND_HALF):
             return "hit %d: rounded dist differs without ROUND_HALF flag" % i
     return None
 
