@@ -253,8 +253,11 @@ def bind_to_gpu_numa_node(device_index):
 
 
 def run_ours(args):
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    # rank 0 must print exactly ONE line on stdout, but NCCL writes its version banner there from C: park the real stdout
+    # and send everything else (python prints, library chatter) to stderr until the JSON line goes out
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import kmergma_jl_b200 as K
@@ -423,7 +426,8 @@ def run_ours(args):
             line["other_configs"] = other_configs(K, ctx, g, lens, total, RV, ws, cons, peak)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
