@@ -113,6 +113,7 @@ struct ProfTab {
     int64_t Tlo = 0, Thi = 0;        // |d - thr| <= 1e-9*thr  <=>  Tlo <= D < Thi  (near-threshold band)
     double  denom = 0;               // 2 k N^2
     double  thr = 0;
+    uint64_t hash = 0;               // fingerprint of (S, Thi, N, nk, k): key of the cached prefilter tables
 };
 int  build_proftab(kgma_ctx *ctx, const kgma_profile &p, ProfTab &t);
 inline uint32_t rev_kmer(uint32_t c, int k) { uint32_t r = 0; for (int j = 0; j < k; j++) { r = (r << 2) | (c & 3); c >>= 2; } return r; }

@@ -13,12 +13,37 @@ namespace kgma {
 
 void merge_runs(std::vector<kgma_run> &runs)
 {
-    std::sort(runs.begin(), runs.end(), [](const kgma_run &a, const kgma_run &b) {
-        if (a.profile != b.profile) return a.profile < b.profile;
-        if (a.record != b.record) return a.record < b.record;
-        if (a.t_first != b.t_first) return a.t_first < b.t_first;
-        return (a.flags & KGMA_RUN_MARKER) < (b.flags & KGMA_RUN_MARKER);
-    });
+    // order by (profile, record, t_first, marker): bucket by (profile, record) with a counting pass, then sort the
+    // (small) buckets - the device appends runs in arbitrary order
+    {
+        int maxp = 0, maxr = 0;
+        for (const kgma_run &r : runs) { maxp = std::max(maxp, r.profile); maxr = std::max(maxr, r.record); }
+        const size_t nbk = (size_t)(maxp + 1) * (size_t)(maxr + 1);
+        bool ok = !runs.empty() && maxp >= 0 && maxr >= 0 && nbk <= ((size_t)1 << 22);
+        for (const kgma_run &r : runs) if (r.profile < 0 || r.record < 0) ok = false;
+        auto less = [](const kgma_run &a, const kgma_run &b) {
+            if (a.profile != b.profile) return a.profile < b.profile;
+            if (a.record != b.record) return a.record < b.record;
+            if (a.t_first != b.t_first) return a.t_first < b.t_first;
+            return (a.flags & KGMA_RUN_MARKER) < (b.flags & KGMA_RUN_MARKER);
+        };
+        if (!ok) std::sort(runs.begin(), runs.end(), less);
+        else {
+            std::vector<uint32_t> start(nbk + 1, 0);
+            for (const kgma_run &r : runs) start[(size_t)r.profile * (maxr + 1) + r.record + 1]++;
+            for (size_t i = 0; i < nbk; i++) start[i + 1] += start[i];
+            std::vector<kgma_run> tmp(runs.size());
+            std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+            for (const kgma_run &r : runs) tmp[fill[(size_t)r.profile * (maxr + 1) + r.record]++] = r;
+            for (size_t i = 0; i < nbk; i++)
+                if (start[i + 1] - start[i] > 1)
+                    std::sort(tmp.begin() + start[i], tmp.begin() + start[i + 1], [](const kgma_run &a, const kgma_run &b) {
+                        if (a.t_first != b.t_first) return a.t_first < b.t_first;
+                        return (a.flags & KGMA_RUN_MARKER) < (b.flags & KGMA_RUN_MARKER);
+                    });
+            runs.swap(tmp);
+        }
+    }
     std::vector<kgma_run> out;
     out.reserve(runs.size());
     for (const kgma_run &r : runs) {
@@ -174,13 +199,25 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
     for (int r = 0; r < nr; r++) {
         const int64_t L = g->recs[r].len, steps = steps_of(r);
         if (steps > 0) {
+            // run-end events of all profiles ordered by (end step, profile index): the reference visits profiles in index order
+            // inside each loop step (:95).  Every profile's runs are already ordered, so this is a C-way merge.
             evs.clear();
-            for (int q = 0; q < C; q++) {
-                Span sp = span[(size_t)q * nr + r];
-                for (size_t i = sp.b; i < sp.e; i++) if (!(runs[i].flags & KGMA_RUN_MARKER)) evs.push_back({ runs[i].t_last + 1, q, i });
+            {
+                size_t head[MAX_PROFILES], tail[MAX_PROFILES];
+                for (int q = 0; q < C; q++) { Span sp = span[(size_t)q * nr + r]; head[q] = sp.b; tail[q] = sp.e; }
+                for (;;) {
+                    int best = -1; int64_t be = 0;
+                    for (int q = 0; q < C; q++) {
+                        while (head[q] < tail[q] && (runs[head[q]].flags & KGMA_RUN_MARKER)) head[q]++;
+                        if (head[q] >= tail[q]) continue;
+                        const int64_t e = runs[head[q]].t_last + 1;
+                        if (best < 0 || e < be) { best = q; be = e; }
+                    }
+                    if (best < 0) break;
+                    evs.push_back({ be, best, head[best] });
+                    head[best]++;
+                }
             }
-            // the reference visits profiles in index order inside each loop step (:95)
-            std::sort(evs.begin(), evs.end(), [](const Ev &a, const Ev &b) { return a.end_step != b.end_step ? a.end_step < b.end_step : a.q < b.q; });
             std::vector<int64_t> cur(C), CMIs(C, 1); std::vector<char> stop(C, 1);
             for (int q = 0; q < C; q++) cur[q] = first_D[(size_t)q * nr + r];     // :73 curr_mins = first-window distance
             int64_t prev_a = 0, prev_b = 0;                                          // :59 prev_hit_range = 0:0

@@ -469,6 +469,14 @@ int build_proftab(kgma_ctx *ctx, const kgma_profile &p, ProfTab &t)
     long long a = 0, b = 0;
     ceil_mul_exact(lo, scale, &a); ceil_mul_exact(hi, scale, &b);
     t.Tlo = a; t.Thi = std::max<long long>(b, t.T);
+    {   // fingerprint of everything the prefilter table depends on (64-bit words of S, then the scalars)
+        uint64_t h = 1469598103934665603ull;
+        auto mixw = [&](uint64_t w) { h ^= w; h *= 1099511628211ull; h ^= h >> 29; };
+        for (size_t c = 0; c + 1 < nb; c += 2) mixw(((uint64_t)(uint32_t)t.S_rev[c] << 32) | (uint32_t)t.S_rev[c + 1]);
+        if (nb & 1) mixw((uint32_t)t.S_rev[nb - 1]);
+        mixw((uint64_t)t.Thi); mixw((uint64_t)t.N); mixw((uint64_t)t.nk); mixw((uint64_t)t.k);
+        t.hash = h;
+    }
     return KGMA_OK;
 }
 
@@ -612,9 +620,9 @@ struct FilterGroup {
 
 static const kgma_ctx::FTab *get_ftab(kgma_ctx *ctx, const ScanPlan &pl, const std::vector<int> &group)
 {
-    uint64_t key = 1469598103934665603ull;                         // FNV-1a over everything the table depends on
+    uint64_t key = 1469598103934665603ull;                         // FNV-1a over the members' fingerprints (ProfTab::hash)
     auto mix = [&](const void *p, size_t n) { const unsigned char *b = (const unsigned char *)p; for (size_t i = 0; i < n; i++) { key ^= b[i]; key *= 1099511628211ull; } };
-    for (int q : group) { const ProfTab &t = pl.tabs[(size_t)q]; mix(t.S_rev.data(), t.S_rev.size() * 4); mix(&t.Thi, 8); mix(&t.N, 4); mix(&t.nk, 8); mix(&t.k, 4); }
+    for (int q : group) mix(&pl.tabs[(size_t)q].hash, 8);
     mix(&pl.maxnk, 8);
     for (const auto &f : ctx->ftabs) if (f.key == key) return &f;
     ctx->ftabs.emplace_back();
