@@ -187,7 +187,7 @@ int kgma_profile_from_kfv(const double *kfv, int64_t n_bins, int32_t max_n, int3
         bool ok = true;
         for (int64_t i = 0; i < n_bins && ok; i++) {
             double x = kfv[i] * (double)N, rx = std::nearbyint(x);
-            if (std::fabs(x - rx) > 1e-7 * std::max(1.0, std::fabs(x)) || rx < 0 || rx > 2.0e9) ok = false;
+            if (std::fabs(x - rx) > 1e-9 * std::max(1.0, std::fabs(x)) || rx < 0 || rx > 2.0e9) ok = false;
         }
         if (!ok) continue;
         for (int64_t i = 0; i < n_bins; i++) S[i] = (int32_t)std::nearbyint(kfv[i] * (double)N);

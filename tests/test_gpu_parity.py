@@ -797,3 +797,46 @@ def test_fuzz_vs_oracle(K, O, tmp_path, seed):
                 assert_parity(K, O, out, lambda: O.Omn_KmerGMA(str(gpath), [np.asarray(v) for v in rvs], wss, cs, k=k, thr_vec=thrs, buff=buff,
                                                                align_hits=align, gap_open_score=go, gap_extend_score=ge)[0],
                               [v.n_refs for v in rvs], cluster=True)
+
+
+def test_error_paths(K, prof):
+    """status codes at the C ABI (no exception crosses it; every failure leaves the context usable)"""
+    RV, ws, cons = prof
+    L = K.L
+    ctx = K.default_context()
+    lib = ctx._lib
+    g = K.Genome.from_records([("r", "ACGT" * 500)])
+
+    def code(fn):
+        with pytest.raises(K.KmerGMAError) as e:
+            fn()
+        return e.value.code
+
+    # k outside 1..7, k >= window, negative threshold, a profile that is not rational
+    big = K.KFV(np.zeros(4 ** 8), np.zeros(4 ** 8, np.int32), 1)
+    assert code(lambda: K.scan_raw(g, [big], [100], ["A" * 100], [10.0], 8, L.MODE_SINGLE, 50, 0, -69, -1)) == L.E_UNSUPPORTED
+    assert code(lambda: K.scan_raw(g, [RV], [6], [cons], [10.0], 6, L.MODE_SINGLE, 50, 0, -69, -1)) == L.E_WINDOW
+    assert code(lambda: K.scan_raw(g, [RV], [ws], [cons], [-1.0], 6, L.MODE_SINGLE, 50, 0, -69, -1)) == L.E_ARG
+    assert code(lambda: K.scan_raw(g, [np.sqrt(np.arange(4096) + 2.0)], [ws], [cons], [30.0], 6, L.MODE_SINGLE, 50, 0, -69, -1)) != 0
+    # single mode takes one profile; profiles must share k; cluster mode needs k >= 2
+    assert code(lambda: K.scan_raw(g, [RV, RV], [ws, ws], [cons, cons], [30.0, 30.0], 6, L.MODE_SINGLE, 50, 0, -69, -1)) == L.E_ARG
+    rv1 = K.gen_ref_ws_cons(TF, 1)
+    assert code(lambda: K.scan_raw(g, [rv1[0]], [rv1[1]], [rv1[2]], [1.0], 1, L.MODE_CLUSTER, 50, 0, -200, -1)) == L.E_UNSUPPORTED
+    # alignment needs a consensus at least as long as the window (BoundsError in the reference)
+    gm = K.Genome.from_fasta(MINI_GENOME)
+    assert code(lambda: K.scan_raw(gm, [RV], [ws], [cons[:100]], [30.0], 6, L.MODE_SINGLE, 50, L.F_ALIGN, -69, -1)) == L.E_ARG
+    # unsealed genome
+    h = C.c_void_p(); lib.kgma_genome_create(C.byref(h))
+    lib.kgma_genome_append_ascii(h, b"x", b"x", b"ACGT" * 100, 400)
+    raw = K.Genome(h, lib)
+    assert code(lambda: K.scan_raw(raw, [RV], [ws], [cons], [30.0], 6, L.MODE_SINGLE, 50, 0, -69, -1)) == L.E_STATE
+    # exact match: symbol outside A,C,G,T,N; empty query
+    assert code(lambda: K.exactMatch("ACGU", g)) == L.E_SYMBOL
+    assert code(lambda: K.exactMatch("", g)) == L.E_ARG
+    # align batch: range outside the record
+    with pytest.raises(K.KmerGMAError):
+        K.align_unitrange((g, 0), (1900, 2100), cons, ws, 2000)
+    # the context still works
+    out = K.scan_raw(g, [RV], [ws], [cons], [30.0], 6, L.MODE_SINGLE, 50, 0, -69, -1)
+    assert len(out.hits) == 0
+    assert "kgma" in str(K.KmerGMAError(L.E_ARG, "x"))
