@@ -337,6 +337,135 @@ static inline uint8_t sym_code(char c)
     }
 }
 
+static int slot_scratch(kgma_ctx *ctx, int slot, size_t dbytes, size_t hbytes, void **d, void **h)
+{
+    if (dbytes > ctx->a_dev_bytes[slot]) {
+        if (ctx->a_dev[slot]) cudaFree(ctx->a_dev[slot]);
+        ctx->a_dev[slot] = nullptr; ctx->a_dev_bytes[slot] = 0;
+        const size_t nb = std::max(dbytes + dbytes / 4, (size_t)1 << 20);
+        KGMA_CUDA(ctx, cudaMalloc(&ctx->a_dev[slot], nb));
+        ctx->a_dev_bytes[slot] = nb;
+    }
+    if (hbytes > ctx->a_host_bytes[slot]) {
+        if (ctx->a_host[slot]) cudaFreeHost(ctx->a_host[slot]);
+        ctx->a_host[slot] = nullptr; ctx->a_host_bytes[slot] = 0;
+        const size_t nb = std::max(hbytes + hbytes / 4, (size_t)1 << 20);
+        KGMA_CUDA(ctx, cudaHostAlloc(&ctx->a_host[slot], nb, cudaHostAllocDefault));
+        ctx->a_host_bytes[slot] = nb;
+    }
+    *d = ctx->a_dev[slot]; *h = ctx->a_host[slot];
+    return KGMA_OK;
+}
+
+// Queue the trace-free extension of `reqs` on stream `st` (own scratch per slot, so it can run next to a scan that is
+// still streaming); align_collect waits for it and converts the results.
+int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &reqs, const kgma_profile *profiles, int n_profiles,
+                  bool single_mode_truncate, int gap_open, int gap_extend, bool tie_open, cudaStream_t st, int slot, AlignTicket *t)
+{
+    *t = AlignTicket{};
+    if (reqs.empty()) return KGMA_OK;
+    KGMA_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<uint8_t> acodes; std::vector<int32_t> a_off(n_profiles), a_len(n_profiles);
+    for (int q = 0; q < n_profiles; q++) {
+        const kgma_profile &p = profiles[q];
+        if (!p.consensus) return set_err(ctx, KGMA_E_ARG, "profile %d has no consensus sequence to align against", q);
+        int len = p.consensus_len;
+        if (single_mode_truncate) {                      // Alignment.jl:42 view(consensus_seq, 1:windowsize)
+            if (len < p.window) return set_err(ctx, KGMA_E_ARG, "BoundsError: consensus (%d) shorter than the window (%lld)", len, (long long)p.window);
+            len = (int)p.window;
+        }
+        a_off[q] = (int32_t)acodes.size(); a_len[q] = len;
+        for (int i = 0; i < len; i++) {
+            uint8_t c = sym_code(p.consensus[i]);
+            if (c == 255) return set_err(ctx, KGMA_E_SYMBOL, "consensus of profile %d holds a symbol outside A,C,G,T,N", q);
+            acodes.push_back(c);
+        }
+    }
+    const std::vector<int64_t> &nruns = genome_nruns(g);
+    const bool on_dev = ctx->dg_uid == g->uid && ctx->d_seq2 && ctx->d_have_hi > ctx->d_have_lo;
+    std::vector<AlignJob2> jobs(reqs.size()); std::vector<uint8_t> bcodes; int maxn = 0;
+    for (size_t i = 0; i < reqs.size(); i++) {
+        const AlignReq &rq = reqs[i];
+        if (rq.record < 0 || rq.record >= (int)g->recs.size() || rq.profile < 0 || rq.profile >= n_profiles)
+            return set_err(ctx, KGMA_E_ARG, "alignment request %zu out of range", i);
+        const kgma::Record &R = g->recs[rq.record];
+        if (rq.first < 1 || rq.last > R.len || rq.last < rq.first) return set_err(ctx, KGMA_E_ARG, "alignment range %lld:%lld invalid", (long long)rq.first, (long long)rq.last);
+        AlignJob2 &J = jobs[i];
+        J.gpos = R.off + rq.first - 1; J.n = (int)(rq.last - rq.first + 1); J.a_off = a_off[rq.profile]; J.m = a_len[rq.profile]; J.b_off = -1;
+        maxn = std::max(maxn, J.n);
+        if (J.m + J.n >= 4095) return set_err(ctx, KGMA_E_UNSUPPORTED, "alignment of %d x %d too long for the extension kernel (12-bit gap lengths)", J.m, J.n);
+        if (!(on_dev && J.gpos >= ctx->d_have_lo && J.gpos + J.n + 16 <= ctx->d_have_hi)) {      // slice lives on another shard's device: ship codes
+            J.b_off = (int32_t)bcodes.size();
+            for (int64_t p = rq.first; p <= rq.last; p++) {
+                int64_t gp = R.off + p - 1;
+                uint8_t c = (uint8_t)base_code(g, gp);
+                if (base_masked(g, gp)) { if (c != 3) return set_err(ctx, KGMA_E_SYMBOL, "subject holds a symbol outside A,C,G,T,N"); c = 4; }
+                bcodes.push_back(c);
+            }
+        }
+    }
+    if (g->ambiguous) return set_err(ctx, KGMA_E_SYMBOL, "subject holds a symbol outside A,C,G,T,N");
+    const int nj = (int)jobs.size();
+    const int ncol = (maxn + 1 + 31) & ~31;
+    const int warps_per_block = 4;
+    constexpr int ROWS = 10;                                   // DP rows per lane: one sweep covers 320 consensus rows
+    int maxm = 0; for (int q = 0; q < n_profiles; q++) maxm = std::max(maxm, a_len[q]);
+    const bool need_boundary = maxm > 32 * ROWS;
+    const size_t per_warp = (((size_t)ncol * (need_boundary ? (6 * 4 + 1) : 1)) + 15) & ~(size_t)15;
+    const size_t smem = (size_t)warps_per_block * per_warp;
+    if (smem > ctx->smem_optin) return set_err(ctx, KGMA_E_UNSUPPORTED, "subject slice of %d bases too long for the extension kernel", maxn);
+    size_t o = 0;
+    auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
+    const size_t o_a = carve(acodes.size()), o_b = carve(bcodes.size()), o_j = carve((size_t)nj * sizeof(AlignJob2));
+    const size_t o_n = carve(nruns.size() * 8 + 8);
+    const size_t up = o;
+    const size_t o_c = carve(256), o_o = carve((size_t)nj * sizeof(AlignOut));
+    void *dv = nullptr, *hv = nullptr;
+    int rc = slot_scratch(ctx, slot, o, up + (size_t)nj * sizeof(AlignOut), &dv, &hv);
+    if (rc) return rc;
+    unsigned char *d = (unsigned char *)dv, *h = (unsigned char *)hv;
+    memcpy(h + o_a, acodes.data(), acodes.size());
+    if (!bcodes.empty()) memcpy(h + o_b, bcodes.data(), bcodes.size());
+    memcpy(h + o_j, jobs.data(), (size_t)nj * sizeof(AlignJob2));
+    if (!nruns.empty()) memcpy(h + o_n, nruns.data(), nruns.size() * 8);
+    KGMA_CUDA(ctx, cudaMemcpyAsync(d, h, up, cudaMemcpyHostToDevice, st));
+    KGMA_CUDA(ctx, cudaMemsetAsync(d + o_c, 0, 256, st));
+    ctx->stats.h2d_bytes += up;
+    AlignArgs2 A{};
+    A.a = d + o_a; A.seq = ctx->d_seq2; A.nruns = (const long long *)(d + o_n); A.n_nruns = (int)(nruns.size() / 2);
+    A.b = d + o_b; A.jobs = (const AlignJob2 *)(d + o_j); A.njobs = nj; A.next_job = (int *)(d + o_c);
+    A.out = (AlignOut *)(d + o_o); A.go = -gap_open; A.ge = -gap_extend; A.tie_open = tie_open ? 1 : 0; A.ncol_cap = ncol;
+    A.need_boundary = need_boundary ? 1 : 0;
+    KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::min((nj + warps_per_block - 1) / warps_per_block, ctx->num_sms * 8);
+    KGMA_CUDA(ctx, cudaEventRecord(ctx->a_ev0[slot], st));
+    if (tie_open) kgma_align_summary<ROWS, true><<<grid, warps_per_block * 32, smem, st>>>(A);
+    else kgma_align_summary<ROWS, false><<<grid, warps_per_block * 32, smem, st>>>(A);
+    KGMA_CUDA(ctx, cudaGetLastError());
+    KGMA_CUDA(ctx, cudaEventRecord(ctx->a_ev1[slot], st));
+    ctx->stats.launches++;
+    AlignOut *ho = (AlignOut *)(h + up);
+    KGMA_CUDA(ctx, cudaMemcpyAsync(ho, d + o_o, (size_t)nj * sizeof(AlignOut), cudaMemcpyDeviceToHost, st));
+    KGMA_CUDA(ctx, cudaEventRecord(ctx->a_done[slot], st));
+    ctx->stats.d2h_bytes += (size_t)nj * sizeof(AlignOut);
+    t->active = true; t->slot = slot; t->nj = nj; t->ho = ho;
+    return KGMA_OK;
+}
+
+int align_collect(kgma_ctx *ctx, AlignTicket *t, std::vector<AlignRes> &out)
+{
+    out.assign((size_t)t->nj, AlignRes{ 1, 0, 0, 0, 0 });
+    if (!t->active) return KGMA_OK;
+    KGMA_CUDA(ctx, cudaEventSynchronize(ctx->a_done[t->slot]));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->a_ev0[t->slot], ctx->a_ev1[t->slot]);
+    ctx->stats.align_ms += ms;
+    const AlignOut *ho = (const AlignOut *)t->ho;
+    for (int q = 0; q < t->nj; q++) { out[(size_t)q].lo = (int64_t)ho[q].lower + 1; out[(size_t)q].hi = ho[q].num_sum; out[(size_t)q].score = ho[q].score; }
+    t->active = false;
+    return KGMA_OK;
+}
+
 int align_batch_device(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &reqs,
                        const kgma_profile *profiles, int n_profiles, bool single_mode_truncate,
                        int gap_open, int gap_extend, bool tie_open, bool want_cigars,
@@ -367,81 +496,10 @@ int align_batch_device(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq
     cudaStream_t st = ctx->s_compute;
     if (!want_cigars) {
         // ---- trace-free path: one launch for everything; subjects come from the packed genome already on the device
-        const std::vector<int64_t> &nruns = genome_nruns(g);
-        const bool on_dev = ctx->dg_uid == g->uid && ctx->d_seq2 && ctx->d_have_hi > ctx->d_have_lo;
-        std::vector<AlignJob2> jobs(reqs.size()); std::vector<uint8_t> bcodes; int maxn = 0;
-        for (size_t i = 0; i < reqs.size(); i++) {
-            const AlignReq &rq = reqs[i];
-            if (rq.record < 0 || rq.record >= (int)g->recs.size() || rq.profile < 0 || rq.profile >= n_profiles)
-                return set_err(ctx, KGMA_E_ARG, "alignment request %zu out of range", i);
-            const kgma::Record &R = g->recs[rq.record];
-            if (rq.first < 1 || rq.last > R.len || rq.last < rq.first) return set_err(ctx, KGMA_E_ARG, "alignment range %lld:%lld invalid", (long long)rq.first, (long long)rq.last);
-            AlignJob2 &J = jobs[i];
-            J.gpos = R.off + rq.first - 1; J.n = (int)(rq.last - rq.first + 1); J.a_off = a_off[rq.profile]; J.m = a_len[rq.profile]; J.b_off = -1;
-            maxn = std::max(maxn, J.n);
-            if (J.m + J.n >= 4095) return set_err(ctx, KGMA_E_UNSUPPORTED, "alignment of %d x %d too long for the extension kernel (12-bit gap lengths)", J.m, J.n);
-            if (!(on_dev && J.gpos >= ctx->d_have_lo && J.gpos + J.n + 16 <= ctx->d_have_hi)) {      // slice lives on another shard's device: ship codes
-                J.b_off = (int32_t)bcodes.size();
-                for (int64_t p = rq.first; p <= rq.last; p++) {
-                    int64_t gp = R.off + p - 1;
-                    uint8_t c = (uint8_t)base_code(g, gp);
-                    if (base_masked(g, gp)) { if (c != 3) return set_err(ctx, KGMA_E_SYMBOL, "subject holds a symbol outside A,C,G,T,N"); c = 4; }
-                    bcodes.push_back(c);
-                }
-            }
-        }
-        if (g->ambiguous) return set_err(ctx, KGMA_E_SYMBOL, "subject holds a symbol outside A,C,G,T,N");
-        const int nj = (int)jobs.size();
-        const int ncol = (maxn + 1 + 31) & ~31;
-        const int warps_per_block = 4;
-        constexpr int ROWS = 10;                                   // DP rows per lane: one sweep covers 320 consensus rows
-        int maxm = 0; for (int q = 0; q < n_profiles; q++) maxm = std::max(maxm, a_len[q]);
-        const bool need_boundary = maxm > 32 * ROWS;
-        const size_t per_warp = (((size_t)ncol * (need_boundary ? (6 * 4 + 1) : 1)) + 15) & ~(size_t)15;
-        const size_t smem = (size_t)warps_per_block * per_warp;
-        if (smem > ctx->smem_optin) return set_err(ctx, KGMA_E_UNSUPPORTED, "subject slice of %d bases too long for the extension kernel", maxn);
-        size_t o = 0;
-        auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
-        const size_t o_a = carve(acodes.size()), o_b = carve(bcodes.size()), o_j = carve((size_t)nj * sizeof(AlignJob2));
-        const size_t o_n = carve(nruns.size() * 8 + 8);
-        const size_t up = o;
-        const size_t o_c = carve(256), o_o = carve((size_t)nj * sizeof(AlignOut));
-        // the scan's scratch (run lists etc.) has been consumed by now: reuse it
-        void *dv = nullptr, *hv = nullptr;
-        int rc = dev_scratch(ctx, o, &dv);
+        AlignTicket t;
+        int rc = align_enqueue(ctx, g, reqs, profiles, n_profiles, single_mode_truncate, gap_open, gap_extend, tie_open, st, 0, &t);
         if (rc) return rc;
-        rc = host_scratch(ctx, up + (size_t)nj * sizeof(AlignOut), &hv);
-        if (rc) return rc;
-        unsigned char *d = (unsigned char *)dv, *h = (unsigned char *)hv;
-        memcpy(h + o_a, acodes.data(), acodes.size());
-        if (!bcodes.empty()) memcpy(h + o_b, bcodes.data(), bcodes.size());
-        memcpy(h + o_j, jobs.data(), (size_t)nj * sizeof(AlignJob2));
-        if (!nruns.empty()) memcpy(h + o_n, nruns.data(), nruns.size() * 8);
-        KGMA_CUDA(ctx, cudaMemcpyAsync(d, h, up, cudaMemcpyHostToDevice, st));
-        KGMA_CUDA(ctx, cudaMemsetAsync(d + o_c, 0, 256, st));
-        ctx->stats.h2d_bytes += up;
-        AlignArgs2 A{};
-        A.a = d + o_a; A.seq = ctx->d_seq2; A.nruns = (const long long *)(d + o_n); A.n_nruns = (int)(nruns.size() / 2);
-        A.b = d + o_b; A.jobs = (const AlignJob2 *)(d + o_j); A.njobs = nj; A.next_job = (int *)(d + o_c);
-        A.out = (AlignOut *)(d + o_o); A.go = -gap_open; A.ge = -gap_extend; A.tie_open = tie_open ? 1 : 0; A.ncol_cap = ncol;
-        A.need_boundary = need_boundary ? 1 : 0;
-        KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int grid = std::min((nj + warps_per_block - 1) / warps_per_block, ctx->num_sms * 8);
-        KGMA_CUDA(ctx, cudaEventRecord(e0, st));
-        if (tie_open) kgma_align_summary<ROWS, true><<<grid, warps_per_block * 32, smem, st>>>(A);
-        else kgma_align_summary<ROWS, false><<<grid, warps_per_block * 32, smem, st>>>(A);
-        KGMA_CUDA(ctx, cudaGetLastError());
-        KGMA_CUDA(ctx, cudaEventRecord(e1, st));
-        ctx->stats.launches++;
-        AlignOut *ho = (AlignOut *)(h + up);
-        KGMA_CUDA(ctx, cudaMemcpyAsync(ho, d + o_o, (size_t)nj * sizeof(AlignOut), cudaMemcpyDeviceToHost, st));
-        KGMA_CUDA(ctx, cudaStreamSynchronize(st));
-        ctx->stats.d2h_bytes += (size_t)nj * sizeof(AlignOut);
-        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); align_ms += ms;
-        for (int q = 0; q < nj; q++) { out[q].lo = (int64_t)ho[q].lower + 1; out[q].hi = ho[q].num_sum; out[q].score = ho[q].score; }
-        ctx->stats.align_ms += align_ms;
-        return KGMA_OK;
+        return align_collect(ctx, &t, out);
     }
     const size_t TRACE_BUDGET = (size_t)768 << 20;
     size_t done = 0;

@@ -24,8 +24,11 @@ int kgma_create(int device, kgma_ctx **out)
     kgma_ctx *c = new kgma_ctx();
     c->device = device; c->num_sms = prop.multiProcessorCount; c->smem_optin = prop.sharedMemPerBlockOptin;
     bool ok = cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking) == cudaSuccess;
+              cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->s_align, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 8 && ok; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++) ok = cudaEventCreate(&c->a_ev0[i]) == cudaSuccess && cudaEventCreate(&c->a_ev1[i]) == cudaSuccess &&
+                                           cudaEventCreate(&c->a_done[i]) == cudaSuccess;
     if (!ok) { kgma_destroy(c); return set_err(nullptr, KGMA_E_CUDA, "stream/event creation failed"); }
     *out = c;
     return KGMA_OK;
@@ -37,9 +40,19 @@ void kgma_destroy(kgma_ctx *c)
     cudaSetDevice(c->device);
     if (c->s_compute) cudaStreamSynchronize(c->s_compute);
     if (c->s_copy) cudaStreamSynchronize(c->s_copy);
+    if (c->s_align) cudaStreamSynchronize(c->s_align);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) {
+        if (c->a_ev0[i]) cudaEventDestroy(c->a_ev0[i]);
+        if (c->a_ev1[i]) cudaEventDestroy(c->a_ev1[i]);
+        if (c->a_done[i]) cudaEventDestroy(c->a_done[i]);
+        if (c->a_dev[i]) cudaFree(c->a_dev[i]);
+        if (c->a_host[i]) cudaFreeHost(c->a_host[i]);
+    }
+    for (auto &e : c->chunk_ev) cudaEventDestroy(e);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    if (c->s_align) cudaStreamDestroy(c->s_align);
     if (c->d_seq2) cudaFree(c->d_seq2);
     if (c->d_mask) cudaFree(c->d_mask);
     if (c->d_scratch) cudaFree(c->d_scratch);

@@ -65,7 +65,7 @@ struct kgma_result {
 
 struct kgma_ctx {
     int device = 0;
-    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_align = nullptr;
     cudaEvent_t  ev[8] = {};
     int num_sms = 0;
     size_t smem_optin = 0;
@@ -81,6 +81,10 @@ struct kgma_ctx {
     // prefilter weight tables of recent scans (rebuilt only when the profiles / thresholds change)
     struct FTab { uint64_t key = 0; std::vector<uint16_t> tab; int M = 0; bool ok = false; double load = 0; };
     std::deque<FTab> ftabs;        // deque: references stay valid while entries are appended
+    // extension scratch, two slots so that extensions can be queued while a scan still streams
+    void     *a_dev[2] = {}, *a_host[2] = {}; size_t a_dev_bytes[2] = {}, a_host_bytes[2] = {};
+    cudaEvent_t a_ev0[2] = {}, a_ev1[2] = {}, a_done[2] = {};
+    std::vector<cudaEvent_t> chunk_ev;             // one event per streamed chunk (pipelined scan)
     // scratch
     void     *d_scratch = nullptr; size_t d_scratch_bytes = 0;
     void     *h_scratch = nullptr; size_t h_scratch_bytes = 0;   // pinned
@@ -121,12 +125,21 @@ inline uint32_t rev_kmer(uint32_t c, int k) { uint32_t r = 0; for (int j = 0; j 
 // ---- replay.cpp
 struct AlignReq { int32_t record, profile; int64_t first, last; };       // 1-based range to extend
 struct AlignRes { int64_t lo, hi, score; uint32_t cig_off, cig_len; };   // cigar_to_UnitRange result (relative, 1-based)
+struct Pending { size_t hit; size_t req; int64_t first; };                 // hit waiting for its extension result
 void merge_runs(std::vector<kgma_run> &runs);
+void apply_extensions(kgma_genome *g, std::vector<kgma_hit> &hits, const std::vector<Pending> &pend, const std::vector<AlignRes> &ares);
+int  replay_single_range(kgma_ctx *ctx, kgma_genome *g, const ProfTab &t, const kgma_scan_params &P,
+                         const std::vector<kgma_run> &runs, const std::vector<int64_t> &first_D, int r0, int r1,
+                         int64_t *genome_pos_io, std::vector<kgma_hit> &hits, std::vector<AlignReq> &reqs, std::vector<Pending> &pend);
 int  replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, const kgma_profile *profiles,
             const kgma_scan_params &P, std::vector<kgma_run> &runs, const std::vector<int64_t> &first_D,
             kgma_result *res);
 
 // ---- align.cu
+struct AlignTicket { bool active = false; int slot = 0, nj = 0; void *ho = nullptr; };
+int  align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &reqs, const kgma_profile *profiles, int n_profiles,
+                   bool single_mode_truncate, int gap_open, int gap_extend, bool tie_open, cudaStream_t st, int slot, AlignTicket *t);
+int  align_collect(kgma_ctx *ctx, AlignTicket *t, std::vector<AlignRes> &out);
 int  align_batch_device(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &reqs,
                         const kgma_profile *profiles, int n_profiles, bool single_mode_truncate,
                         int gap_open, int gap_extend, bool tie_open, bool want_cigars,

@@ -85,6 +85,64 @@ static void remap(int64_t first, int64_t L, const AlignRes &a, int64_t *nf, int6
     *nf = f; *nl = l;
 }
 
+void apply_extensions(kgma_genome *g, std::vector<kgma_hit> &hits, const std::vector<Pending> &pend, const std::vector<AlignRes> &ares)
+{
+    for (const Pending &p : pend) {
+        kgma_hit &h = hits[p.hit];
+        remap(p.first, g->recs[h.record].len, ares[p.req], &h.first, &h.last);
+        h.align_score = ares[p.req].score; h.cigar_off = ares[p.req].cig_off; h.cigar_len = ares[p.req].cig_len;
+    }
+}
+
+// ac_gma_testing! state machine (GenomeMiner.jl:57,82-104) over records [r0, r1) from merged, sorted single-profile runs.
+// Appends hits (unextended ranges) and, when KGMA_F_ALIGN, the extension requests; *genome_pos carries GenomePos across
+// calls, so a genome can be replayed in record ranges as their run lists become available (pipelined streaming scan).
+int replay_single_range(kgma_ctx *ctx, kgma_genome *g, const ProfTab &t, const kgma_scan_params &P,
+                        const std::vector<kgma_run> &runs, const std::vector<int64_t> &first_D, int r0, int r1,
+                        int64_t *genome_pos_io, std::vector<kgma_hit> &hits, std::vector<AlignReq> &reqs, std::vector<Pending> &pend)
+{
+    const int k = t.k; const int64_t ws = t.ws, buff = P.buff;
+    const bool do_align = (P.flags & KGMA_F_ALIGN) != 0;
+    int64_t genome_pos = *genome_pos_io;
+    size_t i = 0;
+    // runs are ordered by (profile, record, t_first): skip to the first record of the range
+    while (i < runs.size() && runs[i].record < r0) i++;
+    for (int r = r0; r < r1; r++) {
+        const int64_t L = g->recs[r].len;
+        size_t b = i; while (i < runs.size() && runs[i].record == r) i++;
+        if (L < ws) continue;                             // GenomeMiner.jl:37-39 (genome_pos not advanced)
+        const int64_t steps = (P.only_record >= 0 && r != P.only_record) ? 0 : std::max<int64_t>(0, L - ws);
+        if (steps > 0 && i > b) {
+            int64_t cur = first_D[r];                     // :57 currminim = kmerDist of the first window
+            if (cur == INT64_MIN) return set_err(ctx, KGMA_E_STATE, "first-window distance of record %d missing", r);
+            int64_t CMI = 2, goal = 0; bool stop = true;
+            for (size_t j = b; j < i; j++) {
+                const kgma_run &ru = runs[j];
+                if (ru.flags & KGMA_RUN_MARKER) continue;
+                uint32_t hflags = ru.flags & (KGMA_HIT_NEAR_THR | KGMA_HIT_ARGMIN_TIE);
+                if (ru.D_min < cur) { cur = ru.D_min; CMI = (k - 1) + ru.t_argmin; stop = false; }   // :82-87 CMI = i_left
+                if (ru.t_last >= steps) break;            // run still open at the record end: never emitted (A.1 step 5)
+                if (!stop) {                              // :90-104 at step t_last+1
+                    stop = true; CMI += 1;
+                    if (CMI > goal) {
+                        goal = CMI + ws - 1;
+                        int64_t a = std::max<int64_t>(CMI - buff, 1), bb = std::min<int64_t>(CMI + ws - 1 + buff, L);
+                        kgma_hit h{};
+                        h.record = r; h.profile = 0; h.cmi = CMI; h.first = a; h.last = bb; h.genome_pos = genome_pos;
+                        h.D = cur; h.dist = (double)cur / t.denom; h.flags = hflags | round_half_flag(h.dist);
+                        if (do_align) { pend.push_back({ hits.size(), reqs.size(), a }); reqs.push_back({ r, 0, a, bb }); }
+                        hits.push_back(h);
+                        cur = INT64_MAX;                  // :102 currminim = kmerDist (some value >= thr)
+                    }
+                }
+            }
+        }
+        genome_pos += L;                                  // :106
+    }
+    *genome_pos_io = genome_pos;
+    return KGMA_OK;
+}
+
 int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, const kgma_profile *profiles,
            const kgma_scan_params &P, std::vector<kgma_run> &runs, const std::vector<int64_t> &first_D,
            kgma_result *res)
@@ -117,55 +175,19 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
 
     std::vector<AlignReq> reqs; std::vector<AlignRes> ares;
     std::vector<int64_t> req_of_run;                      // cluster mode: run index -> request index
-    struct Pending { size_t hit; size_t req; int64_t first; };
     std::vector<Pending> pend;                            // single mode: hits waiting for their extension
 
     if (!cluster) {
         // ---------------- ac_gma_testing! ----------------
-        const ProfTab &t = tabs[0]; const int64_t ws = t.ws;
         int64_t genome_pos = 0;
-        for (int r = 0; r < nr; r++) {
-            const int64_t L = g->recs[r].len;
-            if (L < ws) continue;                         // GenomeMiner.jl:37-39 (genome_pos not advanced)
-            const int64_t steps = steps_of(r);
-            Span sp = span[r];
-            if (steps > 0 && sp.e > sp.b) {
-                int64_t cur = first_D[r];                 // :57 currminim = kmerDist of the first window
-                if (cur == INT64_MIN) return set_err(ctx, KGMA_E_STATE, "first-window distance of record %d missing", r);
-                int64_t CMI = 2, goal = 0; bool stop = true;
-                for (size_t i = sp.b; i < sp.e; i++) {
-                    const kgma_run &ru = runs[i];
-                    if (ru.flags & KGMA_RUN_MARKER) continue;
-                    uint32_t hflags = ru.flags & (KGMA_HIT_NEAR_THR | KGMA_HIT_ARGMIN_TIE);
-                    if (ru.D_min < cur) { cur = ru.D_min; CMI = (k - 1) + ru.t_argmin; stop = false; }   // :82-87 CMI = i_left
-                    if (ru.t_last >= steps) break;        // run still open at the record end: never emitted (A.1 step 5)
-                    if (!stop) {                          // :90-104 at step t_last+1
-                        stop = true; CMI += 1;
-                        if (CMI > goal) {
-                            goal = CMI + ws - 1;
-                            int64_t a = std::max<int64_t>(CMI - buff, 1), b = std::min<int64_t>(CMI + ws - 1 + buff, L);
-                            kgma_hit h{};
-                            h.record = r; h.profile = 0; h.cmi = CMI; h.first = a; h.last = b; h.genome_pos = genome_pos;
-                            h.D = cur; h.dist = (double)cur / t.denom; h.flags = hflags | round_half_flag(h.dist);
-                            if (do_align) { pend.push_back({ res->hits.size(), reqs.size(), a }); reqs.push_back({ r, 0, a, b }); }
-                            res->hits.push_back(h);
-                            cur = INT64_MAX;              // :102 currminim = kmerDist (some value >= thr)
-                        }
-                    }
-                }
-            }
-            genome_pos += L;                              // :106
-        }
+        int rc = replay_single_range(ctx, g, tabs[0], P, runs, first_D, 0, nr, &genome_pos, res->hits, reqs, pend);
+        if (rc) return rc;
         if (do_align && !reqs.empty()) {
-            int rc = align_batch_device(ctx, g, reqs, profiles, 1, true, P.gap_open, P.gap_extend,
-                                        (P.flags & KGMA_F_TIE_OPEN) != 0, want_cig, ares,
-                                        want_cig ? &res->cigar_ops : nullptr, want_cig ? &res->cigar_cnt : nullptr);
+            rc = align_batch_device(ctx, g, reqs, profiles, 1, true, P.gap_open, P.gap_extend,
+                                    (P.flags & KGMA_F_TIE_OPEN) != 0, want_cig, ares,
+                                    want_cig ? &res->cigar_ops : nullptr, want_cig ? &res->cigar_cnt : nullptr);
             if (rc) return rc;
-            for (const Pending &p : pend) {
-                kgma_hit &h = res->hits[p.hit];
-                remap(p.first, g->recs[h.record].len, ares[p.req], &h.first, &h.last);
-                h.align_score = ares[p.req].score; h.cigar_off = ares[p.req].cig_off; h.cigar_len = ares[p.req].cig_len;
-            }
+            apply_extensions(g, res->hits, pend, ares);
         }
         if (ctx) ctx->stats.n_align = (int64_t)reqs.size();
         return KGMA_OK;

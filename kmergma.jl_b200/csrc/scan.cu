@@ -25,6 +25,7 @@
 #include <climits>
 #include <cstdlib>
 #include <chrono>
+#include <functional>
 
 namespace kgma {
 
@@ -149,6 +150,7 @@ struct EvalArgs {
     const uint32_t *cand_count; uint32_t cand_cap;   // record-start blocks of which only window 0 is evaluated
     const uint32_t *bitmap; uint32_t n_seed;
     unsigned long long *next_item;  // [C] dynamic work counters (spans differ a lot in length: static striding leaves warps idle)
+    long long cand_blk_lo, cand_blk_hi;   // candidate mode: only blocks in [lo, hi) (a pipelined scan evaluates record ranges separately)
     long long n_items;              // dense mode: number of implicit items
     const RecDev *recs; int nrec;
     int C, k, span;                 // span: windows per dense item
@@ -218,6 +220,7 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
             int r; long long w0, n;
             if (a.cand) {
                 const long long b = (long long)a.cand[item];
+                if (b < a.cand_blk_lo || b >= a.cand_blk_hi) continue;
                 const long long gp = b * FBLOCK;
                 int lo = 0, hi = a.nrec;                                      // last record with off <= gp
                 while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (a.recs[mid].off <= gp) lo = mid; else hi = mid; }
@@ -610,6 +613,15 @@ constexpr long long NO_D = (long long)0x8080808080808080ull;   // cudaMemset(0x8
 
 using namespace kgma;
 
+// Pipelined streaming scan (single profile): records [0, rec_split) are evaluated as soon as their last block has been
+// filtered; on_first_part is called with their runs while the rest of the genome is still being copied and filtered.
+struct PhaseHook {
+    int rec_split = 0;
+    std::function<int(std::vector<kgma_run> &, const std::vector<int64_t> &)> on_first_part;
+    size_t n_runs_first = 0;       // out: how many entries of res->runs belong to the first part
+    bool used = false;             // out: the scan did run in two parts
+};
+
 // One prefilter pass = one group of profiles sharing a weight table, a candidate list and a block bitmap.
 struct FilterGroup {
     std::vector<int> q;            // profile indices
@@ -636,7 +648,8 @@ static const kgma_ctx::FTab *get_ftab(kgma_ctx *ctx, const ScanPlan &pl, const s
 // kernel reading the candidate lists from device memory, result copies) with ONE host synchronisation at the end.
 // Returns KGMA_E_CAPACITY with *need_runs set when the run list was too small (the caller retries once).
 static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int C,
-                          const kgma_scan_params &P, ScanPlan &pl, kgma_result *res, uint32_t run_cap, uint64_t *need_runs)
+                          const kgma_scan_params &P, ScanPlan &pl, kgma_result *res, uint32_t run_cap, uint64_t *need_runs,
+                          PhaseHook *hook = nullptr)
 {
     const double t_wall0 = now_ms();
     *need_runs = 0;
@@ -739,7 +752,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     const size_t o_seed = carve((seeds.size() + 1) * 4);
     for (FilterGroup &fg : groups) if (!fg.dense) fg.o_tab = carve(65536 * 2);
     const size_t up_bytes = o;                                     // everything above is uploaded from the staging block
-    const size_t o_cnt = carve(256), o_first = carve((size_t)C * std::max(nr, 1) * 8), o_runs = carve((size_t)run_cap * sizeof(kgma_run));
+    const size_t o_cnt = carve(512), o_first = carve((size_t)C * std::max(nr, 1) * 8), o_runs = carve((size_t)run_cap * sizeof(kgma_run));
     const size_t bitmap_bytes = ((size_t)nblk_total / 32 + 4) * 4;
     for (FilterGroup &fg : groups) if (!fg.dense) { fg.o_cand = carve((size_t)cand_cap * 4); fg.o_bits = carve(bitmap_bytes); }
     const size_t o_dists = carve(want_dists ? (size_t)C * (size_t)std::max<int64_t>(ndist, 1) * 8 : 0);
@@ -749,9 +762,9 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     unsigned char *ds = (unsigned char *)dsv;
     const size_t back_bytes = 256 + (size_t)C * std::max(nr, 1) * 8 + (size_t)run_head * sizeof(kgma_run);
     void *hsv = nullptr;
-    rc = host_scratch(ctx, up_bytes + back_bytes, &hsv);
+    rc = host_scratch(ctx, up_bytes + 2 * back_bytes, &hsv);
     if (rc) return rc;
-    unsigned char *hs = (unsigned char *)hsv, *hback = hs + up_bytes;
+    unsigned char *hs = (unsigned char *)hsv, *hback = hs + up_bytes, *hbackA = hback + back_bytes;
     for (int q = 0; q < C; q++) memcpy(hs + o_S + (size_t)q * nb * 4, pl.tabs[q].S_rev.data(), nb * 4);
     for (const FilterGroup &fg : groups) if (!fg.dense) memcpy(hs + fg.o_tab, fg.ft->tab.data(), 65536 * 2);
     memcpy(hs + o_recs, recs.data(), recs.size() * sizeof(RecDev));
@@ -760,11 +773,12 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
 
     cudaStream_t sc_ = ctx->s_compute, sp = ctx->s_copy;
     cudaEvent_t e_start = ctx->ev[0], e_h2d = ctx->ev[1], e_filt = ctx->ev[2], e_exact = ctx->ev[3], e_fstart = ctx->ev[4];
-    // counter block (256 B): [0] run_count, [1 + gi] candidate count of group gi, bytes 128.. next_item[q]
+    // counter block (512 B): [0] run_count, [1 + gi] candidate count of group gi, bytes 128.. next_item[q],
+    // bytes 256.. next_item[q] of the first part of a pipelined scan
     uint32_t *d_counters = (uint32_t *)(ds + o_cnt);
     KGMA_CUDA(ctx, cudaEventRecord(e_start, sc_));
     KGMA_CUDA(ctx, cudaMemcpyAsync(ds, hs, up_bytes, cudaMemcpyHostToDevice, sc_));
-    KGMA_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 256, sc_));
+    KGMA_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 512, sc_));
     KGMA_CUDA(ctx, cudaMemsetAsync(ds + o_first, 0x80, (size_t)C * std::max(nr, 1) * 8, sc_));
     for (size_t gi = 0; gi < groups.size(); gi++) {
         const FilterGroup &fg = groups[gi];
@@ -785,66 +799,28 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     up_hi = (up_hi + 127) / 128 * 128; up_hi = std::min(up_hi, g->G + TAIL_PAD);
     const bool resident_ok = (P.flags & KGMA_F_RESIDENT) && ctx->d_seq_valid && ctx->d_valid_lo <= up_lo && ctx->d_valid_hi >= up_hi;
 
-    // ---- stream the packed genome: chunked cudaMemcpyAsync on the copy stream, prefilter on the
-    //      compute stream chasing it (double buffering falls out of the two streams + per-chunk events)
-    const int64_t CH = (int64_t)128 << 20;                  // bases per chunk (32 MB of packed data)
-    const int fgrid = ctx->num_sms;
-    int64_t done_blk = blk_lo;                               // target blocks already filtered
-    const int64_t need_after = (int64_t)(M + 1) * FBLOCK + 3 * FGROUP;     // bases that must be present past a target block
-    bool first_filter = true;
-    auto run_filter_to = [&](int64_t avail_hi, bool last) -> int {
-        if (!any_filter) return KGMA_OK;
-        int64_t lim = last ? blk_hi : std::min(blk_hi, ((avail_hi - need_after) / FBLOCK) / 32 * 32);
-        if (lim <= done_blk) return KGMA_OK;
-        if (first_filter) { KGMA_CUDA(ctx, cudaEventRecord(e_fstart, sc_)); first_filter = false; }
-        for (size_t gi = 0; gi < groups.size(); gi++) {
-            const FilterGroup &fg = groups[gi];
-            if (fg.dense) continue;
-            FilterArgs fa{};
-            fa.seq = (const uint4 *)ctx->d_seq2; fa.tab = (const uint16_t *)(ds + fg.o_tab); fa.M = fg.ft->M; fa.thrw = 1u << WFRAC;
-            fa.cand = (uint32_t *)(ds + fg.o_cand); fa.cand_cap = cand_cap; fa.cand_count = d_counters + 1 + gi;
-            fa.bitmap = (uint32_t *)(ds + fg.o_bits);
-            fa.blk_begin = done_blk; fa.blk_end = lim;
-            launch_filter_k(pl.k, fa, fgrid, sc_);
-            KGMA_CUDA(ctx, cudaGetLastError());
-            st.launches++;
-        }
-        done_blk = lim;
-        return KGMA_OK;
-    };
-    if (!resident_ok) {
-        cudaEvent_t e_c[2] = { ctx->ev[5], ctx->ev[6] };
-        KGMA_CUDA(ctx, cudaEventRecord(ctx->ev[7], sc_));
-        KGMA_CUDA(ctx, cudaStreamWaitEvent(sp, ctx->ev[7], 0));
-        int ci = 0;
-        for (int64_t a = up_lo; a < up_hi; a += CH, ci++) {
-            int64_t b = std::min(up_hi, a + CH);
-            KGMA_CUDA(ctx, cudaMemcpyAsync((char *)ctx->d_seq2 + a / 4, (char *)g->seq2 + a / 4, (size_t)(b - a) / 4,
-                                           cudaMemcpyHostToDevice, sp));
-            KGMA_CUDA(ctx, cudaEventRecord(e_c[ci & 1], sp));
-            KGMA_CUDA(ctx, cudaStreamWaitEvent(sc_, e_c[ci & 1], 0));
-            st.h2d_bytes += (b - a) / 4;
-            rc = run_filter_to(b, b >= up_hi);
-            if (rc) return rc;
-            if (ci >= 1) KGMA_CUDA(ctx, cudaEventSynchronize(e_c[(ci - 1) & 1]));   // bound the number of in-flight events reused
-        }
-        KGMA_CUDA(ctx, cudaEventRecord(e_h2d, sc_));
-        ctx->d_seq_valid = true; ctx->d_valid_lo = up_lo; ctx->d_valid_hi = up_hi;
-        ctx->d_have_lo = up_lo; ctx->d_have_hi = up_hi;
-    } else {
-        KGMA_CUDA(ctx, cudaEventRecord(e_h2d, sc_));
-        rc = run_filter_to(up_hi, true);
-        if (rc) return rc;
+    // pipelined scan: the records before hook->rec_split form the first part.  Candidates are divided exactly at the block
+    // where record rec_split starts (records start on block boundaries); the prefilter launch in front of the first part's
+    // evaluation ends on the next multiple of 32 blocks (its launches work in whole warp groups), which only means a few
+    // blocks of the second part are filtered early.
+    int64_t split_blk = -1, split_blk_f = -1;
+    bool pipelined = hook && !resident_ok && groups.size() == 1 && !groups[0].dense && C == 1 && sc == 1 && nr > 1 &&
+                     hook->rec_split > 0 && hook->rec_split < nr;
+    if (pipelined) {
+        split_blk = g->recs[(size_t)hook->rec_split].off / FBLOCK;
+        split_blk_f = (split_blk + 31) / 32 * 32;
+        if (split_blk_f >= blk_hi || split_blk <= blk_lo) pipelined = false;
     }
-    if (first_filter) KGMA_CUDA(ctx, cudaEventRecord(e_fstart, sc_));
-    KGMA_CUDA(ctx, cudaEventRecord(e_filt, sc_));
-
+    bool partA_enqueued = false;
+    cudaEvent_t e_partA = ctx->ev[7];
+    std::function<int()> enqueue_part_a;                     // defined below, once the eval arguments exist
     // ---- count-table kernel over the candidate lists (read on the device) or over everything
     EvalArgs ea{};
     ea.seq = ctx->d_seq2; ea.S = (const int32_t *)(ds + o_S);
     ea.cand_cap = cand_cap; ea.n_seed = (uint32_t)seeds.size();
     ea.next_item = (unsigned long long *)(d_counters + 32);        // bytes 128.. of the zeroed counter block
     ea.recs = (const RecDev *)(ds + o_recs); ea.nrec = nr;
+    ea.cand_blk_lo = 0; ea.cand_blk_hi = LLONG_MAX;
     ea.C = C; ea.k = pl.k; ea.span = span;
     for (int q = 0; q < C; q++) {
         const ProfTab &t = pl.tabs[q];
@@ -866,6 +842,20 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
         return KGMA_OK;
     };
     uint32_t cnts[64] = { 0 };
+    enqueue_part_a = [&]() -> int {  // first part of a pipelined scan: evaluate its candidates, queue the copy of its results
+        ea.cand_blk_lo = 0; ea.cand_blk_hi = split_blk;
+        ea.next_item = (unsigned long long *)(d_counters + 64);   // bytes 256..
+        int rc2 = launch_eval(groups[0].q, false, 0, &groups[0]);
+        ea.next_item = (unsigned long long *)(d_counters + 32);
+        ea.cand_blk_lo = split_blk; ea.cand_blk_hi = LLONG_MAX;    // what the final evaluation still has to do
+        if (rc2) return rc2;
+        KGMA_CUDA(ctx, cudaMemcpyAsync(hbackA, d_counters, 256, cudaMemcpyDeviceToHost, sc_));
+        KGMA_CUDA(ctx, cudaMemcpyAsync(hbackA + 256, ds + o_first, (size_t)C * nr * 8, cudaMemcpyDeviceToHost, sc_));
+        KGMA_CUDA(ctx, cudaMemcpyAsync(hbackA + 256 + (size_t)C * nr * 8, ds + o_runs, (size_t)run_head * sizeof(kgma_run), cudaMemcpyDeviceToHost, sc_));
+        KGMA_CUDA(ctx, cudaEventRecord(e_partA, sc_));
+        st.d2h_bytes += back_bytes;
+        return KGMA_OK;
+    };
     auto fetch = [&]() -> int {     // counters + first-window distances + the head of the run list, one synchronisation
         KGMA_CUDA(ctx, cudaMemcpyAsync(hback, d_counters, 256, cudaMemcpyDeviceToHost, sc_));
         KGMA_CUDA(ctx, cudaMemcpyAsync(hback + 256, ds + o_first, (size_t)C * nr * 8, cudaMemcpyDeviceToHost, sc_));
@@ -875,9 +865,106 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
         st.d2h_bytes += back_bytes;
         return KGMA_OK;
     };
+    // ---- stream the packed genome: chunked cudaMemcpyAsync on the copy stream, prefilter on the
+    //      compute stream chasing it (double buffering falls out of the two streams + per-chunk events)
+    const int64_t CH = (int64_t)128 << 20;                  // bases per chunk (32 MB of packed data)
+    const int fgrid = ctx->num_sms;
+    int64_t done_blk = blk_lo;                               // target blocks already filtered
+    const int64_t need_after = (int64_t)(M + 1) * FBLOCK + 3 * FGROUP;     // bases that must be present past a target block
+    bool first_filter = true;
+    auto run_filter_to = [&](int64_t avail_hi, bool last) -> int {
+        if (!any_filter) return KGMA_OK;
+        int64_t lim = last ? blk_hi : std::min(blk_hi, ((avail_hi - need_after) / FBLOCK) / 32 * 32);
+        if (pipelined && !partA_enqueued && lim >= split_blk_f) {
+            // stop this launch on the split so that the first part can be evaluated right behind it, then carry on
+            const int64_t rest = lim;
+            lim = split_blk_f;
+            if (lim > done_blk) {
+                if (first_filter) { KGMA_CUDA(ctx, cudaEventRecord(e_fstart, sc_)); first_filter = false; }
+                const FilterGroup &fg = groups[0];
+                FilterArgs fa{};
+                fa.seq = (const uint4 *)ctx->d_seq2; fa.tab = (const uint16_t *)(ds + fg.o_tab); fa.M = fg.ft->M; fa.thrw = 1u << WFRAC;
+                fa.cand = (uint32_t *)(ds + fg.o_cand); fa.cand_cap = cand_cap; fa.cand_count = d_counters + 1;
+                fa.bitmap = (uint32_t *)(ds + fg.o_bits);
+                fa.blk_begin = done_blk; fa.blk_end = lim;
+                launch_filter_k(pl.k, fa, fgrid, sc_);
+                KGMA_CUDA(ctx, cudaGetLastError());
+                st.launches++;
+                done_blk = lim;
+            }
+            int rc2 = enqueue_part_a();
+            if (rc2) return rc2;
+            partA_enqueued = true;
+            lim = rest;
+        }
+        if (lim <= done_blk) return KGMA_OK;
+        if (first_filter) { KGMA_CUDA(ctx, cudaEventRecord(e_fstart, sc_)); first_filter = false; }
+        for (size_t gi = 0; gi < groups.size(); gi++) {
+            const FilterGroup &fg = groups[gi];
+            if (fg.dense) continue;
+            FilterArgs fa{};
+            fa.seq = (const uint4 *)ctx->d_seq2; fa.tab = (const uint16_t *)(ds + fg.o_tab); fa.M = fg.ft->M; fa.thrw = 1u << WFRAC;
+            fa.cand = (uint32_t *)(ds + fg.o_cand); fa.cand_cap = cand_cap; fa.cand_count = d_counters + 1 + gi;
+            fa.bitmap = (uint32_t *)(ds + fg.o_bits);
+            fa.blk_begin = done_blk; fa.blk_end = lim;
+            launch_filter_k(pl.k, fa, fgrid, sc_);
+            KGMA_CUDA(ctx, cudaGetLastError());
+            st.launches++;
+        }
+        done_blk = lim;
+        return KGMA_OK;
+    };
+    if (!resident_ok) {
+        cudaEvent_t e_c[2] = { ctx->ev[5], ctx->ev[6] };
+        KGMA_CUDA(ctx, cudaEventRecord(ctx->ev[6 + 0], sc_));      // (ev[6] doubles as the "setup queued" marker before the loop)
+        KGMA_CUDA(ctx, cudaStreamWaitEvent(sp, ctx->ev[6], 0));
+        const size_t nchunks = (size_t)((up_hi - up_lo + CH - 1) / CH);
+        if (pipelined) while (ctx->chunk_ev.size() < nchunks) { cudaEvent_t e; KGMA_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
+        ctx->d_have_lo = up_lo; ctx->d_have_hi = up_hi;            // what the queued copies will have delivered (extension of the first part reads it)
+        int ci = 0;
+        for (int64_t a = up_lo; a < up_hi; a += CH, ci++) {
+            int64_t b = std::min(up_hi, a + CH);
+            KGMA_CUDA(ctx, cudaMemcpyAsync((char *)ctx->d_seq2 + a / 4, (char *)g->seq2 + a / 4, (size_t)(b - a) / 4,
+                                           cudaMemcpyHostToDevice, sp));
+            cudaEvent_t ec = pipelined ? ctx->chunk_ev[(size_t)ci] : e_c[ci & 1];
+            KGMA_CUDA(ctx, cudaEventRecord(ec, sp));
+            KGMA_CUDA(ctx, cudaStreamWaitEvent(sc_, ec, 0));
+            st.h2d_bytes += (b - a) / 4;
+            rc = run_filter_to(b, b >= up_hi);
+            if (rc) return rc;
+            // two events are recycled: wait for the older copy before its event is recorded again.  A pipelined scan has one
+            // event per chunk and queues everything without blocking, so the host is free to work on the first part's results.
+            if (!pipelined && ci >= 1) KGMA_CUDA(ctx, cudaEventSynchronize(e_c[(ci - 1) & 1]));
+        }
+        KGMA_CUDA(ctx, cudaEventRecord(e_h2d, sc_));
+        ctx->d_seq_valid = true; ctx->d_valid_lo = up_lo; ctx->d_valid_hi = up_hi;
+        ctx->d_have_lo = up_lo; ctx->d_have_hi = up_hi;
+    } else {
+        KGMA_CUDA(ctx, cudaEventRecord(e_h2d, sc_));
+        rc = run_filter_to(up_hi, true);
+        if (rc) return rc;
+    }
+    if (first_filter) KGMA_CUDA(ctx, cudaEventRecord(e_fstart, sc_));
+    KGMA_CUDA(ctx, cudaEventRecord(e_filt, sc_));
+
     if (nr > 0) {
         for (size_t gi = 0; gi < groups.size(); gi++) { rc = launch_eval(groups[gi].q, groups[gi].dense, gi, &groups[gi]); if (rc) return rc; }
         KGMA_CUDA(ctx, cudaEventRecord(e_exact, sc_));
+        if (pipelined && partA_enqueued) {
+            // everything is queued; while the rest of the genome streams, hand the first part's runs to the caller
+            KGMA_CUDA(ctx, cudaEventSynchronize(e_partA));
+            uint32_t ca[64]; memcpy(ca, hbackA, 256);
+            if (ca[0] <= run_head && ca[1] <= cand_cap) {
+                std::vector<kgma_run> ra((size_t)ca[0]);
+                if (ca[0]) memcpy(ra.data(), hbackA + 256 + (size_t)C * nr * 8, (size_t)ca[0] * sizeof(kgma_run));
+                std::vector<int64_t> fd((size_t)C * nr, INT64_MIN);
+                const long long *fdp = (const long long *)(hbackA + 256);
+                for (size_t i = 0; i < (size_t)C * nr; i++) if (fdp[i] != NO_D) fd[i] = fdp[i];
+                hook->n_runs_first = ca[0]; hook->used = true;
+                rc = hook->on_first_part(ra, fd);
+                if (rc) { cudaStreamSynchronize(sc_); return rc; }
+            }
+        }
         rc = fetch(); if (rc) return rc;
         std::vector<int> redo;                                     // groups whose candidate list overflowed: evaluate every window
         for (size_t gi = 0; gi < groups.size(); gi++)
@@ -934,13 +1021,16 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
 
 // run list capacity: 1 Mi runs to start with, grown to what the device counted when that was not enough
 static int scan_runs_retry(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int C,
-                           const kgma_scan_params &P, ScanPlan &pl, kgma_result *res)
+                           const kgma_scan_params &P, ScanPlan &pl, kgma_result *res,
+                           PhaseHook *hook = nullptr, const std::function<void()> &reset = nullptr)
 {
     uint64_t need = 0;
-    int rc = scan_runs_impl(ctx, g, profiles, C, P, pl, res, 1u << 20, &need);
+    int rc = scan_runs_impl(ctx, g, profiles, C, P, pl, res, 1u << 20, &need, hook);
     if (rc == KGMA_E_CAPACITY && need > 0 && need < (1ull << 28)) {
         pl = ScanPlan();
-        rc = scan_runs_impl(ctx, g, profiles, C, P, pl, res, (uint32_t)(need + need / 8 + 1024), &need);
+        if (hook) { hook->used = false; hook->n_runs_first = 0; }
+        if (reset) reset();
+        rc = scan_runs_impl(ctx, g, profiles, C, P, pl, res, (uint32_t)(need + need / 8 + 1024), &need, nullptr);
     }
     return rc;
 }
@@ -986,14 +1076,61 @@ int kgma_scan(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int n
     kgma_scan_params P = *params; P.shard_index = 0; P.shard_count = 1;
     kgma_result *res = new kgma_result();
     ScanPlan pl;
-    int rc = scan_runs_retry(ctx, g, profiles, n_profiles, P, pl, res);
+
+    // Pipelined form for the streamed single-profile scan with extension: the records in front of a split point are
+    // replayed and their extension is queued on a second stream while the tail of the genome is still being copied, so
+    // that only the last records' share of replay + extension is left once the copy ends.
+    PhaseHook hook;
+    const int nr = (int)g->recs.size();
+    const bool can_pipeline = g->sealed && P.mode == KGMA_MODE_SINGLE && n_profiles == 1 && (P.flags & KGMA_F_ALIGN) && P.only_record < 0 &&
+                              !(P.flags & (KGMA_F_DENSE | KGMA_F_WANT_DISTS | KGMA_F_WANT_CIGARS)) && nr >= 2 && !getenv("KGMA_NO_PIPELINE");
+    if (can_pipeline) {
+        // split in front of the first record that starts in the last eighth of the genome (but keep at least half in the first part)
+        for (int r = 1; r < nr; r++) {
+            const double frac = (double)g->recs[(size_t)r].off / (double)std::max<int64_t>(1, g->G);
+            if (frac >= 0.5 && (hook.rec_split == 0 || frac <= 0.93)) hook.rec_split = r;
+            if (frac > 0.93) break;
+        }
+    }
+    std::vector<kgma_hit> hitsA; std::vector<AlignReq> reqsA, reqsB; std::vector<Pending> pendA, pendB;
+    std::vector<kgma_run> runsA; AlignTicket tA, tB; int64_t genome_pos = 0;
+    auto reset = [&]() { hitsA.clear(); reqsA.clear(); pendA.clear(); runsA.clear(); genome_pos = 0; if (tA.active) { std::vector<AlignRes> d; align_collect(ctx, &tA, d); } };
+    hook.on_first_part = [&](std::vector<kgma_run> &ra, const std::vector<int64_t> &fd) -> int {
+        merge_runs(ra);
+        int rc2 = replay_single_range(ctx, g, pl.tabs[0], P, ra, fd, 0, hook.rec_split, &genome_pos, hitsA, reqsA, pendA);
+        if (rc2) return rc2;
+        runsA.swap(ra);
+        return align_enqueue(ctx, g, reqsA, profiles, 1, true, P.gap_open, P.gap_extend, (P.flags & KGMA_F_TIE_OPEN) != 0, ctx->s_align, 0, &tA);
+    };
+    int rc = scan_runs_retry(ctx, g, profiles, n_profiles, P, pl, res, hook.rec_split > 0 ? &hook : nullptr, reset);
     if (rc == KGMA_OK) {
         const double t0 = now_ms();
-        rc = replay(ctx, g, pl.tabs, profiles, P, res->runs, res->first_D, res);
+        const double align_before = ctx->stats.align_ms;
+        if (hook.used) {
+            // second part: the runs reported after the first part's snapshot, restricted to its records (a dense re-evaluation
+            // after a candidate overflow reports the first part's records again)
+            std::vector<kgma_run> rb;
+            for (size_t i = hook.n_runs_first; i < res->runs.size(); i++) if (res->runs[i].record >= hook.rec_split) rb.push_back(res->runs[i]);
+            merge_runs(rb);
+            std::vector<kgma_hit> hitsB;
+            rc = replay_single_range(ctx, g, pl.tabs[0], P, rb, res->first_D, hook.rec_split, nr, &genome_pos, hitsB, reqsB, pendB);
+            if (rc == KGMA_OK) rc = align_enqueue(ctx, g, reqsB, profiles, 1, true, P.gap_open, P.gap_extend, (P.flags & KGMA_F_TIE_OPEN) != 0, ctx->s_align, 1, &tB);
+            std::vector<AlignRes> aA, aB;
+            if (rc == KGMA_OK) rc = align_collect(ctx, &tA, aA);
+            if (rc == KGMA_OK) rc = align_collect(ctx, &tB, aB);
+            if (rc == KGMA_OK) {
+                apply_extensions(g, hitsA, pendA, aA);
+                apply_extensions(g, hitsB, pendB, aB);
+                res->hits = hitsA; res->hits.insert(res->hits.end(), hitsB.begin(), hitsB.end());
+                res->runs = runsA; res->runs.insert(res->runs.end(), rb.begin(), rb.end());
+                ctx->stats.n_align = (int64_t)(reqsA.size() + reqsB.size());
+                ctx->stats.n_runs = (int64_t)res->runs.size();
+            } else reset();
+        } else rc = replay(ctx, g, pl.tabs, profiles, P, res->runs, res->first_D, res);
         const double dt = now_ms() - t0;
-        ctx->stats.host_replay_ms = dt - ctx->stats.align_ms;
+        ctx->stats.host_replay_ms = dt - (ctx->stats.align_ms - align_before);
         ctx->stats.wall_ms += dt;
-    }
+    } else reset();
     if (rc) { delete res; return rc; }
     *out = res;
     return KGMA_OK;

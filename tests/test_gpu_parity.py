@@ -840,3 +840,44 @@ def test_error_paths(K, prof):
     out = K.scan_raw(g, [RV], [ws], [cons], [30.0], 6, L.MODE_SINGLE, 50, 0, -69, -1)
     assert len(out.hits) == 0
     assert "kgma" in str(K.KmerGMAError(L.E_ARG, "x"))
+
+
+def test_pipelined_streaming_equals_plain(K, prof, synth, monkeypatch):
+    """the streamed single-profile scan replays and extends the leading records while the tail is still being copied
+    (kgma_scan); switching that off must not change a single hit"""
+    path, recs = synth
+    RV, ws, cons = prof
+    key = ["record", "first", "last", "D", "genome_pos", "align_score", "cmi"]
+    for gpath in (path, GENOME):
+        g = K.Genome.from_fasta(gpath)
+        a = K.scan_raw(g, [RV], [ws], [cons], [30.0], 6, K.L.MODE_SINGLE, 50, K.L.F_ALIGN, -69, -1)
+        monkeypatch.setenv("KGMA_NO_PIPELINE", "1")
+        b = K.scan_raw(g, [RV], [ws], [cons], [30.0], 6, K.L.MODE_SINGLE, 50, K.L.F_ALIGN, -69, -1)
+        monkeypatch.delenv("KGMA_NO_PIPELINE")
+        assert len(a.hits) >= 5 and np.array_equal(a.hits[key], b.hits[key])
+        ra, rb = a.runs.view(RUN_DT), b.runs.view(RUN_DT)
+        assert np.array_equal(np.sort(ra, order=["record", "t_first", "flags"]), np.sort(rb, order=["record", "t_first", "flags"]))
+
+
+def test_pipelined_scan_with_overflow_in_second_part(K, O, prof, tmp_path):
+    """first part normal, second part wall-to-wall homologues: its candidate list overflows after the first part has
+    already been replayed; the dense re-evaluation must not duplicate the first part's hits"""
+    RV, ws, cons = prof
+    refs = O.Fasta(TF)
+    rng = np.random.default_rng(12)
+    alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
+    r0 = alphabet[rng.integers(0, 4, size=6_000_000)].copy()
+    for i in range(40):
+        m = np.frombuffer(refs.seq(int(rng.integers(0, len(refs)))).encode(), dtype=np.uint8)
+        p = int(rng.integers(0, r0.size - 400))
+        r0[p:p + m.size] = m
+    wall = "".join(refs.seq(int(rng.integers(0, len(refs)))) for _ in range(18500))
+    path = tmp_path / "two.fasta"
+    with open(path, "wb") as fh:
+        fh.write(b">first random with plants\n" + r0.tobytes() + b"\n>second wall\n" + wall.encode() + b"\n")
+    g = K.Genome.from_fasta(str(path))
+    out = K.scan_raw(g, [RV], [ws], [cons], [30.0], 6, K.L.MODE_SINGLE, 50, K.L.F_ALIGN, -69, -1)
+    st = K.default_context().stats()
+    assert st["blocks_flagged"] > 65536
+    oh = assert_parity(K, O, out, lambda: O.ac_gma_testing(str(path), np.asarray(RV), cons, windowsize=ws, thr=30, buff=50, do_align=True)[0], RV.n_refs)
+    assert sum(1 for h in oh if h.record == 0) >= 30 and sum(1 for h in oh if h.record == 1) >= 50
