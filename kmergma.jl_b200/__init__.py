@@ -9,6 +9,7 @@ All scanning, extension and matching work happens in the CUDA library; there is 
 from __future__ import annotations
 
 import ctypes as C
+import logging
 import os
 import warnings
 from dataclasses import dataclass
@@ -25,6 +26,9 @@ __all__ = [
     "findGenes", "findGenes_cluster_mode", "exactMatch", "write_results", "align_unitrange",
     "julia_round2", "julia_float_str", "kmer_count", "kmer_dist", "as_UInt", "as_kmer",
 ]
+
+
+_log = logging.getLogger("KmerGMA")        # the reference's @info lines (verbose = true) go here
 
 
 class KmerGMAError(RuntimeError):
@@ -622,6 +626,8 @@ def findGenes(*, genome_path, ref_path, k: int = 6, KmerDistThr: Union[int, floa
               do_return_dists: bool = False, do_return_hit_loci: bool = False, do_return_align: bool = False,
               verbose: bool = True, KmerDist_threshold_buffer: float = 8.0, ctx: Optional[Context] = None) -> list:
     """KmerGMA.findGenes (src/API.jl:60-104).  Returns [hit_vector, (hit_loci), (alignments), (dists)]."""
+    if verbose:
+        _log.info("pre-processing references and parameters...")
     warn_helper(k, do_return_dists)
     RV, windowsize, consensus_refseq = gen_ref_ws_cons(ref_path, k)
     if k >= windowsize:
@@ -632,19 +638,24 @@ def findGenes(*, genome_path, ref_path, k: int = 6, KmerDistThr: Union[int, floa
     elif KmerDistThr < est:     # (sic) src/API.jl:75-77
         warnings.warn(f"The kmer distance threshold {_jl_num(KmerDistThr)} for k = {k} is likely too high, and can result in many false positives")
     hit_vector, dist_vec, hit_loci_vec, alignment_vec = [], [], [], []
+    if verbose:
+        _log.info("initializing iteration...")
     ac_gma_testing(genome_path=genome_path, refVec=RV, consensus_refseq=consensus_refseq, k=k,
                    windowsize=windowsize, thr=KmerDistThr, buff=buffer, do_align=do_align,
                    gap_open_score=gap_open_score, gap_extend_score=gap_extend_score,
                    do_return_dists=do_return_dists, do_return_align=do_return_align,
                    get_hit_loci=do_return_hit_loci, dist_vec=dist_vec, result_align_vec=alignment_vec,
                    hit_loci_vec=hit_loci_vec, resultVec=hit_vector, ctx=ctx)
+    info_str = "genome mining completed successfully, returning vector of: vector of hits"
     output_vector: list = [hit_vector]
     if do_return_hit_loci:
-        output_vector.append(hit_loci_vec)
+        output_vector.append(hit_loci_vec); info_str += ", vector of hit locations"
     if do_return_align:
-        output_vector.append(alignment_vec)
+        output_vector.append(alignment_vec); info_str += ", vector of alignments"
     if do_return_dists:
-        output_vector.append(dist_vec)
+        output_vector.append(dist_vec); info_str += ", vector of kmer distances along the genome"
+    if verbose:
+        _log.info(info_str)
     return output_vector
 
 
@@ -655,6 +666,8 @@ def findGenes_cluster_mode(*, genome_path, ref_path, cluster_cutoffs=(7, 12, 20,
                            do_return_align: bool = False, verbose: bool = True,
                            kmerDist_threshold_buffer: float = 7, ctx: Optional[Context] = None) -> list:
     """KmerGMA.findGenes_cluster_mode (src/API.jl:161-226)."""
+    if verbose:
+        _log.info("pre-processing references and parameters...")
     warn_helper(k, do_return_dists)
     RVs, windowsizes, consensus_refseqs, invalids = cluster_ref_API(ref_path, k, cutoffs=cluster_cutoffs)
     RVs, windowsizes, consensus_refseqs = eliminate_null_params(RVs, windowsizes, consensus_refseqs, invalids)
@@ -676,18 +689,24 @@ def findGenes_cluster_mode(*, genome_path, ref_path, cluster_cutoffs=(7, 12, 20,
                           f" for k = {k} is potentially too high, and may result in more false positives.")
     hit_vector, hit_loci_vec, alignment_vec = [], [], []
     dist_vec_vec = [[] for _ in windowsizes]
+    if verbose:
+        _log.info("initializing iteration...")
     Omn_KmerGMA(genome_path=genome_path, refVecs=RVs, windowsizes=windowsizes, consensus_seqs=consensus_refseqs,
                 resultVec=hit_vector, k=k, thr_vec=KmerDistThrs, buff=buffer, align_hits=do_align,
                 gap_open_score=gap_open_score, gap_extend_score=gap_extend_score, get_aligns=do_return_align,
                 get_hit_loci=do_return_hit_loci, hit_loci_vec=hit_loci_vec, align_vec=alignment_vec,
                 do_return_dists=do_return_dists, dist_vec_vec=dist_vec_vec, ctx=ctx)
+    info_str = "genome mining completed successfully, returning vector of: vector of hits"
     output_vector: list = [hit_vector]
     if do_return_hit_loci:
-        output_vector.append(hit_loci_vec)
+        output_vector.append(hit_loci_vec); info_str += ", vector of hit locations"
     if do_return_align:
-        output_vector.append(alignment_vec)
+        output_vector.append(alignment_vec); info_str += ", vector of alignments"
     if do_return_dists:
-        output_vector.append(dist_vec_vec)
+        output_vector.append(dist_vec_vec); info_str += ", vector of vectors of kmer distances along the genome"
+    if verbose:
+        _log.info(info_str)
+        _log.info("To write the results, use `KmerGMA.write_results`")
     return output_vector
 
 
