@@ -193,11 +193,12 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
     const uint32_t kmask = (uint32_t)nb - 1;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     int32_t *sS = reinterpret_cast<int32_t *>(smem_raw);
-    const size_t per_warp = (size_t)nb * 2 + 64 * 2 * 2 + 64 * 8;
+    const size_t per_warp = (size_t)nb * 2 + 64 * 4 + 64 * 4 + 64 * 8;
     unsigned char *wb = smem_raw + (size_t)nb * 4 + (size_t)wid * per_warp;
     uint2 *qa = reinterpret_cast<uint2 *>(wb);                                // [64] (Q, A) of the current 64 windows
     uint16_t *tab = reinterpret_cast<uint16_t *>(wb + 64 * 8);                // [4^k] counts
-    uint32_t *lr = reinterpret_cast<uint32_t *>(tab + nb);                    // [64] leaving | entering << 16 k-mers of 64 steps
+    uint32_t *lr = reinterpret_cast<uint32_t *>(tab + nb);                    // [64] byte offsets 2*leaving | 2*entering << 16 of 64 steps
+    int32_t *dS = reinterpret_cast<int32_t *>(lr + 64);                       // [64] S[entering] - S[leaving] of those steps
     for (int i = lane; i < nb / 2; i += 32) reinterpret_cast<uint32_t *>(tab)[i] = 0;
     if (nb < 2 && lane == 0) tab[0] = 0;
 
@@ -270,24 +271,30 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
             bool c_in = false; long long c_tf = 0, c_ta = 0, c_dmin = 0; uint32_t c_fl = 0;   // run carried across 64-window batches
             for (long long s0 = 0; s0 < n; s0 += 64) {
                 const int m = (int)(n - s0 < 64 ? n - s0 : 64);
-                for (int j = lane; j < m; j += 32)                            // step j: window s0+j -> s0+j+1
-                    lr[j] = kmer_at(a.seq, gpos + s0 + j, kmask) | (kmer_at(a.seq, gpos + s0 + j + nk, kmask) << 16);
+                for (int j = lane; j < 64; j += 32) {                         // step j: window s0+j -> s0+j+1
+                    // everything that does not depend on the counts is prepared by all lanes: the table byte offsets of the
+                    // leaving / entering k-mer and the change of A; steps past the span's last slide are made no-ops (l == r)
+                    const bool slides = j < m && s0 + j + 1 < n;
+                    const uint32_t l = slides ? kmer_at(a.seq, gpos + s0 + j, kmask) : 0u;
+                    const uint32_t r2 = slides ? kmer_at(a.seq, gpos + s0 + j + nk, kmask) : 0u;
+                    lr[j] = (2u * l) | ((2u * r2) << 16);
+                    dS[j] = sS[r2] - sS[l];
+                }
                 __syncwarp();
                 if (lane == 0) {
-                    // the serial part: one warp instruction stream, so every instruction counts (one packed k-mer load,
-                    // one 64-bit store per step; the last slide of the span is cut off by the loop bound, not per step)
-                    const int msl = (int)((n - 1 - s0) < m ? (n - 1 - s0) : m);       // steps that do slide
-                    uint32_t cur = lr[0];
-                    for (int j = 0; j < m; j++) {
+                    // the serial part: a single instruction stream, so every instruction counts
+                    const unsigned char *tb = reinterpret_cast<const unsigned char *>(tab);
+#pragma unroll 4
+                    for (int j = 0; j < 64; j++) {
                         qa[j] = make_uint2(Q, A);
-                        const uint32_t nxt = lr[(j + 1) & 63];                        // software-pipelined k-mer fetch
-                        const uint32_t l = cur & 0xFFFFu, rr = cur >> 16;
-                        if (l != rr && j < msl) {                             // GenomeMiner.jl:69 `if left_ind != right_ind`
-                            const uint32_t cl = tab[l], cr = tab[rr];
-                            Q += 2u * (cr - cl) + 2u; A += (uint32_t)(sS[rr] - sS[l]);
-                            tab[l] = (uint16_t)(cl - 1); tab[rr] = (uint16_t)(cr + 1);
+                        const uint32_t cur = lr[j];
+                        const uint32_t lo = cur & 0xFFFFu, ro = cur >> 16;
+                        if (lo != ro) {                                       // GenomeMiner.jl:69 `if left_ind != right_ind`
+                            uint16_t *pl = (uint16_t *)(tb + lo), *pr = (uint16_t *)(tb + ro);
+                            const uint32_t cl = *pl, cr = *pr;
+                            Q += 2u * (cr - cl) + 2u; A += (uint32_t)dS[j];
+                            *pl = (uint16_t)(cl - 1); *pr = (uint16_t)(cr + 1);
                         }
-                        cur = nxt;
                     }
                 }
                 __syncwarp();
@@ -600,7 +607,7 @@ static double now_ms()
 static int eval_shape(const kgma_ctx *ctx, int k, int *warps_out, size_t *smem_out)
 {
     const size_t nb = (size_t)1 << (2 * k);
-    const size_t per_warp = nb * 2 + 64 * 2 * 2 + 64 * 8;
+    const size_t per_warp = nb * 2 + 64 * 4 + 64 * 4 + 64 * 8;
     if (ctx->smem_optin < nb * 4 + per_warp) return KGMA_E_UNSUPPORTED;
     int w = (int)std::min<size_t>((ctx->smem_optin - nb * 4) / per_warp, 16);
     *warps_out = w; *smem_out = nb * 4 + (size_t)w * per_warp;
