@@ -1,0 +1,19 @@
+"""one-off extended fuzz: run tests/test_gpu_parity.py::test_fuzz_vs_oracle for many more seeds"""
+import sys, os, tempfile, pathlib, traceback
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import pytest
+import test_gpu_parity as T
+import kmergma_jl_b200 as K
+from oracle import oracle as O
+K.default_context()
+lo, hi = int(sys.argv[1]), int(sys.argv[2])
+bad = []
+for seed in range(lo, hi):
+    with tempfile.TemporaryDirectory() as td:
+        try:
+            T.test_fuzz_vs_oracle.__wrapped__(K, O, pathlib.Path(td), seed) if hasattr(T.test_fuzz_vs_oracle, "__wrapped__") else T.test_fuzz_vs_oracle(K, O, pathlib.Path(td), seed)
+        except pytest.skip.Exception:
+            pass
+        except Exception as e:
+            bad.append(seed); print("SEED", seed, "FAILED:", repr(e)[:300]); traceback.print_exc(limit=3)
+print("done", lo, hi, "failures:", bad)
