@@ -9,10 +9,12 @@
 // match > delete (consumes b) > insert (consumes a); on exact open/extend ties the gap is extended
 // unless KGMA_F_TIE_OPEN (BioAlignments' own tie rule is not pinned by any reference test).
 //
-// Mapping: a warp sweeps 32 rows of the DP matrix at a time, lane l owning row 32*rb+l+1, with the
-// classic one-column skew between neighbouring lanes so that the (i-1,j) / (i-1,j-1) operands arrive
-// by __shfl_up from the lane above.  The bottom row of each 32-row block is parked in shared memory
-// for the next block.  Trace bytes are packed four columns at a time into 32-bit global stores.
+// Two kernels.  kgma_align_summary<R> (the default): each lane owns R = 10 consecutive DP rows in registers, lanes are
+// skewed by one column (operands of the row above arrive by __shfl_up), so one sweep of n+31 steps covers 320
+// consensus rows; instead of a trace matrix a packed summary of the canonical optimal path is carried with the
+// scores, from which cigar_to_UnitRange's two numbers follow; the subject is read from the packed genome on the
+// device.  kgma_align (only when CIGARs are requested): 32 rows per sweep, trace bytes packed four columns at a time
+// into 32-bit global stores, lane-0 traceback.
 #include "kgma_internal.h"
 #include <algorithm>
 

@@ -1,10 +1,13 @@
 // exactMatch on the packed genome: every start position whose qlen symbols equal the query.
 // Replaces exactMatch / FindAllOverlap / FindAll (src/ExactMatch.jl:89-121,33-43,20-30), i.e. repeated
 // BioSequences.findfirst(ExactSearchQuery(query), view(seq, start:end)) calls, with one streaming pass:
-// 2-bit codes are compared 16 bases (one 32-bit funnel-shifted word) at a time at every offset, survivors
-// are verified over the whole query including the ambiguity plane (N equals only N), and match starts are
-// appended with warp ballot/popc compaction.  Overlap / non-overlap selection is a host pass over the sorted
-// starts (FindAll resumes at match_end+1, FindAllOverlap at match_start+1).
+//   * queries of >= 31 nt: kgma_exact_match_sampled - one hash probe per sampled aligned 16-base word (every
+//     128 bases for queries >= 143 nt), survivors verified over the whole query on the 2-bit plane and against the
+//     list of masked (N) runs; HBM-bound (one 4-byte load per 32-byte sector);
+//   * shorter queries: kgma_exact_match_kernel - every offset, a zero-byte SIMD test of the first 4 bases (4
+//     offsets per word operation), survivors verified on both planes (N equals only N), ballot/popc compaction.
+// Overlap / non-overlap selection is a host pass over the sorted starts (FindAll resumes at match_end+1,
+// FindAllOverlap at match_start+1).  The 2-bit plane is streamed in chunks with the search chasing the copy.
 #include "kgma_internal.h"
 #include <algorithm>
 
