@@ -141,7 +141,7 @@ struct RecDev {
     long long dist_base;    // do_return_dists: index of step 1 of this record in the D output
 };
 
-struct ProfDev { long long N2, twoN, sumS2, T, Tlo, Thi; int nk, pad; };
+struct ProfDev { long long N2, twoN, sumS2, T, Tlo, Thi, R; int nk, pad; };   // R = N^2 nk + sum S^2 - Thi (<= 0: cannot be bounded)
 
 struct EvalArgs {
     const uint32_t *seq;
@@ -254,6 +254,31 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
             const long long gpos = a.recs[r].off + w0;
             const long long dist_base = a.recs[r].dist_base;
 
+            // ---- candidate spans are flagged per 64-base block with the group's maximum weights over a 384-base cover; check this
+            //      profile's own bound exactly before paying for the serial slide: a window can only be below thr if
+            //      2N * A_w > R (D_w >= N^2 nk - 2N A_w + sum S^2), and A_w of all n windows costs one pass of lookups
+            if (a.cand && P.R > 0 && !(w0 == 0 && n == 1)) {
+                uint32_t A0 = 0;
+                for (int p = lane; p < nk; p += 32) A0 += (uint32_t)sS[kmer_at(a.seq, gpos + p, kmask)];
+#pragma unroll
+                for (int d = 16; d; d >>= 1) A0 += __shfl_xor_sync(FULL, A0, d);
+                long long Aw = A0, Amax = A0;                                  // A of window 0; then 32 windows per round
+                for (long long wb0 = 0; wb0 + 1 < n; wb0 += 32) {
+                    const long long w = wb0 + lane;                            // step w: window w -> w+1
+                    int dlt = 0;
+                    if (w + 1 < n) dlt = sS[kmer_at(a.seq, gpos + w + nk, kmask)] - sS[kmer_at(a.seq, gpos + w, kmask)];
+                    int pre = dlt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, pre, d); if (lane >= d) pre += t; }
+                    long long mine = Aw + pre;                                 // A of window w+1
+                    if (w + 1 >= n) mine = 0;
+#pragma unroll
+                    for (int d = 16; d; d >>= 1) { const long long o = __shfl_xor_sync(FULL, mine, d); mine = o > mine ? o : mine; }
+                    Amax = mine > Amax ? mine : Amax;
+                    Aw += __shfl_sync(FULL, pre, 31);
+                }
+                if (P.twoN * Amax <= P.R) continue;                            // no window of this span can reach thr for this profile
+            }
             // ---- first window of the span: build the table, Q = sum_p c[kmer_p], A = sum_p S[kmer_p]
             for (int p = lane; p < nk; p += 32) {
                 const uint32_t km = kmer_at(a.seq, gpos + p, kmask);
@@ -833,6 +858,10 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
         const ProfTab &t = pl.tabs[q];
         ea.prof[q].N2 = t.N2; ea.prof[q].twoN = t.twoN; ea.prof[q].sumS2 = t.sumS2;
         ea.prof[q].T = t.T; ea.prof[q].Tlo = t.Tlo; ea.prof[q].Thi = t.Thi; ea.prof[q].nk = (int)t.nk; ea.prof[q].pad = 0;
+        {
+            const __int128 R = (__int128)t.N2 * t.nk + t.sumS2 - t.Thi;
+            ea.prof[q].R = R > 0 && R < ((__int128)1 << 62) ? (long long)R : 0;
+        }
     }
     ea.runs = (kgma_run *)(ds + o_runs); ea.run_cap = run_cap; ea.run_count = d_counters;
     ea.first_D = (long long *)(ds + o_first);
