@@ -174,7 +174,6 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
     };
 
     std::vector<AlignReq> reqs; std::vector<AlignRes> ares;
-    std::vector<int64_t> req_of_run;                      // cluster mode: run index -> request index
     std::vector<Pending> pend;                            // single mode: hits waiting for their extension
 
     if (!cluster) {
@@ -194,88 +193,109 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
     }
 
     // ---------------- Omn_KmerGMA! ----------------
-    // extension results feed back into prev_hit_range (:139,:152), so every terminated run's candidate is extended up front
-    req_of_run.assign(runs.size(), -1);
-    if (do_align) {
-        for (size_t i = 0; i < runs.size(); i++) {
-            const kgma_run &ru = runs[i];
-            if (ru.flags & KGMA_RUN_MARKER) continue;
-            const int64_t L = g->recs[ru.record].len, steps = steps_of(ru.record);
-            if (ru.t_last >= steps) continue;
-            const int64_t CMI = ru.t_argmin, wsq = tabs[ru.profile].ws;
-            int64_t a = std::max<int64_t>(CMI - buff, 1), b = std::min<int64_t>(CMI + wsq - 1 + buff, L);
-            req_of_run[i] = (int64_t)reqs.size();
-            reqs.push_back({ ru.record, ru.profile, a, b });
-        }
-        if (!reqs.empty()) {
-            int rc = align_batch_device(ctx, g, reqs, profiles, C, false, P.gap_open, P.gap_extend,
-                                        (P.flags & KGMA_F_TIE_OPEN) != 0, want_cig, ares,
-                                        want_cig ? &res->cigar_ops : nullptr, want_cig ? &res->cigar_cnt : nullptr);
-            if (rc) return rc;
-        }
-    }
-    if (ctx) ctx->stats.n_align = (int64_t)reqs.size();
-    int64_t genome_pos = 0;
+    // Extension results feed back into the state machine (prev_hit_range, :139,:152), and only a fraction of the terminated
+    // runs is ever extended by the reference (most are suppressed by `CMI in prev_hit_range`).  Extending every terminated
+    // run up front costs several times the necessary work, so the replay runs in rounds: a pass over the events uses the
+    // extension results it has and SPECULATES (unextended range) where one is missing, collecting exactly those requests;
+    // they are extended in one batch and the pass is repeated.  A pass that needed no speculation is the reference's
+    // sequential result.  Everything before a record's first missing result is exact, so every round makes progress; after a
+    // few rounds the remaining terminated runs are simply all extended.
     struct Ev { int64_t end_step; int q; size_t run; };
-    std::vector<Ev> evs;
+    std::vector<Ev> evs;                                  // all records, in order
+    std::vector<size_t> ev_begin((size_t)nr + 1, 0);
     for (int r = 0; r < nr; r++) {
-        const int64_t L = g->recs[r].len, steps = steps_of(r);
-        if (steps > 0) {
-            // run-end events of all profiles ordered by (end step, profile index): the reference visits profiles in index order
-            // inside each loop step (:95).  Every profile's runs are already ordered, so this is a C-way merge.
-            evs.clear();
-            {
-                size_t head[MAX_PROFILES], tail[MAX_PROFILES];
-                for (int q = 0; q < C; q++) { Span sp = span[(size_t)q * nr + r]; head[q] = sp.b; tail[q] = sp.e; }
-                for (;;) {
-                    int best = -1; int64_t be = 0;
-                    for (int q = 0; q < C; q++) {
-                        while (head[q] < tail[q] && (runs[head[q]].flags & KGMA_RUN_MARKER)) head[q]++;
-                        if (head[q] >= tail[q]) continue;
-                        const int64_t e = runs[head[q]].t_last + 1;
-                        if (best < 0 || e < be) { best = q; be = e; }
+        ev_begin[(size_t)r] = evs.size();
+        if (steps_of(r) <= 0) continue;
+        // run-end events of all profiles ordered by (end step, profile index): the reference visits profiles in index order
+        // inside each loop step (:95).  Every profile's runs are already ordered, so this is a C-way merge.
+        size_t head[MAX_PROFILES], tail[MAX_PROFILES];
+        for (int q = 0; q < C; q++) { Span sp = span[(size_t)q * nr + r]; head[q] = sp.b; tail[q] = sp.e; }
+        for (;;) {
+            int best = -1; int64_t be = 0;
+            for (int q = 0; q < C; q++) {
+                while (head[q] < tail[q] && (runs[head[q]].flags & KGMA_RUN_MARKER)) head[q]++;
+                if (head[q] >= tail[q]) continue;
+                const int64_t e = runs[head[q]].t_last + 1;
+                if (best < 0 || e < be) { best = q; be = e; }
+            }
+            if (best < 0) break;
+            evs.push_back({ be, best, head[best] });
+            head[best]++;
+        }
+    }
+    ev_begin[(size_t)nr] = evs.size();
+
+    std::vector<char> have(runs.size(), 0);               // extension result of this run's candidate is known
+    std::vector<AlignRes> res_of_run(runs.size());
+    std::vector<size_t> missing;
+    int64_t n_align_total = 0;
+    for (int round = 0;; round++) {
+        res->hits.clear(); missing.clear();
+        int64_t genome_pos = 0;
+        std::vector<int64_t> cur(C), CMIs(C, 1); std::vector<char> stop(C, 1);
+        for (int r = 0; r < nr; r++) {
+            const int64_t L = g->recs[r].len, steps = steps_of(r);
+            if (steps > 0) {
+                for (int q = 0; q < C; q++) { cur[q] = first_D[(size_t)q * nr + r]; CMIs[q] = 1; stop[q] = 1; }   // :73 curr_mins = first-window distance
+                int64_t prev_a = 0, prev_b = 0;                                          // :59 prev_hit_range = 0:0
+                for (size_t ei = ev_begin[(size_t)r]; ei < ev_begin[(size_t)r + 1]; ei++) {
+                    const Ev &e = evs[ei];
+                    const kgma_run &ru = runs[e.run]; const int q = e.q;
+                    if (cur[q] == INT64_MIN) return set_err(ctx, KGMA_E_STATE, "first-window distance of record %d profile %d missing", r, q);
+                    if (ru.D_min < cur[q]) { cur[q] = ru.D_min; CMIs[q] = ru.t_argmin; stop[q] = 0; }   // :114-119 CMI = i
+                    if (ru.t_last >= steps) continue;                                   // open at the end of the loop
+                    if (stop[q]) continue;
+                    stop[q] = 1;                                                        // :122
+                    const int64_t CMI = CMIs[q];
+                    if (CMI >= prev_a && CMI <= prev_b) continue;                       // :126
+                    if (CMI != ru.t_argmin) return set_err(ctx, KGMA_E_STATE, "internal: extension request mismatch");
+                    const int64_t wsq = tabs[q].ws;
+                    const int64_t hl = std::max<int64_t>(CMI - buff, 1), hr = std::min<int64_t>(CMI + wsq - 1 + buff, L);
+                    int64_t a = hl, b = hr; int64_t score = 0; uint32_t co = 0, cl = 0;
+                    if (do_align) {
+                        if (have[e.run]) {
+                            const AlignRes &ar = res_of_run[e.run];
+                            remap(hl, L, ar, &a, &b);
+                            score = ar.score; co = ar.cig_off; cl = ar.cig_len;
+                        } else missing.push_back(e.run);                               // speculate with the unextended range
                     }
-                    if (best < 0) break;
-                    evs.push_back({ be, best, head[best] });
-                    head[best]++;
+                    if (b < prev_a || a > prev_b) {                                     // :139
+                        kgma_hit h{};
+                        h.record = r; h.profile = q + 1; h.cmi = CMI; h.first = a; h.last = b; h.genome_pos = genome_pos;
+                        h.D = cur[q]; h.dist = (double)cur[q] / tabs[q].denom;
+                        h.flags = (ru.flags & (KGMA_HIT_NEAR_THR | KGMA_HIT_ARGMIN_TIE)) | round_half_flag(h.dist);
+                        h.align_score = score; h.cigar_off = co; h.cigar_len = cl;
+                        res->hits.push_back(h);
+                        prev_a = a; prev_b = b;                                         // :152
+                        cur[q] = INT64_MAX;                                             // :153 curr_mins[ind] = kmerDist
+                    }
                 }
             }
-            std::vector<int64_t> cur(C), CMIs(C, 1); std::vector<char> stop(C, 1);
-            for (int q = 0; q < C; q++) cur[q] = first_D[(size_t)q * nr + r];     // :73 curr_mins = first-window distance
-            int64_t prev_a = 0, prev_b = 0;                                          // :59 prev_hit_range = 0:0
-            for (const Ev &e : evs) {
-                const kgma_run &ru = runs[e.run]; const int q = e.q;
-                if (cur[q] == INT64_MIN) return set_err(ctx, KGMA_E_STATE, "first-window distance of record %d profile %d missing", r, q);
-                if (ru.D_min < cur[q]) { cur[q] = ru.D_min; CMIs[q] = ru.t_argmin; stop[q] = 0; }   // :114-119 CMI = i
-                if (ru.t_last >= steps) continue;                                   // open at the end of the loop
-                if (stop[q]) continue;
-                stop[q] = 1;                                                        // :122
-                const int64_t CMI = CMIs[q];
-                if (CMI >= prev_a && CMI <= prev_b) continue;                       // :126
-                const int64_t wsq = tabs[q].ws;
-                int64_t hl = std::max<int64_t>(CMI - buff, 1), hr = std::min<int64_t>(CMI + wsq - 1 + buff, L);
-                int64_t a = hl, b = hr; int64_t score = 0; uint32_t co = 0, cl = 0;
-                if (do_align) {
-                    int64_t ri = req_of_run[e.run];
-                    if (ri < 0 || reqs[(size_t)ri].first != hl || reqs[(size_t)ri].last != hr)
-                        return set_err(ctx, KGMA_E_STATE, "internal: extension request mismatch");
-                    remap(hl, L, ares[(size_t)ri], &a, &b);
-                    score = ares[(size_t)ri].score; co = ares[(size_t)ri].cig_off; cl = ares[(size_t)ri].cig_len;
-                }
-                if (b < prev_a || a > prev_b) {                                     // :139
-                    kgma_hit h{};
-                    h.record = r; h.profile = q + 1; h.cmi = CMI; h.first = a; h.last = b; h.genome_pos = genome_pos;
-                    h.D = cur[q]; h.dist = (double)cur[q] / tabs[q].denom;
-                    h.flags = (ru.flags & (KGMA_HIT_NEAR_THR | KGMA_HIT_ARGMIN_TIE)) | round_half_flag(h.dist);
-                    h.align_score = score; h.cigar_off = co; h.cigar_len = cl;
-                    res->hits.push_back(h);
-                    prev_a = a; prev_b = b;                                         // :152
-                    cur[q] = INT64_MAX;                                             // :153 curr_mins[ind] = kmerDist
-                }
+            genome_pos += L;                                                            // :159 - every record
+        }
+        if (missing.empty()) break;                       // no speculation: this pass is the reference's result
+        if (round >= 3) {                                 // stop chasing: extend every terminated run that is still unknown
+            missing.clear();
+            for (size_t i = 0; i < runs.size(); i++) {
+                const kgma_run &ru = runs[i];
+                if ((ru.flags & KGMA_RUN_MARKER) || have[i] || ru.t_last >= steps_of(ru.record)) continue;
+                missing.push_back(i);
             }
         }
-        genome_pos += L;                                                            // :159 — every record
+        reqs.clear();
+        for (size_t i : missing) {
+            const kgma_run &ru = runs[i];
+            const int64_t L = g->recs[ru.record].len, CMI = ru.t_argmin, wsq = tabs[ru.profile].ws;
+            reqs.push_back({ ru.record, ru.profile, std::max<int64_t>(CMI - buff, 1), std::min<int64_t>(CMI + wsq - 1 + buff, L) });
+        }
+        int rc = align_batch_device(ctx, g, reqs, profiles, C, false, P.gap_open, P.gap_extend,
+                                    (P.flags & KGMA_F_TIE_OPEN) != 0, want_cig, ares,
+                                    want_cig ? &res->cigar_ops : nullptr, want_cig ? &res->cigar_cnt : nullptr);
+        if (rc) return rc;
+        for (size_t j = 0; j < missing.size(); j++) { res_of_run[missing[j]] = ares[j]; have[missing[j]] = 1; }
+        n_align_total += (int64_t)reqs.size();
     }
+    if (ctx) ctx->stats.n_align = n_align_total;
     return KGMA_OK;
 }
 
