@@ -229,13 +229,18 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
     std::vector<AlignRes> res_of_run(runs.size());
     std::vector<size_t> missing;
     int64_t n_align_total = 0;
+    std::vector<std::vector<kgma_hit>> rec_hits((size_t)nr);   // per record: a record whose pass needed no speculation is final
+    std::vector<char> rec_done((size_t)nr, 0);
     for (int round = 0;; round++) {
-        res->hits.clear(); missing.clear();
+        missing.clear();
         int64_t genome_pos = 0;
         std::vector<int64_t> cur(C), CMIs(C, 1); std::vector<char> stop(C, 1);
         for (int r = 0; r < nr; r++) {
             const int64_t L = g->recs[r].len, steps = steps_of(r);
-            if (steps > 0) {
+            if (steps > 0 && !rec_done[(size_t)r]) {
+                const size_t missing_before = missing.size();
+                std::vector<kgma_hit> &hits_r = rec_hits[(size_t)r];
+                hits_r.clear();
                 for (int q = 0; q < C; q++) { cur[q] = first_D[(size_t)q * nr + r]; CMIs[q] = 1; stop[q] = 1; }   // :73 curr_mins = first-window distance
                 int64_t prev_a = 0, prev_b = 0;                                          // :59 prev_hit_range = 0:0
                 for (size_t ei = ev_begin[(size_t)r]; ei < ev_begin[(size_t)r + 1]; ei++) {
@@ -265,11 +270,12 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
                         h.D = cur[q]; h.dist = (double)cur[q] / tabs[q].denom;
                         h.flags = (ru.flags & (KGMA_HIT_NEAR_THR | KGMA_HIT_ARGMIN_TIE)) | round_half_flag(h.dist);
                         h.align_score = score; h.cigar_off = co; h.cigar_len = cl;
-                        res->hits.push_back(h);
+                        hits_r.push_back(h);
                         prev_a = a; prev_b = b;                                         // :152
                         cur[q] = INT64_MAX;                                             // :153 curr_mins[ind] = kmerDist
                     }
                 }
+                if (missing.size() == missing_before) rec_done[(size_t)r] = 1;
             }
             genome_pos += L;                                                            // :159 - every record
         }
@@ -295,6 +301,8 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
         for (size_t j = 0; j < missing.size(); j++) { res_of_run[missing[j]] = ares[j]; have[missing[j]] = 1; }
         n_align_total += (int64_t)reqs.size();
     }
+    res->hits.clear();
+    for (int r = 0; r < nr; r++) res->hits.insert(res->hits.end(), rec_hits[(size_t)r].begin(), rec_hits[(size_t)r].end());
     if (ctx) ctx->stats.n_align = n_align_total;
     return KGMA_OK;
 }
