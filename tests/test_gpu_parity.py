@@ -6,6 +6,7 @@ Bar: hit coordinates / record names / exact-match positions bit-exact; distances
 (the device computes the exact rational D/(2kN^2), the oracle the reference's Float64 accumulator).
 """
 import ctypes as C
+import os
 import warnings
 
 import numpy as np
@@ -881,3 +882,21 @@ def test_pipelined_scan_with_overflow_in_second_part(K, O, prof, tmp_path):
     assert st["blocks_flagged"] > 65536
     oh = assert_parity(K, O, out, lambda: O.ac_gma_testing(str(path), np.asarray(RV), cons, windowsize=ws, thr=30, buff=50, do_align=True)[0], RV.n_refs)
     assert sum(1 for h in oh if h.record == 0) >= 30 and sum(1 for h in oh if h.record == 1) >= 50
+
+
+def test_plain_c_client(tmp_path):
+    """examples/findgenes.c: the C ABI used from plain C (gcc, no Python in the call path) reproduces the reference's golden
+    hits on Alp_V_locus (test-KmerGMA.jl:257-263: 6852:7140, 23907:24201, 33845:34133)"""
+    import subprocess
+    from conftest import ROOT
+    exe = tmp_path / "findgenes"
+    libdir = os.path.join(ROOT, "kmergma.jl_b200")
+    subprocess.check_call(["gcc", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "findgenes.c"), "-o", str(exe),
+                           "-L" + libdir, "-lkmergma_cuda", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([str(exe), MINI_GENOME, TF, "6", "30", "50"], text=True).strip().splitlines()
+    assert len(out) == 3
+    assert [l.split(" | ")[2] for l in out] == ["MatchPos = 6852:7140", "MatchPos = 23907:24201", "MatchPos = 33845:34133"]
+    assert all(l.startswith("AM773548.1 | D = ") and "GenomePos = 0" in l for l in out)
+    D = [int(l.split(" | ")[1].split(" = ")[1].split("/")[0]) for l in out]
+    den = 2 * 6 * 84 * 84
+    assert [round(d / den, 2) for d in D] == [8.1, 24.87, 10.99]
