@@ -11,6 +11,10 @@
 #include <sys/stat.h>
 #include <fcntl.h>
 #include <unistd.h>
+#include <chrono>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace kgma {
 
@@ -46,6 +50,13 @@ int genome_reserve(kgma_genome *g, int64_t bases)
     int64_t nc = std::max<int64_t>(bases, g->cap_bases + g->cap_bases / 2);
     nc = (nc + 4095) / 4096 * 4096;
     if (g->pinned || g->host_alloc) return KGMA_E_STATE;
+    if (!g->seq2 && !g->mask) {                            // first allocation: calloc hands out lazily zeroed pages, so a bulk
+        g->seq2 = (uint32_t *)calloc((size_t)nc / 4, 1);   // ingest faults them in from its packing threads instead of one memset
+        g->mask = (uint32_t *)calloc((size_t)nc / 8, 1);
+        if (!g->seq2 || !g->mask) { free(g->seq2); free(g->mask); g->seq2 = g->mask = nullptr; return KGMA_E_CAPACITY; }
+        g->cap_bases = nc;
+        return KGMA_OK;
+    }
     uint32_t *s = (uint32_t *)realloc(g->seq2, (size_t)nc / 4);
     if (!s) return KGMA_E_CAPACITY;
     g->seq2 = s;
@@ -276,9 +287,19 @@ static inline bool is_ws(unsigned char c) { return c == '\n' || c == '\r' || c =
 
 static void count_task(FastaTask &t)
 {
-    int64_t n = 0;
-    for (const char *p = t.b; p < t.e; ++p) n += !is_ws((unsigned char)*p);
-    t.nres = n;
+    int64_t ws = 0;
+    const char *p = t.b;
+#if defined(__SSE2__)
+    const __m128i c1 = _mm_set1_epi8('\n'), c2 = _mm_set1_epi8('\r'), c3 = _mm_set1_epi8(' '), c4 = _mm_set1_epi8('\t');
+    for (; p + 16 <= t.e; p += 16) {
+        const __m128i v = _mm_loadu_si128((const __m128i *)p);
+        const __m128i m = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(v, c1), _mm_cmpeq_epi8(v, c2)),
+                                       _mm_or_si128(_mm_cmpeq_epi8(v, c3), _mm_cmpeq_epi8(v, c4)));
+        ws += __builtin_popcount((unsigned)_mm_movemask_epi8(m));
+    }
+#endif
+    for (; p < t.e; ++p) ws += is_ws((unsigned char)*p);
+    t.nres = (int64_t)(t.e - t.b) - ws;
 }
 
 static void pack_task(kgma_genome *g, int64_t rec_off, FastaTask &t)
@@ -298,6 +319,27 @@ static void pack_task(kgma_genome *g, int64_t rec_off, FastaTask &t)
     };
     const int64_t first_w = gp >> 4, last_w = (gp_end - 1) >> 4, first_m = gp >> 5, last_m = (gp_end - 1) >> 5;
     for (const char *p = t.b; p < t.e; ++p) {
+        // fast path: 8 plain A/C/G/T residues at a time (no whitespace, N or IUPAC among them), appended as 16 bits
+        while (p + 8 <= t.e) {
+            const unsigned char *u = (const unsigned char *)p;
+            const uint8_t c0 = CT.t[u[0]], c1 = CT.t[u[1]], c2 = CT.t[u[2]], c3 = CT.t[u[3]],
+                          c4 = CT.t[u[4]], c5 = CT.t[u[5]], c6 = CT.t[u[6]], c7 = CT.t[u[7]];
+            if ((c0 | c1 | c2 | c3 | c4 | c5 | c6 | c7) & 0xFC) break;
+            const uint32_t bits = (uint32_t)c0 | ((uint32_t)c1 << 2) | ((uint32_t)c2 << 4) | ((uint32_t)c3 << 6) |
+                                  ((uint32_t)c4 << 8) | ((uint32_t)c5 << 10) | ((uint32_t)c6 << 12) | ((uint32_t)c7 << 14);
+            const int sh = 2 * (int)(gp & 15);
+            const uint64_t wide = (uint64_t)w | ((uint64_t)bits << sh);
+            const int64_t gp_new = gp + 8;
+            if ((gp_new >> 4) != (gp >> 4)) {                 // the word [gp>>4] is complete
+                const int64_t wd = gp >> 4;
+                w = (uint32_t)wide;
+                flush_seq(wd, wd == first_w || wd == last_w);
+                w = (uint32_t)(wide >> 32);
+            } else w = (uint32_t)wide;
+            if ((gp_new >> 5) != (gp >> 5)) { const int64_t wd = gp >> 5; flush_mask(wd, wd == first_m || wd == last_m); }
+            gp = gp_new; i += 8; p += 8;
+        }
+        if (p >= t.e) break;
         const unsigned char ch = (unsigned char)*p;
         if (is_ws(ch)) continue;
         uint8_t c = CT.t[ch];
@@ -339,6 +381,10 @@ int kgma_genome_from_fasta(const char *path, kgma_genome **out)
     if (sz) madvise((void *)buf, sz, MADV_SEQUENTIAL | MADV_WILLNEED);
     const int nthreads = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
     kgma_genome *g = nullptr; kgma_genome_create(&g);
+    const bool trace = getenv("KGMA_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
+    auto lap = [&](const char *what) { if (trace) { double t1 = now(); fprintf(stderr, "[kgma ingest] %-10s %8.2f ms\n", what, t1 - t0); t0 = t1; } };
 
     // ---- header lines: '>' at the start of a line (found in parallel over 8 MB slices)
     const size_t SL = (size_t)8 << 20, nsl = (sz + SL - 1) / SL;
@@ -355,6 +401,7 @@ int kgma_genome_from_fasta(const char *path, kgma_genome **out)
     });
     std::vector<size_t> hpos;
     for (auto &v : hdrs) hpos.insert(hpos.end(), v.begin(), v.end());
+    lap("headers");
 
     // ---- records and tasks
     const size_t TASK = (size_t)4 << 20;
@@ -379,6 +426,7 @@ int kgma_genome_from_fasta(const char *path, kgma_genome **out)
         spans[r].n_tasks = tasks.size() - spans[r].first_task;
     }
     parallel_for(tasks.size(), nthreads, [&](size_t i) { count_task(tasks[i]); });
+    lap("count");
 
     // ---- layout: record lengths, offsets, one reservation
     int rc = KGMA_OK;
@@ -389,8 +437,10 @@ int kgma_genome_from_fasta(const char *path, kgma_genome **out)
         g->total_len += len;
     }
     if (!g->recs.empty()) rc = genome_reserve(g, g->recs.back().off + g->recs.back().len + REC_ALIGN + TAIL_PAD + FGROUP);
+    lap("reserve");
     if (rc == KGMA_OK) {
         parallel_for(tasks.size(), nthreads, [&](size_t i) { if (tasks[i].nres) pack_task(g, g->recs[(size_t)tasks[i].rec].off, tasks[i]); });
+        lap("pack");
         for (const FastaTask &t : tasks) {
             if (t.bad >= 0 && rc == KGMA_OK) { g->err = "record " + std::to_string(t.rec) + ": invalid character at position " + std::to_string(t.bad + 1); rc = KGMA_E_SYMBOL; }
             if (t.amb >= 0 && !g->ambiguous) { g->ambiguous = true; g->amb_record = t.rec; g->amb_pos = t.amb + 1; }
