@@ -217,7 +217,7 @@ extern "C" int kgma_exact_match(kgma_ctx *ctx, kgma_genome *g, const char *query
         q2[(size_t)(i >> 4)] |= (uint32_t)code << (2 * (i & 15));
         if (masked) qm[(size_t)(i >> 5)] |= 1u << (i & 31);
     }
-    int rc = dev_genome_prepare(ctx, g, true);
+    int rc = dev_genome_prepare(ctx, g, qlen < 31);     // the ambiguity plane is only needed on the device for short queries
     if (rc) return rc;
     rc = genome_pin(ctx, g);
     if (rc) return rc;

@@ -73,11 +73,10 @@ int genome_pin(kgma_ctx *ctx, kgma_genome *g)
 {
     if (g->pinned) return KGMA_OK;
     // page-lock in place so cudaMemcpyAsync is a true async DMA (north_star: pinned, double-buffered)
+    // (only the 2-bit plane: the ambiguity plane reaches the device as a list of masked runs, and as a plain pageable copy
+    // in the one case that needs it whole - exact match with a query shorter than 31 nt)
     cudaError_t e1 = cudaHostRegister(g->seq2, (size_t)g->cap_bases / 4, cudaHostRegisterDefault);
-    cudaError_t e2 = cudaHostRegister(g->mask, (size_t)g->cap_bases / 8, cudaHostRegisterDefault);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
-        if (e1 == cudaSuccess) cudaHostUnregister(g->seq2);
-        if (e2 == cudaSuccess) cudaHostUnregister(g->mask);
+    if (e1 != cudaSuccess) {
         cudaGetLastError();
         return set_err(ctx, KGMA_E_CUDA, "cudaHostRegister of the packed genome failed");
     }
@@ -196,7 +195,7 @@ void kgma_genome_destroy(kgma_genome *g)
     if (!g) return;
     if (g->host_alloc) { cudaFreeHost(g->seq2); cudaFreeHost(g->mask); }
     else {
-        if (g->pinned) { cudaHostUnregister(g->seq2); cudaHostUnregister(g->mask); }
+        if (g->pinned) cudaHostUnregister(g->seq2);
         free(g->seq2); free(g->mask);
     }
     delete g;

@@ -523,12 +523,12 @@ int dev_genome_prepare(kgma_ctx *ctx, kgma_genome *g, bool need_mask)
         if (ctx->d_mask) cudaFree(ctx->d_mask);
         ctx->d_seq2 = ctx->d_mask = nullptr; ctx->d_cap_bases = 0; ctx->dg_uid = 0;
         KGMA_CUDA(ctx, cudaMalloc(&ctx->d_seq2, (size_t)need / 4));
-        KGMA_CUDA(ctx, cudaMalloc(&ctx->d_mask, (size_t)need / 8));
+        if (need_mask) KGMA_CUDA(ctx, cudaMalloc(&ctx->d_mask, (size_t)need / 8));
         ctx->d_cap_bases = need; ctx->dg_uid = g->uid;
         ctx->d_seq_valid = ctx->d_mask_valid = false; ctx->d_valid_lo = ctx->d_valid_hi = 0;
         ctx->d_have_lo = ctx->d_have_hi = 0;
     }
-    (void)need_mask;
+    if (need_mask && !ctx->d_mask) { KGMA_CUDA(ctx, cudaMalloc(&ctx->d_mask, (size_t)ctx->d_cap_bases / 8)); ctx->d_mask_valid = false; }
     return KGMA_OK;
 }
 
@@ -1177,15 +1177,14 @@ int kgma_genome_make_resident(kgma_ctx *ctx, kgma_genome *g)
     if (!ctx || !g) return KGMA_E_ARG;
     if (!g->sealed) return set_err(ctx, KGMA_E_STATE, "genome is not sealed");
     KGMA_CUDA(ctx, cudaSetDevice(ctx->device));
-    int rc = dev_genome_prepare(ctx, g, true);
+    int rc = dev_genome_prepare(ctx, g, false);
     if (rc) return rc;
     rc = genome_pin(ctx, g);
     if (rc) return rc;
     size_t bases = (size_t)(g->G + TAIL_PAD);
     KGMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_seq2, g->seq2, bases / 4, cudaMemcpyHostToDevice, ctx->s_compute));
-    KGMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_mask, g->mask, bases / 8, cudaMemcpyHostToDevice, ctx->s_compute));
     KGMA_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
-    ctx->d_seq_valid = ctx->d_mask_valid = true; ctx->d_valid_lo = 0; ctx->d_valid_hi = g->G + TAIL_PAD;
+    ctx->d_seq_valid = true; ctx->d_mask_valid = false; ctx->d_valid_lo = 0; ctx->d_valid_hi = g->G + TAIL_PAD;
     ctx->d_have_lo = 0; ctx->d_have_hi = g->G + TAIL_PAD;
     return KGMA_OK;
 }
@@ -1219,7 +1218,7 @@ int kgma_genome_synth(kgma_ctx *ctx, int n_records, const int64_t *rec_len, uint
     }
     g->host_alloc = true; g->pinned = true; g->cap_bases = cap; g->G = G;
     memset(g->mask, 0, (size_t)cap / 8);
-    int rc = dev_genome_prepare(ctx, g, true);
+    int rc = dev_genome_prepare(ctx, g, false);
     if (rc) { kgma_genome_destroy(g); return rc; }
     int64_t nwords = cap / 16;
     kgma_synth<<<ctx->num_sms * 8, 256, 0, ctx->s_compute>>>(ctx->d_seq2, nwords, seed);
