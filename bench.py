@@ -410,10 +410,12 @@ def run_ours(args):
             "host_ms_per_step": {"call_wall": a_res["wall_ms"], "setup": a_res["host_setup_ms"], "results": a_res["host_cand_ms"],
                                  "replay": a_res["host_replay_ms"], "e2e_call_wall": a_e2e["wall_ms"]},
             "roofline": {"bound": "hbm", "kernel": "kgma_prefilter<6>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": 784.9e6 if args.scale == 1.0 else None,
+                         "frac": achieved / peak, "traffic": 783.9e6 if args.scale == 1.0 else None,
                          "traffic_source": "ncu --set full, profiles/r1_prefilter_ncu_full_summary.csv (dram read+write per launch)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "algorithmic_bytes_per_launch": alg_bytes},
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "limiter": "shared-memory wavefronts, not HBM: ncu l1tex__throughput 95 %, 3.5 wavefronts per random 32-lane table "
+                                    "gather (22 gathers per 64 bases), gpu__dram_throughput 19 % (profiles/r1_prefilter_ncu_full_summary.csv, DESIGN.md 5.1)"},
             "clocks": clocks, "clocks_e2e": clocks_e2e,
             "hits_per_step": int(nhits_all), "runs_per_step": a_res["n_runs"], "hits_equal_resident_vs_e2e": bool(same),
             "prefilter_blocks_flagged_per_step": a_res["blocks_flagged"],
