@@ -25,6 +25,7 @@ __all__ = [
     "estimate_optimal_threshold", "ac_gma_testing", "Omn_KmerGMA", "record_KmerGMA",
     "findGenes", "findGenes_cluster_mode", "exactMatch", "write_results", "align_unitrange",
     "julia_round2", "julia_float_str", "kmer_count", "kmer_dist", "as_UInt", "as_kmer",
+    "randstrobe_score", "get_strobe_2_mer", "ungapped_strobe_2_mer_count",
 ]
 
 
@@ -369,6 +370,40 @@ def as_UInt(seq) -> int:
 def as_kmer(value: int, length: int) -> str:
     """as_kmer (src/Kmers.jl:80): inverse of as_UInt."""
     return "".join("ACGT"[(value >> (2 * (length - 1 - i))) & 3] for i in range(length))
+
+
+# ---- randstrobe utilities of the experimental strobemer path (src/StrobemerGMA/Strobemers.jl).  Host-side mirrors of the
+# functions the reference's tests pin; the strobemer scan itself (StrobeGMA!) is not part of the hot path and not built.
+def randstrobe_score(s1, s2, q: int) -> int:
+    """randstrobe_score (Strobemers.jl:12-14)"""
+    return (as_UInt(s1) + as_UInt(s2)) % q
+
+
+def get_strobe_2_mer(seq, s: int = 2, w_min: int = 3, w_max: int = 5, q: int = 5, withGap: bool = True) -> str:
+    """get_strobe_2_mer (Strobemers.jl:45-65): first s-mer + a second s-mer from starts w_min..w_max.  The reference seeds
+    its running minimum with `2 << 63`, which is 0 in Int64, so the second strobe is the LAST start whose score is 0, else
+    w_min -- the goldens (test-StrobemerGMA.jl:6-7) pin exactly that."""
+    seq = str(seq).upper()
+    first = seq[:s]
+    min_score, min_ind = 0, w_min
+    for i in range(w_min, w_max + 1):                     # 1-based window starts, as in the reference
+        cur = randstrobe_score(first, seq[i - 1:i - 1 + s], q)
+        if cur <= min_score:
+            min_score, min_ind = cur, i
+    second = seq[min_ind - 1:min_ind - 1 + s]
+    if not withGap:
+        return first + second
+    return first + "-" * (min_ind - s - 1) + second + "-" * (len(seq) - min_ind - s + 1)
+
+
+def ungapped_strobe_2_mer_count(seq, s: int = 2, w_min: int = 3, w_max: int = 5, q: int = 5) -> np.ndarray:
+    """ungapped_strobe_2_mer_count (Strobemers.jl:90-103): 4^(2s) bins of the gap-free 2-strobemers of every k = w_max+s-1 window."""
+    seq = str(seq).upper()
+    k = w_max + s - 1
+    bins = np.zeros(4 ** (2 * s))
+    for i in range(len(seq) - k + 1):
+        bins[as_UInt(get_strobe_2_mer(seq[i:i + k], s, w_min, w_max, q, withGap=False))] += 1
+    return bins
 
 
 def estimate_optimal_threshold(RV, average_length, seed: int = 42, num_trials: int = 100, buffer: float = 8):

@@ -175,3 +175,17 @@ def test_host_mirror_goldens():
     assert [int(round(x)) for x in K.estimate_optimal_threshold(rvs5, ws5, buffer=8)] == [38, 33, 41, 37, 29]
     RV, _, _ = K.gen_ref_ws_cons(TF, 6)
     assert abs(K.estimate_optimal_threshold(RV, 299, buffer=12) - 27) <= 1.0
+
+
+def test_strobemer_utility_goldens():
+    """test/test_folder/test-StrobemerGMA.jl:1-18 (the only strobemer functions the reference tests)"""
+    import kmergma_jl_b200 as K
+    ts = "ATGCATGC"
+    assert K.randstrobe_score("ATGC", "GTGT", 5) == 4 and K.randstrobe_score("ATGC", "GTGT", 7) == 6
+    assert K.get_strobe_2_mer("ATCTCTGTTT") == "AT--CT----"
+    assert K.get_strobe_2_mer(ts) == "ATGC----"
+    assert K.get_strobe_2_mer("ATCTCTGTTT", withGap=False) == "ATCT"
+    assert K.get_strobe_2_mer(ts, withGap=False) == "ATGC"
+    counts = K.ungapped_strobe_2_mer_count(ts, s=1, w_min=2, w_max=4)
+    assert round(float(np.mean(counts)), 4) == 0.3125
+    assert counts[3] == 2 and counts[4] == counts[11] == counts[14] == 1
