@@ -490,30 +490,42 @@ def other_configs(K, ctx, g, lens, total, RV, ws, cons, peak):
                                "roofline": {"bound": "hbm", "kernel": "kgma_exact_match_sampled", "achieved": ach, "peak": peak, "unit": "GB/s",
                                             "frac": ach / peak, "algorithmic_bytes": "0.25 B/base: the 2-bit plane, one sampled word per 32 B sector; "
                                             "N is checked against the masked-run list, the ambiguity plane is not read"}}
-    # tier T2: from FASTA text on disk (parallel mmap parse + 2-bit pack on the host cores, then the streamed scan)
+    # tier T2: the reference's own entry point -- findGenes(genome_path = FASTA text on disk).  The whole cfg2 genome is written
+    # out as 80-column FASTA (3.1 GB), then: parallel mmap parse + 2-bit pack on the host cores, and the FIRST scan of the
+    # fresh, pageable genome (staged upload through a small page-locked ring); the second scan page-locks the plane.
+    path = None
     try:
         import tempfile
-        rec = int(np.argmax(lens))
-        seq = np.frombuffer(g.seq(rec).encode(), dtype=np.uint8)
         width = 80
-        body = seq[:seq.size // width * width].reshape(-1, width)
         with tempfile.NamedTemporaryFile(suffix=".fasta", delete=False, dir=os.environ.get("TMPDIR", "/tmp")) as fh:
-            fh.write(b">contig T2 tier\n")
-            fh.write(np.concatenate([body, np.full((body.shape[0], 1), 10, np.uint8)], axis=1).tobytes())
-            fh.write(seq[body.size:].tobytes() + b"\n")
             path = fh.name
+            for r in range(len(lens)):
+                seq = np.frombuffer(g.seq(r).encode(), dtype=np.uint8)
+                body = seq[:seq.size // width * width].reshape(-1, width)
+                fh.write(b">contig%d T2 tier\n" % (r + 1))
+                fh.write(np.concatenate([body, np.full((body.shape[0], 1), 10, np.uint8)], axis=1).tobytes())
+                fh.write(seq[body.size:].tobytes() + b"\n")
         t0 = time.perf_counter()
         g2 = K.Genome.from_fasta(path)
         t1 = time.perf_counter()
         out2 = K.scan_raw(g2, [RV], [ws], [cons], [THR], KMER, L.MODE_SINGLE, BUFF, L.F_ALIGN, GAP_OPEN, GAP_EXT, ctx=ctx)
         t2 = time.perf_counter()
+        K.scan_raw(g2, [RV], [ws], [cons], [THR], KMER, L.MODE_SINGLE, BUFF, L.F_ALIGN, GAP_OPEN, GAP_EXT, ctx=ctx)
+        t3 = time.perf_counter()
+        K.scan_raw(g2, [RV], [ws], [cons], [THR], KMER, L.MODE_SINGLE, BUFF, L.F_ALIGN, GAP_OPEN, GAP_EXT, ctx=ctx)
+        t4 = time.perf_counter()
         res["t2_from_fasta_text"] = {"bases": int(g2.total_len), "file_bytes": os.path.getsize(path), "parse_pack_ms": (t1 - t0) * 1e3,
-                                     "scan_ms": (t2 - t1) * 1e3, "value": g2.total_len / (t2 - t0) / 1e6, "unit": UNIT, "hits": int(len(out2.hits)),
-                                     "host_threads": len(os.sched_getaffinity(0)), "note": "first scan of a fresh genome: includes cudaHostRegister of the packed planes"}
-        os.unlink(path)
+                                     "first_scan_ms": (t2 - t1) * 1e3, "second_scan_ms": (t3 - t2) * 1e3, "third_scan_ms": (t4 - t3) * 1e3,
+                                     "value": g2.total_len / (t2 - t0) / 1e6, "unit": UNIT, "hits": int(len(out2.hits)),
+                                     "host_threads": len(os.sched_getaffinity(0)),
+                                     "note": "value = bases / (parse + first scan); first scan: staged upload from pageable memory; "
+                                             "second: cudaHostRegister of the 2-bit plane + scan; third: the steady streamed scan"}
         del g2
     except Exception as e:                                        # a full /tmp must not cost the headline numbers
         res["t2_from_fasta_text"] = {"error": str(e)}
+    finally:
+        if path and os.path.exists(path):
+            os.unlink(path)
     ms, out = timeit(lambda: K.scan_raw(g, [RV], [ws], [cons], [THR], KMER, L.MODE_SINGLE, BUFF, L.F_ALIGN | L.F_RESIDENT | L.F_DENSE, GAP_OPEN, GAP_EXT, ctx=ctx), 2)
     res["findGenes_dense_count_table"] = {"ms_per_step": ms, "value": total / ms / 1e3, "unit": UNIT, "hits": int(len(out.hits)),
                                           "note": "KGMA_F_DENSE: every window through the shared-memory count-table kernel, no prefilter"}

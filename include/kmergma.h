@@ -164,6 +164,11 @@ const char *kgma_genome_identifier(const kgma_genome *g, int record);   /* FASTA
 const char *kgma_genome_description(const kgma_genome *g, int record);  /* FASTA.description */
 /* view(seq, first:last) as upper-case ASCII (N restored from the mask); 1-based inclusive */
 int  kgma_genome_get_seq(const kgma_genome *g, int record, int64_t first, int64_t last, char *out);
+/* Maximal runs of masked residues (N and any other non-ACGT symbol) of a sealed genome as [start,end) pairs, 0-based in
+ * the packed coordinate space (record r starts at kgma_genome_record_offset).  This is the list the extension and
+ * exact-match kernels consult instead of reading the ambiguity plane.  *out is malloc'd (kgma_free), *n_runs pairs. */
+int  kgma_genome_masked_runs(kgma_genome *g, int64_t **out, int64_t *n_runs);
+int64_t kgma_genome_record_offset(const kgma_genome *g, int record);
 /* Overwrite residues in place before sealing/uploading (used to plant homologues in synthetic genomes). */
 int  kgma_genome_put_seq(kgma_genome *g, int record, int64_t first, const char *seq, int64_t len);
 /* Synthetic genome: record r gets rec_len[r] bases, base(p) = splitmix64(seed ^ global p) & 3,

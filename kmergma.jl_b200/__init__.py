@@ -182,6 +182,20 @@ class Genome:
             raise KmerGMAError(rc, f"range {first}:{last} outside record {r}")
         return buf.value.decode()
 
+    def record_offset(self, r: int) -> int:
+        return self._lib.kgma_genome_record_offset(self._h, r)
+
+    def masked_runs(self) -> np.ndarray:
+        """maximal runs of masked (non-ACGT) residues, [start, end) rows in packed coordinates (see record_offset)"""
+        p = C.POINTER(C.c_int64)()
+        n = C.c_int64()
+        rc = self._lib.kgma_genome_masked_runs(self._h, C.byref(p), C.byref(n))
+        if rc != 0:
+            raise KmerGMAError(rc, "masked_runs failed")
+        out = np.ctypeslib.as_array(p, shape=(max(1, 2 * n.value),))[:2 * n.value].copy().reshape(-1, 2)
+        self._lib.kgma_free(p)
+        return out
+
     def put_seq(self, r: int, first: int, seq: str):
         s = seq.encode()
         rc = self._lib.kgma_genome_put_seq(self._h, r, first, s, len(s))

@@ -76,6 +76,8 @@ SYMBOLS = {
     "kgma_genome_identifier": (C.c_char_p, [_P, C.c_int]),
     "kgma_genome_description": (C.c_char_p, [_P, C.c_int]),
     "kgma_genome_get_seq": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_char_p]),
+    "kgma_genome_masked_runs": (C.c_int, [_P, C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.c_int64)]),
+    "kgma_genome_record_offset": (C.c_int64, [_P, C.c_int]),
     "kgma_genome_put_seq": (C.c_int, [_P, C.c_int, C.c_int64, C.c_char_p, C.c_int64]),
     "kgma_genome_synth": (C.c_int, [_P, C.c_int, _P, C.c_uint64, C.c_int64, C.c_int64, C.POINTER(_P)]),
     "kgma_genome_make_resident": (C.c_int, [_P, _P]),

@@ -339,6 +339,14 @@ static inline uint8_t sym_code(char c)
     }
 }
 
+// Small uploads of the extension batches go through this kernel (reads of the page-locked staging block over the bus)
+// rather than the copy engine: during a streamed scan the engine is busy with 32 MB genome chunks, and a 50 KB copy queued
+// behind one of those waits ~0.6 ms -- per round of the cluster-mode replay.
+__global__ void kgma_fetch_host(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 static int slot_scratch(kgma_ctx *ctx, int slot, size_t dbytes, size_t hbytes, void **d, void **h)
 {
     if (dbytes > ctx->a_dev_bytes[slot]) {
@@ -352,7 +360,7 @@ static int slot_scratch(kgma_ctx *ctx, int slot, size_t dbytes, size_t hbytes, v
         if (ctx->a_host[slot]) cudaFreeHost(ctx->a_host[slot]);
         ctx->a_host[slot] = nullptr; ctx->a_host_bytes[slot] = 0;
         const size_t nb = std::max(hbytes + hbytes / 4, (size_t)1 << 20);
-        KGMA_CUDA(ctx, cudaHostAlloc(&ctx->a_host[slot], nb, cudaHostAllocDefault));
+        KGMA_CUDA(ctx, cudaHostAlloc(&ctx->a_host[slot], nb, cudaHostAllocMapped));   // the kernels read / write it in place
         ctx->a_host_bytes[slot] = nb;
     }
     *d = ctx->a_dev[slot]; *h = ctx->a_host[slot];
@@ -430,13 +438,22 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     if (!bcodes.empty()) memcpy(h + o_b, bcodes.data(), bcodes.size());
     memcpy(h + o_j, jobs.data(), (size_t)nj * sizeof(AlignJob2));
     if (!nruns.empty()) memcpy(h + o_n, nruns.data(), nruns.size() * 8);
-    KGMA_CUDA(ctx, cudaMemcpyAsync(d, h, up, cudaMemcpyHostToDevice, st));
+    void *h_dev = nullptr;                                     // device-side address of the staging block (same as h under UVA)
+    KGMA_CUDA(ctx, cudaHostGetDevicePointer(&h_dev, h, 0));
+    {
+        const size_t n16 = up / 16;                            // (carve rounds every piece to 256 bytes)
+        const int cgrid = (int)std::min<size_t>((n16 + 255) / 256, (size_t)ctx->num_sms * 4);
+        kgma_fetch_host<<<std::max(cgrid, 1), 256, 0, st>>>((uint4 *)d, (const uint4 *)h_dev, n16);
+        KGMA_CUDA(ctx, cudaGetLastError());
+        ctx->stats.launches++;
+    }
     KGMA_CUDA(ctx, cudaMemsetAsync(d + o_c, 0, 256, st));
     ctx->stats.h2d_bytes += up;
     AlignArgs2 A{};
     A.a = d + o_a; A.seq = ctx->d_seq2; A.nruns = (const long long *)(d + o_n); A.n_nruns = (int)(nruns.size() / 2);
     A.b = d + o_b; A.jobs = (const AlignJob2 *)(d + o_j); A.njobs = nj; A.next_job = (int *)(d + o_c);
-    A.out = (AlignOut *)(d + o_o); A.go = -gap_open; A.ge = -gap_extend; A.tie_open = tie_open ? 1 : 0; A.ncol_cap = ncol;
+    // results are written straight into the page-locked block (16 bytes per alignment, posted writes): no copy back
+    A.out = (AlignOut *)((unsigned char *)h_dev + up); A.go = -gap_open; A.ge = -gap_extend; A.tie_open = tie_open ? 1 : 0; A.ncol_cap = ncol;
     A.need_boundary = need_boundary ? 1 : 0;
     KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -448,7 +465,6 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     KGMA_CUDA(ctx, cudaEventRecord(ctx->a_ev1[slot], st));
     ctx->stats.launches++;
     AlignOut *ho = (AlignOut *)(h + up);
-    KGMA_CUDA(ctx, cudaMemcpyAsync(ho, d + o_o, (size_t)nj * sizeof(AlignOut), cudaMemcpyDeviceToHost, st));
     KGMA_CUDA(ctx, cudaEventRecord(ctx->a_done[slot], st));
     ctx->stats.d2h_bytes += (size_t)nj * sizeof(AlignOut);
     t->active = true; t->slot = slot; t->nj = nj; t->ho = ho;
@@ -495,7 +511,7 @@ int align_batch_device(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq
     }
     cudaEvent_t e0 = ctx->ev[0], e1 = ctx->ev[1];
     double align_ms = 0;
-    cudaStream_t st = ctx->s_compute;
+    cudaStream_t st = ctx->s_extend ? ctx->s_extend : ctx->s_compute;
     if (!want_cigars) {
         // ---- trace-free path: one launch for everything; subjects come from the packed genome already on the device
         AlignTicket t;

@@ -1,5 +1,6 @@
 // Context life-cycle and result accessors of the C ABI (include/kmergma.h).
 #include "kgma_internal.h"
+#include <sys/mman.h>
 
 namespace kgma { const char *create_err(); }
 using namespace kgma;
@@ -50,6 +51,8 @@ void kgma_destroy(kgma_ctx *c)
         if (c->a_host[i]) cudaFreeHost(c->a_host[i]);
     }
     for (auto &e : c->chunk_ev) cudaEventDestroy(e);
+    for (auto &e : c->stage_ev) if (e) cudaEventDestroy(e);
+    if (c->stage) { cudaHostUnregister(c->stage); munmap(c->stage, c->stage_bytes); }
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->s_align) cudaStreamDestroy(c->s_align);

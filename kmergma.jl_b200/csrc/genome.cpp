@@ -14,6 +14,9 @@
 #include <chrono>
 #if defined(__SSE2__)
 #include <emmintrin.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #endif
 
 namespace kgma {
@@ -44,27 +47,31 @@ struct CodeTab {
 };
 static const CodeTab CT;
 
+// The planes live in anonymous mappings marked MADV_HUGEPAGE: pages arrive zeroed and lazily, so a bulk ingest faults
+// them in from its packing threads instead of one memset, and with 2 MB pages both those faults and the later
+// cudaHostRegister (which pins page by page) cost a fraction of what they do on 4 KB pages (measured on the B200 box:
+// registering 62 MB 39 ms -> 3.6 ms).  Growth is mremap: contents kept, new pages zero.
+static void *plane_map(void *old, size_t old_bytes, size_t bytes)
+{
+    void *p = old ? mremap(old, old_bytes, bytes, MREMAP_MAYMOVE)
+                  : mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return nullptr;
+    madvise(p, bytes, MADV_HUGEPAGE);                      // advisory: a kernel without THP just keeps 4 KB pages
+    return p;
+}
+
 int genome_reserve(kgma_genome *g, int64_t bases)
 {
     if (bases <= g->cap_bases) return KGMA_OK;
     int64_t nc = std::max<int64_t>(bases, g->cap_bases + g->cap_bases / 2);
     nc = (nc + 4095) / 4096 * 4096;
     if (g->pinned || g->host_alloc) return KGMA_E_STATE;
-    if (!g->seq2 && !g->mask) {                            // first allocation: calloc hands out lazily zeroed pages, so a bulk
-        g->seq2 = (uint32_t *)calloc((size_t)nc / 4, 1);   // ingest faults them in from its packing threads instead of one memset
-        g->mask = (uint32_t *)calloc((size_t)nc / 8, 1);
-        if (!g->seq2 || !g->mask) { free(g->seq2); free(g->mask); g->seq2 = g->mask = nullptr; return KGMA_E_CAPACITY; }
-        g->cap_bases = nc;
-        return KGMA_OK;
-    }
-    uint32_t *s = (uint32_t *)realloc(g->seq2, (size_t)nc / 4);
+    void *s = plane_map(g->seq2, g->seq_map, (size_t)nc / 4);
     if (!s) return KGMA_E_CAPACITY;
-    g->seq2 = s;
-    uint32_t *m = (uint32_t *)realloc(g->mask, (size_t)nc / 8);
+    g->seq2 = (uint32_t *)s; g->seq_map = (size_t)nc / 4;
+    void *m = plane_map(g->mask, g->mask_map, (size_t)nc / 8);
     if (!m) return KGMA_E_CAPACITY;
-    g->mask = m;
-    memset((char *)g->seq2 + g->cap_bases / 4, 0, (size_t)(nc - g->cap_bases) / 4);
-    memset((char *)g->mask + g->cap_bases / 8, 0, (size_t)(nc - g->cap_bases) / 8);
+    g->mask = (uint32_t *)m; g->mask_map = (size_t)nc / 8;
     g->cap_bases = nc;
     return KGMA_OK;
 }
@@ -86,25 +93,59 @@ int genome_pin(kgma_ctx *ctx, kgma_genome *g)
 
 static std::atomic<uint64_t> g_uid{1};
 
-// maximal runs of masked bases as [start,end) pairs in global coordinates; rebuilt when the genome changed
+// runs of set bits in mask words [w0, w1) as [start,end) bit positions, appended to out (runs are clipped to the range)
+static void mask_runs_range(const uint32_t *mask, int64_t w0, int64_t w1, std::vector<int64_t> &out)
+{
+    int64_t open = -1;
+    int64_t w = w0;
+    while (w < w1) {
+        if (open < 0) {
+            // skip clear words, eight bytes at a time where alignment allows
+            while (w + 1 < w1 && (w & 1) == 0 && *(const uint64_t *)(mask + w) == 0) w += 2;
+            if (w >= w1) break;
+        }
+        uint32_t m = mask[w];
+        if (m == 0) { if (open >= 0) { out.push_back(open); out.push_back(w * 32); open = -1; } w++; continue; }
+        if (m == 0xFFFFFFFFu) { if (open < 0) open = w * 32; w++; continue; }
+        int b = 0;
+        while (b < 32) {
+            if (open < 0) {
+                const uint32_t rest = m >> b;
+                if (!rest) break;
+                b += __builtin_ctz(rest); open = w * 32 + b;
+            } else {
+                const uint32_t rest = ~m >> b;            // bits above 31-b read as 0 after the shift: no false "clear" bit
+                if (!rest) break;
+                b += __builtin_ctz(rest);
+                if (b >= 32) break;
+                out.push_back(open); out.push_back(w * 32 + b); open = -1;
+            }
+        }
+        w++;
+    }
+    if (open >= 0) { out.push_back(open); out.push_back(w1 * 32); }
+}
+
+template <typename F> static void parallel_for(size_t n, int nthreads, F f);
+
+// maximal runs of masked bases as [start,end) pairs in global coordinates; rebuilt when the genome changed.  A whole
+// genome's ambiguity plane is hundreds of MB, so large planes are scanned in slices on several threads and stitched.
 const std::vector<int64_t> &genome_nruns(kgma_genome *g)
 {
     if (g->nruns_uid == g->uid) return g->nruns;
     g->nruns.clear();
     if (g->any_mask) {
         const int64_t nwords = (g->G + 31) / 32;
-        int64_t open = -1;
-        for (int64_t w = 0; w < nwords; w++) {
-            uint32_t m = g->mask[w];
-            if (m == 0) { if (open >= 0) { g->nruns.push_back(open); g->nruns.push_back(w * 32); open = -1; } continue; }
-            if (m == 0xFFFFFFFFu) { if (open < 0) open = w * 32; continue; }
-            for (int b = 0; b < 32; b++) {
-                const bool set = (m >> b) & 1;
-                if (set && open < 0) open = w * 32 + b;
-                else if (!set && open >= 0) { g->nruns.push_back(open); g->nruns.push_back(w * 32 + b); open = -1; }
+        const int64_t SL = (int64_t)1 << 20;               // words per slice (4 MB)
+        const size_t nsl = (size_t)((nwords + SL - 1) / SL);
+        std::vector<std::vector<int64_t>> part(nsl);
+        const int nt = (int)std::min<size_t>(nsl, std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+        parallel_for(nsl, nt, [&](size_t i) { mask_runs_range(g->mask, (int64_t)i * SL, std::min(nwords, (int64_t)(i + 1) * SL), part[i]); });
+        for (auto &pv : part)
+            for (size_t j = 0; j + 1 < pv.size(); j += 2) {
+                if (!g->nruns.empty() && g->nruns.back() == pv[j]) g->nruns.back() = pv[j + 1];     // a run continuing across a slice edge
+                else { g->nruns.push_back(pv[j]); g->nruns.push_back(pv[j + 1]); }
             }
-        }
-        if (open >= 0) { g->nruns.push_back(open); g->nruns.push_back(nwords * 32); }
     }
     g->nruns_uid = g->uid;
     return g->nruns;
@@ -196,7 +237,8 @@ void kgma_genome_destroy(kgma_genome *g)
     if (g->host_alloc) { cudaFreeHost(g->seq2); cudaFreeHost(g->mask); }
     else {
         if (g->pinned) cudaHostUnregister(g->seq2);
-        free(g->seq2); free(g->mask);
+        if (g->seq2) munmap(g->seq2, g->seq_map);
+        if (g->mask) munmap(g->mask, g->mask_map);
     }
     delete g;
 }
@@ -353,6 +395,110 @@ static void pack_task(kgma_genome *g, int64_t rec_off, FastaTask &t)
     if (gp & 31) flush_mask(gp >> 5, true);
 }
 
+// ---- AVX2 forms of the two passes (chosen at run time; the SSE2/scalar forms above are the portable fallback and the
+//      behavioural definition: identical planes, counts, first bad / ambiguous positions) -------------------------------
+#if defined(__x86_64__)
+__attribute__((target("avx2,popcnt")))
+static void count_task_avx2(FastaTask &t)
+{
+    int64_t ws = 0;
+    const char *p = t.b;
+    const __m256i c1 = _mm256_set1_epi8('\n'), c2 = _mm256_set1_epi8('\r'), c3 = _mm256_set1_epi8(' '), c4 = _mm256_set1_epi8('\t');
+    for (; p + 32 <= t.e; p += 32) {
+        const __m256i v = _mm256_loadu_si256((const __m256i *)p);
+        const __m256i m = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, c1), _mm256_cmpeq_epi8(v, c2)),
+                                          _mm256_or_si256(_mm256_cmpeq_epi8(v, c3), _mm256_cmpeq_epi8(v, c4)));
+        ws += __builtin_popcount((unsigned)_mm256_movemask_epi8(m));
+    }
+    for (; p < t.e; ++p) ws += is_ws((unsigned char)*p);
+    t.nres = (int64_t)(t.e - t.b) - ws;
+}
+
+// 32 characters at a time: classify (A/C/G/T in either case, N, anything else), turn the leading run of plain or N
+// residues into 2-bit codes with two multiply-adds and a byte shuffle, and append them to a bit accumulator that is
+// written out in whole 32-bit words.  The first character that is neither (line ends, IUPAC codes, invalid bytes) goes
+// through the scalar table, exactly as in pack_task.  With 80-column lines that is 3 vector steps per 81 bytes.
+__attribute__((target("avx2,bmi2")))
+static void pack_task_avx2(kgma_genome *g, int64_t rec_off, FastaTask &t)
+{
+    int64_t gp = rec_off + t.base0;                         // global position of the next residue
+    const int64_t gp_end = gp + t.nres;
+    const int64_t first_w = gp >> 4, last_w = (gp_end - 1) >> 4;
+    uint64_t acc = 0; int nb = 0;                           // pending bits of word gp>>4 (nb = 2 * (gp & 15) once the task is under way)
+    int64_t wd = gp >> 4;                                   // the word acc belongs to
+    nb = 2 * (int)(gp & 15);                                // the task's first word may start in the middle: those low bits stay 0 here
+    auto put_word = [&](uint32_t w) {
+        if (wd == first_w || wd == last_w) { if (w) __atomic_fetch_or(&g->seq2[wd], w, __ATOMIC_RELAXED); }
+        else g->seq2[wd] = w;
+        wd++;
+    };
+    auto append = [&](int n, uint64_t payload, uint32_t nmask) {   // n <= 32 residues, payload = their codes, nmask = which are masked
+        if (nmask) {
+            t.anymask = true;
+            const int sh = (int)(gp & 31);
+            __atomic_fetch_or(&g->mask[gp >> 5], nmask << sh, __ATOMIC_RELAXED);
+            if (sh && (nmask >> (32 - sh))) __atomic_fetch_or(&g->mask[(gp >> 5) + 1], nmask >> (32 - sh), __ATOMIC_RELAXED);
+        }
+        const unsigned __int128 wide = (unsigned __int128)acc | ((unsigned __int128)payload << nb);
+        int tot = nb + 2 * n;
+        uint64_t lo = (uint64_t)wide, hi = (uint64_t)(wide >> 64);
+        while (tot >= 32) {
+            put_word((uint32_t)lo);
+            lo = (lo >> 32) | (hi << 32); hi >>= 32; tot -= 32;
+        }
+        acc = lo; nb = tot; gp += n;
+    };
+    const __m256i lower = _mm256_set1_epi8(0x20), three = _mm256_set1_epi8(3), one = _mm256_set1_epi8(1);
+    const __m256i la = _mm256_set1_epi8('a'), lc = _mm256_set1_epi8('c'), lg = _mm256_set1_epi8('g'), lt = _mm256_set1_epi8('t'), ln = _mm256_set1_epi8('n');
+    const __m256i mul4 = _mm256_set1_epi16(0x0401), mul16 = _mm256_set1_epi32(0x00100001);
+    const __m256i gather = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                            0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    const char *p = t.b;
+    while (p < t.e) {
+        if (p + 32 <= t.e) {
+            const __m256i v = _mm256_loadu_si256((const __m256i *)p);
+            const __m256i u = _mm256_or_si256(v, lower);
+            const __m256i vn = _mm256_cmpeq_epi8(u, ln);
+            const __m256i va = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(u, la), _mm256_cmpeq_epi8(u, lc)),
+                                               _mm256_or_si256(_mm256_cmpeq_epi8(u, lg), _mm256_cmpeq_epi8(u, lt)));
+            const uint32_t mn = (uint32_t)_mm256_movemask_epi8(vn);
+            const uint32_t ok = (uint32_t)_mm256_movemask_epi8(va) | mn;
+            const int nz = ok == 0xFFFFFFFFu ? 32 : __builtin_ctz(~ok);
+            if (nz) {
+                // A=0x41 C=0x43 G=0x47 T=0x54 (and lower case): x = (c >> 1) & 3 gives 0,1,3,2; x ^ (x >> 1) swaps the last two.  N -> 3.
+                const __m256i x = _mm256_and_si256(_mm256_srli_epi16(v, 1), three);
+                __m256i code = _mm256_xor_si256(x, _mm256_and_si256(_mm256_srli_epi16(x, 1), one));
+                code = _mm256_or_si256(code, _mm256_and_si256(vn, three));
+                const __m256i b16 = _mm256_maddubs_epi16(code, mul4);              // c0 + 4 c1 per 16-bit lane
+                const __m256i b32 = _mm256_madd_epi16(b16, mul16);                 // + 16 (c2 + 4 c3): one byte of packed codes per 32-bit lane
+                const __m256i by = _mm256_shuffle_epi8(b32, gather);
+                uint64_t payload = (uint64_t)(uint32_t)_mm256_extract_epi32(by, 0) | ((uint64_t)(uint32_t)_mm256_extract_epi32(by, 4) << 32);
+                uint32_t nm = mn;
+                if (nz < 32) { payload &= ((uint64_t)1 << (2 * nz)) - 1; nm &= (1u << nz) - 1; }
+                append(nz, payload, nm);
+                p += nz;
+                if (nz == 32) continue;
+            }
+        }
+        // one character through the table: white space, IUPAC, invalid bytes, and the last few bytes of the task
+        const unsigned char ch = (unsigned char)*p++;
+        if (is_ws(ch)) continue;
+        uint8_t c = CT.t[ch];
+        const int64_t i = gp - rec_off;
+        if (c == 0xFF) { if (t.bad < 0) t.bad = i; c = 0; }
+        if ((c & 8) && t.amb < 0) t.amb = i;
+        append(1, (uint64_t)(c & 3), (c & 4) ? 1u : 0u);
+    }
+    if (nb) { const uint32_t w = (uint32_t)acc; if (w) __atomic_fetch_or(&g->seq2[wd], w, __ATOMIC_RELAXED); }
+}
+
+static bool have_avx2() { static const bool v = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2") && !getenv("KGMA_NO_AVX2"); return v; }
+#else
+static bool have_avx2() { return false; }
+static void count_task_avx2(FastaTask &) {}
+static void pack_task_avx2(kgma_genome *, int64_t, FastaTask &) {}
+#endif
+
 template <typename F> static void parallel_for(size_t n, int nthreads, F f)
 {
     if (n == 0) return;
@@ -424,7 +570,8 @@ int kgma_genome_from_fasta(const char *path, kgma_genome **out)
         }
         spans[r].n_tasks = tasks.size() - spans[r].first_task;
     }
-    parallel_for(tasks.size(), nthreads, [&](size_t i) { count_task(tasks[i]); });
+    const bool avx2 = have_avx2();
+    parallel_for(tasks.size(), nthreads, [&](size_t i) { if (avx2) count_task_avx2(tasks[i]); else count_task(tasks[i]); });
     lap("count");
 
     // ---- layout: record lengths, offsets, one reservation
@@ -438,7 +585,10 @@ int kgma_genome_from_fasta(const char *path, kgma_genome **out)
     if (!g->recs.empty()) rc = genome_reserve(g, g->recs.back().off + g->recs.back().len + REC_ALIGN + TAIL_PAD + FGROUP);
     lap("reserve");
     if (rc == KGMA_OK) {
-        parallel_for(tasks.size(), nthreads, [&](size_t i) { if (tasks[i].nres) pack_task(g, g->recs[(size_t)tasks[i].rec].off, tasks[i]); });
+        parallel_for(tasks.size(), nthreads, [&](size_t i) {
+            if (!tasks[i].nres) return;
+            if (avx2) pack_task_avx2(g, g->recs[(size_t)tasks[i].rec].off, tasks[i]); else pack_task(g, g->recs[(size_t)tasks[i].rec].off, tasks[i]);
+        });
         lap("pack");
         for (const FastaTask &t : tasks) {
             if (t.bad >= 0 && rc == KGMA_OK) { g->err = "record " + std::to_string(t.rec) + ": invalid character at position " + std::to_string(t.bad + 1); rc = KGMA_E_SYMBOL; }
@@ -459,6 +609,20 @@ int64_t kgma_genome_record_len(const kgma_genome *g, int r) { return (g && r >= 
 int64_t kgma_genome_total_len(const kgma_genome *g) { return g ? g->total_len : 0; }
 const char *kgma_genome_identifier(const kgma_genome *g, int r) { return (g && r >= 0 && r < (int)g->recs.size()) ? g->recs[r].ident.c_str() : nullptr; }
 const char *kgma_genome_description(const kgma_genome *g, int r) { return (g && r >= 0 && r < (int)g->recs.size()) ? g->recs[r].desc.c_str() : nullptr; }
+
+int64_t kgma_genome_record_offset(const kgma_genome *g, int r) { return (g && r >= 0 && r < (int)g->recs.size()) ? g->recs[r].off : -1; }
+
+int kgma_genome_masked_runs(kgma_genome *g, int64_t **out, int64_t *n_runs)
+{
+    if (!g || !out || !n_runs) return KGMA_E_ARG;
+    if (!g->sealed) return KGMA_E_STATE;
+    const std::vector<int64_t> &v = genome_nruns(g);
+    *n_runs = (int64_t)v.size() / 2;
+    *out = (int64_t *)malloc(std::max<size_t>(1, v.size()) * sizeof(int64_t));
+    if (!*out) return KGMA_E_CAPACITY;
+    if (!v.empty()) memcpy(*out, v.data(), v.size() * sizeof(int64_t));
+    return KGMA_OK;
+}
 
 int kgma_genome_get_seq(const kgma_genome *g, int r, int64_t first, int64_t last, char *out)
 {

@@ -41,12 +41,14 @@ struct kgma_genome {
     bool      ambiguous = false;   // a symbol other than A,C,G,T,N was ingested
     bool      any_mask = false;
     bool      pinned = false;      // planes are page-locked (cudaHostRegister / cudaHostAlloc)
-    bool      host_alloc = false;  // allocated with cudaHostAlloc (else malloc)
+    bool      host_alloc = false;  // allocated with cudaHostAlloc (else anonymous mmap, see genome_reserve)
+    size_t    seq_map = 0, mask_map = 0;   // mapped bytes of the two planes when not host_alloc
     int64_t   amb_record = -1, amb_pos = -1;
     uint64_t  uid = 0;
     std::string err;
     std::vector<int64_t> nruns;    // cache: maximal runs of masked bases, [start,end) global positions (genome_nruns)
     uint64_t  nruns_uid = 0;
+    int       n_uploads = 0;       // streamed uploads so far: the first goes through the staging ring, the second page-locks the plane
 };
 
 struct kgma_refs {
@@ -66,6 +68,7 @@ struct kgma_result {
 struct kgma_ctx {
     int device = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr, s_align = nullptr;
+    cudaStream_t s_extend = nullptr;                      // stream of align_batch_device; null = s_compute (a pipelined scan moves it to s_align)
     cudaEvent_t  ev[8] = {};
     int num_sms = 0;
     size_t smem_optin = 0;
@@ -85,6 +88,8 @@ struct kgma_ctx {
     void     *a_dev[2] = {}, *a_host[2] = {}; size_t a_dev_bytes[2] = {}, a_host_bytes[2] = {};
     cudaEvent_t a_ev0[2] = {}, a_ev1[2] = {}, a_done[2] = {};
     std::vector<cudaEvent_t> chunk_ev;             // one event per streamed chunk (pipelined scan)
+    // staging ring for the first upload of a genome whose planes are not page-locked (scan.cu: StagedUpload)
+    void *stage = nullptr; size_t stage_bytes = 0; cudaEvent_t stage_ev[8] = { nullptr };
     // scratch
     void     *d_scratch = nullptr; size_t d_scratch_bytes = 0;
     void     *h_scratch = nullptr; size_t h_scratch_bytes = 0;   // pinned

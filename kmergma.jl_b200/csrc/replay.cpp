@@ -299,6 +299,7 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
                                     want_cig ? &res->cigar_ops : nullptr, want_cig ? &res->cigar_cnt : nullptr);
         if (rc) return rc;
         for (size_t j = 0; j < missing.size(); j++) { res_of_run[missing[j]] = ares[j]; have[missing[j]] = 1; }
+        if (getenv("KGMA_TRACE")) fprintf(stderr, "[kgma replay] round %d: %zu extensions\n", round, missing.size());
         n_align_total += (int64_t)reqs.size();
     }
     res->hits.clear();

@@ -26,6 +26,9 @@
 #include <cstdlib>
 #include <chrono>
 #include <functional>
+#include <atomic>
+#include <thread>
+#include <sys/mman.h>
 
 namespace kgma {
 
@@ -518,13 +521,17 @@ int build_proftab(kgma_ctx *ctx, const kgma_profile &p, ProfTab &t)
 int dev_genome_prepare(kgma_ctx *ctx, kgma_genome *g, bool need_mask)
 {
     int64_t need = (g->G + TAIL_PAD + 4095) / 4096 * 4096;   // same rounding as the host planes (genome_reserve / kgma_genome_synth)
-    if (ctx->dg_uid != g->uid || ctx->d_cap_bases < need) {
+    if (ctx->d_cap_bases < need) {
+        // grow only: cudaFree / cudaMalloc of a genome-sized buffer cost 0.1-0.4 s, far more than a scan, so a context keeps
+        // the planes of the largest genome it has seen and merely invalidates their contents when another genome arrives
         if (ctx->d_seq2) cudaFree(ctx->d_seq2);
         if (ctx->d_mask) cudaFree(ctx->d_mask);
         ctx->d_seq2 = ctx->d_mask = nullptr; ctx->d_cap_bases = 0; ctx->dg_uid = 0;
         KGMA_CUDA(ctx, cudaMalloc(&ctx->d_seq2, (size_t)need / 4));
-        if (need_mask) KGMA_CUDA(ctx, cudaMalloc(&ctx->d_mask, (size_t)need / 8));
-        ctx->d_cap_bases = need; ctx->dg_uid = g->uid;
+        ctx->d_cap_bases = need;
+    }
+    if (ctx->dg_uid != g->uid) {
+        ctx->dg_uid = g->uid;
         ctx->d_seq_valid = ctx->d_mask_valid = false; ctx->d_valid_lo = ctx->d_valid_hi = 0;
         ctx->d_have_lo = ctx->d_have_hi = 0;
     }
@@ -645,7 +652,73 @@ constexpr long long NO_D = (long long)0x8080808080808080ull;   // cudaMemset(0x8
 
 using namespace kgma;
 
-// Pipelined streaming scan (single profile): records [0, rec_split) are evaluated as soon as their last block has been
+// First upload of a genome whose packed plane is ordinary pageable memory.  Page-locking 772 MB costs ~100 ms (the driver
+// pins page by page) and a plain cudaMemcpy from pageable memory runs at ~10 GB/s through the driver's own single-threaded
+// staging; here a few host threads copy 4 MB pieces into a small page-locked ring and the calling thread queues one
+// asynchronous copy per piece as it becomes ready, which keeps the link busy while the prefilter chases the data as usual.
+// A genome that is scanned again is page-locked then (kgma_genome::n_uploads), when the cost is worth paying.
+struct StagedUpload {
+    static constexpr int NS = 8;                           // ring slots
+    static constexpr size_t SB = (size_t)4 << 20;          // bytes per slot
+    kgma_ctx *ctx = nullptr;
+    const char *src = nullptr; size_t total = 0, nsub = 0;
+    std::atomic<size_t> next{0}, issued{0};
+    std::vector<std::atomic<int>> filled;
+    std::atomic<bool> abort{false};
+    std::vector<std::thread> th;
+
+    static int prepare_ring(kgma_ctx *ctx)
+    {
+        if (ctx->stage) return KGMA_OK;
+        const size_t bytes = NS * SB;
+        void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p == MAP_FAILED) return set_err(ctx, KGMA_E_CAPACITY, "staging ring allocation failed");
+        madvise(p, bytes, MADV_HUGEPAGE);
+        memset(p, 0, bytes);
+        if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+            cudaGetLastError(); munmap(p, bytes);
+            return set_err(ctx, KGMA_E_CUDA, "cudaHostRegister of the staging ring failed");
+        }
+        ctx->stage = p; ctx->stage_bytes = bytes;
+        for (auto &e : ctx->stage_ev) KGMA_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        return KGMA_OK;
+    }
+    void start(kgma_ctx *c, const char *s, size_t bytes)
+    {
+        ctx = c; src = s; total = bytes; nsub = (bytes + SB - 1) / SB;
+        filled = std::vector<std::atomic<int>>(nsub);
+        for (auto &f : filled) f.store(0, std::memory_order_relaxed);
+        const int nt = (int)std::min<size_t>(nsub, std::min(4u, std::max(1u, std::thread::hardware_concurrency())));
+        for (int t = 0; t < nt; t++) th.emplace_back([this]() {
+            cudaSetDevice(ctx->device);
+            for (;;) {
+                const size_t j = next.fetch_add(1);
+                if (j >= nsub) return;
+                if (j >= (size_t)NS) {                     // the slot's previous piece must have left for the device
+                    while (issued.load(std::memory_order_acquire) < j - NS + 1) { if (abort.load()) return; std::this_thread::yield(); }
+                    cudaEventSynchronize(ctx->stage_ev[j % NS]);
+                }
+                if (abort.load()) return;
+                memcpy((char *)ctx->stage + (j % NS) * SB, src + j * SB, std::min(SB, total - j * SB));
+                filled[j].store(1, std::memory_order_release);
+            }
+        });
+    }
+    // queue pieces [j0, j1) on the copy stream, in order, as the workers deliver them
+    int issue(size_t j0, size_t j1, char *dst, cudaStream_t sp)
+    {
+        for (size_t j = j0; j < j1; j++) {
+            while (!filled[j].load(std::memory_order_acquire)) std::this_thread::yield();
+            KGMA_CUDA(ctx, cudaMemcpyAsync(dst + j * SB, (char *)ctx->stage + (j % NS) * SB, std::min(SB, total - j * SB), cudaMemcpyHostToDevice, sp));
+            KGMA_CUDA(ctx, cudaEventRecord(ctx->stage_ev[j % NS], sp));
+            issued.store(j + 1, std::memory_order_release);
+        }
+        return KGMA_OK;
+    }
+    ~StagedUpload() { abort.store(true); for (auto &t : th) t.join(); }
+};
+
+// Pipelined streaming scan: records [0, rec_split) are evaluated as soon as their last block has been
 // filtered; on_first_part is called with their runs while the rest of the genome is still being copied and filtered.
 struct PhaseHook {
     int rec_split = 0;
@@ -741,8 +814,6 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
 
     rc = dev_genome_prepare(ctx, g, false);
     if (rc) return rc;
-    rc = genome_pin(ctx, g);
-    if (rc) return rc;
 
     int ewarps = 0; size_t esmem = 0;
     rc = eval_shape(ctx, pl.k, &ewarps, &esmem);
@@ -777,7 +848,8 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
 
     // ---- device scratch layout + one pinned staging block for all small uploads
     const uint32_t cand_cap = (uint32_t)std::min<int64_t>(std::max<int64_t>((blk_hi - blk_lo) / 16, 1 << 16) + (int64_t)seeds.size(), 1 << 26);
-    const uint32_t run_head = 4096;                                // runs copied back with the counters; more only if needed
+    // runs copied back together with the counters (more only if needed); several profiles report several times the runs
+    const uint32_t run_head = C == 1 ? 4096 : 32768;
     size_t o = 0;
     auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
     const size_t o_S = carve((size_t)C * nb * 4), o_recs = carve(recs.size() * sizeof(RecDev));
@@ -835,8 +907,15 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     // where record rec_split starts (records start on block boundaries); the prefilter launch in front of the first part's
     // evaluation ends on the next multiple of 32 blocks (its launches work in whole warp groups), which only means a few
     // blocks of the second part are filtered early.
+    // page-locked source, or (first upload of a pageable genome) the staging ring; a resident genome is not touched at all
+    const bool staged = !resident_ok && !g->pinned && g->n_uploads == 0 && !getenv("KGMA_NO_STAGING");
+    if (!resident_ok) {
+        rc = staged ? StagedUpload::prepare_ring(ctx) : genome_pin(ctx, g);
+        if (rc) return rc;
+        g->n_uploads++;
+    }
     int64_t split_blk = -1, split_blk_f = -1;
-    bool pipelined = hook && !resident_ok && groups.size() == 1 && !groups[0].dense && C == 1 && sc == 1 && nr > 1 &&
+    bool pipelined = hook && !resident_ok && !staged && any_filter && !any_dense && sc == 1 && nr > 1 &&
                      hook->rec_split > 0 && hook->rec_split < nr;
     if (pipelined) {
         split_blk = g->recs[(size_t)hook->rec_split].off / FBLOCK;
@@ -881,7 +960,8 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     enqueue_part_a = [&]() -> int {  // first part of a pipelined scan: evaluate its candidates, queue the copy of its results
         ea.cand_blk_lo = 0; ea.cand_blk_hi = split_blk;
         ea.next_item = (unsigned long long *)(d_counters + 64);   // bytes 256..
-        int rc2 = launch_eval(groups[0].q, false, 0, &groups[0]);
+        int rc2 = KGMA_OK;
+        for (size_t gi = 0; gi < groups.size() && !rc2; gi++) rc2 = launch_eval(groups[gi].q, false, gi, &groups[gi]);
         ea.next_item = (unsigned long long *)(d_counters + 32);
         ea.cand_blk_lo = split_blk; ea.cand_blk_hi = LLONG_MAX;    // what the final evaluation still has to do
         if (rc2) return rc2;
@@ -917,15 +997,17 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
             lim = split_blk_f;
             if (lim > done_blk) {
                 if (first_filter) { KGMA_CUDA(ctx, cudaEventRecord(e_fstart, sc_)); first_filter = false; }
-                const FilterGroup &fg = groups[0];
-                FilterArgs fa{};
-                fa.seq = (const uint4 *)ctx->d_seq2; fa.tab = (const uint16_t *)(ds + fg.o_tab); fa.M = fg.ft->M; fa.thrw = 1u << WFRAC;
-                fa.cand = (uint32_t *)(ds + fg.o_cand); fa.cand_cap = cand_cap; fa.cand_count = d_counters + 1;
-                fa.bitmap = (uint32_t *)(ds + fg.o_bits);
-                fa.blk_begin = done_blk; fa.blk_end = lim;
-                launch_filter_k(pl.k, fa, fgrid, sc_);
-                KGMA_CUDA(ctx, cudaGetLastError());
-                st.launches++;
+                for (size_t gi = 0; gi < groups.size(); gi++) {
+                    const FilterGroup &fg = groups[gi];
+                    FilterArgs fa{};
+                    fa.seq = (const uint4 *)ctx->d_seq2; fa.tab = (const uint16_t *)(ds + fg.o_tab); fa.M = fg.ft->M; fa.thrw = 1u << WFRAC;
+                    fa.cand = (uint32_t *)(ds + fg.o_cand); fa.cand_cap = cand_cap; fa.cand_count = d_counters + 1 + gi;
+                    fa.bitmap = (uint32_t *)(ds + fg.o_bits);
+                    fa.blk_begin = done_blk; fa.blk_end = lim;
+                    launch_filter_k(pl.k, fa, fgrid, sc_);
+                    KGMA_CUDA(ctx, cudaGetLastError());
+                    st.launches++;
+                }
                 done_blk = lim;
             }
             int rc2 = enqueue_part_a();
@@ -958,8 +1040,16 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
         if (pipelined) while (ctx->chunk_ev.size() < nchunks) { cudaEvent_t e; KGMA_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
         ctx->d_have_lo = up_lo; ctx->d_have_hi = up_hi;            // what the queued copies will have delivered (extension of the first part reads it)
         int ci = 0;
+        StagedUpload stager;                                       // (its destructor joins the copy threads on every exit path)
+        if (staged) stager.start(ctx, (const char *)g->seq2 + up_lo / 4, (size_t)(up_hi - up_lo) / 4);
         for (int64_t a = up_lo; a < up_hi; a += CH, ci++) {
             int64_t b = std::min(up_hi, a + CH);
+            if (staged) {
+                const size_t j0 = (size_t)((a - up_lo) / 4) / StagedUpload::SB;
+                const size_t j1 = b >= up_hi ? stager.nsub : (size_t)((b - up_lo) / 4) / StagedUpload::SB;
+                rc = stager.issue(j0, j1, (char *)ctx->d_seq2 + up_lo / 4, sp);
+                if (rc) return rc;
+            } else
             KGMA_CUDA(ctx, cudaMemcpyAsync((char *)ctx->d_seq2 + a / 4, (char *)g->seq2 + a / 4, (size_t)(b - a) / 4,
                                            cudaMemcpyHostToDevice, sp));
             cudaEvent_t ec = pipelined ? ctx->chunk_ev[(size_t)ci] : e_c[ci & 1];
@@ -990,18 +1080,23 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
             // everything is queued; while the rest of the genome streams, hand the first part's runs to the caller
             KGMA_CUDA(ctx, cudaEventSynchronize(e_partA));
             uint32_t ca[64]; memcpy(ca, hbackA, 256);
-            if (ca[0] <= run_head && ca[1] <= cand_cap) {
+            bool fits = ca[0] <= run_head;
+            for (size_t gi = 0; gi < groups.size(); gi++) fits = fits && ca[1 + gi] <= cand_cap;
+            if (fits) {
                 std::vector<kgma_run> ra((size_t)ca[0]);
                 if (ca[0]) memcpy(ra.data(), hbackA + 256 + (size_t)C * nr * 8, (size_t)ca[0] * sizeof(kgma_run));
                 std::vector<int64_t> fd((size_t)C * nr, INT64_MIN);
                 const long long *fdp = (const long long *)(hbackA + 256);
                 for (size_t i = 0; i < (size_t)C * nr; i++) if (fdp[i] != NO_D) fd[i] = fdp[i];
                 hook->n_runs_first = ca[0]; hook->used = true;
+                const double tA0 = now_ms();
                 rc = hook->on_first_part(ra, fd);
+                if (getenv("KGMA_TRACE")) fprintf(stderr, "[kgma scan] first part: %u runs, ready at %.2f ms, handled in %.2f ms\n", ca[0], tA0 - t_wall0, now_ms() - tA0);
                 if (rc) { cudaStreamSynchronize(sc_); return rc; }
             }
         }
         rc = fetch(); if (rc) return rc;
+        if (getenv("KGMA_TRACE")) fprintf(stderr, "[kgma scan] device done at %.2f ms\n", now_ms() - t_wall0);
         std::vector<int> redo;                                     // groups whose candidate list overflowed: evaluate every window
         for (size_t gi = 0; gi < groups.size(); gi++)
             if (!groups[gi].dense && cnts[1 + gi] > cand_cap) { redo.insert(redo.end(), groups[gi].q.begin(), groups[gi].q.end()); groups[gi].dense = true; any_dense = true; }
@@ -1113,25 +1208,40 @@ int kgma_scan(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int n
     kgma_result *res = new kgma_result();
     ScanPlan pl;
 
-    // Pipelined form for the streamed single-profile scan with extension: the records in front of a split point are
-    // replayed and their extension is queued on a second stream while the tail of the genome is still being copied, so
-    // that only the last records' share of replay + extension is left once the copy ends.
+    // Pipelined form of the streamed scan with extension: the records in front of a split point are replayed and extended
+    // on a second stream while the tail of the genome is still being copied, so that only the last records' share of
+    // replay + extension is left once the copy ends.  Records are independent in both state machines (GenomePos is a plain
+    // running sum of record lengths), so the two parts' hit lists simply concatenate.
     PhaseHook hook;
     const int nr = (int)g->recs.size();
-    const bool can_pipeline = g->sealed && P.mode == KGMA_MODE_SINGLE && n_profiles == 1 && (P.flags & KGMA_F_ALIGN) && P.only_record < 0 &&
+    const bool cluster = P.mode == KGMA_MODE_CLUSTER;
+    const bool can_pipeline = g->sealed && (cluster || n_profiles == 1) && (P.flags & KGMA_F_ALIGN) && P.only_record < 0 &&
                               !(P.flags & (KGMA_F_DENSE | KGMA_F_WANT_DISTS | KGMA_F_WANT_CIGARS)) && nr >= 2 && !getenv("KGMA_NO_PIPELINE");
     if (can_pipeline) {
-        // split in front of the first record that starts in the last eighth of the genome (but keep at least half in the first part)
+        // single mode queues one extension batch per part, so the first part should be as large as possible: split in front
+        // of the last record that starts before 93% of the genome.  Cluster mode extends in rounds that block the host, a few
+        // milliseconds for a whole genome: split earlier so that the first part's rounds fit under the rest of the copy.
+        double hi = cluster ? 0.72 : 0.93;
+        if (const char *e = getenv("KGMA_SPLIT")) hi = atof(e);
         for (int r = 1; r < nr; r++) {
             const double frac = (double)g->recs[(size_t)r].off / (double)std::max<int64_t>(1, g->G);
-            if (frac >= 0.5 && (hook.rec_split == 0 || frac <= 0.93)) hook.rec_split = r;
-            if (frac > 0.93) break;
+            if (frac >= 0.5 && (hook.rec_split == 0 || frac <= hi)) hook.rec_split = r;
+            if (frac > hi) break;
         }
     }
     std::vector<kgma_hit> hitsA; std::vector<AlignReq> reqsA, reqsB; std::vector<Pending> pendA, pendB;
-    std::vector<kgma_run> runsA; AlignTicket tA, tB; int64_t genome_pos = 0;
-    auto reset = [&]() { hitsA.clear(); reqsA.clear(); pendA.clear(); runsA.clear(); genome_pos = 0; if (tA.active) { std::vector<AlignRes> d; align_collect(ctx, &tA, d); } };
+    std::vector<kgma_run> runsA; AlignTicket tA, tB; int64_t genome_pos = 0, n_alignA = 0;
+    auto reset = [&]() { hitsA.clear(); reqsA.clear(); pendA.clear(); runsA.clear(); genome_pos = 0; n_alignA = 0; if (tA.active) { std::vector<AlignRes> d; align_collect(ctx, &tA, d); } };
     hook.on_first_part = [&](std::vector<kgma_run> &ra, const std::vector<int64_t> &fd) -> int {
+        if (cluster) {
+            kgma_result part;
+            ctx->s_extend = ctx->s_align;                 // the compute stream is busy with the tail of the genome
+            int rc2 = replay(ctx, g, pl.tabs, profiles, P, ra, fd, &part);
+            ctx->s_extend = nullptr;
+            if (rc2) return rc2;
+            hitsA.swap(part.hits); runsA.swap(ra); n_alignA = ctx->stats.n_align;
+            return KGMA_OK;
+        }
         merge_runs(ra);
         int rc2 = replay_single_range(ctx, g, pl.tabs[0], P, ra, fd, 0, hook.rec_split, &genome_pos, hitsA, reqsA, pendA);
         if (rc2) return rc2;
@@ -1147,23 +1257,35 @@ int kgma_scan(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int n
             // after a candidate overflow reports the first part's records again)
             std::vector<kgma_run> rb;
             for (size_t i = hook.n_runs_first; i < res->runs.size(); i++) if (res->runs[i].record >= hook.rec_split) rb.push_back(res->runs[i]);
-            merge_runs(rb);
-            std::vector<kgma_hit> hitsB;
-            rc = replay_single_range(ctx, g, pl.tabs[0], P, rb, res->first_D, hook.rec_split, nr, &genome_pos, hitsB, reqsB, pendB);
-            if (rc == KGMA_OK) rc = align_enqueue(ctx, g, reqsB, profiles, 1, true, P.gap_open, P.gap_extend, (P.flags & KGMA_F_TIE_OPEN) != 0, ctx->s_align, 1, &tB);
-            std::vector<AlignRes> aA, aB;
-            if (rc == KGMA_OK) rc = align_collect(ctx, &tA, aA);
-            if (rc == KGMA_OK) rc = align_collect(ctx, &tB, aB);
-            if (rc == KGMA_OK) {
-                apply_extensions(g, hitsA, pendA, aA);
-                apply_extensions(g, hitsB, pendB, aB);
-                res->hits = hitsA; res->hits.insert(res->hits.end(), hitsB.begin(), hitsB.end());
-                res->runs = runsA; res->runs.insert(res->runs.end(), rb.begin(), rb.end());
-                ctx->stats.n_align = (int64_t)(reqsA.size() + reqsB.size());
-                ctx->stats.n_runs = (int64_t)res->runs.size();
-            } else reset();
+            if (cluster) {
+                kgma_result part;
+                rc = replay(ctx, g, pl.tabs, profiles, P, rb, res->first_D, &part);
+                if (rc == KGMA_OK) {
+                    res->hits = hitsA; res->hits.insert(res->hits.end(), part.hits.begin(), part.hits.end());
+                    res->runs = runsA; res->runs.insert(res->runs.end(), rb.begin(), rb.end());
+                    ctx->stats.n_align += n_alignA;
+                    ctx->stats.n_runs = (int64_t)res->runs.size();
+                }
+            } else {
+                merge_runs(rb);
+                std::vector<kgma_hit> hitsB;
+                rc = replay_single_range(ctx, g, pl.tabs[0], P, rb, res->first_D, hook.rec_split, nr, &genome_pos, hitsB, reqsB, pendB);
+                if (rc == KGMA_OK) rc = align_enqueue(ctx, g, reqsB, profiles, 1, true, P.gap_open, P.gap_extend, (P.flags & KGMA_F_TIE_OPEN) != 0, ctx->s_align, 1, &tB);
+                std::vector<AlignRes> aA, aB;
+                if (rc == KGMA_OK) rc = align_collect(ctx, &tA, aA);
+                if (rc == KGMA_OK) rc = align_collect(ctx, &tB, aB);
+                if (rc == KGMA_OK) {
+                    apply_extensions(g, hitsA, pendA, aA);
+                    apply_extensions(g, hitsB, pendB, aB);
+                    res->hits = hitsA; res->hits.insert(res->hits.end(), hitsB.begin(), hitsB.end());
+                    res->runs = runsA; res->runs.insert(res->runs.end(), rb.begin(), rb.end());
+                    ctx->stats.n_align = (int64_t)(reqsA.size() + reqsB.size());
+                    ctx->stats.n_runs = (int64_t)res->runs.size();
+                } else reset();
+            }
         } else rc = replay(ctx, g, pl.tabs, profiles, P, res->runs, res->first_D, res);
         const double dt = now_ms() - t0;
+        if (getenv("KGMA_TRACE")) fprintf(stderr, "[kgma scan] replay after the scan: %.2f ms (%zu hits)\n", dt, res->hits.size());
         ctx->stats.host_replay_ms = dt - (ctx->stats.align_ms - align_before);
         ctx->stats.wall_ms += dt;
     } else reset();

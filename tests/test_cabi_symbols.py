@@ -4,6 +4,7 @@ No compute entry point is called here."""
 import ctypes as C
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -189,3 +190,117 @@ def test_strobemer_utility_goldens():
     counts = K.ungapped_strobe_2_mer_count(ts, s=1, w_min=2, w_max=4)
     assert round(float(np.mean(counts)), 4) == 0.3125
     assert counts[3] == 2 and counts[4] == counts[11] == counts[14] == 1
+
+
+def test_masked_runs_match_numpy(tmp_path):
+    """the masked-run list (what the extension / exact-match kernels consult instead of the ambiguity plane) against a
+    numpy scan of the same sequences: runs at record starts/ends, one-base runs, runs spanning 32-base mask words, and a
+    plane large enough for the multi-threaded slices, with one run laid across the slice edge (2^25 bases)"""
+    import kmergma_jl_b200 as K
+    rng = np.random.default_rng(4)
+    small = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=5000)].copy()
+    for a, b in ((0, 1), (5, 6), (31, 33), (64, 128), (200, 263), (1000, 1001), (4990, 5000)):
+        small[a:b] = ord("N")
+    big = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=(1 << 25) + 300_000)].copy()
+    big[(1 << 25) - 70_000:(1 << 25) + 41] = ord("N")              # crosses the slice edge whatever the record offset is
+    big[:7] = ord("N"); big[-1:] = ord("N"); big[12345:12346] = ord("R")
+    for s in rng.integers(100_000, big.size - 100_000, size=200):
+        big[s:s + int(rng.integers(1, 200))] = ord("N")
+    recs = [("a", small.tobytes().decode()), ("empty", ""), ("b", big.tobytes().decode()), ("c", "NNNN"), ("d", "ACGT")]
+    g = K.Genome.from_records(recs)
+    got = g.masked_runs()
+    want = []
+    for r, (_, s) in enumerate(recs):
+        v = np.frombuffer(s.encode(), np.uint8)
+        m = np.concatenate([[0], (~np.isin(v, np.frombuffer(b"ACGT", np.uint8))).astype(np.int8), [0]])
+        d = np.diff(m)
+        off = g.record_offset(r)
+        want += [(off + int(a), off + int(b)) for a, b in zip(np.flatnonzero(d == 1), np.flatnonzero(d == -1))]
+    assert got.tolist() == [list(w) for w in want]
+    # through the FASTA ingest as well
+    p = tmp_path / "m.fasta"
+    with open(p, "w") as fh:
+        for d_, s in recs:
+            fh.write(">" + d_ + "\n" + s + "\n")
+    g2 = K.Genome.from_fasta(str(p))
+    assert g2.masked_runs().tolist() == got.tolist()
+
+
+def _random_fasta(path, seed):
+    """messy FASTA text: random line widths, LF / CRLF, blank lines, lower case stretches, N runs, IUPAC codes, spaces and
+    tabs inside sequence lines, records of 0 .. a few MB (several 4 MB packing tasks), with or without a final newline"""
+    rng = np.random.default_rng(seed)
+    recs = []
+    with open(path, "wb") as fh:
+        for r in range(int(rng.integers(1, 6))):
+            L = int(rng.choice([0, 1, 31, 32, 33, 1000, int(rng.integers(1, 200_000)), int(rng.integers(4_000_000, 9_000_000))]))
+            s = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=L)].copy()
+            for _ in range(int(rng.integers(0, 12))):
+                if L < 2:
+                    break
+                a = int(rng.integers(0, L)); n = int(rng.choice([1, 2, 15, 16, 17, 31, 32, 33, 64, 1000, 70000]))
+                kind = int(rng.integers(0, 3))
+                if kind == 0:
+                    s[a:a + n] = ord("N")
+                elif kind == 1:
+                    s[a:a + n] |= 0x20
+                else:
+                    s[a:a + min(n, 3)] = np.frombuffer(b"RYK", np.uint8)[:len(s[a:a + min(n, 3)])]
+            eol = b"\r\n" if rng.random() < 0.3 else b"\n"
+            width = int(rng.choice([1, 7, 31, 32, 33, 60, 64, 70, 80, 1000]))
+            fh.write(b">rec%d desc %d" % (r, seed) + eol)
+            text = s.tobytes()
+            pieces = []
+            for a in range(0, L, width):
+                line = text[a:a + width]
+                if rng.random() < 0.002 and len(line) > 4:
+                    line = line[:2] + b" \t" + line[2:]                  # white space inside a sequence line is skipped
+                pieces.append(line + eol)
+                if rng.random() < 0.001:
+                    pieces.append(eol)
+            fh.write(b"".join(pieces))
+            want = "".join(c if c in "ACGTN" else "?" for c in text.decode().upper())
+            recs.append(want)
+        if rng.random() < 0.5:
+            fh.seek(0, 2)
+            if fh.tell() > 0:
+                fh.seek(-1, 2); fh.truncate()
+    return recs
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fasta_ingest_vectorised_and_portable_paths(tmp_path, seed):
+    """the AVX2 packing pass and the portable one (KGMA_NO_AVX2, run in a child process: the choice is made once per
+    process) produce the same container: sequences, lengths, masked runs"""
+    import hashlib
+    import subprocess
+    import kmergma_jl_b200 as K
+    p = str(tmp_path / "messy.fasta")
+    want = _random_fasta(p, seed)
+    # a final line cut by the truncation above may have lost its last byte: re-derive the expectation from the file itself
+    text = open(p, "rb").read().decode()
+    want = ["".join(c if c in "ACGTN" else "?" for c in "".join(body.split("\n")[1:]).replace("\r", "").replace(" ", "").replace("\t", "").upper())
+            for body in text.split(">")[1:]]
+    g = K.Genome.from_fasta(p)
+    assert len(g) == len(want)
+    for r, w in enumerate(want):
+        assert g.seqsize(r) == len(w)
+        assert g.seq(r) == w
+    runs = g.masked_runs()
+    ref = []
+    for r, w in enumerate(want):
+        v = np.frombuffer(w.encode(), np.uint8)
+        m = np.concatenate([[0], (~np.isin(v, np.frombuffer(b"ACGT", np.uint8))).astype(np.int8), [0]])
+        d = np.diff(m)
+        off = g.record_offset(r)
+        for a, b in zip(np.flatnonzero(d == 1), np.flatnonzero(d == -1)):
+            if ref and ref[-1][1] == off + int(a):
+                ref[-1][1] = off + int(b)
+            else:
+                ref.append([off + int(a), off + int(b)])
+    assert runs.tolist() == ref
+    digest = hashlib.sha256(("|".join(g.seq(r) for r in range(len(g)))).encode() + runs.tobytes()).hexdigest()
+    code = ("import sys, hashlib; sys.path.insert(0, %r); import kmergma_jl_b200 as K; g = K.Genome.from_fasta(%r); "
+            "print(hashlib.sha256(('|'.join(g.seq(r) for r in range(len(g)))).encode() + g.masked_runs().tobytes()).hexdigest())") % (ROOT, p)
+    out = subprocess.check_output([sys.executable, "-c", code], env=dict(os.environ, KGMA_NO_AVX2="1"), text=True).strip()
+    assert out == digest

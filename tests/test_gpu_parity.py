@@ -858,6 +858,22 @@ def test_pipelined_streaming_equals_plain(K, prof, synth, monkeypatch):
         assert len(a.hits) >= 5 and np.array_equal(a.hits[key], b.hits[key])
         ra, rb = a.runs.view(RUN_DT), b.runs.view(RUN_DT)
         assert np.array_equal(np.sort(ra, order=["record", "t_first", "flags"]), np.sort(rb, order=["record", "t_first", "flags"]))
+    # cluster mode: the first part's lazy extension rounds run on the second stream while the tail streams in
+    rvs, wss, cs, inv = K.cluster_ref_API(TF, 6)
+    rvs, wss, cs = K.eliminate_null_params(rvs, wss, cs, inv)
+    ckey = key + ["profile"]
+    for thrs in ([35, 31, 38, 34, 27, 27], [30] * 6):           # one shared prefilter table / one pass per profile
+        g = K.Genome.from_fasta(path)
+        a = K.scan_raw(g, rvs, wss, cs, thrs, 6, K.L.MODE_CLUSTER, 100, K.L.F_ALIGN, -200, -1)
+        n_align = K.default_context().stats()["n_align"]
+        monkeypatch.setenv("KGMA_NO_PIPELINE", "1")
+        b = K.scan_raw(g, rvs, wss, cs, thrs, 6, K.L.MODE_CLUSTER, 100, K.L.F_ALIGN, -200, -1)
+        monkeypatch.delenv("KGMA_NO_PIPELINE")
+        assert len(a.hits) >= 5 and np.array_equal(a.hits[ckey], b.hits[ckey])
+        assert len(set(a.hits["record"])) >= 3 and n_align == K.default_context().stats()["n_align"]
+        ra, rb = a.runs.view(RUN_DT), b.runs.view(RUN_DT)
+        so = ["profile", "record", "t_first", "flags"]
+        assert np.array_equal(np.sort(ra, order=so), np.sort(rb, order=so))
 
 
 def test_pipelined_scan_with_overflow_in_second_part(K, O, prof, tmp_path):
