@@ -688,7 +688,7 @@ struct StagedUpload {
         ctx = c; src = s; total = bytes; nsub = (bytes + SB - 1) / SB;
         filled = std::vector<std::atomic<int>>(nsub);
         for (auto &f : filled) f.store(0, std::memory_order_relaxed);
-        const int nt = (int)std::min<size_t>(nsub, std::min(4u, std::max(1u, std::thread::hardware_concurrency())));
+        const int nt = (int)std::min<size_t>(nsub, std::min(6u, std::max(1u, std::thread::hardware_concurrency() / 2)));   // (NS - 2 at most: slots must free up)
         for (int t = 0; t < nt; t++) th.emplace_back([this]() {
             cudaSetDevice(ctx->device);
             for (;;) {
