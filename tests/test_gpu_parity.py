@@ -900,6 +900,76 @@ def test_pipelined_scan_with_overflow_in_second_part(K, O, prof, tmp_path):
     assert sum(1 for h in oh if h.record == 0) >= 30 and sum(1 for h in oh if h.record == 1) >= 50
 
 
+def test_staged_first_upload_equals_page_locked(K, O, prof, tmp_path, monkeypatch):
+    """a genome ingested from FASTA text lives in pageable memory: its first scan goes through the page-locked staging
+    ring (here 45 MB of packed data, so the 8-slot ring wraps), the second page-locks the plane, later ones stream it.
+    All must agree with each other, with a scan that page-locks first (KGMA_NO_STAGING), and -- on the planted region --
+    with the oracle; cluster mode and a sharded scan go through the same upload code"""
+    RV, ws, cons = prof
+    refs = O.Fasta(TF)
+    rng = np.random.default_rng(77)
+    alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
+    lens = [70_000_000, 1_000, 60_000_000, 50_000_000]
+    path = tmp_path / "pageable.fasta"
+    planted = 0
+    with open(path, "wb") as fh:
+        for r, L in enumerate(lens):
+            s = alphabet[rng.integers(0, 4, size=L)].copy()
+            if L > 10_000:
+                s[:5000] = ord("N"); s[L // 2:L // 2 + 100_000] = ord("N")
+                for i in range(25):
+                    m = np.frombuffer(_mutate(rng, refs.seq(int(rng.integers(0, len(refs)))), 0.04, i % 3 == 0).encode(), dtype=np.uint8)
+                    p = int(rng.integers(10_000, L - 10_000))
+                    if not (L // 2 - 1000 < p < L // 2 + 101_000):
+                        s[p:p + m.size] = m; planted += 1
+            fh.write(b">rec%d pageable\n" % r)
+            body = s[:L // 100 * 100].reshape(-1, 100)
+            fh.write(np.concatenate([body, np.full((body.shape[0], 1), 10, np.uint8)], axis=1).tobytes())
+            fh.write(s[body.size:].tobytes() + b"\n")
+    key = ["record", "first", "last", "D", "genome_pos", "align_score", "cmi"]
+    ctx = K.default_context()
+
+    def scan(g, **kw):
+        return K.scan_raw(g, [RV], [ws], [cons], [30.0], 6, K.L.MODE_SINGLE, 50, K.L.F_ALIGN, -69, -1, **kw)
+
+    g = K.Genome.from_fasta(str(path))
+    first = scan(g); h2d_first = ctx.stats()["h2d_bytes"]
+    second = scan(g)
+    third = scan(g)
+    assert len(first.hits) >= planted - 5
+    assert np.array_equal(first.hits[key], second.hits[key]) and np.array_equal(first.hits[key], third.hits[key])
+    assert h2d_first >= sum(lens) // 4                                   # the whole plane did cross the bus
+    monkeypatch.setenv("KGMA_NO_STAGING", "1")
+    g2 = K.Genome.from_fasta(str(path))
+    plain = scan(g2)
+    monkeypatch.delenv("KGMA_NO_STAGING")
+    assert np.array_equal(first.hits[key], plain.hits[key])
+    # sharded run lists from a fresh pageable genome (first shard staged, the others from the page-locked plane)
+    g3 = K.Genome.from_fasta(str(path))
+    parts = [K.scan_raw(g3, [RV], [ws], [cons], [30.0], 6, K.L.MODE_SINGLE, 50, 0, -69, -1, runs_only=True, shard=(i, 3)) for i in range(3)]
+    firsts = parts[0].first_D
+    for pt in parts[1:]:
+        firsts = np.maximum(firsts, pt.first_D)
+    merged = K.replay_raw(g3, [RV], [ws], [cons], [30.0], 6, K.L.MODE_SINGLE, 50, K.L.F_ALIGN, -69, -1, np.concatenate([pt.runs for pt in parts]), firsts)
+    assert np.array_equal(first.hits[key], merged.hits[key])
+    # cluster mode, first scan of a fresh genome
+    rvs, wss, cs, inv = K.cluster_ref_API(TF, 6)
+    rvs, wss, cs = K.eliminate_null_params(rvs, wss, cs, inv)
+    thrs = [35, 31, 38, 34, 27, 27]
+    g4 = K.Genome.from_fasta(str(path))
+    ca = K.scan_raw(g4, rvs, wss, cs, thrs, 6, K.L.MODE_CLUSTER, 100, K.L.F_ALIGN, -200, -1)
+    cb = K.scan_raw(g4, rvs, wss, cs, thrs, 6, K.L.MODE_CLUSTER, 100, K.L.F_ALIGN, -200, -1)
+    ckey = key + ["profile"]
+    assert len(ca.hits) >= planted - 5 and np.array_equal(ca.hits[ckey], cb.hits[ckey])
+    # the oracle on one planted neighbourhood of the third record (the full genome would take minutes on one core)
+    h = first.hits[first.hits["record"] == 2][0]
+    lo = max(1, int(h["first"]) - 3000); hi = min(lens[2], int(h["last"]) + 3000)
+    sub = tmp_path / "sub.fasta"
+    sub.write_text(">sub\n" + g.seq(2, lo, hi) + "\n")
+    oh = O.ac_gma_testing(str(sub), np.asarray(RV), cons, windowsize=ws, thr=30, buff=50, do_align=True)[0]
+    assert any(o.first + lo - 1 == int(h["first"]) and o.last + lo - 1 == int(h["last"]) for o in oh)
+
+
 def test_plain_c_client(tmp_path):
     """examples/findgenes.c: the C ABI used from plain C (gcc, no Python in the call path) reproduces the reference's golden
     hits on Alp_V_locus (test-KmerGMA.jl:257-263: 6852:7140, 23907:24201, 33845:34133)"""
