@@ -113,6 +113,7 @@ class Genome:
 
     def __init__(self, handle, lib):
         self._h, self._lib = handle, lib
+        self._resident_ctx = None          # the Context whose GPU was last asked to hold this genome (make_resident)
 
     @classmethod
     def from_fasta(cls, path: str) -> "Genome":
@@ -205,6 +206,7 @@ class Genome:
     def make_resident(self, ctx: Optional[Context] = None):
         ctx = ctx or default_context()
         ctx.check(ctx._lib.kgma_genome_make_resident(ctx._h, self._h))
+        self._resident_ctx = ctx           # a hint only: the library re-uploads when its device copy is not this genome's
 
 
 def _as_genome(genome) -> Genome:
@@ -606,9 +608,11 @@ def ac_gma_testing(*, genome_path, refVec, consensus_refseq: str, k: int = 6, wi
     hit_loci_vec / result_align_vec / dist_vec in place and returns the raw ScanOutput.
     `mask`, `Nt_bits`, `ScaleFactor` are accepted for signature parity (they are functions of k)."""
     resultVec = [] if resultVec is None else resultVec
+    ctx = ctx or default_context()
     g = _as_genome(genome_path)
     flags = (L.F_ALIGN if do_align else 0) | (L.F_WANT_DISTS if do_return_dists else 0) | \
-            (L.F_WANT_CIGARS if (do_align and do_return_align) else 0) | (L.F_DENSE if dense else 0)
+            (L.F_WANT_CIGARS if (do_align and do_return_align) else 0) | (L.F_DENSE if dense else 0) | \
+            (L.F_RESIDENT if g._resident_ctx is ctx else 0)
     out = scan_raw(g, [refVec], [windowsize], [consensus_refseq], [thr], k, L.MODE_SINGLE, buff, flags,
                    gap_open_score, gap_extend_score, ctx=ctx)
     _emit(g, out, False, resultVec, hit_loci_vec if get_hit_loci else None,
@@ -642,10 +646,12 @@ def Omn_KmerGMA(*, genome_path, refVecs, windowsizes, consensus_seqs, resultVec:
                 do_return_dists: bool = False, dist_vec_vec: Optional[List[list]] = None,
                 dense: bool = False, ctx: Optional[Context] = None):
     """Omn_KmerGMA! (src/OmnGenomeMiner.jl:7-162): C profiles scanned together."""
+    ctx = ctx or default_context()
     g = _as_genome(genome_path)
     Cn = len(windowsizes)
     flags = (L.F_ALIGN if align_hits else 0) | (L.F_WANT_DISTS if do_return_dists else 0) | \
-            (L.F_WANT_CIGARS if (align_hits and get_aligns) else 0) | (L.F_DENSE if dense else 0)
+            (L.F_WANT_CIGARS if (align_hits and get_aligns) else 0) | (L.F_DENSE if dense else 0) | \
+            (L.F_RESIDENT if g._resident_ctx is ctx else 0)
     out = scan_raw(g, list(refVecs)[:Cn], windowsizes, list(consensus_seqs)[:Cn], list(thr_vec)[:Cn], k,
                    L.MODE_CLUSTER, buff, flags, gap_open_score, gap_extend_score, ctx=ctx)
     if genome_pos:
@@ -805,7 +811,7 @@ def exactMatch(query, subject_seq, overlap: bool = True, ctx: Optional[Context] 
         g = _as_genome(subject_seq)
     mp = C.POINTER(L.Match)()
     n = C.c_int64()
-    ctx.check(ctx._lib.kgma_exact_match(ctx._h, g._h, q, len(q), int(overlap), L.F_RESIDENT if resident else 0,
+    ctx.check(ctx._lib.kgma_exact_match(ctx._h, g._h, q, len(q), int(overlap), L.F_RESIDENT if (resident or g._resident_ctx is ctx) else 0,
                                         C.byref(mp), C.byref(n)))
     by_rec: Dict[int, List[Tuple[int, int]]] = {}
     for i in range(n.value):

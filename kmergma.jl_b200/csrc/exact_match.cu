@@ -219,13 +219,12 @@ extern "C" int kgma_exact_match(kgma_ctx *ctx, kgma_genome *g, const char *query
     }
     int rc = dev_genome_prepare(ctx, g, qlen < 31);     // the ambiguity plane is only needed on the device for short queries
     if (rc) return rc;
-    rc = genome_pin(ctx, g);
-    if (rc) return rc;
     cudaStream_t st = ctx->s_compute, sp = ctx->s_copy;
     kgma_stats &S = ctx->stats; S = kgma_stats{};
     cudaEvent_t e0 = ctx->ev[0], e1 = ctx->ev[1], e2 = ctx->ev[2], ek = ctx->ev[3];
     const size_t bases = (size_t)(g->G + TAIL_PAD);
     const bool have = (flags & KGMA_F_RESIDENT) && ctx->d_seq_valid && ctx->d_valid_lo == 0 && ctx->d_valid_hi >= (int64_t)bases;
+    if (!have) { rc = genome_pin(ctx, g); if (rc) return rc; }   // a resident genome is not read from the host at all
     // sampling stride in 16-base words: the largest of 8,4,2,1 with qlen >= 16*sw + 15 (0: short query, dense compare)
     int sw = 0;
     for (int c = 8; c >= 1; c >>= 1) if (qlen >= 16 * c + 15) { sw = c; break; }

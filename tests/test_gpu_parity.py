@@ -970,6 +970,25 @@ def test_staged_first_upload_equals_page_locked(K, O, prof, tmp_path, monkeypatc
     assert any(o.first + lo - 1 == int(h["first"]) and o.last + lo - 1 == int(h["last"]) for o in oh)
 
 
+def test_resident_genome_through_the_operator_mirror(K, O, prof, synth):
+    """a Genome made resident once is scanned by the operator mirror with KGMA_F_RESIDENT (tables and jobs are all that
+    crosses the bus); exact match on it needs no page-locking, and a short query fetches the ambiguity plane on demand"""
+    path, recs = synth
+    RV, ws, cons = prof
+    ctx = K.default_context()
+    g = K.Genome.from_fasta(path)
+    g.make_resident(ctx)
+    res_a, res_b = [], []
+    K.ac_gma_testing(genome_path=g, refVec=RV, consensus_refseq=cons, windowsize=ws, thr=30, do_align=True, resultVec=res_a, ctx=ctx)
+    assert ctx.stats()["h2d_bytes"] < 2_000_000
+    K.ac_gma_testing(genome_path=path, refVec=RV, consensus_refseq=cons, windowsize=ws, thr=30, do_align=True, resultVec=res_b, ctx=ctx)
+    assert len(res_a) >= 8 and descs(res_a) == descs(res_b)
+    g.make_resident(ctx)
+    body = recs[3][1]
+    for q in (body[5000:5300], body[7000:7020], "N" * 40):
+        assert K.exactMatch(q, g, ctx=ctx) == O.exactMatch(q, O.Fasta(path))
+
+
 def test_plain_c_client(tmp_path):
     """examples/findgenes.c: the C ABI used from plain C (gcc, no Python in the call path) reproduces the reference's golden
     hits on Alp_V_locus (test-KmerGMA.jl:257-263: 6852:7140, 23907:24201, 33845:34133)"""
