@@ -48,7 +48,7 @@ struct kgma_genome {
     std::string err;
     std::vector<int64_t> nruns;    // cache: maximal runs of masked bases, [start,end) global positions (genome_nruns)
     uint64_t  nruns_uid = 0;
-    int       n_uploads = 0;       // streamed uploads so far: the first goes through the staging ring, the second page-locks the plane
+    int       n_uploads = 0;       // streamed uploads so far: the first three go through the staging ring, the fourth page-locks the plane
 };
 
 struct kgma_refs {

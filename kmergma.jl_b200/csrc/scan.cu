@@ -656,7 +656,7 @@ using namespace kgma;
 // pins page by page) and a plain cudaMemcpy from pageable memory runs at ~10 GB/s through the driver's own single-threaded
 // staging; here a few host threads copy 4 MB pieces into a small page-locked ring and the calling thread queues one
 // asynchronous copy per piece as it becomes ready, which keeps the link busy while the prefilter chases the data as usual.
-// A genome that is scanned again is page-locked then (kgma_genome::n_uploads), when the cost is worth paying.
+// A genome that keeps being streamed is page-locked on its fourth upload (kgma_genome::n_uploads), when the cost is worth paying.
 struct StagedUpload {
     static constexpr int NS = 8;                           // ring slots
     static constexpr size_t SB = (size_t)4 << 20;          // bytes per slot
@@ -908,7 +908,9 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     // evaluation ends on the next multiple of 32 blocks (its launches work in whole warp groups), which only means a few
     // blocks of the second part are filtered early.
     // page-locked source, or (first upload of a pageable genome) the staging ring; a resident genome is not touched at all
-    const bool staged = !resident_ok && !g->pinned && g->n_uploads == 0 && !getenv("KGMA_NO_STAGING");
+    // (page-locking costs 14-150 ms for 772 MB depending on how many huge pages the kernel could hand out; a staged upload costs
+    //  ~10-20 ms more than a page-locked one: lock once the genome has been streamed three times and is clearly being reused)
+    const bool staged = !resident_ok && !g->pinned && g->n_uploads < 3 && !getenv("KGMA_NO_STAGING");
     if (!resident_ok) {
         rc = staged ? StagedUpload::prepare_ring(ctx) : genome_pin(ctx, g);
         if (rc) return rc;
