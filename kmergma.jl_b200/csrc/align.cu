@@ -438,9 +438,14 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     if (!bcodes.empty()) memcpy(h + o_b, bcodes.data(), bcodes.size());
     memcpy(h + o_j, jobs.data(), (size_t)nj * sizeof(AlignJob2));
     if (!nruns.empty()) memcpy(h + o_n, nruns.data(), nruns.size() * 8);
+    // Two ways to move the batch.  Next to a streaming scan (the pipelined parts run on s_align) the copy engine is busy with
+    // 32 MB genome chunks and a small copy queued behind one waits ~0.6 ms, so the jobs are fetched by a kernel and the
+    // results written in place into the mapped block.  Otherwise plain asynchronous copies are at least as fast.
+    const bool in_place = st == ctx->s_align;
     void *h_dev = nullptr;                                     // device-side address of the staging block (same as h under UVA)
-    KGMA_CUDA(ctx, cudaHostGetDevicePointer(&h_dev, h, 0));
-    {
+    if (in_place) KGMA_CUDA(ctx, cudaHostGetDevicePointer(&h_dev, h, 0));
+    if (!in_place) KGMA_CUDA(ctx, cudaMemcpyAsync(d, h, up, cudaMemcpyHostToDevice, st));
+    else {
         const size_t n16 = up / 16;                            // (carve rounds every piece to 256 bytes)
         const int cgrid = (int)std::min<size_t>((n16 + 255) / 256, (size_t)ctx->num_sms * 4);
         kgma_fetch_host<<<std::max(cgrid, 1), 256, 0, st>>>((uint4 *)d, (const uint4 *)h_dev, n16);
@@ -453,7 +458,7 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     A.a = d + o_a; A.seq = ctx->d_seq2; A.nruns = (const long long *)(d + o_n); A.n_nruns = (int)(nruns.size() / 2);
     A.b = d + o_b; A.jobs = (const AlignJob2 *)(d + o_j); A.njobs = nj; A.next_job = (int *)(d + o_c);
     // results are written straight into the page-locked block (16 bytes per alignment, posted writes): no copy back
-    A.out = (AlignOut *)((unsigned char *)h_dev + up); A.go = -gap_open; A.ge = -gap_extend; A.tie_open = tie_open ? 1 : 0; A.ncol_cap = ncol;
+    A.out = in_place ? (AlignOut *)((unsigned char *)h_dev + up) : (AlignOut *)(d + o_o); A.go = -gap_open; A.ge = -gap_extend; A.tie_open = tie_open ? 1 : 0; A.ncol_cap = ncol;
     A.need_boundary = need_boundary ? 1 : 0;
     KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -465,6 +470,7 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     KGMA_CUDA(ctx, cudaEventRecord(ctx->a_ev1[slot], st));
     ctx->stats.launches++;
     AlignOut *ho = (AlignOut *)(h + up);
+    if (!in_place) KGMA_CUDA(ctx, cudaMemcpyAsync(ho, d + o_o, (size_t)nj * sizeof(AlignOut), cudaMemcpyDeviceToHost, st));
     KGMA_CUDA(ctx, cudaEventRecord(ctx->a_done[slot], st));
     ctx->stats.d2h_bytes += (size_t)nj * sizeof(AlignOut);
     t->active = true; t->slot = slot; t->nj = nj; t->ho = ho;

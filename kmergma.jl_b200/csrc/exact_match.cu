@@ -9,6 +9,7 @@
 // Overlap / non-overlap selection is a host pass over the sorted starts (FindAll resumes at match_end+1,
 // FindAllOverlap at match_start+1).  The 2-bit plane is streamed in chunks with the search chasing the copy.
 #include "kgma_internal.h"
+#include "staged_upload.h"
 #include <algorithm>
 
 namespace kgma {
@@ -224,7 +225,9 @@ extern "C" int kgma_exact_match(kgma_ctx *ctx, kgma_genome *g, const char *query
     cudaEvent_t e0 = ctx->ev[0], e1 = ctx->ev[1], e2 = ctx->ev[2], ek = ctx->ev[3];
     const size_t bases = (size_t)(g->G + TAIL_PAD);
     const bool have = (flags & KGMA_F_RESIDENT) && ctx->d_seq_valid && ctx->d_valid_lo == 0 && ctx->d_valid_hi >= (int64_t)bases;
-    if (!have) { rc = genome_pin(ctx, g); if (rc) return rc; }   // a resident genome is not read from the host at all
+    // a resident genome is not read from the host at all; a pageable one goes through the staging ring (scan.cu)
+    const bool staged = !have && !g->pinned && !getenv("KGMA_NO_STAGING");
+    if (!have) { rc = staged ? StagedUpload::prepare_ring(ctx) : genome_pin(ctx, g); if (rc) return rc; }
     // sampling stride in 16-base words: the largest of 8,4,2,1 with qlen >= 16*sw + 15 (0: short query, dense compare)
     int sw = 0;
     for (int c = 8; c >= 1; c >>= 1) if (qlen >= 16 * c + 15) { sw = c; break; }
@@ -300,8 +303,16 @@ extern "C" int kgma_exact_match(kgma_ctx *ctx, kgma_genome *g, const char *query
         KGMA_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
         KGMA_CUDA(ctx, cudaStreamWaitEvent(sp, ctx->ev[7], 0));
         const int64_t CH = (int64_t)128 << 20; int ci = 0;
+        StagedUpload stager;                                       // (its destructor joins the copy threads on every exit path)
+        if (staged) stager.start(ctx, (const char *)g->seq2, bases / 4);
         for (int64_t lo = 0; lo < (int64_t)bases; lo += CH, ci++) {
             const int64_t hi = std::min<int64_t>((int64_t)bases, lo + CH);
+            if (staged) {
+                const size_t j0 = (size_t)(lo / 4) / StagedUpload::SB;
+                const size_t j1 = hi >= (int64_t)bases ? stager.nsub : (size_t)(hi / 4) / StagedUpload::SB;
+                rc = stager.issue(j0, j1, (char *)ctx->d_seq2, sp);
+                if (rc) return rc;
+            } else
             KGMA_CUDA(ctx, cudaMemcpyAsync((char *)ctx->d_seq2 + lo / 4, (char *)g->seq2 + lo / 4, (size_t)(hi - lo) / 4, cudaMemcpyHostToDevice, sp));
             KGMA_CUDA(ctx, cudaEventRecord(e_c[ci & 1], sp));
             KGMA_CUDA(ctx, cudaStreamWaitEvent(st, e_c[ci & 1], 0));

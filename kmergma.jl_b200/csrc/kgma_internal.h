@@ -48,7 +48,6 @@ struct kgma_genome {
     std::string err;
     std::vector<int64_t> nruns;    // cache: maximal runs of masked bases, [start,end) global positions (genome_nruns)
     uint64_t  nruns_uid = 0;
-    int       n_uploads = 0;       // streamed uploads so far: the first three go through the staging ring, the fourth page-locks the plane
 };
 
 struct kgma_refs {
@@ -89,7 +88,7 @@ struct kgma_ctx {
     cudaEvent_t a_ev0[2] = {}, a_ev1[2] = {}, a_done[2] = {};
     std::vector<cudaEvent_t> chunk_ev;             // one event per streamed chunk (pipelined scan)
     // staging ring for the first upload of a genome whose planes are not page-locked (scan.cu: StagedUpload)
-    void *stage = nullptr; size_t stage_bytes = 0; cudaEvent_t stage_ev[8] = { nullptr };
+    void *stage = nullptr; size_t stage_bytes = 0; cudaEvent_t stage_ev[16] = { nullptr };
     // scratch
     void     *d_scratch = nullptr; size_t d_scratch_bytes = 0;
     void     *h_scratch = nullptr; size_t h_scratch_bytes = 0;   // pinned

@@ -29,6 +29,7 @@
 #include <atomic>
 #include <thread>
 #include <sys/mman.h>
+#include "staged_upload.h"
 
 namespace kgma {
 
@@ -652,72 +653,6 @@ constexpr long long NO_D = (long long)0x8080808080808080ull;   // cudaMemset(0x8
 
 using namespace kgma;
 
-// First upload of a genome whose packed plane is ordinary pageable memory.  Page-locking 772 MB costs ~100 ms (the driver
-// pins page by page) and a plain cudaMemcpy from pageable memory runs at ~10 GB/s through the driver's own single-threaded
-// staging; here a few host threads copy 4 MB pieces into a small page-locked ring and the calling thread queues one
-// asynchronous copy per piece as it becomes ready, which keeps the link busy while the prefilter chases the data as usual.
-// A genome that keeps being streamed is page-locked on its fourth upload (kgma_genome::n_uploads), when the cost is worth paying.
-struct StagedUpload {
-    static constexpr int NS = 8;                           // ring slots
-    static constexpr size_t SB = (size_t)4 << 20;          // bytes per slot
-    kgma_ctx *ctx = nullptr;
-    const char *src = nullptr; size_t total = 0, nsub = 0;
-    std::atomic<size_t> next{0}, issued{0};
-    std::vector<std::atomic<int>> filled;
-    std::atomic<bool> abort{false};
-    std::vector<std::thread> th;
-
-    static int prepare_ring(kgma_ctx *ctx)
-    {
-        if (ctx->stage) return KGMA_OK;
-        const size_t bytes = NS * SB;
-        void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-        if (p == MAP_FAILED) return set_err(ctx, KGMA_E_CAPACITY, "staging ring allocation failed");
-        madvise(p, bytes, MADV_HUGEPAGE);
-        memset(p, 0, bytes);
-        if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) {
-            cudaGetLastError(); munmap(p, bytes);
-            return set_err(ctx, KGMA_E_CUDA, "cudaHostRegister of the staging ring failed");
-        }
-        ctx->stage = p; ctx->stage_bytes = bytes;
-        for (auto &e : ctx->stage_ev) KGMA_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        return KGMA_OK;
-    }
-    void start(kgma_ctx *c, const char *s, size_t bytes)
-    {
-        ctx = c; src = s; total = bytes; nsub = (bytes + SB - 1) / SB;
-        filled = std::vector<std::atomic<int>>(nsub);
-        for (auto &f : filled) f.store(0, std::memory_order_relaxed);
-        const int nt = (int)std::min<size_t>(nsub, std::min(6u, std::max(1u, std::thread::hardware_concurrency() / 2)));   // (NS - 2 at most: slots must free up)
-        for (int t = 0; t < nt; t++) th.emplace_back([this]() {
-            cudaSetDevice(ctx->device);
-            for (;;) {
-                const size_t j = next.fetch_add(1);
-                if (j >= nsub) return;
-                if (j >= (size_t)NS) {                     // the slot's previous piece must have left for the device
-                    while (issued.load(std::memory_order_acquire) < j - NS + 1) { if (abort.load()) return; std::this_thread::yield(); }
-                    cudaEventSynchronize(ctx->stage_ev[j % NS]);
-                }
-                if (abort.load()) return;
-                memcpy((char *)ctx->stage + (j % NS) * SB, src + j * SB, std::min(SB, total - j * SB));
-                filled[j].store(1, std::memory_order_release);
-            }
-        });
-    }
-    // queue pieces [j0, j1) on the copy stream, in order, as the workers deliver them
-    int issue(size_t j0, size_t j1, char *dst, cudaStream_t sp)
-    {
-        for (size_t j = j0; j < j1; j++) {
-            while (!filled[j].load(std::memory_order_acquire)) std::this_thread::yield();
-            KGMA_CUDA(ctx, cudaMemcpyAsync(dst + j * SB, (char *)ctx->stage + (j % NS) * SB, std::min(SB, total - j * SB), cudaMemcpyHostToDevice, sp));
-            KGMA_CUDA(ctx, cudaEventRecord(ctx->stage_ev[j % NS], sp));
-            issued.store(j + 1, std::memory_order_release);
-        }
-        return KGMA_OK;
-    }
-    ~StagedUpload() { abort.store(true); for (auto &t : th) t.join(); }
-};
-
 // Pipelined streaming scan: records [0, rec_split) are evaluated as soon as their last block has been
 // filtered; on_first_part is called with their runs while the rest of the genome is still being copied and filtered.
 struct PhaseHook {
@@ -908,13 +843,13 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     // evaluation ends on the next multiple of 32 blocks (its launches work in whole warp groups), which only means a few
     // blocks of the second part are filtered early.
     // page-locked source, or (first upload of a pageable genome) the staging ring; a resident genome is not touched at all
-    // (page-locking costs 14-150 ms for 772 MB depending on how many huge pages the kernel could hand out; a staged upload costs
-    //  ~10-20 ms more than a page-locked one: lock once the genome has been streamed three times and is clearly being reused)
-    const bool staged = !resident_ok && !g->pinned && g->n_uploads < 3 && !getenv("KGMA_NO_STAGING");
+    // (page-locking 772 MB was measured anywhere between 14 and 380 ms on the same box, depending on how many huge pages the
+    //  kernel could hand out; a staged upload costs ~2.5 ms more per scan than a page-locked one, so pageable genomes are
+    //  always staged and only an explicit kgma_genome_make_resident / exact match page-locks)
+    const bool staged = !resident_ok && !g->pinned && !getenv("KGMA_NO_STAGING");
     if (!resident_ok) {
         rc = staged ? StagedUpload::prepare_ring(ctx) : genome_pin(ctx, g);
         if (rc) return rc;
-        g->n_uploads++;
     }
     int64_t split_blk = -1, split_blk_f = -1;
     bool pipelined = hook && !resident_ok && !staged && any_filter && !any_dense && sc == 1 && nr > 1 &&
@@ -1303,11 +1238,22 @@ int kgma_genome_make_resident(kgma_ctx *ctx, kgma_genome *g)
     KGMA_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = dev_genome_prepare(ctx, g, false);
     if (rc) return rc;
-    rc = genome_pin(ctx, g);
-    if (rc) return rc;
     size_t bases = (size_t)(g->G + TAIL_PAD);
-    KGMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_seq2, g->seq2, bases / 4, cudaMemcpyHostToDevice, ctx->s_compute));
-    KGMA_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    if (!g->pinned && !getenv("KGMA_NO_STAGING")) {
+        // pageable planes (FASTA / append ingest): through the staging ring, no page-locking (see StagedUpload)
+        rc = StagedUpload::prepare_ring(ctx);
+        if (rc) return rc;
+        StagedUpload stager;
+        stager.start(ctx, (const char *)g->seq2, bases / 4);
+        rc = stager.issue(0, stager.nsub, (char *)ctx->d_seq2, ctx->s_copy);
+        if (rc) return rc;
+        KGMA_CUDA(ctx, cudaStreamSynchronize(ctx->s_copy));
+    } else {
+        rc = genome_pin(ctx, g);
+        if (rc) return rc;
+        KGMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_seq2, g->seq2, bases / 4, cudaMemcpyHostToDevice, ctx->s_compute));
+        KGMA_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    }
     ctx->d_seq_valid = true; ctx->d_mask_valid = false; ctx->d_valid_lo = 0; ctx->d_valid_hi = g->G + TAIL_PAD;
     ctx->d_have_lo = 0; ctx->d_have_hi = g->G + TAIL_PAD;
     return KGMA_OK;

@@ -902,7 +902,7 @@ def test_pipelined_scan_with_overflow_in_second_part(K, O, prof, tmp_path):
 
 def test_staged_first_upload_equals_page_locked(K, O, prof, tmp_path, monkeypatch):
     """a genome ingested from FASTA text lives in pageable memory: its first scan goes through the page-locked staging
-    ring (here 45 MB of packed data, so the 8-slot ring wraps), the fourth page-locks the plane, later ones stream it.
+    ring (here 45 MB of packed data, so the 16 MB ring wraps), and so does every later one.
     All must agree with each other, with a scan that page-locks first (KGMA_NO_STAGING), and -- on the planted region --
     with the oracle; cluster mode and a sharded scan go through the same upload code"""
     RV, ws, cons = prof
@@ -934,7 +934,7 @@ def test_staged_first_upload_equals_page_locked(K, O, prof, tmp_path, monkeypatc
 
     g = K.Genome.from_fasta(str(path))
     first = scan(g); h2d_first = ctx.stats()["h2d_bytes"]
-    later = [scan(g) for _ in range(4)]                                  # three staged uploads, then the plane is page-locked
+    later = [scan(g) for _ in range(2)]
     assert len(first.hits) >= planted - 5
     assert all(np.array_equal(first.hits[key], o.hits[key]) for o in later)
     assert h2d_first >= sum(lens) // 4                                   # the whole plane did cross the bus
