@@ -342,13 +342,21 @@ def run_ours(args):
         out = None
         for _ in range(args.steps):
             out = step(True)
+        torch.cuda.synchronize()
+        dt_own = time.perf_counter() - t0                # this rank's own loop (diagnostic: shows which rank the max comes from)
         barrier()
         dt = time.perf_counter() - t0
         stop.set(); th.join()
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        own = [dt_own / args.steps * 1e3]
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), out, summarise_clocks(samples), {k_: v / args.steps for k_, v in agg.items()}
+            tl = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+            dist.all_gather(tl, torch.tensor([own[0]], dtype=torch.float64, device="cuda"))
+            own = [float(x.item()) for x in tl]
+        per = {k_: v / args.steps for k_, v in agg.items()}
+        per["per_rank_ms_per_step"] = own
+        return float(t.item()), out, summarise_clocks(samples), per
 
     def allsum(vals):
         if world == 1:
@@ -409,6 +417,8 @@ def run_ours(args):
                                    "scan_total": a_res["total_ms"], "e2e_h2d": a_e2e["h2d_ms"]},
             "host_ms_per_step": {"call_wall": a_res["wall_ms"], "setup": a_res["host_setup_ms"], "results": a_res["host_cand_ms"],
                                  "replay": a_res["host_replay_ms"], "e2e_call_wall": a_e2e["wall_ms"]},
+            "per_rank_ms_per_step": {"resident": a_res["per_rank_ms_per_step"], "e2e": a_e2e["per_rank_ms_per_step"],
+                                     "note": "each rank's own timed loop before the closing barrier; ms_per_step is the max incl. the barrier"},
             "roofline": {"bound": "hbm", "kernel": "kgma_prefilter<6>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": 783.9e6 if args.scale == 1.0 else None,
                          "traffic_source": "ncu --set full, profiles/r1_prefilter_ncu_full_summary.csv (dram read+write per launch)",
