@@ -988,6 +988,29 @@ def test_resident_genome_through_the_operator_mirror(K, O, prof, synth):
         assert K.exactMatch(q, g, ctx=ctx) == O.exactMatch(q, O.Fasta(path))
 
 
+def test_two_contexts_share_nothing(K, prof, synth):
+    """two contexts on the same device, used alternately on different genomes: each keeps its own device planes, tables,
+    staging ring and scratch, so neither disturbs the other's resident genome"""
+    path, recs = synth
+    RV, ws, cons = prof
+    c1, c2 = K.Context(0), K.Context(0)
+    g1, g2 = K.Genome.from_fasta(path), K.Genome.from_fasta(GENOME)
+    key = ["record", "first", "last", "D", "genome_pos", "align_score"]
+
+    def scan(g, ctx, flags):
+        return K.scan_raw(g, [RV], [ws], [cons], [30.0], 6, K.L.MODE_SINGLE, 50, K.L.F_ALIGN | flags, -69, -1, ctx=ctx)
+
+    ref1, ref2 = scan(g1, c1, 0), scan(g2, c2, 0)
+    g1.make_resident(c1); g2.make_resident(c2)
+    for _ in range(3):
+        a, b = scan(g1, c1, K.L.F_RESIDENT), scan(g2, c2, K.L.F_RESIDENT)
+        assert c1.stats()["h2d_bytes"] < 2_000_000 and c2.stats()["h2d_bytes"] < 2_000_000
+        assert np.array_equal(a.hits[key], ref1.hits[key]) and np.array_equal(b.hits[key], ref2.hits[key])
+    # the other way round: every context now has to replace its resident genome
+    a, b = scan(g2, c1, K.L.F_RESIDENT), scan(g1, c2, K.L.F_RESIDENT)
+    assert np.array_equal(a.hits[key], ref2.hits[key]) and np.array_equal(b.hits[key], ref1.hits[key])
+
+
 def test_plain_c_client(tmp_path):
     """examples/findgenes.c: the C ABI used from plain C (gcc, no Python in the call path) reproduces the reference's golden
     hits on Alp_V_locus (test-KmerGMA.jl:257-263: 6852:7140, 23907:24201, 33845:34133)"""
