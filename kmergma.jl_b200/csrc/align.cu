@@ -16,6 +16,7 @@
 // device.  kgma_align (only when CIGARs are requested): 32 rows per sweep, trace bytes packed four columns at a time
 // into 32-bit global stores, lane-0 traceback.
 #include "kgma_internal.h"
+#include <chrono>
 #include <algorithm>
 
 namespace kgma {
@@ -347,6 +348,8 @@ __global__ void kgma_fetch_host(uint4 *__restrict__ dst, const uint4 *__restrict
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 static int slot_scratch(kgma_ctx *ctx, int slot, size_t dbytes, size_t hbytes, void **d, void **h)
 {
     if (dbytes > ctx->a_dev_bytes[slot]) {
@@ -374,6 +377,8 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
 {
     *t = AlignTicket{};
     if (reqs.empty()) return KGMA_OK;
+    const bool trace = getenv("KGMA_TRACE") != nullptr;
+    const double te0 = trace ? now_ms() : 0;
     KGMA_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<uint8_t> acodes; std::vector<int32_t> a_off(n_profiles), a_len(n_profiles);
     for (int q = 0; q < n_profiles; q++) {
@@ -474,6 +479,7 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     KGMA_CUDA(ctx, cudaEventRecord(ctx->a_done[slot], st));
     ctx->stats.d2h_bytes += (size_t)nj * sizeof(AlignOut);
     t->active = true; t->slot = slot; t->nj = nj; t->ho = ho;
+    if (trace) fprintf(stderr, "[kgma align] batch of %d queued in %.3f ms of host time\n", nj, now_ms() - te0);
     return KGMA_OK;
 }
 

@@ -5,6 +5,34 @@
 namespace kgma { const char *create_err(); }
 using namespace kgma;
 
+#include <mutex>
+
+static std::mutex g_pool_mu;
+static std::vector<kgma_result *> g_pool;
+
+kgma_result *result_acquire()
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!g_pool.empty()) { kgma_result *r = g_pool.back(); g_pool.pop_back(); return r; }
+    }
+    return new kgma_result();
+}
+
+void result_release(kgma_result *r)
+{
+    if (!r) return;
+    // keep the capacity of the flat vectors, drop the per-window distance vectors (they can be GBs)
+    r->hits.clear(); r->runs.clear(); r->first_D.clear(); r->cigar_ops.clear(); r->cigar_cnt.clear();
+    std::vector<std::vector<double>>().swap(r->dists);
+    const size_t keep = r->hits.capacity() * sizeof(kgma_hit) + r->runs.capacity() * sizeof(kgma_run) + r->cigar_ops.capacity() + r->cigar_cnt.capacity() * 4;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_pool.size() < 4 && keep < ((size_t)64 << 20)) { g_pool.push_back(r); return; }
+    }
+    delete r;
+}
+
 extern "C" {
 
 int kgma_create(int device, kgma_ctx **out)
@@ -76,7 +104,7 @@ int64_t kgma_result_n_dists(const kgma_result *r, int p) { return (r && p >= 0 &
 const double *kgma_result_dists(const kgma_result *r, int p) { return (r && p >= 0 && p < (int)r->dists.size() && !r->dists[p].empty()) ? r->dists[p].data() : nullptr; }
 const char *kgma_result_cigar_ops(const kgma_result *r) { return r && !r->cigar_ops.empty() ? r->cigar_ops.data() : nullptr; }
 const int32_t *kgma_result_cigar_counts(const kgma_result *r) { return r && !r->cigar_cnt.empty() ? r->cigar_cnt.data() : nullptr; }
-void kgma_result_free(kgma_result *r) { delete r; }
+void kgma_result_free(kgma_result *r) { result_release(r); }
 void kgma_free(void *p) { free(p); }
 
 }  // extern "C"

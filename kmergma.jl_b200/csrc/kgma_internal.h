@@ -64,6 +64,11 @@ struct kgma_result {
     std::vector<int32_t>  cigar_cnt;
 };
 
+// Results are recycled through a small pool: their hit / run vectors are 100-200 KB, which malloc serves with a fresh
+// mmap (and page faults on first touch) per call -- a tenth of a millisecond on a 1.7 ms scan.
+kgma_result *result_acquire();
+void result_release(kgma_result *r);
+
 struct kgma_ctx {
     int device = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr, s_align = nullptr;

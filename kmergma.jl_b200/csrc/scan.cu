@@ -1109,10 +1109,10 @@ int kgma_scan_runs(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, 
                    const kgma_scan_params *params, kgma_result **out)
 {
     if (!ctx || !g || !params || !out) return KGMA_E_ARG;
-    kgma_result *res = new kgma_result();
+    kgma_result *res = result_acquire();
     ScanPlan pl;
     int rc = scan_runs_retry(ctx, g, profiles, n_profiles, *params, pl, res);
-    if (rc) { delete res; return rc; }
+    if (rc) { result_release(res); return rc; }
     *out = res;
     return KGMA_OK;
 }
@@ -1127,12 +1127,12 @@ int kgma_replay(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int
     ScanPlan pl;
     int rc = make_plan(ctx, g, profiles, n_profiles, *params, pl);
     if (rc) return rc;
-    kgma_result *res = new kgma_result();
+    kgma_result *res = result_acquire();
     res->runs.assign(runs, runs + n_runs);
     std::vector<int64_t> fd(first_window_D, first_window_D + (size_t)n_profiles * g->recs.size());
     res->first_D = fd;
     rc = replay(ctx, g, pl.tabs, profiles, *params, res->runs, fd, res);
-    if (rc) { delete res; return rc; }
+    if (rc) { result_release(res); return rc; }
     *out = res;
     return KGMA_OK;
 }
@@ -1142,7 +1142,7 @@ int kgma_scan(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int n
 {
     if (!ctx || !g || !params || !out) return KGMA_E_ARG;
     kgma_scan_params P = *params; P.shard_index = 0; P.shard_count = 1;
-    kgma_result *res = new kgma_result();
+    kgma_result *res = result_acquire();
     ScanPlan pl;
 
     // Pipelined form of the streamed scan with extension: the records in front of a split point are replayed and extended
@@ -1226,7 +1226,7 @@ int kgma_scan(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int n
         ctx->stats.host_replay_ms = dt - (ctx->stats.align_ms - align_before);
         ctx->stats.wall_ms += dt;
     } else reset();
-    if (rc) { delete res; return rc; }
+    if (rc) { result_release(res); return rc; }
     *out = res;
     return KGMA_OK;
 }
