@@ -83,4 +83,6 @@ def test_host_replay_of_scrambled_run_lists(tmp_path, seed):
 
 def test_host_replay_cases_were_not_vacuous():
     """(runs after the parametrised cases above) most of them must have produced hits to compare"""
-    assert len(_HITS_SEEN) == 8 and sum(1 for n in _HITS_SEEN if n >= 3) >= 5, _HITS_SEEN
+    if len(_HITS_SEEN) < 8:
+        pytest.skip("the parametrised cases did not all run in this process")
+    assert sum(1 for n in _HITS_SEEN if n >= 3) >= 5, _HITS_SEEN
