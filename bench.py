@@ -111,13 +111,29 @@ def plant_list(lens, n_plants=N_PLANTS, seed=1234):
     return out
 
 
+_NVML = {}
+
+
+def nvml_handle(device_index):
+    """NVML is initialised once, outside every timed region (nvmlInit alone takes tens of milliseconds)"""
+    if device_index not in _NVML:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            _NVML[device_index] = (pynvml, h, pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM), None)
+        except Exception as e:       # clocks are evidence, not a dependency
+            _NVML[device_index] = (None, None, None, str(e))
+    return _NVML[device_index]
+
+
 def clocks_sampler(device_index, stop, samples):
     """sample SM clock + throttle reasons while the timed region runs (B200_PROFILING.md clocks line)"""
+    pynvml, h, mx, err = nvml_handle(device_index)
+    if pynvml is None:
+        samples.append(("error", err, 0))
+        return
     try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
-        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
         while not stop.is_set():
             sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
             try:
@@ -126,7 +142,7 @@ def clocks_sampler(device_index, stop, samples):
                 rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
             samples.append((sm, mx, int(rs)))
             time.sleep(0.002)
-    except Exception as e:       # clocks are evidence, not a dependency
+    except Exception as e:
         samples.append(("error", str(e), 0))
 
 
@@ -335,6 +351,7 @@ def run_ours(args):
         for _ in range(args.warmup):
             step(False)
         stop, samples = threading.Event(), []
+        nvml_handle(local)                               # (initialised before the timed region)
         th = threading.Thread(target=clocks_sampler, args=(local, stop, samples), daemon=True)
         barrier()
         th.start()
