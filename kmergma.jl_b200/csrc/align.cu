@@ -9,7 +9,8 @@
 // match > delete (consumes b) > insert (consumes a); on exact open/extend ties the gap is extended
 // unless KGMA_F_TIE_OPEN (BioAlignments' own tie rule is not pinned by any reference test).
 //
-// Two kernels.  kgma_align_summary<R> (the default): each lane owns R = 10 consecutive DP rows in registers, lanes are
+// Three kernels.  kgma_align_pair<5>: kgma_align_summary's cell update with two warps per alignment, for small batches.
+// kgma_align_summary<R> (the default): each lane owns R = 10 consecutive DP rows in registers, lanes are
 // skewed by one column (operands of the row above arrive by __shfl_up), so one sweep of n+31 steps covers 320
 // consensus rows; instead of a trace matrix a packed summary of the canonical optimal path is carried with the
 // scores, from which cigar_to_UnitRange's two numbers follow; the subject is read from the packed genome on the
@@ -332,6 +333,155 @@ __global__ void __launch_bounds__(128, 3) kgma_align_summary(AlignArgs2 A)
     }
 }
 
+// Two warps per alignment, for batches too small to fill the machine (the rounds of the cluster-mode replay, the tail part
+// of a pipelined streamed scan): such a batch costs the latency of ONE alignment, and that latency is n+31 steps of R
+// cells.  Here warp 0 sweeps rows 1..32R and warp 1 rows 32R+1..64R of the SAME alignment at the same time, R = 5: warp 1
+// trails by 32 columns and takes the row above its first row from the per-column boundary buffer that warp 0's last lane
+// fills as it goes (the buffer the one-warp kernel uses between successive sweeps), a progress word in shared memory
+// telling it how far warp 0 has come.  n+63 steps of 5 cells instead of n+31 steps of 10.  The cell update is the
+// one-warp kernel's, verbatim.
+__device__ __forceinline__ void pair_bar(int id)                     // (immediate ids: a register id makes ptxas reserve all 16 barriers)
+{
+    if (id == 1) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory");
+}
+
+template <int R, bool TIE_OPEN>
+__global__ void __launch_bounds__(128, 4) kgma_align_pair(AlignArgs2 A)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, pair = wid >> 1, role = wid & 1;
+    const size_t per_pair = ((size_t)A.ncol_cap * (6 * 4 + 1) + 16 + 15) & ~(size_t)15;
+    unsigned char *pb = s_raw + (size_t)pair * per_pair;
+    int *ctl = reinterpret_cast<int *>(pb);                              // [0] job index, [1] last column warp 0 has delivered
+    volatile int *prog = ctl + 1;
+    int *Hb = reinterpret_cast<int *>(pb + 16), *Eb = Hb + A.ncol_cap;
+    uint32_t *sHlo = reinterpret_cast<uint32_t *>(Eb + A.ncol_cap), *sHhi = sHlo + A.ncol_cap;
+    uint32_t *bElo = sHhi + A.ncol_cap, *bEhi = bElo + A.ncol_cap;
+    uint8_t *bs = reinterpret_cast<uint8_t *>(bEhi + A.ncol_cap);
+    const int NEG = -(1 << 29);
+    const int go = A.go, ge = A.ge;
+    const int barid = 1 + pair;
+
+    for (;;) {
+        if (role == 0 && lane == 0) { ctl[0] = atomicAdd(A.next_job, 1); ctl[1] = 0; }
+        pair_bar(barid);
+        const int ji = ctl[0];
+        if (ji >= A.njobs) break;
+        const AlignJob2 J = A.jobs[ji];
+        const int m = J.m, n = J.n;
+        const uint8_t *a = A.a + J.a_off;
+        if (J.b_off >= 0) { for (int j = role * 32 + lane; j < n; j += 64) bs[j] = A.b[J.b_off + j]; }
+        else for (int j = role * 32 + lane; j < n; j += 64) {
+            const long long gp = J.gpos + j;
+            uint32_t c = (__ldg(A.seq + (gp >> 4)) >> (2 * (int)(gp & 15))) & 3u;
+            if (A.n_nruns) {
+                int lo = -1, hi = A.n_nruns;
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (A.nruns[2 * mid] <= gp) lo = mid; else hi = mid; }
+                if (lo >= 0 && gp < A.nruns[2 * lo + 1]) c = 4u;
+            }
+            bs[j] = (uint8_t)c;
+        }
+        pair_bar(barid);
+        const int nrb = (m + 32 * R - 1) / (32 * R);                      // 1 or 2 (the host only sends m <= 64 R here)
+        const int rb = role;
+        if (rb < nrb) {
+            int score = 0; PathSum sfin = { 0u, 0u };
+            const int i0 = rb * 32 * R + lane * R;
+            int H[R], F[R]; PathSum sH[R], bF[R]; uint32_t sc[R]; int gof[R], gef[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int i = i0 + r + 1;
+                H[r] = -(go + i * ge); F[r] = NEG;
+                sH[r] = ps_run((uint32_t)i, PS_I); bF[r].lo = bF[r].hi = 0;
+                const int ai = i <= m ? a[i - 1] : 0;
+                uint32_t t = (uint32_t)ai << 20;
+#pragma unroll
+                for (int c = 0; c < 5; c++) t |= (uint32_t)(edna(ai, c) + 4) << (4 * c);
+                sc[r] = t;
+                gof[r] = (i == m) ? 0 : go + ge; gef[r] = (i == m) ? 0 : ge;
+            }
+            int Hdiag0 = (i0 == 0) ? 0 : -(go + i0 * ge);
+            PathSum sHdiag0 = ps_run((uint32_t)i0, PS_I);
+            int Hout = NEG, Eout = NEG; PathSum sHout = { 0u, 0u }, bEout = { 0u, 0u };
+            const bool lane_ok = i0 < m;
+            const int gog = go + ge;
+            const uint32_t GL1 = 1u << 20, SUMM = GL1 - 1;
+            for (int s = 1; s <= n + 31; s++) {
+                const int j = s - lane;
+                if (rb == 1) {                                           // column s of the row above must have arrived
+                    if (lane == 0 && s <= n) { while (*prog < s) { } }
+                    __syncwarp();
+                }
+                int upH = __shfl_up_sync(FULL, Hout, 1), upE = __shfl_up_sync(FULL, Eout, 1);
+                PathSum supH, ubE;
+                supH.lo = __shfl_up_sync(FULL, sHout.lo, 1); supH.hi = __shfl_up_sync(FULL, sHout.hi, 1);
+                ubE.lo = __shfl_up_sync(FULL, bEout.lo, 1); ubE.hi = __shfl_up_sync(FULL, bEout.hi, 1);
+                if (lane == 0 && j >= 1 && j <= n) {
+                    if (rb == 0) { upH = 0; upE = NEG; supH = ps_run((uint32_t)j, PS_D); ubE.lo = ubE.hi = 0; }
+                    else {
+                        __threadfence_block();
+                        upH = ((volatile int *)Hb)[j]; upE = ((volatile int *)Eb)[j];
+                        supH.lo = ((volatile uint32_t *)sHlo)[j]; supH.hi = ((volatile uint32_t *)sHhi)[j];
+                        ubE.lo = ((volatile uint32_t *)bElo)[j]; ubE.hi = ((volatile uint32_t *)bEhi)[j];
+                    }
+                }
+                if (lane_ok && j >= 1 && j <= n) {
+                    const uint32_t bj = bs[j - 1];
+                    const int bsh = 4 * (int)bj;
+                    int hU = upH, eU = upE; PathSum shU = supH, beU = ubE;
+                    int hD = Hdiag0; PathSum shD = sHdiag0;
+                    Hdiag0 = upH; sHdiag0 = supH;
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const int eo = hU - gog, ee = eU - ge;
+                        const bool xe = TIE_OPEN ? (ee > eo) : (ee >= eo);
+                        const int e = xe ? ee : eo;
+                        PathSum bE; bE.lo = xe ? beU.lo : shU.lo; bE.hi = (xe ? beU.hi : shU.hi) + GL1;
+                        const int fo = H[r] - gof[r], fe = F[r] - gef[r];
+                        const bool xf = TIE_OPEN ? (fe > fo) : (fe >= fo);
+                        const int f = xf ? fe : fo;
+                        bF[r].lo = xf ? bF[r].lo : sH[r].lo; bF[r].hi = (xf ? bF[r].hi : sH[r].hi) + GL1;
+                        const int mm = hD + (int)((sc[r] >> bsh) & 15u) - 4;
+                        const int h = max(mm, max(f, e));
+                        PathSum sHn = ps_append(shD, (sc[r] >> 20) == bj ? PS_EQ : PS_X, 1u);
+                        if (mm != h) {
+                            PathSum g = (f == h) ? bF[r] : bE;
+                            const uint32_t glen = g.hi >> 20; g.hi &= SUMM;
+                            sHn = ps_append(g, (f == h) ? PS_D : PS_I, glen);
+                        }
+                        hD = H[r]; shD = sH[r];
+                        H[r] = h; sH[r] = sHn; F[r] = f;
+                        hU = h; eU = e; shU = sHn; beU = bE;
+                    }
+                    Hout = hU; Eout = eU; sHout = shU; bEout = beU;
+                    if (lane == 31 && rb + 1 < nrb) {
+                        Hb[j] = hU; Eb[j] = eU; sHlo[j] = shU.lo; sHhi[j] = shU.hi; bElo[j] = beU.lo; bEhi[j] = beU.hi;
+                        __threadfence_block();
+                        *prog = j;
+                    }
+                }
+            }
+            if (rb == nrb - 1) {
+                int hs = 0; PathSum ss = { 0u, 0u };
+#pragma unroll
+                for (int r = 0; r < R; r++) if (i0 + r + 1 == m) { hs = H[r]; ss = sH[r]; }
+                const int src = ((m - 1) - rb * 32 * R) / R;
+                score = __shfl_sync(FULL, hs, src); sfin.lo = __shfl_sync(FULL, ss.lo, src); sfin.hi = __shfl_sync(FULL, ss.hi, src);
+                if (lane == 0) {
+                    AlignOut o;
+                    const bool multi = (sfin.hi & PS_MULTI) != 0;
+                    o.score = score; o.nops = multi ? 2 : ((sfin.hi & PS_NE) ? 1 : 0); o.cig_n = 0;
+                    o.lower = multi ? (int)(sfin.lo >> 16) : 0;
+                    o.num_sum = multi ? (int)((sfin.lo & 0xFFFFu) - (sfin.hi & 0xFFFFu)) : 0;
+                    A.out[ji] = o;
+                }
+            }
+        }
+        pair_bar(barid);                                                 // ctl / bs / boundary buffer are reused by the next job
+    }
+}
+
 static inline uint8_t sym_code(char c)
 {
     switch (c) {
@@ -427,7 +577,15 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     int maxm = 0; for (int q = 0; q < n_profiles; q++) maxm = std::max(maxm, a_len[q]);
     const bool need_boundary = maxm > 32 * ROWS;
     const size_t per_warp = (((size_t)ncol * (need_boundary ? (6 * 4 + 1) : 1)) + 15) & ~(size_t)15;
-    const size_t smem = (size_t)warps_per_block * per_warp;
+    size_t smem = (size_t)warps_per_block * per_warp;
+    // small batches are latency-bound: two warps per alignment (kgma_align_pair).  "Small" = both warps of every alignment
+    // still find a free slot in the first wave.
+    constexpr int PROWS = 5;
+    const char *pm_env = getenv("KGMA_ALIGN_PAIR_MAX");                 // 0 switches the two-warp kernel off
+    const int pair_max = pm_env ? atoi(pm_env) : 600;
+    const size_t per_pair = ((size_t)ncol * (6 * 4 + 1) + 16 + 15) & ~(size_t)15;
+    const bool use_pair = nj <= pair_max && maxm <= 64 * PROWS && maxm > 32 * PROWS && 2 * per_pair <= ctx->smem_optin;
+    if (use_pair) smem = 2 * per_pair;
     if (smem > ctx->smem_optin) return set_err(ctx, KGMA_E_UNSUPPORTED, "subject slice of %d bases too long for the extension kernel", maxn);
     size_t o = 0;
     auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
@@ -467,9 +625,17 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     A.need_boundary = need_boundary ? 1 : 0;
     KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = std::min((nj + warps_per_block - 1) / warps_per_block, ctx->num_sms * 8);
+    const int grid = use_pair ? std::min((nj + 1) / 2, ctx->num_sms * 8) : std::min((nj + warps_per_block - 1) / warps_per_block, ctx->num_sms * 8);
+    if (use_pair) {
+        KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_pair<PROWS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_pair<PROWS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     KGMA_CUDA(ctx, cudaEventRecord(ctx->a_ev0[slot], st));
-    if (tie_open) kgma_align_summary<ROWS, true><<<grid, warps_per_block * 32, smem, st>>>(A);
+    if (use_pair) {
+        if (tie_open) kgma_align_pair<PROWS, true><<<grid, 128, smem, st>>>(A);
+        else kgma_align_pair<PROWS, false><<<grid, 128, smem, st>>>(A);
+    }
+    else if (tie_open) kgma_align_summary<ROWS, true><<<grid, warps_per_block * 32, smem, st>>>(A);
     else kgma_align_summary<ROWS, false><<<grid, warps_per_block * 32, smem, st>>>(A);
     KGMA_CUDA(ctx, cudaGetLastError());
     KGMA_CUDA(ctx, cudaEventRecord(ctx->a_ev1[slot], st));

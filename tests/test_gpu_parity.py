@@ -988,6 +988,52 @@ def test_resident_genome_through_the_operator_mirror(K, O, prof, synth):
         assert K.exactMatch(q, g, ctx=ctx) == O.exactMatch(q, O.Fasta(path))
 
 
+def test_two_warp_extension_kernel_equals_one_warp(K, O, prof, monkeypatch):
+    """small extension batches run two warps per alignment (kgma_align_pair); KGMA_ALIGN_PAIR_MAX=0 forces the
+    one-warp kernel, a huge value the two-warp one for every batch: same ranges and scores, for several gap models, subject
+    lengths from 1 to 600 (with N) and consensus lengths on both sides of the 160-row split; then against the oracle"""
+    RV, ws, cons = prof
+    rng = np.random.default_rng(21)
+    whole = O.Fasta(GENOME).seq(3)
+    recs = []
+    for i in range(66):
+        n = int([1, 2, 31, 32, 33, 64, 200, 289, 389, 489, 600][i % 11])
+        p = int(rng.integers(0, len(whole) - 700))
+        sub = whole[p:p + n]
+        if i % 3 == 0 and n >= 200:                       # plant (a mutated copy of) the consensus so that real alignments occur
+            base = list(cons[:int(rng.integers(150, 289))])
+            for _ in range(int(rng.integers(0, 25))):
+                base[int(rng.integers(0, len(base)))] = "ACGTN"[int(rng.integers(0, 5))]
+            sub = (sub[:20] + "".join(base) + sub)[:n]
+        recs.append(("r%d" % i, sub))
+    g = K.Genome.from_records(recs)
+    ctx = K.default_context()
+    n = len(recs)
+    rec = np.arange(n, dtype=np.int32)
+    first = np.ones(n, np.int64)
+    last = np.asarray([len(s_) for _, s_ in recs], np.int64)
+
+    def batch(c, go, ge, setting):
+        monkeypatch.setenv("KGMA_ALIGN_PAIR_MAX", setting)
+        of, ol, sc = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.int64)
+        ctx.check(ctx._lib.kgma_align_batch(ctx._h, g._h, c, len(c), go, ge, 0, n, rec.ctypes.data, first.ctypes.data,
+                                            last.ctypes.data, of.ctypes.data, ol.ctypes.data, sc.ctypes.data))
+        monkeypatch.delenv("KGMA_ALIGN_PAIR_MAX")
+        return of.tolist(), ol.tolist(), sc.tolist()
+
+    for clen in (160, 161, 200, 289, 320):
+        c = cons[:289] if clen <= 289 else (cons[:289] + cons[:clen - 289])
+        c = c[:clen].encode()
+        for go, ge in ((-69, -1), (-200, -1), (-5, -2)):
+            assert batch(c, go, ge, "0") == batch(c, go, ge, "100000000"), (clen, go, ge)
+        of, ol, sc = batch(c, -69, -1, "100000000")
+        for i in range(0, n, 5):
+            s_ = recs[i][1]
+            lo, hi = O.align_unitrange(s_, (1, len(s_)), c.decode(), clen, len(s_), -69, -1)
+            assert (of[i], ol[i]) == (lo, hi), (clen, i)
+            assert sc[i] == O.pairalign_semiglobal(c.decode(), s_, -69, -1)[1]
+
+
 def test_two_contexts_share_nothing(K, prof, synth):
     """two contexts on the same device, used alternately on different genomes: each keeps its own device planes, tables,
     staging ring and scratch, so neither disturbs the other's resident genome"""
