@@ -1,6 +1,6 @@
 """one-off extended fuzz: run tests/test_gpu_parity.py::test_fuzz_vs_oracle for many more seeds"""
 import sys, os, tempfile, pathlib, traceback
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import pytest
 import test_gpu_parity as T
 import kmergma_jl_b200 as K
