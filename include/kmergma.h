@@ -103,6 +103,10 @@ typedef struct {
     uint32_t reserved;
 } kgma_run;
 
+/* Extension result of a run's own candidate window (the window whose start is t_argmin), computed by the shard that
+ * owns the run: what cigar_to_UnitRange returns for it, relative to the window's first base.  lo == 0: not extended. */
+typedef struct { int64_t lo, hi, score; } kgma_run_ext;
+
 typedef struct {
     int32_t  record;              /* 0-based index of the genome record */
     int32_t  profile;             /* "KFV = n" (1-based) in cluster mode, 0 in single mode */
@@ -131,6 +135,8 @@ typedef struct {
     double host_setup_ms;         /* plan, tables, scratch, small uploads (until the genome stream starts) */
     double host_cand_ms;          /* candidate list D2H + sort + segment building */
     double host_replay_ms;        /* run merge + replay of the reference state machine (without the extension kernel) */
+    int64_t n_align_redo;         /* extensions the tagged kernel handed to the path-summary kernel (no leading / trailing deletion run) */
+    int64_t filter_passes;        /* prefilter passes over the shard (one per group of profiles sharing a weight table); filter_ms spans all */
 } kgma_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -155,6 +161,13 @@ int  kgma_genome_append_packed(kgma_genome *g, const char *identifier, const cha
  * first symbol in the least significant nibble, one-hot A=1 C=2 G=4 T=8, N=15. */
 int  kgma_genome_append_bio4(kgma_genome *g, const char *identifier, const char *description,
                              const uint64_t *data, int64_t len);
+/* Zero-copy ingest for a caller that packs the genome itself: the library lays the records out in page-locked planes of its
+ * own (records start at multiples of 128 bases), kgma_genome_record_planes returns where record r's words go (same word
+ * format as kgma_genome_append_packed; the mask words are zero-initialised), the caller fills them in place and seals.
+ * Scans then stream straight from these planes (the e2e tier of bench.py) instead of staging a pageable copy. */
+int  kgma_genome_create_pinned(kgma_ctx *ctx, int n_records, const int64_t *rec_len, kgma_genome **out);
+int  kgma_genome_record_planes(kgma_genome *g, int record, uint32_t **seq2, uint32_t **mask);
+int  kgma_genome_set_names(kgma_genome *g, int record, const char *identifier, const char *description);
 int  kgma_genome_seal(kgma_genome *g);
 void kgma_genome_destroy(kgma_genome *g);
 int     kgma_genome_n_records(const kgma_genome *g);
@@ -211,6 +224,19 @@ int  kgma_replay(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, in
                  const int64_t *first_window_D /* [n_profiles][n_records], from kgma_result_first_D */,
                  kgma_result **out);
 
+/* Multi-GPU, one blocking call per rank and no device work afterwards: scan this context's shard, merge its runs and
+ * extend, on this GPU, the candidate window of every run that can still become a hit (its own first argmin -- a superset
+ * of what the replay selects).  kgma_result_runs / kgma_result_run_ext / kgma_result_first_D describe the outcome;
+ * kgma_result_pack lays them out in one block (returns the bytes needed; nothing is written when cap is smaller), the
+ * ranks exchange equal-sized blocks (one all-gather), and kgma_replay_packed -- host only, ctx may be NULL -- merges the
+ * shards' runs and replays the reference's state machine from them, looking extension results up instead of computing. */
+int  kgma_scan_shard(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int n_profiles,
+                     const kgma_scan_params *params, kgma_result **out);
+const kgma_run_ext *kgma_result_run_ext(const kgma_result *r);
+int64_t kgma_result_pack(const kgma_result *r, void *buf, int64_t cap);
+int  kgma_replay_packed(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int n_profiles,
+                        const kgma_scan_params *params, const void *blocks, int n_blocks, int64_t stride, kgma_result **out);
+
 int64_t kgma_result_n_hits(const kgma_result *r);
 const kgma_hit *kgma_result_hits(const kgma_result *r);
 int64_t kgma_result_n_runs(const kgma_result *r);
@@ -242,6 +268,14 @@ typedef struct {
 } kgma_match;
 int  kgma_exact_match(kgma_ctx *ctx, kgma_genome *g, const char *query, int64_t qlen, int overlap,
                       uint32_t flags /* KGMA_F_RESIDENT */, kgma_match **out, int64_t *n_out);
+/* Multi-GPU form (halo qlen-1): each context searches slice shard_index of shard_count of the packed genome and
+ * returns the occurrence starts it owns (0-based, packed coordinate space -- see kgma_genome_record_offset; *starts is
+ * malloc'd, kgma_free); every occurrence is owned by exactly one slice.  kgma_exact_match_merge (host only) turns the
+ * concatenated starts of all slices into exactMatch's result, applying FindAll's non-overlap rule across slice edges. */
+int  kgma_exact_match_shard(kgma_ctx *ctx, kgma_genome *g, const char *query, int64_t qlen, uint32_t flags,
+                            int shard_index, int shard_count, int64_t **starts, int64_t *n_out);
+int  kgma_exact_match_merge(const kgma_genome *g, const int64_t *starts, int64_t n, int64_t qlen, int overlap,
+                            kgma_match **out, int64_t *n_out);
 void kgma_free(void *p);
 
 #ifdef __cplusplus

@@ -183,6 +183,17 @@ class Genome:
             raise KmerGMAError(rc, f"range {first}:{last} outside record {r}")
         return buf.value.decode()
 
+    def seq_array(self, r: int, first: int = 1, last: Optional[int] = None) -> np.ndarray:
+        """view(seq, first:last) as a uint8 array of upper-case residues (no Python string: records can be 250 Mb)"""
+        if last is None:
+            last = self.seqsize(r)
+        n = max(0, last - first + 1)
+        buf = np.empty(n + 1, dtype=np.uint8)
+        rc = self._lib.kgma_genome_get_seq(self._h, r, first, last, buf.ctypes.data_as(C.c_char_p))
+        if rc != 0:
+            raise KmerGMAError(rc, f"range {first}:{last} outside record {r}")
+        return buf[:n]
+
     def record_offset(self, r: int) -> int:
         return self._lib.kgma_genome_record_offset(self._h, r)
 
@@ -514,6 +525,13 @@ class ScanOutput:
             p = self._lib.kgma_result_dists(self._res, q)
             self.dists.append(np.ctypeslib.as_array(p, shape=(n,)).copy() if n else np.zeros(0))
 
+    def load_run_ext(self) -> np.ndarray:
+        """kgma_result_run_ext as an (n_runs, 3) int64 array [lo, hi, score] (kgma_scan_shard results; lo == 0: not extended)"""
+        p = self._lib.kgma_result_run_ext(self._res)
+        if not p or not self.n_runs:
+            return np.zeros((0, 3), np.int64)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int64)), shape=(self.n_runs, 3)).copy()
+
     def load_first_D(self, n_profiles: int, n_records: int):
         p = self._lib.kgma_result_first_D(self._res)
         self.first_D = np.ctypeslib.as_array(p, shape=(n_profiles * n_records,)).copy() if p else np.zeros(0, np.int64)
@@ -559,6 +577,73 @@ def scan_raw(genome: Genome, refVecs, windowsizes, consensus_seqs, thrs, k: int,
     if runs_only:
         out.load_first_D(len(refVecs), len(genome))
     return out
+
+
+def scan_shard_raw(genome: Genome, refVecs, windowsizes, consensus_seqs, thrs, k: int, mode: int, buff: int,
+                   flags: int, gap_open: int, gap_extend: int, shard: Tuple[int, int], ctx: Optional[Context] = None) -> ScanOutput:
+    """kgma_scan_shard: one rank's share of a multi-GPU scan -- its shard's merged runs plus, with F_ALIGN, the extension
+    result of every run's own candidate window (computed on this GPU).  Ship `pack_shard(out, ...)` blocks between ranks and
+    hand all of them to `replay_packed`."""
+    ctx = ctx or default_context()
+    arr, keep = _make_profiles(refVecs, windowsizes, consensus_seqs, thrs, k, ctx._lib)
+    P = L.ScanParams(mode, flags, buff, gap_open, gap_extend, shard[0], shard[1], -1, 0)
+    res = C.c_void_p()
+    ctx.check(ctx._lib.kgma_scan_shard(ctx._h, genome._h, arr, len(refVecs), C.byref(P), C.byref(res)))
+    out = ScanOutput(ctx._lib, res)
+    out.load_first_D(len(refVecs), len(genome))
+    return out
+
+
+def pack_shard(out: ScanOutput, buf_ptr: int, cap: int) -> int:
+    """kgma_result_pack into caller memory (e.g. a pinned torch tensor's data_ptr); returns the bytes needed."""
+    return int(out._lib.kgma_result_pack(out._res, buf_ptr, cap))
+
+
+def replay_packed(genome: Genome, refVecs, windowsizes, consensus_seqs, thrs, k: int, mode: int, buff: int,
+                  flags: int, gap_open: int, gap_extend: int, blocks_ptr: int, n_blocks: int, stride: int,
+                  ctx: Optional[Context] = None) -> ScanOutput:
+    """kgma_replay_packed: host-only merge + replay of the shards' blocks (ctx is only used for error text / stats)."""
+    lib = L.load()
+    arr, keep = _make_profiles(refVecs, windowsizes, consensus_seqs, thrs, k, lib)
+    P = L.ScanParams(mode, flags, buff, gap_open, gap_extend, 0, 1, -1, 0)
+    res = C.c_void_p()
+    handle = ctx._h if ctx is not None else None
+    rc = lib.kgma_replay_packed(handle, genome._h, arr, len(refVecs), C.byref(P), blocks_ptr, n_blocks, stride, C.byref(res))
+    if rc != 0:
+        raise KmerGMAError(rc, (lib.kgma_last_error(handle) or b"").decode() or "kgma_replay_packed failed")
+    return ScanOutput(lib, res)
+
+
+def exact_match_shard(query: str, genome: Genome, shard: Tuple[int, int], ctx: Optional[Context] = None, resident: bool = False) -> np.ndarray:
+    """kgma_exact_match_shard: occurrence starts (0-based packed coordinates) owned by slice shard[0] of shard[1]."""
+    ctx = ctx or default_context()
+    q = str(query).upper().encode()
+    sp = C.POINTER(C.c_int64)()
+    n = C.c_int64()
+    ctx.check(ctx._lib.kgma_exact_match_shard(ctx._h, genome._h, q, len(q), L.F_RESIDENT if resident else 0, shard[0], shard[1],
+                                              C.byref(sp), C.byref(n)))
+    out = np.ctypeslib.as_array(sp, shape=(n.value,)).copy() if n.value else np.zeros(0, np.int64)
+    if n.value:
+        ctx._lib.kgma_free(sp)
+    return out
+
+
+def exact_match_merge(genome: Genome, starts: np.ndarray, qlen: int, overlap: bool = True):
+    """kgma_exact_match_merge (host only): concatenated slice starts -> what exactMatch(query, reader) returns."""
+    lib = L.load()
+    st = np.ascontiguousarray(starts, dtype=np.int64)
+    mp = C.POINTER(L.Match)()
+    n = C.c_int64()
+    rc = lib.kgma_exact_match_merge(genome._h, st.ctypes.data, st.size, qlen, int(overlap), C.byref(mp), C.byref(n))
+    if rc != 0:
+        raise KmerGMAError(rc, "kgma_exact_match_merge failed")
+    by_rec: Dict[int, List[Tuple[int, int]]] = {}
+    for i in range(n.value):
+        by_rec.setdefault(mp[i].record, []).append((mp[i].first, mp[i].last))
+    if n.value:
+        lib.kgma_free(mp)
+    identify = {genome.identifier(r): by_rec[r] for r in sorted(by_rec)}
+    return identify if identify else "no match"
 
 
 def replay_raw(genome: Genome, refVecs, windowsizes, consensus_seqs, thrs, k: int, mode: int, buff: int,

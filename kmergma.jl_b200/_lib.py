@@ -34,6 +34,10 @@ class Run(C.Structure):
                 ("t_argmin", C.c_int64), ("D_min", C.c_int64), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class RunExt(C.Structure):
+    _fields_ = [("lo", C.c_int64), ("hi", C.c_int64), ("score", C.c_int64)]
+
+
 class Hit(C.Structure):
     _fields_ = [("record", C.c_int32), ("profile", C.c_int32), ("cmi", C.c_int64),
                 ("first", C.c_int64), ("last", C.c_int64), ("genome_pos", C.c_int64),
@@ -48,7 +52,7 @@ class Stats(C.Structure):
                 ("exact_windows", C.c_int64), ("n_runs", C.c_int64), ("n_align", C.c_int64),
                 ("launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("wall_ms", C.c_double), ("host_setup_ms", C.c_double), ("host_cand_ms", C.c_double),
-                ("host_replay_ms", C.c_double)]
+                ("host_replay_ms", C.c_double), ("n_align_redo", C.c_int64), ("filter_passes", C.c_int64)]
 
 
 class Match(C.Structure):
@@ -68,6 +72,9 @@ SYMBOLS = {
     "kgma_genome_append_ascii": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64]),
     "kgma_genome_append_packed": (C.c_int, [_P, C.c_char_p, C.c_char_p, _P, _P, C.c_int64]),
     "kgma_genome_append_bio4": (C.c_int, [_P, C.c_char_p, C.c_char_p, _P, C.c_int64]),
+    "kgma_genome_create_pinned": (C.c_int, [_P, C.c_int, _P, C.POINTER(_P)]),
+    "kgma_genome_record_planes": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
+    "kgma_genome_set_names": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_char_p]),
     "kgma_genome_seal": (C.c_int, [_P]),
     "kgma_genome_destroy": (None, [_P]),
     "kgma_genome_n_records": (C.c_int, [_P]),
@@ -94,6 +101,10 @@ SYMBOLS = {
     "kgma_scan": (C.c_int, [_P, _P, C.POINTER(Profile), C.c_int, C.POINTER(ScanParams), C.POINTER(_P)]),
     "kgma_scan_runs": (C.c_int, [_P, _P, C.POINTER(Profile), C.c_int, C.POINTER(ScanParams), C.POINTER(_P)]),
     "kgma_replay": (C.c_int, [_P, _P, C.POINTER(Profile), C.c_int, C.POINTER(ScanParams), _P, C.c_int64, _P, C.POINTER(_P)]),
+    "kgma_scan_shard": (C.c_int, [_P, _P, C.POINTER(Profile), C.c_int, C.POINTER(ScanParams), C.POINTER(_P)]),
+    "kgma_result_run_ext": (C.POINTER(RunExt), [_P]),
+    "kgma_result_pack": (C.c_int64, [_P, _P, C.c_int64]),
+    "kgma_replay_packed": (C.c_int, [_P, _P, C.POINTER(Profile), C.c_int, C.POINTER(ScanParams), _P, C.c_int, C.c_int64, C.POINTER(_P)]),
     "kgma_result_n_hits": (C.c_int64, [_P]),
     "kgma_result_hits": (C.POINTER(Hit), [_P]),
     "kgma_result_n_runs": (C.c_int64, [_P]),
@@ -107,6 +118,8 @@ SYMBOLS = {
     "kgma_align_batch": (C.c_int, [_P, _P, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_int64,
                                    _P, _P, _P, _P, _P, _P]),
     "kgma_exact_match": (C.c_int, [_P, _P, C.c_char_p, C.c_int64, C.c_int, C.c_uint32, C.POINTER(C.POINTER(Match)), C.POINTER(C.c_int64)]),
+    "kgma_exact_match_shard": (C.c_int, [_P, _P, C.c_char_p, C.c_int64, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.c_int64)]),
+    "kgma_exact_match_merge": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.POINTER(Match)), C.POINTER(C.c_int64)]),
     "kgma_free": (None, [_P]),
 }
 

@@ -9,8 +9,9 @@
 // match > delete (consumes b) > insert (consumes a); on exact open/extend ties the gap is extended
 // unless KGMA_F_TIE_OPEN (BioAlignments' own tie rule is not pinned by any reference test).
 //
-// Three kernels.  kgma_align_pair<5>: kgma_align_summary's cell update with two warps per alignment, for small batches.
-// kgma_align_summary<R> (the default): each lane owns R = 10 consecutive DP rows in registers, lanes are
+// Three kernels.  kgma_align_tagged<C> (the default): one 32-bit word per DP state (score | tie tag | path counters), lanes
+// own subject columns, a DPX three-way max per cell; it hands the rare alignment without a leading or trailing deletion run
+// to kgma_align_summary<R>: each lane owns R = 10 consecutive DP rows in registers, lanes are
 // skewed by one column (operands of the row above arrive by __shfl_up), so one sweep of n+31 steps covers 320
 // consensus rows; instead of a trace matrix a packed summary of the canonical optimal path is carried with the
 // scores, from which cigar_to_UnitRange's two numbers follow; the subject is read from the packed genome on the
@@ -36,7 +37,6 @@ struct AlignJob {
     int32_t pad;
 };
 
-struct AlignOut { long long score; int32_t lower, num_sum, nops, cig_n; };
 
 struct AlignArgs {
     const uint8_t *a, *b;        // codes 0..3, 4 = N
@@ -162,19 +162,6 @@ __global__ void __launch_bounds__(128) kgma_align(AlignArgs A)
 // "path summary" per DP state (H, E, F), choosing the predecessor with exactly the priorities the traceback
 // uses (match > delete > insert; extend-vs-open as configured), so no trace matrix is written or walked.
 // The subject is read straight from the packed genome on the device (2-bit plane + ambiguity plane).
-struct AlignJob2 { long long gpos; int32_t n, a_off, m, b_off; };   // b_off >= 0: subject codes were uploaded (not on the device)
-
-struct AlignArgs2 {
-    const uint8_t *a;            // consensus codes 0..3, 4 = N
-    const uint32_t *seq;         // packed 2-bit genome on the device
-    const long long *nruns; int n_nruns;   // maximal runs of masked (N) bases, [start,end) global positions, ascending
-    const uint8_t *b;            // uploaded subject codes for jobs whose slice is not on the device
-    const AlignJob2 *jobs; int njobs;
-    int *next_job;
-    AlignOut *out;
-    int go, ge, tie_open, ncol_cap, need_boundary;
-};
-
 // path summary, two 32-bit words:
 //   lo = total columns (bits 0-15) | length of the first run << 16   (the first-run field stays 0 while the path is
 //        still ONE run and is captured from `total` at the first change of op)
@@ -333,152 +320,152 @@ __global__ void __launch_bounds__(128, 3) kgma_align_summary(AlignArgs2 A)
     }
 }
 
-// Two warps per alignment, for batches too small to fill the machine (the rounds of the cluster-mode replay, the tail part
-// of a pipelined streamed scan): such a batch costs the latency of ONE alignment, and that latency is n+31 steps of R
-// cells.  Here warp 0 sweeps rows 1..32R and warp 1 rows 32R+1..64R of the SAME alignment at the same time, R = 5: warp 1
-// trails by 32 columns and takes the row above its first row from the per-column boundary buffer that warp 0's last lane
-// fills as it goes (the buffer the one-warp kernel uses between successive sweeps), a progress word in shared memory
-// telling it how far warp 0 has come.  n+63 steps of 5 cells instead of n+31 steps of 10.  The cell update is the
-// one-warp kernel's, verbatim.
-__device__ __forceinline__ void pair_bar(int id)                     // (immediate ids: a register id makes ptxas reserve all 16 barriers)
+// ---------------------------------------------------------------------------------------------
+// kgma_align_tagged: the default extension kernel (prefer-extend tie rule, consensus <= 400, subject <= 511 bases).
+//
+// One 32-bit word per DP state carries everything the state machine of the traceback would need:
+//     [31:20] score (signed)   [19:18] priority tag   [17:9] insert columns so far   [8:0] start column
+// so that ONE signed integer max both selects the better predecessor and moves its bookkeeping along.  The tag
+// makes equal scores resolve exactly as BioAlignments' traceback does (match 2 > delete 1 > insert 0 in the H state,
+// extend 1 > open 0 inside a gap); it is rewritten after every max, so it never reaches the fields below it.
+// The H state is a three-way max: one DPX instruction (__vimax3_s32, VIMNMX3 on sm_90+/sm_100a).  12 instructions per
+// cell against ~79 for the path-summary kernel above.
+//
+// Orientation: lanes own COLUMNS (C consecutive subject bases each, in registers, read straight from the packed genome)
+// and the consensus rows stream by, lane l working on row s-l at step s; the only traffic between lanes is two
+// shuffles per step (H and F of the column to the left).  All rows use the ordinary gap costs; the free trailing
+// deletions of the semi-global alignment are taken at the end: the optimal path leaves the last row at the FIRST
+// column attaining max_j H[m][j] (the traceback extends the zero-cost trailing gap on ties), so with
+//   x = start column of that cell's path (leading free deletions), I = its insert columns, j* = that column:
+//   cigar_to_UnitRange (Alignment.jl:13-30)  lower = x,  num_sum = j* + I      (first run xD, last run (n-j*)D).
+// Alignments without a leading or trailing deletion run (x = 0, or the maximum is (also) attained at column n: their
+// first / last CIGAR run is a match run whose length the word does not carry) are flagged (nops = -1) and redone by
+// kgma_align_summary; they are the rare ones that touch a record edge or run with buff = 0.
+#define TG_SC_SH   20
+#define TG_TAG1    (1 << 18)
+#define TG_TAG2    (2 << 18)
+#define TG_TAGMASK (3 << 18)
+#define TG_IC1     (1 << 9)
+#define TG_MAX_M   400
+#define TG_MAX_N   511
+
+// (v & keep) | tag in ONE LOP3: with the two masks as literals the compiler emits an AND and an OR (an instruction has
+// room for one immediate), so they are handed over in registers it cannot see through
+__device__ __forceinline__ int tg_retag(int v, int keep, int tag)
 {
-    if (id == 1) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory");
+    int r; asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(v), "r"(keep), "r"(tag)); return r;
 }
 
-template <int R, bool TIE_OPEN>
-__global__ void __launch_bounds__(128, 4) kgma_align_pair(AlignArgs2 A)
+template <int C>
+__global__ void __launch_bounds__(128) kgma_align_tagged(AlignArgs2 A)
 {
-    extern __shared__ __align__(16) unsigned char s_raw[];
     const unsigned FULL = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, pair = wid >> 1, role = wid & 1;
-    const size_t per_pair = ((size_t)A.ncol_cap * (6 * 4 + 1) + 16 + 15) & ~(size_t)15;
-    unsigned char *pb = s_raw + (size_t)pair * per_pair;
-    int *ctl = reinterpret_cast<int *>(pb);                              // [0] job index, [1] last column warp 0 has delivered
-    volatile int *prog = ctl + 1;
-    int *Hb = reinterpret_cast<int *>(pb + 16), *Eb = Hb + A.ncol_cap;
-    uint32_t *sHlo = reinterpret_cast<uint32_t *>(Eb + A.ncol_cap), *sHhi = sHlo + A.ncol_cap;
-    uint32_t *bElo = sHhi + A.ncol_cap, *bEhi = bElo + A.ncol_cap;
-    uint8_t *bs = reinterpret_cast<uint8_t *>(bEhi + A.ncol_cap);
-    const int NEG = -(1 << 29);
-    const int go = A.go, ge = A.ge;
-    const int barid = 1 + pair;
+    const int lane = threadIdx.x & 31;
+    const int go = A.go, ge = A.ge, gog = go + ge;
+    // sentinel for "no gap open yet": below every reachable score, and one more extension must not wrap the 12-bit field
+    const int S0 = -2047 + ge;
+    const int K_ee = (int)((unsigned)(-ge) << TG_SC_SH) + TG_TAG1 + TG_IC1;            // E stored with tag 0: extend -> 1, one more insert column
+    const int K_eo = (int)((unsigned)(-gog) << TG_SC_SH) - TG_TAG2 + TG_IC1;           // H stored with tag 2: open   -> 0
+    // The deletion gap F[i][j+1] = max(F[i][j] - ge, H[i][j] - gog) is evaluated as max(F - ge, mm - gog, e - gog): opening
+    // from an H that itself came out of F is never better than extending that F (and carries the same counters), so H drops
+    // out of the recurrence and the chain along a row is one add-max and one retag per cell.  Order on equal scores:
+    // extend 2 > open from a match 1 > open from an insertion 0, the traceback's.
+    const int K_fe  = (int)((unsigned)(-ge) << TG_SC_SH) + TG_TAG1;                    // F stored with tag 1 -> 2
+    const int K_mfo = (int)((unsigned)(-gog) << TG_SC_SH) - TG_TAG1;                   // mm carries tag 2 -> 1
+    const int K_efo = (int)((unsigned)(-gog) << TG_SC_SH);                             // e carries tag 0
+    const int K_fo  = (int)((unsigned)(-gog) << TG_SC_SH) - TG_TAG2;                   // first column of a lane: open from the H handed over
+    int KEEP, T1, T2;
+    asm volatile("mov.b32 %0, %3; mov.b32 %1, %4; mov.b32 %2, %5;" : "=r"(KEEP), "=r"(T1), "=r"(T2) : "n"(~TG_TAGMASK), "n"(TG_TAG1), "n"(TG_TAG2));
 
     for (;;) {
-        if (role == 0 && lane == 0) { ctl[0] = atomicAdd(A.next_job, 1); ctl[1] = 0; }
-        pair_bar(barid);
-        const int ji = ctl[0];
+        int ji = 0;
+        if (lane == 0) ji = atomicAdd(A.next_job, 1);
+        ji = __shfl_sync(FULL, ji, 0);
         if (ji >= A.njobs) break;
         const AlignJob2 J = A.jobs[ji];
         const int m = J.m, n = J.n;
         const uint8_t *a = A.a + J.a_off;
-        if (J.b_off >= 0) { for (int j = role * 32 + lane; j < n; j += 64) bs[j] = A.b[J.b_off + j]; }
-        else for (int j = role * 32 + lane; j < n; j += 64) {
-            const long long gp = J.gpos + j;
-            uint32_t c = (__ldg(A.seq + (gp >> 4)) >> (2 * (int)(gp & 15))) & 3u;
-            if (A.n_nruns) {
-                int lo = -1, hi = A.n_nruns;
-                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (A.nruns[2 * mid] <= gp) lo = mid; else hi = mid; }
-                if (lo >= 0 && gp < A.nruns[2 * lo + 1]) c = 4u;
+        const int j0 = lane * C;                                                  // this lane owns columns j0+1 .. j0+C
+        int Hst[C], Est[C]; uint32_t colsel[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const int j = j0 + c + 1;
+            uint32_t code = 0;
+            if (j <= n) {
+                if (J.b_off >= 0) code = A.b[J.b_off + j - 1];
+                else {
+                    const long long gp = J.gpos + j - 1;
+                    code = (__ldg(A.seq + (gp >> 4)) >> (2 * (int)(gp & 15))) & 3u;
+                    if (A.n_nruns) {
+                        int lo = -1, hi = A.n_nruns;                              // last masked run with start <= gp
+                        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (A.nruns[2 * mid] <= gp) lo = mid; else hi = mid; }
+                        if (lo >= 0 && gp < A.nruns[2 * lo + 1]) code = 4u;
+                    }
+                }
             }
-            bs[j] = (uint8_t)c;
+            // byte permute selector: byte 0 = table[code], bytes 1-3 = its sign  ->  a sign-extended score in one PRMT
+            colsel[c] = code | ((code | 8u) << 4) | ((code | 8u) << 8) | ((code | 8u) << 12);
+            Hst[c] = TG_TAG2 | j;                                                 // row 0: free leading deletions, path = jD
+            Est[c] = (int)((unsigned)S0 << TG_SC_SH);
         }
-        pair_bar(barid);
-        const int nrb = (m + 32 * R - 1) / (32 * R);                      // 1 or 2 (the host only sends m <= 64 R here)
-        const int rb = role;
-        if (rb < nrb) {
-            int score = 0; PathSum sfin = { 0u, 0u };
-            const int i0 = rb * 32 * R + lane * R;
-            int H[R], F[R]; PathSum sH[R], bF[R]; uint32_t sc[R]; int gof[R], gef[R];
+        int prevIn = TG_TAG2 | j0;                                                // H[0][j0]: diagonal of my first column at row 1
+        int Hlast = 0, Flast = 0;
+        for (int s = 1; s <= m + 31; s++) {
+            const int i = s - lane;
+            const int inH = __shfl_up_sync(FULL, Hlast, 1), inF = __shfl_up_sync(FULL, Flast, 1);
+            if (i >= 1 && i <= m) {
+                int left, F, diag = prevIn;
+                if (lane == 0) {                                                  // column 0: H[i][0] = -(go + i ge), path = iI; no deletion gap yet
+                    left = (int)((unsigned)(-(go + i * ge)) << TG_SC_SH) | TG_TAG2 | (i << 9);
+                    F = (int)((unsigned)S0 << TG_SC_SH) | TG_TAG1;
+                } else { left = inH; F = inF; }
+                prevIn = left;
+                F = tg_retag(max(F + K_fe, left + K_fo), KEEP, T1);               // F[i][j0+1]
+                const int ai = a[i - 1];
+                // EDNAFULL row of this consensus symbol as signed bytes: vs A,C,G,T in tlo, vs N in thi
+                const uint32_t tlo = ai < 4 ? ((0xFCFCFCFCu & ~(0xFFu << (8 * ai))) | (5u << (8 * ai))) : 0xFEFEFEFEu;
+                const uint32_t thi = ai < 4 ? 0xFEu : 0xFFu;
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int i = i0 + r + 1;
-                H[r] = -(go + i * ge); F[r] = NEG;
-                sH[r] = ps_run((uint32_t)i, PS_I); bF[r].lo = bF[r].hi = 0;
-                const int ai = i <= m ? a[i - 1] : 0;
-                uint32_t t = (uint32_t)ai << 20;
-#pragma unroll
-                for (int c = 0; c < 5; c++) t |= (uint32_t)(edna(ai, c) + 4) << (4 * c);
-                sc[r] = t;
-                gof[r] = (i == m) ? 0 : go + ge; gef[r] = (i == m) ? 0 : ge;
-            }
-            int Hdiag0 = (i0 == 0) ? 0 : -(go + i0 * ge);
-            PathSum sHdiag0 = ps_run((uint32_t)i0, PS_I);
-            int Hout = NEG, Eout = NEG; PathSum sHout = { 0u, 0u }, bEout = { 0u, 0u };
-            const bool lane_ok = i0 < m;
-            const int gog = go + ge;
-            const uint32_t GL1 = 1u << 20, SUMM = GL1 - 1;
-            for (int s = 1; s <= n + 31; s++) {
-                const int j = s - lane;
-                if (rb == 1) {                                           // column s of the row above must have arrived
-                    if (lane == 0 && s <= n) { while (*prog < s) { } }
-                    __syncwarp();
-                }
-                int upH = __shfl_up_sync(FULL, Hout, 1), upE = __shfl_up_sync(FULL, Eout, 1);
-                PathSum supH, ubE;
-                supH.lo = __shfl_up_sync(FULL, sHout.lo, 1); supH.hi = __shfl_up_sync(FULL, sHout.hi, 1);
-                ubE.lo = __shfl_up_sync(FULL, bEout.lo, 1); ubE.hi = __shfl_up_sync(FULL, bEout.hi, 1);
-                if (lane == 0 && j >= 1 && j <= n) {
-                    if (rb == 0) { upH = 0; upE = NEG; supH = ps_run((uint32_t)j, PS_D); ubE.lo = ubE.hi = 0; }
-                    else {
-                        __threadfence_block();
-                        upH = ((volatile int *)Hb)[j]; upE = ((volatile int *)Eb)[j];
-                        supH.lo = ((volatile uint32_t *)sHlo)[j]; supH.hi = ((volatile uint32_t *)sHhi)[j];
-                        ubE.lo = ((volatile uint32_t *)bElo)[j]; ubE.hi = ((volatile uint32_t *)bEhi)[j];
-                    }
-                }
-                if (lane_ok && j >= 1 && j <= n) {
-                    const uint32_t bj = bs[j - 1];
-                    const int bsh = 4 * (int)bj;
-                    int hU = upH, eU = upE; PathSum shU = supH, beU = ubE;
-                    int hD = Hdiag0; PathSum shD = sHdiag0;
-                    Hdiag0 = upH; sHdiag0 = supH;
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        const int eo = hU - gog, ee = eU - ge;
-                        const bool xe = TIE_OPEN ? (ee > eo) : (ee >= eo);
-                        const int e = xe ? ee : eo;
-                        PathSum bE; bE.lo = xe ? beU.lo : shU.lo; bE.hi = (xe ? beU.hi : shU.hi) + GL1;
-                        const int fo = H[r] - gof[r], fe = F[r] - gef[r];
-                        const bool xf = TIE_OPEN ? (fe > fo) : (fe >= fo);
-                        const int f = xf ? fe : fo;
-                        bF[r].lo = xf ? bF[r].lo : sH[r].lo; bF[r].hi = (xf ? bF[r].hi : sH[r].hi) + GL1;
-                        const int mm = hD + (int)((sc[r] >> bsh) & 15u) - 4;
-                        const int h = max(mm, max(f, e));
-                        PathSum sHn = ps_append(shD, (sc[r] >> 20) == bj ? PS_EQ : PS_X, 1u);
-                        if (mm != h) {
-                            PathSum g = (f == h) ? bF[r] : bE;
-                            const uint32_t glen = g.hi >> 20; g.hi &= SUMM;
-                            sHn = ps_append(g, (f == h) ? PS_D : PS_I, glen);
-                        }
-                        hD = H[r]; shD = sH[r];
-                        H[r] = h; sH[r] = sHn; F[r] = f;
-                        hU = h; eU = e; shU = sHn; beU = bE;
-                    }
-                    Hout = hU; Eout = eU; sHout = shU; bEout = beU;
-                    if (lane == 31 && rb + 1 < nrb) {
-                        Hb[j] = hU; Eb[j] = eU; sHlo[j] = shU.lo; sHhi[j] = shU.hi; bElo[j] = beU.lo; bEhi[j] = beU.hi;
-                        __threadfence_block();
-                        *prog = j;
-                    }
-                }
-            }
-            if (rb == nrb - 1) {
-                int hs = 0; PathSum ss = { 0u, 0u };
-#pragma unroll
-                for (int r = 0; r < R; r++) if (i0 + r + 1 == m) { hs = H[r]; ss = sH[r]; }
-                const int src = ((m - 1) - rb * 32 * R) / R;
-                score = __shfl_sync(FULL, hs, src); sfin.lo = __shfl_sync(FULL, ss.lo, src); sfin.hi = __shfl_sync(FULL, ss.hi, src);
-                if (lane == 0) {
-                    AlignOut o;
-                    const bool multi = (sfin.hi & PS_MULTI) != 0;
-                    o.score = score; o.nops = multi ? 2 : ((sfin.hi & PS_NE) ? 1 : 0); o.cig_n = 0;
-                    o.lower = multi ? (int)(sfin.lo >> 16) : 0;
-                    o.num_sum = multi ? (int)((sfin.lo & 0xFFFFu) - (sfin.hi & 0xFFFFu)) : 0;
-                    A.out[ji] = o;
+                for (int c = 0; c < C; c++) {
+                    const int up = Hst[c];
+                    const int e = max(Est[c] + K_ee, up + K_eo) & KEEP;
+                    const int sub = (int)__byte_perm(tlo, thi, colsel[c]);
+                    const int mm = diag + (int)((unsigned)sub << TG_SC_SH);
+                    const int h = tg_retag(__vimax3_s32(mm, F, e), KEEP, T2);
+                    diag = up; Hst[c] = h; Est[c] = e;
+                    if (c == C - 1) { Hlast = h; Flast = F; }
+                    else F = tg_retag(max(F + K_fe, max(mm + K_mfo, e + K_efo)), KEEP, T1);   // F[i][j+1]
                 }
             }
         }
-        pair_bar(barid);                                                 // ctl / bs / boundary buffer are reused by the next job
+        // ---- last row: first column attaining the maximum (ties -> lowest column), and the value at column n
+        int best = INT_MIN, bestw = 0, bestj = 0, vn = INT_MIN;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const int j = j0 + c + 1;
+            const int v = Hst[c] >> TG_SC_SH;
+            if (j <= n && v > best) { best = v; bestw = Hst[c]; bestj = j; }
+            if (j == n) vn = v;
+        }
+        // warp argmax over (score, lowest column): columns grow with the lane index, so on equal scores the lower lane wins
+        int bv = best, bl = lane;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            const int ov = __shfl_xor_sync(FULL, bv, d), ol = __shfl_xor_sync(FULL, bl, d);
+            if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
+        }
+        const int w = __shfl_sync(FULL, bestw, bl), jstar = __shfl_sync(FULL, bestj, bl);
+        const int vlast = __shfl_sync(FULL, vn, (n - 1) / C);
+        if (lane == 0) {
+            AlignOut o;
+            const int x = w & 0x1FF, ic = (w >> 9) & 0x1FF;
+            const bool redo = x == 0 || vlast == bv || bv <= -(go + m * ge);
+            o.score = bv; o.cig_n = 0;
+            o.nops = redo ? -1 : 2;
+            o.lower = x; o.num_sum = jstar + ic;
+            A.out[ji] = o;
+        }
+        __syncwarp();
     }
 }
 
@@ -521,7 +508,7 @@ static int slot_scratch(kgma_ctx *ctx, int slot, size_t dbytes, size_t hbytes, v
 }
 
 // Queue the trace-free extension of `reqs` on stream `st` (own scratch per slot, so it can run next to a scan that is
-// still streaming); align_collect waits for it and converts the results.
+// still streaming); align_collect waits for it, redoes the few alignments the tagged kernel handed back, and converts.
 int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &reqs, const kgma_profile *profiles, int n_profiles,
                   bool single_mode_truncate, int gap_open, int gap_extend, bool tie_open, cudaStream_t st, int slot, AlignTicket *t)
 {
@@ -573,28 +560,28 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     const int nj = (int)jobs.size();
     const int ncol = (maxn + 1 + 31) & ~31;
     const int warps_per_block = 4;
-    constexpr int ROWS = 10;                                   // DP rows per lane: one sweep covers 320 consensus rows
+    constexpr int ROWS = 10;                                   // kgma_align_summary: DP rows per lane, one sweep covers 320 consensus rows
     int maxm = 0; for (int q = 0; q < n_profiles; q++) maxm = std::max(maxm, a_len[q]);
     const bool need_boundary = maxm > 32 * ROWS;
     const size_t per_warp = (((size_t)ncol * (need_boundary ? (6 * 4 + 1) : 1)) + 15) & ~(size_t)15;
-    size_t smem = (size_t)warps_per_block * per_warp;
-    // small batches are latency-bound: two warps per alignment (kgma_align_pair).  "Small" = both warps of every alignment
-    // still find a free slot in the first wave.
-    constexpr int PROWS = 5;
-    const char *pm_env = getenv("KGMA_ALIGN_PAIR_MAX");                 // 0 switches the two-warp kernel off
-    const int pair_max = pm_env ? atoi(pm_env) : 600;
-    const size_t per_pair = ((size_t)ncol * (6 * 4 + 1) + 16 + 15) & ~(size_t)15;
-    const bool use_pair = nj <= pair_max && maxm <= 64 * PROWS && maxm > 32 * PROWS && 2 * per_pair <= ctx->smem_optin;
-    if (use_pair) smem = 2 * per_pair;
+    const size_t smem = (size_t)warps_per_block * per_warp;    // of the path-summary kernel (the tagged kernel uses none)
     if (smem > ctx->smem_optin) return set_err(ctx, KGMA_E_UNSUPPORTED, "subject slice of %d bases too long for the extension kernel", maxn);
+    // The tagged kernel (one word per DP state, DPX three-way max) takes the batch when its 12-bit score field and 9-bit
+    // counters hold every reachable value and the default tie rule is asked for; KGMA_ALIGN_KERNEL=summary forces the
+    // path-summary kernel (tests compare the two).
+    const int go = -gap_open, ge = -gap_extend;
+    const char *kern_env = getenv("KGMA_ALIGN_KERNEL");
+    const bool tagged = !(kern_env && !strcmp(kern_env, "summary")) && !tie_open && go >= 0 && ge >= 0 && maxm >= 1 && maxm <= TG_MAX_M && maxn <= TG_MAX_N &&
+                        5 * maxm < 2040 && 2LL * go + (long long)(maxm + 3) * ge + 8 < 2040;
     size_t o = 0;
     auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
     const size_t o_a = carve(acodes.size()), o_b = carve(bcodes.size()), o_j = carve((size_t)nj * sizeof(AlignJob2));
     const size_t o_n = carve(nruns.size() * 8 + 8);
     const size_t up = o;
     const size_t o_c = carve(256), o_o = carve((size_t)nj * sizeof(AlignOut));
+    const size_t o_j2 = carve(tagged ? (size_t)nj * sizeof(AlignJob2) : 0), o_o2 = carve(tagged ? (size_t)nj * sizeof(AlignOut) : 0);   // second pass
     void *dv = nullptr, *hv = nullptr;
-    int rc = slot_scratch(ctx, slot, o, up + (size_t)nj * sizeof(AlignOut), &dv, &hv);
+    int rc = slot_scratch(ctx, slot, o, up + (size_t)nj * sizeof(AlignOut) + (tagged ? (size_t)nj * (sizeof(AlignJob2) + sizeof(AlignOut)) : 0), &dv, &hv);
     if (rc) return rc;
     unsigned char *d = (unsigned char *)dv, *h = (unsigned char *)hv;
     memcpy(h + o_a, acodes.data(), acodes.size());
@@ -621,19 +608,15 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     A.a = d + o_a; A.seq = ctx->d_seq2; A.nruns = (const long long *)(d + o_n); A.n_nruns = (int)(nruns.size() / 2);
     A.b = d + o_b; A.jobs = (const AlignJob2 *)(d + o_j); A.njobs = nj; A.next_job = (int *)(d + o_c);
     // results are written straight into the page-locked block (16 bytes per alignment, posted writes): no copy back
-    A.out = in_place ? (AlignOut *)((unsigned char *)h_dev + up) : (AlignOut *)(d + o_o); A.go = -gap_open; A.ge = -gap_extend; A.tie_open = tie_open ? 1 : 0; A.ncol_cap = ncol;
+    A.out = in_place ? (AlignOut *)((unsigned char *)h_dev + up) : (AlignOut *)(d + o_o); A.go = go; A.ge = ge; A.tie_open = tie_open ? 1 : 0; A.ncol_cap = ncol;
     A.need_boundary = need_boundary ? 1 : 0;
     KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = use_pair ? std::min((nj + 1) / 2, ctx->num_sms * 8) : std::min((nj + warps_per_block - 1) / warps_per_block, ctx->num_sms * 8);
-    if (use_pair) {
-        KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_pair<PROWS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_pair<PROWS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
+    const int grid = std::min((nj + warps_per_block - 1) / warps_per_block, ctx->num_sms * 8);
     KGMA_CUDA(ctx, cudaEventRecord(ctx->a_ev0[slot], st));
-    if (use_pair) {
-        if (tie_open) kgma_align_pair<PROWS, true><<<grid, 128, smem, st>>>(A);
-        else kgma_align_pair<PROWS, false><<<grid, 128, smem, st>>>(A);
+    if (tagged) {
+        if (maxn <= 13 * 32) kgma_align_tagged<13><<<grid, warps_per_block * 32, 0, st>>>(A);
+        else kgma_align_tagged<16><<<grid, warps_per_block * 32, 0, st>>>(A);
     }
     else if (tie_open) kgma_align_summary<ROWS, true><<<grid, warps_per_block * 32, smem, st>>>(A);
     else kgma_align_summary<ROWS, false><<<grid, warps_per_block * 32, smem, st>>>(A);
@@ -645,7 +628,10 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     KGMA_CUDA(ctx, cudaEventRecord(ctx->a_done[slot], st));
     ctx->stats.d2h_bytes += (size_t)nj * sizeof(AlignOut);
     t->active = true; t->slot = slot; t->nj = nj; t->ho = ho;
-    if (trace) fprintf(stderr, "[kgma align] batch of %d queued in %.3f ms of host time\n", nj, now_ms() - te0);
+    t->tagged = tagged; t->st = st; t->args = A; t->smem = smem;
+    t->d_jobs2 = d + o_j2; t->d_out2 = d + o_o2; t->d_cnt = d + o_c;
+    t->h_jobs = h + o_j; t->h_jobs2 = h + up + (size_t)nj * sizeof(AlignOut); t->h_out2 = (unsigned char *)t->h_jobs2 + (size_t)nj * sizeof(AlignJob2);
+    if (trace) fprintf(stderr, "[kgma align] batch of %d queued in %.3f ms of host time (%s kernel)\n", nj, now_ms() - te0, tagged ? "tagged" : "summary");
     return KGMA_OK;
 }
 
@@ -656,9 +642,39 @@ int align_collect(kgma_ctx *ctx, AlignTicket *t, std::vector<AlignRes> &out)
     KGMA_CUDA(ctx, cudaEventSynchronize(ctx->a_done[t->slot]));
     float ms = 0; cudaEventElapsedTime(&ms, ctx->a_ev0[t->slot], ctx->a_ev1[t->slot]);
     ctx->stats.align_ms += ms;
-    const AlignOut *ho = (const AlignOut *)t->ho;
-    for (int q = 0; q < t->nj; q++) { out[(size_t)q].lo = (int64_t)ho[q].lower + 1; out[(size_t)q].hi = ho[q].num_sum; out[(size_t)q].score = ho[q].score; }
+    AlignOut *ho = (AlignOut *)t->ho;
     t->active = false;
+    if (t->tagged) {
+        // second pass: alignments without a leading / trailing deletion run go through the path-summary kernel
+        std::vector<int> redo;
+        for (int q = 0; q < t->nj; q++) if (ho[q].nops < 0) redo.push_back(q);
+        if (!redo.empty()) {
+            const AlignJob2 *hj = (const AlignJob2 *)t->h_jobs;
+            AlignJob2 *hj2 = (AlignJob2 *)t->h_jobs2;
+            for (size_t i = 0; i < redo.size(); i++) hj2[i] = hj[redo[i]];
+            const int nf = (int)redo.size();
+            cudaStream_t st = (cudaStream_t)t->st;
+            AlignArgs2 A = t->args;
+            KGMA_CUDA(ctx, cudaMemcpyAsync(t->d_jobs2, hj2, (size_t)nf * sizeof(AlignJob2), cudaMemcpyHostToDevice, st));
+            KGMA_CUDA(ctx, cudaMemsetAsync(t->d_cnt, 0, 256, st));
+            A.jobs = (const AlignJob2 *)t->d_jobs2; A.njobs = nf; A.out = (AlignOut *)t->d_out2; A.next_job = (int *)t->d_cnt;
+            const int grid = std::min((nf + 3) / 4, ctx->num_sms * 8);
+            KGMA_CUDA(ctx, cudaEventRecord(ctx->a_ev0[t->slot], st));
+            kgma_align_summary<10, false><<<grid, 128, t->smem, st>>>(A);
+            KGMA_CUDA(ctx, cudaGetLastError());
+            KGMA_CUDA(ctx, cudaEventRecord(ctx->a_ev1[t->slot], st));
+            KGMA_CUDA(ctx, cudaMemcpyAsync(t->h_out2, t->d_out2, (size_t)nf * sizeof(AlignOut), cudaMemcpyDeviceToHost, st));
+            KGMA_CUDA(ctx, cudaStreamSynchronize(st));
+            cudaEventElapsedTime(&ms, ctx->a_ev0[t->slot], ctx->a_ev1[t->slot]);
+            ctx->stats.align_ms += ms;
+            ctx->stats.launches++;
+            ctx->stats.n_align_redo += nf;
+            const AlignOut *ho2 = (const AlignOut *)t->h_out2;
+            for (int i = 0; i < nf; i++) ho[redo[(size_t)i]] = ho2[i];
+            if (getenv("KGMA_TRACE")) fprintf(stderr, "[kgma align] %d of %d alignments redone by the path-summary kernel\n", nf, t->nj);
+        }
+    }
+    for (int q = 0; q < t->nj; q++) { out[(size_t)q].lo = (int64_t)ho[q].lower + 1; out[(size_t)q].hi = ho[q].num_sum; out[(size_t)q].score = ho[q].score; }
     return KGMA_OK;
 }
 
@@ -796,6 +812,7 @@ extern "C" int kgma_align_batch(kgma_ctx *ctx, kgma_genome *g, const char *conse
     std::vector<AlignReq> reqs((size_t)n);
     for (int64_t i = 0; i < n; i++) reqs[(size_t)i] = { record[i], 0, first[i], last[i] };
     std::vector<AlignRes> res;
+    ctx->stats = kgma_stats{};
     int rc = align_batch_device(ctx, g, reqs, &p, 1, false, gap_open, gap_extend, (flags & KGMA_F_TIE_OPEN) != 0, false, res, nullptr, nullptr);
     if (rc) return rc;
     for (int64_t i = 0; i < n; i++) {

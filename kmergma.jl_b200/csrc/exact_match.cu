@@ -196,11 +196,12 @@ __global__ void __launch_bounds__(256) kgma_exact_match_sampled(SampledArgs a)
 
 using namespace kgma;
 
-extern "C" int kgma_exact_match(kgma_ctx *ctx, kgma_genome *g, const char *query, int64_t qlen, int overlap,
-                                uint32_t flags, kgma_match **out, int64_t *n_out)
+// Search the slice shard_index of shard_count of the packed genome: every occurrence is reported by exactly one slice (the
+// one that owns its first sampled word / its start block), so the slices' lists simply concatenate.  The slice needs
+// qlen - 1 bases past its end (an occurrence starting on its last base) and up to 127 before its start.
+static int exact_match_impl(kgma_ctx *ctx, kgma_genome *g, const char *query, int64_t qlen, uint32_t flags,
+                            int shard_index, int shard_count, std::vector<unsigned long long> &pos)
 {
-    if (!ctx || !g || !query || !out || !n_out) return KGMA_E_ARG;
-    *out = nullptr; *n_out = 0;
     if (!g->sealed) return set_err(ctx, KGMA_E_STATE, "genome is not sealed");
     if (qlen < 1 || qlen > 1 << 20) return set_err(ctx, KGMA_E_ARG, "query length %lld out of range", (long long)qlen);
     KGMA_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -224,7 +225,12 @@ extern "C" int kgma_exact_match(kgma_ctx *ctx, kgma_genome *g, const char *query
     kgma_stats &S = ctx->stats; S = kgma_stats{};
     cudaEvent_t e0 = ctx->ev[0], e1 = ctx->ev[1], e2 = ctx->ev[2], ek = ctx->ev[3];
     const size_t bases = (size_t)(g->G + TAIL_PAD);
-    const bool have = (flags & KGMA_F_RESIDENT) && ctx->d_seq_valid && ctx->d_valid_lo == 0 && ctx->d_valid_hi >= (int64_t)bases;
+    const int sc = std::max(1, shard_count), si = std::min(std::max(0, shard_index), sc - 1);
+    const int64_t ngrp_total = g->G / FGROUP;
+    const int64_t range_lo = (ngrp_total * si / sc) * FGROUP, range_hi = si == sc - 1 ? g->G : (ngrp_total * (si + 1) / sc) * FGROUP;
+    const int64_t up_lo = sc == 1 ? 0 : std::max<int64_t>(0, range_lo - FGROUP);
+    const int64_t up_hi = sc == 1 || si == sc - 1 ? (int64_t)bases : std::min<int64_t>((int64_t)bases, (range_hi + qlen + 6 * FGROUP + 127) / 128 * 128);
+    const bool have = (flags & KGMA_F_RESIDENT) && ctx->d_seq_valid && ctx->d_valid_lo <= up_lo && ctx->d_valid_hi >= up_hi;
     // a resident genome is not read from the host at all; a pageable one goes through the staging ring (scan.cu)
     const bool staged = !have && !g->pinned && !getenv("KGMA_NO_STAGING");
     if (!have) { rc = staged ? StagedUpload::prepare_ring(ctx) : genome_pin(ctx, g); if (rc) return rc; }
@@ -275,8 +281,8 @@ extern "C" int kgma_exact_match(kgma_ctx *ctx, kgma_genome *g, const char *query
     sa.out = a.out; sa.out_cap = cap; sa.out_count = a.out_count;
 
     // search [done, upto) in bases (multiples of 2048), given that the genome is on the device up to avail_hi
-    const int64_t G = g->G;
-    int64_t done = 0; bool first_kernel = true;
+    const int64_t G = range_hi;
+    int64_t done = range_lo; bool first_kernel = true;
     auto search_to = [&](int64_t avail_hi, bool last) -> int {
         int64_t upto = last ? G : std::min<int64_t>(G, (avail_hi - qlen - 4 * FGROUP) / FGROUP * FGROUP);
         if (upto <= done) return KGMA_OK;
@@ -298,36 +304,43 @@ extern "C" int kgma_exact_match(kgma_ctx *ctx, kgma_genome *g, const char *query
     if (!have) {
         // stream the 2-bit plane in 32 MB chunks on the copy stream, the search chasing it (the ambiguity plane is only
         // uploaded for short queries; long ones check N against the list of masked runs)
-        if (need_mask_plane) { KGMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_mask, g->mask, bases / 8, cudaMemcpyHostToDevice, st)); S.h2d_bytes += bases / 8; ctx->d_mask_valid = true; }
+        const bool whole = up_lo == 0 && up_hi == (int64_t)bases;
+        if (need_mask_plane) {
+            KGMA_CUDA(ctx, cudaMemcpyAsync((char *)ctx->d_mask + up_lo / 8, (char *)g->mask + up_lo / 8, (size_t)(up_hi - up_lo) / 8, cudaMemcpyHostToDevice, st));
+            S.h2d_bytes += (up_hi - up_lo) / 8; ctx->d_mask_valid = whole;
+        }
         cudaEvent_t e_c[2] = { ctx->ev[5], ctx->ev[6] };
         KGMA_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
         KGMA_CUDA(ctx, cudaStreamWaitEvent(sp, ctx->ev[7], 0));
         const int64_t CH = (int64_t)128 << 20; int ci = 0;
         StagedUpload stager;                                       // (its destructor joins the copy threads on every exit path)
-        if (staged) stager.start(ctx, (const char *)g->seq2, bases / 4);
-        for (int64_t lo = 0; lo < (int64_t)bases; lo += CH, ci++) {
-            const int64_t hi = std::min<int64_t>((int64_t)bases, lo + CH);
+        if (staged) stager.start(ctx, (const char *)g->seq2 + up_lo / 4, (size_t)(up_hi - up_lo) / 4);
+        for (int64_t lo = up_lo; lo < up_hi; lo += CH, ci++) {
+            const int64_t hi = std::min<int64_t>(up_hi, lo + CH);
             if (staged) {
-                const size_t j0 = (size_t)(lo / 4) / StagedUpload::SB;
-                const size_t j1 = hi >= (int64_t)bases ? stager.nsub : (size_t)(hi / 4) / StagedUpload::SB;
-                rc = stager.issue(j0, j1, (char *)ctx->d_seq2, sp);
+                const size_t j0 = (size_t)((lo - up_lo) / 4) / StagedUpload::SB;
+                const size_t j1 = hi >= up_hi ? stager.nsub : (size_t)((hi - up_lo) / 4) / StagedUpload::SB;
+                rc = stager.issue(j0, j1, (char *)ctx->d_seq2 + up_lo / 4, sp);
                 if (rc) return rc;
             } else
             KGMA_CUDA(ctx, cudaMemcpyAsync((char *)ctx->d_seq2 + lo / 4, (char *)g->seq2 + lo / 4, (size_t)(hi - lo) / 4, cudaMemcpyHostToDevice, sp));
             KGMA_CUDA(ctx, cudaEventRecord(e_c[ci & 1], sp));
             KGMA_CUDA(ctx, cudaStreamWaitEvent(st, e_c[ci & 1], 0));
             S.h2d_bytes += (hi - lo) / 4;
-            rc = search_to(hi, hi >= (int64_t)bases);
+            rc = search_to(hi, hi >= up_hi);
             if (rc) return rc;
             if (ci >= 1) KGMA_CUDA(ctx, cudaEventSynchronize(e_c[(ci - 1) & 1]));
         }
-        ctx->d_seq_valid = true; ctx->d_valid_lo = 0; ctx->d_valid_hi = (int64_t)bases;
-        ctx->d_have_lo = 0; ctx->d_have_hi = (int64_t)bases;
+        ctx->d_seq_valid = true; ctx->d_valid_lo = up_lo; ctx->d_valid_hi = up_hi;
+        ctx->d_have_lo = up_lo; ctx->d_have_hi = up_hi;
         KGMA_CUDA(ctx, cudaEventRecord(e1, st));
     } else {
-        if (need_mask_plane && !ctx->d_mask_valid) { KGMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_mask, g->mask, bases / 8, cudaMemcpyHostToDevice, st)); S.h2d_bytes += bases / 8; ctx->d_mask_valid = true; }
+        if (need_mask_plane && !ctx->d_mask_valid) {
+            KGMA_CUDA(ctx, cudaMemcpyAsync((char *)ctx->d_mask + up_lo / 8, (char *)g->mask + up_lo / 8, (size_t)(up_hi - up_lo) / 8, cudaMemcpyHostToDevice, st));
+            S.h2d_bytes += (up_hi - up_lo) / 8; ctx->d_mask_valid = up_lo == 0 && up_hi == (int64_t)bases;
+        }
         KGMA_CUDA(ctx, cudaEventRecord(e1, st));
-        rc = search_to((int64_t)bases, true);
+        rc = search_to(up_hi, true);
         if (rc) return rc;
     }
     if (first_kernel) KGMA_CUDA(ctx, cudaEventRecord(ek, st));
@@ -336,16 +349,23 @@ extern "C" int kgma_exact_match(kgma_ctx *ctx, kgma_genome *g, const char *query
     KGMA_CUDA(ctx, cudaMemcpyAsync(&cnt, d + o_c, 4, cudaMemcpyDeviceToHost, st));
     KGMA_CUDA(ctx, cudaStreamSynchronize(st));
     if (cnt > cap) return set_err(ctx, KGMA_E_CAPACITY, "more than %u exact matches", cap);
-    std::vector<unsigned long long> pos(cnt);
+    pos.resize(cnt);
     if (cnt) KGMA_CUDA(ctx, cudaMemcpy(pos.data(), d + o_out, (size_t)cnt * 8, cudaMemcpyDeviceToHost));
     S.d2h_bytes += 4 + (size_t)cnt * 8;
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); S.h2d_ms = ms;
     cudaEventElapsedTime(&ms, ek, e2); S.filter_ms = ms;
     cudaEventElapsedTime(&ms, e0, e2); S.total_ms = ms;
-    S.bases_scanned = g->total_len;
+    S.bases_scanned = sc == 1 ? g->total_len : range_hi - range_lo;
     if (!(flags & KGMA_F_RESIDENT)) ctx->d_seq_valid = ctx->d_mask_valid = false;
     std::sort(pos.begin(), pos.end());
-    // map to records; keep matches wholly inside a record; apply FindAll's non-overlap rule per record
+    return KGMA_OK;
+}
+
+// map sorted global starts to records; keep matches wholly inside a record; apply FindAll's non-overlap rule per record
+// (ExactMatch.jl:20-30: the search resumes behind the previous match; FindAllOverlap :33-43 keeps every start)
+static int matches_from_starts(kgma_ctx *ctx, const kgma_genome *g, const std::vector<unsigned long long> &pos, int64_t qlen, int overlap,
+                               kgma_match **out, int64_t *n_out)
+{
     std::vector<kgma_match> res;
     size_t pi = 0;
     for (int r = 0; r < (int)g->recs.size(); r++) {
@@ -368,4 +388,47 @@ extern "C" int kgma_exact_match(kgma_ctx *ctx, kgma_genome *g, const char *query
         memcpy(*out, res.data(), res.size() * sizeof(kgma_match));
     }
     return KGMA_OK;
+}
+
+extern "C" int kgma_exact_match(kgma_ctx *ctx, kgma_genome *g, const char *query, int64_t qlen, int overlap,
+                                uint32_t flags, kgma_match **out, int64_t *n_out)
+{
+    if (!ctx || !g || !query || !out || !n_out) return KGMA_E_ARG;
+    *out = nullptr; *n_out = 0;
+    std::vector<unsigned long long> pos;
+    int rc = exact_match_impl(ctx, g, query, qlen, flags, 0, 1, pos);
+    if (rc) return rc;
+    return matches_from_starts(ctx, g, pos, qlen, overlap, out, n_out);
+}
+
+// Multi-GPU form: each context searches its slice and returns the occurrence starts it owns (0-based positions in the packed
+// coordinate space, ascending; *starts is malloc'd, kgma_free); kgma_exact_match_merge, host only, turns the concatenation of
+// all slices' starts (any order) into what exactMatch returns, applying the overlap rule across slice edges.
+extern "C" int kgma_exact_match_shard(kgma_ctx *ctx, kgma_genome *g, const char *query, int64_t qlen, uint32_t flags,
+                                      int shard_index, int shard_count, int64_t **starts, int64_t *n_out)
+{
+    if (!ctx || !g || !query || !starts || !n_out || shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return KGMA_E_ARG;
+    *starts = nullptr; *n_out = 0;
+    std::vector<unsigned long long> pos;
+    int rc = exact_match_impl(ctx, g, query, qlen, flags, shard_index, shard_count, pos);
+    if (rc) return rc;
+    *n_out = (int64_t)pos.size();
+    if (!pos.empty()) {
+        *starts = (int64_t *)malloc(pos.size() * 8);
+        if (!*starts) return set_err(ctx, KGMA_E_CAPACITY, "out of memory");
+        memcpy(*starts, pos.data(), pos.size() * 8);
+    }
+    return KGMA_OK;
+}
+
+extern "C" int kgma_exact_match_merge(const kgma_genome *g, const int64_t *starts, int64_t n, int64_t qlen, int overlap,
+                                      kgma_match **out, int64_t *n_out)
+{
+    if (!g || !out || !n_out || n < 0 || (n && !starts) || qlen < 1) return KGMA_E_ARG;
+    *out = nullptr; *n_out = 0;
+    std::vector<unsigned long long> pos((size_t)n);
+    for (int64_t i = 0; i < n; i++) pos[(size_t)i] = (unsigned long long)starts[i];
+    std::sort(pos.begin(), pos.end());
+    pos.erase(std::unique(pos.begin(), pos.end()), pos.end());
+    return matches_from_starts(nullptr, g, pos, qlen, overlap, out, n_out);
 }

@@ -301,10 +301,72 @@ int kgma_genome_append_bio4(kgma_genome *g, const char *identifier, const char *
     return KGMA_OK;
 }
 
+// Zero-copy ingest for a caller that packs the genome itself (north_star: "the Julia host code packs the genome to 2 bits
+// per base plus an N/ambiguity mask"): the library lays the records out (every record starts at a multiple of 128 bases, so at
+// a whole word of both planes) in page-locked planes of its own; kgma_genome_record_planes hands out where record r's words
+// go; the caller writes them in place (same word format as kgma_genome_append_packed) and seals.  Scans then stream straight
+// from these planes -- the path bench.py's e2e tier measures -- instead of staging a pageable copy.
+int kgma_genome_create_pinned(kgma_ctx *ctx, int n_records, const int64_t *rec_len, kgma_genome **out)
+{
+    if (!ctx || !out || n_records < 1 || !rec_len) return KGMA_E_ARG;
+    KGMA_CUDA(ctx, cudaSetDevice(ctx->device));
+    kgma_genome *g = nullptr; kgma_genome_create(&g);
+    int64_t end = 0;
+    for (int r = 0; r < n_records; r++) {
+        if (rec_len[r] < 0) { delete g; return set_err(ctx, KGMA_E_ARG, "record %d has a negative length", r); }
+        kgma::Record R; R.ident = "record" + std::to_string(r + 1); R.desc = R.ident; R.len = rec_len[r];
+        R.off = (end + REC_ALIGN - 1) / REC_ALIGN * REC_ALIGN; end = R.off + R.len;
+        g->recs.push_back(R); g->total_len += R.len;
+    }
+    const int64_t G = (end + FGROUP - 1) / FGROUP * FGROUP + FGROUP;
+    const int64_t cap = (G + TAIL_PAD + 4095) / 4096 * 4096;
+    if (cudaHostAlloc((void **)&g->seq2, (size_t)cap / 4, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void **)&g->mask, (size_t)cap / 8, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        if (g->seq2) cudaFreeHost(g->seq2);
+        g->seq2 = g->mask = nullptr; delete g;
+        return set_err(ctx, KGMA_E_CUDA, "cudaHostAlloc of %lld bases failed", (long long)cap);
+    }
+    g->host_alloc = true; g->pinned = true; g->cap_bases = cap; g->G = G;
+    memset(g->seq2, 0, (size_t)cap / 4); memset(g->mask, 0, (size_t)cap / 8);
+    *out = g;
+    return KGMA_OK;
+}
+
+int kgma_genome_record_planes(kgma_genome *g, int record, uint32_t **seq2, uint32_t **mask)
+{
+    if (!g || record < 0 || record >= (int)g->recs.size() || !seq2 || !mask || !g->seq2) return KGMA_E_ARG;
+    const int64_t off = g->recs[(size_t)record].off;
+    *seq2 = g->seq2 + (off >> 4); *mask = g->mask + (off >> 5);
+    return KGMA_OK;
+}
+
+int kgma_genome_set_names(kgma_genome *g, int record, const char *identifier, const char *description)
+{
+    if (!g || record < 0 || record >= (int)g->recs.size()) return KGMA_E_ARG;
+    if (identifier) g->recs[(size_t)record].ident = identifier;
+    if (description) g->recs[(size_t)record].desc = description;
+    return KGMA_OK;
+}
+
 int kgma_genome_seal(kgma_genome *g)
 {
     if (!g) return KGMA_E_ARG;
     if (g->sealed) return KGMA_OK;
+    if (g->host_alloc) {
+        // planes filled in place (kgma_genome_create_pinned): clear whatever the caller left behind the records' last
+        // bases, find out whether anything is masked, and publish the new contents
+        for (const kgma::Record &R : g->recs) {
+            const int64_t e = R.off + R.len;
+            if (e & 15) g->seq2[e >> 4] &= (1u << (2 * (e & 15))) - 1;
+            if (e & 31) g->mask[e >> 5] &= (1u << (e & 31)) - 1;
+        }
+        const uint64_t *mw = (const uint64_t *)g->mask;
+        for (int64_t i = 0, n = g->G / 64; i < n && !g->any_mask; i++) if (mw[i]) g->any_mask = true;
+        g->uid = g_uid.fetch_add(1);
+        g->sealed = true;
+        return KGMA_OK;
+    }
     int64_t end = g->recs.empty() ? 0 : g->recs.back().off + g->recs.back().len;
     int64_t G = (end + FGROUP - 1) / FGROUP * FGROUP + FGROUP;     // whole warp groups + one spare group
     int rc = genome_reserve(g, G + TAIL_PAD);

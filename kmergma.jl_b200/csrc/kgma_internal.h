@@ -58,6 +58,7 @@ struct kgma_refs {
 struct kgma_result {
     std::vector<kgma_hit> hits;
     std::vector<kgma_run> runs;
+    std::vector<kgma_run_ext> run_ext;             // kgma_scan_shard: one per run (lo == 0: not extended)
     std::vector<int64_t>  first_D;                 // [n_profiles][n_records]
     std::vector<std::vector<double>> dists;        // per profile
     std::vector<char>     cigar_ops;
@@ -134,18 +135,36 @@ inline uint32_t rev_kmer(uint32_t c, int k) { uint32_t r = 0; for (int j = 0; j 
 // ---- replay.cpp
 struct AlignReq { int32_t record, profile; int64_t first, last; };       // 1-based range to extend
 struct AlignRes { int64_t lo, hi, score; uint32_t cig_off, cig_len; };   // cigar_to_UnitRange result (relative, 1-based)
-struct Pending { size_t hit; size_t req; int64_t first; };                 // hit waiting for its extension result
-void merge_runs(std::vector<kgma_run> &runs);
+struct Pending { size_t hit; size_t req; int64_t first; size_t run; };     // hit waiting for its extension result (run: index of the run that emitted it)
+void merge_runs(std::vector<kgma_run> &runs, std::vector<kgma_run_ext> *ext = nullptr);
 void apply_extensions(kgma_genome *g, std::vector<kgma_hit> &hits, const std::vector<Pending> &pend, const std::vector<AlignRes> &ares);
 int  replay_single_range(kgma_ctx *ctx, kgma_genome *g, const ProfTab &t, const kgma_scan_params &P,
                          const std::vector<kgma_run> &runs, const std::vector<int64_t> &first_D, int r0, int r1,
                          int64_t *genome_pos_io, std::vector<kgma_hit> &hits, std::vector<AlignReq> &reqs, std::vector<Pending> &pend);
 int  replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, const kgma_profile *profiles,
             const kgma_scan_params &P, std::vector<kgma_run> &runs, const std::vector<int64_t> &first_D,
-            kgma_result *res);
+            kgma_result *res, std::vector<kgma_run_ext> *ext = nullptr);
 
 // ---- align.cu
-struct AlignTicket { bool active = false; int slot = 0, nj = 0; void *ho = nullptr; };
+struct AlignOut { long long score; int32_t lower, num_sum, nops, cig_n; };                 // nops < 0: redo with the path-summary kernel
+struct AlignJob2 { long long gpos; int32_t n, a_off, m, b_off; };   // b_off >= 0: subject codes were uploaded (not on the device)
+struct AlignArgs2 {
+    const uint8_t *a;            // consensus codes 0..3, 4 = N
+    const uint32_t *seq;         // packed 2-bit genome on the device
+    const long long *nruns; int n_nruns;   // maximal runs of masked (N) bases, [start,end) global positions, ascending
+    const uint8_t *b;            // uploaded subject codes for jobs whose slice is not on the device
+    const AlignJob2 *jobs; int njobs;
+    int *next_job;
+    AlignOut *out;
+    int go, ge, tie_open, ncol_cap, need_boundary;
+};
+struct AlignTicket {
+    bool active = false; int slot = 0, nj = 0; void *ho = nullptr;
+    // what align_collect needs to redo the alignments the tagged kernel handed back (align.cu)
+    bool tagged = false; void *st = nullptr; size_t smem = 0;
+    void *d_jobs2 = nullptr, *d_out2 = nullptr, *d_cnt = nullptr, *h_jobs = nullptr, *h_jobs2 = nullptr, *h_out2 = nullptr;
+    AlignArgs2 args{};
+};
 int  align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &reqs, const kgma_profile *profiles, int n_profiles,
                    bool single_mode_truncate, int gap_open, int gap_extend, bool tie_open, cudaStream_t st, int slot, AlignTicket *t);
 int  align_collect(kgma_ctx *ctx, AlignTicket *t, std::vector<AlignRes> &out);

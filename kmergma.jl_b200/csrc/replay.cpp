@@ -14,7 +14,11 @@
 
 namespace kgma {
 
-void merge_runs(std::vector<kgma_run> &runs)
+static void merge_runs_slow(std::vector<kgma_run> &runs, std::vector<kgma_run_ext> *ext);
+
+// `ext` (optional, parallel to `runs`): the extension result a shard computed for each run's own first-argmin window
+// (kgma_scan_shard).  A merged run keeps the result of the piece that supplies its argmin.
+void merge_runs(std::vector<kgma_run> &runs, std::vector<kgma_run_ext> *ext)
 {
     static thread_local std::vector<uint32_t> order;
     bool sorted_by_index = false;
@@ -31,6 +35,7 @@ void merge_runs(std::vector<kgma_run> &runs)
         bool ok = runs.size() > 1 && runs.size() < ((size_t)1 << 31);
         for (const kgma_run &r : runs)
             if (r.profile < 0 || r.profile >= 16 || r.record < 0 || r.record >= (1 << 24) || r.t_first < 0 || r.t_first >= ((int64_t)1 << 35)) { ok = false; break; }
+        if (!ok && ext) { merge_runs_slow(runs, ext); return; }
         if (!ok) std::sort(runs.begin(), runs.end(), less);
         else {
             struct KI { uint64_t key; uint32_t idx; };
@@ -61,10 +66,12 @@ void merge_runs(std::vector<kgma_run> &runs)
         }
     }
     static thread_local std::vector<kgma_run> out;
-    out.clear();
+    static thread_local std::vector<kgma_run_ext> out_ext;
+    out.clear(); out_ext.clear();
     out.reserve(runs.size());
     for (size_t ri = 0; ri < runs.size(); ri++) {
-        const kgma_run &r = sorted_by_index ? runs[order[ri]] : runs[ri];  // (merged straight out of the unsorted array: no gather copy)
+        const size_t src = sorted_by_index ? order[ri] : ri;
+        const kgma_run &r = runs[src];                                      // (merged straight out of the unsorted array: no gather copy)
         if (!out.empty() && out.back().profile == r.profile && out.back().record == r.record) {
             kgma_run &p = out.back();
             const bool pm = (p.flags & KGMA_RUN_MARKER) != 0, rm = (r.flags & KGMA_RUN_MARKER) != 0;
@@ -72,9 +79,13 @@ void merge_runs(std::vector<kgma_run> &runs)
             if (!pm && !rm && r.t_first <= p.t_last + 1) {
                 // pieces of one maximal run: cut by a span / chunk / shard boundary (adjacent), or reported twice because a
                 // span was evaluated again (overlapping, same D values).  Min of minima, earlier argmin on ties.
-                if (r.D_min < p.D_min) { p.D_min = r.D_min; p.t_argmin = r.t_argmin; p.flags = (p.flags & ~KGMA_HIT_ARGMIN_TIE) | (r.flags & KGMA_HIT_ARGMIN_TIE); }
+                if (r.D_min < p.D_min) {
+                    p.D_min = r.D_min; p.t_argmin = r.t_argmin; p.flags = (p.flags & ~KGMA_HIT_ARGMIN_TIE) | (r.flags & KGMA_HIT_ARGMIN_TIE);
+                    if (ext) out_ext.back() = (*ext)[src];
+                }
                 else if (r.D_min == p.D_min) {
                     if (r.t_argmin != p.t_argmin) p.flags |= KGMA_HIT_ARGMIN_TIE;
+                    if (ext && (r.t_argmin < p.t_argmin || (r.t_argmin == p.t_argmin && out_ext.back().lo == 0))) out_ext.back() = (*ext)[src];
                     p.t_argmin = std::min(p.t_argmin, r.t_argmin);
                     p.flags |= (r.flags & KGMA_HIT_ARGMIN_TIE);
                 }
@@ -84,8 +95,48 @@ void merge_runs(std::vector<kgma_run> &runs)
             }
         }
         out.push_back(r);
+        if (ext) out_ext.push_back((*ext)[src]);
     }
     runs.assign(out.begin(), out.end());
+    if (ext) ext->assign(out_ext.begin(), out_ext.end());
+}
+
+// merge with extension results for run lists the radix path does not take (out-of-range keys, fewer than two runs):
+// sort an index array with the same order, permute both arrays, then run the linear merge on the sorted input
+static void merge_runs_slow(std::vector<kgma_run> &runs, std::vector<kgma_run_ext> *ext)
+{
+    std::vector<size_t> idx(runs.size());
+    for (size_t i = 0; i < idx.size(); i++) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](size_t x, size_t y) {
+        const kgma_run &a = runs[x], &b = runs[y];
+        if (a.profile != b.profile) return a.profile < b.profile;
+        if (a.record != b.record) return a.record < b.record;
+        if (a.t_first != b.t_first) return a.t_first < b.t_first;
+        return (a.flags & KGMA_RUN_MARKER) < (b.flags & KGMA_RUN_MARKER);
+    });
+    std::vector<kgma_run> out; std::vector<kgma_run_ext> out_ext;
+    for (size_t src : idx) {
+        const kgma_run &r = runs[src];
+        if (!out.empty() && out.back().profile == r.profile && out.back().record == r.record) {
+            kgma_run &p = out.back();
+            const bool pm = (p.flags & KGMA_RUN_MARKER) != 0, rm = (r.flags & KGMA_RUN_MARKER) != 0;
+            if (pm && rm && p.t_first == r.t_first) continue;
+            if (!pm && !rm && r.t_first <= p.t_last + 1) {
+                if (r.D_min < p.D_min) { p.D_min = r.D_min; p.t_argmin = r.t_argmin; p.flags = (p.flags & ~KGMA_HIT_ARGMIN_TIE) | (r.flags & KGMA_HIT_ARGMIN_TIE); out_ext.back() = (*ext)[src]; }
+                else if (r.D_min == p.D_min) {
+                    if (r.t_argmin != p.t_argmin) p.flags |= KGMA_HIT_ARGMIN_TIE;
+                    if (r.t_argmin < p.t_argmin || (r.t_argmin == p.t_argmin && out_ext.back().lo == 0)) out_ext.back() = (*ext)[src];
+                    p.t_argmin = std::min(p.t_argmin, r.t_argmin);
+                    p.flags |= (r.flags & KGMA_HIT_ARGMIN_TIE);
+                }
+                p.flags |= (r.flags & KGMA_HIT_NEAR_THR);
+                if (r.t_last >= p.t_last) { p.flags = (p.flags & ~KGMA_RUN_OPEN_RIGHT) | (r.flags & KGMA_RUN_OPEN_RIGHT); p.t_last = r.t_last; }
+                continue;
+            }
+        }
+        out.push_back(r); out_ext.push_back((*ext)[src]);
+    }
+    runs.swap(out); ext->swap(out_ext);
 }
 
 static uint32_t round_half_flag(double d)
@@ -148,7 +199,7 @@ int replay_single_range(kgma_ctx *ctx, kgma_genome *g, const ProfTab &t, const k
                         kgma_hit h{};
                         h.record = r; h.profile = 0; h.cmi = CMI; h.first = a; h.last = bb; h.genome_pos = genome_pos;
                         h.D = cur; h.dist = (double)cur / t.denom; h.flags = hflags | round_half_flag(h.dist);
-                        if (do_align) { pend.push_back({ hits.size(), reqs.size(), a }); reqs.push_back({ r, 0, a, bb }); }
+                        if (do_align) { pend.push_back({ hits.size(), reqs.size(), a, j }); reqs.push_back({ r, 0, a, bb }); }
                         hits.push_back(h);
                         cur = INT64_MAX;                  // :102 currminim = kmerDist (some value >= thr)
                     }
@@ -163,7 +214,7 @@ int replay_single_range(kgma_ctx *ctx, kgma_genome *g, const ProfTab &t, const k
 
 int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, const kgma_profile *profiles,
            const kgma_scan_params &P, std::vector<kgma_run> &runs, const std::vector<int64_t> &first_D,
-           kgma_result *res)
+           kgma_result *res, std::vector<kgma_run_ext> *ext)
 {
     const int C = (int)tabs.size(), nr = (int)g->recs.size(), k = tabs[0].k;
     const bool cluster = P.mode == KGMA_MODE_CLUSTER;
@@ -174,7 +225,7 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
     const bool trace = getenv("KGMA_TRACE") != nullptr;
     auto tnow = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tr0 = tnow();
-    merge_runs(runs);
+    merge_runs(runs, ext);
     const double tr1 = tnow();
     res->hits.clear(); res->cigar_ops.clear(); res->cigar_cnt.clear();
 
@@ -205,7 +256,16 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
         if (rc) return rc;
         const double tr2 = tnow();
         if (trace) fprintf(stderr, "[kgma replay] merge %.3f ms, state machine %.3f ms (%zu runs, %zu requests)\n", tr1 - tr0, tr2 - tr1, runs.size(), reqs.size());
-        if (do_align && !reqs.empty()) {
+        if (do_align && !reqs.empty() && ext) {
+            // the shards extended every run's own candidate window already (kgma_scan_shard): look the results up
+            ares.assign(reqs.size(), AlignRes{ 1, 0, 0, 0, 0 });
+            for (const Pending &p : pend) {
+                const kgma_run_ext &e = (*ext)[p.run];
+                if (e.lo == 0) return set_err(ctx, KGMA_E_STATE, "run %zu emits a hit but carries no extension result", p.run);
+                ares[p.req] = AlignRes{ e.lo, e.hi, e.score, 0, 0 };
+            }
+            apply_extensions(g, res->hits, pend, ares);
+        } else if (do_align && !reqs.empty()) {
             rc = align_batch_device(ctx, g, reqs, profiles, 1, true, P.gap_open, P.gap_extend,
                                     (P.flags & KGMA_F_TIE_OPEN) != 0, want_cig, ares,
                                     want_cig ? &res->cigar_ops : nullptr, want_cig ? &res->cigar_cnt : nullptr);
@@ -251,6 +311,7 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
 
     std::vector<char> have(runs.size(), 0);               // extension result of this run's candidate is known
     std::vector<AlignRes> res_of_run(runs.size());
+    if (ext) for (size_t i = 0; i < runs.size(); i++) if ((*ext)[i].lo != 0) { have[i] = 1; res_of_run[i] = AlignRes{ (*ext)[i].lo, (*ext)[i].hi, (*ext)[i].score, 0, 0 }; }
     std::vector<size_t> missing;
     int64_t n_align_total = 0;
     std::vector<std::vector<kgma_hit>> rec_hits((size_t)nr);   // per record: a record whose pass needed no speculation is final
@@ -304,6 +365,7 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
             genome_pos += L;                                                            // :159 - every record
         }
         if (missing.empty()) break;                       // no speculation: this pass is the reference's result
+        if (!ctx) return set_err(ctx, KGMA_E_STATE, "%zu runs emit hits but carry no extension result (host-only replay)", missing.size());
         if (round >= 3) {                                 // stop chasing: extend every terminated run that is still unknown
             missing.clear();
             for (size_t i = 0; i < runs.size(); i++) {

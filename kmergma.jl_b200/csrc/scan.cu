@@ -834,6 +834,13 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     // ---- upload range (bases): shard + halo, unless resident
     const int64_t halo = (int64_t)((M + 1) * FBLOCK + pl.maxws + 64);
     int64_t up_lo = pos_lo, up_hi = std::min(g->G + TAIL_PAD, pos_hi + halo + 3 * FGROUP);
+    if (sc > 1 && (P.flags & KGMA_F_ALIGN)) {
+        // kgma_scan_shard extends its own candidates: their windows reach buff bases to the left of the first owned window
+        // and window + buff to the right of the last one
+        const int64_t reach = (std::max<int64_t>(P.buff, 0) + pl.maxws + FGROUP - 1) / FGROUP * FGROUP;
+        up_lo = std::max<int64_t>(0, pos_lo - reach);
+        up_hi = std::min(g->G + TAIL_PAD, up_hi + reach);
+    }
     if (si == sc - 1) up_hi = g->G + TAIL_PAD;
     up_hi = (up_hi + 127) / 128 * 128; up_hi = std::min(up_hi, g->G + TAIL_PAD);
     const bool resident_ok = (P.flags & KGMA_F_RESIDENT) && ctx->d_seq_valid && ctx->d_valid_lo <= up_lo && ctx->d_valid_hi >= up_hi;
@@ -1047,6 +1054,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     }
     const double t_cand0 = now_ms();
     st.blocks_total = any_filter ? blk_hi - blk_lo : 0;
+    for (const FilterGroup &fg : groups) if (fg.ft) st.filter_passes++;
     for (size_t gi = 0; gi < groups.size(); gi++) {
         if (groups[gi].ft) { st.blocks_flagged += cnts[1 + gi]; }
         st.exact_windows += groups[gi].dense ? span_windows * (int64_t)groups[gi].q.size() : (int64_t)std::min(cnts[1 + gi], cand_cap) * FBLOCK * (int64_t)groups[gi].q.size();
@@ -1094,11 +1102,13 @@ static int scan_runs_retry(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pr
 {
     uint64_t need = 0;
     int rc = scan_runs_impl(ctx, g, profiles, C, P, pl, res, 1u << 20, &need, hook);
-    if (rc == KGMA_E_CAPACITY && need > 0 && need < (1ull << 28)) {
+    // a retry can overflow again: when a candidate list overflowed too, the dense re-evaluation reports every partial run a
+    // second time (up to twice the count the first attempt saw), so the capacity doubles per attempt, a few times at most
+    for (int attempt = 0; attempt < 4 && rc == KGMA_E_CAPACITY && need > 0 && need < (1ull << 28); attempt++) {
         pl = ScanPlan();
         if (hook) { hook->used = false; hook->n_runs_first = 0; }
         if (reset) reset();
-        rc = scan_runs_impl(ctx, g, profiles, C, P, pl, res, (uint32_t)(need + need / 8 + 1024), &need, nullptr);
+        rc = scan_runs_impl(ctx, g, profiles, C, P, pl, res, (uint32_t)std::min<uint64_t>(2 * need + 1024, 1ull << 28), &need, nullptr);
     }
     return rc;
 }
@@ -1112,6 +1122,109 @@ int kgma_scan_runs(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, 
     kgma_result *res = result_acquire();
     ScanPlan pl;
     int rc = scan_runs_retry(ctx, g, profiles, n_profiles, *params, pl, res);
+    if (rc) { result_release(res); return rc; }
+    *out = res;
+    return KGMA_OK;
+}
+
+// ---- multi-GPU, one call per rank ------------------------------------------------------------------------------
+// The shard's runs are merged, and the candidate window of every run that can still end up as a hit (its own first
+// argmin: a superset of what the replay can select) is extended right here, on the GPU that holds
+// the bases.  What leaves the rank is (run, extension result) pairs -- a few KB; the replay of all shards' pairs is
+// pure host logic (kgma_replay_packed) and needs no device at all, so no rank waits for another rank's kernels.
+int kgma_scan_shard(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int n_profiles,
+                    const kgma_scan_params *params, kgma_result **out)
+{
+    if (!ctx || !g || !params || !out) return KGMA_E_ARG;
+    if (params->flags & (KGMA_F_WANT_CIGARS | KGMA_F_WANT_DISTS)) return set_err(ctx, KGMA_E_UNSUPPORTED, "kgma_scan_shard returns neither CIGARs nor distances");
+    kgma_result *res = result_acquire();
+    ScanPlan pl;
+    int rc = scan_runs_retry(ctx, g, profiles, n_profiles, *params, pl, res);
+    if (rc) { result_release(res); return rc; }
+    const double t0 = now_ms();
+    const kgma_scan_params &P = *params;
+    merge_runs(res->runs);
+    res->run_ext.assign(res->runs.size(), kgma_run_ext{ 0, 0, 0 });
+    if (P.flags & KGMA_F_ALIGN) {
+        std::vector<AlignReq> reqs; std::vector<size_t> of_run;
+        for (size_t i = 0; i < res->runs.size(); i++) {
+            const kgma_run &ru = res->runs[i];
+            if (ru.flags & KGMA_RUN_MARKER) continue;
+            if (ru.t_last >= pl.steps[(size_t)ru.record]) continue;          // reaches the record's last step: never emitted
+            const int64_t L = g->recs[(size_t)ru.record].len, wsq = pl.tabs[(size_t)ru.profile].ws;
+            const int64_t CMI = pl.cluster ? ru.t_argmin : (int64_t)pl.k + ru.t_argmin;   // OmnGenomeMiner.jl:117 / GenomeMiner.jl:85,92
+            reqs.push_back({ ru.record, ru.profile, std::max<int64_t>(CMI - P.buff, 1), std::min<int64_t>(CMI + wsq - 1 + P.buff, L) });
+            of_run.push_back(i);
+        }
+        std::vector<AlignRes> ares;
+        rc = align_batch_device(ctx, g, reqs, profiles, n_profiles, !pl.cluster, P.gap_open, P.gap_extend,
+                                (P.flags & KGMA_F_TIE_OPEN) != 0, false, ares, nullptr, nullptr);
+        if (rc) { result_release(res); return rc; }
+        for (size_t j = 0; j < of_run.size(); j++) res->run_ext[of_run[j]] = kgma_run_ext{ ares[j].lo, ares[j].hi, ares[j].score };
+        ctx->stats.n_align = (int64_t)reqs.size();
+    }
+    ctx->stats.n_runs = (int64_t)res->runs.size();
+    const double dt = now_ms() - t0;
+    ctx->stats.host_replay_ms = dt; ctx->stats.wall_ms += dt;
+    *out = res;
+    return KGMA_OK;
+}
+
+const kgma_run_ext *kgma_result_run_ext(const kgma_result *r) { return r && !r->run_ext.empty() ? r->run_ext.data() : nullptr; }
+
+// Fixed-layout transport block of one shard's result: what the ranks exchange (one all-gather of equal-sized blocks).
+struct PackHdr { uint32_t magic, version; int64_t n_runs, n_first, bytes; };
+static const uint32_t PACK_MAGIC = 0x4b474d41u;   // "KGMA"
+
+int64_t kgma_result_pack(const kgma_result *r, void *buf, int64_t cap)
+{
+    if (!r) return KGMA_E_ARG;
+    const size_t n = r->runs.size(), nf = r->first_D.size();
+    const bool with_ext = r->run_ext.size() == n;
+    const int64_t need = (int64_t)(sizeof(PackHdr) + n * (sizeof(kgma_run) + sizeof(kgma_run_ext)) + nf * 8);
+    if (!buf || cap < need) return need;
+    unsigned char *p = (unsigned char *)buf;
+    PackHdr h{ PACK_MAGIC, 1, (int64_t)n, (int64_t)nf, need };
+    memcpy(p, &h, sizeof h); p += sizeof h;
+    if (n) memcpy(p, r->runs.data(), n * sizeof(kgma_run));
+    p += n * sizeof(kgma_run);
+    if (n && with_ext) memcpy(p, r->run_ext.data(), n * sizeof(kgma_run_ext)); else if (n) memset(p, 0, n * sizeof(kgma_run_ext));
+    p += n * sizeof(kgma_run_ext);
+    if (nf) memcpy(p, r->first_D.data(), nf * 8);
+    return need;
+}
+
+int kgma_replay_packed(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int n_profiles,
+                       const kgma_scan_params *params, const void *blocks, int n_blocks, int64_t stride, kgma_result **out)
+{
+    // ctx may be NULL: with extension results in the blocks the replay is host-only
+    if (!g || !params || !out || !blocks || n_blocks < 1 || stride < (int64_t)sizeof(PackHdr)) return KGMA_E_ARG;
+    ScanPlan pl;
+    kgma_scan_params P = *params; P.shard_index = 0; P.shard_count = 1;
+    int rc = make_plan(ctx, g, profiles, n_profiles, P, pl);
+    if (rc) return rc;
+    const size_t nfd = (size_t)n_profiles * g->recs.size();
+    kgma_result *res = result_acquire();
+    res->runs.clear(); res->run_ext.clear();
+    std::vector<int64_t> fd(nfd, INT64_MIN);
+    for (int b = 0; b < n_blocks; b++) {
+        const unsigned char *p = (const unsigned char *)blocks + (size_t)b * (size_t)stride;
+        PackHdr h; memcpy(&h, p, sizeof h);
+        if (h.magic != PACK_MAGIC || h.version != 1 || h.n_runs < 0 || h.bytes > stride || (size_t)h.n_first != nfd) {
+            result_release(res);
+            return set_err(ctx, KGMA_E_ARG, "shard block %d is not a kgma_result_pack block of this scan (or did not fit its %lld bytes)", b, (long long)stride);
+        }
+        const kgma_run *ru = (const kgma_run *)(p + sizeof h);
+        const kgma_run_ext *ex = (const kgma_run_ext *)(ru + h.n_runs);
+        const int64_t *f = (const int64_t *)(ex + h.n_runs);
+        res->runs.insert(res->runs.end(), ru, ru + h.n_runs);
+        res->run_ext.insert(res->run_ext.end(), ex, ex + h.n_runs);
+        for (size_t i = 0; i < nfd; i++) fd[i] = std::max(fd[i], f[i]);     // INT64_MIN where a shard does not own window 0
+    }
+    res->first_D = fd;
+    const double t0 = now_ms();
+    rc = replay(ctx, g, pl.tabs, profiles, P, res->runs, fd, res, (P.flags & KGMA_F_ALIGN) ? &res->run_ext : nullptr);
+    if (ctx) { ctx->stats.host_replay_ms = now_ms() - t0; }
     if (rc) { result_release(res); return rc; }
     *out = res;
     return KGMA_OK;

@@ -36,8 +36,15 @@ struct StagedUpload {
             cudaGetLastError(); munmap(p, bytes);
             return set_err(ctx, KGMA_E_CUDA, "cudaHostRegister of the staging ring failed");
         }
+        // the ring is published only once every event exists: a failed cudaEventCreate must not leave it marked ready
+        for (auto &e : ctx->stage_ev) {
+            if (e) continue;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+                e = nullptr; cudaGetLastError(); cudaHostUnregister(p); munmap(p, bytes);
+                return set_err(ctx, KGMA_E_CUDA, "cudaEventCreate for the staging ring failed");
+            }
+        }
         ctx->stage = p; ctx->stage_bytes = bytes;
-        for (auto &e : ctx->stage_ev) KGMA_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         return KGMA_OK;
     }
     void start(kgma_ctx *c, const char *s, size_t bytes)

@@ -56,6 +56,7 @@ typedef struct {
     char   **desc;    /* FASTA.description: whole header line            */
     char   **seq;     /* upper-cased residues                            */
     int64_t *len;
+    int      borrowed; /* seq[] point into caller-owned memory (orc_fasta_wrap): not freed here */
 } orc_fasta;
 
 static void *xrealloc(void *p, size_t n) { void *q = realloc(p, n ? n : 1); if (!q) abort(); return q; }
@@ -63,8 +64,23 @@ static void *xrealloc(void *p, size_t n) { void *q = realloc(p, n ? n : 1); if (
 void orc_fasta_free(orc_fasta *f)
 {
     if (!f) return;
-    for (int i = 0; i < f->n; i++) { free(f->ident[i]); free(f->desc[i]); free(f->seq[i]); }
+    for (int i = 0; i < f->n; i++) { free(f->ident[i]); free(f->desc[i]); if (!f->borrowed) free(f->seq[i]); }
     free(f->ident); free(f->desc); free(f->seq); free(f->len); free(f);
+}
+
+/* One record over caller-owned, upper-case residues (no copy): lets the full-size parity tests hand a 250 Mb
+ * contig to the scan functions below without writing it to disk first. */
+orc_fasta *orc_fasta_wrap(const char *desc, char *seq, int64_t len)
+{
+    orc_fasta *f = (orc_fasta *)calloc(1, sizeof *f);
+    f->n = 1; f->borrowed = 1;
+    f->ident = (char **)xrealloc(NULL, sizeof(char *)); f->desc = (char **)xrealloc(NULL, sizeof(char *));
+    f->seq = (char **)xrealloc(NULL, sizeof(char *)); f->len = (int64_t *)xrealloc(NULL, sizeof(int64_t));
+    f->desc[0] = strdup(desc);
+    size_t ie = 0; while (desc[ie] && !isspace((unsigned char)desc[ie])) ie++;
+    f->ident[0] = strndup(desc, ie);
+    f->seq[0] = seq; f->len[0] = len;
+    return f;
 }
 
 orc_fasta *orc_fasta_read(const char *path)

@@ -46,12 +46,16 @@ def lib():
         L.orc_fasta_read.restype = C.c_void_p
         L.orc_fasta_read.argtypes = [C.c_char_p]
         L.orc_fasta_free.argtypes = [C.c_void_p]
+        L.orc_fasta_wrap.restype = C.c_void_p
+        L.orc_fasta_wrap.argtypes = [C.c_char_p, C.c_void_p, C.c_int64]
         L.orc_fasta_n.argtypes = [C.c_void_p]
         L.orc_fasta_len.restype = C.c_int64
         L.orc_fasta_len.argtypes = [C.c_void_p, C.c_int]
-        for f in (L.orc_fasta_seq, L.orc_fasta_ident, L.orc_fasta_desc):
+        for f in (L.orc_fasta_ident, L.orc_fasta_desc):
             f.restype = C.c_char_p
             f.argtypes = [C.c_void_p, C.c_int]
+        L.orc_fasta_seq.restype = C.c_void_p          # (a raw address: slices are copied out with string_at)
+        L.orc_fasta_seq.argtypes = [C.c_void_p, C.c_int]
         L.orc_profile_new.restype = C.c_void_p
         L.orc_profile_new.argtypes = [C.c_int64]
         L.orc_profile_del.argtypes = [C.c_void_p]
@@ -115,9 +119,19 @@ class Fasta:
 
     def __init__(self, path: str):
         self.path = path
+        self._keep = None
         self._h = lib().orc_fasta_read(path.encode())
         if not self._h:
             raise OracleError(f"cannot read {path}")
+
+    @classmethod
+    def wrap(cls, description: str, residues: np.ndarray) -> "Fasta":
+        """one record over an in-memory uint8 array of upper-case residues (not copied; kept alive by this object)"""
+        self = cls.__new__(cls)
+        self.path = None
+        self._keep = np.ascontiguousarray(residues, dtype=np.uint8)
+        self._h = lib().orc_fasta_wrap(description.encode(), self._keep.ctypes.data, self._keep.size)
+        return self
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -128,7 +142,12 @@ class Fasta:
         return lib().orc_fasta_n(self._h)
 
     def seq(self, r: int) -> str:
-        return lib().orc_fasta_seq(self._h, r).decode()
+        return C.string_at(lib().orc_fasta_seq(self._h, r), self.seqsize(r)).decode()
+
+    def subseq(self, r: int, first: int, last: int) -> str:
+        """view(seq, first:last), 1-based inclusive, without materialising the whole record"""
+        n = max(0, last - first + 1)
+        return C.string_at(lib().orc_fasta_seq(self._h, r) + first - 1, n).decode() if n else ""
 
     def identifier(self, r: int) -> str:
         return lib().orc_fasta_ident(self._h, r).decode()
@@ -333,9 +352,8 @@ def _hits(f: Fasta, arr, n) -> List[Hit]:
     out = []
     for i in range(n):
         h = arr[i]
-        s = f.seq(h.record)
         out.append(Hit(h.record, f.identifier(h.record), h.kfv, h.dist, h.first, h.last,
-                       h.genome_pos, h.cmi, s[h.first - 1:h.last]))
+                       h.genome_pos, h.cmi, f.subseq(h.record, h.first, h.last)))
     return out
 
 

@@ -26,3 +26,17 @@ def pytest_configure(config):
     import subprocess
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "kmergma.jl_b200", "csrc")], stdout=subprocess.DEVNULL)
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+
+
+# Tie-waiver accounting of tests/test_gpu_parity.py::assert_parity: how many device-vs-oracle comparisons ran, and how many
+# hits (in how many localised blocks) differed from the faithful Float64 oracle next to a run the device had flagged
+# (KGMA_HIT_NEAR_THR / KGMA_HIT_ARGMIN_TIE) while matching the exact-arithmetic oracle bit for bit.
+WAIVER = {"comparisons": 0, "hits_compared": 0, "comparisons_with_waiver": 0, "waived_blocks": 0, "waived_hits": 0}
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    if WAIVER["comparisons"]:
+        terminalreporter.write_line(
+            "tie waiver: %(comparisons)d device-vs-oracle comparisons (%(hits_compared)d hits, all bit-exact against the exact-arithmetic "
+            "oracle); %(comparisons_with_waiver)d of them differed from the faithful Float64 oracle, in %(waived_blocks)d localised blocks "
+            "(%(waived_hits)d hits), each next to a run the device flagged NEAR_THR / ARGMIN_TIE" % WAIVER)

@@ -45,14 +45,6 @@ RUN_DT = np.dtype([("record", "<i4"), ("profile", "<i4"), ("t_first", "<i8"), ("
                    ("D_min", "<i8"), ("flags", "<u4"), ("reserved", "<u4")])
 
 
-def ties_reported(K, kout) -> bool:
-    """did the device report an event whose outcome in the reference depends on Float64 rounding history: a window
-    inside the 1e-9 band around a threshold (KGMA_HIT_NEAR_THR on a run, or a KGMA_RUN_MARKER entry), or a run
-    minimum attained by more than one window (KGMA_HIT_ARGMIN_TIE)?"""
-    runs = np.frombuffer(kout.runs.tobytes(), dtype=RUN_DT)
-    return bool(np.any(runs["flags"] & (K.L.HIT_NEAR_THR | K.L.HIT_ARGMIN_TIE)))
-
-
 def hits_equal(K, kout, ohits, cluster=False):
     if len(kout.hits) != len(ohits):
         return "count %d != %d" % (len(kout.hits), len(ohits))
@@ -74,29 +66,68 @@ def assert_hits_equal(K, kout, ohits, cluster=False):
     assert err is None, err
 
 
-def assert_parity(K, O, kout, run_oracle, N, cluster=False):
-    """run_oracle() -> oracle hits.  Two checks:
+def check_parity(K, kout, oe, of, cluster=False, reach=1500):
+    """oe / of: the oracle's hits in exact arithmetic / in the reference's Float64 accumulation order.
 
-    1. ALWAYS: bit-exact against the oracle's state machine run in exact arithmetic (O.exact_arithmetic: same
-       control flow, integer distance D = d*2kN^2, no rounding) - positions, profile ids and D itself.
-    2. Against the faithful Float64 restatement (the reference's accumulation order): bit-exact positions and
-       dist within 1e-9 UNLESS the device reported a tie (ties_reported).  At an exact tie (d == thr, common for
-       one-member clusters whose distances are multiples of 1/(2k); or two windows with the same run minimum) the
-       reference's own outcome depends on its rounding history, which no segment-parallel scan can reproduce and
-       which is unpinned anyway (Distances.sqeuclidean's summation order); north_star asks for these to be
-       reported separately, which the flags do.  Returns the oracle hits the device agreed with."""
-    with O.exact_arithmetic(N):
-        oe = run_oracle()
+    1. ALWAYS: bit-exact against the exact-arithmetic oracle (same control flow, integer distance D = d*2kN^2, no
+       rounding): positions, profile ids and D itself.
+    2. Against the faithful Float64 restatement: bit-exact positions and dist within 1e-9, EXCEPT inside localised blocks
+       that the device itself marked as rounding-dependent.  The two hit lists are aligned record by record; every maximal
+       block of hits that do not pair up must lie within `reach` bases (two windows + buffers: how far goal_ind /
+       prev_hit_range / the carried minimum propagate a different decision) of a run the device flagged -- a window inside
+       the 1e-9 band around thr (KGMA_HIT_NEAR_THR, incl. KGMA_RUN_MARKER entries) or a run minimum attained twice
+       (KGMA_HIT_ARGMIN_TIE); a hit whose coordinates agree but whose distance does not must carry such a flag itself.
+       There the reference's own outcome depends on its rounding history (and on Distances.sqeuclidean's unpinned
+       summation order); north_star asks for these hits to be reported separately, which the flags do.  Anything else fails.
+    Every use of the waiver is counted (conftest.WAIVER, printed in the pytest summary).  Returns the oracle hits the
+    device agreed with."""
+    import difflib
+    from conftest import WAIVER
     err = hits_equal(K, kout, oe, cluster)
     assert err is None, "exact-arithmetic oracle: " + err
     for h, o in zip(kout.hits, oe):
         assert h.dist == o.dist
-    of = run_oracle()
+    WAIVER["comparisons"] += 1
+    WAIVER["hits_compared"] += len(kout.hits)
     err = hits_equal(K, kout, of, cluster)
     if err is None:
         return of
-    assert ties_reported(K, kout), "faithful Float64 oracle differs although no tie was reported: " + err
+    runs = np.frombuffer(kout.runs.tobytes(), dtype=RUN_DT)
+    fl = runs[(runs["flags"] & (K.L.HIT_NEAR_THR | K.L.HIT_ARGMIN_TIE)) != 0]
+    TIE = K.L.HIT_NEAR_THR | K.L.HIT_ARGMIN_TIE
+    nrec = max([int(h.record) for h in kout.hits] + [int(o.record) for o in of] + [0]) + 1
+    blocks = hits_waived = 0
+    for r in range(nrec):
+        dv = [h for h in kout.hits if int(h.record) == r]
+        fa = [o for o in of if int(o.record) == r]
+        kd = [(int(h.first), int(h.last), int(h.genome_pos), int(h.profile) if cluster else 0) for h in dv]
+        kf = [(int(o.first), int(o.last), int(o.genome_pos), int(o.kfv) if cluster else 0) for o in fa]
+        fr = fl[fl["record"] == r]
+        for tag, i1, i2, j1, j2 in difflib.SequenceMatcher(None, kd, kf, autojunk=False).get_opcodes():
+            if tag == "equal":
+                for h, o in zip(dv[i1:i2], fa[j1:j2]):
+                    if abs(h.dist - o.dist) > REL * max(abs(o.dist), 1e-300):
+                        assert int(h["flags"]) & TIE, "record %d hit %d:%d: distance %r != %r without a tie flag" % (r, h.first, h.last, h.dist, o.dist)
+                        blocks += 1; hits_waived += 1
+                continue
+            span = [k_[0] for k_ in kd[i1:i2] + kf[j1:j2]] + [k_[1] for k_ in kd[i1:i2] + kf[j1:j2]]
+            lo, hi = min(span) - reach, max(span) + reach
+            near = fr[(fr["t_last"] + 1 >= lo) & (fr["t_first"] + 1 <= hi)]
+            assert len(near), ("faithful Float64 oracle differs in record %d around %d..%d although the device flagged no run there: device %r, oracle %r"
+                               % (r, min(span), max(span), kd[i1:i2], kf[j1:j2]))
+            blocks += 1; hits_waived += max(i2 - i1, j2 - j1)
+    assert blocks > 0, "faithful Float64 oracle differs but no differing block was found: " + err
+    WAIVER["comparisons_with_waiver"] += 1
+    WAIVER["waived_blocks"] += blocks
+    WAIVER["waived_hits"] += hits_waived
     return oe
+
+
+def assert_parity(K, O, kout, run_oracle, N, cluster=False, reach=1500):
+    """run_oracle() -> oracle hits; runs it in exact arithmetic (O.exact_arithmetic(N)) and faithfully, then check_parity."""
+    with O.exact_arithmetic(N):
+        oe = run_oracle()
+    return check_parity(K, kout, oe, run_oracle(), cluster, reach)
 
 
 # ------------------------------------------------------------------ goldens: GenomeMiner.jl
@@ -457,6 +488,102 @@ def test_sharded_runs_replay_equals_whole(K, prof, synth, shards):
         assert len(whole.hits) >= 10
 
 
+def _straddling_genome(K, O, n_groups=101, seed=31):
+    """one record of n_groups * 2048 - 77 bases (so that the packed genome has n_groups + 1 warp groups and the slice edges of
+    every shard count are known in advance), with homologues of several clusters planted ON the slice edges for 2, 3 and 8
+    shards, pairs of homologues closer than a window on both sides of an edge, and a second, short record behind it"""
+    rng = np.random.default_rng(seed)
+    refs = O.Fasta(TF)
+    rseq = [refs.seq(i) for i in range(len(refs))]
+    L = n_groups * 2048 - 77
+    seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=L)].copy()
+    ngrp = n_groups + 1                                   # seal: whole groups + one spare
+    edges = sorted(set((ngrp * s_ // n) * 2048 for n in (2, 3, 8) for s_ in range(1, n)))
+    planted = []
+    for i, e in enumerate(edges):
+        for j, d in enumerate((-150, 160) if i % 2 else (-40,)):           # straddling the edge / two copies < ws apart around it
+            m = np.frombuffer(_mutate(rng, rseq[(7 * i + 3 * j) % len(rseq)], 0.03 * (i % 3), i % 4 == 1).encode(), dtype=np.uint8)
+            p = e + d
+            if 0 < p and p + m.size < L:
+                seq[p:p + m.size] = m
+                planted.append(p)
+    for t in range(12):                                   # and some away from every edge
+        m = np.frombuffer(_mutate(rng, rseq[int(rng.integers(0, len(rseq)))], 0.05, t % 3 == 0).encode(), dtype=np.uint8)
+        p = int(rng.integers(3000, L - 3000))
+        seq[p:p + m.size] = m
+    tail = "".join(np.asarray(list("ACGT"))[rng.integers(0, 4, size=3000)]) + rseq[11]
+    return [("edges straddled", seq.tobytes().decode()), ("tail record", tail)], edges
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_scan_shard_blocks_replayed_on_the_host_equal_whole(K, O, prof, synth, shards):
+    """the multi-GPU flow (kgma_scan_shard -> kgma_result_pack -> kgma_replay_packed) on one device, single and cluster mode,
+    prefiltered and dense: identical hits (coordinates, D, alignment score, KFV index) to the unsharded kgma_scan.  The second
+    genome has homologues on every slice edge, so runs are cut there, extension windows reach into the neighbouring slice, and in
+    cluster mode the prev_hit_range interaction (OmnGenomeMiner.jl:126,139,152) straddles the cut."""
+    path, recs = synth
+    RV, ws, cons = prof
+    rvs, wss, cs, inv = K.cluster_ref_API(TF, 6)
+    rvs, wss, cs = K.eliminate_null_params(rvs, wss, cs, inv)
+    L = K.L
+    erecs, edges = _straddling_genome(K, O)
+    key = ["record", "profile", "first", "last", "D", "genome_pos", "align_score", "cmi"]
+    for g in (K.Genome.from_fasta(path), K.Genome.from_records(erecs)):
+        for args, go in ((([RV], [ws], [cons], [30.0], 6, L.MODE_SINGLE, 50), -69),
+                         ((rvs, wss, cs, [35, 31, 38, 34, 27, 27], 6, L.MODE_CLUSTER, 100), -200)):
+            for dense in (0, L.F_DENSE):
+                for align in (L.F_ALIGN, 0):
+                    whole = K.scan_raw(g, *args, align | dense, go, -1)
+                    rep = shards_replayed(K, g, args, align | dense, go, -1, shards, order=list(reversed(range(shards))))
+                    assert np.array_equal(rep.hits[key], whole.hits[key]), (args[5], dense, align)
+                    assert len(whole.hits) >= 8
+    # the straddling genome against the oracle, cluster mode (prev_hit_range across the cuts)
+    g = K.Genome.from_records(erecs)
+    args = (rvs, wss, cs, [35, 31, 38, 34, 27, 27], 6, L.MODE_CLUSTER, 100)
+    rep = shards_replayed(K, g, args, L.F_ALIGN, -200, -1, shards)
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "e.fasta")
+        _write_fasta(p, erecs)
+        assert_parity(K, O, rep, lambda: O.Omn_KmerGMA(p, [np.asarray(v) for v in rvs], wss, cs, thr_vec=[35, 31, 38, 34, 27, 27], buff=100)[0],
+                      [v.n_refs for v in rvs], cluster=True)
+    hit_spans = [(int(h.first), int(h.last)) for h in rep.hits if int(h.record) == 0]
+    assert sum(any(a <= e <= b for a, b in hit_spans) for e in edges) >= 3      # hits do lie across slice edges
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_exact_match_slices_merge_to_whole(K, O, shards):
+    """kgma_exact_match_shard + kgma_exact_match_merge: queries of every kernel class (>= 143 nt sampled, 31..142 nt sampled, < 31 nt
+    dense, with N) with occurrences ON the slice edges and tandem self-overlaps across them; overlap and non-overlap mode"""
+    erecs, edges = _straddling_genome(K, O, seed=32)
+    rng = np.random.default_rng(8)
+    body = np.frombuffer(erecs[0][1].encode(), dtype=np.uint8).copy()
+    unit = "".join(np.asarray(list("ACGT"))[rng.integers(0, 4, size=50)])
+    queries = [unit * 6, unit * 2, unit[:20], unit[:10] + "NNN" + unit[13:40]]
+    for qi, q in enumerate(queries):
+        qb = np.frombuffer(q.encode(), dtype=np.uint8)
+        for ei, e in enumerate(edges):
+            p = e - len(q) // 2 + 500 * qi if qi else e - len(q) // 2          # the first query sits exactly across each edge
+            if qi == 0:
+                t = np.frombuffer((q + unit * 2).encode(), dtype=np.uint8)     # tandem: overlapping self-matches at +50, +100
+                body[p:p + t.size] = t
+            elif 0 < p and p + qb.size < body.size and ei % 2 == 0:
+                body[p:p + qb.size] = qb
+    recs = [(erecs[0][0], body.tobytes().decode()), erecs[1]]
+    g = K.Genome.from_records(recs)
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "x.fasta")
+        _write_fasta(p, recs)
+        f = O.Fasta(p)
+        for q in queries:
+            starts = np.concatenate([K.exact_match_shard(q, g, (s_, shards)) for s_ in reversed(range(shards))])
+            for overlap in (True, False):
+                whole = K.exactMatch(q, g, overlap=overlap)
+                assert K.exact_match_merge(g, starts, len(q), overlap) == whole == O.exactMatch(q, f, overlap=overlap), (q[:12], overlap)
+            assert whole != "no match"
+
+
 def test_scan_rejects_iupac(K, prof):
     """Consts.jl:22-28: symbols outside A,C,G,T,N raise KeyError in the reference scan"""
     RV, ws, cons = prof
@@ -618,6 +745,131 @@ def test_full_size_properties(K, O, prof, big):
             oh = assert_parity(K, O, out, lambda: O.ac_gma_testing(p, np.asarray(RV), cons, windowsize=ws, thr=bench.THR, buff=bench.BUFF, do_align=True)[0], RV.n_refs)
         whole = [(int(h.first), int(h.last), int(h.D)) for h in a.hits if int(h.record) == r]
         assert whole == [(int(h.first), int(h.last), int(h.D)) for h in out.hits] and len(oh) == len(whole) > 10
+
+
+def oracle_by_record(O, g, run, cluster, ws, records=None, threads=None):
+    """the oracle over a genome that only exists in packed form: one task per record on a thread pool (ctypes releases the
+    GIL), each record handed over in memory (O.Fasta.wrap, no FASTA file); record index and GenomePos are put back to their
+    whole-genome values (single mode skips records shorter than the window without advancing GenomePos, GenomeMiner.jl:37-39;
+    cluster mode always advances, OmnGenomeMiner.jl:159)."""
+    from concurrent.futures import ThreadPoolExecutor
+    n = len(g)
+    lens = [g.seqsize(r) for r in range(n)]
+    gp, acc = [], 0
+    for L in lens:
+        gp.append(acc)
+        if cluster or L >= ws:
+            acc += L
+    todo = list(range(n)) if records is None else list(records)
+    threads = threads or max(1, min(16, len(os.sched_getaffinity(0)), len(todo)))
+
+    def one(r):
+        f = O.Fasta.wrap(g.description(r), g.seq_array(r))
+        hs = run(f)
+        for h in hs:
+            h.record = r
+            h.genome_pos = gp[r]
+        return hs
+
+    with ThreadPoolExecutor(threads) as ex:
+        parts = list(ex.map(one, sorted(todo, key=lambda r: -lens[r])))       # longest first
+    by_rec = dict(zip(sorted(todo, key=lambda r: -lens[r]), parts))
+    return [h for r in sorted(todo) for h in by_rec[r]]
+
+
+def test_full_size_cfg2_every_contig_vs_oracle(K, O, prof, big):
+    """BASELINE configs[1] at full size against the oracle, all 24 contigs (3.09 Gb), do_align = true: the streamed scan's hits
+    bit-exact against the exact-arithmetic oracle and, outside flagged blocks, against the faithful Float64 oracle"""
+    import bench
+    g, lens, plants = big
+    RV, ws, cons = prof
+    out = K.scan_raw(g, [RV], [ws], [cons], [bench.THR], 6, K.L.MODE_SINGLE, bench.BUFF, K.L.F_ALIGN, bench.GAP_OPEN, bench.GAP_EXT)
+
+    def run(f):
+        return O.ac_gma_testing(f, np.asarray(RV), cons, windowsize=ws, thr=bench.THR, buff=bench.BUFF, do_align=True,
+                                gap_open_score=bench.GAP_OPEN, gap_extend_score=bench.GAP_EXT, hit_cap=1 << 15)[0]
+
+    with O.exact_arithmetic(RV.n_refs):
+        oe = oracle_by_record(O, g, run, False, ws)
+    of = oracle_by_record(O, g, run, False, ws)
+    agreed = check_parity(K, out, oe, of)
+    assert len(agreed) > 1500 and len(set(h.record for h in agreed)) == len(lens)
+
+
+def test_full_size_cfg3_cluster_mode_vs_oracle(K, O, big):
+    """BASELINE configs[2] at full size: findGenes_cluster_mode's operator (5 clusters + the average profile, thresholds
+    [35,31,38,34,27,27], buffer 100, gap (-200,-1)) over the 3.09 Gb genome against Omn_KmerGMA! in the oracle, every contig;
+    then 8 shards (kgma_scan_shard blocks replayed on the host) against the unsharded scan"""
+    g, lens, plants = big
+    rvs, wss, cs, inv = K.cluster_ref_API(TF, 6)
+    rvs, wss, cs = K.eliminate_null_params(rvs, wss, cs, inv)
+    thr = [35, 31, 38, 34, 27, 27]
+    args = (rvs, wss, cs, thr, 6, K.L.MODE_CLUSTER, 100)
+    out = K.scan_raw(g, *args, K.L.F_ALIGN, -200, -1)
+
+    def run(f):
+        return O.Omn_KmerGMA(f, [np.asarray(v) for v in rvs], wss, cs, thr_vec=thr, buff=100, hit_cap=1 << 15)[0]
+
+    with O.exact_arithmetic([v.n_refs for v in rvs]):
+        oe = oracle_by_record(O, g, run, True, max(wss))
+    of = oracle_by_record(O, g, run, True, max(wss))
+    agreed = check_parity(K, out, oe, of, cluster=True)
+    assert len(agreed) > 1500
+    rep = shards_replayed(K, g, args, K.L.F_ALIGN, -200, -1, 8)
+    key = ["record", "profile", "first", "last", "D", "genome_pos", "align_score", "cmi"]
+    assert np.array_equal(rep.hits[key], out.hits[key])
+
+
+def shards_replayed(K, g, args, flags, go, ge, n_shards, order=None, ctx=None):
+    """the multi-GPU flow on one device: kgma_scan_shard per slice (runs + the slice's own extension results), the packed blocks
+    side by side as an all-gather would leave them, then the host-only kgma_replay_packed (no context: no device work)"""
+    blocks = []
+    for s_ in (order or range(n_shards)):
+        part = K.scan_shard_raw(g, *args, flags, go, ge, shard=(s_, n_shards), ctx=ctx)
+        need = K.pack_shard(part, None, 0)
+        buf = np.zeros(need, dtype=np.uint8)
+        assert K.pack_shard(part, buf.ctypes.data, buf.size) == need
+        blocks.append(buf)
+    stride = (max(b.size for b in blocks) + 255) // 256 * 256
+    allb = np.zeros((len(blocks), stride), dtype=np.uint8)
+    for i, b in enumerate(blocks):
+        allb[i, :b.size] = b
+    return K.replay_packed(g, *args, flags, go, ge, allb.ctypes.data, len(blocks), stride, ctx=None)
+
+
+def test_k7_large_family_one_gigabase_vs_oracle(K, O, tmp_path):
+    """BASELINE configs[4] on a 1.2 Gb subset: k = 7 (16 384 bins), a 500-member family, 240 contigs with log-uniform lengths
+    (10 kb .. 100 Mb before scaling) and planted members, streamed from the host; every contig against the oracle, and
+    8 shards replayed on the host against the unsharded scan"""
+    import bench
+    fam_path, fam = bench.k7_family(str(tmp_path))
+    RV, ws, cons = K.gen_ref_ws_cons(fam_path, 7)
+    orv, ows, ocons = O.gen_ref_ws_cons(fam_path, 7)
+    assert RV.n_refs == len(fam) >= 500 and ws == ows and cons == ocons and np.array_equal(np.asarray(RV), orv)
+    ctx = K.default_context()
+    lens = bench.k7_contig_lengths(240, 1.2e9)
+    assert len(lens) == 240 and sum(lens) > 1.0e9
+    g = K.Genome.synth(lens, seed=77, n_run_len=1000, centromere_len=100_000, ctx=ctx)
+    plants = bench.k7_plant_list(lens, fam, 600)
+    for (r, pos, s_) in plants:
+        g.put_seq(r, pos, s_)
+    thr = bench.k7_threshold(RV, ws)
+    args = ([RV], [ws], [cons], [thr], 7, K.L.MODE_SINGLE, bench.BUFF)
+    out = K.scan_raw(g, *args, K.L.F_ALIGN, -69, -1)
+    st = ctx.stats()
+    assert st["blocks_total"] > 0 and st["h2d_bytes"] > sum(lens) // 4          # prefiltered, streamed from the host
+
+    def run(f):
+        return O.ac_gma_testing(f, orv, cons, k=7, windowsize=ws, thr=thr, buff=bench.BUFF, do_align=True, hit_cap=1 << 14)[0]
+
+    with O.exact_arithmetic(RV.n_refs):
+        oe = oracle_by_record(O, g, run, False, ws)
+    of = oracle_by_record(O, g, run, False, ws)
+    agreed = check_parity(K, out, oe, of)
+    assert len(agreed) > 300
+    rep = shards_replayed(K, g, args, K.L.F_ALIGN, -69, -1, 8, order=(5, 2, 7, 0, 3, 6, 1, 4))
+    key = ["record", "first", "last", "D", "genome_pos", "align_score", "cmi"]
+    assert np.array_equal(rep.hits[key], out.hits[key])
 
 
 def test_full_size_exact_match(K, big):
@@ -988,23 +1240,28 @@ def test_resident_genome_through_the_operator_mirror(K, O, prof, synth):
         assert K.exactMatch(q, g, ctx=ctx) == O.exactMatch(q, O.Fasta(path))
 
 
-def test_two_warp_extension_kernel_equals_one_warp(K, O, prof, monkeypatch):
-    """small extension batches run two warps per alignment (kgma_align_pair); KGMA_ALIGN_PAIR_MAX=0 forces the
-    one-warp kernel, a huge value the two-warp one for every batch: same ranges and scores, for several gap models, subject
-    lengths from 1 to 600 (with N) and consensus lengths on both sides of the 160-row split; then against the oracle"""
+def test_tagged_extension_kernel_equals_path_summary_kernel(K, O, prof, monkeypatch):
+    """the default extension kernel (kgma_align_tagged: one word per DP state, DPX three-way max) against the
+    path-summary kernel it falls back to (KGMA_ALIGN_KERNEL=summary forces that one for the whole batch): same ranges and
+    scores for several gap models, subject lengths from 1 to 511 (with N), consensus lengths 8..400, subjects that start or
+    end inside the homologue (no leading / trailing deletion run: the redo path); then against the oracle"""
     RV, ws, cons = prof
     rng = np.random.default_rng(21)
     whole = O.Fasta(GENOME).seq(3)
     recs = []
-    for i in range(66):
-        n = int([1, 2, 31, 32, 33, 64, 200, 289, 389, 489, 600][i % 11])
+    for i in range(88):
+        n = int([1, 2, 31, 32, 33, 64, 200, 289, 389, 416, 417, 489, 511, 300, 350, 260][i % 16])
         p = int(rng.integers(0, len(whole) - 700))
         sub = whole[p:p + n]
-        if i % 3 == 0 and n >= 200:                       # plant (a mutated copy of) the consensus so that real alignments occur
+        if i % 3 != 1 and n >= 200:                       # plant (a mutated copy of) the consensus so that real alignments occur
             base = list(cons[:int(rng.integers(150, 289))])
             for _ in range(int(rng.integers(0, 25))):
                 base[int(rng.integers(0, len(base)))] = "ACGTN"[int(rng.integers(0, 5))]
-            sub = (sub[:20] + "".join(base) + sub)[:n]
+            if i % 5 == 0:                                # an indel inside the copy
+                q = int(rng.integers(20, len(base) - 20))
+                base[q:q + int(rng.integers(1, 9))] = [] if i % 2 else list("ACGTACGTA"[:int(rng.integers(1, 9))])
+            lead = [0, 20, 57][i % 3] if i % 7 else 0     # lead 0: the alignment starts at the first subject base
+            sub = (sub[:lead] + "".join(base) + sub)[:n]
         recs.append(("r%d" % i, sub))
     g = K.Genome.from_records(recs)
     ctx = K.default_context()
@@ -1013,25 +1270,32 @@ def test_two_warp_extension_kernel_equals_one_warp(K, O, prof, monkeypatch):
     first = np.ones(n, np.int64)
     last = np.asarray([len(s_) for _, s_ in recs], np.int64)
 
-    def batch(c, go, ge, setting):
-        monkeypatch.setenv("KGMA_ALIGN_PAIR_MAX", setting)
+    def batch(c, go, ge, kernel):
+        if kernel:
+            monkeypatch.setenv("KGMA_ALIGN_KERNEL", kernel)
         of, ol, sc = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.int64)
         ctx.check(ctx._lib.kgma_align_batch(ctx._h, g._h, c, len(c), go, ge, 0, n, rec.ctypes.data, first.ctypes.data,
                                             last.ctypes.data, of.ctypes.data, ol.ctypes.data, sc.ctypes.data))
-        monkeypatch.delenv("KGMA_ALIGN_PAIR_MAX")
-        return of.tolist(), ol.tolist(), sc.tolist()
+        if kernel:
+            monkeypatch.delenv("KGMA_ALIGN_KERNEL")
+        return of.tolist(), ol.tolist(), sc.tolist(), ctx.stats()["n_align_redo"]
 
-    for clen in (160, 161, 200, 289, 320):
-        c = cons[:289] if clen <= 289 else (cons[:289] + cons[:clen - 289])
-        c = c[:clen].encode()
-        for go, ge in ((-69, -1), (-200, -1), (-5, -2)):
-            assert batch(c, go, ge, "0") == batch(c, go, ge, "100000000"), (clen, go, ge)
-        of, ol, sc = batch(c, -69, -1, "100000000")
+    redone = 0
+    for clen in (8, 33, 160, 161, 200, 289, 320, 321, 400):
+        c = (cons[:289] * 2)[:clen].encode()
+        for go, ge in ((-69, -1), (-200, -1), (-5, -2), (0, -1), (-30, -3)):
+            a = batch(c, go, ge, None)
+            b = batch(c, go, ge, "summary")
+            assert a[:3] == b[:3], (clen, go, ge)
+            assert b[3] == 0
+            redone += a[3]
+        of, ol, sc, _ = batch(c, -69, -1, None)
         for i in range(0, n, 5):
             s_ = recs[i][1]
             lo, hi = O.align_unitrange(s_, (1, len(s_)), c.decode(), clen, len(s_), -69, -1)
             assert (of[i], ol[i]) == (lo, hi), (clen, i)
             assert sc[i] == O.pairalign_semiglobal(c.decode(), s_, -69, -1)[1]
+    assert redone > 0                                     # the hand-over to the path-summary kernel was exercised
 
 
 def test_two_contexts_share_nothing(K, prof, synth):
