@@ -16,11 +16,13 @@
 //  (2) kgma_eval: the count-table kernel.  One warp per span of consecutive windows (a flagged 64-base
 //      block read straight from the device candidate list, or a slice of a record in dense mode), with a
 //      4^k x u16 count table in shared memory next to the profile's S table; the distance is updated
-//      incrementally as one k-mer leaves and one enters the window, re-initialised per span.  Windows are
-//      classified 64 at a time (ballot + warp min) and run summaries (maximal stretches of D < T) are
-//      appended with an atomic; optionally every D is written (do_return_dists).
+//      incrementally as one k-mer leaves and one enters the window, re-initialised per span -- 16 steps at a
+//      time with all 32 lanes busy (one MATCH.ANY resolves the in-batch dependencies between the 32 events).
+//      Windows are classified 16 at a time (ballot + warp min) and run summaries (maximal stretches of
+//      D < T) are appended with an atomic; optionally every D is written (do_return_dists).
 #include "kgma_internal.h"
 #include <algorithm>
+#include <type_traits>
 #include <cmath>
 #include <climits>
 #include <cstdlib>
@@ -145,7 +147,11 @@ struct RecDev {
     long long dist_base;    // do_return_dists: index of step 1 of this record in the D output
 };
 
-struct ProfDev { long long N2, twoN, sumS2, T, Tlo, Thi, R; int nk, pad; };   // R = N^2 nk + sum S^2 - Thi (<= 0: cannot be bounded)
+struct ProfDev {
+    long long N2, twoN, sumS2, T, Tlo, Thi, R;    // R = N^2 nk + sum S^2 - Thi (<= 0: cannot be bounded)
+    int nk, N;
+    int uThi, u_ok;                               // 32-bit pre-test: D < Thi <=> N Q - 2 A < uThi (valid when u_ok)
+};
 
 struct EvalArgs {
     const uint32_t *seq;
@@ -189,7 +195,9 @@ __device__ __forceinline__ void emit_run(const EvalArgs &a, int rec, int q, long
     }
 }
 
-__global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
+// The round-1 form of the count-table kernel, kept as a cross-check (KGMA_EVAL_KERNEL=serial): the same spans, tables and run
+// bookkeeping, but the slide is one instruction stream on lane 0 (64 steps prepared by all lanes, applied by one).
+__global__ void __launch_bounds__(512, 1) kgma_eval_serial(EvalArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned FULL = 0xFFFFFFFFu;
@@ -393,6 +401,262 @@ __global__ void __launch_bounds__(512, 1) kgma_eval(EvalArgs a)
                                             P.N2 * (long long)qa[i].x - P.twoN * (long long)qa[i].y + P.sumS2, KGMA_RUN_MARKER | KGMA_HIT_NEAR_THR);
                 }
                 __syncwarp();
+            }
+            // ---- return the table to zero: only the k-mers of the last window are still counted
+            for (int p = lane; p < nk; p += 32) tab[kmer_at(a.seq, gpos + n - 1 + p, kmask)] = 0;
+            __syncwarp();
+        }
+    }
+}
+
+// v + (t & mask) with the mask kept as data: written as `if (j >= d) v += t` the compiler re-derives four predicates per batch
+__device__ __forceinline__ int tg_and_add(int v, int t, int mask)
+{
+    int r; asm("{ .reg .b32 x; and.b32 x, %1, %2; add.s32 %0, %3, x; }" : "=r"(r) : "r"(t), "r"(mask), "r"(v)); return r;
+}
+
+// Run bookkeeping of one warp over consecutive groups of windows of a span: an open run is carried from group to group so
+// that every maximal stretch of D < T is emitted once.
+struct RunCarry { bool in; long long tf, ta, dmin; uint32_t fl; };
+
+// Classify a group of `cnt` (<= 32) consecutive windows tb .. tb+cnt-1 of record r, lane i holding the exact D of window
+// tb+i (lanes >= cnt: have = false): window 0 is only recorded (GenomeMiner.jl:57: never compared with thr), every other
+// one is written out when distances are wanted and tested against T (GenomeMiner.jl:82 `kmerDist < thr`) and the 1e-9 band.
+// (kept out of line and fed by value: the slide loop calls it for a handful of batches per million, and must not pay for
+//  its registers or for a stack copy of the kernel parameters)
+struct ClsArgs {
+    kgma_run *runs; uint32_t run_cap; uint32_t *run_count;
+    long long *first_D; long long *dists; long long dist_stride; int nrec;
+    long long T, Tlo, Thi;
+};
+
+__device__ __forceinline__ void emit_run_c(const ClsArgs &a, int rec, int q, long long tf, long long tl, long long ta, long long dmin, uint32_t flags)
+{
+    uint32_t i = atomicAdd(a.run_count, 1u);
+    if (i < a.run_cap) {
+        kgma_run r; r.record = rec; r.profile = q; r.t_first = tf; r.t_last = tl; r.t_argmin = ta;
+        r.D_min = dmin; r.flags = flags; r.reserved = 0;
+        a.runs[i] = r;
+    }
+}
+
+__device__ __noinline__ RunCarry classify_group(ClsArgs a, int r, int q, long long w0, long long tb, int cnt,
+                                                bool have, long long D, bool more, long long dist_base, RunCarry c, int lane)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    const ClsArgs &P = a;
+    const long long t = tb + lane;
+    if (have && t == 0) a.first_D[(size_t)q * a.nrec + r] = D;
+    const bool inloop = have && t >= 1;
+    if (a.dists && inloop) a.dists[(size_t)q * a.dist_stride + dist_base + t - 1] = D;
+    if (!c.in && !__any_sync(FULL, inloop && D < P.Thi)) return c;        // the common case: nothing at or below the threshold band
+    const unsigned below = __ballot_sync(FULL, inloop && D < P.T);
+    const unsigned near = __ballot_sync(FULL, inloop && D >= P.Tlo && D < P.Thi);
+    if (c.in && !(below & 1u)) {                                        // the carried run ended with the previous group
+        if (lane == 0) emit_run_c(a, r, q, c.tf, tb - 1, c.ta, c.dmin, c.fl);
+        c.in = false;
+    }
+    if (!(below | near)) return c;
+    unsigned rem = below;
+    while (rem) {                                                      // maximal stretches of D < T inside this group
+        const int b0 = __ffs((int)rem) - 1;
+        const unsigned sh = rem >> b0;
+        const int len = (~sh == 0u) ? 32 - b0 : (__ffs((int)~sh) - 1);
+        const unsigned stretch = (len >= 32 ? ~0u : ((1u << len) - 1)) << b0;
+        const int b1 = b0 + len - 1;
+        const bool mine = lane >= b0 && lane <= b1;
+        long long bestD = mine ? D : LLONG_MAX; int bestI = mine ? lane : 64;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {                                 // min D, earliest window on ties
+            const long long oD = __shfl_xor_sync(FULL, bestD, d); const int oI = __shfl_xor_sync(FULL, bestI, d);
+            if (oD < bestD || (oD == bestD && oI < bestI)) { bestD = oD; bestI = oI; }
+        }
+        const int ties = __popc(__ballot_sync(FULL, mine && D == bestD));
+        uint32_t fl = (ties > 1 ? KGMA_HIT_ARGMIN_TIE : 0u) | ((near & stretch) ? KGMA_HIT_NEAR_THR : 0u);
+        long long tf = tb + b0, ta = tb + bestI, dmin = bestD;
+        if (c.in && b0 == 0) {                                         // continues the run carried over from the previous group
+            fl |= c.fl;
+            if (c.dmin < dmin) { dmin = c.dmin; ta = c.ta; fl = (fl & ~KGMA_HIT_ARGMIN_TIE) | (c.fl & KGMA_HIT_ARGMIN_TIE); }
+            else if (c.dmin == dmin) { ta = c.ta; fl |= KGMA_HIT_ARGMIN_TIE; }
+            tf = c.tf; c.in = false;
+        } else if (tf == w0 || (w0 == 0 && tf == 1)) fl |= KGMA_RUN_OPEN_LEFT;
+        if (b1 == cnt - 1 && more) { c.in = true; c.tf = tf; c.ta = ta; c.dmin = dmin; c.fl = fl; }   // may continue
+        else if (lane == 0) emit_run_c(a, r, q, tf, tb + b1, ta, dmin, fl | (b1 == cnt - 1 ? KGMA_RUN_OPEN_RIGHT : 0u));
+        rem &= ~stretch;
+    }
+    unsigned mk = near & ~below;                                        // d >= thr inside the 1e-9 band: reported, never replayed
+    while (mk) {
+        const int i = __ffs((int)mk) - 1; mk &= mk - 1;
+        const long long Di = __shfl_sync(FULL, D, i);
+        if (lane == 0) emit_run_c(a, r, q, tb + i, tb + i, tb + i, Di, KGMA_RUN_MARKER | KGMA_HIT_NEAR_THR);
+    }
+    return c;
+}
+
+// One launch per profile: k and the profile's constants are compile-time / direct kernel parameters, so the slide loop
+// keeps nothing but its own state in registers.
+template <int K, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) kgma_eval(EvalArgs a, ProfDev P, int q)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned FULL = 0xFFFFFFFFu;
+    constexpr int nb = 1 << (2 * K);
+    constexpr uint32_t kmask = (uint32_t)nb - 1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int32_t *sS = reinterpret_cast<int32_t *>(smem_raw);
+    uint16_t *tab = reinterpret_cast<uint16_t *>(smem_raw + (size_t)nb * 4 + (size_t)wid * ((size_t)nb * 2));   // [4^k] counts of this warp
+    for (int i = lane; i < nb / 2; i += 32) reinterpret_cast<uint32_t *>(tab)[i] = 0;
+
+    long long nitems = a.n_items;
+    if (a.cand) { uint32_t c = *a.cand_count; nitems = c < a.cand_cap ? c : a.cand_cap; }
+
+    {
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) sS[i] = a.S[(size_t)q * nb + i];
+        __syncthreads();
+        const int nk = P.nk;
+        ClsArgs ca;
+        ca.runs = a.runs; ca.run_cap = a.run_cap; ca.run_count = a.run_count; ca.first_D = a.first_D; ca.dists = a.dists;
+        ca.dist_stride = a.dist_stride; ca.nrec = a.nrec; ca.T = P.T; ca.Tlo = P.Tlo; ca.Thi = P.Thi;
+        for (;;) {
+            long long item = 0;
+            if (lane == 0) item = (long long)atomicAdd(a.next_item + q, 1ull);
+            item = __shfl_sync(FULL, item, 0);
+            if (item >= nitems) break;
+            // ---- locate the span: record r, first window w0 (== loop step), n windows
+            int r; long long w0, n;
+            if (a.cand) {
+                const long long b = (long long)a.cand[item];
+                if (b < a.cand_blk_lo || b >= a.cand_blk_hi) continue;
+                const long long gp = b * FBLOCK;
+                int lo = 0, hi = a.nrec;                                      // last record with off <= gp
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (a.recs[mid].off <= gp) lo = mid; else hi = mid; }
+                r = lo;
+                const RecDev R = a.recs[r];
+                const long long b0 = gp - R.off;
+                if (b0 < 0) continue;
+                if (item < (long long)a.n_seed) { w0 = 0; n = (b0 == 0 && R.w_begin == 0 && R.w_end > 0) ? 1 : 0; }   // window 0 only
+                else {
+                    // consecutive flagged blocks of one record are evaluated as ONE span by the warp that owns their head;
+                    // spans are also cut every 8 blocks so that long flagged stretches still spread over many warps
+                    const bool prev_same_rec = b0 >= FBLOCK;
+                    const bool prev_set = b > 0 && ((a.bitmap[(b - 1) >> 5] >> ((b - 1) & 31)) & 1u);
+                    if (prev_set && prev_same_rec && (b & 7) != 0) continue;
+                    long long e = b;
+                    while (((e + 1) & 7) != 0 && ((a.bitmap[(e + 1) >> 5] >> ((e + 1) & 31)) & 1u)) e++;
+                    w0 = b0 > R.w_begin ? b0 : R.w_begin;
+                    const long long we = (e + 1) * FBLOCK - R.off < R.w_end ? (e + 1) * FBLOCK - R.off : R.w_end;
+                    n = we - w0;
+                }
+            } else {
+                int lo = 0, hi = a.nrec;                                      // last record with item_base <= item
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (a.recs[mid].item_base <= item) lo = mid; else hi = mid; }
+                r = lo;
+                const RecDev R = a.recs[r];
+                w0 = R.w_begin + (item - R.item_base) * a.span;
+                n = R.w_end - w0 < a.span ? R.w_end - w0 : a.span;
+            }
+            if (n <= 0) continue;
+            const long long gpos = a.recs[r].off + w0;
+            const long long dist_base = a.recs[r].dist_base;
+
+            // ---- candidate spans are flagged per 64-base block with the group's maximum weights over a 384-base cover; check this
+            //      profile's own bound exactly before paying for the table: a window can only be below thr if
+            //      2N * A_w > R (D_w >= N^2 nk - 2N A_w + sum S^2), and A_w of all n windows costs one pass of lookups
+            if (a.cand && P.R > 0 && !(w0 == 0 && n == 1)) {
+                uint32_t A0 = 0;
+                for (int p = lane; p < nk; p += 32) A0 += (uint32_t)sS[kmer_at(a.seq, gpos + p, kmask)];
+#pragma unroll
+                for (int d = 16; d; d >>= 1) A0 += __shfl_xor_sync(FULL, A0, d);
+                long long Aw = A0, Amax = A0;                                  // A of window 0; then 32 windows per round
+                for (long long wb0 = 0; wb0 + 1 < n; wb0 += 32) {
+                    const long long w = wb0 + lane;                            // step w: window w -> w+1
+                    int dlt = 0;
+                    if (w + 1 < n) dlt = sS[kmer_at(a.seq, gpos + w + nk, kmask)] - sS[kmer_at(a.seq, gpos + w, kmask)];
+                    int pre = dlt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, pre, d); if (lane >= d) pre += t; }
+                    long long mine = Aw + pre;                                 // A of window w+1
+                    if (w + 1 >= n) mine = 0;
+#pragma unroll
+                    for (int d = 16; d; d >>= 1) { const long long o = __shfl_xor_sync(FULL, mine, d); mine = o > mine ? o : mine; }
+                    Amax = mine > Amax ? mine : Amax;
+                    Aw += __shfl_sync(FULL, pre, 31);
+                }
+                if (P.twoN * Amax <= P.R) continue;                            // no window of this span can reach thr for this profile
+            }
+            // ---- first window of the span: build the table, Q = sum_p c[kmer_p], A = sum_p S[kmer_p]
+            for (int p = lane; p < nk; p += 32) {
+                const uint32_t km = kmer_at(a.seq, gpos + p, kmask);
+                atomicAdd(reinterpret_cast<uint32_t *>(tab) + (km >> 1), 1u << ((km & 1) * 16));
+            }
+            __syncwarp();
+            uint32_t Qb = 0, Ab = 0;                                          // < 2^32: nk <= 65535, nk * max S checked on the host
+            for (int p = lane; p < nk; p += 32) {
+                const uint32_t km = kmer_at(a.seq, gpos + p, kmask);
+                Qb += tab[km]; Ab += (uint32_t)sS[km];
+            }
+#pragma unroll
+            for (int d = 16; d; d >>= 1) { Qb += __shfl_xor_sync(FULL, Qb, d); Ab += __shfl_xor_sync(FULL, Ab, d); }
+
+            RunCarry carry; carry.in = false; carry.tf = carry.ta = carry.dmin = 0; carry.fl = 0;
+            // window w0 itself
+            carry = classify_group(ca, r, q, w0, w0, 1, lane == 0, P.N2 * (long long)Qb - P.twoN * (long long)Ab + P.sumS2, n > 1, dist_base, carry, lane);
+
+            // ---- the slide, 16 steps at a time with every lane busy (GenomeMiner.jl:60-87).  Lanes 0-15 hold the k-mer LEAVING the
+            //      window at steps s..s+15, lanes 16-31 the one ENTERING.  The count a step sees is the table's count at the start
+            //      of the batch plus the enters minus the leaves of the same k-mer at earlier steps of this batch, which one
+            //      MATCH.ANY over the 32 events yields for every lane at once; Q and A then follow from a 16-wide prefix sum of
+            //      2(c_r - c_l) + 2 and S[r] - S[l] (lower half-warp scans Q, upper half-warp scans A, same instructions).  The
+            //      table receives one store per distinct k-mer whose count changed over the batch.
+            //      Windows are pre-tested in 32 bits: D < X  <=>  N (N Q - 2 A) < X - sum S^2  <=>  N Q - 2 A < ceil((X - sum S^2) / N),
+            //      exact; the 64-bit D and the run bookkeeping only happen for a batch that has a window under the band's upper edge.
+            const int j = lane & 15; const bool ent = lane >= 16;
+            const long long pos0 = gpos + j + (ent ? nk : 0);                  // position of my event's k-mer at s = 0
+            const uint32_t *wp = a.seq + (pos0 >> 4); const int sh = (int)(pos0 & 15) * 2;   // 16 steps = one packed word: the shift never changes
+            uint32_t wlo = __ldg(wp), whi = __ldg(wp + 1);
+            const unsigned ltE = (((1u << j) - 1u) << 16), ltL = (1u << j) - 1u;   // enter / leave events of earlier steps
+            const int scan1 = j >= 1 ? -1 : 0, scan2 = j >= 2 ? -1 : 0, scan4 = j >= 4 ? -1 : 0, scan8 = j >= 8 ? -1 : 0;
+            const unsigned lt_lane = (1u << lane) - 1u;
+            const int Nn = P.N, uHi = P.uThi;
+            const int ni = (int)n;                                             // spans are at most 65536 windows
+            int s = 0, widx = 2;
+            auto batch = [&](auto full_c, auto all_c) {
+                constexpr bool FB = decltype(full_c)::value;                   // all 16 steps of the batch are real slides
+                constexpr bool ALL = decltype(all_c)::value;                   // every window goes through the 64-bit path (do_return_dists)
+                const uint32_t x = __funnelshift_r(wlo, whi, sh) & kmask;
+                wlo = whi; whi = __ldg(wp + widx); widx++;
+                const int left = FB ? 16 : ni - 1 - s;
+                const bool valid = FB || j < left;
+                unsigned m = __match_any_sync(FULL, valid ? x : (0x80000000u | (unsigned)lane));
+                if (!FB) m &= ((1u << left) - 1u) * 0x10001u;
+                const uint32_t c0 = tab[x];
+                const int cnt = (int)c0 + __popc(m & ltE) - __popc(m & ltL);
+                const int Sx = sS[x];
+                const int o = __shfl_xor_sync(FULL, ent ? cnt : Sx, 16);       // lower lanes receive c_r, upper lanes S[l]
+                int v = ent ? (Sx - o) : (2 * (o - cnt) + 2);                  // S[r] - S[l]  /  2(c_r - c_l) + 2
+                if (((m >> (lane ^ 16)) & 1u) || !valid) v = 0;                // GenomeMiner.jl:69 `if left_ind != right_ind`
+                v = tg_and_add(v, __shfl_up_sync(FULL, v, 1, 16), scan1);
+                v = tg_and_add(v, __shfl_up_sync(FULL, v, 2, 16), scan2);
+                v = tg_and_add(v, __shfl_up_sync(FULL, v, 4, 16), scan4);
+                v = tg_and_add(v, __shfl_up_sync(FULL, v, 8, 16), scan8);
+                const int ov = __shfl_xor_sync(FULL, v, 16);
+                const uint32_t Qw = Qb + (uint32_t)(ent ? ov : v), Aw = Ab + (uint32_t)(ent ? v : ov);   // window s+j+1
+                const int u = Nn * (int)Qw - 2 * (int)Aw;
+                if (ALL || carry.in || __any_sync(FULL, valid && u < uHi)) {
+                    const long long D = P.N2 * (long long)Qw - P.twoN * (long long)Aw + P.sumS2;
+                    carry = classify_group(ca, r, q, w0, w0 + s + 1, left, !ent && valid, D, s + 1 + left < ni, dist_base, carry, lane);
+                }
+                Qb += (uint32_t)__shfl_sync(FULL, v, 15); Ab += (uint32_t)__shfl_sync(FULL, v, 31);
+                // one store per distinct k-mer (by the lowest lane holding it): count at the start of the batch + enters - leaves
+                if (valid && !(m & lt_lane)) tab[x] = (uint16_t)((int)c0 + __popc(m & 0xFFFF0000u) - __popc(m & 0x0000FFFFu));
+                __syncwarp();
+            };
+            if (a.dists != nullptr || !P.u_ok) {
+                for (; s + 16 < ni; s += 16) batch(std::true_type{}, std::true_type{});
+                if (s + 1 < ni) batch(std::false_type{}, std::true_type{});
+            } else {
+                for (; s + 16 < ni; s += 16) batch(std::true_type{}, std::false_type{});
+                if (s + 1 < ni) batch(std::false_type{}, std::false_type{});
             }
             // ---- return the table to zero: only the k-mers of the last window are still counted
             for (int p = lane; p < nk; p += 32) tab[kmer_at(a.seq, gpos + n - 1 + p, kmask)] = 0;
@@ -630,6 +894,27 @@ static void launch_filter_k(int k, const FilterArgs &fa, int grid, cudaStream_t 
     }
 }
 
+template <int K> static void launch_eval_t(const EvalArgs &ea, const ProfDev &P, int q, int grid, int threads, size_t smem, cudaStream_t st)
+{
+    if (threads > 512) {       // more than 16 warps per CTA: the 85-register build
+        cudaFuncSetAttribute(kgma_eval<K, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kgma_eval<K, 768><<<grid, threads, smem, st>>>(ea, P, q);
+    } else {
+        cudaFuncSetAttribute(kgma_eval<K, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kgma_eval<K, 512><<<grid, threads, smem, st>>>(ea, P, q);
+    }
+}
+
+static void launch_eval_k(int k, const EvalArgs &ea, const ProfDev &P, int q, int grid, int threads, size_t smem, cudaStream_t st)
+{
+    switch (k) {
+    case 1: launch_eval_t<1>(ea, P, q, grid, threads, smem, st); break; case 2: launch_eval_t<2>(ea, P, q, grid, threads, smem, st); break;
+    case 3: launch_eval_t<3>(ea, P, q, grid, threads, smem, st); break; case 4: launch_eval_t<4>(ea, P, q, grid, threads, smem, st); break;
+    case 5: launch_eval_t<5>(ea, P, q, grid, threads, smem, st); break; case 6: launch_eval_t<6>(ea, P, q, grid, threads, smem, st); break;
+    default: launch_eval_t<7>(ea, P, q, grid, threads, smem, st); break;
+    }
+}
+
 static double now_ms()
 {
     using namespace std::chrono;
@@ -637,12 +922,15 @@ static double now_ms()
 }
 
 // warps per CTA and dynamic shared memory of kgma_eval for this k
-static int eval_shape(const kgma_ctx *ctx, int k, int *warps_out, size_t *smem_out)
+static int eval_shape(const kgma_ctx *ctx, int k, bool serial, int *warps_out, size_t *smem_out)
 {
     const size_t nb = (size_t)1 << (2 * k);
-    const size_t per_warp = nb * 2 + 64 * 4 + 64 * 4 + 64 * 8;
+    // one 4^k x u16 count table per warp, next to the profile's S table (the serial kernel adds its 64-step staging arrays)
+    const size_t per_warp = nb * 2 + (serial ? 64 * 4 + 64 * 4 + 64 * 8 : 0);
     if (ctx->smem_optin < nb * 4 + per_warp) return KGMA_E_UNSUPPORTED;
-    int w = (int)std::min<size_t>((ctx->smem_optin - nb * 4) / per_warp, 16);
+    int wmax = serial ? 16 : 24;
+    if (const char *e = getenv("KGMA_EVAL_WARPS")) wmax = std::max(1, std::min(24, atoi(e)));
+    int w = (int)std::min<size_t>((ctx->smem_optin - nb * 4) / per_warp, (size_t)wmax);
     *warps_out = w; *smem_out = nb * 4 + (size_t)w * per_warp;
     return KGMA_OK;
 }
@@ -751,7 +1039,9 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     if (rc) return rc;
 
     int ewarps = 0; size_t esmem = 0;
-    rc = eval_shape(ctx, pl.k, &ewarps, &esmem);
+    const char *ek_env = getenv("KGMA_EVAL_KERNEL");
+    const bool eval_serial = ek_env && !strcmp(ek_env, "serial");
+    rc = eval_shape(ctx, pl.k, eval_serial, &ewarps, &esmem);
     if (rc) return set_err(ctx, rc, "k = %d does not fit the shared-memory count tables", pl.k);
     const size_t nb = (size_t)1 << (2 * pl.k);
     const int egrid = ctx->num_sms;
@@ -880,7 +1170,15 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     for (int q = 0; q < C; q++) {
         const ProfTab &t = pl.tabs[q];
         ea.prof[q].N2 = t.N2; ea.prof[q].twoN = t.twoN; ea.prof[q].sumS2 = t.sumS2;
-        ea.prof[q].T = t.T; ea.prof[q].Tlo = t.Tlo; ea.prof[q].Thi = t.Thi; ea.prof[q].nk = (int)t.nk; ea.prof[q].pad = 0;
+        ea.prof[q].T = t.T; ea.prof[q].Tlo = t.Tlo; ea.prof[q].Thi = t.Thi; ea.prof[q].nk = (int)t.nk; ea.prof[q].N = t.N;
+        {   // D < Thi  <=>  N (N Q - 2 A) < Thi - sum S^2  <=>  N Q - 2 A < ceil((Thi - sum S^2) / N); everything must fit 31 bits
+            int64_t maxS = 0; for (int32_t v : t.S_rev) maxS = std::max<int64_t>(maxS, v);
+            const __int128 umax = (__int128)t.N * t.nk * t.nk + 2 * (__int128)t.nk * maxS;
+            const __int128 num = (__int128)t.Thi - t.sumS2;
+            __int128 uq = num >= 0 ? (num + t.N - 1) / t.N : -((-num) / t.N);          // ceil for either sign
+            ea.prof[q].u_ok = umax < ((__int128)1 << 30) && uq < ((__int128)1 << 30) && uq > -((__int128)1 << 30);
+            ea.prof[q].uThi = ea.prof[q].u_ok ? (int)uq : 0;
+        }
         {
             const __int128 R = (__int128)t.N2 * t.nk + t.sumS2 - t.Thi;
             ea.prof[q].R = R > 0 && R < ((__int128)1 << 62) ? (long long)R : 0;
@@ -889,15 +1187,15 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     ea.runs = (kgma_run *)(ds + o_runs); ea.run_cap = run_cap; ea.run_count = d_counters;
     ea.first_D = (long long *)(ds + o_first);
     ea.dists = want_dists ? (long long *)(ds + o_dists) : nullptr; ea.dist_stride = std::max<int64_t>(ndist, 1);
-    KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+    if (eval_serial) KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_eval_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
     auto launch_eval = [&](const std::vector<int> &qs, bool dense_items, size_t gi, const FilterGroup *fg) -> int {
         ea.nq = (int)qs.size();
         for (size_t i = 0; i < qs.size(); i++) ea.qlist[i] = qs[i];
         if (dense_items) { ea.cand = nullptr; ea.cand_count = nullptr; ea.bitmap = nullptr; ea.n_items = n_items; }
         else { ea.cand = (const uint32_t *)(ds + fg->o_cand); ea.cand_count = d_counters + 1 + gi; ea.bitmap = (const uint32_t *)(ds + fg->o_bits); ea.n_items = 0; }
-        kgma_eval<<<egrid, ewarps * 32, esmem, sc_>>>(ea);
+        if (eval_serial) { kgma_eval_serial<<<egrid, ewarps * 32, esmem, sc_>>>(ea); st.launches++; }
+        else for (int q : qs) { launch_eval_k(pl.k, ea, ea.prof[q], q, egrid, ewarps * 32, esmem, sc_); st.launches++; }
         KGMA_CUDA(ctx, cudaGetLastError());
-        st.launches++;
         return KGMA_OK;
     };
     uint32_t cnts[64] = { 0 };

@@ -1298,6 +1298,57 @@ def test_tagged_extension_kernel_equals_path_summary_kernel(K, O, prof, monkeypa
     assert redone > 0                                     # the hand-over to the path-summary kernel was exercised
 
 
+def test_parallel_slide_kernel_equals_serial_kernel(K, O, prof, synth, tmp_path, monkeypatch):
+    """the count-table kernel slides 16 steps at a time with all lanes busy (kgma_eval, one MATCH.ANY per batch); the round-1
+    form with the slide on lane 0 is kept as kgma_eval_serial (KGMA_EVAL_KERNEL=serial).  Both must report the same runs,
+    first-window distances, hits and -- with do_return_dists -- the same distance for every window, on genomes with
+    homopolymers / N runs (one k-mer entering and leaving at every step), short records, and k = 2 .. 7"""
+    path, recs = synth
+    refs = O.Fasta(TF)
+    rng = np.random.default_rng(6)
+
+    def rnd(n):
+        return "".join(np.asarray(list("ACGT"))[rng.integers(0, 4, size=n)])
+
+    lc = [("lowcomplexity", rnd(700) + "A" * 900 + rnd(33) + "N" * 1500 + refs.seq(3) + "CA" * 500 + refs.seq(10) + "TTTTTTA" * 90 + rnd(800)),
+          ("exact window", rnd(289)), ("one step", rnd(290)), ("seventeen steps", rnd(306)), ("polyT", "T" * 2000)]
+    lcp = tmp_path / "lc.fasta"
+    _write_fasta(lcp, lc)
+    so = ["profile", "record", "t_first", "flags"]
+    L = K.L
+    for gpath in (path, str(lcp), GENOME):
+        g = K.Genome.from_fasta(gpath)
+        for k in (6, 2, 7, 4):
+            RV, ws, cons = K.gen_ref_ws_cons(TF, k)
+            thr = 30.0 if k == 6 else float(np.quantile(O.ac_gma_testing(MINI_GENOME, np.asarray(RV), cons, k=k, windowsize=ws, thr=0, do_align=False,
+                                                                         do_return_dists=True)[2], 0.03))
+            for flags in (0, L.F_DENSE, L.F_WANT_DISTS):
+                if flags == L.F_WANT_DISTS and gpath == GENOME and k != 6:
+                    continue
+                a = K.scan_raw(g, [RV], [ws], [cons], [thr], k, L.MODE_SINGLE, 50, flags, -69, -1)
+                monkeypatch.setenv("KGMA_EVAL_KERNEL", "serial")
+                b = K.scan_raw(g, [RV], [ws], [cons], [thr], k, L.MODE_SINGLE, 50, flags, -69, -1)
+                monkeypatch.delenv("KGMA_EVAL_KERNEL")
+                assert np.array_equal(a.hits[["record", "first", "last", "D", "genome_pos", "cmi", "flags"]],
+                                      b.hits[["record", "first", "last", "D", "genome_pos", "cmi", "flags"]]), (gpath, k, flags)
+                ra, rb = a.runs.view(RUN_DT), b.runs.view(RUN_DT)
+                if flags:      # dense: identical spans, so identical run pieces (the candidate mode joins blocks the same way too)
+                    assert np.array_equal(np.sort(ra, order=so), np.sort(rb, order=so)), (gpath, k, flags)
+                if flags == L.F_WANT_DISTS:
+                    assert np.array_equal(a.dists[0], b.dists[0]) and a.dists[0].size == sum(max(0, g.seqsize(r) - ws) for r in range(len(g)))
+    # cluster mode: one launch per profile now
+    rvs, wss, cs, inv = K.cluster_ref_API(TF, 6)
+    rvs, wss, cs = K.eliminate_null_params(rvs, wss, cs, inv)
+    g = K.Genome.from_fasta(path)
+    for flags in (L.F_ALIGN, L.F_ALIGN | L.F_DENSE):
+        a = K.scan_raw(g, rvs, wss, cs, [35, 31, 38, 34, 27, 27], 6, L.MODE_CLUSTER, 100, flags, -200, -1)
+        monkeypatch.setenv("KGMA_EVAL_KERNEL", "serial")
+        b = K.scan_raw(g, rvs, wss, cs, [35, 31, 38, 34, 27, 27], 6, L.MODE_CLUSTER, 100, flags, -200, -1)
+        monkeypatch.delenv("KGMA_EVAL_KERNEL")
+        key = ["record", "profile", "first", "last", "D", "genome_pos", "cmi", "align_score"]
+        assert len(a.hits) >= 5 and np.array_equal(a.hits[key], b.hits[key])
+
+
 def test_two_contexts_share_nothing(K, prof, synth):
     """two contexts on the same device, used alternately on different genomes: each keeps its own device planes, tables,
     staging ring and scratch, so neither disturbs the other's resident genome"""
