@@ -31,33 +31,81 @@ struct KgmaMatch; record::Int32; reserved::Int32; first::Int64; last::Int64; end
 
 const F_ALIGN, F_DENSE, F_WANT_DISTS, F_WANT_CIGARS = UInt32(1), UInt32(2), UInt32(4), UInt32(8)
 
+const F_RESIDENT = UInt32(32)
+
 check(ctx, rc) = rc == 0 || error(unsafe_string(ccall((:kgma_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx)))
 
-function with_ctx(f; device::Int = 0)
-    ctx = Ref{Ptr{Cvoid}}(C_NULL)
-    rc = ccall((:kgma_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, ctx)
-    rc == 0 || error(unsafe_string(ccall((:kgma_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))   # no GPU => error, never a CPU fallback
-    try f(ctx[]) finally ccall((:kgma_destroy, LIB), Cvoid, (Ptr{Cvoid},), ctx[]) end
+# ---- one context per process and device: a kgma_ctx owns streams, page-locked staging blocks, device scratch and the device
+# planes of the largest genome it has seen (a genome-sized cudaMalloc costs 0.1-0.4 s, a scan 1-20 ms), so it is created on
+# first use and destroyed at exit -- never per call.  One context serves one Julia task at a time (calls are blocking).
+const CONTEXTS = Dict{Int, Ptr{Cvoid}}()
+const CTX_LOCK = ReentrantLock()
+
+function context(device::Int = 0)
+    lock(CTX_LOCK) do
+        get!(CONTEXTS, device) do
+            ctx = Ref{Ptr{Cvoid}}(C_NULL)
+            rc = ccall((:kgma_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, ctx)
+            rc == 0 || error(unsafe_string(ccall((:kgma_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))   # no B200 => error, never a CPU fallback
+            ctx[]
+        end
+    end
 end
 
-# FASTX parses; the 4-bit BioSequences words go over as they are (kgma_genome_append_bio4), no per-base Dict lookup.
-function load_genome(path::String)
+# ---- genomes are ingested once per file (native parallel FASTA parse + 2-bit pack, kgma_genome_from_fasta) and kept, resident
+# on the GPU, for as long as the file does not change: the second findGenes on the same genome pays ~1 ms, not the ingest.
+const GENOMES = Dict{Tuple{String, Float64, Int64}, Ptr{Cvoid}}()
+
+function genome(path::String, ctx)
+    st = stat(path)
+    key = (abspath(path), st.mtime, Int64(st.size))
+    lock(CTX_LOCK) do
+        g = get(GENOMES, key, C_NULL)
+        if g == C_NULL
+            for (k, old) in GENOMES          # one genome at a time: the context holds one set of device planes
+                ccall((:kgma_genome_destroy, LIB), Cvoid, (Ptr{Cvoid},), old); delete!(GENOMES, k)
+            end
+            ref = Ref{Ptr{Cvoid}}(C_NULL)
+            rc = ccall((:kgma_genome_from_fasta, LIB), Cint, (Cstring, Ref{Ptr{Cvoid}}), path, ref)
+            rc == 0 || error(rc == -3 ? "KeyError: $path holds a symbol outside IUPAC DNA" : "cannot ingest $path ($rc)")
+            g = ref[]
+            check(ctx, ccall((:kgma_genome_make_resident, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx, g))
+            GENOMES[key] = g
+        end
+        g
+    end
+end
+
+atexit() do
+    for g in values(GENOMES); ccall((:kgma_genome_destroy, LIB), Cvoid, (Ptr{Cvoid},), g); end
+    for c in values(CONTEXTS); ccall((:kgma_destroy, LIB), Cvoid, (Ptr{Cvoid},), c); end
+end
+
+identifier(g, r) = unsafe_string(ccall((:kgma_genome_identifier, LIB), Cstring, (Ptr{Cvoid}, Cint), g, r))
+
+# view(seq, first:last) of record r, straight from the packed planes (N restored from the mask)
+function subseq(g, r, rng::UnitRange)
+    buf = Vector{UInt8}(undef, length(rng) + 1)
+    ccall((:kgma_genome_get_seq, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{UInt8}), g, r, first(rng), last(rng), buf)
+    return LongDNA{4}(String(buf[1:end-1]))
+end
+
+# A caller that already holds its records as LongDNA{4} (no FASTA file) hands BioSequences' 4-bit words over as they are
+# (kgma_genome_append_bio4, no per-base Dict lookup).  A caller that packs to 2 bits itself can fill page-locked planes of the
+# library in place instead: kgma_genome_create_pinned + kgma_genome_record_planes + kgma_genome_seal (zero copy).
+function genome_from_records(records::Vector{FASTA.Record})
     g = Ref{Ptr{Cvoid}}(C_NULL)
     ccall((:kgma_genome_create, LIB), Cint, (Ref{Ptr{Cvoid}},), g)
-    records = FASTA.Record[]; seqs = KmerGMA.Seq[]
-    open(FASTA.Reader, path) do reader
-        for record in reader
-            seq = getSeq(record)
-            GC.@preserve seq begin
-                rc = ccall((:kgma_genome_append_bio4, LIB), Cint, (Ptr{Cvoid}, Cstring, Cstring, Ptr{UInt64}, Int64),
-                           g[], FASTA.identifier(record), FASTA.description(record), pointer(seq.data), length(seq))
-                rc == 0 || error("kgma_genome_append_bio4 failed ($rc)")
-            end
-            push!(records, record); push!(seqs, seq)
+    for record in records
+        seq = getSeq(record)
+        GC.@preserve seq begin
+            rc = ccall((:kgma_genome_append_bio4, LIB), Cint, (Ptr{Cvoid}, Cstring, Cstring, Ptr{UInt64}, Int64),
+                       g[], FASTA.identifier(record), FASTA.description(record), pointer(seq.data), length(seq))
+            rc == 0 || error("kgma_genome_append_bio4 failed ($rc)")
         end
     end
     ccall((:kgma_genome_seal, LIB), Cint, (Ptr{Cvoid},), g[])
-    return g[], records, seqs
+    return g[]
 end
 
 # refVec = S .* (1/N) (gen_ref_ws_cons) or S ./ N (cluster_ref_API): recover the integers the device needs
@@ -70,40 +118,37 @@ end
 
 function scan!(resultVec, hit_loci_vec, dist_vecs, genome_path, refVecs, windowsizes, consensus_seqs, thrs, k, mode, buff,
                flags, gap_open, gap_extend; cluster::Bool, get_hit_loci::Bool)
-    with_ctx() do ctx
-        g, records, seqs = load_genome(genome_path)
+    ctx = context()
+    g = genome(genome_path, ctx)
+    Ss = [ints_of(Vector{Float64}(rv)) for rv in refVecs]
+    cons = [Vector{UInt8}(string(c)) for c in consensus_seqs]
+    GC.@preserve Ss cons begin
+        profs = [KgmaProfile(k, Ss[i][2], windowsizes[i], pointer(Ss[i][1]), pointer(cons[i]), length(cons[i]), Float64(thrs[i])) for i in eachindex(Ss)]
+        P = Ref(KgmaScanParams(mode, flags | F_RESIDENT, buff, gap_open, gap_extend, 0, 1, -1, 0))
+        res = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ctx, ccall((:kgma_scan, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{KgmaProfile}, Cint, Ref{KgmaScanParams}, Ref{Ptr{Cvoid}}),
+                         ctx, g, profs, length(profs), P, res))
         try
-            Ss = [ints_of(Vector{Float64}(rv)) for rv in refVecs]
-            cons = [Vector{UInt8}(string(c)) for c in consensus_seqs]
-            GC.@preserve Ss cons begin
-                profs = [KgmaProfile(k, Ss[i][2], windowsizes[i], pointer(Ss[i][1]), pointer(cons[i]), length(cons[i]), Float64(thrs[i])) for i in eachindex(Ss)]
-                P = Ref(KgmaScanParams(mode, flags, buff, gap_open, gap_extend, 0, 1, -1, 0))
-                res = Ref{Ptr{Cvoid}}(C_NULL)
-                check(ctx, ccall((:kgma_scan, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{KgmaProfile}, Cint, Ref{KgmaScanParams}, Ref{Ptr{Cvoid}}),
-                                 ctx, g, profs, length(profs), P, res))
-                n = ccall((:kgma_result_n_hits, LIB), Int64, (Ptr{Cvoid},), res[])
-                hits = unsafe_wrap(Array, ccall((:kgma_result_hits, LIB), Ptr{KgmaHit}, (Ptr{Cvoid},), res[]), n)
-                for h in hits
-                    record, seq = records[h.record + 1], seqs[h.record + 1]
-                    rng = h.first:h.last
-                    if cluster      # src/OmnGenomeMiner.jl:141-149
-                        push!(resultVec, FASTA.Record(FASTA.identifier(record) * " | Dist = " * string(round(h.dist, digits = 2)) *
-                              " | KFV = $(h.profile) | MatchPos = $rng | GenomePos = $(h.genome_pos) | Len = " * string(length(rng)), view(seq, rng)))
-                    else            # src/Alignment.jl:57-81 append_hit!
-                        KmerGMA.append_hit!(resultVec, record, seq, false, 0, h.dist, rng, h.genome_pos)
-                    end
-                    get_hit_loci && push!(hit_loci_vec, h.first + h.genome_pos)
+            n = ccall((:kgma_result_n_hits, LIB), Int64, (Ptr{Cvoid},), res[])
+            hits = unsafe_wrap(Array, ccall((:kgma_result_hits, LIB), Ptr{KgmaHit}, (Ptr{Cvoid},), res[]), n)
+            for h in hits
+                rng = h.first:h.last
+                id = identifier(g, h.record)
+                d = string(round(h.dist, digits = 2))                 # Julia's own rounding and printing
+                header = cluster ?                                       # src/OmnGenomeMiner.jl:141-149 / src/Alignment.jl:71-78
+                    id * " | Dist = " * d * " | KFV = $(h.profile) | MatchPos = $rng | GenomePos = $(h.genome_pos) | Len = " * string(length(rng)) :
+                    id * " | dist = " * d * " | MatchPos = $rng | GenomePos = $(h.genome_pos) | Len = " * string(length(rng))
+                push!(resultVec, FASTA.Record(header, subseq(g, h.record, rng)))
+                get_hit_loci && push!(hit_loci_vec, h.first + h.genome_pos)
+            end
+            if (flags & F_WANT_DISTS) != 0
+                for q in eachindex(dist_vecs)
+                    nd = ccall((:kgma_result_n_dists, LIB), Int64, (Ptr{Cvoid}, Cint), res[], q - 1)
+                    append!(dist_vecs[q], unsafe_wrap(Array, ccall((:kgma_result_dists, LIB), Ptr{Float64}, (Ptr{Cvoid}, Cint), res[], q - 1), nd))
                 end
-                if (flags & F_WANT_DISTS) != 0
-                    for q in eachindex(dist_vecs)
-                        nd = ccall((:kgma_result_n_dists, LIB), Int64, (Ptr{Cvoid}, Cint), res[], q - 1)
-                        append!(dist_vecs[q], unsafe_wrap(Array, ccall((:kgma_result_dists, LIB), Ptr{Float64}, (Ptr{Cvoid}, Cint), res[], q - 1), nd))
-                    end
-                end
-                ccall((:kgma_result_free, LIB), Cvoid, (Ptr{Cvoid},), res[])
             end
         finally
-            ccall((:kgma_genome_destroy, LIB), Cvoid, (Ptr{Cvoid},), g)
+            ccall((:kgma_result_free, LIB), Cvoid, (Ptr{Cvoid},), res[])
         end
     end
 end
@@ -129,23 +174,18 @@ function KmerGMA.Omn_KmerGMA!(; genome_path::String, refVecs, windowsizes, conse
 end
 
 function KmerGMA.exactMatch(query, genome_path::String; overlap::Bool = true)
-    with_ctx() do ctx
-        g, records, _ = load_genome(genome_path)
-        try
-            q = Vector{UInt8}(string(query isa FASTA.Record ? getSeq(query) : query))
-            out = Ref{Ptr{KgmaMatch}}(C_NULL); n = Ref{Int64}(0)
-            check(ctx, ccall((:kgma_exact_match, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt8}, Int64, Cint, UInt32, Ref{Ptr{KgmaMatch}}, Ref{Int64}),
-                             ctx, g, q, length(q), overlap, 0, out, n))
-            identify = Dict{String, Vector{UnitRange{Int64}}}()
-            for m in unsafe_wrap(Array, out[], n[])
-                push!(get!(identify, FASTA.identifier(records[m.record + 1]), UnitRange{Int64}[]), m.first:m.last)
-            end
-            n[] > 0 && ccall((:kgma_free, LIB), Cvoid, (Ptr{Cvoid},), out[])
-            return isempty(identify) ? "no match" : identify      # src/ExactMatch.jl:116-120
-        finally
-            ccall((:kgma_genome_destroy, LIB), Cvoid, (Ptr{Cvoid},), g)
-        end
+    ctx = context()
+    g = genome(genome_path, ctx)
+    q = Vector{UInt8}(string(query isa FASTA.Record ? getSeq(query) : query))
+    out = Ref{Ptr{KgmaMatch}}(C_NULL); n = Ref{Int64}(0)
+    check(ctx, ccall((:kgma_exact_match, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt8}, Int64, Cint, UInt32, Ref{Ptr{KgmaMatch}}, Ref{Int64}),
+                     ctx, g, q, length(q), overlap, F_RESIDENT, out, n))
+    identify = Dict{String, Vector{UnitRange{Int64}}}()
+    for m in unsafe_wrap(Array, out[], n[])
+        push!(get!(identify, identifier(g, m.record), UnitRange{Int64}[]), m.first:m.last)
     end
+    n[] > 0 && ccall((:kgma_free, LIB), Cvoid, (Ptr{Cvoid},), out[])
+    return isempty(identify) ? "no match" : identify      # src/ExactMatch.jl:116-120
 end
 
 end # module

@@ -681,6 +681,22 @@ def _emit(genome: Genome, out: ScanOutput, cluster: bool, resultVec, hit_loci_ve
             align_vec.append(cg)
 
 
+def _check_fixed_params(k: int, ScaleFactor, mask, Nt_bits):
+    """The device path computes d = D / (2 k N^2), i.e. ScaleFactor = 1/k, with the k-mer mask 4^k - 1 and the standard
+    NUCLEOTIDE_BITS table -- what findGenes / findGenes_cluster_mode always pass (API.jl:86-87,204-205).  The reference
+    operators' own DEFAULTS are ScaleFactor = 1/6 and mask = 4095 whatever k is (GenomeMiner.jl:12-14): a direct operator call
+    with k != 6 that relies on those defaults gets the findGenes scaling here, and anything explicitly different is refused."""
+    if ScaleFactor is not None and abs(float(ScaleFactor) - 1.0 / k) > 1e-15:
+        raise KmerGMAError(L.E_UNSUPPORTED, f"ScaleFactor = {ScaleFactor}: the device path is fixed to 1/k = {1.0 / k} (rescale thr by ScaleFactor*k instead)")
+    if mask is not None and int(mask) != 4 ** k - 1:
+        raise KmerGMAError(L.E_UNSUPPORTED, f"mask = {mask}: the device path is fixed to 4^k - 1 = {4 ** k - 1}")
+    if Nt_bits is not None:
+        std = {"A": 0, "C": 1, "G": 2, "T": 3, "N": 3}
+        got = {str(a).upper(): int(b) for a, b in dict(Nt_bits).items()}
+        if got != std:
+            raise KmerGMAError(L.E_UNSUPPORTED, "Nt_bits differs from NUCLEOTIDE_BITS (A0 C1 G2 T3, N -> 3): the packed genome is fixed to it")
+
+
 def ac_gma_testing(*, genome_path, refVec, consensus_refseq: str, k: int = 6, windowsize: int = 289,
                    thr: float = 33.5, buff: int = 50, mask=None, Nt_bits=None, ScaleFactor=None,
                    do_align: bool = True, result_align_vec: Optional[list] = None,
@@ -691,7 +707,9 @@ def ac_gma_testing(*, genome_path, refVec, consensus_refseq: str, k: int = 6, wi
                    dense: bool = False, ctx: Optional[Context] = None):
     """ac_gma_testing! (src/GenomeMiner.jl:4-109): single-profile scan; appends to resultVec /
     hit_loci_vec / result_align_vec / dist_vec in place and returns the raw ScanOutput.
-    `mask`, `Nt_bits`, `ScaleFactor` are accepted for signature parity (they are functions of k)."""
+    `mask`, `Nt_bits`, `ScaleFactor` are accepted for signature parity; values other than 4^k-1 / the standard table / 1/k are
+    refused (see _check_fixed_params)."""
+    _check_fixed_params(k, ScaleFactor, mask, Nt_bits)
     resultVec = [] if resultVec is None else resultVec
     ctx = ctx or default_context()
     g = _as_genome(genome_path)
@@ -730,7 +748,10 @@ def Omn_KmerGMA(*, genome_path, refVecs, windowsizes, consensus_seqs, resultVec:
                 get_hit_loci: bool = False, hit_loci_vec: Optional[list] = None, get_aligns: bool = False,
                 do_return_dists: bool = False, dist_vec_vec: Optional[List[list]] = None,
                 dense: bool = False, ctx: Optional[Context] = None):
-    """Omn_KmerGMA! (src/OmnGenomeMiner.jl:7-162): C profiles scanned together."""
+    """Omn_KmerGMA! (src/OmnGenomeMiner.jl:7-162): C profiles scanned together.
+    With get_aligns the reference pushes one alignment per extension it performs, including those whose hit the second overlap
+    test (:139) then rejects; align_vec here holds the alignments of the emitted hits only, in hit order."""
+    _check_fixed_params(k, ScaleFactor, mask, Nt_bits)
     ctx = ctx or default_context()
     g = _as_genome(genome_path)
     Cn = len(windowsizes)

@@ -87,7 +87,13 @@ struct kgma_ctx {
     int64_t   d_valid_lo = 0, d_valid_hi = 0;       // base range of seq2 a RESIDENT scan may reuse without upload
     int64_t   d_have_lo = 0, d_have_hi = 0;         // base range of seq2 physically present (same genome uid) - extension reads it
     // prefilter weight tables of recent scans (rebuilt only when the profiles / thresholds change)
-    struct FTab { uint64_t key = 0; std::vector<uint16_t> tab; int M = 0; bool ok = false; double load = 0; };
+    struct FTab {
+        uint64_t key = 0; int M = 0; bool ok = false; double load = 0;
+        bool nine = false;                 // tab9 (kgma_prefilter9) or tab (kgma_prefilter)
+        std::vector<uint16_t> tab;         // [65536] 8-mer -> sum of the 9-k contained k-mer weights
+        std::vector<uint8_t>  tab9;        // [3 * 65536] 9-mer with a ternary last base -> ceil(sum of 10-k weights / step)
+        uint32_t step = 1, thrw = 0;       // flag when the covering sum of entries > thrw
+    };
     std::deque<FTab> ftabs;        // deque: references stay valid while entries are appended
     // extension scratch, two slots so that extensions can be queued while a scan still streams
     void     *a_dev[2] = {}, *a_host[2] = {}; size_t a_dev_bytes[2] = {}, a_host_bytes[2] = {};

@@ -32,6 +32,7 @@
 #include <thread>
 #include <sys/mman.h>
 #include "staged_upload.h"
+#include <cuda/barrier>
 
 namespace kgma {
 
@@ -116,6 +117,110 @@ __global__ void __launch_bounds__(1024, 1) kgma_prefilter(FilterArgs a)
         bool flag = (F > a.thrw) && tgt >= tb0 && tgt < tb1;
         unsigned bal = __ballot_sync(FULL, flag);
         if (bal) {                                       // warp-aggregated atomic append
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(a.cand_count, (uint32_t)__popc(bal));
+            base = __shfl_sync(FULL, base, 0);
+            if (flag) {
+                uint32_t pos = base + __popc(bal & ((1u << lane) - 1));
+                if (pos < a.cand_cap) a.cand[pos] = (uint32_t)tgt;
+                atomicOr(a.bitmap + (tgt >> 5), 1u << (tgt & 31));
+            }
+        }
+        cur = nxt; nxt = nx2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kgma_prefilter9<K>: the same filter with 10-K k-mers per table lookup instead of 9-K (k = 6: 16 lookups per 64 bases instead
+// of 22, k = 7: 22 instead of 32).  The kernel is bound by shared-memory wavefronts (3.5 per random 32-lane gather), so fewer
+// gathers is the only lever; a table indexed by 9-mers needs 4^9 entries, 256 KB at one byte each -- more than an SM has.
+// Here the LAST base of the 9-mer is ternary {A, C, G|T}: 3 * 4^8 one-byte entries = 192 KB.  The 9-K k-mers that lie in
+// the first eight bases are exact; the one k-mer that reaches the ninth base is exact for A and C and bounded by the larger of
+// its G and T weights otherwise (N is folded to T in the packed genome).  Entries are weights / step, rounded up, so the filter
+// stays a rigorous upper bound; flag when the covering sum of entries exceeds 2^14 / step.
+// The table is staged with bulk asynchronous copies (cp.async.bulk, the TMA engine) completing on an mbarrier; the genome
+// itself is read once, 128 bits per thread, straight into registers -- nothing is reused, so there is nothing to stage.
+struct Filter9Args {
+    const uint4   *seq;
+    const uint8_t *tab;         // [3 * 65536] entry(9-mer with ternary last base)
+    int64_t  blk_begin, blk_end;
+    int      M;
+    uint32_t thrw;              // flag when the covering sum of entries > thrw  (= floor(2^14 / step))
+    uint32_t *cand; uint32_t cand_cap; uint32_t *cand_count; uint32_t *bitmap;
+};
+constexpr uint32_t TAB9_BYTES = 3u * 65536u;
+
+template <int K>
+__device__ __forceinline__ uint32_t block_weight9(const uint8_t *tab, uint4 w, uint32_t nw)
+{
+    constexpr int STRIDE = 10 - K;                      // k-mers fully contained in one 9-mer
+    constexpr int NLOOK = (FBLOCK + STRIDE - 1) / STRIDE;
+    const uint32_t W[5] = { w.x, w.y, w.z, w.w, nw };
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < NLOOK; i++) {
+        const int b = 2 * i * STRIDE;                   // bit offset of the 9-mer
+        const int wi = b >> 5, s = b & 31;
+        uint32_t x;
+        if (s + 18 <= 32) x = (W[wi] >> s) & 0x3FFFFu;
+        else x = __funnelshift_r(W[wi], W[wi + 1], s) & 0x3FFFFu;
+        x &= ~((x >> 1) & 0x10000u);                    // ninth base G (10) or T (11) -> class 2 (10)
+        sum += tab[x];
+    }
+    return sum;
+}
+
+template <int K>
+__global__ void __launch_bounds__(1024, 1) kgma_prefilter9(Filter9Args a)
+{
+    extern __shared__ __align__(128) uint8_t s_tab9[];
+    __shared__ cuda::barrier<cuda::thread_scope_block> bar;
+    if (threadIdx.x == 0) { init(&bar, blockDim.x); cuda::device::experimental::fence_proxy_async_shared_cta(); }
+    __syncthreads();
+    {
+        cuda::barrier<cuda::thread_scope_block>::arrival_token tok;
+        if (threadIdx.x == 0) {
+            constexpr uint32_t CHUNK = 32768;
+            for (uint32_t o = 0; o < TAB9_BYTES; o += CHUNK)
+                cuda::device::memcpy_async_tx(s_tab9 + o, a.tab + o, cuda::aligned_size_t<16>(CHUNK), bar);
+            tok = cuda::device::barrier_arrive_tx(bar, 1, TAB9_BYTES);
+        } else tok = bar.arrive();
+        bar.wait(std::move(tok));
+    }
+
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t grp0 = a.blk_begin >> 5, ngrp = (a.blk_end - a.blk_begin) >> 5;
+    const int64_t gb = grp0 + (ngrp * warp) / nwarps, ge = grp0 + (ngrp * (warp + 1)) / nwarps;
+    if (gb >= ge) return;
+    const int64_t tb0 = gb << 5, tb1 = ge << 5;
+    const int extra = (a.M - 1 + 31) >> 5;
+    const int64_t gend = ge + extra;
+    const int srcl = (lane - a.M) & 31;
+
+    uint4 cur = __ldg(a.seq + (gb << 5) + lane);
+    uint4 nxt = __ldg(a.seq + ((gb + 1) << 5) + lane);
+    uint32_t run = 0, prevP = 0;
+    for (int64_t g = gb; g < gend; ++g) {
+        uint4 nx2 = __ldg(a.seq + ((g + 2) << 5) + lane);
+        uint32_t nw = __shfl_down_sync(FULL, cur.x, 1);
+        uint32_t n0 = __shfl_sync(FULL, nxt.x, 0);
+        if (lane == 31) nw = n0;
+        uint32_t G = block_weight9<K>(s_tab9, cur, nw);
+        uint32_t P = G;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULL, P, d); if (lane >= d) P += t; }
+        P += run;
+        run = __shfl_sync(FULL, P, 31);
+        uint32_t pa = __shfl_sync(FULL, P, srcl), pb = __shfl_sync(FULL, prevP, srcl);
+        uint32_t F = P - (lane >= a.M ? pa : pb);
+        prevP = P;
+        int64_t tgt = (g << 5) + lane - (a.M - 1);
+        bool flag = (F > a.thrw) && tgt >= tb0 && tgt < tb1;
+        unsigned bal = __ballot_sync(FULL, flag);
+        if (bal) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(a.cand_count, (uint32_t)__popc(bal));
             base = __shfl_sync(FULL, base, 0);
@@ -843,10 +948,11 @@ static int make_plan(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles
 // cannot be filtered at all (R <= 0: even a window sharing no k-mer with the profile could be below thr).
 // *load = expected covering sum of a uniformly random sequence as a fraction of the flag threshold: the closer to 1,
 // the more blocks survive the filter.
-static bool build_filter_table(const ScanPlan &pl, const std::vector<int> &group, std::vector<uint16_t> &tab8, int &M, double *load)
+static bool build_filter_table(const ScanPlan &pl, const std::vector<int> &group, kgma_ctx::FTab &ft, bool nine)
 {
     const int k = pl.k; const size_t nb = (size_t)1 << (2 * k);
     if (k > 8) return false;
+    int &M = ft.M;
     M = (int)((pl.maxnk - 1 + FBLOCK - 1) / FBLOCK) + 1;
     if (M > 32 || M < 1) return false;
     std::vector<uint32_t> W(nb, 0);
@@ -864,17 +970,50 @@ static bool build_filter_table(const ScanPlan &pl, const std::vector<int> &group
             W[i] = std::max(W[i], wc);
         }
     }
-    const int nper = 9 - k; const uint32_t kmask = (uint32_t)nb - 1;
-    tab8.resize(65536);
-    double sum = 0;
-    for (uint32_t x = 0; x < 65536; x++) {
-        uint32_t v = 0;
-        for (int j = 0; j < nper; j++) v += W[(x >> (2 * j)) & kmask];
-        tab8[x] = (uint16_t)std::min<uint32_t>(v, 65535u);
-        sum += tab8[x];
+    const uint32_t kmask = (uint32_t)nb - 1;
+    ft.nine = nine;
+    if (!nine) {
+        const int nper = 9 - k;
+        ft.tab.resize(65536);
+        double sum = 0;
+        for (uint32_t x = 0; x < 65536; x++) {
+            uint32_t v = 0;
+            for (int j = 0; j < nper; j++) v += W[(x >> (2 * j)) & kmask];
+            ft.tab[x] = (uint16_t)std::min<uint32_t>(v, 65535u);
+            sum += ft.tab[x];
+        }
+        const int nlook = (FBLOCK + nper - 1) / nper;
+        ft.load = sum / 65536.0 * nlook * M / (double)(1u << WFRAC);
+        ft.step = 1; ft.thrw = 1u << WFRAC;
+        return true;
     }
-    const int nlook = (FBLOCK + nper - 1) / nper;
-    *load = sum / 65536.0 * nlook * M / (double)(1u << WFRAC);
+    // 9-mer table with a ternary last base (kgma_prefilter9): the k-mers at offsets 0 .. 8-k lie inside the first eight bases,
+    // the one at offset 9-k ends on the ninth base; class 2 of the ninth base stands for G or T
+    if (k > 9) return false;
+    const int nin = 9 - k;                                       // exact k-mers per entry (the tail k-mer comes on top)
+    std::vector<uint32_t> raw((size_t)TAB9_BYTES);
+    uint32_t maxv = 0;
+    for (uint32_t c = 0; c < 3; c++)
+        for (uint32_t x8 = 0; x8 < 65536; x8++) {
+            uint32_t v = 0;
+            for (int j = 0; j < nin; j++) v += W[(x8 >> (2 * j)) & kmask];
+            auto tail = [&](uint32_t b9) { return W[(((x8 | (b9 << 16)) >> (2 * nin)) & kmask)]; };
+            v += c < 2 ? tail(c) : std::max(tail(2), tail(3));
+            raw[(size_t)c * 65536 + x8] = v;
+            maxv = std::max(maxv, v);
+        }
+    const uint32_t step = std::max<uint32_t>(1, (maxv + 254) / 255);
+    ft.tab9.resize(TAB9_BYTES);
+    double sum = 0, wsum = 0;
+    for (size_t i = 0; i < raw.size(); i++) {
+        const uint32_t e = (raw[i] + step - 1) / step;           // rounded up: still an upper bound
+        ft.tab9[i] = (uint8_t)e;
+        const double pw = i < 131072 ? 1.0 : 2.0;                // a random ninth base falls into class 2 twice as often
+        sum += pw * e; wsum += pw;
+    }
+    const int nlook = (FBLOCK + (10 - k) - 1) / (10 - k);
+    ft.step = step; ft.thrw = (1u << WFRAC) / step;              // sum * step > 2^14  <=>  sum > floor(2^14 / step)
+    ft.load = sum / wsum * step * nlook * M / (double)(1u << WFRAC);
     return true;
 }
 
@@ -912,6 +1051,22 @@ static void launch_eval_k(int k, const EvalArgs &ea, const ProfDev &P, int q, in
     case 3: launch_eval_t<3>(ea, P, q, grid, threads, smem, st); break; case 4: launch_eval_t<4>(ea, P, q, grid, threads, smem, st); break;
     case 5: launch_eval_t<5>(ea, P, q, grid, threads, smem, st); break; case 6: launch_eval_t<6>(ea, P, q, grid, threads, smem, st); break;
     default: launch_eval_t<7>(ea, P, q, grid, threads, smem, st); break;
+    }
+}
+
+template <int K> static void launch_filter9(const Filter9Args &fa, int grid, cudaStream_t st)
+{
+    cudaFuncSetAttribute(kgma_prefilter9<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAB9_BYTES);
+    kgma_prefilter9<K><<<grid, 1024, TAB9_BYTES, st>>>(fa);
+}
+
+static void launch_filter9_k(int k, const Filter9Args &fa, int grid, cudaStream_t st)
+{
+    switch (k) {
+    case 1: launch_filter9<1>(fa, grid, st); break; case 2: launch_filter9<2>(fa, grid, st); break;
+    case 3: launch_filter9<3>(fa, grid, st); break; case 4: launch_filter9<4>(fa, grid, st); break;
+    case 5: launch_filter9<5>(fa, grid, st); break; case 6: launch_filter9<6>(fa, grid, st); break;
+    default: launch_filter9<7>(fa, grid, st); break;
     }
 }
 
@@ -964,10 +1119,15 @@ static const kgma_ctx::FTab *get_ftab(kgma_ctx *ctx, const ScanPlan &pl, const s
     auto mix = [&](const void *p, size_t n) { const unsigned char *b = (const unsigned char *)p; for (size_t i = 0; i < n; i++) { key ^= b[i]; key *= 1099511628211ull; } };
     for (int q : group) mix(&pl.tabs[(size_t)q].hash, 8);
     mix(&pl.maxnk, 8);
+    // the 9-mer table (kgma_prefilter9) is the default; KGMA_PREFILTER=8mer selects the round-1 kernel and its table
+    const char *pf_env = getenv("KGMA_PREFILTER");
+    const bool nine = !(pf_env && !strcmp(pf_env, "8mer")) && pl.k <= 7;
+    const unsigned char nine_b = nine ? 1 : 0;
+    mix(&nine_b, 1);
     for (const auto &f : ctx->ftabs) if (f.key == key) return &f;
     ctx->ftabs.emplace_back();
     kgma_ctx::FTab &f = ctx->ftabs.back();
-    f.key = key; f.ok = build_filter_table(pl, group, f.tab, f.M, &f.load);
+    f.key = key; f.ok = build_filter_table(pl, group, f, nine);
     return &f;
 }
 
@@ -1079,7 +1239,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
     const size_t o_S = carve((size_t)C * nb * 4), o_recs = carve(recs.size() * sizeof(RecDev));
     const size_t o_seed = carve((seeds.size() + 1) * 4);
-    for (FilterGroup &fg : groups) if (!fg.dense) fg.o_tab = carve(65536 * 2);
+    for (FilterGroup &fg : groups) if (!fg.dense) fg.o_tab = carve(fg.ft->nine ? (size_t)TAB9_BYTES : (size_t)65536 * 2);
     const size_t up_bytes = o;                                     // everything above is uploaded from the staging block
     const size_t o_cnt = carve(512), o_first = carve((size_t)C * std::max(nr, 1) * 8), o_runs = carve((size_t)run_cap * sizeof(kgma_run));
     const size_t bitmap_bytes = ((size_t)nblk_total / 32 + 4) * 4;
@@ -1095,7 +1255,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     if (rc) return rc;
     unsigned char *hs = (unsigned char *)hsv, *hback = hs + up_bytes, *hbackA = hback + back_bytes;
     for (int q = 0; q < C; q++) memcpy(hs + o_S + (size_t)q * nb * 4, pl.tabs[q].S_rev.data(), nb * 4);
-    for (const FilterGroup &fg : groups) if (!fg.dense) memcpy(hs + fg.o_tab, fg.ft->tab.data(), 65536 * 2);
+    for (const FilterGroup &fg : groups) if (!fg.dense) { if (fg.ft->nine) memcpy(hs + fg.o_tab, fg.ft->tab9.data(), TAB9_BYTES); else memcpy(hs + fg.o_tab, fg.ft->tab.data(), 65536 * 2); }
     memcpy(hs + o_recs, recs.data(), recs.size() * sizeof(RecDev));
     if (!seeds.empty()) memcpy(hs + o_seed, seeds.data(), seeds.size() * 4);
     { const uint32_t ns = (uint32_t)seeds.size(); memcpy(hs + o_seed + seeds.size() * 4, &ns, 4); }
@@ -1230,6 +1390,23 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     int64_t done_blk = blk_lo;                               // target blocks already filtered
     const int64_t need_after = (int64_t)(M + 1) * FBLOCK + 3 * FGROUP;     // bases that must be present past a target block
     bool first_filter = true;
+    auto launch_group_filter = [&](const FilterGroup &fg, size_t gi, int64_t b0, int64_t b1) {
+        if (fg.ft->nine) {
+            Filter9Args fa{};
+            fa.seq = (const uint4 *)ctx->d_seq2; fa.tab = (const uint8_t *)(ds + fg.o_tab); fa.M = fg.ft->M; fa.thrw = fg.ft->thrw;
+            fa.cand = (uint32_t *)(ds + fg.o_cand); fa.cand_cap = cand_cap; fa.cand_count = d_counters + 1 + gi;
+            fa.bitmap = (uint32_t *)(ds + fg.o_bits);
+            fa.blk_begin = b0; fa.blk_end = b1;
+            launch_filter9_k(pl.k, fa, fgrid, sc_);
+        } else {
+            FilterArgs fa{};
+            fa.seq = (const uint4 *)ctx->d_seq2; fa.tab = (const uint16_t *)(ds + fg.o_tab); fa.M = fg.ft->M; fa.thrw = fg.ft->thrw;
+            fa.cand = (uint32_t *)(ds + fg.o_cand); fa.cand_cap = cand_cap; fa.cand_count = d_counters + 1 + gi;
+            fa.bitmap = (uint32_t *)(ds + fg.o_bits);
+            fa.blk_begin = b0; fa.blk_end = b1;
+            launch_filter_k(pl.k, fa, fgrid, sc_);
+        }
+    };
     auto run_filter_to = [&](int64_t avail_hi, bool last) -> int {
         if (!any_filter) return KGMA_OK;
         int64_t lim = last ? blk_hi : std::min(blk_hi, ((avail_hi - need_after) / FBLOCK) / 32 * 32);
@@ -1241,12 +1418,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
                 if (first_filter) { KGMA_CUDA(ctx, cudaEventRecord(e_fstart, sc_)); first_filter = false; }
                 for (size_t gi = 0; gi < groups.size(); gi++) {
                     const FilterGroup &fg = groups[gi];
-                    FilterArgs fa{};
-                    fa.seq = (const uint4 *)ctx->d_seq2; fa.tab = (const uint16_t *)(ds + fg.o_tab); fa.M = fg.ft->M; fa.thrw = 1u << WFRAC;
-                    fa.cand = (uint32_t *)(ds + fg.o_cand); fa.cand_cap = cand_cap; fa.cand_count = d_counters + 1 + gi;
-                    fa.bitmap = (uint32_t *)(ds + fg.o_bits);
-                    fa.blk_begin = done_blk; fa.blk_end = lim;
-                    launch_filter_k(pl.k, fa, fgrid, sc_);
+                    launch_group_filter(fg, gi, done_blk, lim);
                     KGMA_CUDA(ctx, cudaGetLastError());
                     st.launches++;
                 }
@@ -1262,12 +1434,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
         for (size_t gi = 0; gi < groups.size(); gi++) {
             const FilterGroup &fg = groups[gi];
             if (fg.dense) continue;
-            FilterArgs fa{};
-            fa.seq = (const uint4 *)ctx->d_seq2; fa.tab = (const uint16_t *)(ds + fg.o_tab); fa.M = fg.ft->M; fa.thrw = 1u << WFRAC;
-            fa.cand = (uint32_t *)(ds + fg.o_cand); fa.cand_cap = cand_cap; fa.cand_count = d_counters + 1 + gi;
-            fa.bitmap = (uint32_t *)(ds + fg.o_bits);
-            fa.blk_begin = done_blk; fa.blk_end = lim;
-            launch_filter_k(pl.k, fa, fgrid, sc_);
+            launch_group_filter(fg, gi, done_blk, lim);
             KGMA_CUDA(ctx, cudaGetLastError());
             st.launches++;
         }

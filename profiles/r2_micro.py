@@ -28,7 +28,7 @@ def scan(flags, n=3, env=None):
         for _ in range(n):
             o = K.scan_raw(g, [RV], [ws], [cons], [30.0], 6, L.MODE_SINGLE, 50, flags | L.F_RESIDENT, -69, -1, ctx=ctx)
             st = ctx.stats()
-            for k_ in ("filter_ms", "exact_ms", "align_ms", "wall_ms", "host_replay_ms", "n_align", "n_align_redo", "n_runs"):
+            for k_ in ("filter_ms", "exact_ms", "align_ms", "wall_ms", "host_replay_ms", "n_align", "n_align_redo", "n_runs", "blocks_flagged"):
                 acc[k_] = acc.get(k_, 0) + st[k_] / n
         acc["call_ms"] = (time.perf_counter() - t0) / n * 1e3
         acc["hits"] = int(len(o.hits))
@@ -41,6 +41,7 @@ def scan(flags, n=3, env=None):
 out["filtered_tagged"] = scan(L.F_ALIGN, 10)
 out["filtered_summary_kernel"] = scan(L.F_ALIGN, 10, {"KGMA_ALIGN_KERNEL": "summary"})
 out["filtered_serial_eval"] = scan(L.F_ALIGN, 10, {"KGMA_EVAL_KERNEL": "serial"})
+out["filtered_8mer_prefilter"] = scan(L.F_ALIGN, 10, {"KGMA_PREFILTER": "8mer"})
 for w in ("24", "20", "16", "12"):
     out["dense_parallel_slide_%s_warps" % w] = scan(L.F_DENSE, 2, {"KGMA_EVAL_WARPS": w})
 out["dense_serial_slide"] = scan(L.F_DENSE, 1, {"KGMA_EVAL_KERNEL": "serial"})
