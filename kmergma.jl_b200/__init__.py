@@ -579,6 +579,72 @@ def scan_raw(genome: Genome, refVecs, windowsizes, consensus_seqs, thrs, k: int,
     return out
 
 
+class PreparedScan:
+    """The arguments of one operator call, marshalled once: profiles (integer sums, consensus bytes), parameters and the
+    genome handle.  A serving loop (bench.py's timed region) then pays only the C-ABI call itself per scan -- building the
+    ctypes structures costs as much as a resident scan's host work otherwise.  `scan()` / `scan_shard()` / `replay_packed()`
+    return the raw kgma_result handle wrapped in a LightResult (hit count and stats without copying the hit list)."""
+
+    def __init__(self, genome: Genome, refVecs, windowsizes, consensus_seqs, thrs, k: int, mode: int, buff: int,
+                 gap_open: int, gap_extend: int, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        self.lib = self.ctx._lib
+        self.genome = genome
+        self.n = len(refVecs)
+        self.arr, self._keep = _make_profiles(refVecs, windowsizes, consensus_seqs, thrs, k, self.lib)
+        self._args = (mode, buff, gap_open, gap_extend)
+
+    def _params(self, flags: int, shard=(0, 1)):
+        mode, buff, go, ge = self._args
+        return L.ScanParams(mode, flags, buff, go, ge, shard[0], shard[1], -1, 0)
+
+    def scan(self, flags: int) -> "LightResult":
+        P = self._params(flags)
+        res = C.c_void_p()
+        self.ctx.check(self.lib.kgma_scan(self.ctx._h, self.genome._h, self.arr, self.n, C.byref(P), C.byref(res)))
+        return LightResult(self.lib, res)
+
+    def scan_shard(self, flags: int, shard: Tuple[int, int]) -> "LightResult":
+        P = self._params(flags, shard)
+        res = C.c_void_p()
+        self.ctx.check(self.lib.kgma_scan_shard(self.ctx._h, self.genome._h, self.arr, self.n, C.byref(P), C.byref(res)))
+        return LightResult(self.lib, res)
+
+    def replay_packed(self, flags: int, blocks_ptr: int, n_blocks: int, stride: int) -> "LightResult":
+        P = self._params(flags)
+        res = C.c_void_p()
+        rc = self.lib.kgma_replay_packed(self.ctx._h, self.genome._h, self.arr, self.n, C.byref(P), blocks_ptr, n_blocks, stride, C.byref(res))
+        self.ctx.check(rc)
+        return LightResult(self.lib, res)
+
+
+class LightResult:
+    """a kgma_result handle: counts and packing without materialising numpy copies; `.full()` converts to a ScanOutput"""
+
+    def __init__(self, lib, res):
+        self._lib, self._res = lib, res
+
+    @property
+    def n_hits(self) -> int:
+        return int(self._lib.kgma_result_n_hits(self._res))
+
+    def pack(self, buf_ptr, cap: int) -> int:
+        return int(self._lib.kgma_result_pack(self._res, buf_ptr, cap))
+
+    def full(self) -> "ScanOutput":
+        out = ScanOutput(self._lib, self._res)
+        self._res = None
+        return out
+
+    def free(self):
+        if self._res:
+            self._lib.kgma_result_free(self._res)
+            self._res = None
+
+    def __del__(self):
+        self.free()
+
+
 def scan_shard_raw(genome: Genome, refVecs, windowsizes, consensus_seqs, thrs, k: int, mode: int, buff: int,
                    flags: int, gap_open: int, gap_extend: int, shard: Tuple[int, int], ctx: Optional[Context] = None) -> ScanOutput:
     """kgma_scan_shard: one rank's share of a multi-GPU scan -- its shard's merged runs plus, with F_ALIGN, the extension

@@ -356,6 +356,13 @@ __device__ __forceinline__ int tg_retag(int v, int keep, int tag)
     int r; asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(v), "r"(keep), "r"(tag)); return r;
 }
 
+// byte permute with the sign-replicating selector bit (PTX prmt default mode: selector nibble bit 3 set = fill the result byte with
+// the sign of the selected byte).  __byte_perm cannot be used: it masks the selector with 0x7777.
+__device__ __forceinline__ int tg_prmt(uint32_t lo, uint32_t hi, uint32_t sel)
+{
+    int r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(sel)); return r;
+}
+
 template <int C>
 __global__ void __launch_bounds__(128) kgma_align_tagged(AlignArgs2 A)
 {
@@ -429,7 +436,7 @@ __global__ void __launch_bounds__(128) kgma_align_tagged(AlignArgs2 A)
                 for (int c = 0; c < C; c++) {
                     const int up = Hst[c];
                     const int e = max(Est[c] + K_ee, up + K_eo) & KEEP;
-                    const int sub = (int)__byte_perm(tlo, thi, colsel[c]);
+                    const int sub = tg_prmt(tlo, thi, colsel[c]);
                     const int mm = diag + (int)((unsigned)sub << TG_SC_SH);
                     const int h = tg_retag(__vimax3_s32(mm, F, e), KEEP, T2);
                     diag = up; Hst[c] = h; Est[c] = e;

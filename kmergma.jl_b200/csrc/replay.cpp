@@ -23,8 +23,10 @@ void merge_runs(std::vector<kgma_run> &runs, std::vector<kgma_run_ext> *ext)
     static thread_local std::vector<uint32_t> order;
     bool sorted_by_index = false;
     // order by (profile, record, t_first, marker) - the device appends runs in arbitrary order.  A few thousand runs per
-    // genome: an LSD radix sort of (key, index) pairs over the key bytes that actually differ, then one gather of the
-    // 48-byte runs (a comparison sort of these spends ~0.1 ms in mispredicted branches, 5 % of a resident scan).
+    // genome: the key is squeezed to the bits that can differ ((profile, record) as one group number, t_first relative to
+    // the smallest one) and sorted with an LSD radix sort of (key, index) pairs, 11 bits per pass -- three or four passes
+    // for a 3 Gb genome -- then the 48-byte runs are read once, in order (a comparison sort of the runs themselves spends
+    // ~0.1 ms in mispredicted branches, 5 % of a resident scan).
     {
         auto less = [](const kgma_run &a, const kgma_run &b) {
             if (a.profile != b.profile) return a.profile < b.profile;
@@ -32,32 +34,41 @@ void merge_runs(std::vector<kgma_run> &runs, std::vector<kgma_run_ext> *ext)
             if (a.t_first != b.t_first) return a.t_first < b.t_first;
             return (a.flags & KGMA_RUN_MARKER) < (b.flags & KGMA_RUN_MARKER);
         };
-        bool ok = runs.size() > 1 && runs.size() < ((size_t)1 << 31);
-        for (const kgma_run &r : runs)
-            if (r.profile < 0 || r.profile >= 16 || r.record < 0 || r.record >= (1 << 24) || r.t_first < 0 || r.t_first >= ((int64_t)1 << 35)) { ok = false; break; }
+        const size_t n = runs.size();
+        bool ok = n > 1 && n < ((size_t)1 << 31);
+        int32_t maxrec = 0, maxprof = 0; int64_t tmin = INT64_MAX, tmax = INT64_MIN;
+        for (const kgma_run &r : runs) {
+            if (r.profile < 0 || r.record < 0 || r.t_first < 0) { ok = false; break; }
+            maxrec = std::max(maxrec, r.record); maxprof = std::max(maxprof, r.profile);
+            tmin = std::min(tmin, r.t_first); tmax = std::max(tmax, r.t_first);
+        }
+        auto bits_of = [](uint64_t v) { int b = 0; while (v) { b++; v >>= 1; } return b; };
+        int tbits = 0, gbits = 0;
+        if (ok) {
+            tbits = bits_of((uint64_t)(tmax - tmin));
+            gbits = bits_of((uint64_t)maxprof * ((uint64_t)maxrec + 1) + (uint64_t)maxrec);
+            if (tbits + gbits + 1 > 62 || (uint64_t)maxprof * ((uint64_t)maxrec + 1) > ((uint64_t)1 << 40)) ok = false;
+        }
         if (!ok && ext) { merge_runs_slow(runs, ext); return; }
         if (!ok) std::sort(runs.begin(), runs.end(), less);
         else {
             struct KI { uint64_t key; uint32_t idx; };
             static thread_local std::vector<KI> ka, kb;               // (scratch kept per thread: no allocation per call)
-            const size_t n = runs.size();
             ka.resize(n); kb.resize(n);
-            uint64_t all_or = 0, all_and = ~0ull;
+            const uint64_t nrec1 = (uint64_t)maxrec + 1;
             for (size_t i = 0; i < n; i++) {
                 const kgma_run &r = runs[i];
-                // 4 bits profile | 24 bits record | 35 bits t_first | 1 bit marker
-                const uint64_t key = ((uint64_t)r.profile << 60) | ((uint64_t)r.record << 36) | ((uint64_t)r.t_first << 1) | ((r.flags & KGMA_RUN_MARKER) ? 1u : 0u);
-                ka[i] = { key, (uint32_t)i };
-                all_or |= key; all_and &= key;
+                const uint64_t grp = (uint64_t)r.profile * nrec1 + (uint64_t)r.record;
+                ka[i] = { (grp << (tbits + 1)) | ((uint64_t)(r.t_first - tmin) << 1) | ((r.flags & KGMA_RUN_MARKER) ? 1u : 0u), (uint32_t)i };
             }
-            const uint64_t varying = all_or ^ all_and;                    // bits that are not the same in every key
+            const int total = gbits + tbits + 1;
             KI *src = ka.data(), *dst = kb.data();
-            for (int byte = 0; byte < 8; byte++) {
-                if (!((varying >> (8 * byte)) & 0xFFu)) continue;
-                uint32_t cnt[257] = { 0 };
-                for (size_t i = 0; i < n; i++) cnt[((src[i].key >> (8 * byte)) & 0xFFu) + 1]++;
-                for (int d = 0; d < 256; d++) cnt[d + 1] += cnt[d];
-                for (size_t i = 0; i < n; i++) dst[cnt[(src[i].key >> (8 * byte)) & 0xFFu]++] = src[i];
+            for (int sh = 0; sh < total; sh += 11) {
+                uint32_t cnt[2049] = { 0 };
+                for (size_t i = 0; i < n; i++) cnt[((src[i].key >> sh) & 0x7FFu) + 1]++;
+                if (cnt[((src[0].key >> sh) & 0x7FFu) + 1] == n) continue;      // this digit is the same everywhere
+                for (int d = 0; d < 2048; d++) cnt[d + 1] += cnt[d];
+                for (size_t i = 0; i < n; i++) dst[cnt[(src[i].key >> sh) & 0x7FFu]++] = src[i];
                 std::swap(src, dst);
             }
             order.resize(n);
@@ -97,8 +108,8 @@ void merge_runs(std::vector<kgma_run> &runs, std::vector<kgma_run_ext> *ext)
         out.push_back(r);
         if (ext) out_ext.push_back((*ext)[src]);
     }
-    runs.assign(out.begin(), out.end());
-    if (ext) ext->assign(out_ext.begin(), out_ext.end());
+    runs.swap(out);                                      // (the scratch vector keeps the old buffer for the next call)
+    if (ext) ext->swap(out_ext);
 }
 
 // merge with extension results for run lists the radix path does not take (out-of-range keys, fewer than two runs):

@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(512, 1) kgma_eval_serial(EvalArgs a)
                     uint32_t fl = (ties > 1 ? KGMA_HIT_ARGMIN_TIE : 0u) | ((near & stretch) ? KGMA_HIT_NEAR_THR : 0u);
                     long long tf = w0 + s0 + b0, ta = w0 + s0 + bestI, dmin = bestD;
                     if (c_in && b0 == 0) {                                     // continues the run carried over from the previous batch
-                        fl |= c_fl;
+                        fl |= (c_fl & ~KGMA_HIT_ARGMIN_TIE);               // (a tie inside a piece that is not the minimum is no tie of the run)
                         if (c_dmin < dmin) { dmin = c_dmin; ta = c_ta; fl = (fl & ~KGMA_HIT_ARGMIN_TIE) | (c_fl & KGMA_HIT_ARGMIN_TIE); }
                         else if (c_dmin == dmin) { ta = c_ta; fl |= KGMA_HIT_ARGMIN_TIE; }
                         tf = c_tf; c_in = false;
@@ -580,7 +580,7 @@ __device__ __noinline__ RunCarry classify_group(ClsArgs a, int r, int q, long lo
         uint32_t fl = (ties > 1 ? KGMA_HIT_ARGMIN_TIE : 0u) | ((near & stretch) ? KGMA_HIT_NEAR_THR : 0u);
         long long tf = tb + b0, ta = tb + bestI, dmin = bestD;
         if (c.in && b0 == 0) {                                         // continues the run carried over from the previous group
-            fl |= c.fl;
+            fl |= (c.fl & ~KGMA_HIT_ARGMIN_TIE);                       // (a tie inside a piece that is not the minimum is no tie of the run)
             if (c.dmin < dmin) { dmin = c.dmin; ta = c.ta; fl = (fl & ~KGMA_HIT_ARGMIN_TIE) | (c.fl & KGMA_HIT_ARGMIN_TIE); }
             else if (c.dmin == dmin) { ta = c.ta; fl |= KGMA_HIT_ARGMIN_TIE; }
             tf = c.tf; c.in = false;
@@ -607,10 +607,15 @@ __global__ void __launch_bounds__(MAXT, 1) kgma_eval(EvalArgs a, ProfDev P, int 
     const unsigned FULL = 0xFFFFFFFFu;
     constexpr int nb = 1 << (2 * K);
     constexpr uint32_t kmask = (uint32_t)nb - 1;
+    // k <= 6: an entry is 32 bits, the count in the low half and a one-byte lane stamp above it (duplicate detection, below);
+    // k = 7: 16-bit counts only (64 KB per warp otherwise) and MATCH.ANY for every batch
+    constexpr bool STAMP = K <= 6;
+    constexpr int ESH = STAMP ? 2 : 1;                                     // log2(bytes per entry)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int32_t *sS = reinterpret_cast<int32_t *>(smem_raw);
-    uint16_t *tab = reinterpret_cast<uint16_t *>(smem_raw + (size_t)nb * 4 + (size_t)wid * ((size_t)nb * 2));   // [4^k] counts of this warp
-    for (int i = lane; i < nb / 2; i += 32) reinterpret_cast<uint32_t *>(tab)[i] = 0;
+    unsigned char *tabb = smem_raw + (size_t)nb * 4 + (size_t)wid * ((size_t)nb << ESH);   // [4^k] entries of this warp
+    auto cnt_ptr = [&](uint32_t km) { return reinterpret_cast<uint16_t *>(tabb + ((size_t)km << ESH)); };
+    for (int i = lane; i < (nb << ESH) / 4; i += 32) reinterpret_cast<uint32_t *>(tabb)[i] = 0;
 
     long long nitems = a.n_items;
     if (a.cand) { uint32_t c = *a.cand_count; nitems = c < a.cand_cap ? c : a.cand_cap; }
@@ -692,13 +697,14 @@ __global__ void __launch_bounds__(MAXT, 1) kgma_eval(EvalArgs a, ProfDev P, int 
             // ---- first window of the span: build the table, Q = sum_p c[kmer_p], A = sum_p S[kmer_p]
             for (int p = lane; p < nk; p += 32) {
                 const uint32_t km = kmer_at(a.seq, gpos + p, kmask);
-                atomicAdd(reinterpret_cast<uint32_t *>(tab) + (km >> 1), 1u << ((km & 1) * 16));
+                if (STAMP) atomicAdd(reinterpret_cast<uint32_t *>(tabb) + km, 1u);
+                else atomicAdd(reinterpret_cast<uint32_t *>(tabb) + (km >> 1), 1u << ((km & 1) * 16));
             }
             __syncwarp();
             uint32_t Qb = 0, Ab = 0;                                          // < 2^32: nk <= 65535, nk * max S checked on the host
             for (int p = lane; p < nk; p += 32) {
                 const uint32_t km = kmer_at(a.seq, gpos + p, kmask);
-                Qb += tab[km]; Ab += (uint32_t)sS[km];
+                Qb += *cnt_ptr(km); Ab += (uint32_t)sS[km];
             }
 #pragma unroll
             for (int d = 16; d; d >>= 1) { Qb += __shfl_xor_sync(FULL, Qb, d); Ab += __shfl_xor_sync(FULL, Ab, d); }
@@ -732,9 +738,24 @@ __global__ void __launch_bounds__(MAXT, 1) kgma_eval(EvalArgs a, ProfDev P, int 
                 wlo = whi; whi = __ldg(wp + widx); widx++;
                 const int left = FB ? 16 : ni - 1 - s;
                 const bool valid = FB || j < left;
-                unsigned m = __match_any_sync(FULL, valid ? x : (0x80000000u | (unsigned)lane));
+                // Which lanes hold the same k-mer?  Nearly always none do (32 events among 4^k values), and MATCH.ANY costs about
+                // two cycles per distinct value.  So every lane stamps its entry with its lane number and reads the entry back
+                // (the count comes with it): a lane that finds another lane's stamp shares its k-mer with that lane, and only a
+                // batch in which some lane does pays for the MATCH.
+                unsigned m = 1u << lane;
+                uint32_t c0;
+                if (STAMP) {
+                    if (valid) tabb[((size_t)x << 2) + 2] = (unsigned char)lane;
+                    __syncwarp();
+                    const uint32_t ent = reinterpret_cast<const uint32_t *>(tabb)[x];
+                    c0 = ent & 0xFFFFu;
+                    if (__any_sync(FULL, valid && ((ent >> 16) & 0xFFu) != (uint32_t)lane))
+                        m = __match_any_sync(FULL, valid ? x : (0x80000000u | (unsigned)lane));
+                } else {
+                    m = __match_any_sync(FULL, valid ? x : (0x80000000u | (unsigned)lane));
+                    c0 = *cnt_ptr(x);
+                }
                 if (!FB) m &= ((1u << left) - 1u) * 0x10001u;
-                const uint32_t c0 = tab[x];
                 const int cnt = (int)c0 + __popc(m & ltE) - __popc(m & ltL);
                 const int Sx = sS[x];
                 const int o = __shfl_xor_sync(FULL, ent ? cnt : Sx, 16);       // lower lanes receive c_r, upper lanes S[l]
@@ -753,7 +774,7 @@ __global__ void __launch_bounds__(MAXT, 1) kgma_eval(EvalArgs a, ProfDev P, int 
                 }
                 Qb += (uint32_t)__shfl_sync(FULL, v, 15); Ab += (uint32_t)__shfl_sync(FULL, v, 31);
                 // one store per distinct k-mer (by the lowest lane holding it): count at the start of the batch + enters - leaves
-                if (valid && !(m & lt_lane)) tab[x] = (uint16_t)((int)c0 + __popc(m & 0xFFFF0000u) - __popc(m & 0x0000FFFFu));
+                if (valid && !(m & lt_lane)) *cnt_ptr(x) = (uint16_t)((int)c0 + __popc(m & 0xFFFF0000u) - __popc(m & 0x0000FFFFu));
                 __syncwarp();
             };
             if (a.dists != nullptr || !P.u_ok) {
@@ -764,7 +785,7 @@ __global__ void __launch_bounds__(MAXT, 1) kgma_eval(EvalArgs a, ProfDev P, int 
                 if (s + 1 < ni) batch(std::false_type{}, std::false_type{});
             }
             // ---- return the table to zero: only the k-mers of the last window are still counted
-            for (int p = lane; p < nk; p += 32) tab[kmer_at(a.seq, gpos + n - 1 + p, kmask)] = 0;
+            for (int p = lane; p < nk; p += 32) *cnt_ptr(kmer_at(a.seq, gpos + n - 1 + p, kmask)) = 0;
             __syncwarp();
         }
     }
@@ -1081,7 +1102,7 @@ static int eval_shape(const kgma_ctx *ctx, int k, bool serial, int *warps_out, s
 {
     const size_t nb = (size_t)1 << (2 * k);
     // one 4^k x u16 count table per warp, next to the profile's S table (the serial kernel adds its 64-step staging arrays)
-    const size_t per_warp = nb * 2 + (serial ? 64 * 4 + 64 * 4 + 64 * 8 : 0);
+    const size_t per_warp = serial ? nb * 2 + 64 * 4 + 64 * 4 + 64 * 8 : nb * (k <= 6 ? 4 : 2);
     if (ctx->smem_optin < nb * 4 + per_warp) return KGMA_E_UNSUPPORTED;
     int wmax = serial ? 16 : 24;
     if (const char *e = getenv("KGMA_EVAL_WARPS")) wmax = std::max(1, std::min(24, atoi(e)));
