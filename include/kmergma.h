@@ -252,6 +252,16 @@ const char *kgma_result_cigar_ops(const kgma_result *r);
 const int32_t *kgma_result_cigar_counts(const kgma_result *r);
 void kgma_result_free(kgma_result *r);
 
+/* ---- result formatting / writing: append_hit! header text (Alignment.jl:57-81; OmnGenomeMiner.jl:141-149 when cluster != 0)
+ * and write_results (API.jl:234-241: records appended to a FASTA file, `width` residues per line) -------------------------- */
+/* "<id> | dist = <round2> | MatchPos = a:b | GenomePos = g | Len = n" with Julia's string(round(d, digits = 2)); returns the
+ * length (the text is written, NUL-terminated, when cap is larger). */
+int64_t kgma_hit_header(const kgma_genome *g, const kgma_hit *h, int cluster, int with_genome_pos, char *buf, int64_t cap);
+int  kgma_result_write_fasta(const kgma_result *r, const kgma_genome *g, const char *path, int cluster, int with_genome_pos,
+                             int width, int64_t *n_written);
+/* fasta_id_to_cumulative_len_dict (ExactMatch.jl:146-158): summed length of the records in front of `record` */
+int64_t kgma_genome_cumulative_len(const kgma_genome *g, int record);
+
 /* ---- batched semi-global extension (Alignment.jl:33-52) ------------------------------------------- */
 /* For each i: align consensus (A,C,G,T,N bytes) against record[first_i:last_i]; returns the remapped
  * 1-based range exactly as align_unitrange does, plus the score. */

@@ -23,7 +23,8 @@ __all__ = [
     "KmerGMAError", "Context", "Genome", "FastaRecord", "KFV", "AlignResult",
     "gen_ref_ws_cons", "cluster_ref_API", "eliminate_null_params", "get_cluster_index",
     "estimate_optimal_threshold", "ac_gma_testing", "Omn_KmerGMA", "record_KmerGMA",
-    "findGenes", "findGenes_cluster_mode", "exactMatch", "write_results", "align_unitrange",
+    "findGenes", "findGenes_cluster_mode", "exactMatch", "write_results", "write_hits", "hit_header",
+    "fasta_id_to_cumulative_len_dict", "align_unitrange",
     "julia_round2", "julia_float_str", "kmer_count", "kmer_dist", "as_UInt", "as_kmer",
     "randstrobe_score", "get_strobe_2_mer", "ungapped_strobe_2_mer_count",
 ]
@@ -945,6 +946,34 @@ def write_results(KmerGMA_result_vec: Sequence[FastaRecord], file_path: str, wid
             s = hit.sequence
             for i in range(0, len(s), width):
                 fh.write(s[i:i + width] + "\n")
+
+
+def write_hits(out: "ScanOutput", genome: Genome, file_path: str, cluster: bool = False, with_genome_pos: bool = True, width: int = 95) -> int:
+    """write_results (src/API.jl:234-241) for the hits of a scan, done by the library (kgma_result_write_fasta): headers as
+    append_hit! builds them, sequences cut from the packed genome, `width` residues per line, appended to file_path."""
+    n = C.c_int64()
+    rc = out._lib.kgma_result_write_fasta(out._res, genome._h, os.fsencode(file_path), int(cluster), int(with_genome_pos), width, C.byref(n))
+    if rc != 0:
+        raise KmerGMAError(rc, f"cannot write {file_path}")
+    return n.value
+
+
+def hit_header(genome: Genome, hit, cluster: bool = False, with_genome_pos: bool = True) -> str:
+    """the header text of one kgma_hit as the library formats it (kgma_hit_header)"""
+    lib = L.load()
+    h = L.Hit.from_buffer_copy(np.asarray(hit).tobytes())
+    buf = C.create_string_buffer(4096)
+    n = lib.kgma_hit_header(genome._h, C.byref(h), int(cluster), int(with_genome_pos), buf, 4096)
+    if n < 0:
+        raise KmerGMAError(int(n), "kgma_hit_header failed")
+    return buf.value.decode()
+
+
+def fasta_id_to_cumulative_len_dict(fasta_file_path) -> Dict[str, int]:
+    """fasta_id_to_cumulative_len_dict (src/ExactMatch.jl:146-158): description of every record -> summed length of the records
+    in front of it."""
+    g = _as_genome(fasta_file_path)
+    return {g.description(r): int(g._lib.kgma_genome_cumulative_len(g._h, r)) for r in range(len(g))}
 
 
 # ------------------------------------------------------------------------------------------------

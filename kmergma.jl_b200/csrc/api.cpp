@@ -1,6 +1,9 @@
 // Context life-cycle and result accessors of the C ABI (include/kmergma.h).
 #include "kgma_internal.h"
 #include <sys/mman.h>
+#include <cmath>
+#include <cstdlib>
+#include <algorithm>
 
 namespace kgma { const char *create_err(); }
 using namespace kgma;
@@ -105,6 +108,89 @@ const double *kgma_result_dists(const kgma_result *r, int p) { return (r && p >=
 const char *kgma_result_cigar_ops(const kgma_result *r) { return r && !r->cigar_ops.empty() ? r->cigar_ops.data() : nullptr; }
 const int32_t *kgma_result_cigar_counts(const kgma_result *r) { return r && !r->cigar_cnt.empty() ? r->cigar_cnt.data() : nullptr; }
 void kgma_result_free(kgma_result *r) { result_release(r); }
+
+// ---- result formatting and writing: append_hit!'s header (Alignment.jl:57-81; OmnGenomeMiner.jl:141-149 in cluster mode) and
+// write_results (API.jl:234-241) natively, for callers without Julia's string(round(d, digits = 2)).
+// string(round(d, digits = 2)): round-half-even of d*100 then /100 (Base.round), printed as the shortest decimal that reads
+// back to the same Float64, always with a fractional part ("8.1", "24.87", "9.0").
+static std::string julia_round2_string(double d)
+{
+    const double y = std::nearbyint(d * 100.0) / 100.0;      // (default rounding mode: ties to even, like Base.round)
+    if (std::isnan(y)) return "NaN";
+    if (std::isinf(y)) return y > 0 ? "Inf" : "-Inf";
+    if (y == 0) return std::signbit(y) ? "-0.0" : "0.0";
+    char buf[64];
+    for (int p = 0; p <= 16; p++) {                           // shortest digit string that reads back to y
+        snprintf(buf, sizeof buf, "%.*e", p, y);
+        if (strtod(buf, nullptr) == y) break;
+    }
+    std::string t(buf), digits;
+    const size_t e = t.find('e');
+    const int ex = atoi(t.c_str() + e + 1);
+    const bool neg = t[0] == '-';
+    for (size_t i = neg ? 1 : 0; i < e; i++) if (t[i] != '.') digits += t[i];
+    std::string s = neg ? "-" : "";
+    if (ex >= -5 && ex < 21) {                                // Base.show(::Float64): fixed notation in [1e-5, 1e21)
+        if (ex < 0) { s += "0." + std::string((size_t)(-ex - 1), '0') + digits; }
+        else if ((size_t)ex + 1 >= digits.size()) { s += digits + std::string((size_t)ex + 1 - digits.size(), '0') + ".0"; }
+        else { s += digits.substr(0, (size_t)ex + 1) + "." + digits.substr((size_t)ex + 1); }
+    } else {                                                  // 1.0e21, 1.5e-7
+        s += digits.substr(0, 1) + "." + (digits.size() > 1 ? digits.substr(1) : std::string("0")) + "e" + std::to_string(ex);
+    }
+    return s;
+}
+
+static std::string hit_header(const kgma_genome *g, const kgma_hit &h, bool cluster, bool with_genome_pos)
+{
+    const std::string id = (h.record >= 0 && h.record < (int)g->recs.size()) ? g->recs[(size_t)h.record].ident : std::string("?");
+    std::string s = id + (cluster ? " | Dist = " : " | dist = ") + julia_round2_string(h.dist);
+    if (cluster) s += " | KFV = " + std::to_string(h.profile);
+    s += " | MatchPos = " + std::to_string(h.first) + ":" + std::to_string(h.last);
+    if (cluster || with_genome_pos) s += " | GenomePos = " + std::to_string(h.genome_pos);     // record_KmerGMA! prints none (MultiThread/GenomeMiner.jl:88-91)
+    s += " | Len = " + std::to_string(h.last - h.first + 1);
+    return s;
+}
+
+int64_t kgma_hit_header(const kgma_genome *g, const kgma_hit *h, int cluster, int with_genome_pos, char *buf, int64_t cap)
+{
+    if (!g || !h) return KGMA_E_ARG;
+    const std::string s = hit_header(g, *h, cluster != 0, with_genome_pos != 0);
+    if (buf && cap > (int64_t)s.size()) memcpy(buf, s.c_str(), s.size() + 1);
+    return (int64_t)s.size();
+}
+
+int kgma_result_write_fasta(const kgma_result *r, const kgma_genome *g, const char *path, int cluster, int with_genome_pos,
+                            int width, int64_t *n_written)
+{
+    if (!r || !g || !path || width < 1) return KGMA_E_ARG;
+    FILE *fp = fopen(path, "ab");                        // API.jl:235 open(file_path, "a")
+    if (!fp) return KGMA_E_IO;
+    std::string seq;
+    int64_t n = 0;
+    for (const kgma_hit &h : r->hits) {
+        const std::string hd = hit_header(g, h, cluster != 0, with_genome_pos != 0);
+        fputc('>', fp); fwrite(hd.data(), 1, hd.size(), fp); fputc('\n', fp);
+        const int64_t len = h.last >= h.first ? h.last - h.first + 1 : 0;
+        seq.assign((size_t)len + 1, '\0');
+        if (len > 0 && kgma_genome_get_seq(g, h.record, h.first, h.last, &seq[0]) != KGMA_OK) { fclose(fp); return KGMA_E_ARG; }
+        for (int64_t o = 0; o < len; o += width) {
+            fwrite(seq.data() + o, 1, (size_t)std::min<int64_t>(width, len - o), fp); fputc('\n', fp);
+        }
+        n++;
+    }
+    if (fclose(fp) != 0) return KGMA_E_IO;
+    if (n_written) *n_written = n;
+    return KGMA_OK;
+}
+
+// fasta_id_to_cumulative_len_dict (ExactMatch.jl:146-158): the summed length of the records in front of `record`
+int64_t kgma_genome_cumulative_len(const kgma_genome *g, int record)
+{
+    if (!g || record < 0 || record >= (int)g->recs.size()) return KGMA_E_ARG;
+    int64_t c = 0;
+    for (int r = 0; r < record; r++) c += g->recs[(size_t)r].len;
+    return c;
+}
 void kgma_free(void *p) { free(p); }
 
 }  // extern "C"

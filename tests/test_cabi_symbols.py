@@ -304,3 +304,61 @@ def test_fasta_ingest_vectorised_and_portable_paths(tmp_path, seed):
             "print(hashlib.sha256(('|'.join(g.seq(r) for r in range(len(g)))).encode() + g.masked_runs().tobytes()).hexdigest())") % (ROOT, p)
     out = subprocess.check_output([sys.executable, "-c", code], env=dict(os.environ, KGMA_NO_AVX2="1"), text=True).strip()
     assert out == digest
+
+
+def test_fixed_operator_parameters_are_checked():
+    """ac_gma_testing! / Omn_KmerGMA! take ScaleFactor, mask and Nt_bits (GenomeMiner.jl:12-14); the device path is fixed to
+    1/k, 4^k - 1 and NUCLEOTIDE_BITS, so anything else is refused before any work is queued (no silent divergence)"""
+    import kmergma_jl_b200 as K
+    K._check_fixed_params(6, 1 / 6, 4095, {"A": 0, "C": 1, "G": 2, "T": 3, "N": 3})
+    K._check_fixed_params(7, None, None, None)
+    for kw in (dict(k=7, ScaleFactor=1 / 6), dict(k=5, mask=4095), dict(k=6, Nt_bits={"A": 0, "C": 1, "G": 2, "T": 2, "N": 3})):
+        with pytest.raises(K.KmerGMAError) as e:
+            K._check_fixed_params(kw["k"], kw.get("ScaleFactor"), kw.get("mask"), kw.get("Nt_bits"))
+        assert e.value.code == K.L.E_UNSUPPORTED
+    with pytest.raises(K.KmerGMAError):       # refused before a context is even asked for
+        K.ac_gma_testing(genome_path=MINI_GENOME, refVec=np.zeros(4 ** 7), consensus_refseq="A" * 300, k=7, ScaleFactor=1 / 6, resultVec=[])
+
+
+def test_cumulative_len_dict_golden():
+    """test-KmerGMA.jl:336-343"""
+    import kmergma_jl_b200 as K
+    assert K.fasta_id_to_cumulative_len_dict(GENOME) == {
+        "JQ684648.1 Lama glama clone V03 IgH locus genomic sequence": 0,
+        "JQ684647.1 Lama glama clone F07 IgH locus genomic sequence": 121478,
+        "AM773548.1 Lama pacos germline IgHV region, Vh3-S1, Vh2-S1 and vhh3-S1 genes": 444023,
+        "AM773729.1 Lama pacos germline IgH locus: proximal IgHV region genes, complete IgHD region genes, complete IgHJ region genes "
+        "and complete IgHC region genes": 221227}
+
+
+def test_native_hit_headers_and_writer(tmp_path):
+    """kgma_hit_header / kgma_result_write_fasta against the host mirror's append_hit! formatting and write_results
+    (Alignment.jl:57-81, OmnGenomeMiner.jl:141-149, API.jl:234-241), incl. Julia's string(round(d, digits = 2)) on values that
+    sit on rounding half-way points, print as integers, or need one decimal; the result comes from a host-only replay"""
+    import kmergma_jl_b200 as K
+    from test_multirank_gloo import RUN_DT
+    g = K.Genome.from_fasta(GENOME)
+    # golden of append_hit!: test-KmerGMA.jl:147-151
+    h = np.zeros(1, dtype=K.HIT_DT)
+    for d, want in ((69.1, "69.1"), (8.100000000000001, "8.1"), (24.874999, "24.87"), (9.0, "9.0"), (0.005, "0.0"), (0.015, "0.02"),
+                    (2.675, "2.68"), (0.125, "0.12"), (0.375, "0.38"), (100.0, "100.0"), (12345.678, "12345.68"), (1e-9, "0.0")):
+        h["record"], h["first"], h["last"], h["genome_pos"], h["dist"], h["profile"] = 1, 2, 5, 3, d, 4
+        assert K.julia_float_str(K.julia_round2(d)) == want
+        assert K.hit_header(g, h[0]) == "JQ684647.1 | dist = %s | MatchPos = 2:5 | GenomePos = 3 | Len = 4" % want
+        assert K.hit_header(g, h[0], with_genome_pos=False) == "JQ684647.1 | dist = %s | MatchPos = 2:5 | Len = 4" % want
+        assert K.hit_header(g, h[0], cluster=True) == "JQ684647.1 | Dist = %s | KFV = 4 | MatchPos = 2:5 | GenomePos = 3 | Len = 4" % want
+    # a replayed result written natively == the mirror's records written by write_results
+    RV, ws, cons = K.gen_ref_ws_cons(TF, 6)
+    runs = np.array([(0, 0, 20300, 20340, 20330, 780000, 0, 0), (3, 0, 6790, 6830, 6801, 686000, 0, 0),
+                     (3, 0, 23850, 23900, 23861, 2100000, 0, 0)], dtype=RUN_DT)
+    fd = np.full(len(g), 10 ** 9, dtype=np.int64)
+    out = K.replay_raw(g, [RV], [ws], [cons], [30.0], 6, K.L.MODE_SINGLE, 50, 0, -69, -1, runs.view(np.uint8), fd, host_only=True)
+    assert len(out.hits) == 3
+    native, mirror = tmp_path / "native.fasta", tmp_path / "mirror.fasta"
+    assert K.write_hits(out, g, str(native), width=95) == 3
+    recs = []
+    K._emit(g, out, False, recs, None, None)
+    K.write_results(recs, str(mirror), 95)
+    assert native.read_text() == mirror.read_text() and native.read_text().count(">") == 3
+    assert max(len(l) for l in native.read_text().splitlines() if not l.startswith(">")) == 95
+    assert K.write_hits(out, g, str(native), width=60) == 3 and native.read_text().count(">") == 6      # appends, like open(path, "a")
