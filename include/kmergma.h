@@ -135,8 +135,9 @@ typedef struct {
     double host_setup_ms;         /* plan, tables, scratch, small uploads (until the genome stream starts) */
     double host_cand_ms;          /* candidate list D2H + sort + segment building */
     double host_replay_ms;        /* run merge + replay of the reference state machine (without the extension kernel) */
-    int64_t n_align_redo;         /* extensions the tagged kernel handed to the path-summary kernel (no leading / trailing deletion run) */
+    int64_t n_align_redo;         /* extensions the fast tagged kernel handed to its two-chain form (no leading / trailing deletion run) */
     int64_t filter_passes;        /* prefilter passes over the shard (one per group of profiles sharing a weight table); filter_ms spans all */
+    int64_t n_align_summary;      /* extensions that went on to the path-summary kernel (paths starting at column 0 of the slice) */
 } kgma_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */

@@ -338,9 +338,17 @@ __global__ void __launch_bounds__(128, 3) kgma_align_summary(AlignArgs2 A)
 // column attaining max_j H[m][j] (the traceback extends the zero-cost trailing gap on ties), so with
 //   x = start column of that cell's path (leading free deletions), I = its insert columns, j* = that column:
 //   cigar_to_UnitRange (Alignment.jl:13-30)  lower = x,  num_sum = j* + I      (first run xD, last run (n-j*)D).
-// Alignments without a leading or trailing deletion run (x = 0, or the maximum is (also) attained at column n: their
-// first / last CIGAR run is a match run whose length the word does not carry) are flagged (nops = -1) and redone by
-// kgma_align_summary; they are the rare ones that touch a record edge or run with buff = 0.
+// That leaves two kinds of alignment open.  (1) The maximum of the last row is (also) attained at column n: the path may end
+// at (m, n) -- the consensus overhangs the subject slice, or ends exactly on its last base -- and its last CIGAR run is then
+// not a deletion run.  The same warp sweeps the alignment a second time with the OTHER payload
+//     [17:9] trailing insert ops of the path   [8:0] trailing diagonal ops   (both 0: the last op is a deletion, or none yet)
+// under identical score / tag arithmetic (so every max picks the same predecessor), and finishes it:
+//   the path ends at (m, n) iff the maximum is first attained at column n, or is attained there by a diagonal step (the
+//   traceback tests match before the free deletion); its last run is the insert run the word counts, or the =/X run
+//   min(trailing diagonal steps, length of the equal-kind stretch of the diagonal through (m, n)), read off the sequences;
+//   cigar_to_UnitRange: lower = x of THAT path, num_sum = n + I - last run.
+// (2) Paths that start at column 0 of the slice (x = 0: the first run is no deletion run; hits at a record edge, buff = 0)
+// are flagged (nops = -1) and redone by kgma_align_summary.
 #define TG_SC_SH   20
 #define TG_TAG1    (1 << 18)
 #define TG_TAG2    (2 << 18)
@@ -348,6 +356,7 @@ __global__ void __launch_bounds__(128, 3) kgma_align_summary(AlignArgs2 A)
 #define TG_IC1     (1 << 9)
 #define TG_MAX_M   400
 #define TG_MAX_N   511
+#define TG_PAY     0x3FFFF               /* the 18 payload bits below the tag */
 
 // (v & keep) | tag in ONE LOP3: with the two masks as literals the compiler emits an AND and an OR (an instruction has
 // room for one immediate), so they are handed over in registers it cannot see through
@@ -363,114 +372,201 @@ __device__ __forceinline__ int tg_prmt(uint32_t lo, uint32_t hi, uint32_t sel)
     int r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(sel)); return r;
 }
 
+// a + b on the FMA pipe (IMAD with a multiplier the compiler cannot see through).  The cell update is all integer ALU work
+// (LOP3, VIADDMNMX, VIMNMX3, PRMT), and that pipe issues one warp instruction every two cycles per scheduler; the plain adds
+// that feed the add-max instructions are the part that can move to the other pipe.
+__device__ __forceinline__ int tg_add(int a, int b, int one)
+{
+    int r; asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b)); return r;
+}
+
+struct TgConst {
+    int go, ge, S0, K_ee, K_eo, K_fe, K_mfo, K_efo, K_fo, KEEP, T1, T2, KHI, KDG, P_I1, ONE, SH20;
+};
+
+template <bool CHAIN_B>
+__device__ __forceinline__ TgConst tg_consts(int go, int ge)
+{
+    TgConst k;
+    const int gog = go + ge;
+    k.go = go; k.ge = ge;
+    // sentinel for "no gap open yet": below every reachable score, and one more extension must not wrap the 12-bit field
+    k.S0 = -2047 + ge;
+    // first payload: an insert column more per E step.  Second payload: an E step is one more trailing insert op (an opening
+    // resets the payload to "1 I" before the constant is added)
+    k.K_ee = (int)((unsigned)(-ge) << TG_SC_SH) + TG_TAG1 + TG_IC1;                     // E stored with tag 0: extend -> 1
+    k.K_eo = (int)((unsigned)(-gog) << TG_SC_SH) - TG_TAG2 + (CHAIN_B ? 0 : TG_IC1);    // H stored with tag 2: open   -> 0
+    // The deletion gap F[i][j+1] = max(F[i][j] - ge, H[i][j] - gog) is evaluated as max(F - ge, mm - gog, e - gog): opening
+    // from an H that itself came out of F is never better than extending that F (and carries the same counters), so H drops
+    // out of the recurrence and the chain along a row is one add-max and one retag per cell.  Order on equal scores:
+    // extend 2 > open from a match 1 > open from an insertion 0, the traceback's.
+    k.K_fe  = (int)((unsigned)(-ge) << TG_SC_SH) + TG_TAG1;                             // F stored with tag 1 -> 2
+    k.K_mfo = (int)((unsigned)(-gog) << TG_SC_SH) - TG_TAG1;                            // mm carries tag 2 -> 1
+    k.K_efo = (int)((unsigned)(-gog) << TG_SC_SH);                                      // e carries tag 0
+    k.K_fo  = (int)((unsigned)(-gog) << TG_SC_SH) - TG_TAG2;                            // first column of a lane: open from the H handed over
+    asm volatile("mov.b32 %0, %4; mov.b32 %1, %5; mov.b32 %2, %6; mov.b32 %3, %7;" : "=r"(k.KEEP), "=r"(k.T1), "=r"(k.T2), "=r"(k.ONE)
+                 : "n"(~TG_TAGMASK), "n"(TG_TAG1), "n"(TG_TAG2), "n"(1));
+    asm volatile("mov.b32 %0, %4; mov.b32 %1, %5; mov.b32 %2, %6; mov.b32 %3, %7;" : "=r"(k.KHI), "=r"(k.KDG), "=r"(k.P_I1), "=r"(k.SH20)
+                 : "n"(~TG_PAY), "n"(~(0x1FF << 9)), "n"(TG_IC1), "n"(1 << TG_SC_SH));
+    return k;
+}
+
+__device__ __forceinline__ uint32_t tg_subject_code(const AlignArgs2 &A, const AlignJob2 &J, int j)      // code of subject base j (1-based)
+{
+    if (J.b_off >= 0) return A.b[J.b_off + j - 1];
+    const long long gp = J.gpos + j - 1;
+    uint32_t code = (__ldg(A.seq + (gp >> 4)) >> (2 * (int)(gp & 15))) & 3u;
+    if (A.n_nruns) {
+        int lo = -1, hi = A.n_nruns;                              // last masked run with start <= gp
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (A.nruns[2 * mid] <= gp) lo = mid; else hi = mid; }
+        if (lo >= 0 && gp < A.nruns[2 * lo + 1]) code = 4u;
+    }
+    return code;
+}
+
+// One sweep of the DP by one warp; leaves row m of H in Hst (lane l: columns l*C+1 .. l*C+C).  CHAIN_B selects the payload.
+template <int C, bool CHAIN_B>
+__device__ __forceinline__ void tg_sweep(const AlignArgs2 &A, const AlignJob2 &J, int lane, int (&Hst)[C])
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    const TgConst k = tg_consts<CHAIN_B>(A.go, A.ge);
+    const int go = k.go, ge = k.ge, S0 = k.S0;
+    const int K_ee = k.K_ee, K_eo = k.K_eo, K_fe = k.K_fe, K_mfo = k.K_mfo, K_efo = k.K_efo, K_fo = k.K_fo;
+    const int KEEP = k.KEEP, T1 = k.T1, T2 = k.T2, KHI = k.KHI, KDG = k.KDG, P_I1 = k.P_I1, ONE = k.ONE, SH20 = k.SH20;
+    const int m = J.m, n = J.n;
+    const uint8_t *a = A.a + J.a_off;
+    const int j0 = lane * C;                                                  // this lane owns columns j0+1 .. j0+C
+    int Est[C]; uint32_t colsel[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const int j = j0 + c + 1;
+        const uint32_t code = j <= n ? tg_subject_code(A, J, j) : 0u;
+        // byte permute selector: byte 0 = table[code], bytes 1-3 = its sign  ->  a sign-extended score in one PRMT
+        colsel[c] = code | ((code | 8u) << 4) | ((code | 8u) << 8) | ((code | 8u) << 12);
+        Hst[c] = TG_TAG2 | (CHAIN_B ? 0 : j);                                 // row 0: free leading deletions, path = jD
+        Est[c] = (int)((unsigned)S0 << TG_SC_SH);
+    }
+    // H[0][j0]: diagonal of my first column at row 1
+    int prevIn = TG_TAG2 | (CHAIN_B ? 0 : j0);
+    int Hlast = 0, Flast = 0;
+    for (int s = 1; s <= m + 31; s++) {
+        const int i = s - lane;
+        const int inH = __shfl_up_sync(FULL, Hlast, 1), inF = __shfl_up_sync(FULL, Flast, 1);
+        if (i >= 1 && i <= m) {
+            int left, F, diag = prevIn;
+            if (lane == 0) {                                                  // column 0: H[i][0] = -(go + i ge), path = iI; no deletion gap yet
+                left = (int)((unsigned)(-(go + i * ge)) << TG_SC_SH) | TG_TAG2 | (i << 9);     // (i insert columns so far / i trailing insert ops)
+                F = (int)((unsigned)S0 << TG_SC_SH) | TG_TAG1;
+            } else { left = inH; F = inF; }
+            prevIn = left;
+            F = tg_retag(max(F + K_fe, (CHAIN_B ? (left & KHI) : left) + K_fo), KEEP, T1);                 // F[i][j0+1]
+            const int ai = a[i - 1];
+            // EDNAFULL row of this consensus symbol as signed bytes: vs A,C,G,T in tlo, vs N in thi
+            const uint32_t tlo = ai < 4 ? ((0xFCFCFCFCu & ~(0xFFu << (8 * ai))) | (5u << (8 * ai))) : 0xFEFEFEFEu;
+            const uint32_t thi = ai < 4 ? 0xFEu : 0xFFu;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const int up = Hst[c];
+                const int sub = tg_prmt(tlo, thi, colsel[c]);
+                int e, mm;
+                if (!CHAIN_B) {
+                    e = max(Est[c] + K_ee, tg_add(up, K_eo, ONE)) & KEEP;
+                    mm = tg_add(sub, diag, SH20);                                                          // diag + (sub << 20), one IMAD
+                } else {
+                    e = max(Est[c] + K_ee, tg_add(tg_retag(up, KHI, P_I1), K_eo, ONE)) & KEEP;             // opening: the path's last run is now 1 I
+                    mm = tg_add(sub, (diag & KDG) + 1, SH20);                                              // one more trailing diagonal op, no trailing insert
+                }
+                const int h = tg_retag(__vimax3_s32(mm, F, e), KEEP, T2);
+                diag = up; Hst[c] = h; Est[c] = e;
+                if (c == C - 1) { Hlast = h; Flast = F; }
+                else if (!CHAIN_B) F = tg_retag(max(F + K_fe, max(mm + K_mfo, tg_add(e, K_efo, ONE))), KEEP, T1);   // F[i][j+1]
+                else F = tg_retag(max(F + K_fe, max(mm + K_mfo, tg_add(e, K_efo, ONE)) & KHI), KEEP, T1);           // (an opened deletion: payload 0)
+            }
+        }
+    }
+}
+
+// One warp per queue entry.  An entry is an alignment (first-payload sweep; when the last-row maximum is also attained at
+// column n and no twin is queued, the same warp adds the second-payload sweep) or the twin of an alignment the host expects to
+// end at (m, n) (second-payload sweep only: its window sits at the edge of a run, where the consensus overhangs the slice) --
+// the two sweeps of such an alignment then run side by side on two warps instead of one after the other.  The host combines
+// the two result records (align_collect).
 template <int C>
 __global__ void __launch_bounds__(128) kgma_align_tagged(AlignArgs2 A)
 {
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
-    const int go = A.go, ge = A.ge, gog = go + ge;
-    // sentinel for "no gap open yet": below every reachable score, and one more extension must not wrap the 12-bit field
-    const int S0 = -2047 + ge;
-    const int K_ee = (int)((unsigned)(-ge) << TG_SC_SH) + TG_TAG1 + TG_IC1;            // E stored with tag 0: extend -> 1, one more insert column
-    const int K_eo = (int)((unsigned)(-gog) << TG_SC_SH) - TG_TAG2 + TG_IC1;           // H stored with tag 2: open   -> 0
-    // The deletion gap F[i][j+1] = max(F[i][j] - ge, H[i][j] - gog) is evaluated as max(F - ge, mm - gog, e - gog): opening
-    // from an H that itself came out of F is never better than extending that F (and carries the same counters), so H drops
-    // out of the recurrence and the chain along a row is one add-max and one retag per cell.  Order on equal scores:
-    // extend 2 > open from a match 1 > open from an insertion 0, the traceback's.
-    const int K_fe  = (int)((unsigned)(-ge) << TG_SC_SH) + TG_TAG1;                    // F stored with tag 1 -> 2
-    const int K_mfo = (int)((unsigned)(-gog) << TG_SC_SH) - TG_TAG1;                   // mm carries tag 2 -> 1
-    const int K_efo = (int)((unsigned)(-gog) << TG_SC_SH);                             // e carries tag 0
-    const int K_fo  = (int)((unsigned)(-gog) << TG_SC_SH) - TG_TAG2;                   // first column of a lane: open from the H handed over
-    int KEEP, T1, T2;
-    asm volatile("mov.b32 %0, %3; mov.b32 %1, %4; mov.b32 %2, %5;" : "=r"(KEEP), "=r"(T1), "=r"(T2) : "n"(~TG_TAGMASK), "n"(TG_TAG1), "n"(TG_TAG2));
-
     for (;;) {
         int ji = 0;
         if (lane == 0) ji = atomicAdd(A.next_job, 1);
         ji = __shfl_sync(FULL, ji, 0);
         if (ji >= A.njobs) break;
         const AlignJob2 J = A.jobs[ji];
-        const int m = J.m, n = J.n;
-        const uint8_t *a = A.a + J.a_off;
-        const int j0 = lane * C;                                                  // this lane owns columns j0+1 .. j0+C
-        int Hst[C], Est[C]; uint32_t colsel[C];
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-            const int j = j0 + c + 1;
-            uint32_t code = 0;
-            if (j <= n) {
-                if (J.b_off >= 0) code = A.b[J.b_off + j - 1];
-                else {
-                    const long long gp = J.gpos + j - 1;
-                    code = (__ldg(A.seq + (gp >> 4)) >> (2 * (int)(gp & 15))) & 3u;
-                    if (A.n_nruns) {
-                        int lo = -1, hi = A.n_nruns;                              // last masked run with start <= gp
-                        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (A.nruns[2 * mid] <= gp) lo = mid; else hi = mid; }
-                        if (lo >= 0 && gp < A.nruns[2 * lo + 1]) code = 4u;
-                    }
-                }
-            }
-            // byte permute selector: byte 0 = table[code], bytes 1-3 = its sign  ->  a sign-extended score in one PRMT
-            colsel[c] = code | ((code | 8u) << 4) | ((code | 8u) << 8) | ((code | 8u) << 12);
-            Hst[c] = TG_TAG2 | j;                                                 // row 0: free leading deletions, path = jD
-            Est[c] = (int)((unsigned)S0 << TG_SC_SH);
-        }
-        int prevIn = TG_TAG2 | j0;                                                // H[0][j0]: diagonal of my first column at row 1
-        int Hlast = 0, Flast = 0;
-        for (int s = 1; s <= m + 31; s++) {
-            const int i = s - lane;
-            const int inH = __shfl_up_sync(FULL, Hlast, 1), inF = __shfl_up_sync(FULL, Flast, 1);
-            if (i >= 1 && i <= m) {
-                int left, F, diag = prevIn;
-                if (lane == 0) {                                                  // column 0: H[i][0] = -(go + i ge), path = iI; no deletion gap yet
-                    left = (int)((unsigned)(-(go + i * ge)) << TG_SC_SH) | TG_TAG2 | (i << 9);
-                    F = (int)((unsigned)S0 << TG_SC_SH) | TG_TAG1;
-                } else { left = inH; F = inF; }
-                prevIn = left;
-                F = tg_retag(max(F + K_fe, left + K_fo), KEEP, T1);               // F[i][j0+1]
-                const int ai = a[i - 1];
-                // EDNAFULL row of this consensus symbol as signed bytes: vs A,C,G,T in tlo, vs N in thi
-                const uint32_t tlo = ai < 4 ? ((0xFCFCFCFCu & ~(0xFFu << (8 * ai))) | (5u << (8 * ai))) : 0xFEFEFEFEu;
-                const uint32_t thi = ai < 4 ? 0xFEu : 0xFFu;
+        const int m = J.m, n = J.n, j0 = lane * C;
+        const int ln = (n - 1) / C;                                           // lane that owns column n
+        bool second = (J.mode & 2) != 0;
+        if (!second) {
+            int w, jstar, bv, wlast;
+            {
+                int Hst[C];
+                tg_sweep<C, false>(A, J, lane, Hst);
+                // ---- last row: first column attaining the maximum (ties -> lowest column), and the word at column n
+                int best = INT_MIN, bestw = 0, bestj = 0, wn = 0;
 #pragma unroll
                 for (int c = 0; c < C; c++) {
-                    const int up = Hst[c];
-                    const int e = max(Est[c] + K_ee, up + K_eo) & KEEP;
-                    const int sub = tg_prmt(tlo, thi, colsel[c]);
-                    const int mm = diag + (int)((unsigned)sub << TG_SC_SH);
-                    const int h = tg_retag(__vimax3_s32(mm, F, e), KEEP, T2);
-                    diag = up; Hst[c] = h; Est[c] = e;
-                    if (c == C - 1) { Hlast = h; Flast = F; }
-                    else F = tg_retag(max(F + K_fe, max(mm + K_mfo, e + K_efo)), KEEP, T1);   // F[i][j+1]
+                    const int j = j0 + c + 1;
+                    const int v = Hst[c] >> TG_SC_SH;
+                    if (j <= n && v > best) { best = v; bestw = Hst[c]; bestj = j; }
+                    if (j == n) wn = Hst[c];
                 }
+                // warp argmax over (score, lowest column): columns grow with the lane index, so on equal scores the lower lane wins
+                bv = best; int bl = lane;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) {
+                    const int ov = __shfl_xor_sync(FULL, bv, d), ol = __shfl_xor_sync(FULL, bl, d);
+                    if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
+                }
+                w = __shfl_sync(FULL, bestw, bl); jstar = __shfl_sync(FULL, bestj, bl);
+                wlast = __shfl_sync(FULL, wn, ln);
             }
+            const bool tie = (wlast >> TG_SC_SH) == bv;                       // the path may end at (m, n): the second payload decides
+            const bool degenerate = bv <= -(A.go + m * A.ge);
+            if (lane == 0) {
+                AlignOut o;
+                const int x = w & 0x1FF, ic = (w >> 9) & 0x1FF;
+                o.score = bv; o.lower = x; o.num_sum = jstar + ic;
+                o.nops = (degenerate || (tie && A.tail_mode == 2) || (!tie && x == 0)) ? -1 : tie ? 3 : 2;
+                o.cig_n = (wlast & 0x3FFFF) | ((jstar == n) << 18);            // x and I of the path to (m, n); is column n the first maximum?
+                A.out[J.slot] = o;
+            }
+            second = tie && !degenerate && A.tail_mode != 2 && !(J.mode & 1);
         }
-        // ---- last row: first column attaining the maximum (ties -> lowest column), and the value at column n
-        int best = INT_MIN, bestw = 0, bestj = 0, vn = INT_MIN;
+        if (second) {
+            int w2;
+            {
+                int Hs2[C];
+                tg_sweep<C, true>(A, J, lane, Hs2);
+                int wn2 = 0;
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-            const int j = j0 + c + 1;
-            const int v = Hst[c] >> TG_SC_SH;
-            if (j <= n && v > best) { best = v; bestw = Hst[c]; bestj = j; }
-            if (j == n) vn = v;
-        }
-        // warp argmax over (score, lowest column): columns grow with the lane index, so on equal scores the lower lane wins
-        int bv = best, bl = lane;
-#pragma unroll
-        for (int d = 16; d; d >>= 1) {
-            const int ov = __shfl_xor_sync(FULL, bv, d), ol = __shfl_xor_sync(FULL, bl, d);
-            if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
-        }
-        const int w = __shfl_sync(FULL, bestw, bl), jstar = __shfl_sync(FULL, bestj, bl);
-        const int vlast = __shfl_sync(FULL, vn, (n - 1) / C);
-        if (lane == 0) {
-            AlignOut o;
-            const int x = w & 0x1FF, ic = (w >> 9) & 0x1FF;
-            const bool redo = x == 0 || vlast == bv || bv <= -(go + m * ge);
-            o.score = bv; o.cig_n = 0;
-            o.nops = redo ? -1 : 2;
-            o.lower = x; o.num_sum = jstar + ic;
-            A.out[ji] = o;
+                for (int c = 0; c < C; c++) if (j0 + c + 1 == n) wn2 = Hs2[c];
+                w2 = __shfl_sync(FULL, wn2, ln);
+            }
+            // length of the equal-kind stretch ending at (m, n) on its diagonal: '=' where the symbols are the same, 'X' elsewhere
+            const int ndiag = w2 & 0x1FF;
+            const uint8_t *a = A.a + J.a_off;
+            const int lim = min(ndiag, min(m, n));
+            const bool k0 = tg_subject_code(A, J, n) == (uint32_t)a[m - 1];
+            int r = lim;
+            for (int t0 = 0; t0 < lim; t0 += 32) {                            // 32 diagonal steps per round
+                const int t = t0 + lane;
+                const unsigned diff = __ballot_sync(FULL, t < lim && (tg_subject_code(A, J, n - t) == (uint32_t)a[m - t - 1]) != k0);
+                if (diff) { r = t0 + __ffs((int)diff) - 1; break; }
+            }
+            if (lane == 0) {
+                AlignOut o;
+                o.score = 0; o.lower = ndiag; o.num_sum = (w2 >> 9) & 0x1FF; o.nops = r; o.cig_n = 1;
+                A.out[A.nslots + J.slot] = o;                                 // trailing diagonal ops, trailing insert ops, equal-kind stretch
+            }
         }
         __syncwarp();
     }
@@ -551,6 +647,7 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
         if (rq.first < 1 || rq.last > R.len || rq.last < rq.first) return set_err(ctx, KGMA_E_ARG, "alignment range %lld:%lld invalid", (long long)rq.first, (long long)rq.last);
         AlignJob2 &J = jobs[i];
         J.gpos = R.off + rq.first - 1; J.n = (int)(rq.last - rq.first + 1); J.a_off = a_off[rq.profile]; J.m = a_len[rq.profile]; J.b_off = -1;
+        J.mode = 0; J.slot = (int32_t)i;
         maxn = std::max(maxn, J.n);
         if (J.m + J.n >= 4095) return set_err(ctx, KGMA_E_UNSUPPORTED, "alignment of %d x %d too long for the extension kernel (12-bit gap lengths)", J.m, J.n);
         if (!(on_dev && J.gpos >= ctx->d_have_lo && J.gpos + J.n + 16 <= ctx->d_have_hi)) {      // slice lives on another shard's device: ship codes
@@ -564,7 +661,7 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
         }
     }
     if (g->ambiguous) return set_err(ctx, KGMA_E_SYMBOL, "subject holds a symbol outside A,C,G,T,N");
-    const int nj = (int)jobs.size();
+    const int nj = (int)jobs.size();                           // requests = result slots
     const int ncol = (maxn + 1 + 31) & ~31;
     const int warps_per_block = 4;
     constexpr int ROWS = 10;                                   // kgma_align_summary: DP rows per lane, one sweep covers 320 consensus rows
@@ -580,20 +677,38 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     const char *kern_env = getenv("KGMA_ALIGN_KERNEL");
     const bool tagged = !(kern_env && !strcmp(kern_env, "summary")) && !tie_open && go >= 0 && ge >= 0 && maxm >= 1 && maxm <= TG_MAX_M && maxn <= TG_MAX_N &&
                         5 * maxm < 2040 && 2LL * go + (long long)(maxm + 3) * ge + 8 < 2040;
+    // KGMA_ALIGN_TAIL = all | off: a second-payload twin for every alignment / no second sweep at all (tests compare the routes)
+    int tail_mode = 0;
+    { const char *tv = getenv("KGMA_ALIGN_TAIL"); tail_mode = tv && !strcmp(tv, "all") ? 1 : tv && !strcmp(tv, "off") ? 2 : 0; }
+    // The queue: twins of the marked alignments first (the longest entries, and the ones whose result the host waits for),
+    // then the marked alignments, then the rest.
+    if (tagged && tail_mode != 2) {
+        std::vector<AlignJob2> q; q.reserve(jobs.size() * 2);
+        for (int pass = 0; pass < 3; pass++)
+            for (size_t i = 0; i < jobs.size(); i++) {
+                const bool marked = tail_mode == 1 || (reqs[i].hint & 1);
+                if (pass == 0 && marked) { AlignJob2 t2 = jobs[i]; t2.mode = 2; q.push_back(t2); }
+                if (pass == 1 && marked) { AlignJob2 t1 = jobs[i]; t1.mode = 1; q.push_back(t1); }
+                if (pass == 2 && !marked) q.push_back(jobs[i]);
+            }
+        jobs.swap(q);
+    }
+    const int nq = (int)jobs.size();                           // queue entries
+    const int nout = tagged ? 2 * nj : nj;                     // result records: [nj] first sweep, [nj] second sweep
     size_t o = 0;
     auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
-    const size_t o_a = carve(acodes.size()), o_b = carve(bcodes.size()), o_j = carve((size_t)nj * sizeof(AlignJob2));
+    const size_t o_a = carve(acodes.size()), o_b = carve(bcodes.size()), o_j = carve((size_t)nq * sizeof(AlignJob2));
     const size_t o_n = carve(nruns.size() * 8 + 8);
     const size_t up = o;
-    const size_t o_c = carve(256), o_o = carve((size_t)nj * sizeof(AlignOut));
+    const size_t o_c = carve(256), o_o = carve((size_t)nout * sizeof(AlignOut));
     const size_t o_j2 = carve(tagged ? (size_t)nj * sizeof(AlignJob2) : 0), o_o2 = carve(tagged ? (size_t)nj * sizeof(AlignOut) : 0);   // second pass
     void *dv = nullptr, *hv = nullptr;
-    int rc = slot_scratch(ctx, slot, o, up + (size_t)nj * sizeof(AlignOut) + (tagged ? (size_t)nj * (sizeof(AlignJob2) + sizeof(AlignOut)) : 0), &dv, &hv);
+    int rc = slot_scratch(ctx, slot, o, up + (size_t)nout * sizeof(AlignOut) + (tagged ? (size_t)nj * (sizeof(AlignJob2) + sizeof(AlignOut)) : 0), &dv, &hv);
     if (rc) return rc;
     unsigned char *d = (unsigned char *)dv, *h = (unsigned char *)hv;
     memcpy(h + o_a, acodes.data(), acodes.size());
     if (!bcodes.empty()) memcpy(h + o_b, bcodes.data(), bcodes.size());
-    memcpy(h + o_j, jobs.data(), (size_t)nj * sizeof(AlignJob2));
+    memcpy(h + o_j, jobs.data(), (size_t)nq * sizeof(AlignJob2));
     if (!nruns.empty()) memcpy(h + o_n, nruns.data(), nruns.size() * 8);
     // Two ways to move the batch.  Next to a streaming scan (the pipelined parts run on s_align) the copy engine is busy with
     // 32 MB genome chunks and a small copy queued behind one waits ~0.6 ms, so the jobs are fetched by a kernel and the
@@ -613,13 +728,20 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     ctx->stats.h2d_bytes += up;
     AlignArgs2 A{};
     A.a = d + o_a; A.seq = ctx->d_seq2; A.nruns = (const long long *)(d + o_n); A.n_nruns = (int)(nruns.size() / 2);
-    A.b = d + o_b; A.jobs = (const AlignJob2 *)(d + o_j); A.njobs = nj; A.next_job = (int *)(d + o_c);
+    A.b = d + o_b; A.jobs = (const AlignJob2 *)(d + o_j); A.njobs = nq; A.nslots = nj; A.next_job = (int *)(d + o_c);
     // results are written straight into the page-locked block (16 bytes per alignment, posted writes): no copy back
     A.out = in_place ? (AlignOut *)((unsigned char *)h_dev + up) : (AlignOut *)(d + o_o); A.go = go; A.ge = ge; A.tie_open = tie_open ? 1 : 0; A.ncol_cap = ncol;
     A.need_boundary = need_boundary ? 1 : 0;
+    A.tail_mode = tail_mode;
     KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KGMA_CUDA(ctx, cudaFuncSetAttribute(kgma_align_summary<ROWS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = std::min((nj + warps_per_block - 1) / warps_per_block, ctx->num_sms * 8);
+    // tagged kernel: 3 CTAs (12 warps) per SM fetch entries from the queue -- with every entry resident at once (3.4 per scheduler
+    // for the 2 022 entries of cfg2) the schedulers that drew four finish last; measured 0.257 ms against 0.280
+    int ctas_per_sm = tagged ? 3 : 8;
+    if (const char *e = getenv("KGMA_ALIGN_CTAS")) ctas_per_sm = std::max(1, std::min(8, atoi(e)));
+    const int grid = std::min((nq + warps_per_block - 1) / warps_per_block, ctx->num_sms * ctas_per_sm);
+    if (tagged && in_place) memset(h + up, 0, (size_t)nout * sizeof(AlignOut));
+    else if (tagged) KGMA_CUDA(ctx, cudaMemsetAsync(d + o_o, 0, (size_t)nout * sizeof(AlignOut), st));   // (cig_n = 0: no second-sweep record)
     KGMA_CUDA(ctx, cudaEventRecord(ctx->a_ev0[slot], st));
     if (tagged) {
         if (maxn <= 13 * 32) kgma_align_tagged<13><<<grid, warps_per_block * 32, 0, st>>>(A);
@@ -631,13 +753,13 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     KGMA_CUDA(ctx, cudaEventRecord(ctx->a_ev1[slot], st));
     ctx->stats.launches++;
     AlignOut *ho = (AlignOut *)(h + up);
-    if (!in_place) KGMA_CUDA(ctx, cudaMemcpyAsync(ho, d + o_o, (size_t)nj * sizeof(AlignOut), cudaMemcpyDeviceToHost, st));
+    if (!in_place) KGMA_CUDA(ctx, cudaMemcpyAsync(ho, d + o_o, (size_t)nout * sizeof(AlignOut), cudaMemcpyDeviceToHost, st));
     KGMA_CUDA(ctx, cudaEventRecord(ctx->a_done[slot], st));
-    ctx->stats.d2h_bytes += (size_t)nj * sizeof(AlignOut);
+    ctx->stats.d2h_bytes += (size_t)nout * sizeof(AlignOut);
     t->active = true; t->slot = slot; t->nj = nj; t->ho = ho;
-    t->tagged = tagged; t->st = st; t->args = A; t->smem = smem;
+    t->tagged = tagged; t->st = st; t->args = A; t->smem = smem; t->maxn = maxn; t->nq = nq;
     t->d_jobs2 = d + o_j2; t->d_out2 = d + o_o2; t->d_cnt = d + o_c;
-    t->h_jobs = h + o_j; t->h_jobs2 = h + up + (size_t)nj * sizeof(AlignOut); t->h_out2 = (unsigned char *)t->h_jobs2 + (size_t)nj * sizeof(AlignJob2);
+    t->h_jobs = h + o_j; t->h_jobs2 = h + up + (size_t)nout * sizeof(AlignOut); t->h_out2 = (unsigned char *)t->h_jobs2 + (size_t)nj * sizeof(AlignJob2);
     if (trace) fprintf(stderr, "[kgma align] batch of %d queued in %.3f ms of host time (%s kernel)\n", nj, now_ms() - te0, tagged ? "tagged" : "summary");
     return KGMA_OK;
 }
@@ -652,13 +774,31 @@ int align_collect(kgma_ctx *ctx, AlignTicket *t, std::vector<AlignRes> &out)
     AlignOut *ho = (AlignOut *)t->ho;
     t->active = false;
     if (t->tagged) {
-        // second pass: alignments without a leading / trailing deletion run go through the path-summary kernel
+        const AlignJob2 *hj = (const AlignJob2 *)t->h_jobs;           // in queue order; .slot = index of the request
+        AlignJob2 *hj2 = (AlignJob2 *)t->h_jobs2;
         std::vector<int> redo;
-        for (int q = 0; q < t->nj; q++) if (ho[q].nops < 0) redo.push_back(q);
+        for (int j = 0; j < t->nq; j++) {
+            const AlignJob2 &J = hj[j];
+            if (J.mode & 2) continue;                                 // a twin: its record is read below
+            AlignOut &A1 = ho[J.slot];
+            if (A1.nops == 3) {
+                // the last-row maximum is also attained at column n: combine with the second-payload record (kgma_align_tagged)
+                const AlignOut &B = ho[t->nj + J.slot];
+                if (B.cig_n != 1) return set_err(ctx, KGMA_E_STATE, "extension: second-sweep record of alignment %d missing", J.slot);
+                const int x_n = A1.cig_n & 0x1FF, i_n = (A1.cig_n >> 9) & 0x1FF; const bool first_max_at_n = (A1.cig_n >> 18) & 1;
+                const bool diag_last = B.lower > 0;                   // the path to (m, n) ends with a diagonal step: match before free deletion
+                if (first_max_at_n || diag_last) {
+                    const int lastrun = diag_last ? std::min(B.lower, B.nops) : B.num_sum;
+                    A1.lower = x_n; A1.num_sum = J.n + i_n - lastrun;
+                }
+                A1.nops = A1.lower == 0 ? -1 : 2;                     // a path from column 0: the path-summary kernel
+                ctx->stats.n_align_redo++;
+            }
+            if (A1.nops < 0) { hj2[redo.size()] = J; redo.push_back(J.slot); }
+        }
+        // second pass: the alignments the tagged kernel cannot finish (paths that start at column 0 of the slice: hits at a
+        // record edge, or buff = 0) go through the path-summary kernel
         if (!redo.empty()) {
-            const AlignJob2 *hj = (const AlignJob2 *)t->h_jobs;
-            AlignJob2 *hj2 = (AlignJob2 *)t->h_jobs2;
-            for (size_t i = 0; i < redo.size(); i++) hj2[i] = hj[redo[i]];
             const int nf = (int)redo.size();
             cudaStream_t st = (cudaStream_t)t->st;
             AlignArgs2 A = t->args;
@@ -675,7 +815,7 @@ int align_collect(kgma_ctx *ctx, AlignTicket *t, std::vector<AlignRes> &out)
             cudaEventElapsedTime(&ms, ctx->a_ev0[t->slot], ctx->a_ev1[t->slot]);
             ctx->stats.align_ms += ms;
             ctx->stats.launches++;
-            ctx->stats.n_align_redo += nf;
+            ctx->stats.n_align_summary += nf;
             const AlignOut *ho2 = (const AlignOut *)t->h_out2;
             for (int i = 0; i < nf; i++) ho[redo[(size_t)i]] = ho2[i];
             if (getenv("KGMA_TRACE")) fprintf(stderr, "[kgma align] %d of %d alignments redone by the path-summary kernel\n", nf, t->nj);
@@ -749,7 +889,7 @@ int align_batch_device(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq
             }
             jobs.push_back(J);
         }
-        const int nj = (int)jobs.size();
+        const int nj = (int)jobs.size();                           // requests = result slots
         const int ncol = (maxn + 1 + 31) & ~31;
         const int warps_per_block = 4;
         size_t smem = (size_t)warps_per_block * 2 * ncol * sizeof(int);

@@ -139,7 +139,9 @@ int  build_proftab(kgma_ctx *ctx, const kgma_profile &p, ProfTab &t);
 inline uint32_t rev_kmer(uint32_t c, int k) { uint32_t r = 0; for (int j = 0; j < k; j++) { r = (r << 2) | (c & 3); c >>= 2; } return r; }
 
 // ---- replay.cpp
-struct AlignReq { int32_t record, profile; int64_t first, last; };       // 1-based range to extend
+struct AlignReq { int32_t record, profile; int64_t first, last; int32_t hint = 0; };   // 1-based range to extend; hint & 1: the window's distance is
+                                                                                     // close to the threshold (edge of a run: the consensus tends to overhang the slice)
+inline int32_t align_hint(int64_t D, int64_t T) { return (__int128)D * 10 > (__int128)T * 9 ? 1 : 0; }
 struct AlignRes { int64_t lo, hi, score; uint32_t cig_off, cig_len; };   // cigar_to_UnitRange result (relative, 1-based)
 struct Pending { size_t hit; size_t req; int64_t first; size_t run; };     // hit waiting for its extension result (run: index of the run that emitted it)
 void merge_runs(std::vector<kgma_run> &runs, std::vector<kgma_run_ext> *ext = nullptr);
@@ -153,7 +155,9 @@ int  replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, con
 
 // ---- align.cu
 struct AlignOut { long long score; int32_t lower, num_sum, nops, cig_n; };                 // nops < 0: redo with the path-summary kernel
-struct AlignJob2 { long long gpos; int32_t n, a_off, m, b_off; };   // b_off >= 0: subject codes were uploaded (not on the device)
+struct AlignJob2 { long long gpos; int32_t n, a_off, m, b_off; int32_t mode, slot; };   // b_off >= 0: subject codes were uploaded (not on the device);
+                                                                        // tagged kernel: mode & 2 = second-payload sweep only (the twin of a marked job), mode & 1 = such a twin is queued;
+                                                                        // slot: index of the request (results are written there)
 struct AlignArgs2 {
     const uint8_t *a;            // consensus codes 0..3, 4 = N
     const uint32_t *seq;         // packed 2-bit genome on the device
@@ -163,11 +167,13 @@ struct AlignArgs2 {
     int *next_job;
     AlignOut *out;
     int go, ge, tie_open, ncol_cap, need_boundary;
+    int tail_mode;               // tagged kernel: 0 = second sweep where needed, 1 = twins for every alignment, 2 = never (hand back instead)
+    int nslots;                  // number of requests: second-sweep results go to out[nslots + slot]
 };
 struct AlignTicket {
     bool active = false; int slot = 0, nj = 0; void *ho = nullptr;
     // what align_collect needs to redo the alignments the tagged kernel handed back (align.cu)
-    bool tagged = false; void *st = nullptr; size_t smem = 0;
+    bool tagged = false; void *st = nullptr; size_t smem = 0; int maxn = 0, nq = 0;   // nq: queue entries (requests + twins)
     void *d_jobs2 = nullptr, *d_out2 = nullptr, *d_cnt = nullptr, *h_jobs = nullptr, *h_jobs2 = nullptr, *h_out2 = nullptr;
     AlignArgs2 args{};
 };

@@ -210,7 +210,7 @@ int replay_single_range(kgma_ctx *ctx, kgma_genome *g, const ProfTab &t, const k
                         kgma_hit h{};
                         h.record = r; h.profile = 0; h.cmi = CMI; h.first = a; h.last = bb; h.genome_pos = genome_pos;
                         h.D = cur; h.dist = (double)cur / t.denom; h.flags = hflags | round_half_flag(h.dist);
-                        if (do_align) { pend.push_back({ hits.size(), reqs.size(), a, j }); reqs.push_back({ r, 0, a, bb }); }
+                        if (do_align) { pend.push_back({ hits.size(), reqs.size(), a, j }); reqs.push_back({ r, 0, a, bb, align_hint(cur, t.T) }); }
                         hits.push_back(h);
                         cur = INT64_MAX;                  // :102 currminim = kmerDist (some value >= thr)
                     }
@@ -389,7 +389,7 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
         for (size_t i : missing) {
             const kgma_run &ru = runs[i];
             const int64_t L = g->recs[ru.record].len, CMI = ru.t_argmin, wsq = tabs[ru.profile].ws;
-            reqs.push_back({ ru.record, ru.profile, std::max<int64_t>(CMI - buff, 1), std::min<int64_t>(CMI + wsq - 1 + buff, L) });
+            reqs.push_back({ ru.record, ru.profile, std::max<int64_t>(CMI - buff, 1), std::min<int64_t>(CMI + wsq - 1 + buff, L), align_hint(ru.D_min, tabs[ru.profile].T) });
         }
         int rc = align_batch_device(ctx, g, reqs, profiles, C, false, P.gap_open, P.gap_extend,
                                     (P.flags & KGMA_F_TIE_OPEN) != 0, want_cig, ares,

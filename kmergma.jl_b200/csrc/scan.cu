@@ -1639,7 +1639,7 @@ int kgma_scan_shard(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles,
             if (ru.t_last >= pl.steps[(size_t)ru.record]) continue;          // reaches the record's last step: never emitted
             const int64_t L = g->recs[(size_t)ru.record].len, wsq = pl.tabs[(size_t)ru.profile].ws;
             const int64_t CMI = pl.cluster ? ru.t_argmin : (int64_t)pl.k + ru.t_argmin;   // OmnGenomeMiner.jl:117 / GenomeMiner.jl:85,92
-            reqs.push_back({ ru.record, ru.profile, std::max<int64_t>(CMI - P.buff, 1), std::min<int64_t>(CMI + wsq - 1 + P.buff, L) });
+            reqs.push_back({ ru.record, ru.profile, std::max<int64_t>(CMI - P.buff, 1), std::min<int64_t>(CMI + wsq - 1 + P.buff, L), align_hint(ru.D_min, pl.tabs[(size_t)ru.profile].T) });
             of_run.push_back(i);
         }
         std::vector<AlignRes> ares;

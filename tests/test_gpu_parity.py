@@ -1249,7 +1249,8 @@ def test_tagged_extension_kernel_equals_path_summary_kernel(K, O, prof, monkeypa
     """the default extension kernel (kgma_align_tagged: one word per DP state, DPX three-way max) against the
     path-summary kernel it falls back to (KGMA_ALIGN_KERNEL=summary forces that one for the whole batch): same ranges and
     scores for several gap models, subject lengths from 1 to 511 (with N), consensus lengths 8..400, subjects that start or
-    end inside the homologue (no leading / trailing deletion run: the redo path); then against the oracle"""
+    end inside the homologue (no trailing deletion run: finished by the kernel's two-chain form, also forced for every alignment
+    and switched off; no leading deletion run: handed to the path-summary kernel); then against the oracle"""
     RV, ws, cons = prof
     rng = np.random.default_rng(21)
     whole = O.Fasta(GENOME).seq(3)
@@ -1275,32 +1276,39 @@ def test_tagged_extension_kernel_equals_path_summary_kernel(K, O, prof, monkeypa
     first = np.ones(n, np.int64)
     last = np.asarray([len(s_) for _, s_ in recs], np.int64)
 
-    def batch(c, go, ge, kernel):
+    def batch(c, go, ge, kernel, tail=None):
         if kernel:
             monkeypatch.setenv("KGMA_ALIGN_KERNEL", kernel)
+        if tail:
+            monkeypatch.setenv("KGMA_ALIGN_TAIL", tail)
         of, ol, sc = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.int64)
         ctx.check(ctx._lib.kgma_align_batch(ctx._h, g._h, c, len(c), go, ge, 0, n, rec.ctypes.data, first.ctypes.data,
                                             last.ctypes.data, of.ctypes.data, ol.ctypes.data, sc.ctypes.data))
-        if kernel:
-            monkeypatch.delenv("KGMA_ALIGN_KERNEL")
-        return of.tolist(), ol.tolist(), sc.tolist(), ctx.stats()["n_align_redo"]
+        monkeypatch.delenv("KGMA_ALIGN_KERNEL", raising=False)
+        monkeypatch.delenv("KGMA_ALIGN_TAIL", raising=False)
+        st = ctx.stats()
+        return of.tolist(), ol.tolist(), sc.tolist(), st["n_align_redo"], st["n_align_summary"]
 
-    redone = 0
+    two_chain = by_summary = 0
     for clen in (8, 33, 160, 161, 200, 289, 320, 321, 400):
         c = (cons[:289] * 2)[:clen].encode()
         for go, ge in ((-69, -1), (-200, -1), (-5, -2), (0, -1), (-30, -3)):
             a = batch(c, go, ge, None)
             b = batch(c, go, ge, "summary")
             assert a[:3] == b[:3], (clen, go, ge)
-            assert b[3] == 0
-            redone += a[3]
-        of, ol, sc, _ = batch(c, -69, -1, None)
+            assert b[3] == 0 and b[4] == 0
+            # the two-chain form for every alignment, and for none (everything it would finish goes to the path-summary kernel)
+            a_all, a_off = batch(c, go, ge, None, "all"), batch(c, go, ge, None, "off")
+            assert a_all[:3] == b[:3] and a_off[:3] == b[:3], (clen, go, ge)
+            assert a_off[3] == 0 and a_off[4] >= a[4] and a_all[4] == a[4]
+            two_chain += a[3]; by_summary += a[4]
+        of, ol, sc, _, _ = batch(c, -69, -1, None)
         for i in range(0, n, 5):
             s_ = recs[i][1]
             lo, hi = O.align_unitrange(s_, (1, len(s_)), c.decode(), clen, len(s_), -69, -1)
             assert (of[i], ol[i]) == (lo, hi), (clen, i)
             assert sc[i] == O.pairalign_semiglobal(c.decode(), s_, -69, -1)[1]
-    assert redone > 0                                     # the hand-over to the path-summary kernel was exercised
+    assert two_chain > 0 and by_summary > 0               # both hand-overs were exercised
 
 
 def test_parallel_slide_kernel_equals_serial_kernel(K, O, prof, synth, tmp_path, monkeypatch):
