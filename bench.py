@@ -415,7 +415,7 @@ def bind_to_gpu_numa_node(device_index):
 
 KEYS = ("launches", "h2d_bytes", "d2h_bytes", "filter_ms", "exact_ms", "align_ms", "total_ms", "h2d_ms", "blocks_total",
         "blocks_flagged", "exact_windows", "wall_ms", "host_setup_ms", "host_cand_ms", "host_replay_ms", "n_runs", "n_align",
-        "n_align_redo", "filter_passes", "n_align_summary")
+        "n_align_redo", "filter_passes", "n_align_summary", "n_align_head")
 
 
 def run_ours(args):
@@ -734,7 +734,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": alg_bytes, "limiter": limiter},
             "clocks": clocks, "clocks_e2e": clocks_e2e,
             "hits_per_step": nh, "runs_per_step": a_res["n_runs"], equal_key: equal_val,
-            "extensions_per_step": a_res["n_align"], "extensions_redone_per_step": a_res["n_align_redo"], "extensions_by_summary_kernel_per_step": a_res["n_align_summary"],
+            "extensions_per_step": a_res["n_align"], "extensions_redone_per_step": a_res["n_align_redo"], "extensions_by_summary_kernel_per_step": a_res["n_align_summary"], "extensions_third_sweep_per_step": a_res["n_align_head"],
             "prefilter_blocks_flagged_per_step": a_res["blocks_flagged"], "count_table_windows_per_step": a_res["exact_windows"],
             "cold": {"context_create_ms": t_ctx * 1e3, "first_call_ms": cold_first_ms, "steady_e2e_ms": dt_e2e / args.steps * 1e3,
                      "note": "first_call = the first operator call on a fresh context, from pinned host planes: device plane + scratch cudaMalloc, "

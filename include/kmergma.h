@@ -135,9 +135,10 @@ typedef struct {
     double host_setup_ms;         /* plan, tables, scratch, small uploads (until the genome stream starts) */
     double host_cand_ms;          /* candidate list D2H + sort + segment building */
     double host_replay_ms;        /* run merge + replay of the reference state machine (without the extension kernel) */
-    int64_t n_align_redo;         /* extensions the fast tagged kernel handed to its two-chain form (no leading / trailing deletion run) */
+    int64_t n_align_redo;         /* extensions whose last-row maximum is also attained at column n (second sweep of the tagged kernel) */
     int64_t filter_passes;        /* prefilter passes over the shard (one per group of profiles sharing a weight table); filter_ms spans all */
-    int64_t n_align_summary;      /* extensions that went on to the path-summary kernel (paths starting at column 0 of the slice) */
+    int64_t n_align_summary;      /* extensions redone by the path-summary kernel (only with KGMA_ALIGN_TAIL=off, a testing switch) */
+    int64_t n_align_head;         /* extensions whose path starts at column 0 of the slice (third sweep of the tagged kernel) */
 } kgma_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */

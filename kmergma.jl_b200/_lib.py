@@ -53,7 +53,7 @@ class Stats(C.Structure):
                 ("launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("wall_ms", C.c_double), ("host_setup_ms", C.c_double), ("host_cand_ms", C.c_double),
                 ("host_replay_ms", C.c_double), ("n_align_redo", C.c_int64), ("filter_passes", C.c_int64),
-                ("n_align_summary", C.c_int64)]
+                ("n_align_summary", C.c_int64), ("n_align_head", C.c_int64)]
 
 
 class Match(C.Structure):

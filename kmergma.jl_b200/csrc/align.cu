@@ -381,10 +381,10 @@ __device__ __forceinline__ int tg_add(int a, int b, int one)
 }
 
 struct TgConst {
-    int go, ge, S0, K_ee, K_eo, K_fe, K_mfo, K_efo, K_fo, KEEP, T1, T2, KHI, KDG, P_I1, ONE, SH20;
+    int go, ge, S0, K_ee, K_eo, K_fe, K_mfo, K_efo, K_fo, KEEP, T1, T2, KHI, KDG, P_I1, ONE, SH20, NOT1, C512;
 };
 
-template <bool CHAIN_B>
+template <int PAY>
 __device__ __forceinline__ TgConst tg_consts(int go, int ge)
 {
     TgConst k;
@@ -394,8 +394,9 @@ __device__ __forceinline__ TgConst tg_consts(int go, int ge)
     k.S0 = -2047 + ge;
     // first payload: an insert column more per E step.  Second payload: an E step is one more trailing insert op (an opening
     // resets the payload to "1 I" before the constant is added)
-    k.K_ee = (int)((unsigned)(-ge) << TG_SC_SH) + TG_TAG1 + TG_IC1;                     // E stored with tag 0: extend -> 1
-    k.K_eo = (int)((unsigned)(-gog) << TG_SC_SH) - TG_TAG2 + (CHAIN_B ? 0 : TG_IC1);    // H stored with tag 2: open   -> 0
+    // Third payload (paths from (0,0) only): nothing to count in a gap
+    k.K_ee = (int)((unsigned)(-ge) << TG_SC_SH) + TG_TAG1 + (PAY == 2 ? 0 : TG_IC1);    // E stored with tag 0: extend -> 1
+    k.K_eo = (int)((unsigned)(-gog) << TG_SC_SH) - TG_TAG2 + (PAY == 0 ? TG_IC1 : 0);   // H stored with tag 2: open   -> 0
     // The deletion gap F[i][j+1] = max(F[i][j] - ge, H[i][j] - gog) is evaluated as max(F - ge, mm - gog, e - gog): opening
     // from an H that itself came out of F is never better than extending that F (and carries the same counters), so H drops
     // out of the recurrence and the chain along a row is one add-max and one retag per cell.  Order on equal scores:
@@ -408,6 +409,7 @@ __device__ __forceinline__ TgConst tg_consts(int go, int ge)
                  : "n"(~TG_TAGMASK), "n"(TG_TAG1), "n"(TG_TAG2), "n"(1));
     asm volatile("mov.b32 %0, %4; mov.b32 %1, %5; mov.b32 %2, %6; mov.b32 %3, %7;" : "=r"(k.KHI), "=r"(k.KDG), "=r"(k.P_I1), "=r"(k.SH20)
                  : "n"(~TG_PAY), "n"(~(0x1FF << 9)), "n"(TG_IC1), "n"(1 << TG_SC_SH));
+    asm volatile("mov.b32 %0, %2; mov.b32 %1, %3;" : "=r"(k.NOT1), "=r"(k.C512) : "n"(~1), "n"(512));
     return k;
 }
 
@@ -424,15 +426,20 @@ __device__ __forceinline__ uint32_t tg_subject_code(const AlignArgs2 &A, const A
     return code;
 }
 
-// One sweep of the DP by one warp; leaves row m of H in Hst (lane l: columns l*C+1 .. l*C+C).  CHAIN_B selects the payload.
-template <int C, bool CHAIN_B>
+// One sweep of the DP by one warp; leaves row m of H in Hst (lane l: columns l*C+1 .. l*C+C).  PAY selects the payload:
+// 0 = start column / insert columns, 1 = trailing ops (above), 2 = the head of a path that starts at (0,0):
+//     [17:9] leading diagonal steps, or the leading insert ops when bit 1 is set   [1] starts with inserts   [0] only diagonal steps so far
+// from which the first CIGAR run of a path without leading deletions follows (the insert run, or the equal-kind stretch of the
+// main diagonal cut at the number of leading diagonal steps).
+template <int C, int PAY>
 __device__ __forceinline__ void tg_sweep(const AlignArgs2 &A, const AlignJob2 &J, int lane, int (&Hst)[C])
 {
     const unsigned FULL = 0xFFFFFFFFu;
-    const TgConst k = tg_consts<CHAIN_B>(A.go, A.ge);
+    constexpr bool CHAIN_B = PAY == 1, CHAIN_C = PAY == 2;
+    const TgConst k = tg_consts<PAY>(A.go, A.ge);
     const int go = k.go, ge = k.ge, S0 = k.S0;
     const int K_ee = k.K_ee, K_eo = k.K_eo, K_fe = k.K_fe, K_mfo = k.K_mfo, K_efo = k.K_efo, K_fo = k.K_fo;
-    const int KEEP = k.KEEP, T1 = k.T1, T2 = k.T2, KHI = k.KHI, KDG = k.KDG, P_I1 = k.P_I1, ONE = k.ONE, SH20 = k.SH20;
+    const int KEEP = k.KEEP, T1 = k.T1, T2 = k.T2, KHI = k.KHI, KDG = k.KDG, P_I1 = k.P_I1, ONE = k.ONE, SH20 = k.SH20, NOT1 = k.NOT1, C512 = k.C512;
     const int m = J.m, n = J.n;
     const uint8_t *a = A.a + J.a_off;
     const int j0 = lane * C;                                                  // this lane owns columns j0+1 .. j0+C
@@ -443,11 +450,11 @@ __device__ __forceinline__ void tg_sweep(const AlignArgs2 &A, const AlignJob2 &J
         const uint32_t code = j <= n ? tg_subject_code(A, J, j) : 0u;
         // byte permute selector: byte 0 = table[code], bytes 1-3 = its sign  ->  a sign-extended score in one PRMT
         colsel[c] = code | ((code | 8u) << 4) | ((code | 8u) << 8) | ((code | 8u) << 12);
-        Hst[c] = TG_TAG2 | (CHAIN_B ? 0 : j);                                 // row 0: free leading deletions, path = jD
+        Hst[c] = TG_TAG2 | (PAY == 0 ? j : 0);                                // row 0: free leading deletions, path = jD
         Est[c] = (int)((unsigned)S0 << TG_SC_SH);
     }
     // H[0][j0]: diagonal of my first column at row 1
-    int prevIn = TG_TAG2 | (CHAIN_B ? 0 : j0);
+    int prevIn = TG_TAG2 | (PAY == 0 ? j0 : (CHAIN_C && j0 == 0) ? 1 : 0);    // (third payload: the empty path at (0,0) is "only diagonal steps so far")
     int Hlast = 0, Flast = 0;
     for (int s = 1; s <= m + 31; s++) {
         const int i = s - lane;
@@ -455,11 +462,11 @@ __device__ __forceinline__ void tg_sweep(const AlignArgs2 &A, const AlignJob2 &J
         if (i >= 1 && i <= m) {
             int left, F, diag = prevIn;
             if (lane == 0) {                                                  // column 0: H[i][0] = -(go + i ge), path = iI; no deletion gap yet
-                left = (int)((unsigned)(-(go + i * ge)) << TG_SC_SH) | TG_TAG2 | (i << 9);     // (i insert columns so far / i trailing insert ops)
+                left = (int)((unsigned)(-(go + i * ge)) << TG_SC_SH) | TG_TAG2 | (i << 9) | (CHAIN_C ? 2 : 0);     // i insert columns so far / trailing / leading insert ops
                 F = (int)((unsigned)S0 << TG_SC_SH) | TG_TAG1;
             } else { left = inH; F = inF; }
             prevIn = left;
-            F = tg_retag(max(F + K_fe, (CHAIN_B ? (left & KHI) : left) + K_fo), KEEP, T1);                 // F[i][j0+1]
+            F = tg_retag(max(F + K_fe, (CHAIN_B ? (left & KHI) : CHAIN_C ? (left & NOT1) : left) + K_fo), KEEP, T1);   // F[i][j0+1]
             const int ai = a[i - 1];
             // EDNAFULL row of this consensus symbol as signed bytes: vs A,C,G,T in tlo, vs N in thi
             const uint32_t tlo = ai < 4 ? ((0xFCFCFCFCu & ~(0xFFu << (8 * ai))) | (5u << (8 * ai))) : 0xFEFEFEFEu;
@@ -469,9 +476,12 @@ __device__ __forceinline__ void tg_sweep(const AlignArgs2 &A, const AlignJob2 &J
                 const int up = Hst[c];
                 const int sub = tg_prmt(tlo, thi, colsel[c]);
                 int e, mm;
-                if (!CHAIN_B) {
+                if (PAY == 0) {
                     e = max(Est[c] + K_ee, tg_add(up, K_eo, ONE)) & KEEP;
                     mm = tg_add(sub, diag, SH20);                                                          // diag + (sub << 20), one IMAD
+                } else if (CHAIN_C) {
+                    e = max(Est[c] + K_ee, tg_add(up & NOT1, K_eo, ONE)) & KEEP;                           // a gap ends the leading diagonal run
+                    mm = tg_add(sub, tg_add(diag & 1, diag, C512), SH20);                                  // one more leading diagonal step while it lasts
                 } else {
                     e = max(Est[c] + K_ee, tg_add(tg_retag(up, KHI, P_I1), K_eo, ONE)) & KEEP;             // opening: the path's last run is now 1 I
                     mm = tg_add(sub, (diag & KDG) + 1, SH20);                                              // one more trailing diagonal op, no trailing insert
@@ -479,18 +489,21 @@ __device__ __forceinline__ void tg_sweep(const AlignArgs2 &A, const AlignJob2 &J
                 const int h = tg_retag(__vimax3_s32(mm, F, e), KEEP, T2);
                 diag = up; Hst[c] = h; Est[c] = e;
                 if (c == C - 1) { Hlast = h; Flast = F; }
-                else if (!CHAIN_B) F = tg_retag(max(F + K_fe, max(mm + K_mfo, tg_add(e, K_efo, ONE))), KEEP, T1);   // F[i][j+1]
-                else F = tg_retag(max(F + K_fe, max(mm + K_mfo, tg_add(e, K_efo, ONE)) & KHI), KEEP, T1);           // (an opened deletion: payload 0)
+                else if (PAY == 0) F = tg_retag(max(F + K_fe, max(mm + K_mfo, tg_add(e, K_efo, ONE))), KEEP, T1);   // F[i][j+1]
+                else F = tg_retag(max(F + K_fe, max(mm + K_mfo, tg_add(e, K_efo, ONE)) & (CHAIN_B ? KHI : NOT1)), KEEP, T1);   // (an opened deletion: payload 0 / run closed)
             }
         }
     }
 }
 
 // One warp per queue entry.  An entry is an alignment (first-payload sweep; when the last-row maximum is also attained at
-// column n and no twin is queued, the same warp adds the second-payload sweep) or the twin of an alignment the host expects to
-// end at (m, n) (second-payload sweep only: its window sits at the edge of a run, where the consensus overhangs the slice) --
-// the two sweeps of such an alignment then run side by side on two warps instead of one after the other.  The host combines
-// the two result records (align_collect).
+// column n and no twin is queued, the same warp adds the second-payload sweep; when the path starts at column 0, the
+// third-payload sweep) or the twin of an alignment the host expects to end at (m, n) (second-payload sweep only: its window
+// sits at the edge of a run, where the consensus overhangs the slice) -- the two sweeps of such an alignment then run side by
+// side on two warps instead of one after the other.  The host combines the result records (align_collect):
+//   out[slot]              score | x and start-to-first-maximum columns | (x, I) of the path to (m, n), is n the first maximum
+//   out[nslots + slot]     trailing diagonal ops, trailing insert ops of the path to (m, n), equal-kind stretch ending there
+//   out[2 nslots + slot]   head words of the paths to the first maximum and to (m, n), equal-kind stretch from (1, 1)
 template <int C>
 __global__ void __launch_bounds__(128) kgma_align_tagged(AlignArgs2 A)
 {
@@ -504,48 +517,55 @@ __global__ void __launch_bounds__(128) kgma_align_tagged(AlignArgs2 A)
         const AlignJob2 J = A.jobs[ji];
         const int m = J.m, n = J.n, j0 = lane * C;
         const int ln = (n - 1) / C;                                           // lane that owns column n
-        bool second = (J.mode & 2) != 0;
+        const uint8_t *a = A.a + J.a_off;
+        bool second = (J.mode & 2) != 0, third = false;
+        int jstar = 0;
+        // last row of a sweep: first column attaining the maximum (ties -> lowest column; column 0, the all-insert path, included)
+        auto first_max = [&](const int (&Hst)[C], int w0, int &bv, int &w, int &wlast) {
+            int best = -(A.go + m * A.ge), bestw = w0, bestj = 0, wn = 0;               // H[m][0]: m inserts, payload w0
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const int j = j0 + c + 1;
+                const int v = Hst[c] >> TG_SC_SH;
+                if (j <= n && v > best) { best = v; bestw = Hst[c]; bestj = j; }
+                if (j == n) wn = Hst[c];
+            }
+            // warp argmax over (score, lowest column): columns grow with the lane index, so on equal scores the lower lane wins
+            bv = best; int bl = lane;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) {
+                const int ov = __shfl_xor_sync(FULL, bv, d), ol = __shfl_xor_sync(FULL, bl, d);
+                if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
+            }
+            w = __shfl_sync(FULL, bestw, bl); jstar = __shfl_sync(FULL, bestj, bl);
+            wlast = __shfl_sync(FULL, wn, ln);
+        };
         if (!second) {
-            int w, jstar, bv, wlast;
+            int w, bv, wlast;
             {
                 int Hst[C];
-                tg_sweep<C, false>(A, J, lane, Hst);
-                // ---- last row: first column attaining the maximum (ties -> lowest column), and the word at column n
-                int best = INT_MIN, bestw = 0, bestj = 0, wn = 0;
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    const int j = j0 + c + 1;
-                    const int v = Hst[c] >> TG_SC_SH;
-                    if (j <= n && v > best) { best = v; bestw = Hst[c]; bestj = j; }
-                    if (j == n) wn = Hst[c];
-                }
-                // warp argmax over (score, lowest column): columns grow with the lane index, so on equal scores the lower lane wins
-                bv = best; int bl = lane;
-#pragma unroll
-                for (int d = 16; d; d >>= 1) {
-                    const int ov = __shfl_xor_sync(FULL, bv, d), ol = __shfl_xor_sync(FULL, bl, d);
-                    if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
-                }
-                w = __shfl_sync(FULL, bestw, bl); jstar = __shfl_sync(FULL, bestj, bl);
-                wlast = __shfl_sync(FULL, wn, ln);
+                tg_sweep<C, 0>(A, J, lane, Hst);
+                first_max(Hst, m << 9, bv, w, wlast);
             }
             const bool tie = (wlast >> TG_SC_SH) == bv;                       // the path may end at (m, n): the second payload decides
-            const bool degenerate = bv <= -(A.go + m * A.ge);
+            const int x = w & 0x1FF, ic = (w >> 9) & 0x1FF;
+            const bool head = x == 0 || (tie && (wlast & 0x1FF) == 0);        // a path from column 0 may be the one: the third payload
+            const bool off = A.tail_mode == 2;
             if (lane == 0) {
                 AlignOut o;
-                const int x = w & 0x1FF, ic = (w >> 9) & 0x1FF;
                 o.score = bv; o.lower = x; o.num_sum = jstar + ic;
-                o.nops = (degenerate || (tie && A.tail_mode == 2) || (!tie && x == 0)) ? -1 : tie ? 3 : 2;
+                o.nops = (off && (tie || head)) ? -1 : tie ? 3 : 2;
                 o.cig_n = (wlast & 0x3FFFF) | ((jstar == n) << 18);            // x and I of the path to (m, n); is column n the first maximum?
                 A.out[J.slot] = o;
             }
-            second = tie && !degenerate && A.tail_mode != 2 && !(J.mode & 1);
+            second = tie && !off && !(J.mode & 1);
+            third = head && !off;
         }
         if (second) {
             int w2;
             {
                 int Hs2[C];
-                tg_sweep<C, true>(A, J, lane, Hs2);
+                tg_sweep<C, 1>(A, J, lane, Hs2);
                 int wn2 = 0;
 #pragma unroll
                 for (int c = 0; c < C; c++) if (j0 + c + 1 == n) wn2 = Hs2[c];
@@ -553,7 +573,6 @@ __global__ void __launch_bounds__(128) kgma_align_tagged(AlignArgs2 A)
             }
             // length of the equal-kind stretch ending at (m, n) on its diagonal: '=' where the symbols are the same, 'X' elsewhere
             const int ndiag = w2 & 0x1FF;
-            const uint8_t *a = A.a + J.a_off;
             const int lim = min(ndiag, min(m, n));
             const bool k0 = tg_subject_code(A, J, n) == (uint32_t)a[m - 1];
             int r = lim;
@@ -565,7 +584,32 @@ __global__ void __launch_bounds__(128) kgma_align_tagged(AlignArgs2 A)
             if (lane == 0) {
                 AlignOut o;
                 o.score = 0; o.lower = ndiag; o.num_sum = (w2 >> 9) & 0x1FF; o.nops = r; o.cig_n = 1;
-                A.out[A.nslots + J.slot] = o;                                 // trailing diagonal ops, trailing insert ops, equal-kind stretch
+                A.out[A.nslots + J.slot] = o;
+            }
+        }
+        if (third) {
+            int w3, w3n, bv3;
+            {
+                int Hs3[C];
+                tg_sweep<C, 2>(A, J, lane, Hs3);
+                first_max(Hs3, (m << 9) | 2, bv3, w3, w3n);                   // the same scores, hence the same first maximum
+            }
+            // length of the equal-kind stretch of the main diagonal from (1, 1), as far as either path follows it
+            const int d0 = max((w3 & 2) ? 0 : (w3 >> 9) & 0x1FF, (w3n & 2) ? 0 : (w3n >> 9) & 0x1FF);
+            const int lim = min(d0, min(m, n));
+            int r = lim;
+            if (lim > 0) {
+                const bool k0 = tg_subject_code(A, J, 1) == (uint32_t)a[0];
+                for (int t0 = 0; t0 < lim; t0 += 32) {
+                    const int t = t0 + lane;
+                    const unsigned diff = __ballot_sync(FULL, t < lim && (tg_subject_code(A, J, 1 + t) == (uint32_t)a[t]) != k0);
+                    if (diff) { r = t0 + __ffs((int)diff) - 1; break; }
+                }
+            }
+            if (lane == 0) {
+                AlignOut o;
+                o.score = 0; o.lower = w3 & 0x3FFFF; o.num_sum = w3n & 0x3FFFF; o.nops = r; o.cig_n = 1;
+                A.out[2 * A.nslots + J.slot] = o;
             }
         }
         __syncwarp();
@@ -694,7 +738,7 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
         jobs.swap(q);
     }
     const int nq = (int)jobs.size();                           // queue entries
-    const int nout = tagged ? 2 * nj : nj;                     // result records: [nj] first sweep, [nj] second sweep
+    const int nout = tagged ? 3 * nj : nj;                     // result records: [nj] first, [nj] second, [nj] third sweep
     size_t o = 0;
     auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
     const size_t o_a = carve(acodes.size()), o_b = carve(bcodes.size()), o_j = carve((size_t)nq * sizeof(AlignJob2));
@@ -781,18 +825,28 @@ int align_collect(kgma_ctx *ctx, AlignTicket *t, std::vector<AlignRes> &out)
             const AlignJob2 &J = hj[j];
             if (J.mode & 2) continue;                                 // a twin: its record is read below
             AlignOut &A1 = ho[J.slot];
-            if (A1.nops == 3) {
-                // the last-row maximum is also attained at column n: combine with the second-payload record (kgma_align_tagged)
-                const AlignOut &B = ho[t->nj + J.slot];
-                if (B.cig_n != 1) return set_err(ctx, KGMA_E_STATE, "extension: second-sweep record of alignment %d missing", J.slot);
+            if (A1.nops >= 2) {
+                // combine the sweeps' records (kgma_align_tagged)
                 const int x_n = A1.cig_n & 0x1FF, i_n = (A1.cig_n >> 9) & 0x1FF; const bool first_max_at_n = (A1.cig_n >> 18) & 1;
-                const bool diag_last = B.lower > 0;                   // the path to (m, n) ends with a diagonal step: match before free deletion
-                if (first_max_at_n || diag_last) {
-                    const int lastrun = diag_last ? std::min(B.lower, B.nops) : B.num_sum;
-                    A1.lower = x_n; A1.num_sum = J.n + i_n - lastrun;
+                bool at_end = false; int lastrun = 0;
+                if (A1.nops == 3) {                                   // the last-row maximum is also attained at column n
+                    const AlignOut &B = ho[t->nj + J.slot];
+                    if (B.cig_n != 1) return set_err(ctx, KGMA_E_STATE, "extension: second-sweep record of alignment %d missing", J.slot);
+                    const bool diag_last = B.lower > 0;               // the path to (m, n) ends with a diagonal step: match before free deletion
+                    at_end = first_max_at_n || diag_last;
+                    lastrun = diag_last ? std::min(B.lower, B.nops) : B.num_sum;
+                    ctx->stats.n_align_redo++;
                 }
-                A1.nops = A1.lower == 0 ? -1 : 2;                     // a path from column 0: the path-summary kernel
-                ctx->stats.n_align_redo++;
+                int lower = at_end ? x_n : A1.lower, num_sum = at_end ? J.n + i_n - lastrun : A1.num_sum;
+                if (lower == 0) {                                     // no leading deletions: the first run comes from the head payload
+                    const AlignOut &Cc = ho[2 * t->nj + J.slot];
+                    if (Cc.cig_n != 1) return set_err(ctx, KGMA_E_STATE, "extension: third-sweep record of alignment %d missing", J.slot);
+                    const int w3 = at_end ? Cc.num_sum : Cc.lower, d0 = (w3 >> 9) & 0x1FF;
+                    lower = (w3 & 2) ? d0 : std::min(d0, Cc.nops);
+                    if (at_end && lower == J.n + i_n) { lower = 0; num_sum = 0; }    // the whole CIGAR is one run: (0 + 1):0
+                    ctx->stats.n_align_head++;
+                }
+                A1.lower = lower; A1.num_sum = num_sum; A1.nops = 2;
             }
             if (A1.nops < 0) { hj2[redo.size()] = J; redo.push_back(J.slot); }
         }

@@ -8,5 +8,5 @@ python profiles/r2_micro3.py > gpurun_out/r2e_micro3.json 2> gpurun_out/r2e_micr
 import json
 d=json.load(open('gpurun_out/r2e_micro3.json'))
 for k,v in d.items():
-    if isinstance(v,dict): print(k, {n:(round(x['align_ms'],3),x['two_sweeps'],x['summary']) for n,x in v.items()})
+    if isinstance(v,dict): print(k, {n:(round(x['align_ms'],3),x['two_sweeps'],x['summary'],x['head']) for n,x in v.items()})
 PY

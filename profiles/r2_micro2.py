@@ -16,7 +16,7 @@ for (r, pos, s) in W.plants:
 g.make_resident(ctx)
 RV, ws, cons = K.gen_ref_ws_cons(bench.TF, 6)
 out = {}
-KEYS = ("filter_ms", "exact_ms", "align_ms", "wall_ms", "host_replay_ms", "n_align", "n_align_redo", "n_align_summary", "n_runs", "launches")
+KEYS = ("filter_ms", "exact_ms", "align_ms", "wall_ms", "host_replay_ms", "n_align", "n_align_redo", "n_align_summary", "n_align_head", "n_runs", "launches")
 
 
 def scan(n=10, env=None):

@@ -34,7 +34,7 @@ for env in ({}, {"KGMA_ALIGN_TAIL": "all"}, {"KGMA_ALIGN_TAIL": "off"}, {"KGMA_A
                                                 of.ctypes.data, ol.ctypes.data, sc.ctypes.data))
             st = ctx.stats()
             ms.append(st["align_ms"])
-        res[str(n)] = {"align_ms": float(np.median(ms[1:])), "two_sweeps": int(st["n_align_redo"]), "summary": int(st["n_align_summary"])}
+        res[str(n)] = {"align_ms": float(np.median(ms[1:])), "two_sweeps": int(st["n_align_redo"]), "summary": int(st["n_align_summary"]), "head": int(st["n_align_head"])}
     out["+".join("%s=%s" % kv for kv in env.items()) or "default"] = res
     for k_ in env:
         os.environ.pop(k_, None)

@@ -1249,8 +1249,8 @@ def test_tagged_extension_kernel_equals_path_summary_kernel(K, O, prof, monkeypa
     """the default extension kernel (kgma_align_tagged: one word per DP state, DPX three-way max) against the
     path-summary kernel it falls back to (KGMA_ALIGN_KERNEL=summary forces that one for the whole batch): same ranges and
     scores for several gap models, subject lengths from 1 to 511 (with N), consensus lengths 8..400, subjects that start or
-    end inside the homologue (no trailing deletion run: finished by the kernel's two-chain form, also forced for every alignment
-    and switched off; no leading deletion run: handed to the path-summary kernel); then against the oracle"""
+    end inside the homologue (no trailing / no leading deletion run: finished by the kernel's second- / third-payload sweep, also with
+    twins forced for every alignment, and with both switched off: the path-summary kernel takes those); then against the oracle"""
     RV, ws, cons = prof
     rng = np.random.default_rng(21)
     whole = O.Fasta(GENOME).seq(3)
@@ -1287,28 +1287,28 @@ def test_tagged_extension_kernel_equals_path_summary_kernel(K, O, prof, monkeypa
         monkeypatch.delenv("KGMA_ALIGN_KERNEL", raising=False)
         monkeypatch.delenv("KGMA_ALIGN_TAIL", raising=False)
         st = ctx.stats()
-        return of.tolist(), ol.tolist(), sc.tolist(), st["n_align_redo"], st["n_align_summary"]
+        return of.tolist(), ol.tolist(), sc.tolist(), st["n_align_redo"], st["n_align_summary"], st["n_align_head"]
 
-    two_chain = by_summary = 0
+    second = third = 0
     for clen in (8, 33, 160, 161, 200, 289, 320, 321, 400):
         c = (cons[:289] * 2)[:clen].encode()
         for go, ge in ((-69, -1), (-200, -1), (-5, -2), (0, -1), (-30, -3)):
             a = batch(c, go, ge, None)
             b = batch(c, go, ge, "summary")
             assert a[:3] == b[:3], (clen, go, ge)
-            assert b[3] == 0 and b[4] == 0
-            # the two-chain form for every alignment, and for none (everything it would finish goes to the path-summary kernel)
+            assert b[3:] == (0, 0, 0) and a[4] == 0
+            # a second-payload twin for every alignment, and no second / third sweep at all (the path-summary kernel finishes those)
             a_all, a_off = batch(c, go, ge, None, "all"), batch(c, go, ge, None, "off")
             assert a_all[:3] == b[:3] and a_off[:3] == b[:3], (clen, go, ge)
-            assert a_off[3] == 0 and a_off[4] >= a[4] and a_all[4] == a[4]
-            two_chain += a[3]; by_summary += a[4]
-        of, ol, sc, _, _ = batch(c, -69, -1, None)
+            assert a_off[3] == 0 and a_off[5] == 0 and a_off[4] > 0 and a_all[3:] == a[3:]
+            second += a[3]; third += a[5]
+        of, ol, sc = batch(c, -69, -1, None)[:3]
         for i in range(0, n, 5):
             s_ = recs[i][1]
             lo, hi = O.align_unitrange(s_, (1, len(s_)), c.decode(), clen, len(s_), -69, -1)
             assert (of[i], ol[i]) == (lo, hi), (clen, i)
             assert sc[i] == O.pairalign_semiglobal(c.decode(), s_, -69, -1)[1]
-    assert two_chain > 0 and by_summary > 0               # both hand-overs were exercised
+    assert second > 0 and third > 0                       # both extra sweeps were exercised
 
 
 def test_parallel_slide_kernel_equals_serial_kernel(K, O, prof, synth, tmp_path, monkeypatch):
