@@ -415,7 +415,7 @@ def bind_to_gpu_numa_node(device_index):
 
 KEYS = ("launches", "h2d_bytes", "d2h_bytes", "filter_ms", "exact_ms", "align_ms", "total_ms", "h2d_ms", "blocks_total",
         "blocks_flagged", "exact_windows", "wall_ms", "host_setup_ms", "host_cand_ms", "host_replay_ms", "n_runs", "n_align",
-        "n_align_redo", "filter_passes", "n_align_summary", "n_align_head")
+        "n_align_redo", "filter_passes", "n_align_summary", "n_align_head", "rank0_replay_ms")
 
 
 def run_ours(args):
@@ -473,28 +473,31 @@ def run_ours(args):
             return n.value
         return K.exact_match_shard(W.query, g_, shard, ctx=ctx, resident=resident)
 
-    # ---- the exchange of a sharded step: equal-sized blocks, one NCCL all-gather, read back on rank 0 only
+    # ---- the exchange of a sharded step: every rank packs its block straight into a shared-memory segment of the host and
+    #      publishes the step number; rank 0 replays the blocks in place (kmergma.jl_b200/exchange.py).  No collective, no
+    #      device round trip on the path; NCCL only sizes the segment (an untimed step) and closes the timed regions.
+    from kmergma_jl_b200 import HostExchange
+
     class Exchange:
         def __init__(self):
-            self.cap = 0
+            self.cap, self.x, self.gen = 0, None, 0
 
         def size(self, need):
             t = torch.tensor([need], dtype=torch.int64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             cap = (2 * int(t.item()) + 4096 + 4095) // 4096 * 4096
             if cap > self.cap:
-                self.cap = cap
-                self.h_in = torch.zeros(cap, dtype=torch.uint8).pin_memory()
-                self.d_in = torch.zeros(cap, dtype=torch.uint8, device="cuda")
-                self.d_all = torch.zeros(cap * world, dtype=torch.uint8, device="cuda")
-                self.h_all = torch.zeros(cap * world, dtype=torch.uint8).pin_memory() if rank == 0 else None
-
-        def gather(self):
-            self.d_in.copy_(self.h_in, non_blocking=True)
-            dist.all_gather_into_tensor(self.d_all, self.d_in)
-            if rank == 0:
-                self.h_all.copy_(self.d_all, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
+                if self.x:
+                    self.x.close()
+                self.gen += 1
+                name = "kgma_xch_%s_%d" % (os.environ.get("MASTER_PORT", "0"), self.gen)
+                if rank == 0:
+                    self.x = HostExchange(name, 0, world, cap, create=True)
+                dist.barrier()
+                if rank != 0:
+                    self.x = HostExchange(name, rank, world, cap, create=False)
+                dist.barrier()
+                self.cap = self.x.cap
 
     xch = Exchange() if world > 1 else None
 
@@ -509,27 +512,35 @@ def run_ours(args):
                 if count:
                     raise RuntimeError("exchange block too small (%d > %d)" % (need, xch.cap))
                 return None, st1, need
-            hv = xch.h_in.numpy()
+            xch.x.begin_step()
+            hv = xch.x.block()
             hv[:8].view(np.int64)[0] = starts.size
             hv[16:16 + starts.size * 8].view(np.int64)[:] = starts
         else:
             part = prep[0].scan_shard(fl, (rank, world))
             st1 = ctx.stats()
-            need = part.pack(xch.h_in.data_ptr() if xch.cap else None, xch.cap)
+            if not xch.cap:
+                need = part.pack(None, 0)
+                part.free()
+                return None, st1, need
+            ptr = xch.x.begin_step()
+            need = part.pack(ptr, xch.cap)
             part.free()
             if need > xch.cap:
-                if count:
-                    raise RuntimeError("exchange block too small (%d > %d)" % (need, xch.cap))
-                return None, st1, need
-        xch.gather()
+                raise RuntimeError("exchange block too small (%d > %d)" % (need, xch.cap))
+        xch.x.publish()
         if rank != 0:
             return None, st1, need
+        base = xch.x.wait_all()
         if exact:
-            ha = xch.h_all.numpy().reshape(world, xch.cap)
+            ha = xch.x.blocks()
             allst = np.concatenate([ha[i, 16:16 + int(ha[i, :8].view(np.int64)[0]) * 8].view(np.int64) for i in range(world)])
+            xch.x.consumed()
             res = K.exact_match_merge(g_, allst, len(W.query), True)
             return res, st1, need
-        out = prep[0].replay_packed(fl, xch.h_all.data_ptr(), world, xch.cap)
+        out = prep[0].replay_packed(fl, base, world, xch.cap)
+        xch.x.consumed()
+        st1 = dict(st1); st1["rank0_replay_ms"] = ctx.stats()["host_replay_ms"]
         return out, st1, need
 
     def whole_step(g_, resident):
@@ -545,7 +556,7 @@ def run_ours(args):
 
         def acc(st):
             for k_ in KEYS:
-                agg[k_] += st[k_]
+                agg[k_] += st.get(k_, 0) if isinstance(st, dict) else st[k_]
             n_acc[0] += 1
 
         def step(count):
@@ -638,8 +649,6 @@ def run_ours(args):
         dt_e2e, out_e2e, clocks_e2e, a_e2e = measure(g, True, False, REG)
         xbytes = xch.cap
         h2d_all, d2h_all = allsum([a_e2e["h2d_bytes"], a_e2e["d2h_bytes"]])
-        h2d_all += world * xch.cap                       # every rank's block goes host -> device before the all-gather
-        d2h_all += world * xch.cap                       # and the gathered blocks come back to rank 0's host
         if rank == 0:
             if exact:
                 ref_d = K.exactMatch(W.query, g, ctx=ctx)
@@ -712,7 +721,7 @@ def run_ours(args):
                        "parallelism": ("one GPU" if world == 1 else
                                        "the one genome cut into %d equal slices of the packed coordinate space with window-length halos; every rank scans "
                                        "and extends its slice (kgma_scan_shard); ONE NCCL all-gather of %d-byte blocks of (run, extension result) pairs; "
-                                       "host-only merge + replay on rank 0 (kgma_replay_packed)" % (world, xbytes)),
+                                       "host-only merge + replay on rank 0 (kgma_replay_packed)" % (world, xbytes)).replace("ONE NCCL all-gather of", "the ranks pack into a shared-memory segment of the host (no collective, no device round trip):"),
                        "l2": "input (%.0f MB packed per GPU) larger than L2; no flush needed" % (total / 4e6 / world) if total / 4 / world > 126e6 else
                              "input %.0f MB packed per GPU: smaller than the 126 MB L2 at this N; the resident timed loop re-reads it from L2/HBM as a serving loop would" % (total / 4e6 / world),
                        "timing": "host clock around blocking C-ABI calls bracketed by device sync + barrier, max over ranks, median of %d regions of "
@@ -723,7 +732,7 @@ def run_ours(args):
             "device_ms_per_step": {"prefilter_or_match": filt_ms, "count_table": a_res["exact_ms"], "extension": a_res["align_ms"],
                                    "scan_total": a_res["total_ms"], "e2e_h2d": a_e2e["h2d_ms"], "note": "rank 0's own slice when N > 1"},
             "host_ms_per_step": {"call_wall": a_res["wall_ms"], "setup": a_res["host_setup_ms"], "results": a_res["host_cand_ms"],
-                                 "replay_or_merge": a_res["host_replay_ms"], "e2e_call_wall": a_e2e["wall_ms"]},
+                                 "replay_or_merge": a_res["host_replay_ms"], "rank0_replay_of_all_blocks": a_res["rank0_replay_ms"], "e2e_call_wall": a_e2e["wall_ms"]},
             "per_rank_ms_per_step": {"resident": a_res["per_rank_ms_per_step"], "e2e": a_e2e["per_rank_ms_per_step"],
                                      "regions_resident": a_res["region_ms_per_step"], "regions_e2e": a_e2e["region_ms_per_step"],
                                      "note": "each rank's own timed loop before the closing barrier; ms_per_step is the max incl. the barrier"},

@@ -18,9 +18,10 @@ from typing import Dict, List, Optional, Sequence, Tuple, Union
 import numpy as np
 
 from . import _lib as L
+from .exchange import HostExchange
 
 __all__ = [
-    "KmerGMAError", "Context", "Genome", "FastaRecord", "KFV", "AlignResult",
+    "KmerGMAError", "Context", "Genome", "FastaRecord", "KFV", "AlignResult", "HostExchange",
     "gen_ref_ws_cons", "cluster_ref_API", "eliminate_null_params", "get_cluster_index",
     "estimate_optimal_threshold", "ac_gma_testing", "Omn_KmerGMA", "record_KmerGMA",
     "findGenes", "findGenes_cluster_mode", "exactMatch", "write_results", "write_hits", "hit_header",

@@ -518,7 +518,8 @@ __global__ void __launch_bounds__(128) kgma_align_tagged(AlignArgs2 A)
         const int m = J.m, n = J.n, j0 = lane * C;
         const int ln = (n - 1) / C;                                           // lane that owns column n
         const uint8_t *a = A.a + J.a_off;
-        bool second = (J.mode & 2) != 0, third = false;
+        bool second = (J.mode & 2) != 0, third = (J.mode & 8) != 0;         // twins: one sweep only
+        const bool twin = second || third;
         int jstar = 0;
         // last row of a sweep: first column attaining the maximum (ties -> lowest column; column 0, the all-insert path, included)
         auto first_max = [&](const int (&Hst)[C], int w0, int &bv, int &w, int &wlast) {
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(128) kgma_align_tagged(AlignArgs2 A)
             w = __shfl_sync(FULL, bestw, bl); jstar = __shfl_sync(FULL, bestj, bl);
             wlast = __shfl_sync(FULL, wn, ln);
         };
-        if (!second) {
+        if (!twin) {
             int w, bv, wlast;
             {
                 int Hst[C];
@@ -559,7 +560,7 @@ __global__ void __launch_bounds__(128) kgma_align_tagged(AlignArgs2 A)
                 A.out[J.slot] = o;
             }
             second = tie && !off && !(J.mode & 1);
-            third = head && !off;
+            third = head && !off && !(J.mode & 4);
         }
         if (second) {
             int w2;
@@ -724,16 +725,27 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     // KGMA_ALIGN_TAIL = all | off: a second-payload twin for every alignment / no second sweep at all (tests compare the routes)
     int tail_mode = 0;
     { const char *tv = getenv("KGMA_ALIGN_TAIL"); tail_mode = tv && !strcmp(tv, "all") ? 1 : tv && !strcmp(tv, "off") ? 2 : 0; }
-    // The queue: twins of the marked alignments first (the longest entries, and the ones whose result the host waits for),
-    // then the marked alignments, then the rest.
+    // The queue: twins first (second-payload twins are the longest entries, and the host waits for their results), then the
+    // alignments that have twins, then the rest.  A twin costs a sweep of its own, so who gets one depends on how full the
+    // machine is: with room for three warps per alignment (small batches: a shard of a multi-GPU scan, the tail batch of a
+    // streamed one) every alignment gets both twins and the batch takes the time of ONE sweep; otherwise the marked
+    // alignments get a second-payload twin, and the third sweep stays with the warp that finds it necessary.
     if (tagged && tail_mode != 2) {
-        std::vector<AlignJob2> q; q.reserve(jobs.size() * 2);
-        for (int pass = 0; pass < 3; pass++)
+        const size_t room = (size_t)ctx->num_sms * 12;                       // resident warps of the tagged kernel (3 CTAs per SM)
+        size_t n_marked = 0;
+        for (const AlignReq &rq : reqs) n_marked += rq.hint & 1;
+        const bool all3 = 3 * jobs.size() <= room;
+        const bool marked3 = !all3 && jobs.size() + 2 * n_marked <= room;
+        std::vector<AlignJob2> q; q.reserve(jobs.size() * 3);
+        for (int pass = 0; pass < 4; pass++)
             for (size_t i = 0; i < jobs.size(); i++) {
-                const bool marked = tail_mode == 1 || (reqs[i].hint & 1);
-                if (pass == 0 && marked) { AlignJob2 t2 = jobs[i]; t2.mode = 2; q.push_back(t2); }
-                if (pass == 1 && marked) { AlignJob2 t1 = jobs[i]; t1.mode = 1; q.push_back(t1); }
-                if (pass == 2 && !marked) q.push_back(jobs[i]);
+                const bool marked = tail_mode == 1 || all3 || (reqs[i].hint & 1);
+                const bool with3 = marked && (all3 || marked3);
+                AlignJob2 t2 = jobs[i];
+                if (pass == 0 && marked) { t2.mode = 2; q.push_back(t2); }
+                if (pass == 1 && with3) { t2.mode = 8; q.push_back(t2); }
+                if (pass == 2 && marked) { t2.mode = 1 | (with3 ? 4 : 0); q.push_back(t2); }
+                if (pass == 3 && !marked) q.push_back(t2);
             }
         jobs.swap(q);
     }
@@ -823,7 +835,7 @@ int align_collect(kgma_ctx *ctx, AlignTicket *t, std::vector<AlignRes> &out)
         std::vector<int> redo;
         for (int j = 0; j < t->nq; j++) {
             const AlignJob2 &J = hj[j];
-            if (J.mode & 2) continue;                                 // a twin: its record is read below
+            if (J.mode & (2 | 8)) continue;                           // a twin: its record is read below
             AlignOut &A1 = ho[J.slot];
             if (A1.nops >= 2) {
                 // combine the sweeps' records (kgma_align_tagged)

@@ -156,7 +156,7 @@ int  replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, con
 // ---- align.cu
 struct AlignOut { long long score; int32_t lower, num_sum, nops, cig_n; };                 // nops < 0: redo with the path-summary kernel
 struct AlignJob2 { long long gpos; int32_t n, a_off, m, b_off; int32_t mode, slot; };   // b_off >= 0: subject codes were uploaded (not on the device);
-                                                                        // tagged kernel: mode & 2 = second-payload sweep only (the twin of a marked job), mode & 1 = such a twin is queued;
+                                                                        // tagged kernel: mode & 2 / & 8 = second- / third-payload sweep only (a twin), mode & 1 / & 4 = such a twin is queued;
                                                                         // slot: index of the request (results are written there)
 struct AlignArgs2 {
     const uint8_t *a;            // consensus codes 0..3, 4 = N

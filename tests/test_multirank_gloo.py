@@ -167,6 +167,26 @@ def _worker_packed(rank, world, port, q):
     mine = torch.from_numpy(pack_block(runs, ext, firsts, cap))
     allb = [torch.zeros(cap, dtype=torch.uint8) for _ in range(world)]
     dist.all_gather(allb, mine)                            # ONE collective of equal-sized blocks
+    # the same blocks through the host shared-memory exchange bench.py uses on the GPU box (kmergma.jl_b200/exchange.py):
+    # several steps, so that both slots and the two-steps-behind wait are exercised
+    name = "kgma_xch_t%d" % port
+    x = K.HostExchange(name, 0, world, cap, create=True) if rank == 0 else None
+    dist.barrier()
+    if rank != 0:
+        x = K.HostExchange(name, rank, world, cap, create=False)
+    shm_ok = True
+    for step in range(5):
+        x.begin_step()
+        x.block()[:cap] = mine.numpy()
+        x.publish()
+        if rank == 0:
+            base = x.wait_all()
+            o2 = K.replay_packed(g, [RV], [ws], [cons], [THR], k, K.L.MODE_SINGLE, buff, K.L.F_ALIGN, -69, -1, base, world, x.cap, ctx=None)
+            x.consumed()
+            shm_ok = shm_ok and len(o2.hits) > 0
+            last_shm = [(int(h.record), int(h.first), int(h.last), int(h.genome_pos), float(h.dist)) for h in o2.hits]
+    dist.barrier()
+    x.close()
     if rank == 0:
         blocks = np.stack([b.numpy() for b in allb[::-1]])  # arrival order must not matter
         out = K.replay_packed(g, [RV], [ws], [cons], [THR], k, K.L.MODE_SINGLE, buff, K.L.F_ALIGN, -69, -1,
@@ -182,7 +202,7 @@ def _worker_packed(rank, world, port, q):
             refused = False
         except K.KmerGMAError:
             refused = True
-        q.put((got == want, len(got), refused, any(h.last - h.first + 1 != ws + 2 * buff for h in oh)))
+        q.put((got == want and shm_ok and last_shm == want, len(got), refused, any(h.last - h.first + 1 != ws + 2 * buff for h in oh)))
     dist.barrier()
     dist.destroy_process_group()
 
