@@ -26,6 +26,13 @@ class HostExchange:
         self.rank, self.world, self.cap = rank, world, (int(cap) + 4095) // 4096 * 4096
         size = _HDR_WORDS * 8 + 2 * world * self.cap
         self._shm = shared_memory.SharedMemory(name=name, create=create, size=size if create else 0)
+        if not create:
+            # the segment belongs to rank 0: keep this process's resource tracker from unlinking it a second time at exit
+            try:
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:
+                pass
         self._buf = np.ndarray((size,), dtype=np.uint8, buffer=self._shm.buf)
         self._hdr = self._buf[:_HDR_WORDS * 8].view(np.int64)
         if create:
