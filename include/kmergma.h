@@ -41,6 +41,8 @@ extern "C" {
 
 #define KGMA_MODE_SINGLE   0      /* ac_gma_testing! semantics */
 #define KGMA_MODE_CLUSTER  1      /* Omn_KmerGMA! semantics   */
+#define KGMA_MODE_STROBE   2      /* StrobeGMA! semantics (src/StrobemerGMA/StrobeGenomeMiner.jl:5-95, experimental in the reference): one profile over
+                                     the 4^(2s) gap-free 2-randstrobe codes; profile.k = w_max + s - 1 bases per code; always the dense pass */
 
 /* kgma_scan_params.flags */
 #define KGMA_F_ALIGN        (1u << 0)  /* do_align / align_hits */
@@ -52,7 +54,7 @@ extern "C" {
 
 /* kgma_hit.flags — hits whose reference-side Float64 result could legitimately differ (reported separately) */
 #define KGMA_HIT_NEAR_THR   (1u << 0)  /* some window of the run lies within 1e-9 rel of thr */
-#define KGMA_HIT_ARGMIN_TIE (1u << 1)  /* run minimum attained at more than one window */
+#define KGMA_HIT_ARGMIN_TIE (1u << 1)  /* run minimum attained at more than one window, or equal to the minimum carried from an earlier run */
 #define KGMA_HIT_ROUND_HALF (1u << 2)  /* dist*100 within 1e-9 of a rounding half-way point */
 
 /* kgma_run.flags (besides KGMA_HIT_NEAR_THR / KGMA_HIT_ARGMIN_TIE) */
@@ -88,6 +90,10 @@ typedef struct {
     int32_t  shard_count;         /* packed genome (window-length halo handled inside); 0/1 = everything */
     int32_t  only_record;         /* >= 0: scan just this record (record_KmerGMA!); -1 = all */
     int32_t  reserved;
+    /* KGMA_MODE_STROBE only (zero otherwise): randstrobe parameters s, w_min, w_max, q (Strobemers.jl:45-65) and process_hit!'s
+     * score_threshold (Alignment.jl: an extended hit whose alignment scores below it is dropped) */
+    int32_t  strobe_s, strobe_w_min, strobe_w_max, strobe_q;
+    int64_t  score_threshold;
 } kgma_scan_params;
 
 /* One maximal stretch of consecutive loop steps with d < thr: the sufficient
@@ -204,6 +210,9 @@ int  kgma_refs_count(const kgma_refs *r);
 int64_t kgma_refs_maxlen(const kgma_refs *r);
 /* gen_ref_ws_cons: S[4^k] (integer sums), n_refs, window = Int(round(sum_len*(1/N))), consensus[maxlen+1] */
 int  kgma_refs_profile(const kgma_refs *r, int k, int32_t *S, int32_t *n_refs, int64_t *window, char *consensus);
+/* gen_ref_ws_cons of the strobemer path (src/StrobemerGMA/StrobeRefGen.jl:4-42): S[4^(2s)] summed counts of the gap-free
+ * 2-randstrobe codes (Strobemers.jl:45-65,105-115) */
+int  kgma_refs_strobe_profile(const kgma_refs *r, int s, int w_min, int w_max, int q, int32_t *S, int32_t *n_refs, int64_t *window, char *consensus);
 /* cluster_ref_API (+ eliminate_null_params when drop_empty): returns the number of profiles written (<= n_cutoffs+2)
  * or < 0.  S: [max][4^k]; consensus: [max][cons_stride] NUL-terminated (truncated to window except the appended average). */
 int  kgma_refs_cluster(const kgma_refs *r, int k, const double *cutoffs, int n_cutoffs, int include_avg,

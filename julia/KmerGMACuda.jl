@@ -21,6 +21,7 @@ struct KgmaScanParams               # kgma_scan_params
     mode::Int32; flags::UInt32; buff::Int64
     gap_open::Int32; gap_extend::Int32
     shard_index::Int32; shard_count::Int32; only_record::Int32; reserved::Int32
+    strobe_s::Int32; strobe_w_min::Int32; strobe_w_max::Int32; strobe_q::Int32; score_threshold::Int64   # KGMA_MODE_STROBE only
 end
 struct KgmaHit                      # kgma_hit
     record::Int32; profile::Int32; cmi::Int64; first::Int64; last::Int64; genome_pos::Int64
@@ -124,7 +125,7 @@ function scan!(resultVec, hit_loci_vec, dist_vecs, genome_path, refVecs, windows
     cons = [Vector{UInt8}(string(c)) for c in consensus_seqs]
     GC.@preserve Ss cons begin
         profs = [KgmaProfile(k, Ss[i][2], windowsizes[i], pointer(Ss[i][1]), pointer(cons[i]), length(cons[i]), Float64(thrs[i])) for i in eachindex(Ss)]
-        P = Ref(KgmaScanParams(mode, flags | F_RESIDENT, buff, gap_open, gap_extend, 0, 1, -1, 0))
+        P = Ref(KgmaScanParams(mode, flags | F_RESIDENT, buff, gap_open, gap_extend, 0, 1, -1, 0, 0, 0, 0, 0, 0))
         res = Ref{Ptr{Cvoid}}(C_NULL)
         check(ctx, ccall((:kgma_scan, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{KgmaProfile}, Cint, Ref{KgmaScanParams}, Ref{Ptr{Cvoid}}),
                          ctx, g, profs, length(profs), P, res))

@@ -27,7 +27,7 @@ __all__ = [
     "findGenes", "findGenes_cluster_mode", "exactMatch", "write_results", "write_hits", "hit_header",
     "fasta_id_to_cumulative_len_dict", "align_unitrange",
     "julia_round2", "julia_float_str", "kmer_count", "kmer_dist", "as_UInt", "as_kmer",
-    "randstrobe_score", "get_strobe_2_mer", "ungapped_strobe_2_mer_count",
+    "randstrobe_score", "get_strobe_2_mer", "ungapped_strobe_2_mer_count", "strobe_gen_ref_ws_cons", "StrobeGMA", "Strobemer_findGenes",
 ]
 
 
@@ -936,6 +936,94 @@ def findGenes_cluster_mode(*, genome_path, ref_path, cluster_cutoffs=(7, 12, 20,
     if verbose:
         _log.info(info_str)
         _log.info("To write the results, use `KmerGMA.write_results`")
+    return output_vector
+
+
+# ------------------------------------------------------------------------------------------------
+# Strobemer path (src/StrobemerGMA/, experimental in the reference; its scan has no test or golden there -- parity is against
+# the oracle's line-by-line restatement, which is assembled from the three utilities the reference's tests do pin).
+def strobe_gen_ref_ws_cons(reference_seqs, s: int = 2, w_min: int = 3, w_max: int = 5, q: int = 5):
+    """gen_ref_ws_cons(refs; s, w_min, w_max, q) (StrobeRefGen.jl:4-42) -> (RV, windowsize, consensus); RV is a KFV over the
+    4^(2s) gap-free 2-randstrobe codes."""
+    refs = _Refs(reference_seqs)
+    lib = refs._lib
+    S = np.zeros(4 ** (2 * s), dtype=np.int32)
+    n, ws = C.c_int32(), C.c_int64()
+    cons = C.create_string_buffer(lib.kgma_refs_maxlen(refs._h) + 2)
+    rc = lib.kgma_refs_strobe_profile(refs._h, s, w_min, w_max, q, S.ctypes.data, C.byref(n), C.byref(ws), cons)
+    if rc != 0:
+        raise KmerGMAError(rc, "gen_ref_ws_cons (strobemers) failed")
+    return KFV(S.astype(np.float64) * (1.0 / n.value), S, n.value), ws.value, cons.value.decode()
+
+
+def strobe_scan_raw(genome: Genome, refVec, windowsize: int, consensus: str, thr: float, s: int, w_min: int, w_max: int, q: int,
+                    buff: int, flags: int, gap_open: int, gap_extend: int, score_threshold: int = 0,
+                    ctx: Optional[Context] = None) -> ScanOutput:
+    """kgma_scan with KGMA_MODE_STROBE"""
+    ctx = ctx or default_context()
+    S, N = _ints_of(refVec, ctx._lib)
+    if S.size != 4 ** (2 * s):
+        raise KmerGMAError(L.E_ARG, "refVec must have 4^(2s) entries")
+    cons = str(consensus).upper().encode()
+    prof = (L.Profile * 1)()
+    prof[0].k, prof[0].n_refs, prof[0].window = w_max + s - 1, N, int(windowsize)
+    prof[0].S = S.ctypes.data_as(C.POINTER(C.c_int32))
+    prof[0].consensus, prof[0].consensus_len, prof[0].thr = cons, len(cons), float(thr)
+    P = L.ScanParams(L.MODE_STROBE, flags, buff, gap_open, gap_extend, 0, 1, -1, 0, s, w_min, w_max, q, int(score_threshold))
+    res = C.c_void_p()
+    ctx.check(ctx._lib.kgma_scan(ctx._h, genome._h, prof, 1, C.byref(P), C.byref(res)))
+    out = ScanOutput(ctx._lib, res)
+    if flags & L.F_WANT_DISTS:
+        out.load_dists(1)
+    return out
+
+
+def StrobeGMA(*, genome_path, refVec, consensus_refseq, s: int = 2, w_min: int = 3, w_max: int = 5, q: int = 5,
+              windowsize: int = 289, thr: float = 33.5, ScaleFactor: Optional[float] = None, buff: int = 50, do_align: bool = True,
+              gap_open_score: int = -69, gap_extend_score: int = -5, score_threshold: int = 0,
+              do_return_dists: bool = False, do_return_align: bool = False, get_hit_loci: bool = False,
+              dist_vec: Optional[list] = None, result_align_vec: Optional[list] = None, hit_loci_vec: Optional[list] = None,
+              genome_pos: int = 0, resultVec: Optional[list] = None, ctx: Optional[Context] = None):
+    """StrobeGMA! (src/StrobemerGMA/StrobeGenomeMiner.jl:5-95): keyword arguments and in-place outputs as the reference's.
+    The device path is fixed to ScaleFactor = 1/(w_max+s-1), what Strobemer_findGenes passes (:139)."""
+    k = w_max + s - 1
+    if ScaleFactor is not None and abs(float(ScaleFactor) - 1.0 / k) > 1e-15:
+        raise KmerGMAError(L.E_UNSUPPORTED, "the device path uses ScaleFactor = 1/(w_max+s-1)")
+    if do_return_align:
+        raise KmerGMAError(L.E_UNSUPPORTED, "do_return_align is not available in strobemer mode")
+    if genome_pos != 0:
+        raise KmerGMAError(L.E_UNSUPPORTED, "genome_pos must start at 0")
+    g = _as_genome(genome_path)
+    flags = (L.F_ALIGN if do_align else 0) | (L.F_WANT_DISTS if do_return_dists else 0)
+    out = strobe_scan_raw(g, refVec, windowsize, consensus_refseq, thr, s, w_min, w_max, q, buff, flags,
+                          gap_open_score, gap_extend_score, score_threshold, ctx=ctx)
+    resultVec = resultVec if resultVec is not None else []
+    _emit(g, out, False, resultVec, hit_loci_vec if get_hit_loci else None, None)
+    if do_return_dists and dist_vec is not None:
+        dist_vec.extend(out.dists[0].tolist())
+    return out
+
+
+def Strobemer_findGenes(*, genome_path, ref_path, s: int = 2, w_min: int = 3, w_max: int = 5, q: int = 5,
+                        KmerDistThr: float = 30, buffer: int = 50, do_align: bool = True, align_score_thr: int = 0,
+                        do_return_dists: bool = False, do_return_hit_loci: bool = False, do_return_align: bool = False,
+                        verbose: bool = True, ctx: Optional[Context] = None):
+    """Strobemer_findGenes (StrobeGenomeMiner.jl:119-158): Any[hit_vector, (hit loci), (alignments), (distances)]"""
+    RV, windowsize, cons = strobe_gen_ref_ws_cons(ref_path, s, w_min, w_max, q)
+    hit_vector, dist_vec, hit_loci_vec = [], [], []
+    if verbose:
+        _log.info("initializing iteration...")
+    StrobeGMA(genome_path=genome_path, refVec=RV, consensus_refseq=cons, s=s, w_min=w_min, w_max=w_max, q=q,
+              windowsize=windowsize, thr=KmerDistThr, ScaleFactor=1.0 / (w_max + s - 1), buff=buffer, score_threshold=align_score_thr,
+              do_align=do_align, do_return_dists=do_return_dists, do_return_align=do_return_align, get_hit_loci=do_return_hit_loci,
+              dist_vec=dist_vec, hit_loci_vec=hit_loci_vec, resultVec=hit_vector, ctx=ctx)
+    output_vector = [hit_vector]
+    if do_return_hit_loci:
+        output_vector.append(hit_loci_vec)
+    if do_return_dists:
+        output_vector.append(dist_vec)
+    if verbose:
+        _log.info("genome mining completed successfully, returning vector of: vector of hits")
     return output_vector
 
 

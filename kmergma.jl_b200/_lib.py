@@ -10,7 +10,7 @@ SO_PATH = os.path.join(_HERE, "libkmergma_cuda.so")
 
 # status codes (kmergma.h)
 OK, E_CUDA, E_ARG, E_SYMBOL, E_IO, E_UNSUPPORTED, E_CAPACITY, E_STATE, E_WINDOW = 0, -1, -2, -3, -4, -5, -6, -7, -8
-MODE_SINGLE, MODE_CLUSTER = 0, 1
+MODE_SINGLE, MODE_CLUSTER, MODE_STROBE = 0, 1, 2
 F_ALIGN, F_DENSE, F_WANT_DISTS, F_WANT_CIGARS, F_TIE_OPEN, F_RESIDENT = 1, 2, 4, 8, 16, 32
 HIT_NEAR_THR, HIT_ARGMIN_TIE, HIT_ROUND_HALF = 1, 2, 4
 RUN_OPEN_LEFT, RUN_OPEN_RIGHT, RUN_MARKER = 1 << 8, 1 << 9, 1 << 10
@@ -26,7 +26,9 @@ class ScanParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("flags", C.c_uint32), ("buff", C.c_int64),
                 ("gap_open", C.c_int32), ("gap_extend", C.c_int32),
                 ("shard_index", C.c_int32), ("shard_count", C.c_int32),
-                ("only_record", C.c_int32), ("reserved", C.c_int32)]
+                ("only_record", C.c_int32), ("reserved", C.c_int32),
+                ("strobe_s", C.c_int32), ("strobe_w_min", C.c_int32), ("strobe_w_max", C.c_int32), ("strobe_q", C.c_int32),
+                ("score_threshold", C.c_int64)]
 
 
 class Run(C.Structure):
@@ -97,6 +99,7 @@ SYMBOLS = {
     "kgma_refs_count": (C.c_int, [_P]),
     "kgma_refs_maxlen": (C.c_int64, [_P]),
     "kgma_refs_profile": (C.c_int, [_P, C.c_int, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_char_p]),
+    "kgma_refs_strobe_profile": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_char_p]),
     "kgma_refs_cluster": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_char_p, C.c_int64, _P, _P]),
     "kgma_profile_from_kfv": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.POINTER(C.c_int32)]),
     "kgma_scan": (C.c_int, [_P, _P, C.POINTER(Profile), C.c_int, C.POINTER(ScanParams), C.POINTER(_P)]),

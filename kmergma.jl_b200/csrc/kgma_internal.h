@@ -127,7 +127,9 @@ int  dev_genome_prepare(kgma_ctx *ctx, kgma_genome *g, bool need_mask);
 // ---- per-profile exact integer tables (host side)
 struct ProfTab {
     int k = 0; int64_t ws = 0, nk = 0; int32_t N = 0;
-    std::vector<int32_t> S_rev;      // S in reversed-2-bit-group index order (matches packed bit order)
+    int kb = 0;                      // the code space has 4^kb codes: kb = k for k-mers, 2s for strobemers (KGMA_MODE_STROBE)
+    bool strobe = false;             // StrobeGMA!: codes through ScanPlan::cmap, loop of L-ws-1 steps, CMI = i, tracked-table quirk (scan.cu)
+    std::vector<int32_t> S_rev;      // S in reversed-2-bit-group index order (matches packed bit order); strobemers: natural order
     int64_t N2 = 0, twoN = 0, sumS2 = 0;
     int64_t T = 0;                   // d < thr  <=>  D < T
     int64_t Tlo = 0, Thi = 0;        // |d - thr| <= 1e-9*thr  <=>  Tlo <= D < Thi  (near-threshold band)
@@ -135,7 +137,7 @@ struct ProfTab {
     double  thr = 0;
     uint64_t hash = 0;               // fingerprint of (S, Thi, N, nk, k): key of the cached prefilter tables
 };
-int  build_proftab(kgma_ctx *ctx, const kgma_profile &p, ProfTab &t);
+int  build_proftab(kgma_ctx *ctx, const kgma_profile &p, ProfTab &t, const kgma_scan_params *P = nullptr);
 inline uint32_t rev_kmer(uint32_t c, int k) { uint32_t r = 0; for (int j = 0; j < k; j++) { r = (r << 2) | (c & 3); c >>= 2; } return r; }
 
 // ---- replay.cpp
@@ -147,7 +149,7 @@ struct Pending { size_t hit; size_t req; int64_t first; size_t run; };     // hi
 void merge_runs(std::vector<kgma_run> &runs, std::vector<kgma_run_ext> *ext = nullptr);
 void apply_extensions(kgma_genome *g, std::vector<kgma_hit> &hits, const std::vector<Pending> &pend, const std::vector<AlignRes> &ares);
 int  replay_single_range(kgma_ctx *ctx, kgma_genome *g, const ProfTab &t, const kgma_scan_params &P,
-                         const std::vector<kgma_run> &runs, const std::vector<int64_t> &first_D, int r0, int r1,
+                         std::vector<kgma_run> &runs, const std::vector<int64_t> &first_D, int r0, int r1,
                          int64_t *genome_pos_io, std::vector<kgma_hit> &hits, std::vector<AlignReq> &reqs, std::vector<Pending> &pend);
 int  replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, const kgma_profile *profiles,
             const kgma_scan_params &P, std::vector<kgma_run> &runs, const std::vector<int64_t> &first_D,

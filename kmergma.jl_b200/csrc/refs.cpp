@@ -117,6 +117,38 @@ int kgma_refs_profile(const kgma_refs *r, int k, int32_t *S, int32_t *n_refs, in
     return KGMA_OK;
 }
 
+// gen_ref_ws_cons of the strobemer path (src/StrobemerGMA/StrobeRefGen.jl:4-42): S[code] = summed counts of the gap-free
+// 2-randstrobe codes (ungapped_strobe_2_mer_count!, Strobemers.jl:105-115) over all references; window and consensus as above.
+// get_strobe_2_mer (Strobemers.jl:45-65): first strobe = bases 1..s, second strobe at the LAST start in w_min..w_max whose
+// randstrobe_score (as_UInt(first) + as_UInt(candidate)) % q is 0 -- the running minimum starts at `2 << 63` == 0 -- else w_min.
+int kgma_refs_strobe_profile(const kgma_refs *r, int s, int w_min, int w_max, int q, int32_t *S, int32_t *n_refs, int64_t *window, char *consensus)
+{
+    if (!r || !S || s < 1 || s > 6 || w_min < 1 || w_max < w_min || q < 1 || r->seqs.empty()) return KGMA_E_ARG;
+    const int k = w_max + s - 1;
+    size_t nb = (size_t)1 << (4 * s);
+    memset(S, 0, nb * sizeof(int32_t));
+    int64_t cum = 0; ColumnVotes cv;
+    auto code = [](char c) -> int { switch (c) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': case 'N': return 3; default: return -1; } };
+    for (auto &sq : r->seqs) {
+        const int64_t L = (int64_t)sq.size();
+        for (int64_t i = 0; i < L; i++) if (code(sq[(size_t)i]) < 0) return KGMA_E_SYMBOL;
+        for (int64_t i = 0; i + k <= L; i++) {
+            auto smer = [&](int i1) { uint32_t v = 0; for (int j = 0; j < s; j++) v = (v << 2) | (uint32_t)code(sq[(size_t)(i + i1 - 1 + j)]); return v; };
+            const uint32_t f = smer(1);
+            int min_ind = w_min;
+            for (int w = w_min; w <= w_max; w++) if ((f + smer(w)) % (uint32_t)q == 0) min_ind = w;
+            S[((size_t)f << (2 * s)) | smer(min_ind)] += 1;
+        }
+        cum += L;
+        if (!cv.add(sq)) return KGMA_E_SYMBOL;
+    }
+    int N = (int)r->seqs.size();
+    if (n_refs) *n_refs = N;
+    if (window) *window = round_half_even((double)cum * (1.0 / (double)N));
+    if (consensus) { std::string c = cv.consensus(); memcpy(consensus, c.c_str(), c.size() + 1); }
+    return KGMA_OK;
+}
+
 int kgma_refs_cluster(const kgma_refs *r, int k, const double *cutoffs, int n_cutoffs, int include_avg,
                       int drop_empty, int32_t *S, int32_t *n_members, int64_t *windows,
                       char *consensus, int64_t cons_stride, int32_t *invalid, double *ref_dists)

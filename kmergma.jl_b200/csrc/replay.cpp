@@ -178,7 +178,7 @@ void apply_extensions(kgma_genome *g, std::vector<kgma_hit> &hits, const std::ve
 // Appends hits (unextended ranges) and, when KGMA_F_ALIGN, the extension requests; *genome_pos carries GenomePos across
 // calls, so a genome can be replayed in record ranges as their run lists become available (pipelined streaming scan).
 int replay_single_range(kgma_ctx *ctx, kgma_genome *g, const ProfTab &t, const kgma_scan_params &P,
-                        const std::vector<kgma_run> &runs, const std::vector<int64_t> &first_D, int r0, int r1,
+                        std::vector<kgma_run> &runs, const std::vector<int64_t> &first_D, int r0, int r1,
                         int64_t *genome_pos_io, std::vector<kgma_hit> &hits, std::vector<AlignReq> &reqs, std::vector<Pending> &pend)
 {
     const int k = t.k; const int64_t ws = t.ws, buff = P.buff;
@@ -191,16 +191,21 @@ int replay_single_range(kgma_ctx *ctx, kgma_genome *g, const ProfTab &t, const k
         const int64_t L = g->recs[r].len;
         size_t b = i; while (i < runs.size() && runs[i].record == r) i++;
         if (L < ws) continue;                             // GenomeMiner.jl:37-39 (genome_pos not advanced)
-        const int64_t steps = (P.only_record >= 0 && r != P.only_record) ? 0 : std::max<int64_t>(0, L - ws);
+        const int64_t steps = (P.only_record >= 0 && r != P.only_record) ? 0 : std::max<int64_t>(0, L - ws - (t.strobe ? 1 : 0));   // StrobeGenomeMiner.jl:45
         if (steps > 0 && i > b) {
             int64_t cur = first_D[r];                     // :57 currminim = kmerDist of the first window
             if (cur == INT64_MIN) return set_err(ctx, KGMA_E_STATE, "first-window distance of record %d missing", r);
             int64_t CMI = 2, goal = 0; bool stop = true;
             for (size_t j = b; j < i; j++) {
-                const kgma_run &ru = runs[j];
+                kgma_run &ru = runs[j];
                 if (ru.flags & KGMA_RUN_MARKER) continue;
                 uint32_t hflags = ru.flags & (KGMA_HIT_NEAR_THR | KGMA_HIT_ARGMIN_TIE);
-                if (ru.D_min < cur) { cur = ru.D_min; CMI = (k - 1) + ru.t_argmin; stop = false; }   // :82-87 CMI = i_left
+                // A run whose minimum EQUALS the minimum the state machine still carries (from the first window or from a run
+                // whose hit goal_ind suppressed: currminim is only reset when a hit is emitted, :100-102) does not lower it here
+                // -- exact repeats in a genome do this.  The reference's Float64 accumulator has drifted by ~1e-13 between the
+                // two windows, so whether ITS `kmerDist < currminim` (:83) fires depends on its rounding history: flag the run.
+                if (ru.D_min == cur) ru.flags |= KGMA_HIT_ARGMIN_TIE;
+                if (ru.D_min < cur) { cur = ru.D_min; CMI = (t.strobe ? 0 : k - 1) + ru.t_argmin; stop = false; }   // :82-87 CMI = i_left (StrobeGMA!: CMI = i)
                 if (ru.t_last >= steps) break;            // run still open at the record end: never emitted (A.1 step 5)
                 if (!stop) {                              // :90-104 at step t_last+1
                     stop = true; CMI += 1;
@@ -254,7 +259,7 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
     auto steps_of = [&](int r) -> int64_t {
         if (P.only_record >= 0 && r != P.only_record) return 0;
         int64_t L = g->recs[r].len;
-        return std::max<int64_t>(0, cluster ? L - maxws - k + 2 : L - maxws);
+        return std::max<int64_t>(0, cluster ? L - maxws - k + 2 : L - maxws - (tabs[0].strobe ? 1 : 0));
     };
 
     std::vector<AlignReq> reqs; std::vector<AlignRes> ares;
@@ -282,6 +287,12 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
                                     want_cig ? &res->cigar_ops : nullptr, want_cig ? &res->cigar_cnt : nullptr);
             if (rc) return rc;
             apply_extensions(g, res->hits, pend, ares);
+        }
+        if (tabs[0].strobe && do_align) {
+            // process_hit! (Alignment.jl): `if aligned_obj.value < score_threshold; return end` -- the hit is dropped AFTER
+            // goal_ind was advanced, so the state machine above is unaffected
+            const int64_t thr_score = P.score_threshold;
+            res->hits.erase(std::remove_if(res->hits.begin(), res->hits.end(), [&](const kgma_hit &h) { return h.align_score < thr_score; }), res->hits.end());
         }
         if (ctx) ctx->stats.n_align = (int64_t)reqs.size();
         return KGMA_OK;
@@ -320,6 +331,8 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
     }
     ev_begin[(size_t)nr] = evs.size();
 
+    const double tr2c = tnow();
+    if (trace) fprintf(stderr, "[kgma replay] cluster: merge %.3f ms, event lists %.3f ms (%zu runs, %zu events)\n", tr1 - tr0, tr2c - tr1, runs.size(), evs.size());
     std::vector<char> have(runs.size(), 0);               // extension result of this run's candidate is known
     std::vector<AlignRes> res_of_run(runs.size());
     if (ext) for (size_t i = 0; i < runs.size(); i++) if ((*ext)[i].lo != 0) { have[i] = 1; res_of_run[i] = AlignRes{ (*ext)[i].lo, (*ext)[i].hi, (*ext)[i].score, 0, 0 }; }
@@ -328,6 +341,7 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
     std::vector<std::vector<kgma_hit>> rec_hits((size_t)nr);   // per record: a record whose pass needed no speculation is final
     std::vector<char> rec_done((size_t)nr, 0);
     for (int round = 0;; round++) {
+        const double trr = tnow();
         missing.clear();
         int64_t genome_pos = 0;
         std::vector<int64_t> cur(C), CMIs(C, 1); std::vector<char> stop(C, 1);
@@ -341,8 +355,9 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
                 int64_t prev_a = 0, prev_b = 0;                                          // :59 prev_hit_range = 0:0
                 for (size_t ei = ev_begin[(size_t)r]; ei < ev_begin[(size_t)r + 1]; ei++) {
                     const Ev &e = evs[ei];
-                    const kgma_run &ru = runs[e.run]; const int q = e.q;
+                    kgma_run &ru = runs[e.run]; const int q = e.q;
                     if (cur[q] == INT64_MIN) return set_err(ctx, KGMA_E_STATE, "first-window distance of record %d profile %d missing", r, q);
+                    if (ru.D_min == cur[q]) ru.flags |= KGMA_HIT_ARGMIN_TIE;            // tie with the carried minimum: see replay_single_range
                     if (ru.D_min < cur[q]) { cur[q] = ru.D_min; CMIs[q] = ru.t_argmin; stop[q] = 0; }   // :114-119 CMI = i
                     if (ru.t_last >= steps) continue;                                   // open at the end of the loop
                     if (stop[q]) continue;
@@ -375,6 +390,7 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
             }
             genome_pos += L;                                                            // :159 - every record
         }
+        if (trace) fprintf(stderr, "[kgma replay] cluster: pass %d took %.3f ms, %zu results missing\n", round, tnow() - trr, missing.size());
         if (missing.empty()) break;                       // no speculation: this pass is the reference's result
         if (!ctx) return set_err(ctx, KGMA_E_STATE, "%zu runs emit hits but carry no extension result (host-only replay)", missing.size());
         if (round >= 3) {                                 // stop chasing: extend every terminated run that is still unknown

@@ -274,6 +274,7 @@ struct EvalArgs {
     kgma_run *runs; uint32_t run_cap; uint32_t *run_count;
     long long *first_D;             // [C][nrec]
     long long *dists; long long dist_stride;
+    const uint16_t *cmap; uint32_t xmask;   // strobemer mode: code of every (xmask+1)-entry base pattern (null: the k-mer itself is the code)
 };
 
 __device__ __forceinline__ uint32_t kmer_at(const uint32_t *seq, long long gp, uint32_t kmask)
@@ -600,7 +601,12 @@ __device__ __noinline__ RunCarry classify_group(ClsArgs a, int r, int q, long lo
 
 // One launch per profile: k and the profile's constants are compile-time / direct kernel parameters, so the slide loop
 // keeps nothing but its own state in registers.
-template <int K, int MAXT>
+// STROBE (StrobeGMA!, StrobeGenomeMiner.jl:45-66): the code of a position is the strobemer code of the bases starting there
+// (a table lookup: MAP[k-mer]), K is the exponent of the code space (4^(2s) codes), and the table the reference tracks is
+// "the nk codes from the window start on plus ONE permanent copy of the code at position nk of the record": its entering code
+// is taken at i+ws-k (:53), the last code of the window that is being left.  Here P.nk is that nk (= ws - k) and the extra code
+// is added when a span's table is built.
+template <int K, int MAXT, bool STROBE = false>
 __global__ void __launch_bounds__(MAXT, 1) kgma_eval(EvalArgs a, ProfDev P, int q)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -613,7 +619,11 @@ __global__ void __launch_bounds__(MAXT, 1) kgma_eval(EvalArgs a, ProfDev P, int 
     constexpr int ESH = STAMP ? 2 : 1;                                     // log2(bytes per entry)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int32_t *sS = reinterpret_cast<int32_t *>(smem_raw);
-    unsigned char *tabb = smem_raw + (size_t)nb * 4 + (size_t)wid * ((size_t)nb << ESH);   // [4^k] entries of this warp
+    const uint32_t xmask = STROBE ? a.xmask : kmask;                        // bits of the base pattern a code is derived from
+    const size_t map_bytes = STROBE ? (((size_t)xmask + 1) * 2 + 15) & ~(size_t)15 : 0;
+    const uint16_t *smap = reinterpret_cast<const uint16_t *>(smem_raw + (size_t)nb * 4);
+    unsigned char *tabb = smem_raw + (size_t)nb * 4 + map_bytes + (size_t)wid * ((size_t)nb << ESH);   // [4^k] entries of this warp
+    auto code_at = [&](long long gp) -> uint32_t { const uint32_t v = kmer_at(a.seq, gp, xmask); return STROBE ? (uint32_t)smap[v] : v; };
     auto cnt_ptr = [&](uint32_t km) { return reinterpret_cast<uint16_t *>(tabb + ((size_t)km << ESH)); };
     for (int i = lane; i < (nb << ESH) / 4; i += 32) reinterpret_cast<uint32_t *>(tabb)[i] = 0;
 
@@ -622,6 +632,7 @@ __global__ void __launch_bounds__(MAXT, 1) kgma_eval(EvalArgs a, ProfDev P, int 
 
     {
         for (int i = threadIdx.x; i < nb; i += blockDim.x) sS[i] = a.S[(size_t)q * nb + i];
+        if (STROBE) for (uint32_t i = threadIdx.x; i <= xmask; i += blockDim.x) const_cast<uint16_t *>(smap)[i] = a.cmap[i];
         __syncthreads();
         const int nk = P.nk;
         ClsArgs ca;
@@ -695,15 +706,18 @@ __global__ void __launch_bounds__(MAXT, 1) kgma_eval(EvalArgs a, ProfDev P, int 
                 if (P.twoN * Amax <= P.R) continue;                            // no window of this span can reach thr for this profile
             }
             // ---- first window of the span: build the table, Q = sum_p c[kmer_p], A = sum_p S[kmer_p]
-            for (int p = lane; p < nk; p += 32) {
-                const uint32_t km = kmer_at(a.seq, gpos + p, kmask);
+            // (strobemer mode: the permanent extra code counts as position nk of the window)
+            const uint32_t zx = STROBE ? code_at(a.recs[r].off + nk) : 0u;
+            const int nel = STROBE ? nk + 1 : nk;
+            for (int p = lane; p < nel; p += 32) {
+                const uint32_t km = (STROBE && p == nk) ? zx : code_at(gpos + p);
                 if (STAMP) atomicAdd(reinterpret_cast<uint32_t *>(tabb) + km, 1u);
                 else atomicAdd(reinterpret_cast<uint32_t *>(tabb) + (km >> 1), 1u << ((km & 1) * 16));
             }
             __syncwarp();
             uint32_t Qb = 0, Ab = 0;                                          // < 2^32: nk <= 65535, nk * max S checked on the host
-            for (int p = lane; p < nk; p += 32) {
-                const uint32_t km = kmer_at(a.seq, gpos + p, kmask);
+            for (int p = lane; p < nel; p += 32) {
+                const uint32_t km = (STROBE && p == nk) ? zx : code_at(gpos + p);
                 Qb += *cnt_ptr(km); Ab += (uint32_t)sS[km];
             }
 #pragma unroll
@@ -734,7 +748,8 @@ __global__ void __launch_bounds__(MAXT, 1) kgma_eval(EvalArgs a, ProfDev P, int 
             auto batch = [&](auto full_c, auto all_c) {
                 constexpr bool FB = decltype(full_c)::value;                   // all 16 steps of the batch are real slides
                 constexpr bool ALL = decltype(all_c)::value;                   // every window goes through the 64-bit path (do_return_dists)
-                const uint32_t x = __funnelshift_r(wlo, whi, sh) & kmask;
+                uint32_t x = __funnelshift_r(wlo, whi, sh) & xmask;
+                if (STROBE) x = smap[x];
                 wlo = whi; whi = __ldg(wp + widx); widx++;
                 const int left = FB ? 16 : ni - 1 - s;
                 const bool valid = FB || j < left;
@@ -785,7 +800,8 @@ __global__ void __launch_bounds__(MAXT, 1) kgma_eval(EvalArgs a, ProfDev P, int 
                 if (s + 1 < ni) batch(std::false_type{}, std::false_type{});
             }
             // ---- return the table to zero: only the k-mers of the last window are still counted
-            for (int p = lane; p < nk; p += 32) *cnt_ptr(kmer_at(a.seq, gpos + n - 1 + p, kmask)) = 0;
+            for (int p = lane; p < nk; p += 32) *cnt_ptr(code_at(gpos + n - 1 + p)) = 0;
+            if (STROBE && lane == 0) *cnt_ptr(zx) = 0;
             __syncwarp();
         }
     }
@@ -864,20 +880,27 @@ static bool ceil_mul_exact(double x, long long m, long long *out)
     return true;
 }
 
-int build_proftab(kgma_ctx *ctx, const kgma_profile &p, ProfTab &t)
+int build_proftab(kgma_ctx *ctx, const kgma_profile &p, ProfTab &t, const kgma_scan_params *P)
 {
     if (p.k < 1 || p.k > MAX_K) return set_err(ctx, KGMA_E_UNSUPPORTED, "k = %d is outside the supported range 1..%d", p.k, MAX_K);
+    const bool strobe = P && P->mode == KGMA_MODE_STROBE;
+    if (strobe) {
+        const int sl = P->strobe_s, a = P->strobe_w_min, b = P->strobe_w_max;
+        if (sl < 1 || sl > 3 || a < 1 || b < a || P->strobe_q < 1 || b + sl - 1 != p.k)
+            return set_err(ctx, KGMA_E_ARG, "strobemer parameters s=%d w_min=%d w_max=%d q=%d do not fit profile.k=%d (k = w_max + s - 1, s <= 3)", sl, a, b, P->strobe_q, p.k);
+    }
+    t.strobe = strobe; t.kb = strobe ? 2 * P->strobe_s : p.k;
     if (!p.S || p.n_refs <= 0) return set_err(ctx, KGMA_E_ARG, "profile needs integer sums S and n_refs > 0");
     if (p.k >= p.window) return set_err(ctx, KGMA_E_WINDOW, "the average reference sequence length %lld exceeds/is equal to the chosen kmer length %d. please reduce k. ", (long long)p.window, p.k);
     if (p.window - p.k + 1 > 60000) return set_err(ctx, KGMA_E_UNSUPPORTED, "window %lld too large for 16-bit count tables", (long long)p.window);
     if (!(p.thr >= 0) || !std::isfinite(p.thr)) return set_err(ctx, KGMA_E_ARG, "threshold must be finite and >= 0");
     t.k = p.k; t.ws = p.window; t.nk = p.window - p.k + 1; t.N = p.n_refs; t.thr = p.thr;
-    size_t nb = (size_t)1 << (2 * p.k);
+    size_t nb = (size_t)1 << (2 * t.kb);
     t.S_rev.assign(nb, 0);
     __int128 s2 = 0;
     for (size_t c = 0; c < nb; c++) {
         if (p.S[c] < 0) return set_err(ctx, KGMA_E_ARG, "negative k-mer sum in profile");
-        t.S_rev[rev_kmer((uint32_t)c, p.k)] = p.S[c];
+        t.S_rev[strobe ? c : rev_kmer((uint32_t)c, p.k)] = p.S[c];
         s2 += (__int128)p.S[c] * p.S[c];
     }
     t.N2 = (int64_t)p.n_refs * p.n_refs; t.twoN = 2LL * p.n_refs;
@@ -903,7 +926,7 @@ int build_proftab(kgma_ctx *ctx, const kgma_profile &p, ProfTab &t)
         auto mixw = [&](uint64_t w) { h ^= w; h *= 1099511628211ull; h ^= h >> 29; };
         for (size_t c = 0; c + 1 < nb; c += 2) mixw(((uint64_t)(uint32_t)t.S_rev[c] << 32) | (uint32_t)t.S_rev[c + 1]);
         if (nb & 1) mixw((uint32_t)t.S_rev[nb - 1]);
-        mixw((uint64_t)t.Thi); mixw((uint64_t)t.N); mixw((uint64_t)t.nk); mixw((uint64_t)t.k);
+        mixw((uint64_t)t.Thi); mixw((uint64_t)t.N); mixw((uint64_t)t.nk); mixw((uint64_t)t.k); mixw((uint64_t)t.kb);
         t.hash = h;
     }
     return KGMA_OK;
@@ -933,7 +956,9 @@ int dev_genome_prepare(kgma_ctx *ctx, kgma_genome *g, bool need_mask)
 // ---------------------------------------------------------------------------------------------
 struct ScanPlan {
     int C = 0, k = 0; int64_t maxws = 0, maxnk = 0;
-    bool cluster = false;
+    int kb = 0;                    // code space 4^kb (= k except in strobemer mode)
+    bool cluster = false, strobe = false;
+    std::vector<uint16_t> cmap;    // strobemer mode: packed base pattern of k bases (first base in the low bits) -> code
     std::vector<ProfTab> tabs;
     // per record: number of loop steps (0 = record not scanned) — GenomeMiner.jl:60 / OmnGenomeMiner.jl:89
     std::vector<int64_t> steps;
@@ -942,16 +967,34 @@ struct ScanPlan {
 static int make_plan(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int C, const kgma_scan_params &P, ScanPlan &pl)
 {
     if (!profiles || C < 1 || C > MAX_PROFILES) return set_err(ctx, KGMA_E_ARG, "n_profiles must be 1..%d", MAX_PROFILES);
-    if (P.mode == KGMA_MODE_SINGLE && C != 1) return set_err(ctx, KGMA_E_ARG, "single mode takes exactly one profile");
-    pl.C = C; pl.k = profiles[0].k; pl.cluster = (P.mode == KGMA_MODE_CLUSTER);
+    if ((P.mode == KGMA_MODE_SINGLE || P.mode == KGMA_MODE_STROBE) && C != 1) return set_err(ctx, KGMA_E_ARG, "single / strobemer mode takes exactly one profile");
+    if (P.mode != KGMA_MODE_SINGLE && P.mode != KGMA_MODE_CLUSTER && P.mode != KGMA_MODE_STROBE) return set_err(ctx, KGMA_E_ARG, "unknown mode %d", P.mode);
+    pl.C = C; pl.k = profiles[0].k; pl.cluster = (P.mode == KGMA_MODE_CLUSTER); pl.strobe = (P.mode == KGMA_MODE_STROBE);
+    if (pl.strobe && (P.only_record >= 0 || (P.flags & KGMA_F_TIE_OPEN))) return set_err(ctx, KGMA_E_UNSUPPORTED, "strobemer mode scans whole genomes with the default tie rule");
     pl.tabs.resize(C);
     for (int q = 0; q < C; q++) {
         if (profiles[q].k != pl.k) return set_err(ctx, KGMA_E_ARG, "all profiles must share k");
-        int rc = build_proftab(ctx, profiles[q], pl.tabs[q]);
+        int rc = build_proftab(ctx, profiles[q], pl.tabs[q], &P);
         if (rc) return rc;
         pl.maxws = std::max(pl.maxws, pl.tabs[q].ws);
     }
+    pl.kb = pl.tabs[0].kb;
     pl.maxnk = pl.maxws - pl.k + 1;
+    if (pl.strobe) {
+        // get_strobe_2_mer (Strobemers.jl:45-65) for every pattern of k bases: the first strobe is bases 1..s; the running
+        // minimum of randstrobe_score = (as_UInt(first) + as_UInt(candidate)) % q starts at `2 << 63` == 0 and is updated on
+        // `<=`, so the second strobe starts at the LAST i in w_min..w_max whose score is 0, else at w_min; the code is
+        // as_UInt(first * second), first base most significant.
+        const int sl = P.strobe_s, a = P.strobe_w_min, b = P.strobe_w_max, qq = P.strobe_q, k = pl.k;
+        pl.cmap.assign((size_t)1 << (2 * k), 0);
+        for (uint32_t pat = 0; pat < pl.cmap.size(); pat++) {
+            auto smer = [&](int i1) { uint32_t v = 0; for (int j = 0; j < sl; j++) v = (v << 2) | ((pat >> (2 * (i1 - 1 + j))) & 3u); return v; };
+            const uint32_t f = smer(1);
+            int min_ind = a;
+            for (int i = a; i <= b; i++) if ((f + smer(i)) % (uint32_t)qq == 0) min_ind = i;
+            pl.cmap[pat] = (uint16_t)((f << (2 * sl)) | smer(min_ind));
+        }
+    }
     if (pl.cluster && pl.k < 2) return set_err(ctx, KGMA_E_UNSUPPORTED, "cluster mode needs k >= 2 (the reference indexes past the record end for k = 1)");
     int nr = (int)g->recs.size();
     pl.steps.assign(nr, 0);
@@ -959,6 +1002,7 @@ static int make_plan(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles
         if (P.only_record >= 0 && r != P.only_record) continue;
         int64_t L = g->recs[r].len;
         int64_t st = pl.cluster ? (L - pl.maxws - pl.k + 2)       // view(seq, k:L-maxws+1)  OmnGenomeMiner.jl:89
+                   : pl.strobe  ? (L - pl.maxws - 1)                // 1:(L-ws-1)              StrobeGenomeMiner.jl:45
                                 : (L - pl.maxws);                   // zip(k:L-ws+k-1, ws+1:L) GenomeMiner.jl:60
         pl.steps[r] = std::max<int64_t>(0, st);
     }
@@ -1054,6 +1098,12 @@ static void launch_filter_k(int k, const FilterArgs &fa, int grid, cudaStream_t 
     }
 }
 
+template <int K> static void launch_eval_strobe(const EvalArgs &ea, const ProfDev &P, int q, int grid, int threads, size_t smem, cudaStream_t st)
+{
+    cudaFuncSetAttribute(kgma_eval<K, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kgma_eval<K, 512, true><<<grid, threads, smem, st>>>(ea, P, q);
+}
+
 template <int K> static void launch_eval_t(const EvalArgs &ea, const ProfDev &P, int q, int grid, int threads, size_t smem, cudaStream_t st)
 {
     if (threads > 512) {       // more than 16 warps per CTA: the 85-register build
@@ -1067,6 +1117,12 @@ template <int K> static void launch_eval_t(const EvalArgs &ea, const ProfDev &P,
 
 static void launch_eval_k(int k, const EvalArgs &ea, const ProfDev &P, int q, int grid, int threads, size_t smem, cudaStream_t st)
 {
+    if (ea.cmap) {                 // strobemer codes: 4^(2s) bins, s = 1..3
+        if (k == 2) launch_eval_strobe<2>(ea, P, q, grid, threads, smem, st);
+        else if (k == 4) launch_eval_strobe<4>(ea, P, q, grid, threads, smem, st);
+        else launch_eval_strobe<6>(ea, P, q, grid, threads, smem, st);
+        return;
+    }
     switch (k) {
     case 1: launch_eval_t<1>(ea, P, q, grid, threads, smem, st); break; case 2: launch_eval_t<2>(ea, P, q, grid, threads, smem, st); break;
     case 3: launch_eval_t<3>(ea, P, q, grid, threads, smem, st); break; case 4: launch_eval_t<4>(ea, P, q, grid, threads, smem, st); break;
@@ -1098,16 +1154,18 @@ static double now_ms()
 }
 
 // warps per CTA and dynamic shared memory of kgma_eval for this k
-static int eval_shape(const kgma_ctx *ctx, int k, bool serial, int *warps_out, size_t *smem_out)
+static int eval_shape(const kgma_ctx *ctx, int k, bool serial, int *warps_out, size_t *smem_out, size_t map_bytes = 0)
 {
     const size_t nb = (size_t)1 << (2 * k);
+    map_bytes = (map_bytes + 15) & ~(size_t)15;                    // strobemer mode: the code map sits between S and the count tables
     // one 4^k x u16 count table per warp, next to the profile's S table (the serial kernel adds its 64-step staging arrays)
     const size_t per_warp = serial ? nb * 2 + 64 * 4 + 64 * 4 + 64 * 8 : nb * (k <= 6 ? 4 : 2);
-    if (ctx->smem_optin < nb * 4 + per_warp) return KGMA_E_UNSUPPORTED;
+    if (ctx->smem_optin < nb * 4 + map_bytes + per_warp) return KGMA_E_UNSUPPORTED;
     int wmax = serial ? 16 : 24;
     if (const char *e = getenv("KGMA_EVAL_WARPS")) wmax = std::max(1, std::min(24, atoi(e)));
-    int w = (int)std::min<size_t>((ctx->smem_optin - nb * 4) / per_warp, (size_t)wmax);
-    *warps_out = w; *smem_out = nb * 4 + (size_t)w * per_warp;
+    if (map_bytes) wmax = std::min(wmax, 16);                       // (the strobemer build of the kernel is the 512-thread one)
+    int w = (int)std::min<size_t>((ctx->smem_optin - nb * 4 - map_bytes) / per_warp, (size_t)wmax);
+    *warps_out = w; *smem_out = nb * 4 + map_bytes + (size_t)w * per_warp;
     return KGMA_OK;
 }
 
@@ -1172,7 +1230,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     kgma_stats &st = ctx->stats; st = kgma_stats{};
     const int nr = (int)g->recs.size();
     const bool want_dists = (P.flags & KGMA_F_WANT_DISTS) != 0;
-    const bool force_dense = (P.flags & KGMA_F_DENSE) != 0 || want_dists;
+    const bool force_dense = (P.flags & KGMA_F_DENSE) != 0 || want_dists || pl.strobe;   // (strobemer codes: no lower-bound table; 4^(2s) bins are all populated)
 
     // ---- shard range in 64-base blocks (whole warp groups)
     const int64_t nblk_total = g->G / FBLOCK;
@@ -1221,10 +1279,10 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
 
     int ewarps = 0; size_t esmem = 0;
     const char *ek_env = getenv("KGMA_EVAL_KERNEL");
-    const bool eval_serial = ek_env && !strcmp(ek_env, "serial");
-    rc = eval_shape(ctx, pl.k, eval_serial, &ewarps, &esmem);
+    const bool eval_serial = ek_env && !strcmp(ek_env, "serial") && !pl.strobe;
+    rc = eval_shape(ctx, pl.kb, eval_serial, &ewarps, &esmem, pl.strobe ? pl.cmap.size() * 2 : 0);
     if (rc) return set_err(ctx, rc, "k = %d does not fit the shared-memory count tables", pl.k);
-    const size_t nb = (size_t)1 << (2 * pl.k);
+    const size_t nb = (size_t)1 << (2 * pl.kb);
     const int egrid = ctx->num_sms;
     const int64_t total_warps = (int64_t)egrid * ewarps;
 
@@ -1258,7 +1316,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     const uint32_t run_head = C == 1 ? 4096 : 32768;
     size_t o = 0;
     auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
-    const size_t o_S = carve((size_t)C * nb * 4), o_recs = carve(recs.size() * sizeof(RecDev));
+    const size_t o_S = carve((size_t)C * nb * 4), o_recs = carve(recs.size() * sizeof(RecDev)), o_cmap = carve(pl.cmap.size() * 2);
     const size_t o_seed = carve((seeds.size() + 1) * 4);
     for (FilterGroup &fg : groups) if (!fg.dense) fg.o_tab = carve(fg.ft->nine ? (size_t)TAB9_BYTES : (size_t)65536 * 2);
     const size_t up_bytes = o;                                     // everything above is uploaded from the staging block
@@ -1276,6 +1334,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     if (rc) return rc;
     unsigned char *hs = (unsigned char *)hsv, *hback = hs + up_bytes, *hbackA = hback + back_bytes;
     for (int q = 0; q < C; q++) memcpy(hs + o_S + (size_t)q * nb * 4, pl.tabs[q].S_rev.data(), nb * 4);
+    if (pl.strobe) memcpy(hs + o_cmap, pl.cmap.data(), pl.cmap.size() * 2);
     for (const FilterGroup &fg : groups) if (!fg.dense) { if (fg.ft->nine) memcpy(hs + fg.o_tab, fg.ft->tab9.data(), TAB9_BYTES); else memcpy(hs + fg.o_tab, fg.ft->tab.data(), 65536 * 2); }
     memcpy(hs + o_recs, recs.data(), recs.size() * sizeof(RecDev));
     if (!seeds.empty()) memcpy(hs + o_seed, seeds.data(), seeds.size() * 4);
@@ -1343,15 +1402,16 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     // ---- count-table kernel over the candidate lists (read on the device) or over everything
     EvalArgs ea{};
     ea.seq = ctx->d_seq2; ea.S = (const int32_t *)(ds + o_S);
+    ea.cmap = pl.strobe ? (const uint16_t *)(ds + o_cmap) : nullptr; ea.xmask = pl.strobe ? (uint32_t)pl.cmap.size() - 1 : 0;
     ea.cand_cap = cand_cap; ea.n_seed = (uint32_t)seeds.size();
     ea.next_item = (unsigned long long *)(d_counters + 32);        // bytes 128.. of the zeroed counter block
     ea.recs = (const RecDev *)(ds + o_recs); ea.nrec = nr;
     ea.cand_blk_lo = 0; ea.cand_blk_hi = LLONG_MAX;
-    ea.C = C; ea.k = pl.k; ea.span = span;
+    ea.C = C; ea.k = pl.kb; ea.span = span;
     for (int q = 0; q < C; q++) {
         const ProfTab &t = pl.tabs[q];
         ea.prof[q].N2 = t.N2; ea.prof[q].twoN = t.twoN; ea.prof[q].sumS2 = t.sumS2;
-        ea.prof[q].T = t.T; ea.prof[q].Tlo = t.Tlo; ea.prof[q].Thi = t.Thi; ea.prof[q].nk = (int)t.nk; ea.prof[q].N = t.N;
+        ea.prof[q].T = t.T; ea.prof[q].Tlo = t.Tlo; ea.prof[q].Thi = t.Thi; ea.prof[q].nk = (int)t.nk - (t.strobe ? 1 : 0); ea.prof[q].N = t.N;   // (strobemers: nk - 1 sliding codes + the permanent one)
         {   // D < Thi  <=>  N (N Q - 2 A) < Thi - sum S^2  <=>  N Q - 2 A < ceil((Thi - sum S^2) / N); everything must fit 31 bits
             int64_t maxS = 0; for (int32_t v : t.S_rev) maxS = std::max<int64_t>(maxS, v);
             const __int128 umax = (__int128)t.N * t.nk * t.nk + 2 * (__int128)t.nk * maxS;
@@ -1375,7 +1435,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
         if (dense_items) { ea.cand = nullptr; ea.cand_count = nullptr; ea.bitmap = nullptr; ea.n_items = n_items; }
         else { ea.cand = (const uint32_t *)(ds + fg->o_cand); ea.cand_count = d_counters + 1 + gi; ea.bitmap = (const uint32_t *)(ds + fg->o_bits); ea.n_items = 0; }
         if (eval_serial) { kgma_eval_serial<<<egrid, ewarps * 32, esmem, sc_>>>(ea); st.launches++; }
-        else for (int q : qs) { launch_eval_k(pl.k, ea, ea.prof[q], q, egrid, ewarps * 32, esmem, sc_); st.launches++; }
+        else for (int q : qs) { launch_eval_k(pl.kb, ea, ea.prof[q], q, egrid, ewarps * 32, esmem, sc_); st.launches++; }
         KGMA_CUDA(ctx, cudaGetLastError());
         return KGMA_OK;
     };
@@ -1638,7 +1698,8 @@ int kgma_scan_shard(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles,
             if (ru.flags & KGMA_RUN_MARKER) continue;
             if (ru.t_last >= pl.steps[(size_t)ru.record]) continue;          // reaches the record's last step: never emitted
             const int64_t L = g->recs[(size_t)ru.record].len, wsq = pl.tabs[(size_t)ru.profile].ws;
-            const int64_t CMI = pl.cluster ? ru.t_argmin : (int64_t)pl.k + ru.t_argmin;   // OmnGenomeMiner.jl:117 / GenomeMiner.jl:85,92
+            const int64_t CMI = pl.cluster ? ru.t_argmin : pl.strobe ? ru.t_argmin + 1    // OmnGenomeMiner.jl:117 / StrobeGenomeMiner.jl:73,79
+                                           : (int64_t)pl.k + ru.t_argmin;                  // GenomeMiner.jl:85,92
             reqs.push_back({ ru.record, ru.profile, std::max<int64_t>(CMI - P.buff, 1), std::min<int64_t>(CMI + wsq - 1 + P.buff, L), align_hint(ru.D_min, pl.tabs[(size_t)ru.profile].T) });
             of_run.push_back(i);
         }
@@ -1751,7 +1812,7 @@ int kgma_scan(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int n
     PhaseHook hook;
     const int nr = (int)g->recs.size();
     const bool cluster = P.mode == KGMA_MODE_CLUSTER;
-    const bool can_pipeline = g->sealed && (cluster || n_profiles == 1) && (P.flags & KGMA_F_ALIGN) && P.only_record < 0 &&
+    const bool can_pipeline = g->sealed && P.mode != KGMA_MODE_STROBE && (cluster || n_profiles == 1) && (P.flags & KGMA_F_ALIGN) && P.only_record < 0 &&
                               !(P.flags & (KGMA_F_DENSE | KGMA_F_WANT_DISTS | KGMA_F_WANT_CIGARS)) && nr >= 2 && !getenv("KGMA_NO_PIPELINE");
     if (can_pipeline) {
         // single mode queues one extension batch per part, so the first part should be as large as possible: split in front

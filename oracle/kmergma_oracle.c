@@ -590,6 +590,158 @@ int orc_ac_gma(const orc_fasta *g, const double *RV, const char *cons, int cons_
     return rc;
 }
 
+/* ------------------------------------------------------------------ */
+/* Experimental strobemer path, src/StrobemerGMA/.  PARITY UNPINNED for the scan itself: the reference's tests
+ * (test-StrobemerGMA.jl) pin randstrobe_score, get_strobe_2_mer and ungapped_strobe_2_mer_count only; StrobeGMA! /
+ * Strobemer_findGenes have no test and no golden.  What follows restates them line by line from those pinned pieces.
+ *
+ * Strobemers.jl:12-14 randstrobe_score = (as_UInt(s1) + as_UInt(s2)) % q.
+ * Strobemers.jl:45-65 get_strobe_2_mer(seq[1:k], s, w_min, w_max, q): first strobe seq[1:s]; the running minimum is seeded
+ * with `2 << 63`, which is 0 in Int64, and updated on `<=`: the second strobe starts at the LAST i in w_min..w_max whose
+ * score is 0, else at w_min.  Returns as_UInt(first * second) (the gap-free strobemer, first base most significant). */
+static int strobe_code(const char *s, int sl, int wmin, int wmax, int q, uint64_t *out)
+{
+    uint64_t f = 0;
+    for (int i = 0; i < sl; i++) { int b = nt_bits(s[i]); if (b < 0) return ORC_E_SYMBOL; f = (f << 2) | (uint64_t)b; }
+    int64_t min_score = 0; int min_ind = wmin;                       /* 2 << 63 == 0 */
+    for (int i = wmin; i <= wmax; i++) {
+        uint64_t v = 0;
+        for (int j = 0; j < sl; j++) { int b = nt_bits(s[i - 1 + j]); if (b < 0) return ORC_E_SYMBOL; v = (v << 2) | (uint64_t)b; }
+        int64_t cur = (int64_t)((f + v) % (uint64_t)q);
+        if (cur <= min_score) { min_score = cur; min_ind = i; }
+    }
+    uint64_t v = 0;
+    for (int j = 0; j < sl; j++) v = (v << 2) | (uint64_t)nt_bits(s[min_ind - 1 + j]);
+    *out = (f << (2 * sl)) | v;
+    return ORC_OK;
+}
+
+/* Strobemers.jl:105-115 ungapped_strobe_2_mer_count!: bins[code of every k = w_max+s-1 window] += 1 */
+int orc_strobe_count_add(const char *s, int64_t len, int sl, int wmin, int wmax, int q, double *bins)
+{
+    int k = wmax + sl - 1;
+    for (int64_t i = 0; i + k <= len; i++) {
+        uint64_t c; int rc = strobe_code(s + i, sl, wmin, wmax, q, &c);
+        if (rc) return rc;
+        bins[c] += 1.0;
+    }
+    return ORC_OK;
+}
+
+/* StrobeRefGen.jl:4-42 gen_ref_ws_cons(refs; s, w_min, w_max, q): 2 << (4s - 1) = 4^(2s) bins */
+int orc_strobe_gen_ref_ws_cons(const orc_fasta *refs, int sl, int wmin, int wmax, int q, double *rv, int64_t *ws,
+                               char *consensus, int64_t *maxlen_out)
+{
+    size_t nb = (size_t)1 << (4 * sl);
+    memset(rv, 0, nb * sizeof(double));
+    int64_t cum = 0, maxlen = 0; int len = 0;
+    orc_profile p; profile_init(&p, 1);
+    for (int r = 0; r < refs->n; r++) {
+        len += 1; cum += refs->len[r]; if (refs->len[r] > maxlen) maxlen = refs->len[r];
+        int rc = orc_strobe_count_add(refs->seq[r], refs->len[r], sl, wmin, wmax, q, rv);
+        if (rc) { profile_free(&p); return rc; }
+        profile_lengthen(&p, refs->len[r]);
+        rc = profile_add(&p, refs->seq[r], refs->len[r]);
+        if (rc) { profile_free(&p); return rc; }
+    }
+    double inv = 1.0 / (double)len;
+    for (size_t i = 0; i < nb; i++) rv[i] = rv[i] * inv;
+    *ws = (int64_t)nearbyint((double)cum * inv);
+    if (consensus) profile_consensus(&p, consensus);
+    if (maxlen_out) *maxlen_out = p.len > maxlen ? p.len : maxlen;
+    profile_free(&p);
+    return ORC_OK;
+}
+
+/* StrobeGenomeMiner.jl:5-95 StrobeGMA!  (Strobemer_findGenes :119-158 calls it with ScaleFactor = 1/(w_max+s-1)).
+ * Differences from ac_gma_testing!: codes are strobemer codes; the loop runs i = 1 .. L-ws-1 (:49); the ENTERING code is the
+ * one at i+ws-k (:55), i.e. the last code of the window that is being left, so the tracked table is "the ws-k codes from i+1
+ * on, plus a permanent copy of the first window's last code"; CMI = i (:79); a hit whose alignment scores below
+ * score_threshold is dropped after goal_ind was advanced (Alignment.jl process_hit!). */
+int orc_strobe_gma(const orc_fasta *g, const double *RV, const char *cons, int cons_len,
+                   int sl, int wmin, int wmax, int q, int64_t ws, double thr, int64_t buff, int do_align,
+                   int gap_open, int gap_extend, int prefer_extend, int64_t score_threshold,
+                   orc_hit *hits, int64_t hit_cap, int64_t *nhits,
+                   double *dist_out, int64_t dist_cap, int64_t *ndist)
+{
+    const int k = wmax + sl - 1;
+    size_t nb = (size_t)1 << (4 * sl);
+    double SF = 1.0 / (double)k;                                   /* :139 ScaleFactor = 1/(w_max+s-1) */
+    double *cf = (double *)calloc(nb, sizeof(double));
+    int64_t genome_pos = 0, nh = 0, nd = 0; int rc = ORC_OK;
+    const int exact = g_exact_n > 0;
+    double EN = 0, Eden = 1, thr_eff = thr, *ES = NULL;
+    if (exact) {
+        EN = (double)g_exact_N[0]; Eden = 2.0 * (double)k * EN * EN;
+        thr_eff = (double)ceil_times(thr, (int64_t)Eden);
+        ES = (double *)malloc(nb * sizeof(double));
+        for (size_t i = 0; i < nb; i++) ES[i] = (double)llround(RV[i] * EN);
+    }
+    for (int r = 0; r < g->n && rc == ORC_OK; r++) {
+        const char *s = g->seq[r]; int64_t L = g->len[r];
+        if (L < ws) continue;                                      /* :33 */
+        memset(cf, 0, nb * sizeof(double));
+        rc = orc_strobe_count_add(s, ws, sl, wmin, wmax, q, cf);   /* :36-38 */
+        if (rc) break;
+        double d = (1.0 / (double)(2 * k)) * sqeuclidean(RV, cf, nb);   /* :40 */
+        if (exact) { d = 0; for (size_t i = 0; i < nb; i++) { double x = EN * cf[i] - ES[i]; d += x * x; } }
+        int64_t CMI = 2, goal = 0; int stop = 1; double cur = d;   /* :43 */
+        for (int64_t i = 1; i <= L - ws - 1; i++) {                /* :45 */
+            uint64_t lk, rk;
+            rc = strobe_code(s + (i - 1), sl, wmin, wmax, q, &lk);             /* :47-49 view(seq, i:i+k-1) */
+            if (!rc) rc = strobe_code(s + (i + ws - k - 1), sl, wmin, wmax, q, &rk);   /* :52-54 view(seq, i+ws-k:i+ws) */
+            if (rc) break;
+            if (lk != rk) {                                        /* :57-65 */
+                double x = 1.0 + cf[rk];
+                if (exact) d += 2.0 * EN * (EN * (x - cf[lk]) + ES[lk] - ES[rk]);
+                else { x = x + RV[lk]; x = x - RV[rk]; x = x - cf[lk]; d += SF * x; }
+                cf[lk] -= 1.0; cf[rk] += 1.0;
+            }
+            if (dist_out) { if (nd >= dist_cap) { rc = ORC_E_CAP; break; } dist_out[nd] = exact ? d / Eden : d; }
+            nd++;
+            if (d < thr_eff) {                                     /* :70-75 */
+                if (d < cur) { cur = d; CMI = i; stop = 0; }
+            } else if (!stop) {                                    /* :78-88 */
+                stop = 1; CMI += 1;
+                if (CMI > goal) {
+                    goal = CMI + ws - 1;
+                    int64_t a = CMI - buff; if (a < 1) a = 1;
+                    int64_t b = CMI + ws - 1 + buff; if (b > L) b = L;
+                    int keep = 1;
+                    if (do_align) {                                /* Alignment.jl process_hit! */
+                        int n = (int)(b - a + 1), cap = (int)ws + n + 2;
+                        char *ops = (char *)malloc((size_t)cap); int32_t *cnt = (int32_t *)malloc((size_t)cap * sizeof(int32_t));
+                        int64_t score = 0;
+                        int nops = orc_semiglobal(cons, (int)ws, s + (a - 1), n, gap_open, gap_extend, prefer_extend, ops, cnt, cap, &score);
+                        if (nops < 0) { free(ops); free(cnt); rc = nops; break; }
+                        if (score < score_threshold) keep = 0;
+                        else {
+                            int64_t lo, hi; orc_cigar_to_unitrange(cnt, nops, &lo, &hi);
+                            int64_t na = a + lo - 1; if (na < 1) na = 1;
+                            int64_t nbb = a + hi - 1; if (nbb > L) nbb = L;
+                            if (nbb < na - 1) nbb = na - 1;
+                            a = na; b = nbb;
+                        }
+                        free(ops); free(cnt);
+                    }
+                    if (keep) {
+                        if (nh >= hit_cap) { rc = ORC_E_CAP; break; }
+                        orc_hit *h = &hits[nh++];
+                        h->record = r; h->kfv = 0; h->dist = exact ? cur / Eden : cur; h->first = a; h->last = b;
+                        h->genome_pos = genome_pos; h->cmi = CMI;
+                    }
+                    cur = d;                                       /* :87 (after process_hit!, kept or not) */
+                }
+            }
+        }
+        genome_pos += L;                                           /* :91 */
+    }
+    (void)cons_len;
+    free(cf); free(ES);
+    *nhits = nh; if (ndist) *ndist = nd;
+    return rc;
+}
+
 /* src/OmnGenomeMiner.jl:7-162 Omn_KmerGMA!  — C profiles; count tables are Float64 (:46);
  * prev_hit_range shared by all profiles, reset per record (:59).
  * cons: C strings at stride cons_stride; the WHOLE consensus_seqs[ind] is aligned (:131). */

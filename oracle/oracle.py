@@ -92,6 +92,12 @@ def lib():
         L.orc_ac_gma_seq.restype = C.c_int64
         L.orc_ac_gma_seq.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_double,
                                      C.c_int64, C.c_void_p, C.c_int64]
+        L.orc_strobe_count_add.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_strobe_gen_ref_ws_cons.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64),
+                                                 C.c_char_p, C.POINTER(C.c_int64)]
+        L.orc_strobe_gma.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                     C.c_double, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                     C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.orc_set_exact.restype = None
         L.orc_set_exact.argtypes = [C.c_int, C.c_void_p]
         L.orc_synth.restype = None
@@ -409,6 +415,52 @@ def record_KmerGMA(genome, record: int, refVec, consensus_refseq, **kw):
     kw.setdefault("thr", 30)
     hits, _, _ = ac_gma_testing(genome, refVec, consensus_refseq, only_record=record, **kw)
     return hits
+
+
+# ---------------------------------------------------------------- StrobemerGMA/ (experimental; scan unpinned by the reference)
+def ungapped_strobe_2_mer_count(seq, s: int = 2, w_min: int = 3, w_max: int = 5, q: int = 5) -> np.ndarray:
+    """Strobemers.jl:90-103"""
+    b = _b(seq)
+    bins = np.zeros(4 ** (2 * s), dtype=np.float64)
+    _check(lib().orc_strobe_count_add(b, len(b), s, w_min, w_max, q, bins.ctypes.data), "ungapped_strobe_2_mer_count")
+    return bins
+
+
+def strobe_gen_ref_ws_cons(refs, s: int = 2, w_min: int = 3, w_max: int = 5, q: int = 5):
+    """StrobeRefGen.jl:4-42 -> (RV, windowsize, consensus)"""
+    f = refs if isinstance(refs, Fasta) else Fasta(refs)
+    rv = np.zeros(4 ** (2 * s), dtype=np.float64)
+    ws = C.c_int64()
+    ml = C.c_int64()
+    cap = max(f.seqsize(r) for r in range(len(f))) + 1
+    cons = C.create_string_buffer(cap + 1)
+    _check(lib().orc_strobe_gen_ref_ws_cons(f._h, s, w_min, w_max, q, rv.ctypes.data, C.byref(ws), cons, C.byref(ml)), "gen_ref_ws_cons")
+    return rv, ws.value, cons.value.decode()
+
+
+def StrobeGMA(genome, refVec: np.ndarray, consensus_refseq: str, s: int = 2, w_min: int = 3, w_max: int = 5, q: int = 5,
+              windowsize: int = 289, thr: float = 33.5, buff: int = 50, do_align: bool = True,
+              gap_open_score: int = -69, gap_extend_score: int = -5, score_threshold: int = 0,
+              do_return_dists: bool = False, prefer_extend: bool = True, hit_cap: int = 1 << 20):
+    """StrobeGenomeMiner.jl:5-95 (ScaleFactor = 1/(w_max+s-1) as Strobemer_findGenes passes it).
+    Returns (hits, hit_loci_vec, dist_vec|None)."""
+    f = genome if isinstance(genome, Fasta) else Fasta(genome)
+    rv = np.ascontiguousarray(refVec, dtype=np.float64)
+    assert rv.size == 4 ** (2 * s)
+    arr = (_Hit * hit_cap)()
+    nh, nd = C.c_int64(), C.c_int64()
+    dist, dcap = None, 0
+    if do_return_dists:
+        dcap = sum(max(0, f.seqsize(r) - windowsize - 1) for r in range(len(f)))
+        dist = np.zeros(max(dcap, 1), dtype=np.float64)
+    cons = _b(consensus_refseq)
+    rc = lib().orc_strobe_gma(f._h, rv.ctypes.data, cons, len(cons), s, w_min, w_max, q, windowsize, float(thr), buff, int(do_align),
+                              gap_open_score, gap_extend_score, int(prefer_extend), C.c_int64(score_threshold),
+                              arr, hit_cap, C.byref(nh), dist.ctypes.data if dist is not None else None, dcap, C.byref(nd))
+    _check(rc, "StrobeGMA!")
+    hits = _hits(f, arr, nh.value)
+    loci = [h.first + h.genome_pos for h in hits]
+    return hits, loci, (dist[:nd.value] if dist is not None else None)
 
 
 # ---------------------------------------------------------------- OmnGenomeMiner.jl

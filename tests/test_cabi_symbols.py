@@ -192,6 +192,34 @@ def test_strobemer_utility_goldens():
     assert counts[3] == 2 and counts[4] == counts[11] == counts[14] == 1
 
 
+def test_strobemer_profile_and_oracle_pieces():
+    """the strobemer path's building blocks: the oracle's restatement and the library's native profile generator
+    (kgma_refs_strobe_profile, StrobeRefGen.jl:4-42) against the host mirror of the utilities the reference's tests pin
+    (get_strobe_2_mer / ungapped_strobe_2_mer_count, test-StrobemerGMA.jl:1-18), for several (s, w_min, w_max, q)"""
+    import kmergma_jl_b200 as K
+    from oracle import oracle as O
+    assert np.array_equal(O.ungapped_strobe_2_mer_count("ATGCATGC", 1, 2, 4), K.ungapped_strobe_2_mer_count("ATGCATGC", s=1, w_min=2, w_max=4))
+    rng = np.random.default_rng(3)
+    refs = O.Fasta(TF)
+    for args in ((2, 3, 5, 5), (1, 2, 4, 5), (3, 4, 5, 7), (2, 3, 5, 7), (2, 4, 6, 3)):
+        for _ in range(12):
+            s_ = "".join(np.asarray(list("ACGTN"))[rng.integers(0, 5, size=int(rng.integers(args[2] + args[0] - 1, 80)))])
+            assert np.array_equal(O.ungapped_strobe_2_mer_count(s_, *args), K.ungapped_strobe_2_mer_count(s_, *args)), (s_, args)
+        RV, ws, cons = K.strobe_gen_ref_ws_cons(TF, *args)
+        orv, ows, ocons = O.strobe_gen_ref_ws_cons(TF, *args)
+        assert ws == ows == 289 and cons == ocons and np.array_equal(np.asarray(RV), orv) and RV.n_refs == 84
+        tot = sum(K.ungapped_strobe_2_mer_count(refs.seq(r), *args) for r in range(len(refs)))
+        assert np.array_equal(np.asarray(RV.S, dtype=np.float64), tot)
+    # the scan on the one-record fixture: the same three loci findGenes reports there (test-KmerGMA.jl:257-263)
+    RV, ws, cons = O.strobe_gen_ref_ws_cons(TF)
+    hits, loci, d = O.StrobeGMA(MINI_GENOME, RV, cons, windowsize=ws, thr=30, do_return_dists=True)
+    assert [(h.first, h.last) for h in hits] == [(6852, 7140), (23907, 24201), (33845, 34133)]
+    assert d.size == O.Fasta(MINI_GENOME).seqsize(0) - ws - 1                # StrobeGenomeMiner.jl:45: 1:(L-ws-1)
+    with O.exact_arithmetic(84):
+        he, _, de = O.StrobeGMA(MINI_GENOME, RV, cons, windowsize=ws, thr=30, do_return_dists=True)
+    assert [(h.first, h.last) for h in he] == [(h.first, h.last) for h in hits] and np.max(np.abs(d - de)) < 1e-9
+
+
 def test_masked_runs_match_numpy(tmp_path):
     """the masked-run list (what the extension / exact-match kernels consult instead of the ambiguity plane) against a
     numpy scan of the same sequences: runs at record starts/ends, one-base runs, runs spanning 32-base mask words, and a

@@ -1369,6 +1369,56 @@ def test_parallel_slide_kernel_equals_serial_kernel(K, O, prof, synth, tmp_path,
         assert len(a.hits) >= 5 and np.array_equal(a.hits[key], b.hits[key])
 
 
+def test_strobemer_scan_vs_oracle(K, O, synth, tmp_path):
+    """StrobeGMA! / Strobemer_findGenes (src/StrobemerGMA/StrobeGenomeMiner.jl; experimental and untested in the reference, so the
+    oracle's line-by-line restatement is the yardstick -- parity unpinned beyond the utilities): hits, headers, sequences and every
+    per-step distance, on the fixture genome, the synthetic genome, records of ws .. ws+3 bases, with and without extension, with
+    an alignment-score threshold, and for other randstrobe parameters (s = 1: 16 codes, s = 3: 4096 codes)"""
+    path, recs = synth
+    rng = np.random.default_rng(12)
+    refs = O.Fasta(TF)
+
+    def rnd(n):
+        return "".join(np.asarray(list("ACGT"))[rng.integers(0, 4, size=n)])
+
+    short = [("exact", refs.seq(0)[:289]), ("plus one", rnd(290)), ("plus two", rnd(291)), ("plus three", refs.seq(5)[:289] + "ACG"),
+             ("shorter", rnd(200)), ("with N", rnd(400) + "N" * 700 + refs.seq(7) + rnd(300)), ("polyA", "A" * 900)]
+    sp = tmp_path / "short.fasta"
+    _write_fasta(sp, short)
+    for args in ((2, 3, 5, 5), (1, 2, 4, 5), (3, 4, 5, 7), (2, 4, 6, 3)):
+        RV, ws, cons = K.strobe_gen_ref_ws_cons(TF, *args)
+        orv = np.asarray(RV)
+        for gpath in (GENOME, path, str(sp)):
+            # a threshold that yields hits for every parameter set: the 2 % quantile of the distances on the small genome
+            _, _, d0 = O.StrobeGMA(MINI_GENOME, orv, cons, *args, windowsize=ws, thr=0, do_align=False, do_return_dists=True)
+            thr = 30.0 if args == (2, 3, 5, 5) else float(np.quantile(d0, 0.02))
+            for do_align, sthr in ((False, 0), (True, 0), (True, 900)):
+                res, loci, dv = [], [], []
+                out = K.StrobeGMA(genome_path=gpath, refVec=RV, consensus_refseq=cons, s=args[0], w_min=args[1], w_max=args[2], q=args[3],
+                                  windowsize=ws, thr=thr, do_align=do_align, score_threshold=sthr, do_return_dists=not do_align,
+                                  get_hit_loci=True, dist_vec=dv, hit_loci_vec=loci, resultVec=res)
+
+                def run():
+                    return O.StrobeGMA(gpath, orv, cons, *args, windowsize=ws, thr=thr, do_align=do_align, score_threshold=sthr,
+                                       do_return_dists=not do_align)
+                with O.exact_arithmetic(RV.n_refs):
+                    oe, _, _ = run()
+                of, oloci, od = run()
+                agreed = check_parity(K, out, oe, of)
+                if agreed is of:
+                    assert descs(res) == [h.description() for h in of] and [r.sequence for r in res] == [h.seq for h in of] and loci == oloci
+                if not do_align:
+                    d = np.asarray(dv)
+                    assert d.shape == od.shape and (d.size == 0 or np.max(np.abs(d - od) / np.maximum(np.abs(od), 1e-300)) <= REL)
+            if gpath == GENOME and args == (2, 3, 5, 5):
+                assert 1 <= len(of) < len(O.StrobeGMA(gpath, orv, cons, *args, windowsize=ws, thr=thr, do_align=True)[0])   # the score threshold drops hits
+    # the API function: Any[hits, loci, dists]
+    outv = K.Strobemer_findGenes(genome_path=GENOME, ref_path=TF, KmerDistThr=30, do_return_hit_loci=True, do_return_dists=True, verbose=False)
+    RV, ws, cons = O.strobe_gen_ref_ws_cons(TF)
+    oh, ol, od = O.StrobeGMA(GENOME, RV, cons, windowsize=ws, thr=30, do_return_dists=True)
+    assert descs(outv[0]) == [h.description() for h in oh] and outv[1] == ol and len(outv[2]) == od.size
+
+
 def test_two_contexts_share_nothing(K, prof, synth):
     """two contexts on the same device, used alternately on different genomes: each keeps its own device planes, tables,
     staging ring and scratch, so neither disturbs the other's resident genome"""
