@@ -797,6 +797,17 @@ def other_configs(K, ctx, g, W, total, RV, ws, cons, peak):
                                           "device_ms": {"count_table": st["exact_ms"]},
                                           "note": "KGMA_F_DENSE: every window through the shared-memory count-table kernel, no prefilter "
                                                   "(what do_return_dists and unfilterable profiles run)"}
+    # the reference's experimental strobemer search (Strobemer_findGenes): same genome, randstrobe profile of the same family,
+    # always the dense count-table pass (256 codes, nothing to filter on)
+    try:
+        SRV, sws, scons = K.strobe_gen_ref_ws_cons(TF)
+        ms, out = timeit(lambda: K.strobe_scan_raw(g, SRV, sws, scons, 20.0, 2, 3, 5, 5, BUFF, L.F_ALIGN | L.F_RESIDENT, GAP_OPEN, -5, ctx=ctx), 2)
+        st = ctx.stats()
+        res["Strobemer_findGenes"] = {"ms_per_step": ms, "value": total / ms / 1e3, "unit": UNIT, "hits": int(len(out.hits)),
+                                      "device_ms": {"count_table": st["exact_ms"], "extension": st["align_ms"]}, "runs": int(st["n_runs"]),
+                                      "note": "KGMA_MODE_STROBE, s=2 w_min=3 w_max=5 q=5, KmerDistThr 20, gap (-69,-5)"}
+    except Exception as e:
+        res["Strobemer_findGenes"] = {"error": str(e)}
     rng = np.random.default_rng(5)
     query = "".join(np.asarray(list("ACGT"))[rng.integers(0, 4, size=300)])
     for i in range(1000):
