@@ -118,14 +118,14 @@ function ints_of(refVec::Vector{Float64})
 end
 
 function scan!(resultVec, hit_loci_vec, dist_vecs, genome_path, refVecs, windowsizes, consensus_seqs, thrs, k, mode, buff,
-               flags, gap_open, gap_extend; cluster::Bool, get_hit_loci::Bool)
+               flags, gap_open, gap_extend; cluster::Bool, get_hit_loci::Bool, strobe = (0, 0, 0, 0), score_threshold::Int = 0)
     ctx = context()
     g = genome(genome_path, ctx)
     Ss = [ints_of(Vector{Float64}(rv)) for rv in refVecs]
     cons = [Vector{UInt8}(string(c)) for c in consensus_seqs]
     GC.@preserve Ss cons begin
         profs = [KgmaProfile(k, Ss[i][2], windowsizes[i], pointer(Ss[i][1]), pointer(cons[i]), length(cons[i]), Float64(thrs[i])) for i in eachindex(Ss)]
-        P = Ref(KgmaScanParams(mode, flags | F_RESIDENT, buff, gap_open, gap_extend, 0, 1, -1, 0, 0, 0, 0, 0, 0))
+        P = Ref(KgmaScanParams(mode, flags | F_RESIDENT, buff, gap_open, gap_extend, 0, 1, -1, 0, strobe..., score_threshold))
         res = Ref{Ptr{Cvoid}}(C_NULL)
         check(ctx, ccall((:kgma_scan, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{KgmaProfile}, Cint, Ref{KgmaScanParams}, Ref{Ptr{Cvoid}}),
                          ctx, g, profs, length(profs), P, res))
@@ -172,6 +172,18 @@ function KmerGMA.Omn_KmerGMA!(; genome_path::String, refVecs, windowsizes, conse
     flags = (align_hits ? F_ALIGN : UInt32(0)) | (do_return_dists ? F_WANT_DISTS : UInt32(0))
     scan!(resultVec, hit_loci_vec, dist_vec_vec, genome_path, refVecs, windowsizes, consensus_seqs, thr_vec, k, 1, buff,
           flags, gap_open_score, gap_extend_score; cluster = true, get_hit_loci = get_hit_loci)
+end
+
+# src/StrobemerGMA/StrobeGenomeMiner.jl:5-95 (KGMA_MODE_STROBE = 2; profile.k = w_max + s - 1, refVec over the 4^(2s) codes)
+function KmerGMA.StrobeGMA!(; genome_path::String, refVec, consensus_refseq, s::Int = 2, w_min::Int = 3, w_max::Int = 5, q::Int = 5,
+        windowsize::Int64 = 289, thr = 33.5, ScaleFactor = nothing, buff::Int64 = 50, do_align::Bool = true,
+        score_model = AffineGapScoreModel(EDNAFULL, gap_open = -69, gap_extend = -5), score_threshold::Int = 0,
+        do_return_dists::Bool = false, do_return_align::Bool = false, get_hit_loci::Bool = false, dist_vec = Float64[],
+        result_align_vec = [], hit_loci_vec = Int[], genome_pos::Int = 0, resultVec = FASTA.Record[])
+    flags = (do_align ? F_ALIGN : UInt32(0)) | (do_return_dists ? F_WANT_DISTS : UInt32(0))
+    scan!(resultVec, hit_loci_vec, [dist_vec], genome_path, [collect(refVec)], [windowsize], [consensus_refseq], [thr], w_max + s - 1, 2, buff,
+          flags, score_model.gap_open, score_model.gap_extend; cluster = false, get_hit_loci = get_hit_loci,
+          strobe = (Int32(s), Int32(w_min), Int32(w_max), Int32(q)), score_threshold = score_threshold)
 end
 
 function KmerGMA.exactMatch(query, genome_path::String; overlap::Bool = true)
