@@ -707,9 +707,11 @@ def run_ours(args):
             limiter = "HBM: one sampled 4-byte word per 32-byte sector of the 2-bit plane"
         else:
             alg_bytes, npass = a_res["blocks_total"] * 64 * 0.25, max(1, int(round(a_res["filter_passes"])))
-            kname = "kgma_prefilter<%d>" % W.k
-            limiter = ("shared-memory wavefronts, not HBM: 3.5 wavefronts per random 32-lane table gather (%d gathers per 64 bases), "
-                       "DESIGN.md 5.1; %d pass(es) over the genome per step (one per group of profiles sharing a weight table)" % (22 if W.k == 6 else 32, npass))
+            nine = os.environ.get("KGMA_PREFILTER") != "8mer"
+            kname = ("kgma_prefilter9<%d>" if nine else "kgma_prefilter<%d>") % W.k
+            limiter = ("shared-memory wavefronts, not HBM: 4.1 wavefronts per random 32-lane table gather (%d gathers per 64 bases), "
+                       "DESIGN.md 5.1; %d pass(es) over the genome per step (one per group of profiles sharing a weight table)"
+                       % ((64 + (10 if nine else 9) - W.k - 1) // ((10 if nine else 9) - W.k), npass))
         # filter_ms spans every prefilter pass of the step: each pass streams the slice once
         achieved = npass * alg_bytes / (filt_ms * 1e-3) / 1e9 if filt_ms > 0 else 0.0
         nh = (sum(len(v) for v in out_res.values()) if isinstance(out_res, dict) else int(out_res)) if exact else int(len(out_res.hits))
@@ -737,8 +739,8 @@ def run_ours(args):
                                      "regions_resident": a_res["region_ms_per_step"], "regions_e2e": a_e2e["region_ms_per_step"],
                                      "note": "each rank's own timed loop before the closing barrier; ms_per_step is the max incl. the barrier"},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": (783.9e6 if (args.scale == 1.0 and W.config == "single" and world == 1) else None),
-                         "traffic_source": "ncu --set full, profiles/ (dram read+write per launch)",
+                         "frac": achieved / peak, "traffic": (784.4e6 if (args.scale == 1.0 and W.config == "single" and world == 1) else None),
+                         "traffic_source": "ncu --set full, profiles/r2_kernels_ncu_full_summary.csv (dram read 780.2 MB + write 4.2 MB per launch of the N=1 default config)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "algorithmic_bytes_per_launch": alg_bytes, "limiter": limiter},
             "clocks": clocks, "clocks_e2e": clocks_e2e,
