@@ -501,8 +501,45 @@ def run_ours(args):
 
     xch = Exchange() if world > 1 else None
 
+    # N > 1, two ways to cut the one genome (north_star: "by contig/chunk with window-length halo overlap"):
+    #  contigs  whole records per rank (longest-first assignment): every rank runs the ordinary kgma_scan on its records -- its own
+    #           replay, exactly the reference's extensions -- and ships finished hits; used when the records balance within 10 %
+    #  slices   equal slices of the packed genome with window-length halos (kgma_scan_shard + kgma_replay_packed): a genome of a
+    #           few huge contigs, and exact match
+    parts = None
+    if world > 1 and not exact and args.shard != "slices":
+        parts = K.partition_records(W.lens, world)
+        if parts is None and args.shard == "contigs":
+            raise SystemExit("--shard contigs: the records do not balance over %d ranks" % world)
+    sub = [None, None, None]  # this rank's sub-genome, its prepared scan, rank 0's merger (contig mode)
+
+    def contig_step(resident, count):
+        fl = L.F_ALIGN | (L.F_RESIDENT if resident else 0)
+        part = sub[1].scan(fl)
+        st1 = ctx.stats()
+        if not xch.cap:
+            need = part.copy_hits(None, 0)
+            part.free()
+            return None, st1, need
+        ptr = xch.x.begin_step()
+        need = part.copy_hits(ptr, xch.cap)
+        part.free()
+        if need > xch.cap:
+            raise RuntimeError("exchange block too small (%d > %d)" % (need, xch.cap))
+        xch.x.publish()
+        if rank != 0:
+            return None, st1, need
+        base = xch.x.wait_all()
+        t0 = time.perf_counter()
+        merged = sub[2].merge(base, xch.cap)
+        xch.x.consumed()
+        st1 = dict(st1); st1["rank0_replay_ms"] = (time.perf_counter() - t0) * 1e3
+        return merged, st1, need
+
     def shard_step(g_, resident, count):
         """one step of the sharded single-genome run; returns (result on rank 0 | None, stats of this rank's scan)"""
+        if parts is not None:
+            return contig_step(resident, count)
         fl = (0 if exact else L.F_ALIGN) | (L.F_RESIDENT if resident else 0)
         if exact:
             starts = exact_call(g_, resident, (rank, world))
@@ -572,6 +609,8 @@ def run_ours(args):
 
         if resident and not sharded:
             g_.make_resident(ctx)
+        if resident and sharded and parts is not None:
+            sub[0].make_resident(ctx)
         if sharded:                                    # size the exchange blocks from one untimed step (2x the largest block)
             _, _, need = shard_step(g_, resident, False)
             xch.size(need)
@@ -619,7 +658,8 @@ def run_ours(args):
     def key_of(out_):
         if exact:
             return out_
-        return out_.hits[["record", "profile", "first", "last", "D", "genome_pos", "align_score"]]
+        h = out_ if isinstance(out_, np.ndarray) else out_.hits
+        return h[["record", "profile", "first", "last", "D", "genome_pos", "align_score"]]
 
     # ---- the genome (the same one on every rank: in the sharded run each rank only ever touches its own slice)
     t_setup = time.perf_counter()
@@ -628,6 +668,10 @@ def run_ours(args):
     total = g.total_len
     if not exact:
         prep[0] = K.PreparedScan(g, rvs, wss, cs, thr, W.k, mode, W.buff, W.gap_open, GAP_EXT, ctx=ctx)
+    if parts is not None:
+        sub[0] = g.subset(parts[rank], ctx=ctx)
+        sub[1] = K.PreparedScan(sub[0], rvs, wss, cs, thr, W.k, mode, W.buff, W.gap_open, GAP_EXT, ctx=ctx)
+        sub[2] = K.PartitionMerger(parts, W.lens, 0 if W.config == "cluster" else int(wss[0]))
     # cold costs the warm-up hides: context creation, and the first call on a fresh context (prefilter weight-table build,
     # cudaMalloc of scratch / device planes, page-locked staging blocks)
     t0 = time.perf_counter()
@@ -714,16 +758,22 @@ def run_ours(args):
                        % ((64 + (10 if nine else 9) - W.k - 1) // ((10 if nine else 9) - W.k), npass))
         # filter_ms spans every prefilter pass of the step: each pass streams the slice once
         achieved = npass * alg_bytes / (filt_ms * 1e-3) / 1e9 if filt_ms > 0 else 0.0
-        nh = (sum(len(v) for v in out_res.values()) if isinstance(out_res, dict) else int(out_res)) if exact else int(len(out_res.hits))
+        nh = (sum(len(v) for v in out_res.values()) if isinstance(out_res, dict) else int(out_res)) if exact else int(len(out_res if isinstance(out_res, np.ndarray) else out_res.hits))
         line = {
             "metric": METRICS[W.config], "value": total * args.steps / dt_res / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt_res / args.steps * 1e3,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": {"workload": W.describe(world),
                        "parallelism": ("one GPU" if world == 1 else
-                                       "the one genome cut into %d equal slices of the packed coordinate space with window-length halos; every rank scans "
-                                       "and extends its slice (kgma_scan_shard); ONE NCCL all-gather of %d-byte blocks of (run, extension result) pairs; "
-                                       "host-only merge + replay on rank 0 (kgma_replay_packed)" % (world, xbytes)).replace("ONE NCCL all-gather of", "the ranks pack into a shared-memory segment of the host (no collective, no device round trip):"),
+                                       ("the one genome partitioned by contig over %d ranks (longest-first, fullest rank %.1f %% above the even share); every rank "
+                                        "runs the ordinary kgma_scan on its records and writes its finished hits (%d-byte blocks) into a shared-memory segment "
+                                        "of the host (no collective, no device round trip); rank 0 renumbers records / GenomePos and concatenates"
+                                        % (world, 100.0 * (max(sum(W.lens[r] for r in p) for p in parts) * world / float(sum(W.lens)) - 1.0), xbytes)) if parts is not None else
+                                       ("the one genome cut into %d equal slices of the packed coordinate space with window-length halos; every rank scans "
+                                        "and extends its slice (kgma_scan_shard); the ranks pack %d-byte blocks of (run, extension result) pairs into a "
+                                        "shared-memory segment of the host (no collective, no device round trip); host-only merge + replay on rank 0 "
+                                        "(kgma_replay_packed)" % (world, xbytes))),
+                       "shard": None if world == 1 else ("contigs" if parts is not None else "slices"),
                        "l2": "input (%.0f MB packed per GPU) larger than L2; no flush needed" % (total / 4e6 / world) if total / 4 / world > 126e6 else
                              "input %.0f MB packed per GPU: smaller than the 126 MB L2 at this N; the resident timed loop re-reads it from L2/HBM as a serving loop would" % (total / 4e6 / world),
                        "timing": "host clock around blocking C-ABI calls bracketed by device sync + barrier, max over ranks, median of %d regions of "
@@ -948,6 +998,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the other_configs / replicas blocks")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--shard", default="auto", choices=["auto", "contigs", "slices"],
+                    help="N > 1: whole records per rank (when they balance within 10 %%) or equal slices of the packed genome")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -247,6 +247,12 @@ const kgma_run_ext *kgma_result_run_ext(const kgma_result *r);
 int64_t kgma_result_pack(const kgma_result *r, void *buf, int64_t cap);
 int  kgma_replay_packed(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int n_profiles,
                         const kgma_scan_params *params, const void *blocks, int n_blocks, int64_t stride, kgma_result **out);
+/* The other cut: whole records per GPU (a genome whose contigs balance over the GPUs).  Every rank runs the ordinary kgma_scan on
+ * a genome of its own records and ships [int64 n][8 bytes][kgma_hit x n]; this merges the blocks on one host: rec_map[rec_off[b] +
+ * local record] = global record index, genome_pos_of[global record] = GenomePos of that record in the whole genome.  *out is
+ * malloc'ed (kgma_free). */
+int  kgma_hits_merge_partition(const void *blocks, int n_blocks, int64_t stride, const int32_t *rec_map, const int32_t *rec_off,
+                               int32_t n_records, const int64_t *genome_pos_of, kgma_hit **out, int64_t *n_out);
 
 int64_t kgma_result_n_hits(const kgma_result *r);
 const kgma_hit *kgma_result_hits(const kgma_result *r);

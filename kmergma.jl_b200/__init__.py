@@ -21,7 +21,7 @@ from . import _lib as L
 from .exchange import HostExchange
 
 __all__ = [
-    "KmerGMAError", "Context", "Genome", "FastaRecord", "KFV", "AlignResult", "HostExchange",
+    "KmerGMAError", "Context", "Genome", "FastaRecord", "KFV", "AlignResult", "HostExchange", "partition_records", "merge_partition_hits", "PartitionMerger",
     "gen_ref_ws_cons", "cluster_ref_API", "eliminate_null_params", "get_cluster_index",
     "estimate_optimal_threshold", "ac_gma_testing", "Omn_KmerGMA", "record_KmerGMA",
     "findGenes", "findGenes_cluster_mode", "exactMatch", "write_results", "write_hits", "hit_header",
@@ -152,6 +152,29 @@ class Genome:
         h = C.c_void_p()
         ctx.check(ctx._lib.kgma_genome_synth(ctx._h, lens.size, lens.ctypes.data, seed, n_run_len, centromere_len, C.byref(h)))
         return cls(h, ctx._lib)
+
+    def subset(self, records: Sequence[int], ctx: Optional[Context] = None) -> "Genome":
+        """a genome of its own holding copies of `records` (in that order) in page-locked planes: what one rank of a
+        contig-partitioned multi-GPU scan works on (north_star: "partitioned ... by contig").  Records start at multiples of
+        128 bases in both genomes, so the packed words are copied as they are."""
+        ctx = ctx or default_context()
+        recs = [int(r) for r in records]
+        lens = np.asarray([self.seqsize(r) for r in recs], dtype=np.int64)
+        h = C.c_void_p()
+        ctx.check(ctx._lib.kgma_genome_create_pinned(ctx._h, lens.size, lens.ctypes.data, C.byref(h)))
+        sub = Genome(h, ctx._lib)
+        for i, r in enumerate(recs):
+            s_src, m_src, s_dst, m_dst = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+            ctx.check(self._lib.kgma_genome_record_planes(self._h, r, C.byref(s_src), C.byref(m_src)))
+            ctx.check(ctx._lib.kgma_genome_record_planes(sub._h, i, C.byref(s_dst), C.byref(m_dst)))
+            n = int(lens[i])
+            C.memmove(s_dst, s_src, (n + 15) // 16 * 4)
+            C.memmove(m_dst, m_src, (n + 31) // 32 * 4)
+            ctx._lib.kgma_genome_set_names(sub._h, i, self.identifier(r).encode(), self.description(r).encode())
+        rc = ctx._lib.kgma_genome_seal(sub._h)
+        if rc != 0:
+            raise KmerGMAError(rc, "sealing the sub-genome failed")
+        return sub
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -633,6 +656,16 @@ class LightResult:
     def pack(self, buf_ptr, cap: int) -> int:
         return int(self._lib.kgma_result_pack(self._res, buf_ptr, cap))
 
+    def copy_hits(self, buf_ptr, cap: int) -> int:
+        """[int64 n][kgma_hit x n] into caller memory (a rank's block of a contig-partitioned scan); returns the bytes needed"""
+        n = self.n_hits
+        need = 16 + n * C.sizeof(L.Hit)
+        if buf_ptr and cap >= need:
+            C.memmove(buf_ptr, C.byref(C.c_int64(n)), 8)
+            if n:
+                C.memmove(buf_ptr + 16, self._lib.kgma_result_hits(self._res), n * C.sizeof(L.Hit))
+        return need
+
     def full(self) -> "ScanOutput":
         out = ScanOutput(self._lib, self._res)
         self._res = None
@@ -940,8 +973,61 @@ def findGenes_cluster_mode(*, genome_path, ref_path, cluster_cutoffs=(7, 12, 20,
 
 
 # ------------------------------------------------------------------------------------------------
-# Strobemer path (src/StrobemerGMA/, experimental in the reference; its scan has no test or golden there -- parity is against
-# the oracle's line-by-line restatement, which is assembled from the three utilities the reference's tests do pin).
+# Multi-GPU by contig (north_star: "the genome is partitioned across the GPUs by contig/chunk"): records are independent in both
+# state machines and GenomePos is a running sum of record lengths, so a rank that holds whole records runs the ordinary kgma_scan
+# on them -- its own replay, exactly the extensions the reference performs -- and ships finished hits.  Used when the records
+# balance over the ranks; a genome of a few huge contigs goes by slices instead (kgma_scan_shard / kgma_replay_packed).
+def partition_records(lens: Sequence[int], world: int, tolerance: float = 1.10) -> Optional[List[List[int]]]:
+    """longest-processing-time assignment of records to `world` ranks (each list ascending); None when the fullest rank would
+    hold more than `tolerance` times the even share"""
+    lens = [int(x) for x in lens]
+    load = [0] * world
+    parts: List[List[int]] = [[] for _ in range(world)]
+    for r in sorted(range(len(lens)), key=lambda i: -lens[i]):
+        j = min(range(world), key=lambda i: load[i])
+        parts[j].append(r)
+        load[j] += lens[r]
+    if any(not p for p in parts) or max(load) > tolerance * sum(lens) / world:
+        return None
+    return [sorted(p) for p in parts]
+
+
+class PartitionMerger:
+    """rank 0's side of a contig-partitioned scan: the maps are built once, merge() is one C call (kgma_hits_merge_partition)"""
+
+    def __init__(self, parts: List[List[int]], lens: Sequence[int], min_len: int = 0):
+        """min_len: single mode skips records shorter than the window WITHOUT advancing GenomePos (GenomeMiner.jl:37-39,106) --
+        pass the window size; cluster mode advances for every record (OmnGenomeMiner.jl:159) -- pass 0."""
+        lens = np.asarray(lens, dtype=np.int64)
+        self._lib = L.load()
+        self.n_records = int(lens.size)
+        self.glob_cum = np.ascontiguousarray(np.concatenate([[0], np.cumsum(np.where(lens >= min_len, lens, 0))])[:-1], dtype=np.int64)
+        self.rec_map = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.int32) for p in parts]), dtype=np.int32)
+        self.rec_off = np.ascontiguousarray(np.concatenate([[0], np.cumsum([len(p) for p in parts])]), dtype=np.int32)
+        self.world = len(parts)
+
+    def merge(self, blocks_ptr: int, stride: int) -> np.ndarray:
+        hp = C.POINTER(L.Hit)()
+        n = C.c_int64()
+        rc = self._lib.kgma_hits_merge_partition(blocks_ptr, self.world, stride, self.rec_map.ctypes.data, self.rec_off.ctypes.data,
+                                                 self.n_records, self.glob_cum.ctypes.data, C.byref(hp), C.byref(n))
+        if rc != 0:
+            raise KmerGMAError(rc, "kgma_hits_merge_partition failed")
+        out = np.frombuffer(C.string_at(hp, n.value * C.sizeof(L.Hit)), dtype=HIT_DT) if n.value else np.zeros(0, dtype=HIT_DT)
+        self._lib.kgma_free(hp)
+        return out
+
+
+def merge_partition_hits(blocks: np.ndarray, parts: List[List[int]], lens: Sequence[int], min_len: int = 0) -> np.ndarray:
+    """blocks[rank] = what LightResult.copy_hits wrote on that rank (records numbered within the rank's sub-genome) -> the hits of
+    the whole genome in the reference's order: global record indices, GenomePos = summed length of the records in front."""
+    blocks = np.ascontiguousarray(blocks)
+    return PartitionMerger(parts, lens, min_len).merge(blocks.ctypes.data, blocks.shape[1])
+
+
+# ------------------------------------------------------------------------------------------------
+# Strobemer path (src/StrobemerGMA/, experimental in the reference; its scan has no test or golden there -- parity is against a
+# line-by-line CPU restatement under tests/, assembled from the three utilities the reference's tests do pin).
 def strobe_gen_ref_ws_cons(reference_seqs, s: int = 2, w_min: int = 3, w_max: int = 5, q: int = 5):
     """gen_ref_ws_cons(refs; s, w_min, w_max, q) (StrobeRefGen.jl:4-42) -> (RV, windowsize, consensus); RV is a KFV over the
     4^(2s) gap-free 2-randstrobe codes."""

@@ -119,6 +119,7 @@ SYMBOLS = {
     "kgma_result_cigar_ops": (C.POINTER(C.c_char), [_P]),
     "kgma_result_cigar_counts": (C.POINTER(C.c_int32), [_P]),
     "kgma_result_free": (None, [_P]),
+    "kgma_hits_merge_partition": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, C.c_int32, _P, C.POINTER(C.POINTER(Hit)), C.POINTER(C.c_int64)]),
     "kgma_hit_header": (C.c_int64, [_P, C.POINTER(Hit), C.c_int, C.c_int, C.c_char_p, C.c_int64]),
     "kgma_result_write_fasta": (C.c_int, [_P, _P, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
     "kgma_genome_cumulative_len": (C.c_int64, [_P, C.c_int]),

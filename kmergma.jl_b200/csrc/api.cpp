@@ -191,6 +191,43 @@ int64_t kgma_genome_cumulative_len(const kgma_genome *g, int record)
     for (int r = 0; r < record; r++) c += g->recs[(size_t)r].len;
     return c;
 }
+// Contig-partitioned multi-GPU scan, the merge on rank 0: block b = [int64 n][8 bytes][kgma_hit x n] as written by rank b (records
+// numbered within that rank's sub-genome); rec_map[rec_off[b] + local] = global record index; genome_pos_of[global] = GenomePos of
+// that record in the whole genome.  Records are independent (GenomePos is a running sum of record lengths, GenomeMiner.jl:106),
+// so the result is the blocks' hits renumbered and ordered by global record (a counting sort; hits of one record keep their order).
+int kgma_hits_merge_partition(const void *blocks, int n_blocks, int64_t stride, const int32_t *rec_map, const int32_t *rec_off,
+                              int32_t n_records, const int64_t *genome_pos_of, kgma_hit **out, int64_t *n_out)
+{
+    if (!blocks || n_blocks < 1 || stride < 16 || !rec_map || !rec_off || n_records < 1 || !genome_pos_of || !out || !n_out) return KGMA_E_ARG;
+    int64_t total = 0;
+    for (int b = 0; b < n_blocks; b++) {
+        int64_t n; memcpy(&n, (const char *)blocks + (size_t)b * (size_t)stride, 8);
+        if (n < 0 || 16 + n * (int64_t)sizeof(kgma_hit) > stride) return KGMA_E_ARG;
+        total += n;
+    }
+    kgma_hit *res = (kgma_hit *)malloc((size_t)std::max<int64_t>(total, 1) * sizeof(kgma_hit));
+    if (!res) return KGMA_E_CAPACITY;
+    std::vector<int64_t> start((size_t)n_records + 1, 0);
+    for (int pass = 0; pass < 2; pass++) {
+        for (int b = 0; b < n_blocks; b++) {
+            const char *p = (const char *)blocks + (size_t)b * (size_t)stride;
+            int64_t n; memcpy(&n, p, 8);
+            const kgma_hit *h = (const kgma_hit *)(p + 16);
+            const int32_t lo = rec_off[b], hi = rec_off[b + 1];
+            for (int64_t i = 0; i < n; i++) {
+                if (h[i].record < 0 || h[i].record >= hi - lo) { free(res); return KGMA_E_ARG; }
+                const int32_t gr = rec_map[lo + h[i].record];
+                if (gr < 0 || gr >= n_records) { free(res); return KGMA_E_ARG; }
+                if (pass == 0) start[(size_t)gr + 1]++;
+                else { kgma_hit &o = res[start[(size_t)gr]++]; o = h[i]; o.record = gr; o.genome_pos = genome_pos_of[gr]; }
+            }
+        }
+        if (pass == 0) for (int32_t r = 0; r < n_records; r++) start[(size_t)r + 1] += start[(size_t)r];
+    }
+    *out = res; *n_out = total;
+    return KGMA_OK;
+}
+
 void kgma_free(void *p) { free(p); }
 
 }  // extern "C"

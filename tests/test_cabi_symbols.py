@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     import kmergma_jl_b200 as K
     L = K.L
     assert C.sizeof(L.Run) == 48 and C.sizeof(L.Hit) == 80 and C.sizeof(L.Match) == 24
-    assert C.sizeof(L.ScanParams) == 40 and C.sizeof(L.Profile) == 48
+    assert C.sizeof(L.ScanParams) == 64 and C.sizeof(L.Profile) == 48
 
 
 def test_no_gpu_means_loud_failure():

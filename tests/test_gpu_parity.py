@@ -1419,6 +1419,42 @@ def test_strobemer_scan_vs_oracle(K, O, synth, tmp_path):
     assert descs(outv[0]) == [h.description() for h in oh] and outv[1] == ol and len(outv[2]) == od.size
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_contig_partition_equals_whole(K, O, prof, synth, world):
+    """the other multi-GPU cut (north_star: "partitioned ... by contig"): whole records per rank (partition_records), every rank's
+    sub-genome (Genome.subset) through the ordinary kgma_scan, finished hits merged with record indices and GenomePos renumbered
+    (merge_partition_hits) -- equal to the scan of the whole genome, single and cluster mode, incl. a record shorter than the
+    window (which single mode skips without advancing GenomePos, GenomeMiner.jl:37-39, and cluster mode counts)"""
+    path, recs = synth
+    RV, ws, cons = prof
+    rvs, wss, cs, inv = K.cluster_ref_API(TF, 6)
+    rvs, wss, cs = K.eliminate_null_params(rvs, wss, cs, inv)
+    L = K.L
+    rng = np.random.default_rng(2)
+    extra = [("short one", "ACGT" * 40)] + [("filler %d" % i, "".join(np.asarray(list("ACGT"))[rng.integers(0, 4, size=int(n))])) for i, n in enumerate((5000, 900, 12000))]
+    allrecs = [recs[0], extra[0]] + list(recs[1:]) + extra[1:]
+    g = K.Genome.from_records(allrecs)
+    lens = [g.seqsize(r) for r in range(len(g))]
+    parts = K.partition_records(lens, world, tolerance=10.0)
+    assert parts is not None and sorted(r for p in parts for r in p) == list(range(len(g)))
+    assert K.partition_records([10, 1000], 2, tolerance=1.1) is None           # two records that cannot balance
+    key = ["record", "profile", "first", "last", "D", "genome_pos", "align_score", "cmi"]
+    cap = 1 << 20
+    for args, go, min_len in ((([RV], [ws], [cons], [30.0], 6, L.MODE_SINGLE, 50), -69, ws),
+                              ((rvs, wss, cs, [35, 31, 38, 34, 27, 27], 6, L.MODE_CLUSTER, 100), -200, 0)):
+        whole = K.scan_raw(g, *args, L.F_ALIGN, go, -1)
+        blocks = np.zeros((world, cap), dtype=np.uint8)
+        for rank, p in enumerate(parts):
+            sub = g.subset(p)
+            assert [sub.identifier(i) for i in range(len(sub))] == [g.identifier(r) for r in p] and sub.seq(0) == g.seq(p[0])
+            ps = K.PreparedScan(sub, *args, go, -1)
+            lr = ps.scan(L.F_ALIGN)
+            assert lr.copy_hits(blocks[rank].ctypes.data, cap) <= cap
+            lr.free()
+        merged = K.merge_partition_hits(blocks, parts, lens, min_len)
+        assert len(whole.hits) >= 8 and np.array_equal(merged[key], whole.hits[key]), args[5]
+
+
 def test_two_contexts_share_nothing(K, prof, synth):
     """two contexts on the same device, used alternately on different genomes: each keeps its own device planes, tables,
     staging ring and scratch, so neither disturbs the other's resident genome"""
