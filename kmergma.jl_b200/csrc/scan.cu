@@ -1245,7 +1245,8 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     if (ctx->ftabs.size() > 96) ctx->ftabs.clear();                // bounded cache; nothing points into it between calls
     {
         std::vector<int> all((size_t)C); for (int q = 0; q < C; q++) all[(size_t)q] = q;
-        const double LOAD_OK = 0.62, LOAD_MAX = 0.85;
+        double LOAD_OK = 0.62; const double LOAD_MAX = 0.85;
+        if (const char *e = getenv("KGMA_LOAD_OK")) LOAD_OK = atof(e);     // (experiments: how full a shared table may be)
         FilterGroup dg; dg.dense = true;
         if (force_dense) dg.q = all;
         else {
