@@ -812,6 +812,8 @@ def run_ours(args):
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
+        if xch is not None and xch.x is not None:
+            xch.x.close()                                     # (rank 0 unlinks the segment)
         dist.destroy_process_group()
 
 
