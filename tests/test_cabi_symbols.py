@@ -220,6 +220,46 @@ def test_strobemer_profile_and_oracle_pieces():
     assert [(h.first, h.last) for h in he] == [(h.first, h.last) for h in hits] and np.max(np.abs(d - de)) < 1e-9
 
 
+def test_partition_records_and_hit_merge_host_only():
+    """the contig cut of a multi-GPU scan, host side only (no device): longest-first assignment of records to ranks, and
+    kgma_hits_merge_partition -- blocks of [n][kgma_hit x n] with rank-local record numbers -> global record indices,
+    GenomePos = summed length of the records in front (single mode: records shorter than the window do not count,
+    GenomeMiner.jl:37-39,106; cluster mode: every record, OmnGenomeMiner.jl:159), ordered by record, order inside a record kept"""
+    import kmergma_jl_b200 as K
+    lens = [5000, 120, 9000, 3000, 289, 7000, 100, 4000]
+    for world in (2, 3, 4):
+        parts = K.partition_records(lens, world, tolerance=10.0)
+        assert sorted(r for p in parts for r in p) == list(range(len(lens))) and all(p == sorted(p) for p in parts)
+        load = [sum(lens[r] for r in p) for p in parts]
+        assert max(load) - min(load) <= max(lens)                       # longest-first keeps the ranks within one record of each other
+    assert K.partition_records([10, 1000], 2) is None and K.partition_records([5, 5], 3) is None
+    parts = K.partition_records(lens, 3, tolerance=10.0)
+    rng = np.random.default_rng(0)
+    cap = 1 << 16
+    blocks = np.zeros((3, cap), dtype=np.uint8)
+    want = []
+    for rank, p in enumerate(parts):
+        n = 0
+        hits = np.zeros(64, dtype=K.HIT_DT)
+        for local, r in enumerate(p):
+            for t in range(int(rng.integers(0, 5))):                 # several hits per record, in order
+                hits[n]["record"], hits[n]["first"], hits[n]["last"], hits[n]["D"] = local, 10 * t + 1, 10 * t + 5, 1000 * r + t
+                hits[n]["genome_pos"] = -12345                         # whatever the sub-genome's own count was: it is replaced
+                want.append((r, 10 * t + 1, 1000 * r + t))
+                n += 1
+        blocks[rank, :8].view(np.int64)[0] = n
+        blocks[rank, 16:16 + n * K.HIT_DT.itemsize] = hits[:n].view(np.uint8).reshape(-1)
+    want.sort(key=lambda x: (x[0], x[1]))
+    for min_len, counted in ((289, [l if l >= 289 else 0 for l in lens]), (0, lens)):
+        out = K.merge_partition_hits(blocks, parts, lens, min_len)
+        gp = np.concatenate([[0], np.cumsum(counted)])[:-1]
+        assert [(int(h["record"]), int(h["first"]), int(h["D"])) for h in out] == want
+        assert [int(h["genome_pos"]) for h in out] == [int(gp[r]) for r, _, _ in want]
+    bad = blocks.copy(); bad[0, :8].view(np.int64)[0] = 10 ** 9       # a count that cannot fit the block is refused
+    with pytest.raises(K.KmerGMAError):
+        K.merge_partition_hits(bad, parts, lens, 0)
+
+
 def test_masked_runs_match_numpy(tmp_path):
     """the masked-run list (what the extension / exact-match kernels consult instead of the ambiguity plane) against a
     numpy scan of the same sequences: runs at record starts/ends, one-base runs, runs spanning 32-base mask words, and a
