@@ -1684,6 +1684,7 @@ int kgma_scan_shard(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles,
 {
     if (!ctx || !g || !params || !out) return KGMA_E_ARG;
     if (params->flags & (KGMA_F_WANT_CIGARS | KGMA_F_WANT_DISTS)) return set_err(ctx, KGMA_E_UNSUPPORTED, "kgma_scan_shard returns neither CIGARs nor distances");
+    if (params->mode == KGMA_MODE_STROBE) return set_err(ctx, KGMA_E_UNSUPPORTED, "strobemer mode is not sharded (use one genome of whole records per device)");
     kgma_result *res = result_acquire();
     ScanPlan pl;
     int rc = scan_runs_retry(ctx, g, profiles, n_profiles, *params, pl, res);
