@@ -34,6 +34,10 @@
 #include "staged_upload.h"
 #include <cuda/barrier>
 
+#ifndef KGMA_NSTAMP
+#define KGMA_NSTAMP 2048
+#endif
+
 namespace kgma {
 
 // =============================================================================================
@@ -613,19 +617,23 @@ __global__ void __launch_bounds__(MAXT, 1) kgma_eval(EvalArgs a, ProfDev P, int 
     const unsigned FULL = 0xFFFFFFFFu;
     constexpr int nb = 1 << (2 * K);
     constexpr uint32_t kmask = (uint32_t)nb - 1;
-    // k <= 6: an entry is 32 bits, the count in the low half and a one-byte lane stamp above it (duplicate detection, below);
-    // k = 7: 16-bit counts only (64 KB per warp otherwise) and MATCH.ANY for every batch
+    // 16-bit counts.  k <= 6: next to them a small array of one-byte lane stamps, indexed by the low bits of the code (duplicate
+    // detection, below; 2 KB at most -- with the 8 KB of counts at k = 6 that is 10 KB per warp, 20 warps per SM, where 32-bit
+    // stamped entries allowed 13); k = 7: MATCH.ANY for every batch
     constexpr bool STAMP = K <= 6;
-    constexpr int ESH = STAMP ? 2 : 1;                                     // log2(bytes per entry)
+    constexpr int ESH = 1;                                                 // log2(bytes per entry)
+    constexpr int NSTAMP = STAMP ? (nb < KGMA_NSTAMP ? nb : KGMA_NSTAMP) : 0;    // stamp slots (bytes) per warp
+    constexpr uint32_t SMASK = NSTAMP ? (uint32_t)NSTAMP - 1 : 0;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int32_t *sS = reinterpret_cast<int32_t *>(smem_raw);
     const uint32_t xmask = STROBE ? a.xmask : kmask;                        // bits of the base pattern a code is derived from
     const size_t map_bytes = STROBE ? (((size_t)xmask + 1) * 2 + 15) & ~(size_t)15 : 0;
     const uint16_t *smap = reinterpret_cast<const uint16_t *>(smem_raw + (size_t)nb * 4);
-    unsigned char *tabb = smem_raw + (size_t)nb * 4 + map_bytes + (size_t)wid * ((size_t)nb << ESH);   // [4^k] entries of this warp
+    unsigned char *tabb = smem_raw + (size_t)nb * 4 + map_bytes + (size_t)wid * (((size_t)nb << ESH) + NSTAMP);   // [4^k] counts (+ stamps) of this warp
+    unsigned char *stampb = tabb + ((size_t)nb << ESH);
     auto code_at = [&](long long gp) -> uint32_t { const uint32_t v = kmer_at(a.seq, gp, xmask); return STROBE ? (uint32_t)smap[v] : v; };
     auto cnt_ptr = [&](uint32_t km) { return reinterpret_cast<uint16_t *>(tabb + ((size_t)km << ESH)); };
-    for (int i = lane; i < (nb << ESH) / 4; i += 32) reinterpret_cast<uint32_t *>(tabb)[i] = 0;
+    for (int i = lane; i < ((nb << ESH) + NSTAMP) / 4; i += 32) reinterpret_cast<uint32_t *>(tabb)[i] = 0;
 
     long long nitems = a.n_items;
     if (a.cand) { uint32_t c = *a.cand_count; nitems = c < a.cand_cap ? c : a.cand_cap; }
@@ -711,8 +719,7 @@ __global__ void __launch_bounds__(MAXT, 1) kgma_eval(EvalArgs a, ProfDev P, int 
             const int nel = STROBE ? nk + 1 : nk;
             for (int p = lane; p < nel; p += 32) {
                 const uint32_t km = (STROBE && p == nk) ? zx : code_at(gpos + p);
-                if (STAMP) atomicAdd(reinterpret_cast<uint32_t *>(tabb) + km, 1u);
-                else atomicAdd(reinterpret_cast<uint32_t *>(tabb) + (km >> 1), 1u << ((km & 1) * 16));
+                atomicAdd(reinterpret_cast<uint32_t *>(tabb) + (km >> 1), 1u << ((km & 1) * 16));
             }
             __syncwarp();
             uint32_t Qb = 0, Ab = 0;                                          // < 2^32: nk <= 65535, nk * max S checked on the host
@@ -754,17 +761,17 @@ __global__ void __launch_bounds__(MAXT, 1) kgma_eval(EvalArgs a, ProfDev P, int 
                 const int left = FB ? 16 : ni - 1 - s;
                 const bool valid = FB || j < left;
                 // Which lanes hold the same k-mer?  Nearly always none do (32 events among 4^k values), and MATCH.ANY costs about
-                // two cycles per distinct value.  So every lane stamps its entry with its lane number and reads the entry back
-                // (the count comes with it): a lane that finds another lane's stamp shares its k-mer with that lane, and only a
-                // batch in which some lane does pays for the MATCH.
+                // two cycles per distinct value.  So every lane writes its lane number into the stamp slot of its code and reads the
+                // slot back: a lane that finds another lane's stamp shares its slot -- its k-mer, or one with the same low bits --
+                // with that lane, and only a batch in which some lane does pays for the MATCH (which then finds the real duplicates).
                 unsigned m = 1u << lane;
                 uint32_t c0;
                 if (STAMP) {
-                    if (valid) tabb[((size_t)x << 2) + 2] = (unsigned char)lane;
+                    if (valid) stampb[x & SMASK] = (unsigned char)lane;
                     __syncwarp();
-                    const uint32_t ent = reinterpret_cast<const uint32_t *>(tabb)[x];
-                    c0 = ent & 0xFFFFu;
-                    if (__any_sync(FULL, valid && ((ent >> 16) & 0xFFu) != (uint32_t)lane))
+                    c0 = *cnt_ptr(x);
+                    const uint32_t stp = stampb[x & SMASK];
+                    if (__any_sync(FULL, valid && stp != (uint32_t)lane))
                         m = __match_any_sync(FULL, valid ? x : (0x80000000u | (unsigned)lane));
                 } else {
                     m = __match_any_sync(FULL, valid ? x : (0x80000000u | (unsigned)lane));
@@ -1100,15 +1107,20 @@ static void launch_filter_k(int k, const FilterArgs &fa, int grid, cudaStream_t 
 
 template <int K> static void launch_eval_strobe(const EvalArgs &ea, const ProfDev &P, int q, int grid, int threads, size_t smem, cudaStream_t st)
 {
-    cudaFuncSetAttribute(kgma_eval<K, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kgma_eval<K, 512, true><<<grid, threads, smem, st>>>(ea, P, q);
+    if (threads > 512) {
+        cudaFuncSetAttribute(kgma_eval<K, 640, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kgma_eval<K, 640, true><<<grid, threads, smem, st>>>(ea, P, q);
+    } else {
+        cudaFuncSetAttribute(kgma_eval<K, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kgma_eval<K, 512, true><<<grid, threads, smem, st>>>(ea, P, q);
+    }
 }
 
 template <int K> static void launch_eval_t(const EvalArgs &ea, const ProfDev &P, int q, int grid, int threads, size_t smem, cudaStream_t st)
 {
-    if (threads > 512) {       // more than 16 warps per CTA: the 85-register build
-        cudaFuncSetAttribute(kgma_eval<K, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kgma_eval<K, 768><<<grid, threads, smem, st>>>(ea, P, q);
+    if (threads > 512) {       // more than 16 warps per CTA: the 640-thread build, 96 registers (672 / 736 threads make ptxas drop to 80 and spill)
+        cudaFuncSetAttribute(kgma_eval<K, 640>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kgma_eval<K, 640><<<grid, threads, smem, st>>>(ea, P, q);
     } else {
         cudaFuncSetAttribute(kgma_eval<K, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kgma_eval<K, 512><<<grid, threads, smem, st>>>(ea, P, q);
@@ -1159,11 +1171,10 @@ static int eval_shape(const kgma_ctx *ctx, int k, bool serial, int *warps_out, s
     const size_t nb = (size_t)1 << (2 * k);
     map_bytes = (map_bytes + 15) & ~(size_t)15;                    // strobemer mode: the code map sits between S and the count tables
     // one 4^k x u16 count table per warp, next to the profile's S table (the serial kernel adds its 64-step staging arrays)
-    const size_t per_warp = serial ? nb * 2 + 64 * 4 + 64 * 4 + 64 * 8 : nb * (k <= 6 ? 4 : 2);
+    const size_t per_warp = serial ? nb * 2 + 64 * 4 + 64 * 4 + 64 * 8 : nb * 2 + (k <= 6 ? std::min<size_t>(nb, KGMA_NSTAMP) : 0);
     if (ctx->smem_optin < nb * 4 + map_bytes + per_warp) return KGMA_E_UNSUPPORTED;
-    int wmax = serial ? 16 : 24;
-    if (const char *e = getenv("KGMA_EVAL_WARPS")) wmax = std::max(1, std::min(24, atoi(e)));
-    if (map_bytes) wmax = std::min(wmax, 16);                       // (the strobemer build of the kernel is the 512-thread one)
+    int wmax = serial ? 16 : 20;
+    if (const char *e = getenv("KGMA_EVAL_WARPS")) wmax = std::max(1, std::min(20, atoi(e)));
     int w = (int)std::min<size_t>((ctx->smem_optin - nb * 4 - map_bytes) / per_warp, (size_t)wmax);
     *warps_out = w; *smem_out = nb * 4 + map_bytes + (size_t)w * per_warp;
     return KGMA_OK;
