@@ -22,6 +22,8 @@ void merge_runs(std::vector<kgma_run> &runs, std::vector<kgma_run_ext> *ext)
 {
     static thread_local std::vector<uint32_t> order;
     bool sorted_by_index = false;
+    auto tnow_ = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const bool trace_ = getenv("KGMA_TRACE_MERGE") != nullptr; const double tm0 = trace_ ? tnow_() : 0; double tm1 = 0, tm2 = 0;
     // order by (profile, record, t_first, marker) - the device appends runs in arbitrary order.  A few thousand runs per
     // genome: the key is squeezed to the bits that can differ ((profile, record) as one group number, t_first relative to
     // the smallest one) and sorted with an LSD radix sort of (key, index) pairs, 11 bits per pass -- three or four passes
@@ -62,13 +64,19 @@ void merge_runs(std::vector<kgma_run> &runs, std::vector<kgma_run_ext> *ext)
                 ka[i] = { (grp << (tbits + 1)) | ((uint64_t)(r.t_first - tmin) << 1) | ((r.flags & KGMA_RUN_MARKER) ? 1u : 0u), (uint32_t)i };
             }
             const int total = gbits + tbits + 1;
+            if (trace_) tm1 = tnow_();
             KI *src = ka.data(), *dst = kb.data();
-            for (int sh = 0; sh < total; sh += 11) {
-                uint32_t cnt[2049] = { 0 };
-                for (size_t i = 0; i < n; i++) cnt[((src[i].key >> sh) & 0x7FFu) + 1]++;
-                if (cnt[((src[0].key >> sh) & 0x7FFu) + 1] == n) continue;      // this digit is the same everywhere
-                for (int d = 0; d < 2048; d++) cnt[d + 1] += cnt[d];
-                for (size_t i = 0; i < n; i++) dst[cnt[(src[i].key >> sh) & 0x7FFu]++] = src[i];
+            // digits of 8 bits for short lists (the prefix over the buckets is a fixed cost per pass: 256 steps instead of 2048),
+            // of 11 bits otherwise; either way ceil(total / digit) passes
+            const int dig = (n < 16384 && (total + 7) / 8 <= (total + 10) / 11) ? 8 : 11;
+            const uint32_t dmask = (1u << dig) - 1u;
+            for (int sh = 0; sh < total; sh += dig) {
+                uint32_t cnt[2049];
+                memset(cnt, 0, ((size_t)dmask + 2) * sizeof(uint32_t));
+                for (size_t i = 0; i < n; i++) cnt[((src[i].key >> sh) & dmask) + 1]++;
+                if (cnt[((src[0].key >> sh) & dmask) + 1] == n) continue;       // this digit is the same everywhere
+                for (uint32_t d = 0; d <= dmask; d++) cnt[d + 1] += cnt[d];
+                for (size_t i = 0; i < n; i++) dst[cnt[(src[i].key >> sh) & dmask]++] = src[i];
                 std::swap(src, dst);
             }
             order.resize(n);
@@ -76,12 +84,48 @@ void merge_runs(std::vector<kgma_run> &runs, std::vector<kgma_run_ext> *ext)
             sorted_by_index = true;
         }
     }
+    if (trace_) tm2 = tnow_();
     static thread_local std::vector<kgma_run> out;
     static thread_local std::vector<kgma_run_ext> out_ext;
     out.clear(); out_ext.clear();
     out.reserve(runs.size());
+    if (!ext && !runs.empty()) {
+        // the common case (no per-run extension results to carry along): the open run is kept in registers and the updates are
+        // written without data-dependent branches -- whether two neighbours join is a coin flip the branch predictor loses
+        out.resize(runs.size());
+        kgma_run *o = out.data(); size_t no = 0;
+        kgma_run cur = runs[sorted_by_index ? order[0] : 0];
+        for (size_t ri = 1; ri < runs.size(); ri++) {
+            const kgma_run &r = runs[sorted_by_index ? order[ri] : ri];
+            const bool same = cur.profile == r.profile && cur.record == r.record;
+            const bool pm = (cur.flags & KGMA_RUN_MARKER) != 0, rm = (r.flags & KGMA_RUN_MARKER) != 0;
+            if (same && pm && rm && cur.t_first == r.t_first) continue;              // the same marker reported twice
+            if (same && !pm && !rm && r.t_first <= cur.t_last + 1) {
+                // pieces of one maximal run (see below): min of minima, earlier argmin on ties
+                const bool lt = r.D_min < cur.D_min, eq = r.D_min == cur.D_min;
+                const uint32_t tie_new = lt ? (r.flags & KGMA_HIT_ARGMIN_TIE)
+                                            : ((cur.flags & KGMA_HIT_ARGMIN_TIE) | (eq ? ((r.flags & KGMA_HIT_ARGMIN_TIE) | (r.t_argmin != cur.t_argmin ? KGMA_HIT_ARGMIN_TIE : 0u)) : 0u));
+                const int64_t arg_new = lt ? r.t_argmin : (eq ? std::min(cur.t_argmin, r.t_argmin) : cur.t_argmin);
+                cur.D_min = lt ? r.D_min : cur.D_min;
+                cur.t_argmin = arg_new;
+                uint32_t fl = (cur.flags & ~KGMA_HIT_ARGMIN_TIE) | tie_new | (r.flags & KGMA_HIT_NEAR_THR);
+                const bool ext_right = r.t_last >= cur.t_last;
+                fl = ext_right ? ((fl & ~KGMA_RUN_OPEN_RIGHT) | (r.flags & KGMA_RUN_OPEN_RIGHT)) : fl;
+                cur.t_last = ext_right ? r.t_last : cur.t_last;
+                cur.flags = fl;
+                continue;
+            }
+            o[no++] = cur; cur = r;
+        }
+        o[no++] = cur;
+        out.resize(no);
+        runs.swap(out);
+        if (trace_) fprintf(stderr, "[kgma merge] keys %.3f ms, sort %.3f ms, merge %.3f ms\n", tm1 - tm0, tm2 - tm1, tnow_() - tm2);
+        return;
+    }
     for (size_t ri = 0; ri < runs.size(); ri++) {
         const size_t src = sorted_by_index ? order[ri] : ri;
+        if (sorted_by_index && ri + 12 < runs.size()) __builtin_prefetch(&runs[order[ri + 12]]);   // (the reads hop around a 200 KB array)
         const kgma_run &r = runs[src];                                      // (merged straight out of the unsorted array: no gather copy)
         if (!out.empty() && out.back().profile == r.profile && out.back().record == r.record) {
             kgma_run &p = out.back();
@@ -110,6 +154,7 @@ void merge_runs(std::vector<kgma_run> &runs, std::vector<kgma_run_ext> *ext)
     }
     runs.swap(out);                                      // (the scratch vector keeps the old buffer for the next call)
     if (ext) ext->swap(out_ext);
+    if (trace_) fprintf(stderr, "[kgma merge] keys %.3f ms, sort %.3f ms, merge %.3f ms\n", tm1 - tm0, tm2 - tm1, tnow_() - tm2);
 }
 
 // merge with extension results for run lists the radix path does not take (out-of-range keys, fewer than two runs):
