@@ -665,7 +665,10 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     const bool trace = getenv("KGMA_TRACE") != nullptr;
     const double te0 = trace ? now_ms() : 0;
     KGMA_CUDA(ctx, cudaSetDevice(ctx->device));
-    std::vector<uint8_t> acodes; std::vector<int32_t> a_off(n_profiles), a_len(n_profiles);
+    // (scratch kept per thread: the queue of a cfg2 batch is 160 KB, which malloc would serve with a fresh mmap per call)
+    static thread_local std::vector<uint8_t> acodes, bcodes; static thread_local std::vector<AlignJob2> jobs, q;
+    acodes.clear(); bcodes.clear();
+    std::vector<int32_t> a_off(n_profiles), a_len(n_profiles);
     for (int q = 0; q < n_profiles; q++) {
         const kgma_profile &p = profiles[q];
         if (!p.consensus) return set_err(ctx, KGMA_E_ARG, "profile %d has no consensus sequence to align against", q);
@@ -683,7 +686,7 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
     }
     const std::vector<int64_t> &nruns = genome_nruns(g);
     const bool on_dev = ctx->dg_uid == g->uid && ctx->d_seq2 && ctx->d_have_hi > ctx->d_have_lo;
-    std::vector<AlignJob2> jobs(reqs.size()); std::vector<uint8_t> bcodes; int maxn = 0;
+    jobs.resize(reqs.size()); int maxn = 0;
     for (size_t i = 0; i < reqs.size(); i++) {
         const AlignReq &rq = reqs[i];
         if (rq.record < 0 || rq.record >= (int)g->recs.size() || rq.profile < 0 || rq.profile >= n_profiles)
@@ -736,7 +739,7 @@ int align_enqueue(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq> &re
         for (const AlignReq &rq : reqs) n_marked += rq.hint & 1;
         const bool all3 = 3 * jobs.size() <= room;
         const bool marked3 = !all3 && jobs.size() + 2 * n_marked <= room;
-        std::vector<AlignJob2> q; q.reserve(jobs.size() * 3);
+        q.clear(); q.reserve(jobs.size() * 3);
         for (int pass = 0; pass < 4; pass++)
             for (size_t i = 0; i < jobs.size(); i++) {
                 const bool marked = tail_mode == 1 || all3 || (reqs[i].hint & 1);

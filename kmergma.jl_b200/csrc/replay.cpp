@@ -307,8 +307,10 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
         return std::max<int64_t>(0, cluster ? L - maxws - k + 2 : L - maxws - (tabs[0].strobe ? 1 : 0));
     };
 
-    std::vector<AlignReq> reqs; std::vector<AlignRes> ares;
-    std::vector<Pending> pend;                            // single mode: hits waiting for their extension
+    // (scratch kept per thread: a few hundred KB per call otherwise, each a fresh mmap)
+    static thread_local std::vector<AlignReq> reqs; static thread_local std::vector<AlignRes> ares;
+    static thread_local std::vector<Pending> pend;        // single mode: hits waiting for their extension
+    reqs.clear(); ares.clear(); pend.clear();
 
     if (!cluster) {
         // ---------------- ac_gma_testing! ----------------
