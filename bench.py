@@ -614,7 +614,19 @@ def run_ours(args):
         if sharded:                                    # size the exchange blocks from one untimed step (2x the largest block)
             _, _, need = shard_step(g_, resident, False)
             xch.size(need)
+        t_w = time.perf_counter()
         for _ in range(args.warmup):
+            step(False)
+        # a step is ~1 ms: W steps are over before host and device clocks have settled (the first of five regions used to read
+        # 10-35 % slower than the last).  Keep stepping, untimed, for about 80 ms more -- the same number of steps on every rank
+        # (the ranks of a sharded run move in lock-step through the exchange).
+        per = (time.perf_counter() - t_w) / max(1, args.warmup)
+        n_extra = int(min(400, max(0, 0.08 / max(per, 1e-5))))
+        if world > 1:
+            t = torch.tensor([n_extra], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            n_extra = int(t.item())
+        for _ in range(n_extra):
             step(False)
         stop, samples = threading.Event(), []
         nvml_handle(local)                               # (initialised before the timed region)
@@ -777,7 +789,8 @@ def run_ours(args):
                        "l2": "input (%.0f MB packed per GPU) larger than L2; no flush needed" % (total / 4e6 / world) if total / 4 / world > 126e6 else
                              "input %.0f MB packed per GPU: smaller than the 126 MB L2 at this N; the resident timed loop re-reads it from L2/HBM as a serving loop would" % (total / 4e6 / world),
                        "timing": "host clock around blocking C-ABI calls bracketed by device sync + barrier, max over ranks, median of %d regions of "
-                                 "exactly K steps (>= the CUDA-event device time reported in device_ms_per_step)" % REG},
+                                 "exactly K steps (>= the CUDA-event device time reported in device_ms_per_step); after the W warm-up steps the "
+                                 "loop keeps stepping untimed for about 80 ms more (clocks settle: a step is ~1 ms)" % REG},
             "e2e": {"value": total * args.steps / dt_e2e / 1e6, "unit": UNIT, "ms_per_step": dt_e2e / args.steps * 1e3,
                     "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all, "h2d_ceiling": h2d_ceiling},
             "gpu_launches": int(launches_all),
