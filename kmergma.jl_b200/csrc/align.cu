@@ -971,6 +971,7 @@ int align_batch_device(kgma_ctx *ctx, kgma_genome *g, const std::vector<AlignReq
         size_t o_cg = carve(want_cigars ? cig_entries * 4 : 0), o_tr = carve(tr_bytes);
         void *dv = nullptr;
         int rc = dev_scratch(ctx, o, &dv);
+        ctx->tab_sig = 0;                                  // (the arena is carved anew: the scan's resident tables are gone)
         if (rc) return rc;
         unsigned char *d = (unsigned char *)dv;
         KGMA_CUDA(ctx, cudaMemcpyAsync(d + o_a, acodes.data(), acodes.size(), cudaMemcpyHostToDevice, st));

@@ -256,6 +256,7 @@ static int exact_match_impl(kgma_ctx *ctx, kgma_genome *g, const char *query, in
     size_t o_c = carve(256), o_out = carve((size_t)cap * 8);
     void *dv = nullptr, *hv = nullptr;
     rc = dev_scratch(ctx, o, &dv);
+    ctx->tab_sig = 0;                                  // (the arena is carved anew: the scan's resident tables are gone)
     if (rc) return rc;
     rc = host_scratch(ctx, up, &hv);
     if (rc) return rc;

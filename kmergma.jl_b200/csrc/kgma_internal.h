@@ -103,6 +103,7 @@ struct kgma_ctx {
     void *stage = nullptr; size_t stage_bytes = 0; cudaEvent_t stage_ev[16] = { nullptr };
     // scratch
     void     *d_scratch = nullptr; size_t d_scratch_bytes = 0;
+    uint64_t  tab_sig = 0;          // which prefilter tables sit where in d_scratch (0 = none: whoever else carves the arena clears it)
     void     *h_scratch = nullptr; size_t h_scratch_bytes = 0;   // pinned
 };
 

@@ -844,7 +844,7 @@ int dev_scratch(kgma_ctx *ctx, size_t bytes, void **out)
 {
     if (bytes > ctx->d_scratch_bytes) {
         if (ctx->d_scratch) cudaFree(ctx->d_scratch);
-        ctx->d_scratch = nullptr; ctx->d_scratch_bytes = 0;
+        ctx->d_scratch = nullptr; ctx->d_scratch_bytes = 0; ctx->tab_sig = 0;
         size_t nb = std::max(bytes, (size_t)1 << 20);
         KGMA_CUDA(ctx, cudaMalloc(&ctx->d_scratch, nb));
         ctx->d_scratch_bytes = nb;
@@ -1330,6 +1330,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
     const size_t o_S = carve((size_t)C * nb * 4), o_recs = carve(recs.size() * sizeof(RecDev)), o_cmap = carve(pl.cmap.size() * 2);
     const size_t o_seed = carve((seeds.size() + 1) * 4);
+    const size_t up_small = o;                                     // ... up to here on every call; the weight tables only when they changed
     for (FilterGroup &fg : groups) if (!fg.dense) fg.o_tab = carve(fg.ft->nine ? (size_t)TAB9_BYTES : (size_t)65536 * 2);
     const size_t up_bytes = o;                                     // everything above is uploaded from the staging block
     const size_t o_cnt = carve(512), o_first = carve((size_t)C * std::max(nr, 1) * 8), o_runs = carve((size_t)run_cap * sizeof(kgma_run));
@@ -1347,7 +1348,18 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     unsigned char *hs = (unsigned char *)hsv, *hback = hs + up_bytes, *hbackA = hback + back_bytes;
     for (int q = 0; q < C; q++) memcpy(hs + o_S + (size_t)q * nb * 4, pl.tabs[q].S_rev.data(), nb * 4);
     if (pl.strobe) memcpy(hs + o_cmap, pl.cmap.data(), pl.cmap.size() * 2);
-    for (const FilterGroup &fg : groups) if (!fg.dense) { if (fg.ft->nine) memcpy(hs + fg.o_tab, fg.ft->tab9.data(), TAB9_BYTES); else memcpy(hs + fg.o_tab, fg.ft->tab.data(), 65536 * 2); }
+    // The prefilter tables (192 KB each) stay in the device arena between scans: a serving loop with the same profiles uploads
+    // them once.  The signature covers which table sits at which offset of which allocation.
+    uint64_t tsig = 1469598103934665603ull;
+    {
+        auto mix = [&](uint64_t w) { tsig ^= w; tsig *= 1099511628211ull; tsig ^= tsig >> 31; };
+        mix((uint64_t)(uintptr_t)ds);
+        for (const FilterGroup &fg : groups) if (!fg.dense) { mix(fg.ft->key); mix((uint64_t)fg.o_tab); mix(fg.ft->nine ? 9 : 8); }
+        if (tsig == 0) tsig = 1;
+    }
+    const bool tabs_resident = up_bytes > up_small && ctx->tab_sig == tsig && !getenv("KGMA_NO_TABLE_CACHE");
+    if (!tabs_resident)
+        for (const FilterGroup &fg : groups) if (!fg.dense) { if (fg.ft->nine) memcpy(hs + fg.o_tab, fg.ft->tab9.data(), TAB9_BYTES); else memcpy(hs + fg.o_tab, fg.ft->tab.data(), 65536 * 2); }
     memcpy(hs + o_recs, recs.data(), recs.size() * sizeof(RecDev));
     if (!seeds.empty()) memcpy(hs + o_seed, seeds.data(), seeds.size() * 4);
     { const uint32_t ns = (uint32_t)seeds.size(); memcpy(hs + o_seed + seeds.size() * 4, &ns, 4); }
@@ -1358,7 +1370,8 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
     // bytes 256.. next_item[q] of the first part of a pipelined scan
     uint32_t *d_counters = (uint32_t *)(ds + o_cnt);
     KGMA_CUDA(ctx, cudaEventRecord(e_start, sc_));
-    KGMA_CUDA(ctx, cudaMemcpyAsync(ds, hs, up_bytes, cudaMemcpyHostToDevice, sc_));
+    KGMA_CUDA(ctx, cudaMemcpyAsync(ds, hs, tabs_resident ? up_small : up_bytes, cudaMemcpyHostToDevice, sc_));
+    ctx->tab_sig = up_bytes > up_small ? tsig : 0;
     KGMA_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 512, sc_));
     KGMA_CUDA(ctx, cudaMemsetAsync(ds + o_first, 0x80, (size_t)C * std::max(nr, 1) * 8, sc_));
     for (size_t gi = 0; gi < groups.size(); gi++) {
@@ -1370,7 +1383,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
             KGMA_CUDA(ctx, cudaMemcpyAsync(d_counters + 1 + gi, ds + o_seed + seeds.size() * 4, 4, cudaMemcpyDeviceToDevice, sc_));
         }
     }
-    st.h2d_bytes += up_bytes;
+    st.h2d_bytes += tabs_resident ? up_small : up_bytes;
     st.host_setup_ms = now_ms() - t_wall0;
 
     // ---- upload range (bases): shard + halo, unless resident
