@@ -176,6 +176,9 @@ int  kgma_genome_append_bio4(kgma_genome *g, const char *identifier, const char 
 int  kgma_genome_create_pinned(kgma_ctx *ctx, int n_records, const int64_t *rec_len, kgma_genome **out);
 int  kgma_genome_record_planes(kgma_genome *g, int record, uint32_t **seq2, uint32_t **mask);
 int  kgma_genome_set_names(kgma_genome *g, int record, const char *identifier, const char *description);
+/* a genome of its own (page-locked planes) holding copies of the given records of g, in that order: one device's share of a
+ * contig-partitioned multi-GPU scan (kgma_hits_merge_partition puts the devices' hits together) */
+int  kgma_genome_subset(kgma_ctx *ctx, const kgma_genome *g, const int32_t *records, int n_records, kgma_genome **out);
 int  kgma_genome_seal(kgma_genome *g);
 void kgma_genome_destroy(kgma_genome *g);
 int     kgma_genome_n_records(const kgma_genome *g);

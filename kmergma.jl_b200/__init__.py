@@ -158,23 +158,10 @@ class Genome:
         contig-partitioned multi-GPU scan works on (north_star: "partitioned ... by contig").  Records start at multiples of
         128 bases in both genomes, so the packed words are copied as they are."""
         ctx = ctx or default_context()
-        recs = [int(r) for r in records]
-        lens = np.asarray([self.seqsize(r) for r in recs], dtype=np.int64)
+        recs = np.ascontiguousarray([int(r) for r in records], dtype=np.int32)
         h = C.c_void_p()
-        ctx.check(ctx._lib.kgma_genome_create_pinned(ctx._h, lens.size, lens.ctypes.data, C.byref(h)))
-        sub = Genome(h, ctx._lib)
-        for i, r in enumerate(recs):
-            s_src, m_src, s_dst, m_dst = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-            ctx.check(self._lib.kgma_genome_record_planes(self._h, r, C.byref(s_src), C.byref(m_src)))
-            ctx.check(ctx._lib.kgma_genome_record_planes(sub._h, i, C.byref(s_dst), C.byref(m_dst)))
-            n = int(lens[i])
-            C.memmove(s_dst, s_src, (n + 15) // 16 * 4)
-            C.memmove(m_dst, m_src, (n + 31) // 32 * 4)
-            ctx._lib.kgma_genome_set_names(sub._h, i, self.identifier(r).encode(), self.description(r).encode())
-        rc = ctx._lib.kgma_genome_seal(sub._h)
-        if rc != 0:
-            raise KmerGMAError(rc, "sealing the sub-genome failed")
-        return sub
+        ctx.check(ctx._lib.kgma_genome_subset(ctx._h, self._h, recs.ctypes.data, recs.size, C.byref(h)))
+        return Genome(h, ctx._lib)
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -78,6 +78,7 @@ SYMBOLS = {
     "kgma_genome_create_pinned": (C.c_int, [_P, C.c_int, _P, C.POINTER(_P)]),
     "kgma_genome_record_planes": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
     "kgma_genome_set_names": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_char_p]),
+    "kgma_genome_subset": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(_P)]),
     "kgma_genome_seal": (C.c_int, [_P]),
     "kgma_genome_destroy": (None, [_P]),
     "kgma_genome_n_records": (C.c_int, [_P]),

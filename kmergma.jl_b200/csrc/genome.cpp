@@ -341,6 +341,36 @@ int kgma_genome_record_planes(kgma_genome *g, int record, uint32_t **seq2, uint3
     return KGMA_OK;
 }
 
+// A genome of its own holding copies of `records` of g (in that order) in page-locked planes: what one device of a
+// contig-partitioned multi-GPU scan works on.  Records start at multiples of 128 bases in both genomes, so the packed words and
+// the mask words are copied as they are.
+int kgma_genome_subset(kgma_ctx *ctx, const kgma_genome *g, const int32_t *records, int n_records, kgma_genome **out)
+{
+    if (!ctx || !g || !records || n_records < 1 || !out || !g->sealed) return KGMA_E_ARG;
+    std::vector<int64_t> lens((size_t)n_records);
+    for (int i = 0; i < n_records; i++) {
+        if (records[i] < 0 || records[i] >= (int)g->recs.size()) return set_err(ctx, KGMA_E_ARG, "record %d out of range", records[i]);
+        lens[(size_t)i] = g->recs[(size_t)records[i]].len;
+    }
+    kgma_genome *sub = nullptr;
+    int rc = kgma_genome_create_pinned(ctx, n_records, lens.data(), &sub);
+    if (rc) return rc;
+    for (int i = 0; i < n_records; i++) {
+        const kgma::Record &S = g->recs[(size_t)records[i]]; kgma::Record &D = sub->recs[(size_t)i];
+        memcpy(sub->seq2 + (D.off >> 4), g->seq2 + (S.off >> 4), (size_t)((S.len + 15) / 16) * 4);
+        memcpy(sub->mask + (D.off >> 5), g->mask + (S.off >> 5), (size_t)((S.len + 31) / 32) * 4);
+        D.ident = S.ident; D.desc = S.desc;
+    }
+    if (g->ambiguous) {                                  // a symbol outside A,C,G,T,N somewhere in g: scans of the subset are refused as well
+        sub->ambiguous = true; sub->amb_record = -1; sub->amb_pos = g->amb_pos;
+        for (int i = 0; i < n_records; i++) if (records[i] == g->amb_record) sub->amb_record = i;
+    }
+    rc = kgma_genome_seal(sub);
+    if (rc) { kgma_genome_destroy(sub); return rc; }
+    *out = sub;
+    return KGMA_OK;
+}
+
 int kgma_genome_set_names(kgma_genome *g, int record, const char *identifier, const char *description)
 {
     if (!g || record < 0 || record >= (int)g->recs.size()) return KGMA_E_ARG;
