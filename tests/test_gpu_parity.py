@@ -1455,6 +1455,37 @@ def test_contig_partition_equals_whole(K, O, prof, synth, world):
         assert len(whole.hits) >= 8 and np.array_equal(merged[key], whole.hits[key]), args[5]
 
 
+def test_resident_prefilter_tables_follow_the_profiles(K, O, prof, synth, monkeypatch):
+    """the prefilter tables stay in the device arena between scans (a signature of table, offset and allocation decides whether
+    they are uploaded again): alternate thresholds, modes and genomes on ONE context, with an exact match and a CIGAR extension in
+    between (both carve the arena anew), and compare every result with the same call made with KGMA_NO_TABLE_CACHE=1"""
+    path, recs = synth
+    RV, ws, cons = prof
+    rvs, wss, cs, inv = K.cluster_ref_API(TF, 6)
+    rvs, wss, cs = K.eliminate_null_params(rvs, wss, cs, inv)
+    L = K.L
+    ctx = K.Context(0)
+    g1, g2 = K.Genome.from_fasta(path), K.Genome.from_fasta(GENOME)
+    key = ["record", "profile", "first", "last", "D", "genome_pos", "align_score"]
+
+    def calls():
+        out = []
+        for g in (g1, g2, g1):
+            for thr in (30.0, 24.0, 30.0):
+                out.append(K.scan_raw(g, [RV], [ws], [cons], [thr], 6, L.MODE_SINGLE, 50, L.F_ALIGN, -69, -1, ctx=ctx).hits[key].copy())
+            out.append(K.scan_raw(g, rvs, wss, cs, [35, 31, 38, 34, 27, 27], 6, L.MODE_CLUSTER, 100, L.F_ALIGN, -200, -1, ctx=ctx).hits[key].copy())
+            K.exactMatch(cons[20:90], g, ctx=ctx)
+            out.append(K.scan_raw(g, [RV], [ws], [cons], [30.0], 6, L.MODE_SINGLE, 50, L.F_ALIGN | L.F_WANT_CIGARS, -69, -1, ctx=ctx).hits[key].copy())
+            out.append(K.scan_raw(g, [RV], [ws], [cons], [30.0], 6, L.MODE_SINGLE, 50, L.F_ALIGN, -69, -1, ctx=ctx).hits[key].copy())
+        return out
+
+    cached = calls()
+    assert ctx.stats()["h2d_bytes"] > 0
+    monkeypatch.setenv("KGMA_NO_TABLE_CACHE", "1")
+    plain = calls()
+    assert len(cached) == len(plain) and all(np.array_equal(a, b) for a, b in zip(cached, plain)) and len(cached[0]) >= 8
+
+
 def test_two_contexts_share_nothing(K, prof, synth):
     """two contexts on the same device, used alternately on different genomes: each keeps its own device planes, tables,
     staging ring and scratch, so neither disturbs the other's resident genome"""
