@@ -35,6 +35,18 @@ def test_struct_layouts_match_header():
     L = K.L
     assert C.sizeof(L.Run) == 48 and C.sizeof(L.Hit) == 80 and C.sizeof(L.Match) == 24
     assert C.sizeof(L.ScanParams) == 64 and C.sizeof(L.Profile) == 48
+    # field by field against the header text, and the prototypes' argument counts
+    cty = {"int32_t": C.c_int32, "uint32_t": C.c_uint32, "int64_t": C.c_int64, "double": C.c_double}
+    hs = _header_structs()
+    for cls, cname in ((L.Profile, "kgma_profile"), (L.ScanParams, "kgma_scan_params"), (L.Run, "kgma_run"), (L.RunExt, "kgma_run_ext"),
+                       (L.Hit, "kgma_hit"), (L.Stats, "kgma_stats"), (L.Match, "kgma_match")):
+        assert [n for n, _ in cls._fields_] == [n for _, n in hs[cname]], cname
+        for (n, t), (ht, _) in zip(cls._fields_, hs[cname]):
+            assert (C.sizeof(t) == C.sizeof(C.c_void_p) and not issubclass(t, (C.c_int64, C.c_double))) if ht == "ptr" else t is cty[ht], (cname, n)
+    arity = _header_arity()
+    assert set(arity) == set(L.SYMBOLS)
+    for n, (_, argt) in L.SYMBOLS.items():
+        assert len(argt) == arity[n], (n, len(argt), arity[n])
 
 
 def test_no_gpu_means_loud_failure():
@@ -430,3 +442,64 @@ def test_native_hit_headers_and_writer(tmp_path):
     assert native.read_text() == mirror.read_text() and native.read_text().count(">") == 3
     assert max(len(l) for l in native.read_text().splitlines() if not l.startswith(">")) == 95
     assert K.write_hits(out, g, str(native), width=60) == 3 and native.read_text().count(">") == 6      # appends, like open(path, "a")
+
+
+def _header_text():
+    txt = open(os.path.join(ROOT, "include", "kmergma.h")).read()
+    return re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+
+
+def _header_structs():
+    """{typedef name: [(C type, field name)]} of the anonymous POD structs in include/kmergma.h"""
+    out = {}
+    for body, name in re.findall(r"typedef\s+struct\s*\{(.*?)\}\s*(kgma_\w+)\s*;", _header_text(), flags=re.S):
+        fields = []
+        for decl in body.split(";"):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            m = re.match(r"(?:const\s+)?(\w+)\s*(\**)\s*(.*)$", decl)
+            ctype, ptr, names = m.group(1), m.group(2), m.group(3)
+            for nm in names.split(","):
+                nm = nm.strip()
+                fields.append(("ptr" if ptr or nm.startswith("*") else ctype, nm.lstrip("* ")))
+        out[name] = fields
+    return out
+
+
+def _header_arity():
+    """{function: number of parameters} from the prototypes in include/kmergma.h"""
+    out = {}
+    for name, args in re.findall(r"\b(kgma_\w+)\s*\(([^()]*)\)\s*;", _header_text()):
+        args = args.strip()
+        out[name] = 0 if args in ("", "void") else len(args.split(","))
+    return out
+
+
+def test_julia_shim_follows_the_header():
+    """julia/KmerGMACuda.jl cannot run here (no Julia in the image): keep its struct mirrors and ccall signatures tied to
+    include/kmergma.h textually -- same field order and widths, every ccall'ed symbol declared, same number of arguments."""
+    src = open(os.path.join(ROOT, "julia", "KmerGMACuda.jl")).read()
+    code = "\n".join(l.split("#", 1)[0] for l in src.splitlines())
+    jl2c = {"Int32": "int32_t", "UInt32": "uint32_t", "Int64": "int64_t", "Float64": "double"}
+    hs = _header_structs()
+    seen = 0
+    for jname, cname in re.findall(r"^struct\s+(\w+)\s*#\s*(kgma_\w+)", src, flags=re.M) + [("KgmaMatch", "kgma_match")]:
+        body = re.search(r"struct\s+" + jname + r"\b(.*?)\bend\b", code, flags=re.S).group(1)
+        jf = [(("ptr" if t.startswith("Ptr{") else jl2c[t]), n) for n, t in re.findall(r"(\w+)::([\w{}]+)", body)]
+        assert [t for t, _ in jf] == [t for t, _ in hs[cname]], (jname, jf, hs[cname])
+        assert [n for _, n in jf] == [n for _, n in hs[cname]], (jname, cname)
+        seen += 1
+    assert seen == 4
+    arity, called = _header_arity(), set()
+    for m in re.finditer(r"ccall\(\(:(kgma_\w+), LIB\),\s*[\w{}]+,\s*\(", code):
+        name, i, depth = m.group(1), m.end(), 1
+        start = i
+        while depth:
+            depth += {"(": 1, ")": -1}.get(code[i], 0)
+            i += 1
+        types = [t for t in re.split(r",(?![^{]*\})", code[start:i - 1]) if t.strip()]
+        assert name in arity, name + " is not declared in include/kmergma.h"
+        assert len(types) == arity[name], (name, types, arity[name])
+        called.add(name)
+    assert {"kgma_create", "kgma_scan", "kgma_exact_match", "kgma_genome_from_fasta", "kgma_result_hits"} <= called
