@@ -1190,6 +1190,7 @@ using namespace kgma;
 // filtered; on_first_part is called with their runs while the rest of the genome is still being copied and filtered.
 struct PhaseHook {
     int rec_split = 0;
+    bool resident = false;         // the split was chosen for a genome that is already on the device (KGMA_RESIDENT_SPLIT)
     std::function<int(std::vector<kgma_run> &, const std::vector<int64_t> &)> on_first_part;
     size_t n_runs_first = 0;       // out: how many entries of res->runs belong to the first part
     bool used = false;             // out: the scan did run in two parts
@@ -1414,7 +1415,7 @@ static int scan_runs_impl(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *pro
         if (rc) return rc;
     }
     int64_t split_blk = -1, split_blk_f = -1;
-    bool pipelined = hook && !resident_ok && !staged && any_filter && !any_dense && sc == 1 && nr > 1 &&
+    bool pipelined = hook && (resident_ok ? hook->resident : !staged) && any_filter && !any_dense && sc == 1 && nr > 1 &&
                      hook->rec_split > 0 && hook->rec_split < nr;
     if (pipelined) {
         split_blk = g->recs[(size_t)hook->rec_split].off / FBLOCK;
@@ -1840,7 +1841,23 @@ int kgma_scan(kgma_ctx *ctx, kgma_genome *g, const kgma_profile *profiles, int n
     const bool cluster = P.mode == KGMA_MODE_CLUSTER;
     const bool can_pipeline = g->sealed && P.mode != KGMA_MODE_STROBE && (cluster || n_profiles == 1) && (P.flags & KGMA_F_ALIGN) && P.only_record < 0 &&
                               !(P.flags & (KGMA_F_DENSE | KGMA_F_WANT_DISTS | KGMA_F_WANT_CIGARS)) && nr >= 2 && !getenv("KGMA_NO_PIPELINE");
-    if (can_pipeline) {
+    // A genome that is already on the device has no copy to hide work under, but the same two-part form lets the host replay
+    // the first part's runs (and its extension batch run) next to the prefilter of the second: KGMA_RESIDENT_SPLIT = fraction
+    // of the genome in the first part (0 / unset: one part).
+    double res_split = 0;
+    if (const char *e = getenv("KGMA_RESIDENT_SPLIT")) res_split = atof(e);
+    const bool resident_now = (P.flags & KGMA_F_RESIDENT) && ctx->d_seq_valid && ctx->dg_uid == g->uid && ctx->d_valid_lo <= 0 &&
+                              ctx->d_valid_hi >= g->G;
+    if (can_pipeline && resident_now) {
+        if (res_split > 0 && res_split < 1) {
+            double best = 2;
+            for (int r = 1; r < nr; r++) {
+                const double frac = (double)g->recs[(size_t)r].off / (double)std::max<int64_t>(1, g->G);
+                if (fabs(frac - res_split) < best) { best = fabs(frac - res_split); hook.rec_split = r; }
+            }
+            hook.resident = true;
+        }
+    } else if (can_pipeline) {
         // single mode queues one extension batch per part, so the first part should be as large as possible: split in front
         // of the last record that starts before 93% of the genome.  Cluster mode extends in rounds that block the host, a few
         // milliseconds for a whole genome: split earlier so that the first part's rounds fit under the rest of the copy.

@@ -1133,6 +1133,32 @@ def test_pipelined_streaming_equals_plain(K, prof, synth, monkeypatch):
         assert np.array_equal(np.sort(ra, order=so), np.sort(rb, order=so))
 
 
+def test_resident_two_part_scan_equals_one_part(K, prof, synth, monkeypatch):
+    """KGMA_RESIDENT_SPLIT: a genome that is already on the device scanned in two parts (the host replays the first part
+    next to the second part's prefilter) reports the hits and runs of the one-part scan, single and cluster mode"""
+    path, recs = synth
+    RV, ws, cons = prof
+    key = ["record", "first", "last", "D", "genome_pos", "align_score", "cmi", "profile"]
+    rvs, wss, cs, inv = K.cluster_ref_API(TF, 6)
+    rvs, wss, cs = K.eliminate_null_params(rvs, wss, cs, inv)
+    g = K.Genome.from_fasta(path)
+    g.make_resident()
+    F = K.L.F_ALIGN | K.L.F_RESIDENT
+    for args in (([RV], [ws], [cons], [30.0], 6, K.L.MODE_SINGLE, 50, F, -69, -1),
+                 (rvs, wss, cs, [35, 31, 38, 34, 27, 27], 6, K.L.MODE_CLUSTER, 100, F, -200, -1)):
+        a = K.scan_raw(g, *args)
+        la = K.default_context().stats()["launches"]
+        for frac in ("0.3", "0.5", "0.8"):
+            monkeypatch.setenv("KGMA_RESIDENT_SPLIT", frac)
+            b = K.scan_raw(g, *args)
+            lb = K.default_context().stats()["launches"]
+            monkeypatch.delenv("KGMA_RESIDENT_SPLIT")
+            assert len(a.hits) >= 5 and np.array_equal(a.hits[key], b.hits[key])
+            assert lb > la                                                # it did run in two parts
+            so = ["profile", "record", "t_first", "flags"]
+            assert np.array_equal(np.sort(a.runs.view(RUN_DT), order=so), np.sort(b.runs.view(RUN_DT), order=so))
+
+
 def test_pipelined_scan_with_overflow_in_second_part(K, O, prof, tmp_path):
     """first part normal, second part wall-to-wall homologues: its candidate list overflows after the first part has
     already been replayed; the dense re-evaluation must not duplicate the first part's hits"""
