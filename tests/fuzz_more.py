@@ -15,5 +15,7 @@ for seed in range(lo, hi):
         except pytest.skip.Exception:
             pass
         except Exception as e:
-            bad.append(seed); print("SEED", seed, "FAILED:", repr(e)[:300]); traceback.print_exc(limit=3)
+            bad.append(seed); print("SEED", seed, "FAILED:", repr(e)[:300], flush=True); traceback.print_exc(limit=3)
+    if seed % 20 == 0:
+        print("... up to seed", seed, "failures so far:", bad, flush=True)
 print("done", lo, hi, "failures:", bad)
