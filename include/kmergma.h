@@ -270,6 +270,21 @@ const double *kgma_result_dists(const kgma_result *r, int profile);
 /* CIGAR ops of aligned hits: op chars ('=','X','I','D') and run lengths */
 const char *kgma_result_cigar_ops(const kgma_result *r);
 const int32_t *kgma_result_cigar_counts(const kgma_result *r);
+/* Cluster mode with KGMA_F_WANT_CIGARS: one entry per extension the reference performs, in its order.  Omn_KmerGMA! pushes
+ * the alignment (`get_aligns`, OmnGenomeMiner.jl:131-133) BEFORE the second overlap test (:139), so the list also holds the
+ * extensions whose hit was then rejected (emitted == 0); the emitted ones are the hits, in hit order.  Empty otherwise (in
+ * single mode every extension is a hit: Alignment.jl:46). */
+typedef struct {
+    int32_t  record;              /* 0-based */
+    int32_t  profile;             /* 1-based, like kgma_hit.profile */
+    int64_t  cmi;
+    int64_t  align_score;
+    uint32_t cigar_off, cigar_len;/* into kgma_result_cigar_* */
+    uint32_t emitted;             /* 1: passed the second overlap test and became a hit */
+    uint32_t reserved;
+} kgma_align_event;
+int64_t kgma_result_n_align_events(const kgma_result *r);
+const kgma_align_event *kgma_result_align_events(const kgma_result *r);
 void kgma_result_free(kgma_result *r);
 
 /* ---- result formatting / writing: append_hit! header text (Alignment.jl:57-81; OmnGenomeMiner.jl:141-149 when cluster != 0)

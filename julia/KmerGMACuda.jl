@@ -28,6 +28,10 @@ struct KgmaHit                      # kgma_hit
     D::Int64; dist::Float64; align_score::Int64
     flags::UInt32; cigar_off::UInt32; cigar_len::UInt32; reserved::UInt32
 end
+struct KgmaAlignEvent               # kgma_align_event
+    record::Int32; profile::Int32; cmi::Int64; align_score::Int64
+    cigar_off::UInt32; cigar_len::UInt32; emitted::UInt32; reserved::UInt32
+end
 struct KgmaMatch; record::Int32; reserved::Int32; first::Int64; last::Int64; end
 
 const F_ALIGN, F_DENSE, F_WANT_DISTS, F_WANT_CIGARS = UInt32(1), UInt32(2), UInt32(4), UInt32(8)
@@ -118,7 +122,8 @@ function ints_of(refVec::Vector{Float64})
 end
 
 function scan!(resultVec, hit_loci_vec, dist_vecs, genome_path, refVecs, windowsizes, consensus_seqs, thrs, k, mode, buff,
-               flags, gap_open, gap_extend; cluster::Bool, get_hit_loci::Bool, strobe = (0, 0, 0, 0), score_threshold::Int = 0)
+               flags, gap_open, gap_extend; cluster::Bool, get_hit_loci::Bool, strobe = (0, 0, 0, 0), score_threshold::Int = 0,
+               align_vec = nothing)
     ctx = context()
     g = genome(genome_path, ctx)
     Ss = [ints_of(Vector{Float64}(rv)) for rv in refVecs]
@@ -142,6 +147,20 @@ function scan!(resultVec, hit_loci_vec, dist_vecs, genome_path, refVecs, windows
                 push!(resultVec, FASTA.Record(header, subseq(g, h.record, rng)))
                 get_hit_loci && push!(hit_loci_vec, h.first + h.genome_pos)
             end
+            if align_vec !== nothing && (flags & F_WANT_CIGARS) != 0
+                # do_return_align / get_aligns: (cigar, score) of every extension the reference pushes -- single mode one per hit
+                # (Alignment.jl:46), cluster mode one per extension PERFORMED, rejected hits included (OmnGenomeMiner.jl:133)
+                ops = ccall((:kgma_result_cigar_ops, LIB), Ptr{UInt8}, (Ptr{Cvoid},), res[])
+                cnt = ccall((:kgma_result_cigar_counts, LIB), Ptr{Int32}, (Ptr{Cvoid},), res[])
+                cig(off, len) = join(string(unsafe_load(cnt, off + t)) * Char(unsafe_load(ops, off + t)) for t in 1:len)
+                if cluster
+                    ne = ccall((:kgma_result_n_align_events, LIB), Int64, (Ptr{Cvoid},), res[])
+                    evs = unsafe_wrap(Array, ccall((:kgma_result_align_events, LIB), Ptr{KgmaAlignEvent}, (Ptr{Cvoid},), res[]), ne)
+                    for e in evs; push!(align_vec, (cigar = cig(e.cigar_off, e.cigar_len), score = e.align_score)); end
+                else
+                    for h in hits; push!(align_vec, (cigar = cig(h.cigar_off, h.cigar_len), score = h.align_score)); end
+                end
+            end
             if (flags & F_WANT_DISTS) != 0
                 for q in eachindex(dist_vecs)
                     nd = ccall((:kgma_result_n_dists, LIB), Int64, (Ptr{Cvoid}, Cint), res[], q - 1)
@@ -162,16 +181,16 @@ function KmerGMA.ac_gma_testing!(; genome_path::String, refVec, consensus_refseq
         resultVec = FASTA.Record[])
     flags = (do_align ? F_ALIGN : UInt32(0)) | (do_return_dists ? F_WANT_DISTS : UInt32(0)) | ((do_align && do_return_align) ? F_WANT_CIGARS : UInt32(0))
     scan!(resultVec, hit_loci_vec, [dist_vec], genome_path, [collect(refVec)], [windowsize], [consensus_refseq], [thr], k, 0, buff,
-          flags, gap_open_score, gap_extend_score; cluster = false, get_hit_loci = get_hit_loci)
+          flags, gap_open_score, gap_extend_score; cluster = false, get_hit_loci = get_hit_loci, align_vec = result_align_vec)
 end
 
 function KmerGMA.Omn_KmerGMA!(; genome_path::String, refVecs, windowsizes, consensus_seqs, resultVec, k::Int = 6, ScaleFactor = nothing,
         mask = nothing, thr_vec = Float64[35, 31, 38, 34, 27, 27], buff::Int = 50, Nt_bits = nothing, align_hits::Bool = true,
         align_vec = [], gap_open_score::Int = -200, gap_extend_score::Int = -1, genome_pos::Int = 0, get_hit_loci::Bool = false,
         hit_loci_vec = Int[], get_aligns::Bool = false, do_return_dists::Bool = false, dist_vec_vec = [Float64[] for _ in windowsizes])
-    flags = (align_hits ? F_ALIGN : UInt32(0)) | (do_return_dists ? F_WANT_DISTS : UInt32(0))
+    flags = (align_hits ? F_ALIGN : UInt32(0)) | (do_return_dists ? F_WANT_DISTS : UInt32(0)) | ((align_hits && get_aligns) ? F_WANT_CIGARS : UInt32(0))
     scan!(resultVec, hit_loci_vec, dist_vec_vec, genome_path, refVecs, windowsizes, consensus_seqs, thr_vec, k, 1, buff,
-          flags, gap_open_score, gap_extend_score; cluster = true, get_hit_loci = get_hit_loci)
+          flags, gap_open_score, gap_extend_score; cluster = true, get_hit_loci = get_hit_loci, align_vec = align_vec)
 end
 
 # src/StrobemerGMA/StrobeGenomeMiner.jl:5-95 (KGMA_MODE_STROBE = 2; profile.k = w_max + s - 1, refVec over the 4^(2s) codes)

@@ -531,6 +531,20 @@ class ScanOutput:
             self._cigars = out
         return self._cigars
 
+    @property
+    def align_events(self) -> List[tuple]:
+        """kgma_result_align_events: (record, profile, cmi, AlignResult, emitted) for every extension of a cluster-mode scan with
+        KGMA_F_WANT_CIGARS, in the reference's order (OmnGenomeMiner.jl:131-133: pushed before the second overlap test)"""
+        n = self._lib.kgma_result_n_align_events(self._res)
+        ev = self._lib.kgma_result_align_events(self._res)
+        ops, cnt = self._lib.kgma_result_cigar_ops(self._res), self._lib.kgma_result_cigar_counts(self._res)
+        out = []
+        for i in range(n):
+            e = ev[i]
+            s = "".join(f"{cnt[e.cigar_off + t]}{ops[e.cigar_off + t].decode()}" for t in range(e.cigar_len)) if ops else ""
+            out.append((int(e.record), int(e.profile), int(e.cmi), AlignResult(s, int(e.align_score)), bool(e.emitted)))
+        return out
+
     def load_dists(self, n_profiles: int):
         for q in range(n_profiles):
             n = self._lib.kgma_result_n_dists(self._res, q)
@@ -757,7 +771,9 @@ def replay_raw(genome: Genome, refVecs, windowsizes, consensus_seqs, thrs, k: in
 
 
 def _emit(genome: Genome, out: ScanOutput, cluster: bool, resultVec, hit_loci_vec, align_vec, with_genome_pos=True):
-    cigars = out.cigars if align_vec is not None else [None] * len(out.hits)
+    cigars = out.cigars if (align_vec is not None and not cluster) else [None] * len(out.hits)
+    if cluster and align_vec is not None:          # one alignment per extension performed, emitted or not (OmnGenomeMiner.jl:133)
+        align_vec.extend(e[3] for e in out.align_events)
     for h, cg in zip(out.hits, cigars):
         rec, first, last = int(h.record), int(h.first), int(h.last)
         ident = genome.identifier(rec)
@@ -838,7 +854,7 @@ def Omn_KmerGMA(*, genome_path, refVecs, windowsizes, consensus_seqs, resultVec:
                 dense: bool = False, ctx: Optional[Context] = None):
     """Omn_KmerGMA! (src/OmnGenomeMiner.jl:7-162): C profiles scanned together.
     With get_aligns the reference pushes one alignment per extension it performs, including those whose hit the second overlap
-    test (:139) then rejects; align_vec here holds the alignments of the emitted hits only, in hit order."""
+    test (:139) then rejects (:133); align_vec receives exactly that list (kgma_result_align_events)."""
     _check_fixed_params(k, ScaleFactor, mask, Nt_bits)
     ctx = ctx or default_context()
     g = _as_genome(genome_path)

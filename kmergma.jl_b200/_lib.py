@@ -58,6 +58,11 @@ class Stats(C.Structure):
                 ("n_align_summary", C.c_int64), ("n_align_head", C.c_int64)]
 
 
+class AlignEvent(C.Structure):
+    _fields_ = [("record", C.c_int32), ("profile", C.c_int32), ("cmi", C.c_int64), ("align_score", C.c_int64),
+                ("cigar_off", C.c_uint32), ("cigar_len", C.c_uint32), ("emitted", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class Match(C.Structure):
     _fields_ = [("record", C.c_int32), ("reserved", C.c_int32), ("first", C.c_int64), ("last", C.c_int64)]
 
@@ -119,6 +124,8 @@ SYMBOLS = {
     "kgma_result_dists": (C.POINTER(C.c_double), [_P, C.c_int]),
     "kgma_result_cigar_ops": (C.POINTER(C.c_char), [_P]),
     "kgma_result_cigar_counts": (C.POINTER(C.c_int32), [_P]),
+    "kgma_result_n_align_events": (C.c_int64, [_P]),
+    "kgma_result_align_events": (C.POINTER(AlignEvent), [_P]),
     "kgma_result_free": (None, [_P]),
     "kgma_hits_merge_partition": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, C.c_int32, _P, C.POINTER(C.POINTER(Hit)), C.POINTER(C.c_int64)]),
     "kgma_hit_header": (C.c_int64, [_P, C.POINTER(Hit), C.c_int, C.c_int, C.c_char_p, C.c_int64]),

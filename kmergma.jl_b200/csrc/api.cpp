@@ -26,7 +26,7 @@ void result_release(kgma_result *r)
 {
     if (!r) return;
     // keep the capacity of the flat vectors, drop the per-window distance vectors (they can be GBs)
-    r->hits.clear(); r->runs.clear(); r->first_D.clear(); r->cigar_ops.clear(); r->cigar_cnt.clear();
+    r->hits.clear(); r->runs.clear(); r->first_D.clear(); r->cigar_ops.clear(); r->cigar_cnt.clear(); r->align_events.clear();
     std::vector<std::vector<double>>().swap(r->dists);
     const size_t keep = r->hits.capacity() * sizeof(kgma_hit) + r->runs.capacity() * sizeof(kgma_run) + r->cigar_ops.capacity() + r->cigar_cnt.capacity() * 4;
     {
@@ -107,6 +107,8 @@ int64_t kgma_result_n_dists(const kgma_result *r, int p) { return (r && p >= 0 &
 const double *kgma_result_dists(const kgma_result *r, int p) { return (r && p >= 0 && p < (int)r->dists.size() && !r->dists[p].empty()) ? r->dists[p].data() : nullptr; }
 const char *kgma_result_cigar_ops(const kgma_result *r) { return r && !r->cigar_ops.empty() ? r->cigar_ops.data() : nullptr; }
 const int32_t *kgma_result_cigar_counts(const kgma_result *r) { return r && !r->cigar_cnt.empty() ? r->cigar_cnt.data() : nullptr; }
+int64_t kgma_result_n_align_events(const kgma_result *r) { return r ? (int64_t)r->align_events.size() : 0; }
+const kgma_align_event *kgma_result_align_events(const kgma_result *r) { return r && !r->align_events.empty() ? r->align_events.data() : nullptr; }
 void kgma_result_free(kgma_result *r) { result_release(r); }
 
 // ---- result formatting and writing: append_hit!'s header (Alignment.jl:57-81; OmnGenomeMiner.jl:141-149 in cluster mode) and

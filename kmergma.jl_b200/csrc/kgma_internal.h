@@ -63,6 +63,7 @@ struct kgma_result {
     std::vector<std::vector<double>> dists;        // per profile
     std::vector<char>     cigar_ops;
     std::vector<int32_t>  cigar_cnt;
+    std::vector<kgma_align_event> align_events;    // cluster mode + KGMA_F_WANT_CIGARS: every extension of the final pass
 };
 
 // Results are recycled through a small pool: their hit / run vectors are 100-200 KB, which malloc serves with a fresh

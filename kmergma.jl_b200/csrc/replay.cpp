@@ -288,7 +288,7 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
     const double tr0 = tnow();
     merge_runs(runs, ext);
     const double tr1 = tnow();
-    res->hits.clear(); res->cigar_ops.clear(); res->cigar_cnt.clear();
+    res->hits.clear(); res->cigar_ops.clear(); res->cigar_cnt.clear(); res->align_events.clear();
 
     // index runs per (profile, record)
     struct Span { size_t b = 0, e = 0; };
@@ -387,6 +387,7 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
     int64_t n_align_total = 0;
     std::vector<std::vector<kgma_hit>> rec_hits((size_t)nr);   // per record: a record whose pass needed no speculation is final
     std::vector<char> rec_done((size_t)nr, 0);
+    std::vector<std::vector<kgma_align_event>> rec_events(want_cig ? (size_t)nr : 0);   // get_aligns: every extension, emitted or not (:133)
     for (int round = 0;; round++) {
         const double trr = tnow();
         missing.clear();
@@ -398,6 +399,7 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
                 const size_t missing_before = missing.size();
                 std::vector<kgma_hit> &hits_r = rec_hits[(size_t)r];
                 hits_r.clear();
+                if (want_cig) rec_events[(size_t)r].clear();
                 for (int q = 0; q < C; q++) { cur[q] = first_D[(size_t)q * nr + r]; CMIs[q] = 1; stop[q] = 1; }   // :73 curr_mins = first-window distance
                 int64_t prev_a = 0, prev_b = 0;                                          // :59 prev_hit_range = 0:0
                 for (size_t ei = ev_begin[(size_t)r]; ei < ev_begin[(size_t)r + 1]; ei++) {
@@ -422,7 +424,10 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
                             score = ar.score; co = ar.cig_off; cl = ar.cig_len;
                         } else missing.push_back(e.run);                               // speculate with the unextended range
                     }
-                    if (b < prev_a || a > prev_b) {                                     // :139
+                    const bool emit = b < prev_a || a > prev_b;                         // :139
+                    if (want_cig && do_align && have[e.run])
+                        rec_events[(size_t)r].push_back(kgma_align_event{ r, q + 1, CMI, score, co, cl, emit ? 1u : 0u, 0u });
+                    if (emit) {
                         kgma_hit h{};
                         h.record = r; h.profile = q + 1; h.cmi = CMI; h.first = a; h.last = b; h.genome_pos = genome_pos;
                         h.D = cur[q]; h.dist = (double)cur[q] / tabs[q].denom;
@@ -464,6 +469,8 @@ int replay(kgma_ctx *ctx, kgma_genome *g, const std::vector<ProfTab> &tabs, cons
     }
     res->hits.clear();
     for (int r = 0; r < nr; r++) res->hits.insert(res->hits.end(), rec_hits[(size_t)r].begin(), rec_hits[(size_t)r].end());
+    res->align_events.clear();
+    if (want_cig) for (int r = 0; r < nr; r++) res->align_events.insert(res->align_events.end(), rec_events[(size_t)r].begin(), rec_events[(size_t)r].end());
     if (ctx) ctx->stats.n_align = n_align_total;
     return KGMA_OK;
 }

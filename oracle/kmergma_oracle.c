@@ -745,6 +745,12 @@ int orc_strobe_gma(const orc_fasta *g, const double *RV, const char *cons, int c
 /* src/OmnGenomeMiner.jl:7-162 Omn_KmerGMA!  — C profiles; count tables are Float64 (:46);
  * prev_hit_range shared by all profiles, reset per record (:59).
  * cons: C strings at stride cons_stride; the WHOLE consensus_seqs[ind] is aligned (:131). */
+/* Test hook for `get_aligns` (OmnGenomeMiner.jl:131-133): while a sink is set, orc_omn_gma records every extension it performs,
+ * in order, as 6 int64: record (0-based), profile (1-based), CMI, hit_left, hit_right (the range handed to align_unitrange),
+ * emitted (1 when the second overlap test :139 then lets the hit through). */
+static int64_t *g_ev_buf = NULL, g_ev_cap = 0, *g_ev_n = NULL;
+void orc_set_event_sink(int64_t *buf, int64_t cap, int64_t *n) { g_ev_buf = buf; g_ev_cap = cap; g_ev_n = n; if (n) *n = 0; }
+
 int orc_omn_gma(const orc_fasta *g, const double *RVs, const int64_t *wss, int C,
                 const char *cons, int64_t cons_stride,
                 int k, const double *thr, int64_t buff, int align_hits,
@@ -822,6 +828,10 @@ int orc_omn_gma(const orc_fasta *g, const double *RVs, const int64_t *wss, int C
                             const char *cq = cons + (size_t)q * (size_t)cons_stride;
                             rc = orc_align_unitrange(s, L, hl, hr, cq, (int)strlen(cq), gap_open, gap_extend, prefer_extend, &a, &b);
                             if (rc) break;
+                        }
+                        if (align_hits && g_ev_buf && g_ev_n && *g_ev_n < g_ev_cap) {
+                            int64_t *e = g_ev_buf + 6 * (*g_ev_n)++;
+                            e[0] = r; e[1] = q + 1; e[2] = CMI; e[3] = hl; e[4] = hr; e[5] = (b < prev_a || a > prev_b) ? 1 : 0;
                         }
                         if (b < prev_a || a > prev_b) {        /* :139 */
                             if (nh >= hit_cap) { rc = ORC_E_CAP; break; }

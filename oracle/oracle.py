@@ -501,6 +501,28 @@ def Omn_KmerGMA(genome, refVecs, windowsizes, consensus_seqs, k: int = 6,
     return hits, loci, dv
 
 
+class align_events:
+    """with align_events() as ev: Omn_KmerGMA(...); ev.list -> [(record, profile, CMI, hit_left, hit_right, emitted)] for every
+    extension performed, in order (what `get_aligns` pushes, OmnGenomeMiner.jl:131-133)"""
+
+    def __init__(self, cap: int = 1 << 16):
+        self.buf = np.zeros(6 * cap, dtype=np.int64)
+        self.n = C.c_int64(0)
+        self.cap = cap
+
+    def __enter__(self):
+        lib().orc_set_event_sink(C.c_void_p(self.buf.ctypes.data), C.c_int64(self.cap), C.byref(self.n))
+        return self
+
+    def __exit__(self, *a):
+        lib().orc_set_event_sink(None, C.c_int64(0), None)
+        return False
+
+    @property
+    def list(self):
+        return [tuple(int(x) for x in self.buf[6 * i:6 * i + 6]) for i in range(self.n.value)]
+
+
 # ---------------------------------------------------------------- ExactMatch.jl
 def exactMatch(query, subject, overlap: bool = True):
     """src/ExactMatch.jl:89-121.  subject: sequence string -> list of (first,last) or None;

@@ -34,12 +34,12 @@ def test_struct_layouts_match_header():
     import kmergma_jl_b200 as K
     L = K.L
     assert C.sizeof(L.Run) == 48 and C.sizeof(L.Hit) == 80 and C.sizeof(L.Match) == 24
-    assert C.sizeof(L.ScanParams) == 64 and C.sizeof(L.Profile) == 48
+    assert C.sizeof(L.ScanParams) == 64 and C.sizeof(L.Profile) == 48 and C.sizeof(L.AlignEvent) == 40
     # field by field against the header text, and the prototypes' argument counts
     cty = {"int32_t": C.c_int32, "uint32_t": C.c_uint32, "int64_t": C.c_int64, "double": C.c_double}
     hs = _header_structs()
     for cls, cname in ((L.Profile, "kgma_profile"), (L.ScanParams, "kgma_scan_params"), (L.Run, "kgma_run"), (L.RunExt, "kgma_run_ext"),
-                       (L.Hit, "kgma_hit"), (L.Stats, "kgma_stats"), (L.Match, "kgma_match")):
+                       (L.Hit, "kgma_hit"), (L.Stats, "kgma_stats"), (L.Match, "kgma_match"), (L.AlignEvent, "kgma_align_event")):
         assert [n for n, _ in cls._fields_] == [n for _, n in hs[cname]], cname
         for (n, t), (ht, _) in zip(cls._fields_, hs[cname]):
             assert (C.sizeof(t) == C.sizeof(C.c_void_p) and not issubclass(t, (C.c_int64, C.c_double))) if ht == "ptr" else t is cty[ht], (cname, n)
@@ -490,7 +490,7 @@ def test_julia_shim_follows_the_header():
         assert [t for t, _ in jf] == [t for t, _ in hs[cname]], (jname, jf, hs[cname])
         assert [n for _, n in jf] == [n for _, n in hs[cname]], (jname, cname)
         seen += 1
-    assert seen == 4
+    assert seen == 5
     arity, called = _header_arity(), set()
     for m in re.finditer(r"ccall\(\(:(kgma_\w+), LIB\),\s*[\w{}]+,\s*\(", code):
         name, i, depth = m.group(1), m.end(), 1

@@ -204,6 +204,41 @@ def test_omn_golden(K):
         "AM773548.1 | Dist = 26.17 | KFV = 3 | MatchPos = 33845:34132 | GenomePos = 0 | Len = 288"]
 
 
+def test_cluster_get_aligns_lists_every_extension(K, O, synth):
+    """get_aligns (OmnGenomeMiner.jl:131-133): the alignment is pushed BEFORE the second overlap test (:139), so align_vec also
+    holds the extensions whose hit was rejected.  kgma_result_align_events against the oracle's record of every extension it
+    performs (same order, same candidate, same CIGAR and score; the emitted ones are the hits, in hit order)."""
+    path, recs = synth
+    rvs, wss, cs, inv = K.cluster_ref_API(TF, 6)
+    rvs, wss, cs = K.eliminate_null_params(rvs, wss, cs, inv)
+    seen_rejected = 0
+    for gpath, thr, buff in ((MINI_GENOME, [35, 31, 38, 34, 27, 27], 100), (path, [35, 31, 38, 34, 27, 27], 100), (path, [31] * 6, 30), (path, [38] * 6, 200)):
+        res, av = [], []
+        out = K.Omn_KmerGMA(genome_path=gpath, refVecs=rvs, windowsizes=wss, consensus_seqs=cs, resultVec=res, thr_vec=thr, buff=buff,
+                            get_aligns=True, align_vec=av)
+        f = O.Fasta(gpath)
+        # (exact-arithmetic form of the oracle: the synthetic genome holds exact repeats, where the Float64 form's outcome
+        #  depends on its rounding history -- check_parity's waiver; this test is about the event list)
+        with O.exact_arithmetic([int(v.n_refs) for v in rvs]), O.align_events() as sink:
+            oh = O.Omn_KmerGMA(gpath, [np.asarray(v) for v in rvs], wss, cs, thr_vec=thr, buff=buff)[0]
+        want = sink.list
+        got = out.align_events
+        assert len(got) == len(want) == len(av) and len(want) >= len(oh) >= 3
+        assert [(e[0], e[1], e[2], e[4]) for e in got] == [(w[0], w[1], w[2], bool(w[5])) for w in want]
+        for e, w, a in zip(got, want, av):
+            cig, score = O.pairalign_semiglobal(cs[w[1] - 1], f.subseq(w[0], w[3], w[4]), -200, -1)
+            assert (e[3].cigar, e[3].score) == (cig, score) and a == e[3]
+        assert sum(1 for e in got if e[4]) == len(out.hits) == len(oh)
+        assert [(e[0], e[1], e[2]) for e in got if e[4]] == [(int(h.record), int(h.profile), int(h.cmi)) for h in out.hits]
+        seen_rejected += sum(1 for e in got if not e[4])
+    assert seen_rejected >= 1, "no case exercised an extension rejected by the second overlap test"
+    # single mode: every extension is a hit (Alignment.jl:46); the event list stays empty and the hits carry the CIGARs
+    RV, ws, cons = K.gen_ref_ws_cons(TF, 6)
+    av = []
+    out = K.ac_gma_testing(genome_path=MINI_GENOME, refVec=RV, consensus_refseq=cons, windowsize=ws, thr=30.0, do_return_align=True, result_align_vec=av)
+    assert out.align_events == [] and len(av) == len(out.hits) == 3
+
+
 def test_findgenes_cluster_mode_golden(K):
     """test-KmerGMA.jl:265-271"""
     with warnings.catch_warnings():

@@ -200,3 +200,16 @@ def test_exact_arithmetic_mode_agrees_with_faithful_on_goldens():
         b = O.Omn_KmerGMA(MINI_GENOME, rvs, wss, cs, thr_vec=[37, 33, 38, 34, 28, 27], buff=200)[0]
     assert [h.description() for h in a] == [h.description() for h in b]
     assert a[0].description() == "AM773548.1 | Dist = 20.17 | KFV = 3 | MatchPos = 6852:7139 | GenomePos = 0 | Len = 288"
+
+
+def test_oracle_records_every_cluster_mode_extension():
+    """the `get_aligns` sink (OmnGenomeMiner.jl:131-133): one event per extension performed, the emitted ones being the hits"""
+    rvs, wss, cs, inv = O.cluster_ref_API(TF, 6, eliminate_null=True)
+    with O.align_events() as sink:
+        hits = O.Omn_KmerGMA(MINI_GENOME, rvs, wss, cs, thr_vec=[35, 31, 38, 34, 27, 27], buff=100)[0]
+    ev = sink.list
+    assert len(hits) == 3 and len(ev) >= 3
+    assert [(e[0], e[1], e[2]) for e in ev if e[5]] == [(h.record, h.kfv, h.cmi) for h in hits]
+    with O.align_events() as sink:
+        O.Omn_KmerGMA(MINI_GENOME, rvs, wss, cs, thr_vec=[35, 31, 38, 34, 27, 27], buff=100, align_hits=False)
+    assert sink.list == []                                            # no extension, nothing pushed
