@@ -25,7 +25,7 @@ __all__ = [
     "gen_ref_ws_cons", "cluster_ref_API", "eliminate_null_params", "get_cluster_index",
     "estimate_optimal_threshold", "ac_gma_testing", "Omn_KmerGMA", "record_KmerGMA",
     "findGenes", "findGenes_cluster_mode", "exactMatch", "write_results", "write_hits", "hit_header",
-    "fasta_id_to_cumulative_len_dict", "align_unitrange",
+    "fasta_id_to_cumulative_len_dict", "align_unitrange", "cigar_to_UnitRange", "firstMatch",
     "julia_round2", "julia_float_str", "kmer_count", "kmer_dist", "as_UInt", "as_kmer",
     "randstrobe_score", "get_strobe_2_mer", "ungapped_strobe_2_mer_count", "strobe_gen_ref_ws_cons", "StrobeGMA", "Strobemer_findGenes",
 ]
@@ -1174,6 +1174,51 @@ def align_unitrange(seq, seq_UnitRange: Tuple[int, int], consensus_seq: str, win
     return int(of[0]), int(ol[0])
 
 
+def cigar_to_UnitRange(aligned_obj) -> Tuple[int, int]:
+    """cigar_to_UnitRange (src/Alignment.jl:13-30) on an AlignResult or a CIGAR string: (lower + 1, num_sum) with `lower` the
+    count of the FIRST operation whatever it is and `num_sum` the counts of all operations but the last (the loop returns when
+    it reaches the last character, before that operation is added).  The scan computes the same two numbers on the device
+    without a CIGAR; this is the text form for callers holding `do_return_align` results."""
+    cig = aligned_obj.cigar if isinstance(aligned_obj, AlignResult) else str(aligned_obj)
+    curr, nops, num_sum, lower = 0, 0, 0, 0
+    for i, ch in enumerate(cig):
+        if i == len(cig) - 1:
+            return lower + 1, num_sum
+        if ch.isdigit():
+            curr = curr * 10 + int(ch)
+        else:
+            nops += 1
+            if nops == 1:
+                lower = curr
+            num_sum += curr
+            curr = 0
+    return None                                            # empty CIGAR: the reference's loop falls through (returns nothing)
+
+
+def firstMatch(reader, query, file=None, ctx: Optional[Context] = None) -> None:
+    """firstMatch (src/ExactMatch.jl:8-16): prints "first:last identifier" for every record holding the query, the FIRST occurrence
+    only (findfirst == the first range FindAllOverlap reports)."""
+    ctx = ctx or default_context()
+    g = _as_genome(reader)
+    q = (query.sequence if isinstance(query, FastaRecord) else str(query)).upper().encode()
+    by_rec = _exact_match_by_record(ctx, g, q, True, g._resident_ctx is ctx)
+    for r in sorted(by_rec):                                # every record with a match, in file order (duplicate identifiers too)
+        a, b = by_rec[r][0]
+        print(f"{a}:{b} {g.identifier(r)}", file=file)
+
+
+def _exact_match_by_record(ctx: Context, g: Genome, q: bytes, overlap: bool, resident: bool) -> Dict[int, List[Tuple[int, int]]]:
+    mp = C.POINTER(L.Match)()
+    n = C.c_int64()
+    ctx.check(ctx._lib.kgma_exact_match(ctx._h, g._h, q, len(q), int(overlap), L.F_RESIDENT if resident else 0, C.byref(mp), C.byref(n)))
+    by_rec: Dict[int, List[Tuple[int, int]]] = {}
+    for i in range(n.value):
+        by_rec.setdefault(mp[i].record, []).append((mp[i].first, mp[i].last))
+    if n.value:
+        ctx._lib.kgma_free(mp)
+    return by_rec
+
+
 def exactMatch(query, subject_seq, overlap: bool = True, ctx: Optional[Context] = None, resident: bool = False):
     """exactMatch (src/ExactMatch.jl:89-121).
     subject = residue string / FastaRecord  -> list of (first, last) ranges, or None when there is no match;
@@ -1188,15 +1233,7 @@ def exactMatch(query, subject_seq, overlap: bool = True, ctx: Optional[Context] 
         g = Genome.from_records([("subject", s)])
     else:
         g = _as_genome(subject_seq)
-    mp = C.POINTER(L.Match)()
-    n = C.c_int64()
-    ctx.check(ctx._lib.kgma_exact_match(ctx._h, g._h, q, len(q), int(overlap), L.F_RESIDENT if (resident or g._resident_ctx is ctx) else 0,
-                                        C.byref(mp), C.byref(n)))
-    by_rec: Dict[int, List[Tuple[int, int]]] = {}
-    for i in range(n.value):
-        by_rec.setdefault(mp[i].record, []).append((mp[i].first, mp[i].last))
-    if n.value:
-        ctx._lib.kgma_free(mp)
+    by_rec = _exact_match_by_record(ctx, g, q, overlap, resident or g._resident_ctx is ctx)
     if single:
         return by_rec.get(0) or None
     identify = {}

@@ -503,3 +503,18 @@ def test_julia_shim_follows_the_header():
         assert len(types) == arity[name], (name, types, arity[name])
         called.add(name)
     assert {"kgma_create", "kgma_scan", "kgma_exact_match", "kgma_genome_from_fasta", "kgma_result_hits"} <= called
+
+
+def test_cigar_to_unitrange_text_form():
+    """cigar_to_UnitRange (Alignment.jl:13-30) on CIGAR text: the goldens of test-KmerGMA.jl:129-136 (6:13, 6:15) through the
+    oracle's pairalign, and the quirks -- `lower` is the first operation's count whatever it is, the last operation is never
+    added, counts of I columns are"""
+    import kmergma_jl_b200 as K
+    from oracle import oracle as O
+    for subj, want in (("GGGGGATGCATGCAAAAA", (6, 13)), ("GGGGGATGCTTATGCAAAAA", (6, 15))):
+        cig, score = O.pairalign_semiglobal("ATGCATGC", subj, -5, -1)
+        assert K.cigar_to_UnitRange(cig) == want == tuple(O.cigar_to_UnitRange(cig))
+        assert K.cigar_to_UnitRange(K.AlignResult(cig, score)) == want
+    for cig in ("8=", "3=2I5=4D", "12D300=", "7I2=", "10D5=3I5=10D", "1D1=1D"):
+        assert K.cigar_to_UnitRange(cig) == tuple(O.cigar_to_UnitRange(cig)), cig
+    assert K.cigar_to_UnitRange("8=") == (1, 0) and K.cigar_to_UnitRange("3=2I5=4D") == (4, 10)

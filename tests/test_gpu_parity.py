@@ -239,6 +239,26 @@ def test_cluster_get_aligns_lists_every_extension(K, O, synth):
     assert out.align_events == [] and len(av) == len(out.hits) == 3
 
 
+def test_first_match_prints_first_occurrence_per_record(K, O, tmp_path):
+    """firstMatch (ExactMatch.jl:8-16): "range identifier" for every record holding the query -- findfirst per record, records
+    with the same identifier each get their line"""
+    import io
+    recs = [("a one", "TTTTACGTACGTAC"), ("b", "GGGG"), ("a two", "ACGTAC"), ("c", "CCACGTACGTAC")]
+    p = tmp_path / "fm.fasta"
+    _write_fasta(p, recs)
+    buf = io.StringIO()
+    K.firstMatch(str(p), "ACGTAC", file=buf)
+    want = []
+    for d, s in recs:
+        m = O.exactMatch("ACGTAC", s, True)
+        if m:
+            want.append(f"{m[0][0]}:{m[0][1]} {d.split()[0]}")
+    assert buf.getvalue().splitlines() == want == ["5:10 a", "1:6 a", "3:8 c"]
+    buf = io.StringIO()
+    K.firstMatch(str(p), "GATTACA", file=buf)
+    assert buf.getvalue() == ""
+
+
 def test_findgenes_cluster_mode_golden(K):
     """test-KmerGMA.jl:265-271"""
     with warnings.catch_warnings():
