@@ -518,3 +518,42 @@ def test_cigar_to_unitrange_text_form():
     for cig in ("8=", "3=2I5=4D", "12D300=", "7I2=", "10D5=3I5=10D", "1D1=1D"):
         assert K.cigar_to_UnitRange(cig) == tuple(O.cigar_to_UnitRange(cig)), cig
     assert K.cigar_to_UnitRange("8=") == (1, 0) and K.cigar_to_UnitRange("3=2I5=4D") == (4, 10)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_exact_match_merge_host_only(tmp_path, seed):
+    """kgma_exact_match_merge needs no device: all occurrence starts of a query (found here with str.find, handed over in
+    arbitrary order, as the slices of several GPUs would deliver them) -> exactMatch's result, overlapping and not
+    (FindAllOverlap / FindAll, ExactMatch.jl:20-43), against the oracle.  Self-overlapping queries, copies across record
+    edges (which do not match), duplicate identifiers (the later record wins, :112)."""
+    import kmergma_jl_b200 as K
+    from oracle import oracle as O
+    rng = np.random.default_rng(40 + seed)
+    q = ["ACACACA", "AAAA", "ACGTTGCAACGT", "GATTACAGATTACA", "T", "ACGTACGTAC"][seed]
+    recs = []
+    for r in range(5):
+        s = list(np.asarray(list("ACGT"))[rng.integers(0, 4, size=int(rng.integers(30, 400)))])
+        for _ in range(int(rng.integers(0, 6))):
+            p = int(rng.integers(0, max(1, len(s) - 2 * len(q))))
+            rep = (q * 3)[:int(rng.integers(len(q), 3 * len(q)))]               # runs of the query: self-overlaps
+            s[p:p + len(rep)] = list(rep)
+        recs.append(("dup" if r in (1, 3) else "r%d" % r, "".join(s)))
+    recs.append(("tail", q[:len(q) // 2 + 1]))                                   # shorter than the query
+    path = tmp_path / "em.fasta"
+    with open(path, "w") as fh:
+        for d_, s in recs:
+            fh.write(">" + d_ + " x\n" + s + "\n")
+    g = K.Genome.from_fasta(str(path))
+    lib = K.L.load()
+    starts = []
+    for r, (_, s) in enumerate(recs):
+        off = lib.kgma_genome_record_offset(g._h, r)
+        p = s.find(q)
+        while p >= 0:
+            starts.append(off + p)
+            p = s.find(q, p + 1)
+    starts = np.asarray(starts, np.int64)[rng.permutation(len(starts))]
+    f = O.Fasta(str(path))
+    for overlap in (True, False):
+        assert K.exact_match_merge(g, starts, len(q), overlap) == O.exactMatch(q, f, overlap=overlap), (q, overlap)
+    assert K.exact_match_merge(g, np.zeros(0, np.int64), len(q), True) == "no match"
